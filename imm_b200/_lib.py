@@ -1,0 +1,127 @@
+"""ctypes binding of libimm_b200.so (the C ABI declared in include/imm_b200.h).
+
+The product path has NO CPU fallback: if the shared library is missing or a CUDA device is absent,
+calls fail loudly.  PyTorch is used only for device memory and streams."""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libimm_b200.so')
+
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
+PREC_TF32X3, PREC_TF32 = 0, 1
+EPI_BIAS, EPI_BIAS_RELU = 0, 1
+
+
+class ImmbError(RuntimeError):
+  pass
+
+
+class ConvDesc(ctypes.Structure):
+  _fields_ = [(n, ctypes.c_int32) for n in
+              ('N', 'H', 'W', 'Cin', 'Cout', 'kh', 'kw', 'stride', 'Ho', 'Wo', 'pad_t', 'pad_l',
+               'x_cstride', 'y_cstride', 'cin_pad', 'epilogue', 'precision', 'engine')]
+
+
+_P, _I, _L, _F, _Z = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
+_D = ctypes.POINTER(ConvDesc)
+
+# name -> argtypes (everything returns int unless listed in _RESTYPES)
+_SIGS = {
+  'immb_conv_engine_for': [_D, _I],
+  'immb_conv2d_fwd': [_D, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+  'immb_conv2d_dgrad': [_D, _P, _P, _P, _P, _P, _P, _P],
+  'immb_conv2d_wgrad_workspace': [_D],
+  'immb_conv2d_wgrad': [_D, _P, _P, _P, _P, _P, _P, _Z, _P],
+  'immb_pack_weights': [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+  'immb_split_planes': [_P, _P, _P, _L, _P],
+  'immb_bn_stats': [_P, _L, _I, _I, _P, _P],
+  'immb_bn_finalize': [_P, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P],
+  'immb_bn_apply': [_P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P],
+  'immb_upsample2x_bwd': [_P, _I, _I, _I, _I, _I, _P, _P],
+  'immb_bn_bwd_reduce': [_P, _I, _P, _I, _L, _I, _P, _P, _P, _P, _I, _P, _P],
+  'immb_bn_bwd_apply': [_P, _I, _P, _I, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P],
+  'immb_bias_grad': [_P, _P, _I, _L, _I, _P, _P],
+  'immb_cast_d2f': [_P, _P, _L, _P],
+  'immb_softargmax_gauss_fwd': [_P, _I, _I, _I, _I, _F, _P, _P, _P, _I, _P, _P, _I, _I, _P],
+  'immb_softargmax_gauss_bwd': [_P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _F, _P, _I, _P],
+  'immb_gaussian_maps': [_P, _I, _I, _I, _F, _P, _P],
+  'immb_vgg_prologue': [_P, _P, _I, _I, _I, _P, _P, _P],
+  'immb_maxpool2x2_fwd': [_P, _P, _I, _I, _I, _I, _P, _P, _P],
+  'immb_maxpool2x2_bwd': [_P, _P, _P, _I, _I, _I, _I, _P, _P],
+  'immb_perceptual_level_sum': [_P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P, _P],
+  'immb_perceptual_finalize': [_P, _P, _I, _P, _I, _P, _P, _P, _P],
+  'immb_vgg_bwd_combine': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P],
+  'immb_pred_grad': [_P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P],
+  'immb_resize_ac_fwd': [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P],
+  'immb_resize_ac_bwd': [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+  'immb_adam_norms': [_P, _P, _L, _P, _P, _P, _I, _P, _F, _P, _P, _P],
+  'immb_adam_apply': [_P, _P, _P, _P, _L, _P, _P, _P, _I, _P, _F, _P, _F, _F, _F, _F, _F, _P],
+  'immb_total_loss': [_P, _P, _P, _I, _P, _P, _P],
+}
+_RESTYPES = {'immb_conv2d_wgrad_workspace': _Z}
+
+_lib = None
+
+
+def lib():
+  global _lib
+  if _lib is None:
+    if not os.path.exists(LIB_PATH):
+      raise ImmbError('libimm_b200.so not found at %s -- run `python -c "import __graft_entry__ as g; g.build()"` '
+                      '(there is no CPU fallback)' % LIB_PATH)
+    l = ctypes.CDLL(LIB_PATH)
+    l.immb_version.restype = ctypes.c_int
+    l.immb_last_error.restype = ctypes.c_char_p
+    l.immb_launch_count.restype = ctypes.c_int64
+    for name, argtypes in _SIGS.items():
+      fn = getattr(l, name)
+      fn.argtypes = argtypes
+      fn.restype = _RESTYPES.get(name, ctypes.c_int)
+    _lib = l
+  return _lib
+
+
+def exported_symbols():
+  return ['immb_version', 'immb_last_error', 'immb_launch_count'] + sorted(_SIGS.keys())
+
+
+def ptr(t):
+  """device pointer of a tensor (or None).  Tensors must be fp32/fp64/int CUDA tensors laid out as the
+  kernel expects; only data_ptr() crosses the ABI."""
+  if t is None:
+    return None
+  if isinstance(t, int):
+    return t
+  return t.data_ptr()
+
+
+def stream_ptr():
+  return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+  """Calls a C-ABI function; tensors are converted to raw pointers; raises ImmbError on failure."""
+  l = lib()
+  conv = []
+  for a in args:
+    if isinstance(a, torch.Tensor):
+      if not a.is_cuda:
+        raise ImmbError('%s: got a CPU tensor; the CUDA path has no CPU fallback' % name)
+      conv.append(a.data_ptr())
+    elif isinstance(a, ConvDesc):
+      conv.append(ctypes.byref(a))
+    else:
+      conv.append(a)
+  rc = getattr(l, name)(*conv)
+  if name in _RESTYPES:
+    return rc
+  if rc != 0:
+    raise ImmbError('%s failed (%d): %s' % (name, rc, l.immb_last_error().decode()))
+  return rc
+
+
+def launch_count():
+  return int(lib().immb_launch_count())

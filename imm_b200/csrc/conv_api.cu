@@ -1,0 +1,112 @@
+// C-ABI entry points for the convolutions: validates the descriptor and dispatches to the tcgen05 engine
+// (conv_tc.cu) or the SIMT engine (conv_simt.cu).
+#include "common.cuh"
+
+namespace immb {
+int conv_simt_fwd(const immb_conv_desc*, const float*, const float*, const float*, const float*, float*, float*,
+                  cudaStream_t);
+int conv_simt_dgrad(const immb_conv_desc*, const float*, const float*, const float*, float*, cudaStream_t);
+int conv_simt_wgrad(const immb_conv_desc*, const float*, const float*, const float*, const float*, float*,
+                    cudaStream_t);
+// tcgen05 engine (conv_tc.cu)
+bool conv_tc_eligible(const immb_conv_desc* d, int op);
+int conv_tc_fwd(const immb_conv_desc*, const float* x_hi, const float* x_lo, const float* wp_hi,
+                const float* wp_lo, const float* bias, float* y_hi, float* y_lo, cudaStream_t);
+int conv_tc_dgrad(const immb_conv_desc*, const float* dy_hi, const float* dy_lo, const float* wh_hi,
+                  const float* wh_lo, float* dx, cudaStream_t);
+size_t conv_tc_wgrad_workspace(const immb_conv_desc*);
+int conv_tc_wgrad(const immb_conv_desc*, const float* x_hi, const float* x_lo, const float* dy_hi,
+                  const float* dy_lo, float* dw, void* ws, size_t ws_bytes, cudaStream_t);
+
+static int validate(const immb_conv_desc* d) {
+  IMMB_REQUIRE(d, "conv: null descriptor");
+  IMMB_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "conv: bad extents");
+  IMMB_REQUIRE(d->kh > 0 && d->kw > 0 && d->kh <= 7 && d->kw <= 7, "conv: kernel size must be 1..7");
+  IMMB_REQUIRE(d->stride == 1 || d->stride == 2, "conv: stride must be 1 or 2");
+  IMMB_REQUIRE(d->Ho == (d->H + d->stride - 1) / d->stride && d->Wo == (d->W + d->stride - 1) / d->stride,
+               "conv: Ho/Wo must be ceil(H/stride), ceil(W/stride) (TF SAME)");
+  IMMB_REQUIRE(d->x_cstride >= d->Cin && d->y_cstride >= d->Cout, "conv: channel strides too small");
+  IMMB_REQUIRE(d->pad_t >= 0 && d->pad_l >= 0 && d->pad_t < d->kh && d->pad_l < d->kw, "conv: bad padding");
+  return IMMB_OK;
+}
+
+static int pick_engine(const immb_conv_desc* d, int op, int* engine) {
+  bool ok = conv_tc_eligible(d, op);
+  if (d->engine == IMMB_ENGINE_TC) {
+    if (!ok) return set_error(IMMB_ERR_UNSUPPORTED, "conv: shape not eligible for the tcgen05 engine");
+    *engine = IMMB_ENGINE_TC;
+  } else if (d->engine == IMMB_ENGINE_SIMT) {
+    *engine = IMMB_ENGINE_SIMT;
+  } else {
+    *engine = ok ? IMMB_ENGINE_TC : IMMB_ENGINE_SIMT;
+  }
+  return IMMB_OK;
+}
+}  // namespace immb
+
+using namespace immb;
+
+extern "C" int immb_conv_engine_for(const immb_conv_desc* d, int op) {
+  if (validate(d) != IMMB_OK) return IMMB_ERR_INVALID;
+  immb_conv_desc t = *d;
+  t.engine = IMMB_ENGINE_AUTO;
+  int e = IMMB_ENGINE_SIMT;
+  pick_engine(&t, op, &e);
+  return e;
+}
+
+extern "C" int immb_conv2d_fwd(const immb_conv_desc* d, const float* x_hi, const float* x_lo, const float* w,
+                               const float* wp_hi, const float* wp_lo, const float* bias, float* y_hi,
+                               float* y_lo, void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  IMMB_REQUIRE(x_hi && y_hi, "conv2d_fwd: null tensors");
+  int engine = IMMB_ENGINE_SIMT;
+  if ((rc = pick_engine(d, 0, &engine))) return rc;
+  if (engine == IMMB_ENGINE_TC) {
+    IMMB_REQUIRE(wp_hi && (d->precision == IMMB_PREC_TF32 || (wp_lo && x_lo)),
+                 "conv2d_fwd: tcgen05 engine needs packed weights and (for TF32x3) lo planes");
+    return conv_tc_fwd(d, x_hi, x_lo, wp_hi, wp_lo, bias, y_hi, y_lo, (cudaStream_t)stream);
+  }
+  IMMB_REQUIRE(w, "conv2d_fwd: SIMT engine needs the master weights");
+  return conv_simt_fwd(d, x_hi, x_lo, w, bias, y_hi, y_lo, (cudaStream_t)stream);
+}
+
+extern "C" int immb_conv2d_dgrad(const immb_conv_desc* d, const float* dy_hi, const float* dy_lo,
+                                 const float* w, const float* wh_hi, const float* wh_lo, float* dx,
+                                 void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  IMMB_REQUIRE(dy_hi && dx, "conv2d_dgrad: null tensors");
+  int engine = IMMB_ENGINE_SIMT;
+  if ((rc = pick_engine(d, 1, &engine))) return rc;
+  if (engine == IMMB_ENGINE_TC) {
+    IMMB_REQUIRE(wh_hi && (d->precision == IMMB_PREC_TF32 || (wh_lo && dy_lo)),
+                 "conv2d_dgrad: tcgen05 engine needs split weights and (for TF32x3) lo planes");
+    return conv_tc_dgrad(d, dy_hi, dy_lo, wh_hi, wh_lo, dx, (cudaStream_t)stream);
+  }
+  IMMB_REQUIRE(w, "conv2d_dgrad: SIMT engine needs the master weights");
+  return conv_simt_dgrad(d, dy_hi, dy_lo, w, dx, (cudaStream_t)stream);
+}
+
+extern "C" size_t immb_conv2d_wgrad_workspace(const immb_conv_desc* d) {
+  if (validate(d) != IMMB_OK) return 0;
+  int engine = IMMB_ENGINE_SIMT;
+  if (pick_engine(d, 2, &engine)) return 0;
+  return engine == IMMB_ENGINE_TC ? conv_tc_wgrad_workspace(d) : 0;
+}
+
+extern "C" int immb_conv2d_wgrad(const immb_conv_desc* d, const float* x_hi, const float* x_lo,
+                                 const float* dy_hi, const float* dy_lo, float* dw, void* workspace,
+                                 size_t ws_bytes, void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  IMMB_REQUIRE(x_hi && dy_hi && dw, "conv2d_wgrad: null tensors");
+  int engine = IMMB_ENGINE_SIMT;
+  if ((rc = pick_engine(d, 2, &engine))) return rc;
+  if (engine == IMMB_ENGINE_TC) {
+    IMMB_REQUIRE(d->precision == IMMB_PREC_TF32 || (x_lo && dy_lo), "conv2d_wgrad: TF32x3 needs lo planes");
+    return conv_tc_wgrad(d, x_hi, x_lo, dy_hi, dy_lo, dw, workspace, ws_bytes, (cudaStream_t)stream);
+  }
+  return conv_simt_wgrad(d, x_hi, x_lo, dy_hi, dy_lo, dw, (cudaStream_t)stream);
+}

@@ -1,0 +1,914 @@
+// Bandwidth-bound kernels of the IMM hot path: batch norm (stats / apply / backward), legacy bilinear
+// upsample, landmark bottleneck (softargmax + Gaussian maps), perceptual-loss glue, max-pool, and the
+// fused clip+Adam optimiser.  All NHWC fp32; channel index is the fastest-moving thread index so every
+// warp-level access is a contiguous 128-byte line.
+#include "common.cuh"
+
+namespace immb {
+
+constexpr float kBnEps = 1e-3f;       // tf.layers.batch_normalization default epsilon
+constexpr float kBnMomentum = 0.99f;  // default momentum
+
+// =====================================================================================================
+// per-channel reductions over pixels.  block = (32 channels, 8 pixel rows); grid = (pixel chunks, C/32)
+// =====================================================================================================
+constexpr int kRedRows = 8;
+constexpr int kRedPixPerBlock = 512;
+
+template <int NV, class F>
+__device__ __forceinline__ void channel_reduce(int64_t npix, int C, double* out, int out_stride, F f) {
+  const int c = blockIdx.y * 32 + threadIdx.x;
+  double acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+  if (c < C) {
+    int64_t p0 = (int64_t)blockIdx.x * kRedPixPerBlock;
+    int64_t p1 = p0 + kRedPixPerBlock;
+    if (p1 > npix) p1 = npix;
+    for (int64_t p = p0 + threadIdx.y; p < p1; p += kRedRows) {
+      float v[NV];
+      f(p, c, v);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) acc[i] += (double)v[i];
+    }
+  }
+  __shared__ double sm[NV][kRedRows][33];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) sm[i][threadIdx.y][threadIdx.x] = acc[i];
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int r = 0; r < kRedRows; ++r) s += sm[i][r][threadIdx.x];
+      atomicAdd(out + (size_t)i * out_stride + c, s);
+    }
+  }
+}
+
+__global__ void bn_stats_kernel(const float* __restrict__ y, int64_t npix, int C, int ycs, double* sums) {
+  channel_reduce<2>(npix, C, sums, C, [&](int64_t p, int c, float* v) {
+    float t = __ldg(y + p * ycs + c);
+    v[0] = t;
+    v[1] = t * t;
+  });
+}
+
+// sumsq in fp32 of a single value is exact enough; accumulation is in double.  (t*t rounds once.)
+
+__global__ void bn_finalize_kernel(const double* sums, double count, int C, const float* gamma,
+                                   const float* beta, float* mm, float* mv, int training, float* scale,
+                                   float* shift, float* mean_o, float* invstd_o) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, var;
+  if (training) {
+    double m = sums[c] / count;
+    double v = sums[C + c] / count - m * m;
+    if (v < 0.0) v = 0.0;
+    mean = (float)m;
+    var = (float)v;
+    double vu = v * (count / (count > 1.0 ? count - 1.0 : 1.0));
+    mm[c] = mm[c] - (mm[c] - mean) * (1.0f - kBnMomentum);
+    mv[c] = mv[c] - (mv[c] - (float)vu) * (1.0f - kBnMomentum);
+  } else {
+    mean = mm[c];
+    var = mv[c];
+  }
+  float inv = rsqrtf(var + kBnEps);
+  // one Newton step: rsqrtf is ~2 ulp; make it correctly rounded to match the CPU rsqrt path
+  inv = inv * (1.5f - 0.5f * (var + kBnEps) * inv * inv);
+  float sc = gamma[c] * inv;
+  scale[c] = sc;
+  shift[c] = beta[c] - mean * sc;
+  mean_o[c] = mean;
+  invstd_o[c] = inv;
+}
+
+__device__ __forceinline__ float bn_act(float y, float sc, float sh, int relu) {
+  float z = fmaf(y, sc, sh);
+  return (relu && z < 0.f) ? 0.f : z;
+}
+
+__global__ void bn_apply_kernel(const float* __restrict__ y, int64_t npix, int C, int ycs,
+                                const float* __restrict__ scale, const float* __restrict__ shift, int relu,
+                                float* out_hi, float* out_lo, int ocs) {
+  int64_t total = npix * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = i / C;
+    int c = (int)(i - p * C);
+    float v = bn_act(__ldg(y + p * ycs + c), __ldg(scale + c), __ldg(shift + c), relu);
+    store_split(out_hi, out_lo, (size_t)(p * ocs + c), v);
+  }
+}
+
+// fused [relu](bn(y)) + TF1 legacy bilinear x2 (src = dst/2, no half-pixel): out[2i]=a[i], out[2i+1]=(a[i]+a[min(i+1,n-1)])/2
+__global__ void bn_apply_up2x_kernel(const float* __restrict__ y, int N, int H, int W, int C, int ycs,
+                                     const float* __restrict__ scale, const float* __restrict__ shift,
+                                     int relu, float* out_hi, float* out_lo, int ocs) {
+  const int Ho = 2 * H, Wo = 2 * W;
+  int64_t total = (int64_t)N * Ho * Wo * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t p = i / C;
+    int wo = (int)(p % Wo);
+    int64_t q = p / Wo;
+    int ho = (int)(q % Ho);
+    int n = (int)(q / Ho);
+    int h0 = ho >> 1, w0 = wo >> 1;
+    int h1 = min(h0 + 1, H - 1), w1 = min(w0 + 1, W - 1);
+    float fh = (ho & 1) ? 0.5f : 0.f, fw = (wo & 1) ? 0.5f : 0.f;
+    float sc = __ldg(scale + c), sh = __ldg(shift + c);
+    const float* base = y + (int64_t)n * H * W * ycs + c;
+    float a00 = bn_act(__ldg(base + ((int64_t)h0 * W + w0) * ycs), sc, sh, relu);
+    float a01 = bn_act(__ldg(base + ((int64_t)h0 * W + w1) * ycs), sc, sh, relu);
+    float a10 = bn_act(__ldg(base + ((int64_t)h1 * W + w0) * ycs), sc, sh, relu);
+    float a11 = bn_act(__ldg(base + ((int64_t)h1 * W + w1) * ycs), sc, sh, relu);
+    float top = a00 + (a01 - a00) * fw;
+    float bot = a10 + (a11 - a10) * fw;
+    float v = top + (bot - top) * fh;
+    store_split(out_hi, out_lo, (size_t)(p * ocs + c), v);
+  }
+}
+
+__global__ void upsample2x_bwd_kernel(const float* __restrict__ gup, int N, int H, int W, int C, int gcs,
+                                      float* g) {
+  const int Ho = 2 * H, Wo = 2 * W;
+  int64_t total = (int64_t)N * H * W * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t p = i / C;
+    int w = (int)(p % W);
+    int64_t q = p / W;
+    int h = (int)(q % H);
+    int n = (int)(q / H);
+    const float* base = gup + (int64_t)n * Ho * Wo * gcs + c;
+    float acc = 0.f;
+#pragma unroll
+    for (int dh = -1; dh <= 1; ++dh) {
+      int hh = 2 * h + dh;
+      if (hh < 0) continue;
+      float wh = dh == 0 ? 1.f : (dh < 0 ? 0.5f : (h == H - 1 ? 1.f : 0.5f));
+#pragma unroll
+      for (int dw = -1; dw <= 1; ++dw) {
+        int ww = 2 * w + dw;
+        if (ww < 0) continue;
+        float wwt = dw == 0 ? 1.f : (dw < 0 ? 0.5f : (w == W - 1 ? 1.f : 0.5f));
+        acc += wh * wwt * __ldg(base + ((int64_t)hh * Wo + ww) * gcs);
+      }
+    }
+    g[i] = acc;
+  }
+}
+
+__global__ void bn_bwd_reduce_kernel(const float* __restrict__ g, int gcs, const float* __restrict__ y,
+                                     int ycs, int64_t npix, int C, const float* __restrict__ scale,
+                                     const float* __restrict__ shift, const float* __restrict__ mean,
+                                     const float* __restrict__ invstd, int relu, double* sums) {
+  channel_reduce<2>(npix, C, sums, C, [&](int64_t p, int c, float* v) {
+    float yy = __ldg(y + p * ycs + c);
+    float gg = __ldg(g + p * gcs + c);
+    float z = fmaf(yy, __ldg(scale + c), __ldg(shift + c));
+    float dz = (relu && !(z > 0.f)) ? 0.f : gg;
+    float xh = (yy - __ldg(mean + c)) * __ldg(invstd + c);
+    v[0] = dz;
+    v[1] = dz * xh;
+  });
+}
+
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ g, int gcs, const float* __restrict__ y,
+                                    int ycs, int64_t npix, int C, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, int relu, const double* __restrict__ sums,
+                                    float* dy_hi, float* dy_lo, float* dgamma, float* dbeta,
+                                    double* dbias_acc) {
+  const double inv_n = 1.0 / (double)npix;
+  if (blockIdx.x == 0 && threadIdx.y == 0) {
+    int c = blockIdx.y * 32 + threadIdx.x;
+    if (c < C) {
+      dbeta[c] = (float)sums[c];
+      dgamma[c] = (float)sums[C + c];
+    }
+  }
+  channel_reduce<1>(npix, C, dbias_acc, C, [&](int64_t p, int c, float* v) {
+    float yy = __ldg(y + p * ycs + c);
+    float gg = __ldg(g + p * gcs + c);
+    float sc = __ldg(scale + c);
+    float z = fmaf(yy, sc, __ldg(shift + c));
+    float dz = (relu && !(z > 0.f)) ? 0.f : gg;
+    float xh = (yy - __ldg(mean + c)) * __ldg(invstd + c);
+    float mdz = (float)(sums[c] * inv_n);
+    float mdzx = (float)(sums[C + c] * inv_n);
+    float dy = sc * (dz - mdz - xh * mdzx);
+    store_split(dy_hi, dy_lo, (size_t)(p * C + c), dy);
+    v[0] = dy;
+  });
+}
+
+__global__ void bias_grad_kernel(const float* __restrict__ g_hi, const float* __restrict__ g_lo, int gcs,
+                                 int64_t npix, int C, double* acc) {
+  channel_reduce<1>(npix, C, acc, C, [&](int64_t p, int c, float* v) {
+    v[0] = load_split(g_hi, g_lo, (size_t)(p * gcs + c));
+  });
+}
+
+__global__ void cast_d2f_kernel(const double* s, float* d, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = (float)s[i];
+}
+
+__global__ void split_planes_kernel(const float* __restrict__ v, float* hi, float* lo, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    store_split(hi, lo, (size_t)i, __ldg(v + i));
+}
+
+// =====================================================================================================
+// landmark bottleneck: one warp per (b, k)
+// =====================================================================================================
+__device__ __forceinline__ float lin_coord(int i, int S) {
+  // tf.linspace(-1, 1, S): start + i * (stop - start) / (S - 1)
+  return S > 1 ? -1.0f + (float)i * (2.0f / (float)(S - 1)) : -1.0f;
+}
+
+__global__ void softargmax_gauss_fwd_kernel(const float* __restrict__ heat, int B, int S, int K, int hcs,
+                                            float inv_std, float* mu, float* py, float* px, int Sg,
+                                            float* maps_hi, float* maps_lo, int ocs, int c_off) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= B * K) return;
+  int b = warp / K, k = warp - b * K;
+  const float* hb = heat + (int64_t)b * S * S * hcs + k;
+  float ly = 0.f, lx = 0.f;
+  if (lane < S) {
+    for (int j = 0; j < S; ++j) {
+      ly += __ldg(hb + ((int64_t)lane * S + j) * hcs);   // mean over w for row `lane`
+      lx += __ldg(hb + ((int64_t)j * S + lane) * hcs);   // mean over h for col `lane`
+    }
+    ly /= (float)S;
+    lx /= (float)S;
+  } else {
+    ly = -INFINITY;
+    lx = -INFINITY;
+  }
+  float my = ly, mx = lx;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    my = fmaxf(my, __shfl_xor_sync(0xffffffffu, my, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  float ey = lane < S ? expf(ly - my) : 0.f;
+  float ex = lane < S ? expf(lx - mx) : 0.f;
+  float sy = warp_sum(ey), sx = warp_sum(ex);
+  float pyv = ey / sy, pxv = ex / sx;
+  float c = lin_coord(lane, S);
+  float muy = warp_sum(lane < S ? pyv * c : 0.f);
+  float mux = warp_sum(lane < S ? pxv * c : 0.f);
+  if (lane < S) {
+    py[((int64_t)b * S + lane) * K + k] = pyv;
+    px[((int64_t)b * S + lane) * K + k] = pxv;
+  }
+  if (lane == 0) {
+    mu[((int64_t)b * K + k) * 2 + 0] = muy;
+    mu[((int64_t)b * K + k) * 2 + 1] = mux;
+  }
+  if (maps_hi) {
+    float inv2 = inv_std * inv_std;
+    for (int t = lane; t < Sg * Sg; t += 32) {
+      int i = t / Sg, j = t - i * Sg;
+      float dy = lin_coord(i, Sg) - muy, dx = lin_coord(j, Sg) - mux;
+      float gval = expf(-(dy * dy + dx * dx) * inv2);
+      store_split(maps_hi, maps_lo, (size_t)(((int64_t)b * Sg * Sg + t) * ocs + c_off + k), gval);
+    }
+  }
+}
+
+__global__ void softargmax_gauss_bwd_kernel(const float* __restrict__ gmaps, int gcs, int c_off,
+                                            const float* __restrict__ mu, const float* __restrict__ py,
+                                            const float* __restrict__ px, int B, int S, int K, int Sg,
+                                            float inv_std, float* gheat, int ghcs) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= B * K) return;
+  int b = warp / K, k = warp - b * K;
+  float muy = mu[((int64_t)b * K + k) * 2 + 0], mux = mu[((int64_t)b * K + k) * 2 + 1];
+  float inv2 = inv_std * inv_std;
+  float gy = 0.f, gx = 0.f;
+  for (int t = lane; t < Sg * Sg; t += 32) {
+    int i = t / Sg, j = t - i * Sg;
+    float dy = lin_coord(i, Sg) - muy, dx = lin_coord(j, Sg) - mux;
+    float gval = expf(-(dy * dy + dx * dx) * inv2);
+    float gg = __ldg(gmaps + ((int64_t)b * Sg * Sg + t) * gcs + c_off + k) * gval * 2.0f * inv2;
+    gy += gg * dy;
+    gx += gg * dx;
+  }
+  gy = warp_sum(gy);
+  gx = warp_sum(gx);
+  // d mu_y / d ly[h] = py[h] (c[h] - mu_y);  ly[h] = mean_w x[h, w]
+  float ay = 0.f, ax = 0.f;
+  if (lane < S) {
+    float c = lin_coord(lane, S);
+    ay = py[((int64_t)b * S + lane) * K + k] * (c - muy) * gy / (float)S;
+    ax = px[((int64_t)b * S + lane) * K + k] * (c - mux) * gx / (float)S;
+  }
+  for (int h = 0; h < S; ++h) {
+    float ayh = __shfl_sync(0xffffffffu, ay, h);
+    if (lane < S) gheat[((int64_t)b * S * S + (int64_t)h * S + lane) * ghcs + k] = ayh + ax;
+  }
+}
+
+__global__ void gaussian_maps_kernel(const float* __restrict__ mu, int B, int K, int S, float inv_std,
+                                     float* maps) {
+  int64_t total = (int64_t)B * S * S * K;
+  float inv2 = inv_std * inv_std;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int k = (int)(i % K);
+    int64_t p = i / K;
+    int j = (int)(p % S);
+    int64_t q = p / S;
+    int ii = (int)(q % S);
+    int b = (int)(q / S);
+    float dy = lin_coord(ii, S) - mu[((int64_t)b * K + k) * 2 + 0];
+    float dx = lin_coord(j, S) - mu[((int64_t)b * K + k) * 2 + 1];
+    maps[i] = expf(-(dy * dy + dx * dx) * inv2);
+  }
+}
+
+// =====================================================================================================
+// perceptual-loss glue
+// =====================================================================================================
+__global__ void vgg_prologue_kernel(const float* __restrict__ gt, const float* __restrict__ pred, int pcs,
+                                    int B, int R, float* out_hi, float* out_lo) {
+  int64_t per = (int64_t)B * R * R;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * per;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float r, g, b;
+    if (i < per) {
+      r = __ldg(gt + i * 3);
+      g = __ldg(gt + i * 3 + 1);
+      b = __ldg(gt + i * 3 + 2);
+    } else {
+      int64_t j = i - per;
+      r = __ldg(pred + j * pcs);
+      g = __ldg(pred + j * pcs + 1);
+      b = __ldg(pred + j * pcs + 2);
+    }
+    float v = (r + g + b) / 3.0f;
+    v = v / 255.0f;
+    v = v - (114.451f / 255.0f);
+    store_split(out_hi, out_lo, (size_t)i, v);
+  }
+}
+
+__global__ void maxpool2x2_fwd_kernel(const float* __restrict__ x_hi, const float* __restrict__ x_lo, int N,
+                                      int H, int W, int C, float* o_hi, float* o_lo) {
+  int Ho = H / 2, Wo = W / 2;
+  int64_t total = (int64_t)N * Ho * Wo * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t p = i / C;
+    int wo = (int)(p % Wo);
+    int64_t q = p / Wo;
+    int ho = (int)(q % Ho);
+    int n = (int)(q / Ho);
+    size_t base = (((size_t)n * H + 2 * ho) * W + 2 * wo) * C + c;
+    float v = load_split(x_hi, x_lo, base);
+    v = fmaxf(v, load_split(x_hi, x_lo, base + C));
+    v = fmaxf(v, load_split(x_hi, x_lo, base + (size_t)W * C));
+    v = fmaxf(v, load_split(x_hi, x_lo, base + (size_t)W * C + C));
+    store_split(o_hi, o_lo, (size_t)i, v);
+  }
+}
+
+__global__ void maxpool2x2_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ x_hi,
+                                      const float* __restrict__ x_lo, int N, int H, int W, int C,
+                                      float* g_in) {
+  int Ho = H / 2, Wo = W / 2;
+  int64_t total = (int64_t)N * Ho * Wo * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t p = i / C;
+    int wo = (int)(p % Wo);
+    int64_t q = p / Wo;
+    int ho = (int)(q % Ho);
+    int n = (int)(q / Ho);
+    size_t base = (((size_t)n * H + 2 * ho) * W + 2 * wo) * C + c;
+    size_t idx[4] = {base, base + C, base + (size_t)W * C, base + (size_t)W * C + C};
+    int best = 0;
+    float bv = load_split(x_hi, x_lo, idx[0]);
+#pragma unroll
+    for (int t = 1; t < 4; ++t) {
+      float v = load_split(x_hi, x_lo, idx[t]);
+      if (v > bv) {
+        bv = v;
+        best = t;
+      }
+    }
+    float gg = __ldg(g_out + i);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) g_in[idx[t]] = (t == best) ? gg : 0.f;
+  }
+}
+
+__global__ void perceptual_level_sum_kernel(const float* __restrict__ fg_hi, const float* __restrict__ fg_lo,
+                                            int gcs, const float* __restrict__ fp_hi,
+                                            const float* __restrict__ fp_lo, int pcs, int B, int h, int w, int C,
+                                            const float* __restrict__ mask, int R, double* acc) {
+  int64_t per = (int64_t)B * h * w;
+  int64_t total = per * C;
+  int s = R / h;
+  double local = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t p = i / C;
+    float d = load_split(fg_hi, fg_lo, (size_t)(p * gcs + c)) - load_split(fp_hi, fp_lo, (size_t)(p * pcs + c));
+    float m = 1.f;
+    if (mask) {
+      int ww = (int)(p % w);
+      int64_t q = p / w;
+      int hh = (int)(q % h);
+      int b = (int)(q / h);
+      m = __ldg(mask + ((int64_t)b * R + (int64_t)hh * s) * R + (int64_t)ww * s);
+    }
+    local += (double)(m * (d * d));
+  }
+  local = warp_sum(local);
+  __shared__ double sm[32];
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) sm[wid] = local;
+  __syncthreads();
+  if (wid == 0) {
+    double v = lane < (blockDim.x >> 5) ? sm[lane] : 0.0;
+    v = warp_sum(v);
+    if (lane == 0) atomicAdd(acc, v);
+  }
+}
+
+__global__ void perceptual_finalize_kernel(const double* acc, const double* counts, int n_levels, float* agg,
+                                           int training, float* levels, float* rec_loss, float* coef) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  float total = 0.f;
+  for (int k = 0; k < n_levels; ++k) {
+    float s = (float)(acc[k] / counts[k]);
+    float a = agg[k];
+    float wl = a + (1.0f - 0.99f) * (s - a);
+    float L = s / wl;
+    levels[k] = L;
+    total += L;
+    coef[k] = (float)(1000.0 * 0.99 * (double)a / ((double)wl * (double)wl) * (-2.0 / counts[k]));
+    if (training) agg[k] = wl;
+  }
+  rec_loss[0] = 1000.0f * total;
+}
+
+__global__ void vgg_bwd_combine_kernel(const float* __restrict__ g_next, const float* __restrict__ fg_hi,
+                                       const float* __restrict__ fg_lo, const float* __restrict__ fp_hi,
+                                       const float* __restrict__ fp_lo, int B, int h, int w, int C,
+                                       const float* __restrict__ mask, int R, const float* __restrict__ coef,
+                                       float* dy_hi, float* dy_lo) {
+  int64_t per = (int64_t)B * h * w;
+  int64_t total = per * C;
+  int s = R / h;
+  float cf = coef ? __ldg(coef) : 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = i / C;
+    float fp = load_split(fp_hi, fp_lo, (size_t)i);
+    float g = g_next ? __ldg(g_next + i) : 0.f;
+    if (coef) {
+      float fg = load_split(fg_hi, fg_lo, (size_t)i);
+      float m = 1.f;
+      if (mask) {
+        int ww = (int)(p % w);
+        int64_t q = p / w;
+        int hh = (int)(q % h);
+        int b = (int)(q / h);
+        m = __ldg(mask + ((int64_t)b * R + (int64_t)hh * s) * R + (int64_t)ww * s);
+      }
+      g += cf * m * (fg - fp);
+    }
+    store_split(dy_hi, dy_lo, (size_t)i, fp > 0.f ? g : 0.f);
+  }
+}
+
+__global__ void pred_grad_kernel(const float* __restrict__ gt, const float* __restrict__ pred, int pcs,
+                                 const float* __restrict__ mask, const float* __restrict__ coef_in,
+                                 const float* __restrict__ g_vggin, int B, int R, float* g_hi, float* g_lo) {
+  int64_t per = (int64_t)B * R * R;
+  float cf = __ldg(coef_in);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per * pcs;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % pcs);
+    int64_t p = i / pcs;
+    float g = 0.f;
+    if (c < 3) {
+      float m = mask ? __ldg(mask + p) : 1.f;
+      g = cf * m * (__ldg(gt + p * 3 + c) - __ldg(pred + i));
+      if (g_vggin) g += __ldg(g_vggin + p) * (1.0f / 3.0f) * (1.0f / 255.0f);
+    }
+    store_split(g_hi, g_lo, (size_t)i, g);
+  }
+}
+
+__device__ __forceinline__ void ac_src(int o, int n_in, int n_out, int& lo, int& hi, float& f) {
+  float scale = n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.f;
+  float s = (float)o * scale;
+  lo = min((int)floorf(s), n_in - 1);
+  hi = min(lo + 1, n_in - 1);
+  f = s - (float)lo;
+}
+
+__global__ void resize_ac_fwd_kernel(const float* __restrict__ x_hi, const float* __restrict__ x_lo, int xcs,
+                                     int N, int H, int W, int C, int Ho, int Wo, float* o_hi, float* o_lo,
+                                     int ocs) {
+  int64_t total = (int64_t)N * Ho * Wo * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t p = i / C;
+    int wo = (int)(p % Wo);
+    int64_t q = p / Wo;
+    int ho = (int)(q % Ho);
+    int n = (int)(q / Ho);
+    int h0, h1, w0, w1;
+    float fh, fw;
+    ac_src(ho, H, Ho, h0, h1, fh);
+    ac_src(wo, W, Wo, w0, w1, fw);
+    size_t nb = (size_t)n * H * W;
+    float a00 = load_split(x_hi, x_lo, (nb + (size_t)h0 * W + w0) * xcs + c);
+    float a01 = load_split(x_hi, x_lo, (nb + (size_t)h0 * W + w1) * xcs + c);
+    float a10 = load_split(x_hi, x_lo, (nb + (size_t)h1 * W + w0) * xcs + c);
+    float a11 = load_split(x_hi, x_lo, (nb + (size_t)h1 * W + w1) * xcs + c);
+    float top = a00 + (a01 - a00) * fw, bot = a10 + (a11 - a10) * fw;
+    store_split(o_hi, o_lo, (size_t)(p * ocs + c), top + (bot - top) * fh);
+  }
+}
+
+// adjoint by scatter; g_in must be zeroed by the caller
+__global__ void resize_ac_bwd_kernel(const float* __restrict__ g_out, int gcs, int N, int H, int W, int C,
+                                     int Ho, int Wo, float* g_in) {
+  int64_t total = (int64_t)N * Ho * Wo * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t p = i / C;
+    int wo = (int)(p % Wo);
+    int64_t q = p / Wo;
+    int ho = (int)(q % Ho);
+    int n = (int)(q / Ho);
+    int h0, h1, w0, w1;
+    float fh, fw;
+    ac_src(ho, H, Ho, h0, h1, fh);
+    ac_src(wo, W, Wo, w0, w1, fw);
+    float g = __ldg(g_out + p * gcs + c);
+    size_t nb = (size_t)n * H * W;
+    atomicAdd(g_in + (nb + (size_t)h0 * W + w0) * C + c, g * (1.f - fh) * (1.f - fw));
+    atomicAdd(g_in + (nb + (size_t)h0 * W + w1) * C + c, g * (1.f - fh) * fw);
+    atomicAdd(g_in + (nb + (size_t)h1 * W + w0) * C + c, g * fh * (1.f - fw));
+    atomicAdd(g_in + (nb + (size_t)h1 * W + w1) * C + c, g * fh * fw);
+  }
+}
+
+// =====================================================================================================
+// optimiser: per-tensor clip_by_norm + TF Adam over flat buffers; one block per chunk
+// =====================================================================================================
+__global__ void adam_norms_kernel(const float* __restrict__ p, const float* __restrict__ g,
+                                  const int32_t* __restrict__ chunk_tensor, const int64_t* __restrict__ chunk_off,
+                                  const int32_t* __restrict__ chunk_len, const float* __restrict__ tensor_wd,
+                                  float gscale, double* sq, double* wsq) {
+  int ch = blockIdx.x;
+  int t = chunk_tensor[ch];
+  int64_t off = chunk_off[ch];
+  int len = chunk_len[ch];
+  float wd = tensor_wd[t];
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    float pv = __ldg(p + off + i);
+    float gv = fmaf(wd, pv, __ldg(g + off + i) * gscale);
+    a += (double)gv * (double)gv;
+    b += (double)pv * (double)pv;
+  }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  __shared__ double sa[32], sb[32];
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) {
+    sa[wid] = a;
+    sb[wid] = b;
+  }
+  __syncthreads();
+  if (wid == 0) {
+    a = lane < (blockDim.x >> 5) ? sa[lane] : 0.0;
+    b = lane < (blockDim.x >> 5) ? sb[lane] : 0.0;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (lane == 0) {
+      atomicAdd(sq + t, a);
+      atomicAdd(wsq + t, b);
+    }
+  }
+}
+
+__global__ void adam_apply_kernel(float* p, const float* __restrict__ g, float* m, float* v,
+                                  const int32_t* __restrict__ chunk_tensor, const int64_t* __restrict__ chunk_off,
+                                  const int32_t* __restrict__ chunk_len, const float* __restrict__ tensor_wd,
+                                  float gscale, const double* __restrict__ sq, float clip, float lr_t,
+                                  float beta1, float beta2, float eps) {
+  int ch = blockIdx.x;
+  int t = chunk_tensor[ch];
+  int64_t off = chunk_off[ch];
+  int len = chunk_len[ch];
+  float wd = tensor_wd[t];
+  // tf.clip_by_norm: g * clip / max(||g||, clip)
+  float nrm = (float)sqrt(sq[t]);
+  float cscale = clip > 0.f ? clip / fmaxf(nrm, clip) : 1.f;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    int64_t j = off + i;
+    float pv = p[j];
+    float gv = fmaf(wd, pv, __ldg(g + j) * gscale) * cscale;
+    float mv = beta1 * m[j] + (1.f - beta1) * gv;
+    float vv = beta2 * v[j] + (1.f - beta2) * gv * gv;
+    m[j] = mv;
+    v[j] = vv;
+    p[j] = pv - lr_t * mv / (sqrtf(vv) + eps);
+  }
+}
+
+__global__ void total_loss_kernel(const float* rec_loss, const double* wsq, const float* tensor_wd,
+                                  int n_tensors, float* weights_loss, float* total) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  double s = 0.0;
+  for (int t = 0; t < n_tensors; ++t) s += 0.5 * (double)tensor_wd[t] * wsq[t];
+  weights_loss[0] = (float)s;
+  total[0] = rec_loss[0] + (float)s;
+}
+
+// HWIO master -> packed [tap][Cout][cin_pad] and split [tap][cin_pad][Cout], both as (hi, lo) planes
+__global__ void pack_weights_kernel(const float* __restrict__ w, int taps, int Cin, int Cout, int cin_pad,
+                                    float* wp_hi, float* wp_lo, float* wh_hi, float* wh_lo) {
+  int64_t total = (int64_t)taps * cin_pad * Cout;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int co = (int)(i % Cout);
+    int64_t q = i / Cout;
+    int ci = (int)(q % cin_pad);
+    int tap = (int)(q / cin_pad);
+    float val = ci < Cin ? __ldg(w + ((int64_t)tap * Cin + ci) * Cout + co) : 0.f;
+    float hi, lo;
+    split_tf32(val, hi, lo);
+    if (wh_hi) {
+      wh_hi[i] = hi;
+      if (wh_lo) wh_lo[i] = lo;
+    }
+    if (wp_hi) {
+      size_t j = ((size_t)tap * Cout + co) * cin_pad + ci;
+      wp_hi[j] = hi;
+      if (wp_lo) wp_lo[j] = lo;
+    }
+  }
+}
+
+static inline int ew_grid(int64_t total, int block = 256) {
+  int64_t g = (total + block - 1) / block;
+  int64_t cap = (int64_t)kNumSMs * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+static inline dim3 red_grid(int64_t npix, int C) {
+  return dim3((unsigned)((npix + kRedPixPerBlock - 1) / kRedPixPerBlock), (unsigned)((C + 31) / 32));
+}
+
+}  // namespace immb
+
+using namespace immb;
+#define ST(s) ((cudaStream_t)(s))
+
+extern "C" int immb_split_planes(const float* v, float* hi, float* lo, int64_t n, void* stream) {
+  IMMB_REQUIRE(v && hi && n >= 0, "split_planes: bad args");
+  if (n == 0) return IMMB_OK;
+  split_planes_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(v, hi, lo, n);
+  return check_launch("split_planes");
+}
+
+extern "C" int immb_bn_stats(const float* y, int64_t npix, int C, int ycs, double* sums, void* stream) {
+  IMMB_REQUIRE(y && sums && npix > 0 && C > 0 && ycs >= C, "bn_stats: bad args");
+  bn_stats_kernel<<<red_grid(npix, C), dim3(32, kRedRows), 0, ST(stream)>>>(y, npix, C, ycs, sums);
+  return check_launch("bn_stats");
+}
+
+extern "C" int immb_bn_finalize(const double* sums, int64_t count, int C, const float* gamma,
+                                const float* beta, float* mm, float* mv, int training, float* scale,
+                                float* shift, float* mean, float* invstd, void* stream) {
+  IMMB_REQUIRE(gamma && beta && mm && mv && scale && shift && mean && invstd && C > 0, "bn_finalize: bad args");
+  IMMB_REQUIRE(!training || sums, "bn_finalize: training needs sums");
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, ST(stream)>>>(sums, (double)count, C, gamma, beta, mm, mv,
+                                                               training, scale, shift, mean, invstd);
+  return check_launch("bn_finalize");
+}
+
+extern "C" int immb_bn_apply(const float* y, int N, int H, int W, int C, int ycs, const float* scale,
+                             const float* shift, int relu, int up2x, float* out_hi, float* out_lo, int ocs,
+                             void* stream) {
+  IMMB_REQUIRE(y && scale && shift && out_hi && ycs >= C && ocs >= C, "bn_apply: bad args");
+  int64_t npix = (int64_t)N * H * W;
+  if (up2x) {
+    bn_apply_up2x_kernel<<<ew_grid(npix * 4 * C), 256, 0, ST(stream)>>>(y, N, H, W, C, ycs, scale, shift,
+                                                                         relu, out_hi, out_lo, ocs);
+  } else {
+    bn_apply_kernel<<<ew_grid(npix * C), 256, 0, ST(stream)>>>(y, npix, C, ycs, scale, shift, relu, out_hi,
+                                                                out_lo, ocs);
+  }
+  return check_launch("bn_apply");
+}
+
+extern "C" int immb_upsample2x_bwd(const float* g_up, int N, int H, int W, int C, int gcs, float* g,
+                                   void* stream) {
+  IMMB_REQUIRE(g_up && g && gcs >= C, "upsample2x_bwd: bad args");
+  upsample2x_bwd_kernel<<<ew_grid((int64_t)N * H * W * C), 256, 0, ST(stream)>>>(g_up, N, H, W, C, gcs, g);
+  return check_launch("upsample2x_bwd");
+}
+
+extern "C" int immb_bn_bwd_reduce(const float* g, int gcs, const float* y, int ycs, int64_t npix, int C,
+                                  const float* scale, const float* shift, const float* mean,
+                                  const float* invstd, int relu, double* sums, void* stream) {
+  IMMB_REQUIRE(g && y && sums && gcs >= C && ycs >= C, "bn_bwd_reduce: bad args");
+  bn_bwd_reduce_kernel<<<red_grid(npix, C), dim3(32, kRedRows), 0, ST(stream)>>>(
+      g, gcs, y, ycs, npix, C, scale, shift, mean, invstd, relu, sums);
+  return check_launch("bn_bwd_reduce");
+}
+
+extern "C" int immb_bn_bwd_apply(const float* g, int gcs, const float* y, int ycs, int64_t npix, int C,
+                                 const float* scale, const float* shift, const float* mean,
+                                 const float* invstd, int relu, const double* sums, float* dy_hi,
+                                 float* dy_lo, float* dgamma, float* dbeta, double* dbias_acc, void* stream) {
+  IMMB_REQUIRE(g && y && sums && dy_hi && dgamma && dbeta && dbias_acc, "bn_bwd_apply: bad args");
+  bn_bwd_apply_kernel<<<red_grid(npix, C), dim3(32, kRedRows), 0, ST(stream)>>>(
+      g, gcs, y, ycs, npix, C, scale, shift, mean, invstd, relu, sums, dy_hi, dy_lo, dgamma, dbeta, dbias_acc);
+  return check_launch("bn_bwd_apply");
+}
+
+extern "C" int immb_bias_grad(const float* g_hi, const float* g_lo, int gcs, int64_t npix, int C, double* acc,
+                              void* stream) {
+  IMMB_REQUIRE(g_hi && acc && gcs >= C, "bias_grad: bad args");
+  bias_grad_kernel<<<red_grid(npix, C), dim3(32, kRedRows), 0, ST(stream)>>>(g_hi, g_lo, gcs, npix, C, acc);
+  return check_launch("bias_grad");
+}
+
+extern "C" int immb_cast_d2f(const double* src, float* dst, int64_t n, void* stream) {
+  IMMB_REQUIRE(src && dst && n > 0, "cast_d2f: bad args");
+  cast_d2f_kernel<<<ceil_div(n, 256), 256, 0, ST(stream)>>>(src, dst, n);
+  return check_launch("cast_d2f");
+}
+
+extern "C" int immb_softargmax_gauss_fwd(const float* heat, int B, int S, int K, int hcs, float inv_std,
+                                         float* mu, float* py, float* px, int Sg, float* maps_hi,
+                                         float* maps_lo, int ocs, int c_off, void* stream) {
+  IMMB_REQUIRE(heat && mu && py && px && S >= 1 && S <= 32 && K >= 1 && hcs >= K, "softargmax_fwd: bad args (S<=32)");
+  IMMB_REQUIRE(!maps_hi || (Sg >= 1 && ocs >= c_off + K), "softargmax_fwd: bad map args");
+  int warps = B * K;
+  softargmax_gauss_fwd_kernel<<<ceil_div((int64_t)warps * 32, 128), 128, 0, ST(stream)>>>(
+      heat, B, S, K, hcs, inv_std, mu, py, px, Sg, maps_hi, maps_lo, ocs, c_off);
+  return check_launch("softargmax_gauss_fwd");
+}
+
+extern "C" int immb_softargmax_gauss_bwd(const float* g_maps, int gcs, int c_off, const float* mu,
+                                         const float* py, const float* px, int B, int S, int K, int Sg,
+                                         float inv_std, float* g_heat, int ghcs, void* stream) {
+  IMMB_REQUIRE(g_maps && mu && py && px && g_heat && S <= 32 && ghcs >= K, "softargmax_bwd: bad args");
+  int warps = B * K;
+  softargmax_gauss_bwd_kernel<<<ceil_div((int64_t)warps * 32, 128), 128, 0, ST(stream)>>>(
+      g_maps, gcs, c_off, mu, py, px, B, S, K, Sg, inv_std, g_heat, ghcs);
+  return check_launch("softargmax_gauss_bwd");
+}
+
+extern "C" int immb_gaussian_maps(const float* mu, int B, int K, int S, float inv_std, float* maps,
+                                  void* stream) {
+  IMMB_REQUIRE(mu && maps && B > 0 && K > 0 && S > 0, "gaussian_maps: bad args");
+  gaussian_maps_kernel<<<ew_grid((int64_t)B * S * S * K), 256, 0, ST(stream)>>>(mu, B, K, S, inv_std, maps);
+  return check_launch("gaussian_maps");
+}
+
+extern "C" int immb_vgg_prologue(const float* gt, const float* pred, int pcs, int B, int R, float* out_hi,
+                                 float* out_lo, void* stream) {
+  IMMB_REQUIRE(gt && pred && out_hi && pcs >= 3, "vgg_prologue: bad args");
+  vgg_prologue_kernel<<<ew_grid((int64_t)2 * B * R * R), 256, 0, ST(stream)>>>(gt, pred, pcs, B, R, out_hi,
+                                                                              out_lo);
+  return check_launch("vgg_prologue");
+}
+
+extern "C" int immb_maxpool2x2_fwd(const float* x_hi, const float* x_lo, int N, int H, int W, int C,
+                                   float* o_hi, float* o_lo, void* stream) {
+  IMMB_REQUIRE(x_hi && o_hi && (H % 2 == 0) && (W % 2 == 0), "maxpool_fwd: bad args (even sizes only)");
+  maxpool2x2_fwd_kernel<<<ew_grid((int64_t)N * (H / 2) * (W / 2) * C), 256, 0, ST(stream)>>>(x_hi, x_lo, N, H,
+                                                                                            W, C, o_hi, o_lo);
+  return check_launch("maxpool2x2_fwd");
+}
+
+extern "C" int immb_maxpool2x2_bwd(const float* g_out, const float* x_hi, const float* x_lo, int N, int H,
+                                   int W, int C, float* g_in, void* stream) {
+  IMMB_REQUIRE(g_out && x_hi && g_in && (H % 2 == 0) && (W % 2 == 0), "maxpool_bwd: bad args");
+  maxpool2x2_bwd_kernel<<<ew_grid((int64_t)N * (H / 2) * (W / 2) * C), 256, 0, ST(stream)>>>(g_out, x_hi, x_lo,
+                                                                                            N, H, W, C, g_in);
+  return check_launch("maxpool2x2_bwd");
+}
+
+extern "C" int immb_perceptual_level_sum(const float* fg_hi, const float* fg_lo, int gcs, const float* fp_hi,
+                                         const float* fp_lo, int pcs, int B, int h, int w, int C,
+                                         const float* mask, int R, double* acc, void* stream) {
+  IMMB_REQUIRE(fg_hi && fp_hi && acc && gcs >= C && pcs >= C && h > 0 && (!mask || R % h == 0),
+               "perceptual_level_sum: bad args");
+  perceptual_level_sum_kernel<<<ew_grid((int64_t)B * h * w * C), 256, 0, ST(stream)>>>(
+      fg_hi, fg_lo, gcs, fp_hi, fp_lo, pcs, B, h, w, C, mask, R, acc);
+  return check_launch("perceptual_level_sum");
+}
+
+extern "C" int immb_perceptual_finalize(const double* acc, const double* counts, int n_levels, float* agg,
+                                        int training, float* levels, float* rec_loss, float* coef,
+                                        void* stream) {
+  IMMB_REQUIRE(acc && counts && agg && levels && rec_loss && coef && n_levels > 0, "perceptual_finalize: bad args");
+  perceptual_finalize_kernel<<<1, 32, 0, ST(stream)>>>(acc, counts, n_levels, agg, training, levels, rec_loss,
+                                                       coef);
+  return check_launch("perceptual_finalize");
+}
+
+extern "C" int immb_vgg_bwd_combine(const float* g_next, const float* fg_hi, const float* fg_lo,
+                                    const float* fp_hi, const float* fp_lo, int B, int h, int w, int C,
+                                    const float* mask, int R, const float* coef, float* dy_hi, float* dy_lo,
+                                    void* stream) {
+  IMMB_REQUIRE(fp_hi && dy_hi && (g_next || coef) && (!coef || fg_hi), "vgg_bwd_combine: bad args");
+  vgg_bwd_combine_kernel<<<ew_grid((int64_t)B * h * w * C), 256, 0, ST(stream)>>>(
+      g_next, fg_hi, fg_lo, fp_hi, fp_lo, B, h, w, C, mask, R, coef, dy_hi, dy_lo);
+  return check_launch("vgg_bwd_combine");
+}
+
+extern "C" int immb_pred_grad(const float* gt, const float* pred, int pcs, const float* mask,
+                              const float* coef_input, const float* g_vggin, int B, int R, float* g_hi,
+                              float* g_lo, void* stream) {
+  IMMB_REQUIRE(gt && pred && coef_input && g_hi && pcs >= 3, "pred_grad: bad args");
+  pred_grad_kernel<<<ew_grid((int64_t)B * R * R * pcs), 256, 0, ST(stream)>>>(gt, pred, pcs, mask, coef_input,
+                                                                             g_vggin, B, R, g_hi, g_lo);
+  return check_launch("pred_grad");
+}
+
+extern "C" int immb_resize_ac_fwd(const float* x_hi, const float* x_lo, int xcs, int N, int H, int W, int C,
+                                  int Ho, int Wo, float* o_hi, float* o_lo, int ocs, void* stream) {
+  IMMB_REQUIRE(x_hi && o_hi && xcs >= C && ocs >= C, "resize_ac_fwd: bad args");
+  resize_ac_fwd_kernel<<<ew_grid((int64_t)N * Ho * Wo * C), 256, 0, ST(stream)>>>(x_hi, x_lo, xcs, N, H, W, C,
+                                                                                 Ho, Wo, o_hi, o_lo, ocs);
+  return check_launch("resize_ac_fwd");
+}
+
+extern "C" int immb_resize_ac_bwd(const float* g_out, int gcs, int N, int H, int W, int C, int Ho, int Wo,
+                                  float* g_in, void* stream) {
+  IMMB_REQUIRE(g_out && g_in && gcs >= C, "resize_ac_bwd: bad args");
+  cudaError_t e = cudaMemsetAsync(g_in, 0, sizeof(float) * (size_t)N * H * W * C, ST(stream));
+  if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "resize_ac_bwd memset: %s", cudaGetErrorString(e));
+  resize_ac_bwd_kernel<<<ew_grid((int64_t)N * Ho * Wo * C), 256, 0, ST(stream)>>>(g_out, gcs, N, H, W, C, Ho,
+                                                                                 Wo, g_in);
+  return check_launch("resize_ac_bwd");
+}
+
+extern "C" int immb_adam_norms(const float* p, const float* g, int64_t n, const int32_t* chunk_tensor,
+                               const int64_t* chunk_off, const int32_t* chunk_len, int n_chunks,
+                               const float* tensor_wd, float gscale, double* sq, double* wsq, void* stream) {
+  IMMB_REQUIRE(p && g && chunk_tensor && chunk_off && chunk_len && tensor_wd && sq && wsq && n_chunks > 0,
+               "adam_norms: bad args");
+  adam_norms_kernel<<<n_chunks, 256, 0, ST(stream)>>>(p, g, chunk_tensor, chunk_off, chunk_len, tensor_wd,
+                                                      gscale, sq, wsq);
+  return check_launch("adam_norms");
+}
+
+extern "C" int immb_adam_apply(float* p, const float* g, float* m, float* v, int64_t n,
+                               const int32_t* chunk_tensor, const int64_t* chunk_off, const int32_t* chunk_len,
+                               int n_chunks, const float* tensor_wd, float gscale, const double* sq, float clip,
+                               float lr_t, float beta1, float beta2, float eps, void* stream) {
+  IMMB_REQUIRE(p && g && m && v && chunk_tensor && chunk_off && chunk_len && tensor_wd && sq && n_chunks > 0,
+               "adam_apply: bad args");
+  adam_apply_kernel<<<n_chunks, 256, 0, ST(stream)>>>(p, g, m, v, chunk_tensor, chunk_off, chunk_len,
+                                                      tensor_wd, gscale, sq, clip, lr_t, beta1, beta2, eps);
+  return check_launch("adam_apply");
+}
+
+extern "C" int immb_total_loss(const float* rec_loss, const double* wsq, const float* tensor_wd, int n_tensors,
+                               float* weights_loss, float* total, void* stream) {
+  IMMB_REQUIRE(rec_loss && wsq && tensor_wd && weights_loss && total, "total_loss: bad args");
+  total_loss_kernel<<<1, 32, 0, ST(stream)>>>(rec_loss, wsq, tensor_wd, n_tensors, weights_loss, total);
+  return check_launch("total_loss");
+}
+
+extern "C" int immb_pack_weights(const float* w, int kh, int kw, int Cin, int Cout, int cin_pad, float* wp_hi,
+                                 float* wp_lo, float* wh_hi, float* wh_lo, void* stream) {
+  IMMB_REQUIRE(w && (wp_hi || wh_hi) && cin_pad >= Cin, "pack_weights: bad args");
+  pack_weights_kernel<<<ew_grid((int64_t)kh * kw * cin_pad * Cout), 256, 0, ST(stream)>>>(
+      w, kh * kw, Cin, Cout, cin_pad, wp_hi, wp_lo, wh_hi, wh_lo);
+  return check_launch("pack_weights");
+}

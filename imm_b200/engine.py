@@ -1,0 +1,669 @@
+"""Device-side execution engine of the IMM training step.
+
+Owns every device buffer (PyTorch tensors = memory only) and drives the hand-written sm_100a kernels of
+libimm_b200.so through the C ABI (imm_b200/_lib.py).  No torch op computes anything on the hot path and
+there is no CPU fallback.  The arithmetic follows the reference call sites cited in include/imm_b200.h and
+in the docstrings below (file:line under /root/reference).
+
+Data layout in HBM (per GPU, batch B, NHWC fp32):
+  * trainable parameters / gradients / Adam m,v : four flat fp32 buffers, tensors back to back in the
+    reference's variable order (TF names), one NCCL all-reduce over the flat gradient buffer;
+  * conv operands are "split planes" (hi, lo) = error-compensated TF32 pairs written by the producing kernel;
+  * raw conv outputs y (pre-BN) are kept for the BN backward; gradients wrt activations are single fp32.
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, call
+
+WD = 1e-5                 # base_model.py:65
+INIT_STD = 0.01           # base_model.py:66
+PERCEPTUAL_WS = [100.0, 1.6, 2.3, 1.8, 2.8, 100.0]    # imm_model.py:131
+VGG_ORDER = [('conv1_1', 64), ('conv1_2', 64), 'pool1', ('conv2_1', 128), ('conv2_2', 128), 'pool2',
+             ('conv3_1', 256), ('conv3_2', 256), ('conv3_3', 256), 'pool3',
+             ('conv4_1', 512), ('conv4_2', 512), ('conv4_3', 512), 'pool4',
+             ('conv5_1', 512), ('conv5_2', 512), ('conv5_3', 512), 'pool5']     # vgg16.py:338-373
+ADAM_CHUNK = 2048
+
+
+def same_pad(in_size, k, stride):
+  """TF SAME: out = ceil(in/stride); total = max((out-1)*stride + k - in, 0); before = total//2."""
+  out = -(-in_size // stride)
+  total = max((out - 1) * stride + k - in_size, 0)
+  return total // 2, total - total // 2
+
+
+def round_up(x, m):
+  return (x + m - 1) // m * m
+
+
+def encoder_spec(n_filters):
+  """imm_model.py:182-217 -> [(name, k, stride, cout)]."""
+  f = n_filters
+  return [('conv_1', 7, 1, f), ('conv_2', 3, 1, f), ('conv_3', 3, 2, 2 * f), ('conv_4', 3, 1, 2 * f),
+          ('conv_5', 3, 2, 4 * f), ('conv_6', 3, 1, 4 * f), ('conv_7', 3, 2, 8 * f), ('conv_8', 3, 1, 8 * f)]
+
+
+def renderer_spec(n_filters_render, final_res, n_final_out, start_res=16):
+  """imm_model.py:154-179 -> [(name, cout, batch_norm, relu, upsample_after)]."""
+  filters = n_filters_render * 8
+  size, conv_id, spec = start_res, 1, []
+  while size <= final_res:
+    spec.append(('conv_%d' % conv_id, filters, True, True, False))
+    if size == final_res:
+      spec.append(('conv_%d' % (conv_id + 1), n_final_out, False, False, False))
+      break
+    spec.append(('conv_%d' % (conv_id + 1), filters, True, True, True))
+    size *= 2
+    conv_id += 2
+    if filters >= 8:
+      filters //= 2
+  return spec
+
+
+class Planes(object):
+  """A split tensor: hi (+ optional lo) fp32 planes of identical shape [N,H,W,Cs]."""
+
+  def __init__(self, hi, lo=None):
+    self.hi, self.lo = hi, lo
+
+  @staticmethod
+  def alloc(shape, device, lo=True, zero=False):
+    f = torch.zeros if zero else torch.empty
+    return Planes(f(shape, dtype=torch.float32, device=device),
+                  f(shape, dtype=torch.float32, device=device) if lo else None)
+
+  def value(self):
+    return self.hi if self.lo is None else self.hi + self.lo
+
+  def half(self, i, B):
+    """i-th batch half of a [2B,...] tensor."""
+    return Planes(self.hi[i * B:(i + 1) * B], None if self.lo is None else self.lo[i * B:(i + 1) * B])
+
+
+class ConvLayer(object):
+  """One conv (+BN)(+ReLU)(+x2 upsample) block: IMMModel.conv -> nnu.conv_block (nn_utils.py:151-210)."""
+
+  def __init__(self, eng, prefix, name, k, stride, cin, cout, N, H, W, xcs, bn, relu, up2x, needs_dgrad,
+               trainable=True, epilogue=_lib.EPI_BIAS):
+    self.eng, self.prefix, self.name = eng, prefix, name
+    self.k, self.stride, self.cin, self.cout = k, stride, cin, cout
+    self.N, self.H, self.W, self.xcs = N, H, W, xcs
+    self.Ho, self.Wo = -(-H // stride), -(-W // stride)
+    self.bn, self.relu, self.up2x, self.needs_dgrad, self.trainable = bn, relu, up2x, needs_dgrad, trainable
+    self.cin_pad = round_up(cin, 32)
+    self.pad_t = same_pad(H, k, stride)[0]
+    self.pad_l = same_pad(W, k, stride)[0]
+    self.epilogue = epilogue
+    self.engine_override = None
+
+  def desc(self, N=None):
+    d = ConvDesc()
+    d.N, d.H, d.W, d.Cin = (self.N if N is None else N), self.H, self.W, self.cin
+    d.Cout, d.kh, d.kw, d.stride = self.cout, self.k, self.k, self.stride
+    d.Ho, d.Wo, d.pad_t, d.pad_l = self.Ho, self.Wo, self.pad_t, self.pad_l
+    d.x_cstride, d.y_cstride, d.cin_pad = self.xcs, self.cout, self.cin_pad
+    d.epilogue, d.precision = self.epilogue, self.eng.precision
+    d.engine = self.eng.engine if self.engine_override is None else self.engine_override
+    return d
+
+  def engines(self):
+    d = self.desc()
+    return tuple(_lib.lib().immb_conv_engine_for(d, op) for op in range(3))
+
+
+class IMMEngine(object):
+  """Buffers + kernel schedule for one model replica on one GPU.
+
+  config: attribute-style object with the reference's `model` section keys (configs/experiments/*.yaml):
+  n_maps, n_filters, n_filters_render, gauss_std, gauss_mode, renderer_stride, min_res, loss_mask,
+  channels_bug_fix, perceptual.comp, reconstruction_loss, perceptual.l2."""
+
+  def __init__(self, config, batch, image_size=128, device='cuda:0', precision=_lib.PREC_TF32X3,
+               engine=_lib.ENGINE_AUTO, world_size=1):
+    if not torch.cuda.is_available():
+      raise _lib.ImmbError('IMMEngine needs a CUDA device; there is no CPU fallback')
+    _lib.lib()
+    self.cfg = config
+    self.B, self.R = int(batch), int(image_size)
+    self.dev = torch.device(device)
+    self.precision, self.engine = precision, engine
+    self.world_size = world_size
+    self.K = int(config.n_maps)
+    if config.gauss_mode != 'rot':
+      raise _lib.ImmbError("only gauss_mode 'rot' (used by every shipped config) is built; got %r" % config.gauss_mode)
+    if config.reconstruction_loss != 'perceptual' or not config.perceptual.l2:
+      raise _lib.ImmbError('only reconstruction_loss=perceptual with perceptual.l2=True is built')
+    if int(config.renderer_stride) != 2 or int(config.min_res) != 16:
+      raise _lib.ImmbError('renderer_stride 2 / min_res 16 expected')
+    self.comp = list(config.perceptual.comp)
+    self.use_mask = bool(config.loss_mask)
+    self.n_extra = len(self.comp) if getattr(config, 'channels_bug_fix', False) else 0
+    self.n_out = 3 + self.n_extra
+    self.nf, self.nfr = int(config.n_filters), int(config.n_filters_render)
+    self.inv_std = 1.0 / float(config.gauss_std)
+    self.global_step = -1.0           # scripts/train.py:87-89,192: initialised to --reset-global-step (default -1)
+    self.adam_t = 0
+    self._build_layers()
+    self._alloc_params()
+    self._alloc_buffers()
+    self.vgg_loaded = False
+
+  # ------------------------------------------------------------------------------------------------
+  # construction
+  # ------------------------------------------------------------------------------------------------
+  def _build_layers(self):
+    B, R, K = self.B, self.R, self.K
+    self.enc_feat = 8 * self.nf
+    self.Cj = round_up(self.enc_feat + K, 32)          # channel stride of the renderer's concat input
+    self.layers = OrderedDict()                        # key = TF scope prefix of the conv
+
+    def add(prefix, name, k, stride, cin, cout, H, W, xcs, bn, relu, up2x, needs_dgrad):
+      L = ConvLayer(self, prefix, name, k, stride, cin, cout, B, H, W, xcs, bn, relu, up2x, needs_dgrad)
+      self.layers['%s/%s' % (prefix, name)] = L
+      return L
+
+    self.enc_layers = {}
+    for enc in ('image_encoder', 'pose_encoder'):
+      prefix = 'model/%s/encoder' % enc
+      cin, size, lst = 3, R, []
+      for i, (name, k, stride, cout) in enumerate(encoder_spec(self.nf)):
+        L = add(prefix, name, k, stride, cin, cout, size, size, cin, True, True, False, i > 0)
+        lst.append(L)
+        cin, size = cout, L.Ho
+      self.enc_layers[enc] = lst
+    self.enc_out_size = size                           # 16 for R=128, 32 for R=256
+    self.pose_conv = add('model/pose_encoder', 'conv_1', 1, 1, self.enc_feat, K, size, size, self.enc_feat,
+                         False, False, False, True)
+    self.ren_layers = []
+    cin, size, xcs = self.enc_feat + K, 16, self.Cj
+    for name, cout, bn, relu, up in renderer_spec(self.nfr, R, self.n_out):
+      L = add('model/renderer', name, 3, 1, cin, cout, size, size, xcs, bn, relu, up, True)
+      self.ren_layers.append(L)
+      cin, xcs = cout, cout
+      if up:
+        size *= 2
+    # frozen VGG16 up to the deepest level the loss reads (conv3_3 / conv4_3 feed pools)
+    needed = [c for c in self.comp if c != 'input']
+    last = max((i for i, it in enumerate(VGG_ORDER) if not isinstance(it, str) and it[0] in needed), default=-1)
+    self.vgg_seq = []
+    cin, size = 1, R
+    for it in VGG_ORDER[:last + 1]:
+      if isinstance(it, str):
+        self.vgg_seq.append(('pool', it, cin, size))
+        size //= 2
+      else:
+        name, cout = it
+        L = ConvLayer(self, 'SelfSupReconstructionLoss/vgg16', name, 3, 1, cin, cout, 2 * B, size, size, cin,
+                      False, True, False, True, trainable=False, epilogue=_lib.EPI_BIAS_RELU)
+        self.vgg_seq.append(('conv', L, cin, size))
+        cin = cout
+
+  def _alloc_params(self):
+    dev = self.dev
+    names, shapes, wds = [], [], []
+
+    def reg(name, shape, wd=0.0):
+      names.append(name)
+      shapes.append(tuple(shape))
+      wds.append(wd)
+
+    for key, L in self.layers.items():
+      reg('%s/%s/w' % (key, L.name), (L.k, L.k, L.cin, L.cout), WD)     # nn_utils.py:44-46 (w only)
+      reg('%s/%s/b' % (key, L.name), (L.cout,))
+      if L.bn:
+        reg('%s/batch_normalization/gamma' % key, (L.cout,))
+        reg('%s/batch_normalization/beta' % key, (L.cout,))
+    self.param_names, self.param_shapes = names, shapes
+    offs, off = [], 0
+    for s in shapes:
+      offs.append(off)
+      off += round_up(int(np.prod(s)), 4)
+    self.param_offsets, self.n_flat = offs, off
+    z = lambda: torch.zeros(off, dtype=torch.float32, device=dev)
+    self.flat_p, self.flat_g, self.flat_m, self.flat_v = z(), z(), z(), z()
+    view = lambda flat: OrderedDict((n, flat[o:o + int(np.prod(s))].view(s)) for n, o, s in zip(names, offs, shapes))
+    self.params, self.grads = view(self.flat_p), view(self.flat_g)
+    self.adam_m, self.adam_v = view(self.flat_m), view(self.flat_v)
+    # optimiser chunk table
+    ct, co, cl = [], [], []
+    for t, (o, s) in enumerate(zip(offs, shapes)):
+      n = int(np.prod(s))
+      for c0 in range(0, n, ADAM_CHUNK):
+        ct.append(t)
+        co.append(o + c0)
+        cl.append(min(ADAM_CHUNK, n - c0))
+    self.chunk_tensor = torch.tensor(ct, dtype=torch.int32, device=dev)
+    self.chunk_off = torch.tensor(co, dtype=torch.int64, device=dev)
+    self.chunk_len = torch.tensor(cl, dtype=torch.int32, device=dev)
+    self.n_chunks = len(ct)
+    self.tensor_wd = torch.tensor(wds, dtype=torch.float32, device=dev)
+    self.n_tensors = len(names)
+    self.sq = torch.zeros(2 * self.n_tensors, dtype=torch.float64, device=dev)     # [sq ; wsq]
+    # non-trainable state: BN moving stats + loss normalisers
+    bnames, bshapes = [], []
+    for key, L in self.layers.items():
+      if L.bn:
+        bnames += ['%s/batch_normalization/moving_mean' % key, '%s/batch_normalization/moving_variance' % key]
+        bshapes += [(L.cout,), (L.cout,)]
+    boffs, off = [], 0
+    for s in bshapes:
+      boffs.append(off)
+      off += s[0]
+    self.flat_bn = torch.zeros(off, dtype=torch.float32, device=dev)
+    self.buffers = OrderedDict((n, self.flat_bn[o:o + s[0]]) for n, o, s in zip(bnames, boffs, bshapes))
+    for n in bnames:
+      if n.endswith('moving_variance'):
+        self.buffers[n].fill_(1.0)
+    self.agg = torch.tensor(PERCEPTUAL_WS[:len(self.comp)], dtype=torch.float32, device=dev)
+    for k, nm in enumerate(self.comp):
+      self.buffers['SelfSupReconstructionLoss/%s_agg' % nm] = self.agg[k:k + 1].view(())
+    # per-layer handles
+    for key, L in self.layers.items():
+      L.w, L.b = self.params['%s/%s/w' % (key, L.name)], self.params['%s/%s/b' % (key, L.name)]
+      L.dw, L.db = self.grads['%s/%s/w' % (key, L.name)], self.grads['%s/%s/b' % (key, L.name)]
+      if L.bn:
+        pre = '%s/batch_normalization/' % key
+        L.gamma, L.beta = self.params[pre + 'gamma'], self.params[pre + 'beta']
+        L.dgamma, L.dbeta = self.grads[pre + 'gamma'], self.grads[pre + 'beta']
+        L.mm, L.mv = self.buffers[pre + 'moving_mean'], self.buffers[pre + 'moving_variance']
+
+  def _alloc_weight_planes(self, L):
+    dev, taps = self.dev, L.k * L.k
+    e = torch.empty
+    L.wp = Planes(e((taps, L.cout, L.cin_pad), dtype=torch.float32, device=dev),
+                  e((taps, L.cout, L.cin_pad), dtype=torch.float32, device=dev))
+    L.wh = Planes(e((taps, L.cin_pad, L.cout), dtype=torch.float32, device=dev),
+                  e((taps, L.cin_pad, L.cout), dtype=torch.float32, device=dev))
+
+  def _alloc_buffers(self):
+    dev, B, R, K = self.dev, self.B, self.R, self.K
+    f32 = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+    f64z = lambda n: torch.zeros(n, dtype=torch.float64, device=dev)
+    self.joint = Planes.alloc((B, 16, 16, self.Cj), dev, zero=True)     # pad channels stay zero
+    ws_bytes = 0
+    for key, L in self.layers.items():
+      self._alloc_weight_planes(L)
+      L.y = f32(B, L.Ho, L.Wo, L.cout)
+      L.dy = Planes.alloc((B, L.Ho, L.Wo, L.cout), dev)
+      L.dbias_acc = f64z(L.cout)
+      if L.bn:
+        L.sums, L.bsums = f64z(2 * L.cout), f64z(2 * L.cout)
+        L.scale, L.shift, L.mean, L.invstd = f32(L.cout), f32(L.cout), f32(L.cout), f32(L.cout)
+        L.g_low = f32(B, L.Ho, L.Wo, L.cout) if L.up2x else None
+      if L.needs_dgrad:
+        L.dx = torch.zeros((B, L.H, L.W, L.xcs), dtype=torch.float32, device=dev)
+      ws_bytes = max(ws_bytes, int(call('immb_conv2d_wgrad_workspace', L.desc())))
+    # activation planes: output of each trainable block
+    for enc in ('image_encoder', 'pose_encoder'):
+      for i, L in enumerate(self.enc_layers[enc]):
+        last = i == len(self.enc_layers[enc]) - 1
+        if enc == 'image_encoder' and last and L.Ho == 16:
+          L.out, L.ocs = self.joint, self.Cj               # written straight into the concat buffer
+        else:
+          L.out, L.ocs = Planes.alloc((B, L.Ho, L.Wo, L.cout), dev), L.cout
+    if self.enc_out_size != 16:
+      self.g_enc_resized = f32(B, self.enc_out_size, self.enc_out_size, self.enc_feat)
+    for L in self.ren_layers:
+      if L.bn:
+        s = 2 if L.up2x else 1
+        L.out, L.ocs = Planes.alloc((B, L.Ho * s, L.Wo * s, L.cout), dev), L.cout
+    S = self.enc_out_size
+    self.mu, self.py, self.px = f32(B, K, 2), f32(B, S, K), f32(B, S, K)
+    self.g_heat = f32(B, S, S, K)
+    # perceptual tower
+    self.vgg_in = Planes.alloc((2 * B, R, R, 1), dev)
+    self.vgg_act = OrderedDict()
+    for kind, item, cin, size in self.vgg_seq:
+      if kind == 'conv':
+        L = item
+        self._alloc_weight_planes(L)
+        L.w = f32(3, 3, L.cin, L.cout)
+        L.b = f32(L.cout)
+        L.out = Planes.alloc((2 * B, size, size, L.cout), dev)
+        L.dy = Planes.alloc((B, size, size, L.cout), dev)        # pred half only
+        L.dx = f32(B, size, size, L.cin)
+        self.vgg_act[L.name] = L.out
+        ws_bytes = max(ws_bytes, 0)
+      else:
+        self.vgg_act[item] = Planes.alloc((2 * B, size // 2, size // 2, cin), dev)
+    self.g_pool = {item: f32(B, size, size, cin) for kind, item, cin, size in self.vgg_seq if kind == 'pool'}
+    self.level_acc = f64z(len(self.comp))
+    counts = []
+    for nm in self.comp:
+      if nm == 'input':
+        counts.append(float(B * R * R * 3))
+      else:
+        P = self.vgg_act[nm].hi
+        counts.append(float(B * P.shape[1] * P.shape[2] * P.shape[3]))
+    self.level_counts = torch.tensor(counts, dtype=torch.float64, device=dev)
+    self.levels = f32(len(self.comp))
+    self.coef = f32(len(self.comp))
+    self.rec_loss, self.weights_loss, self.total_loss = f32(1), f32(1), f32(1)
+    self.pred_dy = Planes.alloc((B, R, R, self.n_out), dev)
+    self.workspace = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+
+  # ------------------------------------------------------------------------------------------------
+  # parameters
+  # ------------------------------------------------------------------------------------------------
+  def init_parameters(self, seed=0):
+    """Reference initialisers: w ~ truncated_normal(std .01) (nn_utils.py:47), b = 0 (:106), gamma 1,
+    beta 0, moving_mean 0, moving_var 1 (tf.layers defaults), *_agg = ws (imm_model.py:131)."""
+    gen = torch.Generator().manual_seed(seed)
+    for key, L in self.layers.items():
+      w = torch.empty(L.w.shape, dtype=torch.float32)
+      torch.nn.init.trunc_normal_(w, mean=0.0, std=INIT_STD, a=-2 * INIT_STD, b=2 * INIT_STD, generator=gen)
+      L.w.copy_(w)
+      L.b.zero_()
+      if L.bn:
+        L.gamma.fill_(1.0)
+        L.beta.zero_()
+        L.mm.zero_()
+        L.mv.fill_(1.0)
+    self.agg.copy_(torch.tensor(PERCEPTUAL_WS[:len(self.comp)]))
+    self.flat_m.zero_()
+    self.flat_v.zero_()
+    self.adam_t = 0
+    self.global_step = -1.0
+    self.repack_weights()
+
+  def load_state(self, params=None, buffers=None, adam_m=None, adam_v=None):
+    """Copies tensors keyed by TF variable name (HWIO weights) into the device buffers."""
+    for src, dst in ((params, self.params), (buffers, self.buffers), (adam_m, self.adam_m), (adam_v, self.adam_v)):
+      if src is None:
+        continue
+      for k, v in src.items():
+        if k in dst:
+          dst[k].copy_(torch.as_tensor(v, dtype=torch.float32).reshape(dst[k].shape))
+    self.repack_weights()
+
+  def load_vgg_caffe_dict(self, data):
+    """vgg16.py:17-47,74-92 with pre_adjust_batch_norm=True (build_vgg16.py:30): OIHW->HWIO, BGR flip only for
+    Cin==3, BN folding W /= sigma, b = (b-mu)/sigma, sigma = sqrt(1e-5 + bn['1']/bn['2']), mu = bn['0']/bn['2']."""
+    self.vgg_params = OrderedDict()
+    for kind, item, cin, size in self.vgg_seq:
+      if kind != 'conv':
+        continue
+      L = item
+      W = np.array(data[L.name]['0'], dtype=np.float32).copy().transpose(2, 3, 1, 0)
+      if L.name == 'conv1_1' and W.shape[2] == 3:
+        W = W[:, :, ::-1]
+      bias = np.array(data[L.name]['1'], dtype=np.float32).copy()
+      bn_name = 'batch_' + L.name
+      if bn_name in data:
+        bn = data[bn_name]
+        sigma = np.sqrt(1e-5 + np.asarray(bn['1']) / np.asarray(bn['2']))
+        mu = np.asarray(bn['0']) / np.asarray(bn['2'])
+        W = W / sigma
+        bias = (bias - mu) / sigma
+      assert tuple(W.shape) == (3, 3, L.cin, L.cout), 'Incorrect weights shape for %s' % L.name   # vgg16.py:171
+      L.w.copy_(torch.from_numpy(np.ascontiguousarray(W, dtype=np.float32)))
+      L.b.copy_(torch.from_numpy(np.ascontiguousarray(bias, dtype=np.float32)))
+      self.vgg_params['SelfSupReconstructionLoss/vgg16/%s/weights' % L.name] = L.w
+      self.vgg_params['SelfSupReconstructionLoss/vgg16/%s/biases' % L.name] = L.b
+      self._pack(L)
+    self.vgg_loaded = True
+
+  def _pack(self, L):
+    call('immb_pack_weights', L.w, L.k, L.k, L.cin, L.cout, L.cin_pad, L.wp.hi, L.wp.lo, L.wh.hi, L.wh.lo,
+         _lib.stream_ptr())
+
+  def repack_weights(self):
+    for L in self.layers.values():
+      self._pack(L)
+
+  # ------------------------------------------------------------------------------------------------
+  # forward
+  # ------------------------------------------------------------------------------------------------
+  def _conv_fwd(self, L, X, y_hi, y_lo=None, N=None):
+    call('immb_conv2d_fwd', L.desc(N), X.hi, X.lo, L.w, L.wp.hi, L.wp.lo, L.b, y_hi, y_lo, _lib.stream_ptr())
+
+  def _block_fwd(self, L, X, training):
+    """conv -> bias -> [BN] -> [ReLU] -> [x2 legacy bilinear]  (nn_utils.py:151-210, imm_model.py:175)."""
+    st = _lib.stream_ptr()
+    L.x = X
+    self._conv_fwd(L, X, L.y)
+    if not L.bn:
+      return None
+    npix = L.N * L.Ho * L.Wo
+    if training:
+      L.sums.zero_()
+      call('immb_bn_stats', L.y, npix, L.cout, L.cout, L.sums, st)
+    call('immb_bn_finalize', L.sums, npix, L.cout, L.gamma, L.beta, L.mm, L.mv, 1 if training else 0,
+         L.scale, L.shift, L.mean, L.invstd, st)
+    call('immb_bn_apply', L.y, L.N, L.Ho, L.Wo, L.cout, L.cout, L.scale, L.shift, 1 if L.relu else 0,
+         1 if L.up2x else 0, L.out.hi, L.out.lo, L.ocs, st)
+    return L.out
+
+  def forward(self, image, future_image, mask=None, training=True, build_loss=True):
+    """IMMModel.build (imm_model.py:413-490).  image / future_image [B,R,R,3] fp32 in [0,255]; mask [B,R,R,1]."""
+    st = _lib.stream_ptr()
+    B, R, K = self.B, self.R, self.K
+    assert tuple(image.shape) == (B, R, R, 3) and tuple(future_image.shape) == (B, R, R, 3)
+    self.image, self.future_image = image, future_image
+    self.mask = mask if (self.use_mask and mask is not None) else None
+    if self.use_mask and mask is None and build_loss:
+      raise RuntimeError('No loss mask recieved but is required.')      # imm_model.py:363-367
+    self.training = training
+    # image encoder (imm_model.py:220-230) and pose encoder (:233-248)
+    for enc, inp in (('image_encoder', image), ('pose_encoder', future_image)):
+      X = Planes(inp, None)
+      for L in self.enc_layers[enc]:
+        X = self._block_fwd(L, X, training)
+    img_last, pose_last = self.enc_layers['image_encoder'][-1], self.enc_layers['pose_encoder'][-1]
+    if self.enc_out_size != 16:     # imm_model.py:324-335: resize_bilinear(align_corners=True) to the render size
+      S = self.enc_out_size
+      call('immb_resize_ac_fwd', img_last.out.hi, img_last.out.lo, img_last.cout, B, S, S, self.enc_feat, 16, 16,
+           self.joint.hi, self.joint.lo, self.Cj, st)
+    # heatmaps -> (mu_y, mu_x) -> Gaussian maps into the concat buffer (imm_model.py:247-274,341-344)
+    self._block_fwd(self.pose_conv, pose_last.out, training)
+    S = self.enc_out_size
+    call('immb_softargmax_gauss_fwd', self.pose_conv.y, B, S, K, K, self.inv_std, self.mu, self.py, self.px, 16,
+         self.joint.hi, self.joint.lo, self.Cj, self.enc_feat, st)
+    # renderer (imm_model.py:154-179)
+    X = self.joint
+    for L in self.ren_layers:
+      X = self._block_fwd(L, X, training)
+    self.pred = self.ren_layers[-1].y           # [B,R,R,n_out]; first 3 channels = future_im_pred (:348-355)
+    if build_loss:
+      self._loss_fwd(training)
+    return self.pred
+
+  def _loss_fwd(self, training):
+    """_colorization_reconstruction_loss (imm_model.py:111-151) + build_vgg16 (build_vgg16.py:14-35)."""
+    if not self.vgg_loaded:
+      raise _lib.ImmbError('VGG16 weights not loaded (load_vgg_caffe_dict)')
+    st = _lib.stream_ptr()
+    B, R = self.B, self.R
+    call('immb_vgg_prologue', self.future_image, self.pred, self.n_out, B, R, self.vgg_in.hi, self.vgg_in.lo, st)
+    X = self.vgg_in
+    for kind, item, cin, size in self.vgg_seq:
+      if kind == 'conv':
+        item.x = X
+        self._conv_fwd(item, X, item.out.hi, item.out.lo)
+        X = item.out
+      else:
+        O = self.vgg_act[item]
+        call('immb_maxpool2x2_fwd', X.hi, X.lo, 2 * B, size, size, cin, O.hi, O.lo, st)
+        X = O
+    self.level_acc.zero_()
+    for k, nm in enumerate(self.comp):
+      if nm == 'input':
+        call('immb_perceptual_level_sum', self.future_image, None, 3, self.pred, None, self.n_out, B, R, R, 3,
+             self.mask, R, self.level_acc[k:], st)
+      else:
+        P = self.vgg_act[nm]
+        h, w, C = P.hi.shape[1], P.hi.shape[2], P.hi.shape[3]
+        g, p = P.half(0, B), P.half(1, B)
+        call('immb_perceptual_level_sum', g.hi, g.lo, C, p.hi, p.lo, C, B, h, w, C, self.mask, R,
+             self.level_acc[k:], st)
+    call('immb_perceptual_finalize', self.level_acc, self.level_counts, len(self.comp), self.agg,
+         1 if training else 0, self.levels, self.rec_loss, self.coef, st)
+
+  def loss_value(self):
+    """total = reconstruction + sum_w 1e-5*0.5*||w||^2 (imm_model.py:395-400).  Device tensor [1]."""
+    st = _lib.stream_ptr()
+    self.sq.zero_()
+    call('immb_adam_norms', self.flat_p, self.flat_g, self.n_flat, self.chunk_tensor, self.chunk_off,
+         self.chunk_len, self.n_chunks, self.tensor_wd, 1.0, self.sq, self.sq[self.n_tensors:], st)
+    call('immb_total_loss', self.rec_loss, self.sq[self.n_tensors:], self.tensor_wd, self.n_tensors,
+         self.weights_loss, self.total_loss, st)
+    return self.total_loss
+
+  # ------------------------------------------------------------------------------------------------
+  # backward
+  # ------------------------------------------------------------------------------------------------
+  def _block_bwd(self, L, g, gcs):
+    """g: gradient wrt the block output (after the optional x2 upsample), channel stride gcs.
+    Returns the gradient wrt the block input [N,H,W,xcs] or None."""
+    st = _lib.stream_ptr()
+    npix = L.N * L.Ho * L.Wo
+    if L.bn:
+      if L.up2x:
+        call('immb_upsample2x_bwd', g, L.N, L.Ho, L.Wo, L.cout, gcs, L.g_low, st)
+        g, gcs = L.g_low, L.cout
+      L.bsums.zero_()
+      L.dbias_acc.zero_()
+      relu = 1 if L.relu else 0
+      call('immb_bn_bwd_reduce', g, gcs, L.y, L.cout, npix, L.cout, L.scale, L.shift, L.mean, L.invstd, relu,
+           L.bsums, st)
+      call('immb_bn_bwd_apply', g, gcs, L.y, L.cout, npix, L.cout, L.scale, L.shift, L.mean, L.invstd, relu,
+           L.bsums, L.dy.hi, L.dy.lo, L.dgamma, L.dbeta, L.dbias_acc, st)
+      dy = L.dy
+    else:
+      dy = g if isinstance(g, Planes) else None
+      if dy is None:
+        assert gcs == L.cout
+        call('immb_split_planes', g, L.dy.hi, L.dy.lo, npix * L.cout, st)
+        dy = L.dy
+      L.dbias_acc.zero_()
+      call('immb_bias_grad', dy.hi, dy.lo, L.cout, npix, L.cout, L.dbias_acc, st)
+    call('immb_cast_d2f', L.dbias_acc, L.db, L.cout, st)
+    d = L.desc()
+    call('immb_conv2d_wgrad', d, L.x.hi, L.x.lo, dy.hi, dy.lo, L.dw, self.workspace, self.workspace.numel(), st)
+    if L.needs_dgrad:
+      call('immb_conv2d_dgrad', d, dy.hi, dy.lo, L.w, L.wh.hi, L.wh.lo, L.dx, st)
+      return L.dx
+    return None
+
+  def _loss_bwd(self):
+    """Backward of the perceptual loss down to the renderer output; returns dy planes [B,R,R,n_out]."""
+    st = _lib.stream_ptr()
+    B, R = self.B, self.R
+    level_of = {nm: k for k, nm in enumerate(self.comp)}
+    g = None                       # gradient wrt the current activation (pred half), fp32 [B,h,w,C]
+    for kind, item, cin, size in reversed(self.vgg_seq):
+      if kind == 'conv':
+        L = item
+        P = L.out
+        coef = self.coef[level_of[L.name]:] if L.name in level_of else None
+        if g is None and coef is None:
+          continue                  # above the deepest level used by the loss
+        fg, fp = P.half(0, B), P.half(1, B)
+        call('immb_vgg_bwd_combine', g, fg.hi, fg.lo, fp.hi, fp.lo, B, size, size, L.cout, self.mask, R, coef,
+             L.dy.hi, L.dy.lo, st)
+        call('immb_conv2d_dgrad', L.desc(B), L.dy.hi, L.dy.lo, L.w, L.wh.hi, L.wh.lo, L.dx, st)
+        g = L.dx
+      else:
+        if g is None:
+          continue
+        xin = None
+        # input of the pool = previous conv's activation (pred half)
+        idx = [i for i, v in enumerate(self.vgg_seq) if v[1] == item][0]
+        prev = self.vgg_seq[idx - 1][1]
+        xin = prev.out.half(1, B)
+        call('immb_maxpool2x2_bwd', g, xin.hi, xin.lo, B, size, size, cin, self.g_pool[item], st)
+        g = self.g_pool[item]
+    coef_in = self.coef[level_of['input']:] if 'input' in level_of else None
+    if coef_in is None:
+      raise _lib.ImmbError("perceptual.comp without 'input' is not built")
+    call('immb_pred_grad', self.future_image, self.pred, self.n_out, self.mask, coef_in, g, B, R,
+         self.pred_dy.hi, self.pred_dy.lo, st)
+    return self.pred_dy
+
+  def backward(self):
+    """Gradients of (reconstruction loss) wrt every trainable tensor; the L2 term is added in the optimiser."""
+    st = _lib.stream_ptr()
+    B, K = self.B, self.K
+    g = self._loss_bwd()
+    gcs = self.n_out
+    for L in reversed(self.ren_layers):
+      g = self._block_bwd(L, g, gcs)
+      gcs = L.xcs
+    dJ = g                                             # [B,16,16,Cj]
+    # pose branch: Gaussian maps -> mu -> softmax marginals -> heatmaps (imm_model.py:252-274)
+    S = self.enc_out_size
+    call('immb_softargmax_gauss_bwd', dJ, self.Cj, self.enc_feat, self.mu, self.py, self.px, B, S, K, 16,
+         self.inv_std, self.g_heat, K, st)
+    gp = self._block_bwd(self.pose_conv, self.g_heat, K)
+    gcs_p = self.enc_feat
+    for L in reversed(self.enc_layers['pose_encoder']):
+      gp = self._block_bwd(L, gp, gcs_p)
+      gcs_p = L.xcs
+    # image branch
+    gi, gcs_i = dJ, self.Cj
+    if self.enc_out_size != 16:
+      call('immb_resize_ac_bwd', dJ, self.Cj, B, S, S, self.enc_feat, 16, 16, self.g_enc_resized, st)
+      gi, gcs_i = self.g_enc_resized, self.enc_feat
+    for L in reversed(self.enc_layers['image_encoder']):
+      gi = self._block_bwd(L, gi, gcs_i)
+      gcs_i = L.xcs
+
+  # ------------------------------------------------------------------------------------------------
+  # optimiser  (cnn_train_multi.py:93-98,232-241; scripts/train.py:92-98)
+  # ------------------------------------------------------------------------------------------------
+  def learning_rate(self, start_val=1e-3, step=100000, decay=0.95, lr_multiple=1.0):
+    return lr_multiple * start_val * decay ** math.floor(self.global_step / float(step))
+
+  def optimizer_step(self, clip_value=1.0, lr=None, beta1=0.9, beta2=0.999, eps=1e-8, allreduce=None):
+    """mean over replicas (one all-reduce on the flat gradient buffer) -> +wd*w -> per-tensor clip_by_norm
+    -> TF Adam -> repack the tensor-core weight planes.  Also produces the total loss value."""
+    st = _lib.stream_ptr()
+    if allreduce is not None:
+      allreduce(self.flat_g)
+    gscale = 1.0 / float(self.world_size)
+    if lr is None:
+      lr = self.learning_rate()
+    self.adam_t += 1
+    lr_t = lr * math.sqrt(1.0 - beta2 ** self.adam_t) / (1.0 - beta1 ** self.adam_t)
+    self.sq.zero_()
+    nt = self.n_tensors
+    call('immb_adam_norms', self.flat_p, self.flat_g, self.n_flat, self.chunk_tensor, self.chunk_off,
+         self.chunk_len, self.n_chunks, self.tensor_wd, gscale, self.sq, self.sq[nt:], st)
+    call('immb_total_loss', self.rec_loss, self.sq[nt:], self.tensor_wd, nt, self.weights_loss, self.total_loss, st)
+    call('immb_adam_apply', self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.n_flat, self.chunk_tensor,
+         self.chunk_off, self.chunk_len, self.n_chunks, self.tensor_wd, gscale, self.sq,
+         float(clip_value) if clip_value is not None else 0.0, lr_t, beta1, beta2, eps, st)
+    self.repack_weights()
+    self.global_step += 1.0
+    return lr
+
+  def train_step(self, image, future_image, mask=None, clip_value=1.0, lr_multiple=1.0, allreduce=None):
+    """One iteration of train_loop's hot loop (cnn_train_multi.py:445-460): fwd + loss + bwd + update."""
+    self.forward(image, future_image, mask, training=True, build_loss=True)
+    self.backward()
+    self.optimizer_step(clip_value, lr=self.learning_rate(lr_multiple=lr_multiple), allreduce=allreduce)
+    return self.total_loss
+
+  # ------------------------------------------------------------------------------------------------
+  # introspection
+  # ------------------------------------------------------------------------------------------------
+  def engine_table(self):
+    out = OrderedDict()
+    for key, L in self.layers.items():
+      out[key] = L.engines()
+    for kind, item, cin, size in self.vgg_seq:
+      if kind == 'conv':
+        out['vgg16/' + item.name] = item.engines()
+    return out
+
+  def gaussian_maps(self, mu, size):
+    """get_gaussian_maps(mu, [size,size], inv_std, 'rot') (imm_model.py:34-78) -> [B,size,size,K]."""
+    B, K = mu.shape[0], mu.shape[1]
+    out = torch.empty((B, size, size, K), dtype=torch.float32, device=self.dev)
+    call('immb_gaussian_maps', mu.contiguous(), B, K, size, self.inv_std, out, _lib.stream_ptr())
+    return out

@@ -1,0 +1,206 @@
+/*
+ * imm_b200.h -- C ABI of libimm_b200.so: the sm_100a kernels of the IMM training hot path.
+ *
+ * The reference (tomasjakab/imm) has NO FFI/plugin interface: its hot path is a Python class
+ * (imm/models/imm_model.py:95 IMMModel) whose arithmetic is executed by TensorFlow-1.10 ops.
+ * Each entry point below therefore replaces one TF op call site of the reference; the call site is
+ * cited as file:line (relative to /root/reference) next to the function.  INTEGRATION.md shows the
+ * ctypes binding.
+ *
+ * Conventions
+ *  - plain C, no torch types: raw device pointers + sizes + a cudaStream_t passed as void*.
+ *  - tensors are NHWC fp32 with an explicit channel stride ("cstride", in elements) so that several
+ *    producers can write into one concat buffer.
+ *  - "split" tensors are a pair of fp32 planes (hi, lo) with hi = rna_tf32(v), lo = rna_tf32(v - hi).
+ *    They are the operands of the 3xTF32 tensor-core convolutions.  lo may be NULL (single-pass TF32 /
+ *    plain fp32 consumers use hi only, or hi+lo when lo is given).
+ *  - every function only ENQUEUES work on the given stream; no allocation, no synchronisation, no
+ *    host<->device copies, no global state except the thread-local last-error string.
+ *  - return value: 0 on success, negative immb_status otherwise; never throws, never exits.
+ *    Asynchronous CUDA errors surface at the caller's next synchronisation.
+ */
+#ifndef IMM_B200_H_
+#define IMM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IMMB_VERSION 100
+
+typedef enum {
+  IMMB_OK = 0,
+  IMMB_ERR_INVALID = -1,      /* bad argument / unsupported shape */
+  IMMB_ERR_CUDA = -2,         /* a CUDA runtime/driver call failed at enqueue time */
+  IMMB_ERR_WORKSPACE = -3,    /* caller-provided workspace too small */
+  IMMB_ERR_UNSUPPORTED = -4   /* engine cannot run this shape (e.g. forced tensor-core engine) */
+} immb_status;
+
+typedef enum {
+  IMMB_ENGINE_AUTO = 0,       /* tcgen05 engine when the shape is eligible, else the SIMT engine */
+  IMMB_ENGINE_SIMT = 1,       /* fp32 CUDA-core implicit GEMM (odd shapes: Cin=3/1, Cout=9/K; cross-check) */
+  IMMB_ENGINE_TC = 2          /* tcgen05 + TMA implicit GEMM; fails with IMMB_ERR_UNSUPPORTED if not eligible */
+} immb_engine;
+
+typedef enum {
+  IMMB_PREC_TF32X3 = 0,       /* error-compensated: hi*hi + hi*lo + lo*hi, fp32 accumulate (parity grade) */
+  IMMB_PREC_TF32 = 1          /* single pass on the hi planes (does NOT meet the 1e-3 parity bar) */
+} immb_precision;
+
+typedef enum {
+  IMMB_EPI_BIAS = 0,          /* y = conv + b              (trainable stack: nn_utils.py:100,108) */
+  IMMB_EPI_BIAS_RELU = 1      /* y = relu(conv + b)        (VGG: selfsup/vgg16.py:182-230) */
+} immb_epilogue;
+
+/* One convolution.  tf.nn.conv2d(x, w, [1,s,s,1], 'SAME') semantics: NHWC x HWIO cross-correlation,
+ * TF SAME padding (pad_t/pad_l = the "before" pads; the remainder goes after). */
+typedef struct {
+  int32_t N, H, W, Cin;       /* input tensor (logical channels) */
+  int32_t Cout, kh, kw, stride;
+  int32_t Ho, Wo;             /* ceil(H/stride), ceil(W/stride) */
+  int32_t pad_t, pad_l;
+  int32_t x_cstride;          /* channel stride of the input tensor (>= Cin) */
+  int32_t y_cstride;          /* channel stride of the output tensor (>= Cout) */
+  int32_t cin_pad;            /* Cin rounded up to 32: K-extent of the packed weights (zero filled) */
+  int32_t epilogue;           /* immb_epilogue (fwd only) */
+  int32_t precision;          /* immb_precision */
+  int32_t engine;             /* immb_engine */
+} immb_conv_desc;
+
+int immb_version(void);
+const char* immb_last_error(void);
+/* which engine AUTO resolves to for this problem: returns IMMB_ENGINE_SIMT or IMMB_ENGINE_TC.
+ * op: 0 fwd, 1 dgrad, 2 wgrad */
+int immb_conv_engine_for(const immb_conv_desc* d, int op);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+int64_t immb_launch_count(void);
+
+/* ---- convolution: nn_utils.py:100 (tf.nn.conv2d) + :108 (bias_add); vgg16.py:182-230 -------------- */
+/* w      : master weights HWIO [kh,kw,Cin,Cout] (checkpoint layout, base_model.py:110)
+ * wp_*   : packed copy  [kh*kw][Cout][cin_pad]   (K-major B operand of the forward GEMM)
+ * wh_*   : split copy   [kh*kw][cin_pad][Cout]   (K-major B operand of the dgrad GEMM)
+ * y_lo   : NULL -> y_hi receives the full fp32 result; else the result is written as split planes. */
+int immb_conv2d_fwd(const immb_conv_desc* d, const float* x_hi, const float* x_lo, const float* w,
+                    const float* wp_hi, const float* wp_lo, const float* bias, float* y_hi, float* y_lo,
+                    void* stream);
+/* dx[N,H,W,x_cstride] = conv2d_backprop_input(dy[N,Ho,Wo,y_cstride], w)  (autodiff of nn_utils.py:100) */
+int immb_conv2d_dgrad(const immb_conv_desc* d, const float* dy_hi, const float* dy_lo, const float* w,
+                      const float* wh_hi, const float* wh_lo, float* dx, void* stream);
+/* dw[kh,kw,Cin,Cout] = conv2d_backprop_filter(x, dy).  workspace: split-K partials (query size first). */
+size_t immb_conv2d_wgrad_workspace(const immb_conv_desc* d);
+int immb_conv2d_wgrad(const immb_conv_desc* d, const float* x_hi, const float* x_lo, const float* dy_hi,
+                      const float* dy_lo, float* dw, void* workspace, size_t ws_bytes, void* stream);
+/* master HWIO -> wp_{hi,lo}, wh_{hi,lo} (either pair may be NULL) */
+int immb_pack_weights(const float* w, int kh, int kw, int Cin, int Cout, int cin_pad, float* wp_hi,
+                      float* wp_lo, float* wh_hi, float* wh_lo, void* stream);
+/* v -> (hi, lo) planes, contiguous n elements */
+int immb_split_planes(const float* v, float* hi, float* lo, int64_t n, void* stream);
+
+/* ---- batch norm: nn_utils.py:201 tf.layers.batch_normalization(training=..., fused=True) ---------- */
+/* sums[2*C] (double, zeroed by the caller): sum(y), sum(y^2) per channel over npix pixels */
+int immb_bn_stats(const float* y, int64_t npix, int C, int y_cstride, double* sums, void* stream);
+/* training!=0: batch mean / biased var from sums; moving_mean/var updated in place (momentum .99, Bessel);
+ * training==0: moving stats.  Outputs: scale = gamma*rsqrt(var+1e-3), shift = beta-mean*scale, mean, invstd. */
+int immb_bn_finalize(const double* sums, int64_t count, int C, const float* gamma, const float* beta,
+                     float* moving_mean, float* moving_var, int training, float* scale, float* shift,
+                     float* mean, float* invstd, void* stream);
+/* out = [relu](y*scale+shift), written as split planes; up2x!=0 additionally applies
+ * tf.image.resize_images(x, 2x) (imm_model.py:175; TF1 legacy bilinear) to the activated tensor, so the
+ * output is [N,2H,2W,C]. */
+int immb_bn_apply(const float* y, int N, int H, int W, int C, int y_cstride, const float* scale,
+                  const float* shift, int relu, int up2x, float* out_hi, float* out_lo, int out_cstride,
+                  void* stream);
+/* adjoint of the legacy x2 bilinear resize: g_up[N,2H,2W,C] -> g[N,H,W,C] */
+int immb_upsample2x_bwd(const float* g_up, int N, int H, int W, int C, int gup_cstride, float* g, void* stream);
+/* sums[2*C] (double, zeroed): sum(dz), sum(dz*xhat) with dz = g * (relu ? (y*scale+shift > 0) : 1) */
+int immb_bn_bwd_reduce(const float* g, int g_cstride, const float* y, int y_cstride, int64_t npix, int C,
+                       const float* scale, const float* shift, const float* mean, const float* invstd,
+                       int relu, double* sums, void* stream);
+/* dy = scale*(dz - mean(dz) - xhat*mean(dz*xhat)) as split planes; dgamma = sum(dz*xhat), dbeta = sum(dz),
+ * dbias = sum(dy) (double accumulators dbias_acc[C], zeroed by the caller; finalised by immb_cast_d2f) */
+int immb_bn_bwd_apply(const float* g, int g_cstride, const float* y, int y_cstride, int64_t npix, int C,
+                      const float* scale, const float* shift, const float* mean, const float* invstd,
+                      int relu, const double* sums, float* dy_hi, float* dy_lo, float* dgamma, float* dbeta,
+                      double* dbias_acc, void* stream);
+/* column sums: acc[C] (double, zeroed) += sum over pixels of g[:, c] */
+int immb_bias_grad(const float* g_hi, const float* g_lo, int g_cstride, int64_t npix, int C, double* acc,
+                   void* stream);
+int immb_cast_d2f(const double* src, float* dst, int64_t n, void* stream);
+
+/* ---- landmark bottleneck: imm_model.py:252-263 (get_coord) + :34-78 (get_gaussian_maps, 'rot') ---- */
+/* heat[B,S,S,K] -> mu[B,K,2] (y,x), py[B,S,K], px[B,S,K]; and the Sg x Sg Gaussian maps written as split
+ * planes into channels [c_off, c_off+K) of a [B,Sg,Sg,out_cstride] buffer (the renderer's concat input,
+ * imm_model.py:341-344).  maps_hi may be NULL (coordinates only). */
+int immb_softargmax_gauss_fwd(const float* heat, int B, int S, int K, int heat_cstride, float inv_std,
+                              float* mu, float* py, float* px, int Sg, float* maps_hi, float* maps_lo,
+                              int out_cstride, int c_off, void* stream);
+/* g_maps[B,Sg,Sg,g_cstride] (channels c_off..c_off+K) -> g_heat[B,S,S,K] */
+int immb_softargmax_gauss_bwd(const float* g_maps, int g_cstride, int c_off, const float* mu,
+                              const float* py, const float* px, int B, int S, int K, int Sg, float inv_std,
+                              float* g_heat, int gheat_cstride, void* stream);
+/* free function get_gaussian_maps(mu, [S,S], inv_std, mode='rot') -> maps[B,S,S,K] fp32 */
+int immb_gaussian_maps(const float* mu, int B, int K, int S, float inv_std, float* maps, void* stream);
+
+/* ---- perceptual tower glue: build_vgg16.py:22-26, ops.py:16-26, imm_model.py:111-151,408-410 ------ */
+/* vgg_in[2B,R,R,1] split planes: gray = mean_c(rgb)/255 - 114.451/255 for [gt ; pred[..., :3]] */
+int immb_vgg_prologue(const float* gt, const float* pred, int pred_cstride, int B, int R, float* out_hi,
+                      float* out_lo, void* stream);
+/* 2x2/2 max pool on split planes [N,H,W,C] -> [N,H/2,W/2,C] split planes */
+int immb_maxpool2x2_fwd(const float* x_hi, const float* x_lo, int N, int H, int W, int C, float* o_hi,
+                        float* o_lo, void* stream);
+/* g_in[N,H,W,C] from g_out[N,H/2,W/2,C]; first-max-wins tie rule of TF's CPU MaxPoolGrad */
+int immb_maxpool2x2_bwd(const float* g_out, const float* x_hi, const float* x_lo, int N, int H, int W,
+                        int C, float* g_in, void* stream);
+/* acc[0] (double, zeroed) += sum_{b,h,w,c} m[b, h*s, w*s] * (fg[b] - fp[b])^2 ; fg / fp are the gt / pred
+ * halves [B,h,w,C] of one feature level (separate pointers + channel strides; for the VGG levels fp is the
+ * second half of the same [2B,...] activation).  *_lo may be NULL.  mask[B,R,R,1] may be NULL.  s = R/h. */
+int immb_perceptual_level_sum(const float* fg_hi, const float* fg_lo, int fg_cstride, const float* fp_hi,
+                              const float* fp_lo, int fp_cstride, int B, int h, int w, int C,
+                              const float* mask, int R, double* acc, void* stream);
+/* Given the n_levels sums: s_k = acc_k / count_k; wl_k = a_k + 0.01 (s_k - a_k); L_k = s_k / wl_k;
+ * rec = 1000 sum L_k; coef_k = 1000 * 0.99 a_k / wl_k^2 * (-2 / count_k)  (gradient wrt f_pred is coef*m*d);
+ * training: a_k <- wl_k (base_model.py:39-50).  out: levels[n_levels], rec_loss[1], coef[n_levels]. */
+int immb_perceptual_finalize(const double* acc, const double* counts, int n_levels, float* agg, int training,
+                             float* levels, float* rec_loss, float* coef, void* stream);
+/* VGG backward glue for one activation a_k = relu(.) of the pred half:
+ *   g = (g_next ? g_next : 0) + (coef ? coef[0]*m*(fg - fp) : 0);  dy = g * (fp > 0) -> split planes
+ * fg / fp: gt / pred halves [B,h,w,C] (contiguous, split planes; fg may be NULL when coef is NULL);
+ * g_next [B,h,w,C] or NULL. */
+int immb_vgg_bwd_combine(const float* g_next, const float* fg_hi, const float* fg_lo, const float* fp_hi,
+                         const float* fp_lo, int B, int h, int w, int C, const float* mask, int R,
+                         const float* coef, float* dy_hi, float* dy_lo, void* stream);
+/* gradient wrt the renderer output [B,R,R,pred_cstride] (channels >=3 get 0) as split planes:
+ *   g_pred_c = coef_input * m * (gt_c - pred_c) + g_vggin / (3*255)   (g_vggin [B,R,R,1] may be NULL) */
+int immb_pred_grad(const float* gt, const float* pred, int pred_cstride, const float* mask,
+                   const float* coef_input, const float* g_vggin, int B, int R, float* g_hi, float* g_lo,
+                   void* stream);
+/* tf.image.resize_bilinear(align_corners=True) (imm_model.py:334) on split planes, and its adjoint */
+int immb_resize_ac_fwd(const float* x_hi, const float* x_lo, int x_cstride, int N, int H, int W, int C,
+                       int Ho, int Wo, float* o_hi, float* o_lo, int o_cstride, void* stream);
+int immb_resize_ac_bwd(const float* g_out, int g_cstride, int N, int H, int W, int C, int Ho, int Wo,
+                       float* g_in, void* stream);
+
+/* ---- optimiser: cnn_train_multi.py:93-98,232-241 + scripts/train.py:92-98 + nn_utils.py:44-46 ---- */
+/* Flat buffers of n floats hold every trainable tensor back to back.  The chunk table splits them into
+ * chunks: chunk_tensor[i] = tensor id, chunk_off[i] = start offset, chunk_len[i] <= 1024*? elements.
+ * Step 1 (norms): sq[t] (double, zeroed) += sum (g*gscale + wd_t*p)^2; wsq[t] += sum p^2.
+ * Step 2 (apply): g' = (g*gscale + wd_t*p) * clip/max(||.||, clip); TF Adam with lr_t (device scalar pair
+ * hyper[0]=lr_t, hyper[1]=clip); params updated in place. */
+int immb_adam_norms(const float* p, const float* g, int64_t n, const int32_t* chunk_tensor,
+                    const int64_t* chunk_off, const int32_t* chunk_len, int n_chunks, const float* tensor_wd,
+                    float gscale, double* sq, double* wsq, void* stream);
+int immb_adam_apply(float* p, const float* g, float* m, float* v, int64_t n, const int32_t* chunk_tensor,
+                    const int64_t* chunk_off, const int32_t* chunk_len, int n_chunks, const float* tensor_wd,
+                    float gscale, const double* sq, float clip, float lr_t, float beta1, float beta2,
+                    float eps, void* stream);
+/* total = rec_loss[0] + sum_t 0.5*wd_t*wsq[t]  (imm_model.py:395-400, base_model.py:33-37) */
+int immb_total_loss(const float* rec_loss, const double* wsq, const float* tensor_wd, int n_tensors,
+                    float* weights_loss, float* total, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMM_B200_H_ */

@@ -1,0 +1,329 @@
+"""Kernel-level parity tests: each C-ABI op against the oracle's restatement of the TF op it replaces
+(fp64 on CPU, autograd for the backward ops).  Edge cases: odd channel counts, channel-strided concat
+buffers, stride-2 asymmetric SAME padding, 1x1 / 7x7 kernels, tiny and ragged sizes."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from imm_b200 import _lib
+from imm_b200._lib import ConvDesc, call
+from oracle import imm_oracle as O
+from tests.gpu_util import rel_err
+
+pytestmark = pytest.mark.gpu
+ST = lambda: _lib.stream_ptr()
+
+
+def split(t):
+  """host-side TF32 split (round-to-nearest-even vs the kernel's rna only differ on exact ties)."""
+  hi = O.round_tf32(t)
+  lo = O.round_tf32(t - hi)
+  return hi, lo
+
+
+def conv_desc(N, H, W, Cin, Cout, k, stride, xcs=None, engine=_lib.ENGINE_AUTO, epilogue=0, precision=0):
+  d = ConvDesc()
+  d.N, d.H, d.W, d.Cin, d.Cout, d.kh, d.kw, d.stride = N, H, W, Cin, Cout, k, k, stride
+  d.Ho, d.Wo = -(-H // stride), -(-W // stride)
+  d.pad_t, d.pad_l = O.same_pad(H, k, stride)[0], O.same_pad(W, k, stride)[0]
+  d.x_cstride = xcs or Cin
+  d.y_cstride = Cout
+  d.cin_pad = (Cin + 31) // 32 * 32
+  d.epilogue, d.precision, d.engine = epilogue, precision, engine
+  return d
+
+
+CONV_CASES = [
+  # N, H, W, Cin, Cout, k, stride, xcs
+  (2, 16, 16, 3, 32, 7, 1, None),        # encoder conv_1 (7x7, Cin=3)
+  (1, 12, 20, 1, 64, 3, 1, None),        # vgg conv1_1 (Cin=1), non-square
+  (2, 16, 16, 32, 64, 3, 2, None),       # stride-2, asymmetric SAME pad
+  (1, 9, 7, 5, 6, 3, 2, None),           # odd sizes, stride 2 (pad 1/1), ragged tiles
+  (2, 16, 16, 266, 256, 3, 1, 288),      # renderer conv_1: concat input with padded channel stride
+  (2, 16, 16, 256, 10, 1, 1, None),      # pose 1x1 -> K heatmaps
+  (1, 32, 32, 32, 9, 3, 1, None),        # renderer last conv (Cout=9)
+  (3, 8, 8, 64, 64, 3, 1, None),
+]
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+def test_conv_fwd_dgrad_wgrad_simt(case):
+  N, H, W, Cin, Cout, k, stride, xcs = case
+  g = torch.Generator().manual_seed(hash(case) % 1000)
+  xcs_ = xcs or Cin
+  x = torch.randn(N, H, W, xcs_, generator=g)
+  x[..., Cin:] = 0
+  w = torch.randn(k, k, Cin, Cout, generator=g) * 0.1
+  b = torch.randn(Cout, generator=g)
+  d = conv_desc(N, H, W, Cin, Cout, k, stride, xcs, engine=_lib.ENGINE_SIMT)
+  xd = x.double()[..., :Cin].clone().requires_grad_(True)
+  wd = w.double().clone().requires_grad_(True)
+  y_ref = O.conv2d_same(xd, wd, b.double(), stride)
+  gy = torch.randn(y_ref.shape, generator=g)
+  y_ref.backward(gy.double())
+  xh, xl = split(x)
+  y = torch.empty(N, d.Ho, d.Wo, Cout, device='cuda')
+  call('immb_conv2d_fwd', d, xh.cuda(), xl.cuda(), w.cuda(), None, None, b.cuda(), y, None, ST())
+  assert rel_err(y, y_ref) < 1e-5
+  gh, gl = split(gy)
+  dx = torch.zeros(N, H, W, xcs_, device='cuda')
+  call('immb_conv2d_dgrad', d, gh.cuda(), gl.cuda(), w.cuda(), None, None, dx, ST())
+  assert rel_err(dx[..., :Cin], xd.grad) < 1e-5
+  dw = torch.empty(k, k, Cin, Cout, device='cuda')
+  ws = torch.empty(16, dtype=torch.uint8, device='cuda')
+  call('immb_conv2d_wgrad', d, xh.cuda(), xl.cuda(), gh.cuda(), gl.cuda(), dw, ws, 16, ST())
+  assert rel_err(dw, wd.grad) < 1e-5
+  # fused bias+ReLU epilogue writing split planes (VGG path)
+  d2 = conv_desc(N, H, W, Cin, Cout, k, stride, xcs, engine=_lib.ENGINE_SIMT, epilogue=_lib.EPI_BIAS_RELU)
+  yh, yl = torch.empty_like(y), torch.empty_like(y)
+  call('immb_conv2d_fwd', d2, xh.cuda(), xl.cuda(), w.cuda(), None, None, b.cuda(), yh, yl, ST())
+  assert rel_err(yh + yl, torch.relu(y_ref)) < 1e-5
+  assert float((yh.cpu() - O.round_tf32(yh.cpu())).abs().max()) == 0.0      # hi plane is exactly TF32
+
+
+def test_pack_weights_layouts():
+  w = torch.randn(3, 3, 5, 7)
+  wp_h, wp_l = torch.empty(9, 7, 32, device='cuda'), torch.empty(9, 7, 32, device='cuda')
+  wh_h, wh_l = torch.empty(9, 32, 7, device='cuda'), torch.empty(9, 32, 7, device='cuda')
+  call('immb_pack_weights', w.cuda(), 3, 3, 5, 7, 32, wp_h, wp_l, wh_h, wh_l, ST())
+  full = torch.zeros(9, 32, 7)
+  full[:, :5] = w.view(9, 5, 7)
+  assert rel_err(wh_h + wh_l, full) < 1e-6
+  assert rel_err(wp_h + wp_l, full.permute(0, 2, 1)) < 1e-6
+  assert float(wh_h[:, 5:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('shape', [(2, 8, 8, 32), (3, 5, 7, 48), (1, 16, 16, 256)])
+@pytest.mark.parametrize('up2x', [0, 1])
+def test_bn_train_fwd_bwd(shape, up2x):
+  N, H, W, C = shape
+  g = torch.Generator().manual_seed(N * 100 + C + up2x)
+  y = torch.randn(shape, generator=g) * 3 + 5
+  gamma = torch.rand(C, generator=g) + 0.5
+  beta = torch.randn(C, generator=g) * 0.1
+  mm0, mv0 = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
+  yd = y.double().requires_grad_(True)
+  gd, bd = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+  z, mm_ref, mv_ref = O.batch_norm(yd, gd, bd, mm0.double(), mv0.double(), True)
+  a = torch.relu(z)
+  if up2x:
+    a = O.resize_bilinear(a, [2 * H, 2 * W])
+  go = torch.randn(a.shape, generator=g)
+  a.backward(go.double())
+  dev = 'cuda'
+  yc = y.to(dev)
+  sums = torch.zeros(2 * C, dtype=torch.float64, device=dev)
+  mm, mv = mm0.to(dev), mv0.to(dev)
+  scale, shift, mean, invstd = (torch.empty(C, device=dev) for _ in range(4))
+  npix = N * H * W
+  call('immb_bn_stats', yc, npix, C, C, sums, ST())
+  call('immb_bn_finalize', sums, npix, C, gamma.to(dev), beta.to(dev), mm, mv, 1, scale, shift, mean, invstd, ST())
+  s = 2 if up2x else 1
+  ocs = C + 8       # write into a wider (concat-style) buffer
+  oh = torch.zeros(N, H * s, W * s, ocs, device=dev)
+  ol = torch.zeros_like(oh)
+  call('immb_bn_apply', yc, N, H, W, C, C, scale, shift, 1, up2x, oh, ol, ocs, ST())
+  assert rel_err((oh + ol)[..., :C], a) < 1e-5
+  assert float((oh + ol)[..., C:].abs().max()) == 0.0
+  assert rel_err(mm, mm_ref) < 1e-5 and rel_err(mv, mv_ref) < 1e-5
+  # backward
+  gdev = go.to(dev)
+  if up2x:
+    glow = torch.empty(N, H, W, C, device=dev)
+    call('immb_upsample2x_bwd', gdev, N, H, W, C, C, glow, ST())
+    gdev = glow
+  bs = torch.zeros(2 * C, dtype=torch.float64, device=dev)
+  dbacc = torch.zeros(C, dtype=torch.float64, device=dev)
+  dyh, dyl = torch.empty(N, H, W, C, device=dev), torch.empty(N, H, W, C, device=dev)
+  dg, db_ = torch.empty(C, device=dev), torch.empty(C, device=dev)
+  call('immb_bn_bwd_reduce', gdev, C, yc, C, npix, C, scale, shift, mean, invstd, 1, bs, ST())
+  call('immb_bn_bwd_apply', gdev, C, yc, C, npix, C, scale, shift, mean, invstd, 1, bs, dyh, dyl, dg, db_, dbacc, ST())
+  assert rel_err(dyh + dyl, yd.grad) < 1e-4
+  assert rel_err(dg, gd.grad) < 1e-4 and rel_err(db_, bd.grad) < 1e-4
+  assert float(dbacc.abs().max()) < 1e-3 * float(yd.grad.abs().sum())     # sum(dy) is analytically 0
+
+
+def test_bn_eval_uses_moving_stats():
+  C = 16
+  y = torch.randn(2, 4, 4, C)
+  gamma, beta = torch.rand(C) + 0.5, torch.randn(C)
+  mm, mv = torch.randn(C), torch.rand(C) + 0.5
+  ref, _, _ = O.batch_norm(y.double(), gamma.double(), beta.double(), mm.double(), mv.double(), False)
+  dev = 'cuda'
+  mmd, mvd = mm.to(dev), mv.to(dev)
+  scale, shift, mean, invstd = (torch.empty(C, device=dev) for _ in range(4))
+  call('immb_bn_finalize', None, 32, C, gamma.to(dev), beta.to(dev), mmd, mvd, 0, scale, shift, mean, invstd, ST())
+  oh, ol = torch.empty(2, 4, 4, C, device=dev), torch.empty(2, 4, 4, C, device=dev)
+  call('immb_bn_apply', y.to(dev), 2, 4, 4, C, C, scale, shift, 0, 0, oh, ol, C, ST())
+  assert rel_err(oh + ol, ref) < 1e-5
+  assert torch.equal(mmd.cpu(), mm) and torch.equal(mvd.cpu(), mv)
+
+
+@pytest.mark.parametrize('cfg', [(2, 16, 10, 16), (1, 32, 30, 16), (3, 16, 50, 16), (1, 4, 1, 3)])
+def test_softargmax_gauss_fwd_bwd(cfg):
+  B, S, K, Sg = cfg
+  g = torch.Generator().manual_seed(S + K)
+  heat = torch.randn(B, S, S, K, generator=g) * 2
+  hd = heat.double().requires_grad_(True)
+  gy, py = O.get_coord(hd, 2, S)
+  gx, px = O.get_coord(hd, 1, S)
+  mu = torch.stack([gy, gx], dim=2)
+  maps = O.get_gaussian_maps(mu, [Sg, Sg], 10.0, 'rot')
+  gm = torch.randn(maps.shape, generator=g)
+  maps.backward(gm.double())
+  dev, Cs, off = 'cuda', 64, 7
+  mu_d, py_d, px_d = torch.empty(B, K, 2, device=dev), torch.empty(B, S, K, device=dev), torch.empty(B, S, K, device=dev)
+  mh, ml = torch.zeros(B, Sg, Sg, Cs, device=dev), torch.zeros(B, Sg, Sg, Cs, device=dev)
+  call('immb_softargmax_gauss_fwd', heat.to(dev), B, S, K, K, 10.0, mu_d, py_d, px_d, Sg, mh, ml, Cs, off, ST())
+  assert float((mu_d.cpu().double() - mu).abs().max()) < 1e-5
+  assert rel_err(py_d, py) < 1e-5 and rel_err(px_d, px) < 1e-5
+  assert rel_err((mh + ml)[..., off:off + K], maps) < 1e-4
+  assert float((mh + ml)[..., :off].abs().max()) == 0.0
+  gfull = torch.zeros(B, Sg, Sg, Cs)
+  gfull[..., off:off + K] = gm
+  gh = torch.empty(B, S, S, K, device=dev)
+  call('immb_softargmax_gauss_bwd', gfull.to(dev), Cs, off, mu_d, py_d, px_d, B, S, K, Sg, 10.0, gh, K, ST())
+  assert rel_err(gh, hd.grad) < 1e-4
+  full = torch.empty(B, Sg, Sg, K, device=dev)
+  call('immb_gaussian_maps', mu_d, B, K, Sg, 10.0, full, ST())
+  assert rel_err(full, maps) < 1e-4
+
+
+def test_maxpool_fwd_bwd_first_max_wins():
+  g = torch.Generator().manual_seed(3)
+  x = torch.relu(torch.randn(2, 8, 6, 5, generator=g))       # many exact-zero ties, like post-ReLU VGG maps
+  xd = x.double().requires_grad_(True)
+  ref = O.max_pool_2x2(xd)
+  go = torch.randn(ref.shape, generator=g)
+  ref.backward(go.double())
+  dev = 'cuda'
+  xh, xl = split(x)
+  oh, ol = torch.empty(2, 4, 3, 5, device=dev), torch.empty(2, 4, 3, 5, device=dev)
+  call('immb_maxpool2x2_fwd', xh.to(dev), xl.to(dev), 2, 8, 6, 5, oh, ol, ST())
+  assert rel_err(oh + ol, ref) < 1e-6
+  gi = torch.empty(2, 8, 6, 5, device=dev)
+  call('immb_maxpool2x2_bwd', go.to(dev), xh.to(dev), xl.to(dev), 2, 8, 6, 5, gi, ST())
+  # positions with a strictly positive max are unambiguous; tie windows (all zeros) route to the first element
+  pos = (ref.detach() > 0).float()
+  up = lambda t: t.repeat_interleave(2, 1).repeat_interleave(2, 2)
+  assert rel_err(gi.cpu() * up(pos), xd.grad.float() * up(pos)) < 1e-6
+  assert rel_err(gi.cpu().view(2, 4, 2, 3, 2, 5).sum((2, 4)), go) < 1e-6      # each window passes its gradient once
+
+
+def test_perceptual_sum_finalize_and_grads():
+  B, R, h, C = 2, 16, 4, 6
+  g = torch.Generator().manual_seed(9)
+  f = torch.relu(torch.randn(2 * B, h, h, C, generator=g))
+  mask = torch.rand(B, R, R, 1, generator=g)
+  fd = f.double()
+  fp = fd[B:].clone().requires_grad_(True)
+  m = O.resize_bilinear(mask.double(), [h, h])
+  l = (fd[:B] - fp) ** 2
+  s = (l * m).mean()
+  a = 2.3
+  wl = a + 0.01 * (s - a)
+  L = (l / wl * m).mean()
+  (1000.0 * L).backward()
+  dev = 'cuda'
+  fh, fl = split(f)
+  fh, fl = fh.to(dev), fl.to(dev)
+  acc = torch.zeros(1, dtype=torch.float64, device=dev)
+  call('immb_perceptual_level_sum', fh[:B], fl[:B], C, fh[B:], fl[B:], C, B, h, h, C, mask.to(dev), R, acc, ST())
+  cnt = float(B * h * h * C)
+  assert abs(float(acc.item()) / cnt - float(s)) / float(s) < 1e-5
+  agg = torch.tensor([a], device=dev)
+  lev, rec, coef = torch.empty(1, device=dev), torch.empty(1, device=dev), torch.empty(1, device=dev)
+  call('immb_perceptual_finalize', acc, torch.tensor([cnt], dtype=torch.float64, device=dev), 1, agg, 1, lev, rec, coef, ST())
+  assert abs(float(lev.item()) - float(L)) / float(L) < 1e-5
+  assert abs(float(rec.item()) - 1000 * float(L)) / (1000 * float(L)) < 1e-5
+  assert abs(float(agg.item()) - float(wl)) / float(wl) < 1e-6
+  dyh, dyl = torch.empty(B, h, h, C, device=dev), torch.empty(B, h, h, C, device=dev)
+  call('immb_vgg_bwd_combine', None, fh[:B], fl[:B], fh[B:], fl[B:], B, h, h, C, mask.to(dev), R, coef, dyh, dyl, ST())
+  ref = fp.grad * (fp.detach() > 0)
+  assert rel_err(dyh + dyl, ref) < 1e-4
+
+
+def test_vgg_prologue_and_pred_grad():
+  B, R = 2, 8
+  g = torch.Generator().manual_seed(4)
+  gt = torch.rand(B, R, R, 3, generator=g) * 255
+  pred9 = torch.randn(B, R, R, 9, generator=g) * 50
+  dev = 'cuda'
+  oh, ol = torch.empty(2 * B, R, R, 1, device=dev), torch.empty(2 * B, R, R, 1, device=dev)
+  call('immb_vgg_prologue', gt.to(dev), pred9.to(dev), 9, B, R, oh, ol, ST())
+  ims = torch.cat([gt, pred9[..., :3]], 0).double()
+  ref = ims.mean(3, keepdim=True) / 255.0 - O.VGG_MEAN / 255.0
+  assert rel_err(oh + ol, ref) < 1e-5
+  mask = torch.rand(B, R, R, 1, generator=g)
+  coef = torch.tensor([-0.37])
+  gv = torch.randn(B, R, R, 1, generator=g)
+  gh, gl = torch.empty(B, R, R, 9, device=dev), torch.empty(B, R, R, 9, device=dev)
+  call('immb_pred_grad', gt.to(dev), pred9.to(dev), 9, mask.to(dev), coef.to(dev), gv.to(dev), B, R, gh, gl, ST())
+  ref = torch.zeros(B, R, R, 9, dtype=torch.float64)
+  ref[..., :3] = -0.37 * mask.double() * (gt.double() - pred9[..., :3].double()) + gv.double() / (3 * 255.0)
+  assert rel_err(gh + gl, ref) < 1e-5
+
+
+def test_resize_align_corners_fwd_bwd():
+  N, H, C, Ho = 2, 32, 8, 16
+  x = torch.randn(N, H, H, C)
+  xd = x.double().requires_grad_(True)
+  ref = O.resize_bilinear(xd, [Ho, Ho], align_corners=True)
+  go = torch.randn(ref.shape)
+  ref.backward(go.double())
+  dev = 'cuda'
+  xh, xl = split(x)
+  oh, ol = torch.empty(N, Ho, Ho, C, device=dev), torch.empty(N, Ho, Ho, C, device=dev)
+  call('immb_resize_ac_fwd', xh.to(dev), xl.to(dev), C, N, H, H, C, Ho, Ho, oh, ol, C, ST())
+  assert rel_err(oh + ol, ref) < 1e-5
+  gi = torch.empty(N, H, H, C, device=dev)
+  call('immb_resize_ac_bwd', go.to(dev), C, N, H, H, C, Ho, Ho, gi, ST())
+  assert rel_err(gi, xd.grad) < 1e-5
+
+
+def test_clip_adam_multi_tensor():
+  """Two tensors in one flat buffer: one gets clipped (norm>1), one does not; wd only on the first."""
+  dev = 'cuda'
+  g = torch.Generator().manual_seed(11)
+  n0, n1 = 3000, 37
+  p = torch.randn(n0 + n1, generator=g)
+  gr = torch.cat([torch.randn(n0, generator=g), torch.randn(n1, generator=g) * 1e-3])
+  m0, v0 = torch.rand(n0 + n1, generator=g) * 0.01, torch.rand(n0 + n1, generator=g) * 1e-4
+  wd = [1e-5, 0.0]
+  ct, co, cl = [], [], []
+  for t, (o, n) in enumerate([(0, n0), (n0, n1)]):
+    for c0 in range(0, n, 2048):
+      ct.append(t); co.append(o + c0); cl.append(min(2048, n - c0))
+  T = lambda a, dt: torch.tensor(a, dtype=dt, device=dev)
+  pd, gd, md, vd = p.to(dev), gr.to(dev), m0.to(dev), v0.to(dev)
+  sq = torch.zeros(4, dtype=torch.float64, device=dev)
+  world = 2.0
+  args = (T(ct, torch.int32), T(co, torch.int64), T(cl, torch.int32), len(ct), T(wd, torch.float32), 1.0 / world)
+  call('immb_adam_norms', pd, gd, n0 + n1, *args, sq, sq[2:], ST())
+  lr, t = 1e-3, 3
+  lr_t = lr * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
+  call('immb_adam_apply', pd, gd, md, vd, n0 + n1, *args, sq, 1.0, lr_t, 0.9, 0.999, 1e-8, ST())
+  for (o, n), w in zip([(0, n0), (n0, n1)], wd):
+    pe, ge = p[o:o + n].double(), gr[o:o + n].double() / world
+    ge = ge + w * pe
+    gc = O.clip_by_norm(ge, 1.0)
+    var, mm, vv = O.adam_step(pe, gc, m0[o:o + n].double(), v0[o:o + n].double(), lr, t)
+    assert rel_err(pd[o:o + n], var) < 1e-6
+    assert rel_err(md[o:o + n], mm) < 1e-5 and rel_err(vd[o:o + n], vv) < 1e-5
+  wl, tot = torch.empty(1, device=dev), torch.empty(1, device=dev)
+  call('immb_total_loss', T([5.0], torch.float32), sq[2:], T(wd, torch.float32), 2, wl, tot, ST())
+  ref_wl = 0.5 * 1e-5 * float((p[:n0].double() ** 2).sum())
+  assert abs(float(wl.item()) - ref_wl) / ref_wl < 1e-5 and abs(float(tot.item()) - 5.0 - ref_wl) < 1e-5
+
+
+def test_error_reporting_no_throw():
+  d = conv_desc(1, 8, 8, 4, 4, 3, 1)
+  d.kh = 9
+  with pytest.raises(_lib.ImmbError) as e:
+    call('immb_conv2d_fwd', d, torch.zeros(1, device='cuda'), None, torch.zeros(1, device='cuda'), None, None, None,
+         torch.zeros(1, device='cuda'), None, ST())
+  assert 'kernel size' in str(e.value)
+  with pytest.raises(_lib.ImmbError):
+    call('immb_split_planes', torch.zeros(4), torch.zeros(4), None, 4, ST())       # CPU tensors are refused

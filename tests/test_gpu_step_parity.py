@@ -1,0 +1,132 @@
+"""Parity of the CUDA training step (through the C ABI) against the CPU oracle on identical inputs.
+
+Bars (BASELINE.json north_star): landmarks / reconstruction / loss within 1e-3 relative of the fp32 reference,
+landmark MSE < 1e-3.  The oracle is evaluated in fp64; the fp32 oracle's own distance to fp64 is measured in
+the same test and gradient tolerances are expressed relative to it (gradients are ill-conditioned at
+initialisation: even fp32-vs-fp64 differ by ~5e-4 median, 3e-3 max; see tests/test_oracle_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from imm_b200 import _lib
+from oracle import imm_oracle as O
+from tests.gpu_util import make_pair, rel_err, to_dev
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_step(batch, n_maps, image_size=128, engine=_lib.ENGINE_AUTO, seed=0):
+  eng, st64, st32, inputs = make_pair(batch, n_maps, image_size, seed, engine=engine)
+  inp64 = {k: v.double() for k, v in inputs.items()}
+  r64 = O.train_step(st64, inp64)
+  r32 = O.train_step(st32, inputs)
+  d = to_dev(inputs)
+  eng.train_step(d['image'], d['future_image'], d['mask'])
+  torch.cuda.synchronize()
+  return eng, st64, st32, r64, r32
+
+
+def _check_step(eng, st64, st32, r64, r32):
+  out = r64['out']
+  # loss / levels
+  loss = float(eng.total_loss.item())
+  assert abs(loss - float(r64['loss'])) / float(r64['loss']) < 1e-4
+  lv = eng.levels.cpu().double().numpy()
+  ref_lv = np.array([float(x) for x in out['level_losses']])
+  np.testing.assert_allclose(lv, ref_lv, rtol=1e-3)
+  # landmarks (y,x) in [-1,1]
+  yx = eng.mu.cpu().double()
+  assert float((yx - out['gauss_yx']).abs().max()) < 1e-4
+  assert float(((yx - out['gauss_yx']) ** 2).mean()) < 1e-3
+  # reconstruction
+  pred = eng.pred[..., :3].cpu()
+  assert rel_err(pred, out['future_im_pred']) < 1e-3
+  assert rel_err(eng.pose_conv.y.cpu(), out['heatmaps']) < 1e-3
+  # gradients: compare with the fp64 oracle; tolerance = max(5x the fp32 oracle's own error, 2e-3)
+  worst = []
+  for k, g64 in r64['grads'].items():
+    if k.endswith('/b') and ('/'.join(k.split('/')[:-2]) + '/batch_normalization/gamma') in r64['grads']:
+      continue      # conv bias in front of a training-mode BN: analytically zero gradient (noise only)
+    e_gpu = rel_err(eng.grads[k], g64)
+    e_cpu = rel_err(r32['grads'][k], g64)
+    tol = max(5.0 * e_cpu, 2e-3)
+    worst.append((e_gpu / tol, k, e_gpu, e_cpu))
+  worst.sort(reverse=True)
+  assert worst[0][0] < 1.0, 'gradient parity: %s' % (worst[:5],)
+  # BN-biases: absolute noise floor only
+  for k, g64 in r64['grads'].items():
+    if k.endswith('/b') and float(g64.abs().max()) < 1e-6:
+      assert float(eng.grads[k].abs().max()) < 1e-4
+  # state after the step: BN moving stats, loss normalisers, updated weights
+  for k, v in st64.buffers.items():
+    assert rel_err(eng.buffers[k], v) < 1e-4, k
+  return worst
+
+
+def test_step_parity_config1_batch2():
+  """BASELINE config 1: CelebA-10pts, batch 2, 128x128, one fwd+loss+bwd+clip+Adam step."""
+  eng, st64, st32, r64, r32 = _run_step(2, 10)
+  worst = _check_step(eng, st64, st32, r64, r32)
+  print('worst gradient ratios:', worst[:3])
+
+
+def test_step_parity_k30_batch3():
+  """CelebA-30pts shape (config 3 per-GPU model), odd batch."""
+  eng, st64, st32, r64, r32 = _run_step(3, 30, seed=1)
+  _check_step(eng, st64, st32, r64, r32)
+
+
+def test_param_update_matches_oracle():
+  """After one step every parameter (except noise-gradient biases) moved as the oracle's TF-Adam says."""
+  eng, st64, st32, inputs = make_pair(2, 10)
+  before = {k: v.clone() for k, v in st64.params.items()}
+  r64 = O.train_step(st64, {k: v.double() for k, v in inputs.items()})
+  d = to_dev(inputs)
+  eng.train_step(d['image'], d['future_image'], d['mask'])
+  torch.cuda.synchronize()
+  for k, v in st64.params.items():
+    g = r64['grads'][k]
+    if float(g.abs().max()) < 1e-6:
+      continue
+    upd_ref = (v - before[k]).double()
+    upd_gpu = eng.params[k].cpu().double() - before[k]
+    # elements whose gradient is far from zero have |update| = lr_t*m/(sqrt(v)+eps) ~ lr: direction must agree
+    big = g.abs() > 1e-3 * g.abs().max()
+    agree = (torch.sign(upd_ref[big]) == torch.sign(upd_gpu[big])).double().mean()
+    assert float(agree) > 0.999, (k, float(agree))
+    assert rel_err(upd_gpu[big], upd_ref[big]) < 2e-2, k
+  assert eng.global_step == 0.0 and eng.adam_t == 1
+
+
+def test_eval_mode_forward_matches_oracle():
+  """training_pl=False: BN uses moving statistics, *_agg is not updated (base_model.py:46-48)."""
+  eng, st64, st32, inputs = make_pair(2, 10)
+  # make the moving stats non-trivial
+  g = torch.Generator().manual_seed(5)
+  for k in list(st64.buffers.keys()):
+    if k.endswith('moving_mean'):
+      st64.buffers[k] = torch.randn(st64.buffers[k].shape, generator=g, dtype=torch.float64) * 0.01
+    elif k.endswith('moving_variance'):
+      st64.buffers[k] = 0.5 + torch.rand(st64.buffers[k].shape, generator=g, dtype=torch.float64) * 0.01
+  eng.load_state(None, {k: v.float() for k, v in st64.buffers.items()})
+  out = O.forward(st64, {k: v.double() for k, v in inputs.items()}, training=False)
+  d = to_dev(inputs)
+  agg_before = eng.agg.clone()
+  eng.forward(d['image'], d['future_image'], d['mask'], training=False)
+  loss = float(eng.loss_value().item())
+  assert abs(loss - float(out['loss'])) / float(out['loss']) < 1e-4
+  assert float((eng.mu.cpu().double() - out['gauss_yx']).abs().max()) < 1e-4
+  assert rel_err(eng.pred[..., :3].cpu(), out['future_im_pred']) < 1e-3
+  assert torch.equal(agg_before, eng.agg)
+
+
+def test_two_steps_track_oracle():
+  """Two consecutive steps: loss of the second step (which sees updated weights, BN stats, normalisers)."""
+  eng, st64, st32, inputs = make_pair(2, 10)
+  inp64 = {k: v.double() for k, v in inputs.items()}
+  d = to_dev(inputs)
+  for _ in range(2):
+    r64 = O.train_step(st64, inp64)
+    eng.train_step(d['image'], d['future_image'], d['mask'])
+  assert abs(float(eng.total_loss.item()) - float(r64['loss'])) / float(r64['loss']) < 2e-3
+  assert float((eng.mu.cpu().double() - r64['out']['gauss_yx']).abs().max()) < 1e-3
