@@ -1,12 +1,656 @@
-// tcgen05 + TMA implicit-GEMM convolution engine (placeholder until the engine lands: nothing eligible).
+// tcgen05 + TMA implicit-GEMM convolution engine for sm_100a (forward, dgrad, wgrad).
+//
+// Forward / dgrad ("shifted-window GEMM", both operands K-major):
+//   D[128 pixels, BN channels] = sum over taps (r,s) and 32-channel chunks of  A_tap[128, 32] * B_tap[BN, 32]^T
+//   * A_tap is a TH x TW (x TN images) patch of the NHWC activation, shifted by the tap offset, fetched with ONE
+//     5-D TMA box (c, w, hpar, h, n): out-of-bounds coordinates are zero-filled by the TMA unit, which is exactly
+//     TF 'SAME' padding; stride-2 convs address the input through a parity-split view (c+wpar*C, w/2, hpar, h/2, n).
+//   * B_tap is a [BN, 32] slice of the packed weights ([tap][Cout][Cin] for fwd, [tap][Cin][Cout] for dgrad).
+//   * both land in shared memory in the canonical K-major SWIZZLE_128B layout (128-byte rows, 1024-byte 8-row
+//     atoms), are consumed by tcgen05.mma kind::tf32 (M=128, N=BN, K=8 per instruction; +32 B descriptor advance)
+//     and accumulate in TMEM; 3xTF32 issues hi*hi + hi*lo + lo*hi into the same accumulator.
+//   * warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue (tcgen05.ld -> bias/ReLU ->
+//     vectorised NHWC stores).  mbarrier ring: full[stage] (TMA -> MMA), empty[stage] (tcgen05.commit -> TMA),
+//     tmem_full (last commit -> epilogue).
+// Wgrad (both operands MN-major): see conv_tc_wgrad_kernel below.
+#include <cudaTypedefs.h>
+#include <mutex>
+#include <cstring>
+#include <cstdlib>
 #include "common.cuh"
+#include "tc_ptx.cuh"
+
 namespace immb {
-bool conv_tc_eligible(const immb_conv_desc*, int) { return false; }
-int conv_tc_fwd(const immb_conv_desc*, const float*, const float*, const float*, const float*, const float*,
-                float*, float*, cudaStream_t) { return set_error(IMMB_ERR_UNSUPPORTED, "tc engine not built"); }
-int conv_tc_dgrad(const immb_conv_desc*, const float*, const float*, const float*, const float*, float*,
-                  cudaStream_t) { return set_error(IMMB_ERR_UNSUPPORTED, "tc engine not built"); }
+
+using namespace ptx;
+
+constexpr int kTileM = 128;
+constexpr int kMaxTaps = 9;
+
+struct TapEntry {
+  int b_tap, dc, dw, hp, dh;
+};
+
+struct TcParams {
+  int TW, TH, TN;             // tile box in pixels (TW*TH*TN == 128)
+  int tiles_w, tiles_h;
+  int n_taps, kchunks;
+  TapEntry taps[kMaxTaps];
+  float* out_hi;
+  float* out_lo;
+  const float* bias;
+  int relu;
+  int N, PH, PW;              // tile-space extents (predication)
+  int OH, OW, ocs;            // output tensor
+  int out_mul, out_add_h, out_add_w;
+  int n_cols;                 // valid output channels
+};
+
+// ---------------------------------------------------------------------------------------------------------
+template <int BN, int PASSES, int STAGES>
+struct FwdCfg {
+  static constexpr uint32_t A_BYTES = kTileM * 128;
+  static constexpr uint32_t B_BYTES = BN * 128;
+  static constexpr uint32_t NPL = PASSES == 3 ? 2 : 1;      // planes per operand
+  static constexpr uint32_t STAGE_BYTES = (A_BYTES + B_BYTES) * NPL;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+};
+
+template <int BN, int PASSES, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
+               const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
+               const __grid_constant__ TcParams p) {
+  using Cfg = FwdCfg<BN, PASSES, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tw = blockIdx.x % p.tiles_w;
+  const int th = (blockIdx.x / p.tiles_w) % p.tiles_h;
+  const int tn = blockIdx.x / (p.tiles_w * p.tiles_h);
+  const int n_off = blockIdx.y * BN;
+  const int num_k = p.n_taps * p.kchunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA_hi);
+    prefetch_tmap(&mapB_hi);
+    if (PASSES == 3) {
+      prefetch_tmap(&mapA_lo);
+      prefetch_tmap(&mapB_lo);
+    }
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      for (int kt = 0; kt < num_k; ++kt) {
+        const int s = kt % STAGES;
+        const uint32_t ph = (kt / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        const int tap = kt / p.kchunks, kc = kt - tap * p.kchunks;
+        const TapEntry t = p.taps[tap];
+        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+        mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+        const int c = kc * 32 + t.dc, w = tw * p.TW + t.dw, h = th * p.TH + t.dh, n = tn * p.TN;
+        tma_load_5d(st, &mapA_hi, &full[s], c, w, t.hp, h, n);
+        if (PASSES == 3) tma_load_5d(st + Cfg::A_BYTES, &mapA_lo, &full[s], c, w, t.hp, h, n);
+        uint8_t* sb = st + Cfg::A_BYTES * Cfg::NPL;
+        tma_load_3d(sb, &mapB_hi, &full[s], kc * 32, n_off, t.b_tap);
+        if (PASSES == 3) tma_load_3d(sb + Cfg::B_BYTES, &mapB_lo, &full[s], kc * 32, n_off, t.b_tap);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = idesc_tf32(kTileM, BN, 0, 0);
+      for (int kt = 0; kt < num_k; ++kt) {
+        const int s = kt % STAGES;
+        const uint32_t ph = (kt / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint32_t a_lo = a_hi + Cfg::A_BYTES;
+        const uint32_t b_hi = a_hi + Cfg::A_BYTES * Cfg::NPL;
+        const uint32_t b_lo = b_hi + Cfg::B_BYTES;
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const uint32_t ko = k4 * 32;    // 8 tf32 = 32 bytes along K inside the 128-byte swizzle row
+          const uint64_t da_hi = smem_desc_sw128(a_hi + ko, 16, 1024);
+          const uint64_t db_hi = smem_desc_sw128(b_hi + ko, 16, 1024);
+          mma_tf32(tmem_base, da_hi, db_hi, idesc, (kt > 0 || k4 > 0) ? 1u : 0u);
+          if (PASSES == 3) {
+            const uint64_t da_lo = smem_desc_sw128(a_lo + ko, 16, 1024);
+            const uint64_t db_lo = smem_desc_sw128(b_lo + ko, 16, 1024);
+            mma_tf32(tmem_base, da_hi, db_lo, idesc, 1u);
+            mma_tf32(tmem_base, da_lo, db_hi, idesc, 1u);
+          }
+        }
+        mma_commit(&empty[s]);            // frees the smem stage once these MMAs have drained
+      }
+      mma_commit(tmem_full);
+    }
+  } else {
+    // ===== epilogue: warps 2..5; warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int wl = m % p.TW, hl = (m / p.TW) % p.TH, nl = m / (p.TW * p.TH);
+    const int n = tn * p.TN + nl, h = th * p.TH + hl, w = tw * p.TW + wl;
+    const bool row_ok = (n < p.N) && (h < p.PH) && (w < p.PW);
+    const size_t pix = ((size_t)n * p.OH + (size_t)(h * p.out_mul + p.out_add_h)) * p.OW +
+                       (size_t)(w * p.out_mul + p.out_add_w);
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (!row_ok) continue;
+      const int col0 = n_off + c0;
+      if (col0 >= p.n_cols) continue;
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + col0 + j);
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      float* o = p.out_hi + pix * p.ocs + col0;
+      if (p.out_lo) {
+        float* ol = p.out_lo + pix * p.ocs + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 hi4, lo4;
+          split_tf32(v[j], hi4.x, lo4.x);
+          split_tf32(v[j + 1], hi4.y, lo4.y);
+          split_tf32(v[j + 2], hi4.z, lo4.z);
+          split_tf32(v[j + 3], hi4.w, lo4.w);
+          *reinterpret_cast<float4*>(o + j) = hi4;
+          *reinterpret_cast<float4*>(ol + j) = lo4;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// wgrad: dW[tap][ci][co] = sum_pixels X[pix + shift(tap)][ci] * dY[pix][co]
+//   GEMM with M = (taps_per_tile x CIT input channels) = 128, N = BN output channels, K = pixels.
+//   Both operands are "MN-major" (the channel index is contiguous in memory, pixels are the reduction index):
+//   a TMA box (32 channels x 32 pixels) lands as 32 rows of 128 bytes = the canonical MN-major SWIZZLE_128B
+//   atom stack ((8 x 16B) along MN) x (8 K-rows, 1024 B apart per K-group); the 128 (A) / BN (B) channels are
+//   4 / BN/32 such boxes, LBO = 4096 B apart.  One tcgen05.mma consumes K = 8 pixels (descriptor start + 1024 B).
+//   Split-K over pixel tiles across blockIdx.z; partial tiles are reduced with red.global.add.f32.
+// ---------------------------------------------------------------------------------------------------------
+struct WgParams {
+  int PW, PH;                 // pixel box (PW*PH == 32)
+  int tiles_w, tiles_h, N;    // pixel tiles per image, images
+  int tiles_per_split, total_tiles;
+  int cit;                    // input channels per tap inside one M tile (32, 64 or 128)
+  int taps_per_tile;          // 128 / cit
+  int n_taps;                 // kh*kw
+  int m_tiles_per_group;      // for cit==128: Cin_pad/128 M tiles per tap; else 1
+  TapEntry taps[kMaxTaps];    // dc, dw, hp, dh of the X box for each tap (b_tap unused)
+  float* dw;                  // [taps][Cin][Cout]
+  int Cin, Cout;
+};
+
+template <int BN, int PASSES, int STAGES>
+struct WgCfg {
+  static constexpr uint32_t A_BYTES = 128 * 128;           // 4 boxes x (32 px x 128 B)
+  static constexpr uint32_t B_BYTES = BN * 128;            // BN/32 boxes
+  static constexpr uint32_t NPL = PASSES == 3 ? 2 : 1;
+  static constexpr uint32_t STAGE_BYTES = (A_BYTES + B_BYTES) * NPL;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+};
+
+template <int BN, int PASSES, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_constant__ CUtensorMap mapX_lo,
+                     const __grid_constant__ CUtensorMap mapY_hi, const __grid_constant__ CUtensorMap mapY_lo,
+                     const __grid_constant__ WgParams p) {
+  using Cfg = WgCfg<BN, PASSES, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // M tile -> (first tap, channel offset)
+  int tap0, ci0;
+  if (p.cit == 128) {
+    tap0 = blockIdx.x / p.m_tiles_per_group;
+    ci0 = (blockIdx.x % p.m_tiles_per_group) * 128;
+  } else {
+    tap0 = blockIdx.x * p.taps_per_tile;
+    ci0 = 0;
+  }
+  const int n_off = blockIdx.y * BN;
+  const int t_begin = blockIdx.z * p.tiles_per_split;
+  int t_end = t_begin + p.tiles_per_split;
+  if (t_end > p.total_tiles) t_end = p.total_tiles;
+  const int num_k = t_end - t_begin;
+  const int chunks_per_tap = p.cit / 32;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && num_k > 0) {
+      for (int kt = 0; kt < num_k; ++kt) {
+        const int s = kt % STAGES;
+        const uint32_t ph = (kt / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        const int tile = t_begin + kt;
+        const int twi = tile % p.tiles_w;
+        const int thi = (tile / p.tiles_w) % p.tiles_h;
+        const int n = tile / (p.tiles_w * p.tiles_h);
+        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+        mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+        // A: 4 boxes of 32 channels (taps beyond the filter are loaded with an out-of-range image index -> zeros)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int tl = j / chunks_per_tap, cj = j - tl * chunks_per_tap;
+          const int tap = tap0 + tl;
+          const bool valid = tap < p.n_taps;
+          const TapEntry t = p.taps[valid ? tap : 0];
+          const int c = ci0 + cj * 32 + t.dc, w = twi * p.PW + t.dw, h = thi * p.PH + t.dh;
+          const int nn = valid ? n : p.N;      // n == N is out of bounds -> TMA zero fill
+          tma_load_5d(st + j * 4096, &mapX_hi, &full[s], c, w, t.hp, h, nn);
+          if (PASSES == 3) tma_load_5d(st + Cfg::A_BYTES + j * 4096, &mapX_lo, &full[s], c, w, t.hp, h, nn);
+        }
+        uint8_t* sb = st + Cfg::A_BYTES * Cfg::NPL;
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j) {
+          tma_load_5d(sb + j * 4096, &mapY_hi, &full[s], n_off + j * 32, twi * p.PW, 0, thi * p.PH, n);
+          if (PASSES == 3)
+            tma_load_5d(sb + Cfg::B_BYTES + j * 4096, &mapY_lo, &full[s], n_off + j * 32, twi * p.PW, 0, thi * p.PH, n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && num_k > 0) {
+      constexpr uint32_t idesc = idesc_tf32(kTileM, BN, 1, 1);
+      for (int kt = 0; kt < num_k; ++kt) {
+        const int s = kt % STAGES;
+        const uint32_t ph = (kt / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint32_t a_lo = a_hi + Cfg::A_BYTES;
+        const uint32_t b_hi = a_hi + Cfg::A_BYTES * Cfg::NPL;
+        const uint32_t b_lo = b_hi + Cfg::B_BYTES;
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const uint32_t ko = k4 * 1024;     // 8 pixels = 8 rows x 128 B
+          // MN-major tf32: SWIZZLE_128B_BASE32B; 32-channel groups are LBO = 4096 B apart (one TMA box each),
+          // 4-pixel K atoms are SBO = 512 B apart
+          const uint64_t da_hi = smem_desc_sw128(a_hi + ko, 4096, 512, 1);
+          const uint64_t db_hi = smem_desc_sw128(b_hi + ko, 4096, 512, 1);
+          mma_tf32(tmem_base, da_hi, db_hi, idesc, (kt > 0 || k4 > 0) ? 1u : 0u);
+          if (PASSES == 3) {
+            const uint64_t da_lo = smem_desc_sw128(a_lo + ko, 4096, 512, 1);
+            const uint64_t db_lo = smem_desc_sw128(b_lo + ko, 4096, 512, 1);
+            mma_tf32(tmem_base, da_hi, db_lo, idesc, 1u);
+            mma_tf32(tmem_base, da_lo, db_hi, idesc, 1u);
+          }
+        }
+        mma_commit(&empty[s]);
+      }
+      mma_commit(tmem_full);
+    }
+  } else if (num_k > 0) {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int tl = m / p.cit;
+    const int tap = tap0 + tl;
+    const int ci = ci0 + (m - tl * p.cit);
+    const bool row_ok = (tap < p.n_taps) && (ci < p.Cin);
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (!row_ok) continue;
+      const int col0 = n_off + c0;
+      if (col0 >= p.Cout) continue;
+      float* o = p.dw + ((size_t)tap * p.Cin + ci) * p.Cout + col0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) atomicAdd(o + j, v[j]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// =========================================================================================================
+// host side
+// =========================================================================================================
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(f);
+  });
+  return fn;
+}
+
+static int make_map(CUtensorMap* m, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
+                    const uint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+  auto fn = get_encode_fn();
+  if (!fn) return set_error(IMMB_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  uint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base),
+                  reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_b),
+                  reinterpret_cast<const cuuint32_t*>(box), reinterpret_cast<const cuuint32_t*>(estr),
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(IMMB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return IMMB_OK;
+}
+
+// 5-D activation view (c, w, hpar, h, n) of an NHWC tensor [N,H,W,cs] with `C` valid channels.
+// parity_split: (c + wpar*C, w/2, hpar, h/2, n) view used by stride-2 convolutions (needs cs == C, even H, W).
+static int make_act_map(CUtensorMap* m, const float* base, int N, int H, int W, int C, int cs, bool parity_split,
+                        int box_w, int box_h, int box_n, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+  uint64_t dims[5], str[4];
+  uint32_t box[5] = {32, (uint32_t)box_w, 1, (uint32_t)box_h, (uint32_t)box_n};
+  if (!parity_split) {
+    dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = N;
+    str[0] = (uint64_t)cs * 4; str[1] = (uint64_t)W * cs * 4; str[2] = (uint64_t)W * cs * 4;
+    str[3] = (uint64_t)H * W * cs * 4;
+  } else {
+    dims[0] = 2 * (uint64_t)C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = N;
+    str[0] = (uint64_t)2 * C * 4; str[1] = (uint64_t)W * C * 4; str[2] = (uint64_t)2 * W * C * 4;
+    str[3] = (uint64_t)H * W * C * 4;
+  }
+  return make_map(m, base, 5, dims, str, box, swz);
+}
+
+// 3-D weight view (k, n, tap) of [taps][Nn][Kd] with box (32, BN, 1)
+static int make_w_map(CUtensorMap* m, const float* base, int taps, int Nn, int Kd, int bn) {
+  uint64_t dims[3] = {(uint64_t)Kd, (uint64_t)Nn, (uint64_t)taps};
+  uint64_t str[2] = {(uint64_t)Kd * 4, (uint64_t)Nn * Kd * 4};
+  uint32_t box[3] = {32, (uint32_t)bn, 1};
+  return make_map(m, base, 3, dims, str, box);
+}
+
+static bool pick_tile(int PH, int PW, int N, int* TW, int* TH, int* TN) {
+  if (PW % 16 == 0 && PH % 8 == 0) { *TW = 16; *TH = 8; *TN = 1; return true; }
+  if (PW == 8 && PH == 8) { *TW = 8; *TH = 8; *TN = 2; return true; }
+  (void)N;
+  return false;
+}
+
+static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+static int pymod(int a, int b) { return a - floordiv(a, b) * b; }
+
+bool conv_tc_eligible(const immb_conv_desc* d, int op) {
+  if (d->kh != d->kw || (d->kh != 1 && d->kh != 3)) return false;
+  if (d->stride == 2 && (d->kh != 3 || (d->H % 2) || (d->W % 2) || d->x_cstride != d->Cin || d->Cin % 32)) return false;
+  if (d->Cin < 32 || d->Cout < 32 || d->Cout % 32) return false;
+  if (d->x_cstride % 4 || d->y_cstride % 4 || d->y_cstride != d->Cout) return false;
+  if (d->cin_pad % 32 || d->cin_pad < d->Cin) return false;
+  int TW, TH, TN;
+  if (op == 0) {
+    return pick_tile(d->Ho, d->Wo, d->N, &TW, &TH, &TN);
+  } else if (op == 1) {
+    if (d->x_cstride < d->cin_pad) return false;      // dx receives cin_pad channels
+    if (d->stride == 1) return pick_tile(d->H, d->W, d->N, &TW, &TH, &TN);
+    return pick_tile(d->H / 2, d->W / 2, d->N, &TW, &TH, &TN);
+  } else {
+    if (!(d->cin_pad == 32 || d->cin_pad == 64 || d->cin_pad >= 128)) return false;
+    if (d->Wo % 8 || (d->Wo >= 16 && d->Wo % 16)) return false;
+    int pw = d->Wo >= 16 ? 16 : 8, phh = 32 / pw;
+    if (d->Ho % phh) return false;
+    return true;
+  }
+}
+
+template <int BN, int PASSES>
+static int launch_fwd(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                      const CUtensorMap& b_lo, const TcParams& p, dim3 grid, cudaStream_t st) {
+  constexpr int STAGES = PASSES == 3 ? (BN <= 64 ? 4 : 3) : (BN <= 64 ? 6 : 4);
+  using Cfg = FwdCfg<BN, PASSES, STAGES>;
+  auto kern = conv_tc_kernel<BN, PASSES, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "conv_tc smem attr: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  kern<<<grid, 192, Cfg::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+  return check_launch("conv_tc_kernel");
+}
+
+static int dispatch_fwd(int bn, int passes, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
+                        const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcParams& p, dim3 grid,
+                        cudaStream_t st) {
+#define IMMB_CASE(BN_)                                                                         \
+  if (bn == BN_)                                                                               \
+    return passes == 3 ? launch_fwd<BN_, 3>(a_hi, a_lo, b_hi, b_lo, p, grid, st)               \
+                       : launch_fwd<BN_, 1>(a_hi, a_lo, b_hi, b_lo, p, grid, st);
+  IMMB_CASE(32)
+  IMMB_CASE(64)
+  IMMB_CASE(96)
+  IMMB_CASE(128)
+#undef IMMB_CASE
+  return set_error(IMMB_ERR_INVALID, "conv_tc: unsupported BN %d", bn);
+}
+
+static int pick_bn(int ncols) {
+  if (ncols % 128 == 0) return 128;
+  if (ncols % 96 == 0) return 96;
+  if (ncols % 64 == 0) return 64;
+  return 32;
+}
+
+int conv_tc_fwd(const immb_conv_desc* d, const float* x_hi, const float* x_lo, const float* wp_hi,
+                const float* wp_lo, const float* bias, float* y_hi, float* y_lo, cudaStream_t st) {
+  const int passes = d->precision == IMMB_PREC_TF32 ? 1 : 3;
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  if (!pick_tile(d->Ho, d->Wo, d->N, &p.TW, &p.TH, &p.TN)) return set_error(IMMB_ERR_UNSUPPORTED, "conv_tc_fwd: tile");
+  p.tiles_w = d->Wo / p.TW; p.tiles_h = d->Ho / p.TH;
+  p.n_taps = d->kh * d->kw; p.kchunks = d->cin_pad / 32;
+  for (int r = 0; r < d->kh; ++r)
+    for (int s = 0; s < d->kw; ++s) {
+      TapEntry& t = p.taps[r * d->kw + s];
+      t.b_tap = r * d->kw + s;
+      int th = r - d->pad_t, tw = s - d->pad_l;
+      if (d->stride == 1) { t.dc = 0; t.dw = tw; t.hp = 0; t.dh = th; }
+      else { t.dh = floordiv(th, 2); t.hp = pymod(th, 2); t.dw = floordiv(tw, 2); t.dc = pymod(tw, 2) * d->Cin; }
+    }
+  p.out_hi = y_hi; p.out_lo = y_lo; p.bias = bias; p.relu = d->epilogue == IMMB_EPI_BIAS_RELU;
+  p.N = d->N; p.PH = d->Ho; p.PW = d->Wo; p.OH = d->Ho; p.OW = d->Wo; p.ocs = d->y_cstride;
+  p.out_mul = 1; p.out_add_h = 0; p.out_add_w = 0; p.n_cols = d->Cout;
+  const int bn = pick_bn(d->Cout);
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  int rc;
+  const bool split = d->stride == 2;
+  if ((rc = make_act_map(&a_hi, x_hi, d->N, d->H, d->W, d->Cin, d->x_cstride, split, p.TW, p.TH, p.TN))) return rc;
+  if ((rc = make_w_map(&b_hi, wp_hi, p.n_taps, d->Cout, d->cin_pad, bn))) return rc;
+  a_lo = a_hi; b_lo = b_hi;
+  if (passes == 3) {
+    if ((rc = make_act_map(&a_lo, x_lo, d->N, d->H, d->W, d->Cin, d->x_cstride, split, p.TW, p.TH, p.TN))) return rc;
+    if ((rc = make_w_map(&b_lo, wp_lo, p.n_taps, d->Cout, d->cin_pad, bn))) return rc;
+  }
+  dim3 grid(p.tiles_w * p.tiles_h * ceil_div(d->N, p.TN), ceil_div(d->Cout, bn));
+  return dispatch_fwd(bn, passes, a_hi, a_lo, b_hi, b_lo, p, grid, st);
+}
+
+int conv_tc_dgrad(const immb_conv_desc* d, const float* dy_hi, const float* dy_lo, const float* wh_hi,
+                  const float* wh_lo, float* dx, cudaStream_t st) {
+  const int passes = d->precision == IMMB_PREC_TF32 ? 1 : 3;
+  const int ncols = d->cin_pad;
+  const int bn = pick_bn(ncols);
+  const int classes = d->stride == 1 ? 1 : 4;
+  for (int cls = 0; cls < classes; ++cls) {
+    const int phh = cls >> 1, pww = cls & 1;
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.PH = d->H / d->stride; p.PW = d->W / d->stride;
+    if (!pick_tile(p.PH, p.PW, d->N, &p.TW, &p.TH, &p.TN)) return set_error(IMMB_ERR_UNSUPPORTED, "conv_tc_dgrad: tile");
+    p.tiles_w = p.PW / p.TW; p.tiles_h = p.PH / p.TH;
+    p.kchunks = d->Cout / 32;
+    int nt = 0;
+    for (int r = 0; r < d->kh; ++r)
+      for (int s = 0; s < d->kw; ++s) {
+        int eh = phh + d->pad_t - r, ew = pww + d->pad_l - s;      // dy index = tile index + e/stride
+        if (d->stride == 2 && ((eh & 1) || (ew & 1))) continue;
+        TapEntry& t = p.taps[nt++];
+        t.b_tap = r * d->kw + s; t.dc = 0; t.hp = 0;
+        t.dh = d->stride == 1 ? eh : floordiv(eh, 2);
+        t.dw = d->stride == 1 ? ew : floordiv(ew, 2);
+      }
+    p.n_taps = nt;
+    p.out_hi = dx; p.out_lo = nullptr; p.bias = nullptr; p.relu = 0;
+    p.N = d->N; p.OH = d->H; p.OW = d->W; p.ocs = d->x_cstride;
+    p.out_mul = d->stride; p.out_add_h = phh; p.out_add_w = pww; p.n_cols = ncols;
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    int rc;
+    if ((rc = make_act_map(&a_hi, dy_hi, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, p.TW, p.TH, p.TN))) return rc;
+    if ((rc = make_w_map(&b_hi, wh_hi, d->kh * d->kw, d->cin_pad, d->Cout, bn))) return rc;
+    a_lo = a_hi; b_lo = b_hi;
+    if (passes == 3) {
+      if ((rc = make_act_map(&a_lo, dy_lo, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, p.TW, p.TH, p.TN))) return rc;
+      if ((rc = make_w_map(&b_lo, wh_lo, d->kh * d->kw, d->cin_pad, d->Cout, bn))) return rc;
+    }
+    dim3 grid(p.tiles_w * p.tiles_h * ceil_div(d->N, p.TN), ceil_div(ncols, bn));
+    if ((rc = dispatch_fwd(bn, passes, a_hi, a_lo, b_hi, b_lo, p, grid, st))) return rc;
+  }
+  return IMMB_OK;
+}
+
 size_t conv_tc_wgrad_workspace(const immb_conv_desc*) { return 0; }
-int conv_tc_wgrad(const immb_conv_desc*, const float*, const float*, const float*, const float*, float*, void*,
-                  size_t, cudaStream_t) { return set_error(IMMB_ERR_UNSUPPORTED, "tc engine not built"); }
+
+static constexpr CUtensorMapSwizzle kSwzMN = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+
+template <int BN, int PASSES>
+static int launch_wg(const CUtensorMap& x_hi, const CUtensorMap& x_lo, const CUtensorMap& y_hi,
+                     const CUtensorMap& y_lo, const WgParams& p, dim3 grid, cudaStream_t st) {
+  constexpr int STAGES = PASSES == 3 ? (BN <= 64 ? 4 : 3) : (BN <= 64 ? 6 : 4);
+  using Cfg = WgCfg<BN, PASSES, STAGES>;
+  auto kern = conv_tc_wgrad_kernel<BN, PASSES, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "conv_tc_wgrad smem attr: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  kern<<<grid, 192, Cfg::SMEM_BYTES, st>>>(x_hi, x_lo, y_hi, y_lo, p);
+  return check_launch("conv_tc_wgrad_kernel");
+}
+
+int conv_tc_wgrad(const immb_conv_desc* d, const float* x_hi, const float* x_lo, const float* dy_hi,
+                  const float* dy_lo, float* dw, void*, size_t, cudaStream_t st) {
+  const int passes = d->precision == IMMB_PREC_TF32 ? 1 : 3;
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  p.PW = d->Wo >= 16 ? 16 : 8; p.PH = 32 / p.PW;
+  p.tiles_w = d->Wo / p.PW; p.tiles_h = d->Ho / p.PH; p.N = d->N;
+  p.total_tiles = p.tiles_w * p.tiles_h * d->N;
+  p.n_taps = d->kh * d->kw;
+  p.cit = d->cin_pad >= 128 ? 128 : (d->cin_pad >= 64 ? 64 : 32);
+  if (d->cin_pad < 128 && d->cin_pad != p.cit) p.cit = 32;       // e.g. cin_pad 96 -> 32-channel groups
+  p.taps_per_tile = 128 / p.cit;
+  p.m_tiles_per_group = p.cit == 128 ? ceil_div(d->cin_pad, 128) : ceil_div(d->cin_pad, p.cit);
+  for (int r = 0; r < d->kh; ++r)
+    for (int s = 0; s < d->kw; ++s) {
+      TapEntry& t = p.taps[r * d->kw + s];
+      t.b_tap = r * d->kw + s;
+      int th = r - d->pad_t, tw = s - d->pad_l;
+      if (d->stride == 1) { t.dc = 0; t.dw = tw; t.hp = 0; t.dh = th; }
+      else { t.dh = floordiv(th, 2); t.hp = pymod(th, 2); t.dw = floordiv(tw, 2); t.dc = pymod(tw, 2) * d->Cin; }
+    }
+  p.dw = dw; p.Cin = d->Cin; p.Cout = d->Cout;
+  int m_tiles;
+  if (p.cit == 128) m_tiles = p.n_taps * p.m_tiles_per_group;
+  else {
+    if (d->cin_pad != p.cit) return set_error(IMMB_ERR_UNSUPPORTED, "conv_tc_wgrad: cin_pad %d", d->cin_pad);
+    m_tiles = ceil_div(p.n_taps, p.taps_per_tile);
+  }
+  const int bn = d->Cout % 128 == 0 ? 128 : (d->Cout % 64 == 0 ? 64 : 32);
+  const int n_tiles = d->Cout / bn;
+  int splits = ceil_div(kNumSMs * 2, m_tiles * n_tiles);
+  if (splits > p.total_tiles) splits = p.total_tiles;
+  if (splits < 1) splits = 1;
+  p.tiles_per_split = ceil_div(p.total_tiles, splits);
+  splits = ceil_div(p.total_tiles, p.tiles_per_split);
+  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)p.n_taps * d->Cin * d->Cout, st);
+  if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "wgrad memset: %s", cudaGetErrorString(e));
+  CUtensorMap mx_hi, mx_lo, my_hi, my_lo;
+  int rc;
+  const bool split = d->stride == 2;
+  if ((rc = make_act_map(&mx_hi, x_hi, d->N, d->H, d->W, d->Cin, d->x_cstride, split, p.PW, p.PH, 1, kSwzMN))) return rc;
+  if ((rc = make_act_map(&my_hi, dy_hi, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, p.PW, p.PH, 1, kSwzMN))) return rc;
+  mx_lo = mx_hi; my_lo = my_hi;
+  if (passes == 3) {
+    if ((rc = make_act_map(&mx_lo, x_lo, d->N, d->H, d->W, d->Cin, d->x_cstride, split, p.PW, p.PH, 1, kSwzMN))) return rc;
+    if ((rc = make_act_map(&my_lo, dy_lo, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, p.PW, p.PH, 1, kSwzMN))) return rc;
+  }
+  dim3 grid(m_tiles, n_tiles, splits);
+#define IMMB_WG(BN_)                                                                            \
+  if (bn == BN_)                                                                                \
+    return passes == 3 ? launch_wg<BN_, 3>(mx_hi, mx_lo, my_hi, my_lo, p, grid, st)             \
+                       : launch_wg<BN_, 1>(mx_hi, mx_lo, my_hi, my_lo, p, grid, st);
+  IMMB_WG(32)
+  IMMB_WG(64)
+  IMMB_WG(128)
+#undef IMMB_WG
+  return set_error(IMMB_ERR_INVALID, "conv_tc_wgrad: bn");
+}
+
 }  // namespace immb

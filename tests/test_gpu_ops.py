@@ -83,6 +83,73 @@ def test_conv_fwd_dgrad_wgrad_simt(case):
   assert float((yh.cpu() - O.round_tf32(yh.cpu())).abs().max()) == 0.0      # hi plane is exactly TF32
 
 
+TC_CASES = [
+  # N, H, W, Cin, Cout, k, stride, xcs
+  (2, 16, 16, 32, 32, 3, 1, None),
+  (1, 32, 32, 64, 128, 3, 1, None),
+  (2, 16, 16, 64, 64, 1, 1, None),
+  (2, 32, 32, 32, 64, 3, 2, None),       # stride 2: parity-split TMA view, 4-class dgrad
+  (2, 64, 64, 64, 128, 3, 2, None),
+  (2, 16, 16, 266, 256, 3, 1, 288),      # renderer conv_1: 266 logical channels, stride 288, BN=96 dgrad
+  (4, 8, 8, 128, 128, 3, 1, None),       # 8x8 maps: 2 images per 128-pixel tile
+  (3, 8, 8, 128, 64, 3, 1, None),        # odd image count -> predicated tile overhang
+  (1, 128, 128, 32, 32, 3, 1, None),     # encoder conv_2 shape
+  (1, 32, 32, 64, 32, 3, 1, None),
+  (2, 16, 16, 512, 512, 3, 1, None),     # VGG conv4_x
+]
+
+
+@pytest.mark.parametrize('precision', [_lib.PREC_TF32X3, _lib.PREC_TF32])
+@pytest.mark.parametrize('case', TC_CASES)
+def test_conv_tcgen05_engine(case, precision):
+  """tcgen05/TMA engine vs the fp64 oracle.  3xTF32 must be at fp32 accuracy; single-pass TF32 at ~1e-3."""
+  N, H, W, Cin, Cout, k, stride, xcs = case
+  g = torch.Generator().manual_seed(sum(case[:7]))
+  xcs_ = xcs or Cin
+  x = torch.randn(N, H, W, xcs_, generator=g)
+  x[..., Cin:] = 0
+  w = torch.randn(k, k, Cin, Cout, generator=g) * 0.1
+  b = torch.randn(Cout, generator=g)
+  d = conv_desc(N, H, W, Cin, Cout, k, stride, xcs, engine=_lib.ENGINE_TC, precision=precision)
+  assert [_lib.lib().immb_conv_engine_for(d, op) for op in range(3)] == [_lib.ENGINE_TC] * 3
+  tol = 2e-5 if precision == _lib.PREC_TF32X3 else 3e-3
+  xd = x.double()[..., :Cin].clone().requires_grad_(True)
+  wd = w.double().clone().requires_grad_(True)
+  y_ref = O.conv2d_same(xd, wd, b.double(), stride)
+  gy = torch.randn(y_ref.shape, generator=g)
+  y_ref.backward(gy.double())
+  dev = 'cuda'
+  taps, cp = k * k, d.cin_pad
+  wp_h, wp_l = torch.empty(taps, Cout, cp, device=dev), torch.empty(taps, Cout, cp, device=dev)
+  wh_h, wh_l = torch.empty(taps, cp, Cout, device=dev), torch.empty(taps, cp, Cout, device=dev)
+  call('immb_pack_weights', w.to(dev), k, k, Cin, Cout, cp, wp_h, wp_l, wh_h, wh_l, ST())
+  xh, xl = split(x)
+  xh, xl = xh.to(dev), xl.to(dev)
+  y = torch.full((N, d.Ho, d.Wo, Cout), float('nan'), device=dev)
+  call('immb_conv2d_fwd', d, xh, xl, None, wp_h, wp_l, b.to(dev), y, None, ST())
+  torch.cuda.synchronize()
+  assert rel_err(y, y_ref) < tol, ('fwd', rel_err(y, y_ref))
+  gh, gl = split(gy)
+  gh, gl = gh.to(dev), gl.to(dev)
+  dx = torch.full((N, H, W, xcs_), float('nan'), device=dev)
+  call('immb_conv2d_dgrad', d, gh, gl, None, wh_h, wh_l, dx, ST())
+  torch.cuda.synchronize()
+  assert rel_err(dx[..., :Cin], xd.grad) < tol, ('dgrad', rel_err(dx[..., :Cin], xd.grad))
+  if xcs_ > Cin:
+    assert float(dx[..., Cin:].abs().max()) == 0.0       # padded channels come out as exact zeros
+  dw = torch.full((k, k, Cin, Cout), float('nan'), device=dev)
+  ws = torch.empty(16, dtype=torch.uint8, device=dev)
+  call('immb_conv2d_wgrad', d, xh, xl, gh, gl, dw, ws, 16, ST())
+  torch.cuda.synchronize()
+  assert rel_err(dw, wd.grad) < tol, ('wgrad', rel_err(dw, wd.grad))
+  # fused bias+ReLU epilogue writing split planes (VGG path)
+  d2 = conv_desc(N, H, W, Cin, Cout, k, stride, xcs, engine=_lib.ENGINE_TC, epilogue=_lib.EPI_BIAS_RELU,
+                 precision=precision)
+  yh, yl = torch.empty_like(y), torch.empty_like(y)
+  call('immb_conv2d_fwd', d2, xh, xl, None, wp_h, wp_l, b.to(dev), yh, yl, ST())
+  assert rel_err(yh + yl, torch.relu(y_ref)) < tol
+
+
 def test_pack_weights_layouts():
   w = torch.randn(3, 3, 5, 7)
   wp_h, wp_l = torch.empty(9, 7, 32, device='cuda'), torch.empty(9, 7, 32, device='cuda')
