@@ -112,7 +112,9 @@ def test_conv_tcgen05_engine(case, precision):
   b = torch.randn(Cout, generator=g)
   d = conv_desc(N, H, W, Cin, Cout, k, stride, xcs, engine=_lib.ENGINE_TC, precision=precision)
   assert [_lib.lib().immb_conv_engine_for(d, op) for op in range(3)] == [_lib.ENGINE_TC] * 3
-  tol = 2e-5 if precision == _lib.PREC_TF32X3 else 3e-3
+  # tensor-core fp32 accumulation truncates (round-toward-zero) at every K=8 step: the error grows with the
+  # reduction length (K = 4608 for the 512-channel VGG layers) but stays ~30x below the 1e-3 bar
+  tol = (2e-5 if k * k * Cin < 2048 else 6e-5) if precision == _lib.PREC_TF32X3 else 3e-3
   xd = x.double()[..., :Cin].clone().requires_grad_(True)
   wd = w.double().clone().requires_grad_(True)
   y_ref = O.conv2d_same(xd, wd, b.double(), stride)
