@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libimm_b200.so')
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
 PREC_TF32X3, PREC_TF32 = 0, 1
 EPI_BIAS, EPI_BIAS_RELU = 0, 1
+XLAYOUT_NHWC, XLAYOUT_ROWWIN4 = 0, 1
 
 
 class ImmbError(RuntimeError):
@@ -22,7 +23,7 @@ class ImmbError(RuntimeError):
 class ConvDesc(ctypes.Structure):
   _fields_ = [(n, ctypes.c_int32) for n in
               ('N', 'H', 'W', 'Cin', 'Cout', 'kh', 'kw', 'stride', 'Ho', 'Wo', 'pad_t', 'pad_l',
-               'x_cstride', 'y_cstride', 'cin_pad', 'epilogue', 'precision', 'engine')]
+               'x_cstride', 'y_cstride', 'cin_pad', 'epilogue', 'precision', 'engine', 'x_layout')]
 
 
 _P, _I, _L, _F, _Z = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
@@ -35,7 +36,7 @@ _SIGS = {
   'immb_conv2d_dgrad': [_D, _P, _P, _P, _P, _P, _P, _P],
   'immb_conv2d_wgrad_workspace': [_D],
   'immb_conv2d_wgrad': [_D, _P, _P, _P, _P, _P, _P, _Z, _P],
-  'immb_pack_weights': [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+  'immb_pack_weights': [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
   'immb_split_planes': [_P, _P, _P, _L, _P],
   'immb_bn_stats': [_P, _L, _I, _I, _P, _P],
   'immb_bn_finalize': [_P, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P],
@@ -48,13 +49,15 @@ _SIGS = {
   'immb_softargmax_gauss_fwd': [_P, _I, _I, _I, _I, _F, _P, _P, _P, _I, _P, _P, _I, _I, _P],
   'immb_softargmax_gauss_bwd': [_P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _F, _P, _I, _P],
   'immb_gaussian_maps': [_P, _I, _I, _I, _F, _P, _P],
-  'immb_vgg_prologue': [_P, _P, _I, _I, _I, _P, _P, _P],
+  'immb_vgg_prologue': [_P, _P, _I, _I, _I, _I, _P, _P, _P],
+  'immb_stage_image_rowwin': [_P, _I, _I, _I, _P, _P, _P],
+  'immb_pack_weights_rowwin': [_P, _I, _P, _P, _P],
   'immb_maxpool2x2_fwd': [_P, _P, _I, _I, _I, _I, _P, _P, _P],
   'immb_maxpool2x2_bwd': [_P, _P, _P, _I, _I, _I, _I, _P, _P],
   'immb_perceptual_level_sum': [_P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P, _P],
   'immb_perceptual_finalize': [_P, _P, _I, _P, _I, _P, _P, _P, _P],
   'immb_vgg_bwd_combine': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P],
-  'immb_pred_grad': [_P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P],
+  'immb_pred_grad': [_P, _P, _I, _P, _P, _P, _I, _I, _I, _P, _P, _P],
   'immb_resize_ac_fwd': [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P],
   'immb_resize_ac_bwd': [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
   'immb_adam_norms': [_P, _P, _L, _P, _P, _P, _I, _P, _F, _P, _P, _P],
@@ -102,8 +105,23 @@ def stream_ptr():
   return torch.cuda.current_stream().cuda_stream
 
 
+PROFILE = None          # development aid: when a list, every call is timed with CUDA events -> (name, tag, ms)
+TAG = ''
+
+
 def call(name, *args):
   """Calls a C-ABI function; tensors are converted to raw pointers; raises ImmbError on failure."""
+  if PROFILE is not None and name not in _RESTYPES:
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = _call(name, *args)
+    e1.record()
+    PROFILE.append((name, TAG, e0, e1))
+    return rc
+  return _call(name, *args)
+
+
+def _call(name, *args):
   l = lib()
   conv = []
   for a in args:

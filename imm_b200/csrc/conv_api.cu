@@ -27,6 +27,8 @@ static int validate(const immb_conv_desc* d) {
                "conv: Ho/Wo must be ceil(H/stride), ceil(W/stride) (TF SAME)");
   IMMB_REQUIRE(d->x_cstride >= d->Cin && d->y_cstride >= d->Cout, "conv: channel strides too small");
   IMMB_REQUIRE(d->pad_t >= 0 && d->pad_l >= 0 && d->pad_t < d->kh && d->pad_l < d->kw, "conv: bad padding");
+  IMMB_REQUIRE(d->x_layout == IMMB_XLAYOUT_NHWC || d->engine != IMMB_ENGINE_SIMT,
+               "conv: the SIMT engine reads plain NHWC only");
   return IMMB_OK;
 }
 
@@ -39,6 +41,8 @@ static int pick_engine(const immb_conv_desc* d, int op, int* engine) {
     *engine = IMMB_ENGINE_SIMT;
   } else {
     *engine = ok ? IMMB_ENGINE_TC : IMMB_ENGINE_SIMT;
+    if (!ok && d->x_layout != IMMB_XLAYOUT_NHWC)
+      return set_error(IMMB_ERR_UNSUPPORTED, "conv: x_layout ROWWIN4 needs the tcgen05 engine");
   }
   return IMMB_OK;
 }

@@ -44,6 +44,7 @@ struct TcParams {
   int OH, OW, ocs;            // output tensor
   int out_mul, out_add_h, out_add_w;
   int n_cols;                 // valid output channels
+  int n_store;                // channels written (n_cols rounded up to 4, <= ocs; the excess is exact zeros)
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -168,7 +169,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
       if (col0 >= p.n_cols) continue;
       if (p.bias) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + col0 + j);
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.n_cols) v[j] += __ldg(p.bias + col0 + j);
       }
       if (p.relu) {
 #pragma unroll
@@ -179,6 +181,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
         float* ol = p.out_lo + pix * p.ocs + col0;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
+          if (col0 + j >= p.n_store) break;
           float4 hi4, lo4;
           split_tf32(v[j], hi4.x, lo4.x);
           split_tf32(v[j + 1], hi4.y, lo4.y);
@@ -189,8 +192,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
+        for (int j = 0; j < 32; j += 4) {
+          if (col0 + j >= p.n_store) break;
           *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
       }
     }
   }
@@ -222,6 +227,7 @@ struct WgParams {
   TapEntry taps[kMaxTaps];    // dc, dw, hp, dh of the X box for each tap (b_tap unused)
   float* dw;                  // [taps][Cin][Cout]
   int Cin, Cout;
+  int rowwin;                 // 1: rows are (filter row r, j = s*4+c) of the 7x7x3 first layer
 };
 
 template <int BN, int PASSES, int STAGES>
@@ -348,7 +354,12 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_c
     const int tl = m / p.cit;
     const int tap = tap0 + tl;
     const int ci = ci0 + (m - tl * p.cit);
-    const bool row_ok = (tap < p.n_taps) && (ci < p.Cin);
+    bool row_ok = (tap < p.n_taps) && (ci < p.Cin);
+    size_t row_off = ((size_t)tap * p.Cin + ci) * p.Cout;
+    if (p.rowwin) {      // dw[r][s][c][co] with j = s*4 + c
+      row_ok = (tap < 7) && (ci < 28) && ((ci & 3) < 3);
+      row_off = ((size_t)(tap * 7 + (ci >> 2)) * 3 + (ci & 3)) * p.Cout;
+    }
     mbar_wait(tmem_full, 0);
     tc_fence_after();
 #pragma unroll 1
@@ -358,9 +369,10 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_c
       if (!row_ok) continue;
       const int col0 = n_off + c0;
       if (col0 >= p.Cout) continue;
-      float* o = p.dw + ((size_t)tap * p.Cin + ci) * p.Cout + col0;
+      float* o = p.dw + row_off + col0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) atomicAdd(o + j, v[j]);
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.Cout) atomicAdd(o + j, v[j]);
     }
   }
   tc_fence_before();
@@ -419,6 +431,18 @@ static int make_act_map(CUtensorMap* m, const float* base, int N, int H, int W, 
   return make_map(m, base, 5, dims, str, box, swz);
 }
 
+// Row-window view of the staged first-layer image [N,H,W+8,4]: element (j, w, 0, h, n) = x4[n, h, w + j/4, j%4],
+// i.e. the 8 pixels x 4 channels starting at padded column w are ONE 128-byte row (overlapping windows: the w
+// stride is 16 bytes).  Filter row r of the 7x7 conv is then a single K = 32 chunk (28 real taps + 4 zero weights).
+static int make_rowwin_map(CUtensorMap* m, const float* base, int N, int H, int W, int box_w, int box_h, int box_n,
+                           CUtensorMapSwizzle swz) {
+  const uint64_t Wp = (uint64_t)W + 8;
+  uint64_t dims[5] = {32, (uint64_t)W, 1, (uint64_t)H, (uint64_t)N};
+  uint64_t str[4] = {16, Wp * 16, Wp * 16, (uint64_t)H * Wp * 16};
+  uint32_t box[5] = {32, (uint32_t)box_w, 1, (uint32_t)box_h, (uint32_t)box_n};
+  return make_map(m, base, 5, dims, str, box, swz);
+}
+
 // 3-D weight view (k, n, tap) of [taps][Nn][Kd] with box (32, BN, 1)
 static int make_w_map(CUtensorMap* m, const float* base, int taps, int Nn, int Kd, int bn) {
   uint64_t dims[3] = {(uint64_t)Kd, (uint64_t)Nn, (uint64_t)taps};
@@ -438,16 +462,22 @@ static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b
 static int pymod(int a, int b) { return a - floordiv(a, b) * b; }
 
 bool conv_tc_eligible(const immb_conv_desc* d, int op) {
+  int TW, TH, TN;
+  if (d->x_layout == IMMB_XLAYOUT_ROWWIN4) {
+    // first encoder layer: 7x7, Cin = 3, stride 1 on the staged [N,H,W+8,4] image (no dgrad: the input is data)
+    if (d->kh != 7 || d->kw != 7 || d->Cin != 3 || d->stride != 1 || op == 1) return false;
+    if (d->Cout % 32 || d->Cout > 128 || d->y_cstride != d->Cout) return false;
+    return d->W % 16 == 0 && d->H % 8 == 0;
+  }
   if (d->kh != d->kw || (d->kh != 1 && d->kh != 3)) return false;
   if (d->stride == 2 && (d->kh != 3 || (d->H % 2) || (d->W % 2) || d->x_cstride != d->Cin || d->Cin % 32)) return false;
-  if (d->Cin < 32 || d->Cout < 32 || d->Cout % 32) return false;
-  if (d->x_cstride % 4 || d->y_cstride % 4 || d->y_cstride != d->Cout) return false;
+  if (d->Cin < 1 || d->Cout < 1) return false;
+  if (d->x_cstride % 4 || d->y_cstride % 4 || d->y_cstride < d->Cout) return false;
+  if (d->Cout > 128 && d->Cout % 32) return false;
   if (d->cin_pad % 32 || d->cin_pad < d->Cin) return false;
-  int TW, TH, TN;
   if (op == 0) {
     return pick_tile(d->Ho, d->Wo, d->N, &TW, &TH, &TN);
   } else if (op == 1) {
-    if (d->x_cstride < d->cin_pad) return false;      // dx receives cin_pad channels
     if (d->stride == 1) return pick_tile(d->H, d->W, d->N, &TW, &TH, &TN);
     return pick_tile(d->H / 2, d->W / 2, d->N, &TW, &TH, &TN);
   } else {
@@ -482,6 +512,7 @@ static int dispatch_fwd(int bn, int passes, const CUtensorMap& a_hi, const CUten
   if (bn == BN_)                                                                               \
     return passes == 3 ? launch_fwd<BN_, 3>(a_hi, a_lo, b_hi, b_lo, p, grid, st)               \
                        : launch_fwd<BN_, 1>(a_hi, a_lo, b_hi, b_lo, p, grid, st);
+  IMMB_CASE(16)
   IMMB_CASE(32)
   IMMB_CASE(64)
   IMMB_CASE(96)
@@ -494,7 +525,12 @@ static int pick_bn(int ncols) {
   if (ncols % 128 == 0) return 128;
   if (ncols % 96 == 0) return 96;
   if (ncols % 64 == 0) return 64;
-  return 32;
+  if (ncols % 32 == 0) return 32;
+  if (ncols <= 16) return 16;         // small / ragged channel counts: one tile, TMA zero-fills the missing rows
+  if (ncols <= 32) return 32;
+  if (ncols <= 64) return 64;
+  if (ncols <= 96) return 96;
+  return 128;
 }
 
 int conv_tc_fwd(const immb_conv_desc* d, const float* x_hi, const float* x_lo, const float* wp_hi,
@@ -504,28 +540,40 @@ int conv_tc_fwd(const immb_conv_desc* d, const float* x_hi, const float* x_lo, c
   memset(&p, 0, sizeof(p));
   if (!pick_tile(d->Ho, d->Wo, d->N, &p.TW, &p.TH, &p.TN)) return set_error(IMMB_ERR_UNSUPPORTED, "conv_tc_fwd: tile");
   p.tiles_w = d->Wo / p.TW; p.tiles_h = d->Ho / p.TH;
-  p.n_taps = d->kh * d->kw; p.kchunks = d->cin_pad / 32;
-  for (int r = 0; r < d->kh; ++r)
-    for (int s = 0; s < d->kw; ++s) {
-      TapEntry& t = p.taps[r * d->kw + s];
-      t.b_tap = r * d->kw + s;
-      int th = r - d->pad_t, tw = s - d->pad_l;
-      if (d->stride == 1) { t.dc = 0; t.dw = tw; t.hp = 0; t.dh = th; }
-      else { t.dh = floordiv(th, 2); t.hp = pymod(th, 2); t.dw = floordiv(tw, 2); t.dc = pymod(tw, 2) * d->Cin; }
-    }
+  const bool rowwin = d->x_layout == IMMB_XLAYOUT_ROWWIN4;
+  if (rowwin) {
+    p.n_taps = 7; p.kchunks = 1;
+    for (int r = 0; r < 7; ++r) { TapEntry& t = p.taps[r]; t.b_tap = r; t.dc = 0; t.dw = 0; t.hp = 0; t.dh = r - d->pad_t; }
+  } else {
+    p.n_taps = d->kh * d->kw; p.kchunks = d->cin_pad / 32;
+    for (int r = 0; r < d->kh; ++r)
+      for (int s = 0; s < d->kw; ++s) {
+        TapEntry& t = p.taps[r * d->kw + s];
+        t.b_tap = r * d->kw + s;
+        int th = r - d->pad_t, tw = s - d->pad_l;
+        if (d->stride == 1) { t.dc = 0; t.dw = tw; t.hp = 0; t.dh = th; }
+        else { t.dh = floordiv(th, 2); t.hp = pymod(th, 2); t.dw = floordiv(tw, 2); t.dc = pymod(tw, 2) * d->Cin; }
+      }
+  }
   p.out_hi = y_hi; p.out_lo = y_lo; p.bias = bias; p.relu = d->epilogue == IMMB_EPI_BIAS_RELU;
   p.N = d->N; p.PH = d->Ho; p.PW = d->Wo; p.OH = d->Ho; p.OW = d->Wo; p.ocs = d->y_cstride;
   p.out_mul = 1; p.out_add_h = 0; p.out_add_w = 0; p.n_cols = d->Cout;
+  p.n_store = (d->Cout + 3) / 4 * 4;
   const int bn = pick_bn(d->Cout);
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
   int rc;
   const bool split = d->stride == 2;
-  if ((rc = make_act_map(&a_hi, x_hi, d->N, d->H, d->W, d->Cin, d->x_cstride, split, p.TW, p.TH, p.TN))) return rc;
-  if ((rc = make_w_map(&b_hi, wp_hi, p.n_taps, d->Cout, d->cin_pad, bn))) return rc;
+  const int kd = rowwin ? 32 : d->cin_pad;
+  auto amap = [&](CUtensorMap* m, const float* base) {
+    return rowwin ? make_rowwin_map(m, base, d->N, d->H, d->W, p.TW, p.TH, p.TN, CU_TENSOR_MAP_SWIZZLE_128B)
+                  : make_act_map(m, base, d->N, d->H, d->W, d->Cin, d->x_cstride, split, p.TW, p.TH, p.TN);
+  };
+  if ((rc = amap(&a_hi, x_hi))) return rc;
+  if ((rc = make_w_map(&b_hi, wp_hi, p.n_taps, d->Cout, kd, bn))) return rc;
   a_lo = a_hi; b_lo = b_hi;
   if (passes == 3) {
-    if ((rc = make_act_map(&a_lo, x_lo, d->N, d->H, d->W, d->Cin, d->x_cstride, split, p.TW, p.TH, p.TN))) return rc;
-    if ((rc = make_w_map(&b_lo, wp_lo, p.n_taps, d->Cout, d->cin_pad, bn))) return rc;
+    if ((rc = amap(&a_lo, x_lo))) return rc;
+    if ((rc = make_w_map(&b_lo, wp_lo, p.n_taps, d->Cout, kd, bn))) return rc;
   }
   dim3 grid(p.tiles_w * p.tiles_h * ceil_div(d->N, p.TN), ceil_div(d->Cout, bn));
   return dispatch_fwd(bn, passes, a_hi, a_lo, b_hi, b_lo, p, grid, st);
@@ -534,7 +582,7 @@ int conv_tc_fwd(const immb_conv_desc* d, const float* x_hi, const float* x_lo, c
 int conv_tc_dgrad(const immb_conv_desc* d, const float* dy_hi, const float* dy_lo, const float* wh_hi,
                   const float* wh_lo, float* dx, cudaStream_t st) {
   const int passes = d->precision == IMMB_PREC_TF32 ? 1 : 3;
-  const int ncols = d->cin_pad;
+  const int ncols = d->cin_pad < d->x_cstride ? d->cin_pad : d->x_cstride;   // channels of dx that get written
   const int bn = pick_bn(ncols);
   const int classes = d->stride == 1 ? 1 : 4;
   for (int cls = 0; cls < classes; ++cls) {
@@ -544,7 +592,7 @@ int conv_tc_dgrad(const immb_conv_desc* d, const float* dy_hi, const float* dy_l
     p.PH = d->H / d->stride; p.PW = d->W / d->stride;
     if (!pick_tile(p.PH, p.PW, d->N, &p.TW, &p.TH, &p.TN)) return set_error(IMMB_ERR_UNSUPPORTED, "conv_tc_dgrad: tile");
     p.tiles_w = p.PW / p.TW; p.tiles_h = p.PH / p.TH;
-    p.kchunks = d->Cout / 32;
+    p.kchunks = ceil_div(d->y_cstride, 32);
     int nt = 0;
     for (int r = 0; r < d->kh; ++r)
       for (int s = 0; s < d->kw; ++s) {
@@ -558,15 +606,15 @@ int conv_tc_dgrad(const immb_conv_desc* d, const float* dy_hi, const float* dy_l
     p.n_taps = nt;
     p.out_hi = dx; p.out_lo = nullptr; p.bias = nullptr; p.relu = 0;
     p.N = d->N; p.OH = d->H; p.OW = d->W; p.ocs = d->x_cstride;
-    p.out_mul = d->stride; p.out_add_h = phh; p.out_add_w = pww; p.n_cols = ncols;
+    p.out_mul = d->stride; p.out_add_h = phh; p.out_add_w = pww; p.n_cols = ncols; p.n_store = ncols;
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     int rc;
     if ((rc = make_act_map(&a_hi, dy_hi, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, p.TW, p.TH, p.TN))) return rc;
-    if ((rc = make_w_map(&b_hi, wh_hi, d->kh * d->kw, d->cin_pad, d->Cout, bn))) return rc;
+    if ((rc = make_w_map(&b_hi, wh_hi, d->kh * d->kw, d->cin_pad, d->y_cstride, bn))) return rc;
     a_lo = a_hi; b_lo = b_hi;
     if (passes == 3) {
       if ((rc = make_act_map(&a_lo, dy_lo, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, p.TW, p.TH, p.TN))) return rc;
-      if ((rc = make_w_map(&b_lo, wh_lo, d->kh * d->kw, d->cin_pad, d->Cout, bn))) return rc;
+      if ((rc = make_w_map(&b_lo, wh_lo, d->kh * d->kw, d->cin_pad, d->y_cstride, bn))) return rc;
     }
     dim3 grid(p.tiles_w * p.tiles_h * ceil_div(d->N, p.TN), ceil_div(ncols, bn));
     if ((rc = dispatch_fwd(bn, passes, a_hi, a_lo, b_hi, b_lo, p, grid, st))) return rc;
@@ -602,43 +650,54 @@ int conv_tc_wgrad(const immb_conv_desc* d, const float* x_hi, const float* x_lo,
   p.PW = d->Wo >= 16 ? 16 : 8; p.PH = 32 / p.PW;
   p.tiles_w = d->Wo / p.PW; p.tiles_h = d->Ho / p.PH; p.N = d->N;
   p.total_tiles = p.tiles_w * p.tiles_h * d->N;
-  p.n_taps = d->kh * d->kw;
-  p.cit = d->cin_pad >= 128 ? 128 : (d->cin_pad >= 64 ? 64 : 32);
-  if (d->cin_pad < 128 && d->cin_pad != p.cit) p.cit = 32;       // e.g. cin_pad 96 -> 32-channel groups
+  const bool rowwin = d->x_layout == IMMB_XLAYOUT_ROWWIN4;
+  const int cin_pad = rowwin ? 32 : d->cin_pad;
+  p.rowwin = rowwin ? 1 : 0;
+  p.n_taps = rowwin ? 7 : d->kh * d->kw;
+  p.cit = cin_pad >= 128 ? 128 : (cin_pad >= 64 ? 64 : 32);
+  if (cin_pad < 128 && cin_pad != p.cit) p.cit = 32;       // e.g. cin_pad 96 -> 32-channel groups
   p.taps_per_tile = 128 / p.cit;
-  p.m_tiles_per_group = p.cit == 128 ? ceil_div(d->cin_pad, 128) : ceil_div(d->cin_pad, p.cit);
-  for (int r = 0; r < d->kh; ++r)
-    for (int s = 0; s < d->kw; ++s) {
-      TapEntry& t = p.taps[r * d->kw + s];
-      t.b_tap = r * d->kw + s;
-      int th = r - d->pad_t, tw = s - d->pad_l;
-      if (d->stride == 1) { t.dc = 0; t.dw = tw; t.hp = 0; t.dh = th; }
-      else { t.dh = floordiv(th, 2); t.hp = pymod(th, 2); t.dw = floordiv(tw, 2); t.dc = pymod(tw, 2) * d->Cin; }
-    }
+  p.m_tiles_per_group = p.cit == 128 ? ceil_div(cin_pad, 128) : ceil_div(cin_pad, p.cit);
+  if (rowwin) {
+    for (int r = 0; r < 7; ++r) { TapEntry& t = p.taps[r]; t.b_tap = r; t.dc = 0; t.dw = 0; t.hp = 0; t.dh = r - d->pad_t; }
+  } else {
+    for (int r = 0; r < d->kh; ++r)
+      for (int s = 0; s < d->kw; ++s) {
+        TapEntry& t = p.taps[r * d->kw + s];
+        t.b_tap = r * d->kw + s;
+        int th = r - d->pad_t, tw = s - d->pad_l;
+        if (d->stride == 1) { t.dc = 0; t.dw = tw; t.hp = 0; t.dh = th; }
+        else { t.dh = floordiv(th, 2); t.hp = pymod(th, 2); t.dw = floordiv(tw, 2); t.dc = pymod(tw, 2) * d->Cin; }
+      }
+  }
   p.dw = dw; p.Cin = d->Cin; p.Cout = d->Cout;
   int m_tiles;
   if (p.cit == 128) m_tiles = p.n_taps * p.m_tiles_per_group;
   else {
-    if (d->cin_pad != p.cit) return set_error(IMMB_ERR_UNSUPPORTED, "conv_tc_wgrad: cin_pad %d", d->cin_pad);
+    if (cin_pad != p.cit) return set_error(IMMB_ERR_UNSUPPORTED, "conv_tc_wgrad: cin_pad %d", cin_pad);
     m_tiles = ceil_div(p.n_taps, p.taps_per_tile);
   }
   const int bn = d->Cout % 128 == 0 ? 128 : (d->Cout % 64 == 0 ? 64 : 32);
-  const int n_tiles = d->Cout / bn;
+  const int n_tiles = ceil_div(d->Cout, bn);
   int splits = ceil_div(kNumSMs * 2, m_tiles * n_tiles);
   if (splits > p.total_tiles) splits = p.total_tiles;
   if (splits < 1) splits = 1;
   p.tiles_per_split = ceil_div(p.total_tiles, splits);
   splits = ceil_div(p.total_tiles, p.tiles_per_split);
-  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)p.n_taps * d->Cin * d->Cout, st);
+  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->kh * d->kw * d->Cin * d->Cout, st);
   if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "wgrad memset: %s", cudaGetErrorString(e));
   CUtensorMap mx_hi, mx_lo, my_hi, my_lo;
   int rc;
   const bool split = d->stride == 2;
-  if ((rc = make_act_map(&mx_hi, x_hi, d->N, d->H, d->W, d->Cin, d->x_cstride, split, p.PW, p.PH, 1, kSwzMN))) return rc;
+  auto xmap = [&](CUtensorMap* m, const float* base) {
+    return rowwin ? make_rowwin_map(m, base, d->N, d->H, d->W, p.PW, p.PH, 1, kSwzMN)
+                  : make_act_map(m, base, d->N, d->H, d->W, d->Cin, d->x_cstride, split, p.PW, p.PH, 1, kSwzMN);
+  };
+  if ((rc = xmap(&mx_hi, x_hi))) return rc;
   if ((rc = make_act_map(&my_hi, dy_hi, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, p.PW, p.PH, 1, kSwzMN))) return rc;
   mx_lo = mx_hi; my_lo = my_hi;
   if (passes == 3) {
-    if ((rc = make_act_map(&mx_lo, x_lo, d->N, d->H, d->W, d->Cin, d->x_cstride, split, p.PW, p.PH, 1, kSwzMN))) return rc;
+    if ((rc = xmap(&mx_lo, x_lo))) return rc;
     if ((rc = make_act_map(&my_lo, dy_lo, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, p.PW, p.PH, 1, kSwzMN))) return rc;
   }
   dim3 grid(m_tiles, n_tiles, splits);

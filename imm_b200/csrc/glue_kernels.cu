@@ -342,26 +342,73 @@ __global__ void gaussian_maps_kernel(const float* __restrict__ mu, int B, int K,
 // =====================================================================================================
 // perceptual-loss glue
 // =====================================================================================================
+__device__ __forceinline__ float gray_norm(const float* __restrict__ p) {
+  float v = (__ldg(p) + __ldg(p + 1) + __ldg(p + 2)) / 3.0f;
+  v = v / 255.0f;
+  return v - (114.451f / 255.0f);
+}
+
 __global__ void vgg_prologue_kernel(const float* __restrict__ gt, const float* __restrict__ pred, int pcs,
                                     int B, int R, float* out_hi, float* out_lo) {
   int64_t per = (int64_t)B * R * R;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * per;
        i += (int64_t)gridDim.x * blockDim.x) {
-    float r, g, b;
-    if (i < per) {
-      r = __ldg(gt + i * 3);
-      g = __ldg(gt + i * 3 + 1);
-      b = __ldg(gt + i * 3 + 2);
-    } else {
-      int64_t j = i - per;
-      r = __ldg(pred + j * pcs);
-      g = __ldg(pred + j * pcs + 1);
-      b = __ldg(pred + j * pcs + 2);
-    }
-    float v = (r + g + b) / 3.0f;
-    v = v / 255.0f;
-    v = v - (114.451f / 255.0f);
+    float v = i < per ? gray_norm(gt + i * 3) : gray_norm(pred + (i - per) * pcs);
     store_split(out_hi, out_lo, (size_t)i, v);
+  }
+}
+
+// 3x3 SAME patches of the grayscale image: out[n,h,w,r*3+s] = gray[n,h+r-1,w+s-1] (0 outside), channels 9..11 = 0
+__global__ void vgg_prologue_patch_kernel(const float* __restrict__ gt, const float* __restrict__ pred, int pcs,
+                                          int B, int R, float* out_hi, float* out_lo) {
+  int64_t per = (int64_t)B * R * R;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * per * 12;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int t = (int)(i % 12);
+    int64_t p = i / 12;
+    float v = 0.f;
+    if (t < 9) {
+      int w = (int)(p % R);
+      int64_t q = p / R;
+      int h = (int)(q % R);
+      int64_t n = q / R;
+      int hh = h + t / 3 - 1, ww = w + t % 3 - 1;
+      if (hh >= 0 && hh < R && ww >= 0 && ww < R) {
+        int64_t src = (n * R + hh) * R + ww;
+        v = src < per ? gray_norm(gt + src * 3) : gray_norm(pred + (src - per) * pcs);
+      }
+    }
+    store_split(out_hi, out_lo, (size_t)i, v);
+  }
+}
+
+// first-layer staging: image [N,H,W,3] -> [N,H,W+8,4] (3 zero columns left, 5 right, 4th channel zero)
+__global__ void stage_image_rowwin_kernel(const float* __restrict__ img, int N, int H, int W, float* x_hi,
+                                          float* x_lo) {
+  const int Wp = W + 8;
+  int64_t total = (int64_t)N * H * Wp * 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i & 3);
+    int64_t p = i >> 2;
+    int wp = (int)(p % Wp);
+    int64_t row = p / Wp;
+    int w = wp - 3;
+    float v = (c < 3 && w >= 0 && w < W) ? __ldg(img + (row * W + w) * 3 + c) : 0.f;
+    store_split(x_hi, x_lo, (size_t)i, v);
+  }
+}
+
+// [7,7,3,Cout] -> [7][Cout][32], k = s*4 + c
+__global__ void pack_weights_rowwin_kernel(const float* __restrict__ w, int Cout, float* wp_hi, float* wp_lo) {
+  int total = 7 * Cout * 32;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int k = i & 31;
+    int co = (i >> 5) % Cout;
+    int r = (i >> 5) / Cout;
+    int s = k >> 2, c = k & 3;
+    float v = (s < 7 && c < 3) ? __ldg(w + ((size_t)(r * 7 + s) * 3 + c) * Cout + co) : 0.f;
+    store_split(wp_hi, wp_lo, (size_t)i, v);
   }
 }
 
@@ -501,7 +548,8 @@ __global__ void vgg_bwd_combine_kernel(const float* __restrict__ g_next, const f
 
 __global__ void pred_grad_kernel(const float* __restrict__ gt, const float* __restrict__ pred, int pcs,
                                  const float* __restrict__ mask, const float* __restrict__ coef_in,
-                                 const float* __restrict__ g_vggin, int B, int R, float* g_hi, float* g_lo) {
+                                 const float* __restrict__ g_vggin, int g_is_patch, int B, int R, float* g_hi,
+                                 float* g_lo) {
   int64_t per = (int64_t)B * R * R;
   float cf = __ldg(coef_in);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per * pcs;
@@ -512,7 +560,24 @@ __global__ void pred_grad_kernel(const float* __restrict__ gt, const float* __re
     if (c < 3) {
       float m = mask ? __ldg(mask + p) : 1.f;
       g = cf * m * (__ldg(gt + p * 3 + c) - __ldg(pred + i));
-      if (g_vggin) g += __ldg(g_vggin + p) * (1.0f / 3.0f) * (1.0f / 255.0f);
+      if (g_vggin) {
+        float gg;
+        if (!g_is_patch) {
+          gg = __ldg(g_vggin + p);
+        } else {      // adjoint of the 3x3 patch extraction
+          int w = (int)(p % R);
+          int64_t q = p / R;
+          int h = (int)(q % R);
+          int64_t n = q / R;
+          gg = 0.f;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            int hh = h - (t / 3 - 1), ww = w - (t % 3 - 1);
+            if (hh >= 0 && hh < R && ww >= 0 && ww < R) gg += __ldg(g_vggin + ((n * R + hh) * R + ww) * 12 + t);
+          }
+        }
+        g += gg * (1.0f / 3.0f) * (1.0f / 255.0f);
+      }
     }
     store_split(g_hi, g_lo, (size_t)i, g);
   }
@@ -651,24 +716,24 @@ __global__ void total_loss_kernel(const float* rec_loss, const double* wsq, cons
   total[0] = rec_loss[0] + (float)s;
 }
 
-// HWIO master -> packed [tap][Cout][cin_pad] and split [tap][cin_pad][Cout], both as (hi, lo) planes
+// HWIO master -> packed [tap][Cout][cin_pad] and split [tap][cin_pad][cout_pad], both as (hi, lo) planes
 __global__ void pack_weights_kernel(const float* __restrict__ w, int taps, int Cin, int Cout, int cin_pad,
-                                    float* wp_hi, float* wp_lo, float* wh_hi, float* wh_lo) {
-  int64_t total = (int64_t)taps * cin_pad * Cout;
+                                    int cout_pad, float* wp_hi, float* wp_lo, float* wh_hi, float* wh_lo) {
+  int64_t total = (int64_t)taps * cin_pad * cout_pad;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
-    int co = (int)(i % Cout);
-    int64_t q = i / Cout;
+    int co = (int)(i % cout_pad);
+    int64_t q = i / cout_pad;
     int ci = (int)(q % cin_pad);
     int tap = (int)(q / cin_pad);
-    float val = ci < Cin ? __ldg(w + ((int64_t)tap * Cin + ci) * Cout + co) : 0.f;
+    float val = (ci < Cin && co < Cout) ? __ldg(w + ((int64_t)tap * Cin + ci) * Cout + co) : 0.f;
     float hi, lo;
     split_tf32(val, hi, lo);
     if (wh_hi) {
       wh_hi[i] = hi;
       if (wh_lo) wh_lo[i] = lo;
     }
-    if (wp_hi) {
+    if (wp_hi && co < Cout) {
       size_t j = ((size_t)tap * Cout + co) * cin_pad + ci;
       wp_hi[j] = hi;
       if (wp_lo) wp_lo[j] = lo;
@@ -797,12 +862,30 @@ extern "C" int immb_gaussian_maps(const float* mu, int B, int K, int S, float in
   return check_launch("gaussian_maps");
 }
 
-extern "C" int immb_vgg_prologue(const float* gt, const float* pred, int pcs, int B, int R, float* out_hi,
-                                 float* out_lo, void* stream) {
+extern "C" int immb_vgg_prologue(const float* gt, const float* pred, int pcs, int B, int R, int patches,
+                                 float* out_hi, float* out_lo, void* stream) {
   IMMB_REQUIRE(gt && pred && out_hi && pcs >= 3, "vgg_prologue: bad args");
-  vgg_prologue_kernel<<<ew_grid((int64_t)2 * B * R * R), 256, 0, ST(stream)>>>(gt, pred, pcs, B, R, out_hi,
-                                                                              out_lo);
+  if (patches)
+    vgg_prologue_patch_kernel<<<ew_grid((int64_t)2 * B * R * R * 12), 256, 0, ST(stream)>>>(gt, pred, pcs, B, R,
+                                                                                         out_hi, out_lo);
+  else
+    vgg_prologue_kernel<<<ew_grid((int64_t)2 * B * R * R), 256, 0, ST(stream)>>>(gt, pred, pcs, B, R, out_hi,
+                                                                                out_lo);
   return check_launch("vgg_prologue");
+}
+
+extern "C" int immb_stage_image_rowwin(const float* image, int N, int H, int W, float* x4_hi, float* x4_lo,
+                                       void* stream) {
+  IMMB_REQUIRE(image && x4_hi && N > 0 && H > 0 && W > 0, "stage_image_rowwin: bad args");
+  stage_image_rowwin_kernel<<<ew_grid((int64_t)N * H * (W + 8) * 4), 256, 0, ST(stream)>>>(image, N, H, W, x4_hi,
+                                                                                          x4_lo);
+  return check_launch("stage_image_rowwin");
+}
+
+extern "C" int immb_pack_weights_rowwin(const float* w, int Cout, float* wp_hi, float* wp_lo, void* stream) {
+  IMMB_REQUIRE(w && wp_hi && Cout > 0, "pack_weights_rowwin: bad args");
+  pack_weights_rowwin_kernel<<<ew_grid((int64_t)7 * Cout * 32), 256, 0, ST(stream)>>>(w, Cout, wp_hi, wp_lo);
+  return check_launch("pack_weights_rowwin");
 }
 
 extern "C" int immb_maxpool2x2_fwd(const float* x_hi, const float* x_lo, int N, int H, int W, int C,
@@ -851,11 +934,11 @@ extern "C" int immb_vgg_bwd_combine(const float* g_next, const float* fg_hi, con
 }
 
 extern "C" int immb_pred_grad(const float* gt, const float* pred, int pcs, const float* mask,
-                              const float* coef_input, const float* g_vggin, int B, int R, float* g_hi,
-                              float* g_lo, void* stream) {
+                              const float* coef_input, const float* g_vggin, int g_is_patch, int B, int R,
+                              float* g_hi, float* g_lo, void* stream) {
   IMMB_REQUIRE(gt && pred && coef_input && g_hi && pcs >= 3, "pred_grad: bad args");
-  pred_grad_kernel<<<ew_grid((int64_t)B * R * R * pcs), 256, 0, ST(stream)>>>(gt, pred, pcs, mask, coef_input,
-                                                                             g_vggin, B, R, g_hi, g_lo);
+  pred_grad_kernel<<<ew_grid((int64_t)B * R * R * pcs), 256, 0, ST(stream)>>>(
+      gt, pred, pcs, mask, coef_input, g_vggin, g_is_patch, B, R, g_hi, g_lo);
   return check_launch("pred_grad");
 }
 
@@ -905,10 +988,10 @@ extern "C" int immb_total_loss(const float* rec_loss, const double* wsq, const f
   return check_launch("total_loss");
 }
 
-extern "C" int immb_pack_weights(const float* w, int kh, int kw, int Cin, int Cout, int cin_pad, float* wp_hi,
-                                 float* wp_lo, float* wh_hi, float* wh_lo, void* stream) {
-  IMMB_REQUIRE(w && (wp_hi || wh_hi) && cin_pad >= Cin, "pack_weights: bad args");
-  pack_weights_kernel<<<ew_grid((int64_t)kh * kw * cin_pad * Cout), 256, 0, ST(stream)>>>(
-      w, kh * kw, Cin, Cout, cin_pad, wp_hi, wp_lo, wh_hi, wh_lo);
+extern "C" int immb_pack_weights(const float* w, int kh, int kw, int Cin, int Cout, int cin_pad, int cout_pad,
+                                 float* wp_hi, float* wp_lo, float* wh_hi, float* wh_lo, void* stream) {
+  IMMB_REQUIRE(w && (wp_hi || wh_hi) && cin_pad >= Cin && cout_pad >= Cout, "pack_weights: bad args");
+  pack_weights_kernel<<<ew_grid((int64_t)kh * kw * cin_pad * cout_pad), 256, 0, ST(stream)>>>(
+      w, kh * kw, Cin, Cout, cin_pad, cout_pad, wp_hi, wp_lo, wh_hi, wh_lo);
   return check_launch("pack_weights");
 }

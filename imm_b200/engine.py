@@ -96,19 +96,22 @@ class ConvLayer(object):
     self.Ho, self.Wo = -(-H // stride), -(-W // stride)
     self.bn, self.relu, self.up2x, self.needs_dgrad, self.trainable = bn, relu, up2x, needs_dgrad, trainable
     self.cin_pad = round_up(cin, 32)
+    self.ycs = round_up(cout, 4)          # channel stride of y / dy (TMA needs 16-byte pixel strides)
     self.pad_t = same_pad(H, k, stride)[0]
     self.pad_l = same_pad(W, k, stride)[0]
     self.epilogue = epilogue
     self.engine_override = None
+    self.x_layout = _lib.XLAYOUT_NHWC
 
   def desc(self, N=None):
     d = ConvDesc()
     d.N, d.H, d.W, d.Cin = (self.N if N is None else N), self.H, self.W, self.cin
     d.Cout, d.kh, d.kw, d.stride = self.cout, self.k, self.k, self.stride
     d.Ho, d.Wo, d.pad_t, d.pad_l = self.Ho, self.Wo, self.pad_t, self.pad_l
-    d.x_cstride, d.y_cstride, d.cin_pad = self.xcs, self.cout, self.cin_pad
+    d.x_cstride, d.y_cstride, d.cin_pad = self.xcs, self.ycs, self.cin_pad
     d.epilogue, d.precision = self.epilogue, self.eng.precision
     d.engine = self.eng.engine if self.engine_override is None else self.engine_override
+    d.x_layout = self.x_layout
     return d
 
   def engines(self):
@@ -173,6 +176,9 @@ class IMMEngine(object):
       cin, size, lst = 3, R, []
       for i, (name, k, stride, cout) in enumerate(encoder_spec(self.nf)):
         L = add(prefix, name, k, stride, cin, cout, size, size, cin, True, True, False, i > 0)
+        if i == 0 and self.engine != _lib.ENGINE_SIMT and k == 7 and size % 16 == 0:
+          # first layer (7x7, Cin=3) runs on the tensor cores from a staged row-window image (include/imm_b200.h)
+          L.x_layout, L.xcs = _lib.XLAYOUT_ROWWIN4, 4
         lst.append(L)
         cin, size = cout, L.Ho
       self.enc_layers[enc] = lst
@@ -198,8 +204,13 @@ class IMMEngine(object):
         size //= 2
       else:
         name, cout = it
-        L = ConvLayer(self, 'SelfSupReconstructionLoss/vgg16', name, 3, 1, cin, cout, 2 * B, size, size, cin,
-                      False, True, False, True, trainable=False, epilogue=_lib.EPI_BIAS_RELU)
+        if name == 'conv1_1':
+          # Cin = 1, 3x3 == 1x1 convolution over the [.,R,R,12] tensor of 3x3 patches written by immb_vgg_prologue
+          L = ConvLayer(self, 'SelfSupReconstructionLoss/vgg16', name, 1, 1, 9, cout, 2 * B, size, size, 12,
+                        False, True, False, True, trainable=False, epilogue=_lib.EPI_BIAS_RELU)
+        else:
+          L = ConvLayer(self, 'SelfSupReconstructionLoss/vgg16', name, 3, 1, cin, cout, 2 * B, size, size, cin,
+                        False, True, False, True, trainable=False, epilogue=_lib.EPI_BIAS_RELU)
         self.vgg_seq.append(('conv', L, cin, size))
         cin = cout
 
@@ -275,10 +286,15 @@ class IMMEngine(object):
   def _alloc_weight_planes(self, L):
     dev, taps = self.dev, L.k * L.k
     e = torch.empty
+    if L.x_layout == _lib.XLAYOUT_ROWWIN4:
+      L.wp = Planes(e((7, L.cout, 32), dtype=torch.float32, device=dev), e((7, L.cout, 32), dtype=torch.float32, device=dev))
+      L.wh = Planes(None, None)
+      L.stage = Planes.alloc((L.N, L.H, L.W + 8, 4), dev)
+      return
     L.wp = Planes(e((taps, L.cout, L.cin_pad), dtype=torch.float32, device=dev),
                   e((taps, L.cout, L.cin_pad), dtype=torch.float32, device=dev))
-    L.wh = Planes(e((taps, L.cin_pad, L.cout), dtype=torch.float32, device=dev),
-                  e((taps, L.cin_pad, L.cout), dtype=torch.float32, device=dev))
+    L.wh = Planes(e((taps, L.cin_pad, L.ycs), dtype=torch.float32, device=dev),
+                  e((taps, L.cin_pad, L.ycs), dtype=torch.float32, device=dev))
 
   def _alloc_buffers(self):
     dev, B, R, K = self.dev, self.B, self.R, self.K
@@ -288,8 +304,8 @@ class IMMEngine(object):
     ws_bytes = 0
     for key, L in self.layers.items():
       self._alloc_weight_planes(L)
-      L.y = f32(B, L.Ho, L.Wo, L.cout)
-      L.dy = Planes.alloc((B, L.Ho, L.Wo, L.cout), dev)
+      L.y = torch.zeros((B, L.Ho, L.Wo, L.ycs), dtype=torch.float32, device=dev)
+      L.dy = Planes.alloc((B, L.Ho, L.Wo, L.ycs), dev, zero=True)
       L.dbias_acc = f64z(L.cout)
       if L.bn:
         L.sums, L.bsums = f64z(2 * L.cout), f64z(2 * L.cout)
@@ -314,19 +330,20 @@ class IMMEngine(object):
         L.out, L.ocs = Planes.alloc((B, L.Ho * s, L.Wo * s, L.cout), dev), L.cout
     S = self.enc_out_size
     self.mu, self.py, self.px = f32(B, K, 2), f32(B, S, K), f32(B, S, K)
-    self.g_heat = f32(B, S, S, K)
+    self.Kp = self.pose_conv.ycs
+    self.g_heat = torch.zeros((B, S, S, self.Kp), dtype=torch.float32, device=dev)
     # perceptual tower
-    self.vgg_in = Planes.alloc((2 * B, R, R, 1), dev)
+    self.vgg_in = Planes.alloc((2 * B, R, R, 12), dev)        # 3x3 patches of the normalised gray image
     self.vgg_act = OrderedDict()
     for kind, item, cin, size in self.vgg_seq:
       if kind == 'conv':
         L = item
         self._alloc_weight_planes(L)
-        L.w = f32(3, 3, L.cin, L.cout)
+        L.w = f32(L.k, L.k, L.cin, L.cout)
         L.b = f32(L.cout)
         L.out = Planes.alloc((2 * B, size, size, L.cout), dev)
         L.dy = Planes.alloc((B, size, size, L.cout), dev)        # pred half only
-        L.dx = f32(B, size, size, L.cin)
+        L.dx = torch.zeros((B, size, size, L.xcs), dtype=torch.float32, device=dev)
         self.vgg_act[L.name] = L.out
         ws_bytes = max(ws_bytes, 0)
       else:
@@ -344,7 +361,8 @@ class IMMEngine(object):
     self.levels = f32(len(self.comp))
     self.coef = f32(len(self.comp))
     self.rec_loss, self.weights_loss, self.total_loss = f32(1), f32(1), f32(1)
-    self.pred_dy = Planes.alloc((B, R, R, self.n_out), dev)
+    self.pcs = self.ren_layers[-1].ycs      # channel stride of the renderer output / its gradient
+    self.pred_dy = Planes.alloc((B, R, R, self.pcs), dev, zero=True)
     self.workspace = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
 
   # ------------------------------------------------------------------------------------------------
@@ -400,16 +418,20 @@ class IMMEngine(object):
         mu = np.asarray(bn['0']) / np.asarray(bn['2'])
         W = W / sigma
         bias = (bias - mu) / sigma
-      assert tuple(W.shape) == (3, 3, L.cin, L.cout), 'Incorrect weights shape for %s' % L.name   # vgg16.py:171
-      L.w.copy_(torch.from_numpy(np.ascontiguousarray(W, dtype=np.float32)))
+      cin_true = 1 if L.name == 'conv1_1' else L.cin
+      assert tuple(W.shape) == (3, 3, cin_true, L.cout), 'Incorrect weights shape for %s' % L.name   # vgg16.py:171
+      L.w.copy_(torch.from_numpy(np.ascontiguousarray(W, dtype=np.float32)).reshape(L.w.shape))
       L.b.copy_(torch.from_numpy(np.ascontiguousarray(bias, dtype=np.float32)))
-      self.vgg_params['SelfSupReconstructionLoss/vgg16/%s/weights' % L.name] = L.w
+      self.vgg_params['SelfSupReconstructionLoss/vgg16/%s/weights' % L.name] = L.w.view(3, 3, cin_true, L.cout)
       self.vgg_params['SelfSupReconstructionLoss/vgg16/%s/biases' % L.name] = L.b
       self._pack(L)
     self.vgg_loaded = True
 
   def _pack(self, L):
-    call('immb_pack_weights', L.w, L.k, L.k, L.cin, L.cout, L.cin_pad, L.wp.hi, L.wp.lo, L.wh.hi, L.wh.lo,
+    if L.x_layout == _lib.XLAYOUT_ROWWIN4:
+      call('immb_pack_weights_rowwin', L.w, L.cout, L.wp.hi, L.wp.lo, _lib.stream_ptr())
+      return
+    call('immb_pack_weights', L.w, L.k, L.k, L.cin, L.cout, L.cin_pad, L.ycs, L.wp.hi, L.wp.lo, L.wh.hi, L.wh.lo,
          _lib.stream_ptr())
 
   def repack_weights(self):
@@ -425,6 +447,7 @@ class IMMEngine(object):
   def _block_fwd(self, L, X, training):
     """conv -> bias -> [BN] -> [ReLU] -> [x2 legacy bilinear]  (nn_utils.py:151-210, imm_model.py:175)."""
     st = _lib.stream_ptr()
+    _lib.TAG = 'fwd:%s/%s' % (L.prefix.split('/')[-2] if L.prefix.endswith('encoder') else L.prefix.split('/')[-1], L.name)
     L.x = X
     self._conv_fwd(L, X, L.y)
     if not L.bn:
@@ -432,10 +455,10 @@ class IMMEngine(object):
     npix = L.N * L.Ho * L.Wo
     if training:
       L.sums.zero_()
-      call('immb_bn_stats', L.y, npix, L.cout, L.cout, L.sums, st)
+      call('immb_bn_stats', L.y, npix, L.cout, L.ycs, L.sums, st)
     call('immb_bn_finalize', L.sums, npix, L.cout, L.gamma, L.beta, L.mm, L.mv, 1 if training else 0,
          L.scale, L.shift, L.mean, L.invstd, st)
-    call('immb_bn_apply', L.y, L.N, L.Ho, L.Wo, L.cout, L.cout, L.scale, L.shift, 1 if L.relu else 0,
+    call('immb_bn_apply', L.y, L.N, L.Ho, L.Wo, L.cout, L.ycs, L.scale, L.shift, 1 if L.relu else 0,
          1 if L.up2x else 0, L.out.hi, L.out.lo, L.ocs, st)
     return L.out
 
@@ -452,6 +475,10 @@ class IMMEngine(object):
     # image encoder (imm_model.py:220-230) and pose encoder (:233-248)
     for enc, inp in (('image_encoder', image), ('pose_encoder', future_image)):
       X = Planes(inp, None)
+      L0 = self.enc_layers[enc][0]
+      if L0.x_layout == _lib.XLAYOUT_ROWWIN4:
+        call('immb_stage_image_rowwin', inp, B, R, R, L0.stage.hi, L0.stage.lo, st)
+        X = L0.stage
       for L in self.enc_layers[enc]:
         X = self._block_fwd(L, X, training)
     img_last, pose_last = self.enc_layers['image_encoder'][-1], self.enc_layers['pose_encoder'][-1]
@@ -462,13 +489,13 @@ class IMMEngine(object):
     # heatmaps -> (mu_y, mu_x) -> Gaussian maps into the concat buffer (imm_model.py:247-274,341-344)
     self._block_fwd(self.pose_conv, pose_last.out, training)
     S = self.enc_out_size
-    call('immb_softargmax_gauss_fwd', self.pose_conv.y, B, S, K, K, self.inv_std, self.mu, self.py, self.px, 16,
+    call('immb_softargmax_gauss_fwd', self.pose_conv.y, B, S, K, self.Kp, self.inv_std, self.mu, self.py, self.px, 16,
          self.joint.hi, self.joint.lo, self.Cj, self.enc_feat, st)
     # renderer (imm_model.py:154-179)
     X = self.joint
     for L in self.ren_layers:
       X = self._block_fwd(L, X, training)
-    self.pred = self.ren_layers[-1].y           # [B,R,R,n_out]; first 3 channels = future_im_pred (:348-355)
+    self.pred = self.ren_layers[-1].y           # [B,R,R,pcs]; first 3 channels = future_im_pred (:348-355)
     if build_loss:
       self._loss_fwd(training)
     return self.pred
@@ -479,11 +506,12 @@ class IMMEngine(object):
       raise _lib.ImmbError('VGG16 weights not loaded (load_vgg_caffe_dict)')
     st = _lib.stream_ptr()
     B, R = self.B, self.R
-    call('immb_vgg_prologue', self.future_image, self.pred, self.n_out, B, R, self.vgg_in.hi, self.vgg_in.lo, st)
+    call('immb_vgg_prologue', self.future_image, self.pred, self.pcs, B, R, 1, self.vgg_in.hi, self.vgg_in.lo, st)
     X = self.vgg_in
     for kind, item, cin, size in self.vgg_seq:
       if kind == 'conv':
         item.x = X
+        _lib.TAG = 'fwd:vgg/%s' % item.name
         self._conv_fwd(item, X, item.out.hi, item.out.lo)
         X = item.out
       else:
@@ -493,7 +521,7 @@ class IMMEngine(object):
     self.level_acc.zero_()
     for k, nm in enumerate(self.comp):
       if nm == 'input':
-        call('immb_perceptual_level_sum', self.future_image, None, 3, self.pred, None, self.n_out, B, R, R, 3,
+        call('immb_perceptual_level_sum', self.future_image, None, 3, self.pred, None, self.pcs, B, R, R, 3,
              self.mask, R, self.level_acc[k:], st)
       else:
         P = self.vgg_act[nm]
@@ -521,6 +549,7 @@ class IMMEngine(object):
     """g: gradient wrt the block output (after the optional x2 upsample), channel stride gcs.
     Returns the gradient wrt the block input [N,H,W,xcs] or None."""
     st = _lib.stream_ptr()
+    _lib.TAG = 'bwd:%s/%s' % (L.prefix.split('/')[-2] if L.prefix.endswith('encoder') else L.prefix.split('/')[-1], L.name)
     npix = L.N * L.Ho * L.Wo
     if L.bn:
       if L.up2x:
@@ -537,11 +566,11 @@ class IMMEngine(object):
     else:
       dy = g if isinstance(g, Planes) else None
       if dy is None:
-        assert gcs == L.cout
-        call('immb_split_planes', g, L.dy.hi, L.dy.lo, npix * L.cout, st)
+        assert gcs == L.ycs
+        call('immb_split_planes', g, L.dy.hi, L.dy.lo, npix * L.ycs, st)
         dy = L.dy
       L.dbias_acc.zero_()
-      call('immb_bias_grad', dy.hi, dy.lo, L.cout, npix, L.cout, L.dbias_acc, st)
+      call('immb_bias_grad', dy.hi, dy.lo, L.ycs, npix, L.cout, L.dbias_acc, st)
     call('immb_cast_d2f', L.dbias_acc, L.db, L.cout, st)
     d = L.desc()
     call('immb_conv2d_wgrad', d, L.x.hi, L.x.lo, dy.hi, dy.lo, L.dw, self.workspace, self.workspace.numel(), st)
@@ -564,6 +593,7 @@ class IMMEngine(object):
         if g is None and coef is None:
           continue                  # above the deepest level used by the loss
         fg, fp = P.half(0, B), P.half(1, B)
+        _lib.TAG = 'bwd:vgg/%s' % L.name
         call('immb_vgg_bwd_combine', g, fg.hi, fg.lo, fp.hi, fp.lo, B, size, size, L.cout, self.mask, R, coef,
              L.dy.hi, L.dy.lo, st)
         call('immb_conv2d_dgrad', L.desc(B), L.dy.hi, L.dy.lo, L.w, L.wh.hi, L.wh.lo, L.dx, st)
@@ -581,7 +611,7 @@ class IMMEngine(object):
     coef_in = self.coef[level_of['input']:] if 'input' in level_of else None
     if coef_in is None:
       raise _lib.ImmbError("perceptual.comp without 'input' is not built")
-    call('immb_pred_grad', self.future_image, self.pred, self.n_out, self.mask, coef_in, g, B, R,
+    call('immb_pred_grad', self.future_image, self.pred, self.pcs, self.mask, coef_in, g, 1, B, R,
          self.pred_dy.hi, self.pred_dy.lo, st)
     return self.pred_dy
 
@@ -590,7 +620,7 @@ class IMMEngine(object):
     st = _lib.stream_ptr()
     B, K = self.B, self.K
     g = self._loss_bwd()
-    gcs = self.n_out
+    gcs = self.pcs
     for L in reversed(self.ren_layers):
       g = self._block_bwd(L, g, gcs)
       gcs = L.xcs
@@ -598,8 +628,8 @@ class IMMEngine(object):
     # pose branch: Gaussian maps -> mu -> softmax marginals -> heatmaps (imm_model.py:252-274)
     S = self.enc_out_size
     call('immb_softargmax_gauss_bwd', dJ, self.Cj, self.enc_feat, self.mu, self.py, self.px, B, S, K, 16,
-         self.inv_std, self.g_heat, K, st)
-    gp = self._block_bwd(self.pose_conv, self.g_heat, K)
+         self.inv_std, self.g_heat, self.Kp, st)
+    gp = self._block_bwd(self.pose_conv, self.g_heat, self.Kp)
     gcs_p = self.enc_feat
     for L in reversed(self.enc_layers['pose_encoder']):
       gp = self._block_bwd(L, gp, gcs_p)

@@ -51,6 +51,13 @@ typedef enum {
 } immb_precision;
 
 typedef enum {
+  IMMB_XLAYOUT_NHWC = 0,      /* x is [N,H,W,x_cstride] */
+  IMMB_XLAYOUT_ROWWIN4 = 1    /* 7x7 / Cin=3 / stride-1 first layer only: x is the staged image [N,H,W+8,4]
+                                 (immb_stage_image_rowwin): 3 zero columns left, 5 right, 4th channel zero, so that
+                                 the 7 taps of one filter row are ONE contiguous 128-byte TMA row per output pixel */
+} immb_xlayout;
+
+typedef enum {
   IMMB_EPI_BIAS = 0,          /* y = conv + b              (trainable stack: nn_utils.py:100,108) */
   IMMB_EPI_BIAS_RELU = 1      /* y = relu(conv + b)        (VGG: selfsup/vgg16.py:182-230) */
 } immb_epilogue;
@@ -68,6 +75,7 @@ typedef struct {
   int32_t epilogue;           /* immb_epilogue (fwd only) */
   int32_t precision;          /* immb_precision */
   int32_t engine;             /* immb_engine */
+  int32_t x_layout;           /* immb_xlayout */
 } immb_conv_desc;
 
 int immb_version(void);
@@ -81,7 +89,7 @@ int64_t immb_launch_count(void);
 /* ---- convolution: nn_utils.py:100 (tf.nn.conv2d) + :108 (bias_add); vgg16.py:182-230 -------------- */
 /* w      : master weights HWIO [kh,kw,Cin,Cout] (checkpoint layout, base_model.py:110)
  * wp_*   : packed copy  [kh*kw][Cout][cin_pad]   (K-major B operand of the forward GEMM)
- * wh_*   : split copy   [kh*kw][cin_pad][Cout]   (K-major B operand of the dgrad GEMM)
+ * wh_*   : split copy   [kh*kw][cin_pad][cout_pad] (K-major B operand of the dgrad GEMM; cout_pad = y_cstride)
  * y_lo   : NULL -> y_hi receives the full fp32 result; else the result is written as split planes. */
 int immb_conv2d_fwd(const immb_conv_desc* d, const float* x_hi, const float* x_lo, const float* w,
                     const float* wp_hi, const float* wp_lo, const float* bias, float* y_hi, float* y_lo,
@@ -93,9 +101,14 @@ int immb_conv2d_dgrad(const immb_conv_desc* d, const float* dy_hi, const float* 
 size_t immb_conv2d_wgrad_workspace(const immb_conv_desc* d);
 int immb_conv2d_wgrad(const immb_conv_desc* d, const float* x_hi, const float* x_lo, const float* dy_hi,
                       const float* dy_lo, float* dw, void* workspace, size_t ws_bytes, void* stream);
-/* master HWIO -> wp_{hi,lo}, wh_{hi,lo} (either pair may be NULL) */
-int immb_pack_weights(const float* w, int kh, int kw, int Cin, int Cout, int cin_pad, float* wp_hi,
+/* master HWIO -> wp_{hi,lo} [taps][Cout][cin_pad], wh_{hi,lo} [taps][cin_pad][cout_pad] (either pair may be NULL;
+ * padding is zero filled; cout_pad >= Cout is the channel stride of the layer's output / dy tensors) */
+int immb_pack_weights(const float* w, int kh, int kw, int Cin, int Cout, int cin_pad, int cout_pad, float* wp_hi,
                       float* wp_lo, float* wh_hi, float* wh_lo, void* stream);
+/* first-layer staging for IMMB_XLAYOUT_ROWWIN4: image [N,H,W,3] -> x4 split planes [N,H,W+8,4];
+ * weights [7,7,3,Cout] -> wp_{hi,lo} [7][Cout][32] with k = s*4 + c (zero for c == 3 and s == 7) */
+int immb_stage_image_rowwin(const float* image, int N, int H, int W, float* x4_hi, float* x4_lo, void* stream);
+int immb_pack_weights_rowwin(const float* w, int Cout, float* wp_hi, float* wp_lo, void* stream);
 /* v -> (hi, lo) planes, contiguous n elements */
 int immb_split_planes(const float* v, float* hi, float* lo, int64_t n, void* stream);
 
@@ -145,9 +158,12 @@ int immb_softargmax_gauss_bwd(const float* g_maps, int g_cstride, int c_off, con
 int immb_gaussian_maps(const float* mu, int B, int K, int S, float inv_std, float* maps, void* stream);
 
 /* ---- perceptual tower glue: build_vgg16.py:22-26, ops.py:16-26, imm_model.py:111-151,408-410 ------ */
-/* vgg_in[2B,R,R,1] split planes: gray = mean_c(rgb)/255 - 114.451/255 for [gt ; pred[..., :3]] */
-int immb_vgg_prologue(const float* gt, const float* pred, int pred_cstride, int B, int R, float* out_hi,
-                      float* out_lo, void* stream);
+/* gray = mean_c(rgb)/255 - 114.451/255 for [gt ; pred[..., :3]] as split planes.
+ * patches == 0: out is vgg_in [2B,R,R,1].
+ * patches != 0: out is the 3x3 SAME-padded patch tensor [2B,R,R,12] (channel r*3+s = gray[h+r-1, w+s-1], channels
+ *   9..11 zero), which turns conv1_1 (Cin = 1) into a tensor-core friendly 1x1 convolution with Cin = 9. */
+int immb_vgg_prologue(const float* gt, const float* pred, int pred_cstride, int B, int R, int patches,
+                      float* out_hi, float* out_lo, void* stream);
 /* 2x2/2 max pool on split planes [N,H,W,C] -> [N,H/2,W/2,C] split planes */
 int immb_maxpool2x2_fwd(const float* x_hi, const float* x_lo, int N, int H, int W, int C, float* o_hi,
                         float* o_lo, void* stream);
@@ -173,10 +189,12 @@ int immb_vgg_bwd_combine(const float* g_next, const float* fg_hi, const float* f
                          const float* fp_lo, int B, int h, int w, int C, const float* mask, int R,
                          const float* coef, float* dy_hi, float* dy_lo, void* stream);
 /* gradient wrt the renderer output [B,R,R,pred_cstride] (channels >=3 get 0) as split planes:
- *   g_pred_c = coef_input * m * (gt_c - pred_c) + g_vggin / (3*255)   (g_vggin [B,R,R,1] may be NULL) */
+ *   g_pred_c = coef_input * m * (gt_c - pred_c) + g_gray / (3*255)
+ * g_vggin (may be NULL): gradient wrt the VGG input; [B,R,R,1] when g_is_patch == 0, else the gradient wrt the
+ * [B,R,R,12] patch tensor (g_gray[h,w] = sum_{r,s} g[h-r+1, w-s+1, r*3+s], the adjoint of the patch extraction). */
 int immb_pred_grad(const float* gt, const float* pred, int pred_cstride, const float* mask,
-                   const float* coef_input, const float* g_vggin, int B, int R, float* g_hi, float* g_lo,
-                   void* stream);
+                   const float* coef_input, const float* g_vggin, int g_is_patch, int B, int R, float* g_hi,
+                   float* g_lo, void* stream);
 /* tf.image.resize_bilinear(align_corners=True) (imm_model.py:334) on split planes, and its adjoint */
 int immb_resize_ac_fwd(const float* x_hi, const float* x_lo, int x_cstride, int N, int H, int W, int C,
                        int Ho, int Wo, float* o_hi, float* o_lo, int o_cstride, void* stream);

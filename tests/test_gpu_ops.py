@@ -23,13 +23,13 @@ def split(t):
   return hi, lo
 
 
-def conv_desc(N, H, W, Cin, Cout, k, stride, xcs=None, engine=_lib.ENGINE_AUTO, epilogue=0, precision=0):
+def conv_desc(N, H, W, Cin, Cout, k, stride, xcs=None, engine=_lib.ENGINE_AUTO, epilogue=0, precision=0, ycs=None):
   d = ConvDesc()
   d.N, d.H, d.W, d.Cin, d.Cout, d.kh, d.kw, d.stride = N, H, W, Cin, Cout, k, k, stride
   d.Ho, d.Wo = -(-H // stride), -(-W // stride)
   d.pad_t, d.pad_l = O.same_pad(H, k, stride)[0], O.same_pad(W, k, stride)[0]
   d.x_cstride = xcs or Cin
-  d.y_cstride = Cout
+  d.y_cstride = ycs or Cout
   d.cin_pad = (Cin + 31) // 32 * 32
   d.epilogue, d.precision, d.engine = epilogue, precision, engine
   return d
@@ -96,6 +96,10 @@ TC_CASES = [
   (1, 128, 128, 32, 32, 3, 1, None),     # encoder conv_2 shape
   (1, 32, 32, 64, 32, 3, 1, None),
   (2, 16, 16, 512, 512, 3, 1, None),     # VGG conv4_x
+  (1, 32, 32, 32, 9, 3, 1, None),        # renderer last conv: Cout=9 in a 12-channel-stride tensor (BN=16 tile)
+  (2, 16, 16, 256, 10, 1, 1, None),      # pose 1x1 -> 10 heatmaps (stride 12)
+  (1, 16, 16, 256, 50, 1, 1, None),      # pose 1x1 -> 50 heatmaps (stride 52, BN=64 tile)
+  (2, 32, 32, 9, 64, 1, 1, 12),          # vgg conv1_1 as a 1x1 conv over 3x3 patches (Cin=9, stride 12)
 ]
 
 
@@ -110,7 +114,8 @@ def test_conv_tcgen05_engine(case, precision):
   x[..., Cin:] = 0
   w = torch.randn(k, k, Cin, Cout, generator=g) * 0.1
   b = torch.randn(Cout, generator=g)
-  d = conv_desc(N, H, W, Cin, Cout, k, stride, xcs, engine=_lib.ENGINE_TC, precision=precision)
+  ycs = (Cout + 3) // 4 * 4
+  d = conv_desc(N, H, W, Cin, Cout, k, stride, xcs, engine=_lib.ENGINE_TC, precision=precision, ycs=ycs)
   assert [_lib.lib().immb_conv_engine_for(d, op) for op in range(3)] == [_lib.ENGINE_TC] * 3
   # tensor-core fp32 accumulation truncates (round-toward-zero) at every K=8 step: the error grows with the
   # reduction length (K = 4608 for the 512-channel VGG layers) but stays ~30x below the 1e-3 bar
@@ -123,15 +128,19 @@ def test_conv_tcgen05_engine(case, precision):
   dev = 'cuda'
   taps, cp = k * k, d.cin_pad
   wp_h, wp_l = torch.empty(taps, Cout, cp, device=dev), torch.empty(taps, Cout, cp, device=dev)
-  wh_h, wh_l = torch.empty(taps, cp, Cout, device=dev), torch.empty(taps, cp, Cout, device=dev)
-  call('immb_pack_weights', w.to(dev), k, k, Cin, Cout, cp, wp_h, wp_l, wh_h, wh_l, ST())
+  wh_h, wh_l = torch.empty(taps, cp, ycs, device=dev), torch.empty(taps, cp, ycs, device=dev)
+  call('immb_pack_weights', w.to(dev), k, k, Cin, Cout, cp, ycs, wp_h, wp_l, wh_h, wh_l, ST())
   xh, xl = split(x)
   xh, xl = xh.to(dev), xl.to(dev)
-  y = torch.full((N, d.Ho, d.Wo, Cout), float('nan'), device=dev)
+  y = torch.full((N, d.Ho, d.Wo, ycs), float('nan'), device=dev)
   call('immb_conv2d_fwd', d, xh, xl, None, wp_h, wp_l, b.to(dev), y, None, ST())
   torch.cuda.synchronize()
-  assert rel_err(y, y_ref) < tol, ('fwd', rel_err(y, y_ref))
-  gh, gl = split(gy)
+  assert rel_err(y[..., :Cout], y_ref) < tol, ('fwd', rel_err(y[..., :Cout], y_ref))
+  if ycs > Cout:
+    assert float(y[..., Cout:].abs().max()) == 0.0
+  gyp = torch.zeros(N, d.Ho, d.Wo, ycs)
+  gyp[..., :Cout] = gy
+  gh, gl = split(gyp)
   gh, gl = gh.to(dev), gl.to(dev)
   dx = torch.full((N, H, W, xcs_), float('nan'), device=dev)
   call('immb_conv2d_dgrad', d, gh, gl, None, wh_h, wh_l, dx, ST())
@@ -146,22 +155,22 @@ def test_conv_tcgen05_engine(case, precision):
   assert rel_err(dw, wd.grad) < tol, ('wgrad', rel_err(dw, wd.grad))
   # fused bias+ReLU epilogue writing split planes (VGG path)
   d2 = conv_desc(N, H, W, Cin, Cout, k, stride, xcs, engine=_lib.ENGINE_TC, epilogue=_lib.EPI_BIAS_RELU,
-                 precision=precision)
+                 precision=precision, ycs=ycs)
   yh, yl = torch.empty_like(y), torch.empty_like(y)
   call('immb_conv2d_fwd', d2, xh, xl, None, wp_h, wp_l, b.to(dev), yh, yl, ST())
-  assert rel_err(yh + yl, torch.relu(y_ref)) < tol
+  assert rel_err((yh + yl)[..., :Cout], torch.relu(y_ref)) < tol
 
 
 def test_pack_weights_layouts():
   w = torch.randn(3, 3, 5, 7)
   wp_h, wp_l = torch.empty(9, 7, 32, device='cuda'), torch.empty(9, 7, 32, device='cuda')
-  wh_h, wh_l = torch.empty(9, 32, 7, device='cuda'), torch.empty(9, 32, 7, device='cuda')
-  call('immb_pack_weights', w.cuda(), 3, 3, 5, 7, 32, wp_h, wp_l, wh_h, wh_l, ST())
-  full = torch.zeros(9, 32, 7)
-  full[:, :5] = w.view(9, 5, 7)
+  wh_h, wh_l = torch.empty(9, 32, 8, device='cuda'), torch.empty(9, 32, 8, device='cuda')
+  call('immb_pack_weights', w.cuda(), 3, 3, 5, 7, 32, 8, wp_h, wp_l, wh_h, wh_l, ST())
+  full = torch.zeros(9, 32, 8)
+  full[:, :5, :7] = w.view(9, 5, 7)
   assert rel_err(wh_h + wh_l, full) < 1e-6
-  assert rel_err(wp_h + wp_l, full.permute(0, 2, 1)) < 1e-6
-  assert float(wh_h[:, 5:].abs().max()) == 0.0
+  assert rel_err(wp_h + wp_l, full[:, :, :7].permute(0, 2, 1)) < 1e-6
+  assert float(wh_h[:, 5:].abs().max()) == 0.0 and float(wh_h[:, :, 7:].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize('shape', [(2, 8, 8, 32), (3, 5, 7, 48), (1, 16, 16, 256)])
@@ -321,7 +330,7 @@ def test_vgg_prologue_and_pred_grad():
   pred9 = torch.randn(B, R, R, 9, generator=g) * 50
   dev = 'cuda'
   oh, ol = torch.empty(2 * B, R, R, 1, device=dev), torch.empty(2 * B, R, R, 1, device=dev)
-  call('immb_vgg_prologue', gt.to(dev), pred9.to(dev), 9, B, R, oh, ol, ST())
+  call('immb_vgg_prologue', gt.to(dev), pred9.to(dev), 9, B, R, 0, oh, ol, ST())
   ims = torch.cat([gt, pred9[..., :3]], 0).double()
   ref = ims.mean(3, keepdim=True) / 255.0 - O.VGG_MEAN / 255.0
   assert rel_err(oh + ol, ref) < 1e-5
@@ -329,10 +338,70 @@ def test_vgg_prologue_and_pred_grad():
   coef = torch.tensor([-0.37])
   gv = torch.randn(B, R, R, 1, generator=g)
   gh, gl = torch.empty(B, R, R, 9, device=dev), torch.empty(B, R, R, 9, device=dev)
-  call('immb_pred_grad', gt.to(dev), pred9.to(dev), 9, mask.to(dev), coef.to(dev), gv.to(dev), B, R, gh, gl, ST())
+  call('immb_pred_grad', gt.to(dev), pred9.to(dev), 9, mask.to(dev), coef.to(dev), gv.to(dev), 0, B, R, gh, gl, ST())
   ref = torch.zeros(B, R, R, 9, dtype=torch.float64)
   ref[..., :3] = -0.37 * mask.double() * (gt.double() - pred9[..., :3].double()) + gv.double() / (3 * 255.0)
   assert rel_err(gh + gl, ref) < 1e-5
+
+
+def test_vgg_patch_prologue_and_adjoint():
+  """conv1_1 (Cin=1, 3x3) == 1x1 conv over 3x3 patches; pred_grad applies the adjoint of the patch extraction."""
+  B, R = 2, 16
+  g = torch.Generator().manual_seed(6)
+  gt = torch.rand(B, R, R, 3, generator=g) * 255
+  pred12 = torch.zeros(B, R, R, 12)
+  pred12[..., :9] = torch.randn(B, R, R, 9, generator=g) * 50
+  dev = 'cuda'
+  ph, pl = torch.empty(2 * B, R, R, 12, device=dev), torch.empty(2 * B, R, R, 12, device=dev)
+  call('immb_vgg_prologue', gt.to(dev), pred12.to(dev), 12, B, R, 1, ph, pl, ST())
+  ims = torch.cat([gt, pred12[..., :3]], 0).double().requires_grad_(True)
+  gray = ims.mean(3, keepdim=True) / 255.0 - O.VGG_MEAN / 255.0
+  pad = torch.nn.functional.pad(gray[..., 0], (1, 1, 1, 1))
+  patches = torch.stack([pad[:, r:r + R, s:s + R] for r in range(3) for s in range(3)], dim=-1)
+  assert rel_err((ph + pl)[..., :9], patches) < 1e-5
+  assert float((ph + pl)[..., 9:].abs().max()) == 0.0
+  gp = torch.randn(2 * B, R, R, 9, generator=g)
+  patches.backward(gp.double())
+  gfull = torch.zeros(B, R, R, 12)
+  gfull[..., :9] = gp[B:]
+  coef = torch.tensor([0.0])
+  gh, gl = torch.empty(B, R, R, 12, device=dev), torch.empty(B, R, R, 12, device=dev)
+  call('immb_pred_grad', gt.to(dev), pred12.to(dev), 12, None, coef.to(dev), gfull.to(dev), 1, B, R, gh, gl, ST())
+  assert rel_err((gh + gl)[..., :3], ims.grad[B:]) < 1e-5
+
+
+def test_first_layer_rowwin_tcgen05():
+  """7x7 / Cin=3 encoder conv_1 on the tensor cores via the staged row-window image (fwd + wgrad)."""
+  N, R, Cout = 2, 32, 32
+  g = torch.Generator().manual_seed(8)
+  img = torch.rand(N, R, R, 3, generator=g) * 255
+  w = torch.randn(7, 7, 3, Cout, generator=g) * 0.01
+  b = torch.randn(Cout, generator=g)
+  xd, wd = img.double().requires_grad_(True), w.double().requires_grad_(True)
+  y_ref = O.conv2d_same(xd, wd, b.double(), 1)
+  gy = torch.randn(y_ref.shape, generator=g)
+  y_ref.backward(gy.double())
+  dev = 'cuda'
+  d = conv_desc(N, R, R, 3, Cout, 7, 1, xcs=4, engine=_lib.ENGINE_TC)
+  d.x_layout = _lib.XLAYOUT_ROWWIN4
+  assert _lib.lib().immb_conv_engine_for(d, 0) == _lib.ENGINE_TC and _lib.lib().immb_conv_engine_for(d, 2) == _lib.ENGINE_TC
+  sh, sl = torch.empty(N, R, R + 8, 4, device=dev), torch.empty(N, R, R + 8, 4, device=dev)
+  call('immb_stage_image_rowwin', img.to(dev), N, R, R, sh, sl, ST())
+  ref = torch.zeros(N, R, R + 8, 4)
+  ref[:, :, 3:3 + R, :3] = img
+  assert rel_err(sh + sl, ref) < 1e-6
+  wph, wpl = torch.empty(7, Cout, 32, device=dev), torch.empty(7, Cout, 32, device=dev)
+  call('immb_pack_weights_rowwin', w.to(dev), Cout, wph, wpl, ST())
+  y = torch.full((N, R, R, Cout), float('nan'), device=dev)
+  call('immb_conv2d_fwd', d, sh, sl, None, wph, wpl, b.to(dev), y, None, ST())
+  torch.cuda.synchronize()
+  assert rel_err(y, y_ref) < 2e-5, rel_err(y, y_ref)
+  gh, gl = split(gy)
+  dw = torch.full((7, 7, 3, Cout), float('nan'), device=dev)
+  ws = torch.empty(16, dtype=torch.uint8, device=dev)
+  call('immb_conv2d_wgrad', d, sh, sl, gh.to(dev), gl.to(dev), dw, ws, 16, ST())
+  torch.cuda.synchronize()
+  assert rel_err(dw, wd.grad) < 2e-5, rel_err(dw, wd.grad)
 
 
 def test_resize_align_corners_fwd_bwd():

@@ -41,7 +41,7 @@ def _check_step(eng, st64, st32, r64, r32):
   # reconstruction
   pred = eng.pred[..., :3].cpu()
   assert rel_err(pred, out['future_im_pred']) < 1e-3
-  assert rel_err(eng.pose_conv.y.cpu(), out['heatmaps']) < 1e-3
+  assert rel_err(eng.pose_conv.y[..., :eng.K].cpu(), out['heatmaps']) < 1e-3
   # gradients: compare with the fp64 oracle; tolerance = max(5x the fp32 oracle's own error, 1e-2)
   worst = []
   for k, g64 in r64['grads'].items():

@@ -30,3 +30,20 @@ def timed(fn, n=3):
 print('fwd %.2f ms' % timed(lambda: eng.forward(inp['image'], inp['future_image'], inp['mask'])))
 print('bwd %.2f ms' % timed(lambda: eng.backward()))
 print('opt %.2f ms' % timed(lambda: eng.optimizer_step()))
+
+# per-call attribution (CUDA events around every C-ABI call)
+_lib.PROFILE = []
+eng.train_step(inp['image'], inp['future_image'], inp['mask'])
+torch.cuda.synchronize()
+import collections
+by = collections.defaultdict(float); by_k = collections.defaultdict(float)
+for name, tag, a, b in _lib.PROFILE:
+  ms_ = a.elapsed_time(b); by[(tag, name)] += ms_; by_k[name] += ms_
+_lib.PROFILE = None
+tot = sum(by.values())
+print('sum of per-call times %.2f ms' % tot)
+for (tag, name), v in sorted(by.items(), key=lambda kv: -kv[1])[:45]:
+  print('  %-34s %-28s %7.3f ms' % (tag, name.replace('immb_', ''), v))
+print('by kernel family:')
+for name, v in sorted(by_k.items(), key=lambda kv: -kv[1])[:14]:
+  print('  %-28s %7.3f ms' % (name.replace('immb_', ''), v))
