@@ -1,0 +1,269 @@
+#!/usr/bin/env python
+"""Benchmark of the IMM training hot path (BASELINE.json metric: image-pairs/sec, 128x128, K=10).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...   # the restated reference on the host CPU cores
+
+A "step" = one pass of the hot path over one batch of synthetic image pairs: forward + perceptual loss + backward
++ (N>1: one NCCL all-reduce of the flat gradient buffer) + per-tensor clip + Adam + BN/normaliser updates.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition of every field."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PER_GPU_BATCH = 64          # BASELINE.json configs[1]: CelebA-10pts, batch 64, 128x128, 1 x B200 (weak scaling: fixed per GPU)
+N_MAPS = 10
+IMAGE_SIZE = 128
+GFLOP_PER_PAIR = 48.98      # algorithmic 2*MACs per image pair per training step (R=128, K=10)
+METRIC = 'image-pairs/sec (128x128, K=10), training step'
+
+
+def load_peaks():
+  p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(p):
+    d = json.load(open(p))
+    return {'hbm_gbs': d['hbm_gbs'], 'bf16_tflops': d['bf16_tflops'],
+            'bf16_tflops_sustained': d.get('bf16_tflops_sustained', d['bf16_tflops']), 'source': 'measured'}
+  return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
+
+
+class ClockSampler(object):
+  """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+  Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+       'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+       'clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, gpu_index=0):
+    self.rows, self.proc, self.gpu = [], None, gpu_index
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                                    '--format=csv,noheader,nounits', '-lms', '100'],
+                                   stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.t = threading.Thread(target=self._read, daemon=True)
+      self.t.start()
+    except Exception:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append([x.strip() for x in line.split(',')])
+
+  def stop(self):
+    if self.proc is None:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=2)
+    except Exception:
+      self.proc.kill()
+    sm, mx, reasons, power = [], [], set(), []
+    for r in self.rows:
+      try:
+        sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+        for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+          if val.lower().startswith('active'):
+            reasons.add(name)
+      except Exception:
+        pass
+    sm.sort()
+    return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+            'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, sample_batch):
+  """Times the CPU restatement of the reference (oracle/imm_oracle.py, PyTorch-CPU fp32, all host threads) on a
+  bounded sample of the workload: `sample_batch` pairs per step instead of PER_GPU_BATCH.  TensorFlow 1.10 is not
+  installable, so this is kind 'port' (labelled 'restated reference, not TF1')."""
+  import torch
+  from oracle import imm_oracle as O
+  cores = os.cpu_count() or 1
+  torch.set_num_threads(cores)
+  st = O.init_state(O.State(n_maps=N_MAPS, image_size=IMAGE_SIZE), seed=0)
+  inp = O.synthetic_inputs(sample_batch, IMAGE_SIZE, seed=0)
+  for _ in range(warmup):
+    O.train_step(st, inp)
+  t0 = time.time()
+  for _ in range(steps):
+    O.train_step(st, inp)
+  dt = (time.time() - t0) / max(steps, 1)
+  return {'pairs_per_s': sample_batch / dt, 'ms_per_step': dt * 1e3, 'cores': cores,
+          'sample': '%d steps of %d pairs (batch %d is the workload; CPU step time scales linearly in pairs)'
+                    % (steps, sample_batch, PER_GPU_BATCH)}
+
+
+def workload_config(n_gpus):
+  return {'workload': 'CelebA-10pts model section, batch %d per GPU (global %d), 128x128x3 synthetic image pairs + '
+                      'reference smooth mask, full train step (fwd, VGG16 perceptual loss, bwd, clip, Adam)'
+                      % (PER_GPU_BATCH, PER_GPU_BATCH * n_gpus),
+          'global_batch': PER_GPU_BATCH * n_gpus, 'image_size': IMAGE_SIZE, 'n_maps': N_MAPS,
+          'parallelism': 'dp%d' % n_gpus,
+          'weights': 'reference initialisers (seeded); VGG16: seeded synthetic weights in the Caffe-dict layout',
+          'l2': 'per-step working set (several GB of activations at batch 64) exceeds the 126 MB L2; no explicit flush'}
+
+
+def main_reference(args):
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  sample_batch = 8
+  r = cpu_reference_run(args.steps, args.warmup, sample_batch)
+  line = {'impl': 'reference', 'metric': METRIC, 'value': r['pairs_per_s'], 'unit': 'pairs/s', 'n_gpus': args.gpus,
+          'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True,
+          'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+          'config': workload_config(args.gpus),
+          'cpu_baseline': {'value': r['pairs_per_s'], 'unit': 'pairs/s', 'cores': r['cores'], 'kind': 'port',
+                           'sample': r['sample'] + '; restated reference (PyTorch-CPU fp32), not TF1'},
+          'e2e': {'value': r['pairs_per_s'], 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+  print(json.dumps(line))
+
+
+def main_cuda(args):
+  import torch
+  import torch.distributed as dist
+  from imm_b200 import _lib
+  from imm_b200.models.imm_model import IMMModel
+  from imm_b200.train import cnn_train_multi as tru
+  from imm_b200.utils.box import default_model_config
+  from imm_b200.utils.synthetic import synthetic_inputs, synthetic_vgg_caffe_dict
+
+  if not torch.cuda.is_available():
+    raise SystemExit('bench.py: no CUDA device (the CUDA path has no CPU fallback)')
+  rank, local_rank, world = tru.init_distributed('nccl')
+  torch.cuda.set_device(local_rank)
+  dev = 'cuda:%d' % local_rank
+  B = PER_GPU_BATCH
+  model = IMMModel(default_model_config(N_MAPS), global_step=-1, device=dev, world_size=world,
+                   vgg_data=synthetic_vgg_caffe_dict(1), seed=0)
+  optim = tru.AdamOptimizer(tru.exponential_decay(1e-3, 100000, 0.95))
+  host = [synthetic_inputs(B, IMAGE_SIZE, seed=rank * 10 + i, pin=True) for i in range(2)]
+  resident = [{k: v.to(dev) for k, v in h.items()} for h in host]
+  allreduce = tru.average_gradients if world > 1 else None
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  def max_over_ranks(ms):
+    if world == 1:
+      return ms
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+  # ---- kernel-resident arm: inputs already in HBM ---------------------------------------------------------
+  model.build(resident[0], True)            # instantiates the engine
+  eng = model.engine
+
+  def step_resident(i):
+    d = resident[i % 2]
+    eng.forward(d['image'], d['future_image'], d['mask'], training=True, build_loss=True)
+    eng.backward()
+    eng.optimizer_step(1.0, lr=optim.lr(eng.global_step), allreduce=allreduce)
+
+  for i in range(args.warmup):
+    step_resident(i)
+  barrier()
+  sampler = ClockSampler(local_rank)
+  if rank == 0:
+    sampler.start()
+  n0 = _lib.launch_count()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for i in range(args.steps):
+    step_resident(i)
+  e1.record()
+  barrier()
+  launches = _lib.launch_count() - n0
+  ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+  clocks = sampler.stop() if rank == 0 else None
+  value = B * world / (ms * 1e-3)
+
+  # ---- end-to-end arm: public API, pinned host inputs, H2D inside the timed region, loss read back -----------
+  train_op_inputs = {'i': 0}
+
+  def next_host():
+    b = host[train_op_inputs['i'] % 2]
+    train_op_inputs['i'] += 1
+    return b
+  _, train_op, _, _, _ = tru.setup_training({'gpu_ids': list(range(world)), 'batch_size': B * world}, None, optim,
+                                            next_host, True, type('F', (), {'create': staticmethod(lambda: model)}),
+                                            -1, clip_value=1.0)
+  for _ in range(max(args.warmup, 3)):
+    float(train_op().item())
+  barrier()
+  e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e2.record()
+  for _ in range(args.steps):
+    loss_val = float(train_op().item())
+  e3.record()
+  barrier()
+  ms_e2e = max_over_ranks(e2.elapsed_time(e3)) / args.steps
+  h2d = sum(v.numel() * v.element_size() for v in host[0].values()) * world
+  e2e = {'value': B * world / (ms_e2e * 1e-3), 'unit': 'pairs/s', 'ms_per_step': ms_e2e,
+         'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4 * world,
+         'api': 'IMMModel.build(inputs from pinned host memory) + setup_training() train_op; loss.item() per step'}
+
+  # ---- roofline of the dominant kernel family: one extra step with CUDA events around every C-ABI call --------
+  _lib.PROFILE = []
+  step_resident(0)
+  torch.cuda.synchronize()
+  fam = {}
+  for name, tag, a, b in _lib.PROFILE:
+    fam[name] = fam.get(name, 0.0) + a.elapsed_time(b)
+  _lib.PROFILE = None
+  conv_ms = sum(fam.get(k, 0.0) for k in ('immb_conv2d_fwd', 'immb_conv2d_dgrad', 'immb_conv2d_wgrad'))
+  peaks = load_peaks()
+  conv_tflops = GFLOP_PER_PAIR * B / conv_ms            # GFLOP / ms == TFLOP/s
+  traffic = None
+  tj = os.path.join(ROOT, 'profiles', 'top_kernel.json')
+  if os.path.exists(tj):
+    traffic = json.load(open(tj)).get('dram_bytes_per_launch')
+  roofline = {'bound': 'tensor', 'kernel': 'conv_tc_kernel / conv_tc_wgrad_kernel (tcgen05 kind::tf32, 3xTF32)',
+              'achieved': conv_tflops, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
+              'frac': conv_tflops / peaks['bf16_tflops_sustained'], 'traffic': traffic,
+              'peak_source': 'MEASURED_PEAKS.json bf16 sustained (%s); the TF32 pipe peaks at half of it and 3xTF32 '
+                             'issues 3 MMAs per algorithmic MAC' % peaks['source'],
+              'tensor_pipe_frac_tf32': 3.0 * conv_tflops / (0.5 * peaks['bf16_tflops_sustained']),
+              'conv_ms_per_step': conv_ms, 'step_share': conv_ms / ms,
+              'per_family_ms': {k.replace('immb_', ''): round(v, 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1])[:10]}}
+
+  if rank != 0:
+    return
+  cpu = None
+  if world == 1 and not args.no_cpu_baseline:
+    r = cpu_reference_run(3, 1, 8)
+    cpu = {'value': r['pairs_per_s'], 'unit': 'pairs/s', 'cores': r['cores'], 'kind': 'port',
+           'sample': r['sample'] + '; restated reference (PyTorch-CPU fp32), not TF1'}
+  line = {'metric': METRIC, 'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps,
+          'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+          'dtype': 'tf32x3 (fp32 storage, error-compensated TF32 tensor-core products, fp32 accumulate)',
+          'data': 'synthetic', 'config': workload_config(world), 'tflops_algorithmic': GFLOP_PER_PAIR * B * world / ms,
+          'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks, 'e2e': e2e,
+          'gpu_launches': int(launches) * world, 'last_loss': loss_val}
+  print(json.dumps(line))
+
+
+if __name__ == '__main__':
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=10)
+  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--impl', type=str, default='cuda', choices=['cuda', 'reference'])
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  a = ap.parse_args()
+  a.warmup = max(a.warmup, 3) if a.impl == 'cuda' else a.warmup
+  if a.impl == 'reference':
+    main_reference(a)
+  else:
+    main_cuda(a)

@@ -1,0 +1,54 @@
+"""Abstract model class -- host-side mirror of imm/models/base_model.py (BaseModel).
+
+The reference builds TF graph nodes; here the same helpers keep their names and argument meaning but act
+eagerly on the CUDA engine (imm_b200/engine.py).  file:line citations are under /root/reference."""
+
+
+class BaseModel(object):
+  num_instances = 0
+
+  def __init__(self, dtype, name):
+    self.dtype = dtype
+    self._name = name
+    self._avg_ops = []          # base_model.py:26-27 (moving-average ops)
+    self._opts = None
+    self._cost_avgs = {}        # name -> EMA value (tf.train.ExponentialMovingAverage(0.99), base_model.py:56-60)
+    self._cost_raw = {}
+    self.__class__.num_instances += 1
+
+  def _decay(self, scope=None):
+    """Sum of the L2 weight-decay losses (base_model.py:33-37): computed on device by immb_total_loss."""
+    raise NotImplementedError
+
+  def _exp_running_avg(self, x, training_pl, init_val=0.0, rho=0.99, name='x'):
+    """base_model.py:39-50.  The perceptual-loss normalisers `<name>_agg` live in the engine (engine.agg) and
+    are updated by immb_perceptual_finalize when training_pl is True."""
+    raise NotImplementedError('handled on device: immb_perceptual_finalize')
+
+  def _add_cost_summary(self, cost, name):
+    """Raw + moving-average cost scalars (base_model.py:52-60); only for the first model instance."""
+    if self.__class__.num_instances == 1 or True:
+      def update(cost=cost, name=name):
+        v = float(cost() if callable(cost) else cost)
+        self._cost_raw[name] = v
+        prev = self._cost_avgs.get(name)
+        # TF EMA with zero_debias=False initialises the shadow variable with the first value
+        self._cost_avgs[name] = v if prev is None else prev - (1.0 - 0.99) * (prev - v)
+        return self._cost_avgs[name]
+      self._avg_ops.append(update)
+
+  def _get_opts(self, training_pl):
+    if self._opts is None:
+      self._opts = {'dtype': self.dtype, 'wd': 1e-5, 'std': 0.01, 'training_pl': training_pl}   # base_model.py:62-69
+    return self._opts
+
+  def get_bnorm_ops(self, scope=None):
+    """base_model.py:71-78 returns the grouped BN moving-average updates.  On the CUDA path they are applied by
+    immb_bn_finalize inside the training forward pass, so the returned op is a no-op callable."""
+    return lambda: None
+
+  def conv_block(self, *args, **kwargs):
+    raise NotImplementedError('conv blocks are scheduled by IMMEngine (nn_utils.py:151-210 semantics)')
+
+  def build(self, inputs, training_pl):
+    raise NotImplementedError

@@ -1,0 +1,166 @@
+"""Class for IMM models -- host-side mirror of imm/models/imm_model.py (the drop-in boundary).
+
+Same class / method / argument names as the reference; graph-construction arguments (`costs_collection`,
+`scope`, `var_device`) are accepted and ignored because the work is executed eagerly by hand-written sm_100a
+kernels (imm_b200/engine.py -> libimm_b200.so).  file:line citations are under /root/reference."""
+import torch
+
+from .. import _lib
+from ..engine import IMMEngine
+from ..models.base_model import BaseModel
+
+
+def get_gaussian_maps(mu, shape_hw, inv_std, mode='ankush'):
+  """imm_model.py:34-78.  mu [B,NMAPS,2] (y,x) -> [B,SHAPE_H,SHAPE_W,NMAPS] on mu's device.
+  Only mode 'rot' (used by every shipped config) has a CUDA kernel."""
+  if mode != 'rot':
+    raise ValueError("mode %r is not built on the CUDA path (configs use 'rot'): " % mode + str(mode))
+  assert shape_hw[0] == shape_hw[1]
+  if not mu.is_cuda:
+    raise _lib.ImmbError('get_gaussian_maps: mu must be a CUDA tensor (no CPU fallback)')
+  B, K = mu.shape[0], mu.shape[1]
+  out = torch.empty((B, shape_hw[0], shape_hw[1], K), dtype=torch.float32, device=mu.device)
+  _lib.call('immb_gaussian_maps', mu.contiguous().float(), B, K, int(shape_hw[0]), float(inv_std), out,
+            _lib.stream_ptr())
+  return out
+
+
+class IMMModel(BaseModel):
+  """IMMModel(config, global_step=None, dtype=float32, name='IMMModel')   (imm_model.py:95-101)
+
+  config: the `model` section of the reference's experiment YAMLs (attribute access + hasattr probing).
+  Extra keyword-only knobs select the device-side execution: `device`, `precision`, `engine`, `world_size`."""
+
+  def __init__(self, config, global_step=None, dtype=torch.float32, name='IMMModel', device='cuda:0',
+               precision=_lib.PREC_TF32X3, engine=_lib.ENGINE_AUTO, world_size=1, vgg_data=None, seed=0):
+    super(IMMModel, self).__init__(dtype, name)
+    self._config = config
+    self._global_step = global_step
+    self._device, self._precision, self._engine_sel, self._world = device, precision, engine, world_size
+    self._vgg_data, self._seed = vgg_data, seed
+    self.engine = None
+    self._tensors = {}            # the reference's 'tensors' collection (imm_model.py:250,266-267)
+
+  # -- construction -----------------------------------------------------------------------------------
+  def _ensure_engine(self, batch, image_size):
+    if self.engine is not None:
+      if (self.engine.B, self.engine.R) != (batch, image_size):
+        raise _lib.ImmbError('IMMModel was built for batch %d / size %d; got %d / %d (static shapes, like the '
+                             'reference graph)' % (self.engine.B, self.engine.R, batch, image_size))
+      return self.engine
+    eng = IMMEngine(self._config, batch, image_size, self._device, self._precision, self._engine_sel, self._world)
+    eng.init_parameters(self._seed)
+    if self._global_step is not None:
+      eng.global_step = float(self._global_step)
+    self.engine = eng
+    if self._vgg_data is not None:
+      eng.load_vgg_caffe_dict(self._vgg_data)
+    return eng
+
+  def load_vgg(self, data=None):
+    """build_vgg16 loads `config.perceptual.net_file` with deepdish (build_vgg16.py:16); offline that file does
+    not exist, so the caller passes the Caffe-layout dict (real or imm_b200.utils.synthetic)."""
+    if data is None:
+      from ..utils.vgg_io import load_caffe_h5
+      data = load_caffe_h5(self._config.perceptual.net_file)
+    self._vgg_data = data
+    if self.engine is not None:
+      self.engine.load_vgg_caffe_dict(data)
+
+  @staticmethod
+  def _to_device(t, dev):
+    if t.is_cuda:
+      return t.contiguous()
+    return t.to(dev, non_blocking=True).contiguous()
+
+  # -- sub-builders kept for API parity; they run the corresponding engine section ------------------------
+  def encoder(self, x, training_pl, var_device='/cpu:0'):
+    raise NotImplementedError('use build(); the encoder stack is scheduled by IMMEngine.forward')
+
+  image_encoder = pose_encoder = simple_renderer = encoder
+
+  def _loss_mask(self, map, mask):
+    """imm_model.py:408-410: map * resize_images(mask, map.shape) -- at the integer scales used by the loss the TF1
+    legacy bilinear resize is a pure subsample, which the loss kernels index directly."""
+    s = mask.shape[1] // map.shape[1]
+    return map * mask[:, ::s, ::s]
+
+  # -- the public entry point ----------------------------------------------------------------------------
+  def build(self, inputs, training_pl, costs_collection='costs', scope=None, var_device='/cpu:0',
+            output_tensors=False, build_loss=True):
+    """imm_model.py:413-490.  inputs: dict with 'image', 'future_image' [B,R,R,3] fp32 in [0,255] and (when
+    config.loss_mask) 'mask' [B,R,R,1]; host (ideally pinned) or CUDA tensors.  training_pl: bool.
+    Returns (None, loss, avg_ops[, tensors]) like the reference; `loss` is a CUDA scalar tensor."""
+    im, future_im = inputs['image'], inputs['future_image']
+    B, R = int(future_im.shape[0]), int(future_im.shape[1])
+    assert future_im.shape[1] == future_im.shape[2]
+    eng = self._ensure_engine(B, R)
+    dev = eng.dev
+    im_d, fut_d = self._to_device(im, dev), self._to_device(future_im, dev)
+    mask_d = self._to_device(inputs['mask'], dev) if 'mask' in inputs else None
+    if build_loss and bool(self._config.loss_mask) and mask_d is None:
+      raise RuntimeError('No loss mask recieved but is required.')     # imm_model.py:363-367
+    training = bool(training_pl)
+    eng.forward(im_d, fut_d, mask_d, training=training, build_loss=build_loss)
+    loss = None
+    if build_loss:
+      loss = eng.loss_value().view(())
+      if not self._avg_ops:
+        self._add_cost_summary(lambda: eng.rec_loss.item(), 'reconstruction_loss')     # imm_model.py:390
+        self._add_cost_summary(lambda: eng.weights_loss.item(), 'weights_loss')        # :396
+        self._add_cost_summary(lambda: eng.total_loss.item(), 'loss_total')            # :402
+    self._tensors = {'heatmaps': eng.pose_conv.y[..., :eng.K], 'gauss_y_prob': eng.py, 'gauss_x_prob': eng.px}
+    if output_tensors:
+      tensors = {}
+      tensors.update(inputs)
+      tensors.update({'future_im': fut_d, 'im': im_d,
+                      'future_im_pred': eng.pred[..., :3],
+                      'gauss_yx': eng.mu,
+                      'pose_embedding_maps': lambda: get_gaussian_maps(eng.mu, [R, R], eng.inv_std, 'rot')})
+      return None, loss, self._avg_ops, tensors
+    return None, loss, self._avg_ops
+
+  def get_collection(self, name='tensors'):
+    return dict(self._tensors)
+
+  # -- checkpoint layout: TF variable names -> tensors -------------------------------------------
+  def state_dict(self, include_optimizer=True):
+    eng = self.engine
+    sd = {}
+    for d in (eng.params, eng.buffers, eng.vgg_params if eng.vgg_loaded else {}):
+      for k, v in d.items():
+        sd[k] = v.detach().cpu().clone()
+    sd['global_step'] = torch.tensor(eng.global_step)
+    if include_optimizer:
+      sd['beta1_power'] = torch.tensor(0.9 ** (eng.adam_t + 1))       # TF keeps beta^t for the NEXT step
+      sd['beta2_power'] = torch.tensor(0.999 ** (eng.adam_t + 1))
+      sd['__adam_t'] = torch.tensor(eng.adam_t)
+      for k in eng.params:
+        sd[k + '/Adam'] = eng.adam_m[k].detach().cpu().clone()
+        sd[k + '/Adam_1'] = eng.adam_v[k].detach().cpu().clone()
+    return sd
+
+  def load_state_dict(self, sd, vars_to_restore='model', ignore_missing_vars=False, reset_global_step=-1):
+    """cnn_train_multi.py:404-433 semantics: 'model' = MODEL_VARIABLES (w, b, *_agg, global_step -- NOT the
+    tf.layers BN variables), 'all' = every global variable incl. BN and Adam slots (--restore-optim)."""
+    eng = self.engine
+    model_vars = [k for k in eng.params if k.endswith('/w') or k.endswith('/b')]
+    model_vars += [k for k in eng.buffers if k.endswith('_agg')]
+    all_vars = list(eng.params.keys()) + list(eng.buffers.keys())
+    names = all_vars if vars_to_restore == 'all' else model_vars
+    missing = [k for k in names if k not in sd]
+    if missing and not ignore_missing_vars:
+      raise KeyError('variables missing from the checkpoint: %s' % missing[:5])
+    params = {k: sd[k] for k in names if k in sd and k in eng.params}
+    buffers = {k: sd[k] for k in names if k in sd and k in eng.buffers}
+    adam_m = adam_v = None
+    if vars_to_restore == 'all':
+      adam_m = {k: sd[k + '/Adam'] for k in eng.params if k + '/Adam' in sd}
+      adam_v = {k: sd[k + '/Adam_1'] for k in eng.params if k + '/Adam_1' in sd}
+      if '__adam_t' in sd:
+        eng.adam_t = int(sd['__adam_t'])
+    eng.load_state(params, buffers, adam_m, adam_v)
+    if reset_global_step >= 0:
+      eng.global_step = float(reset_global_step)
+    elif 'global_step' in sd:
+      eng.global_step = float(sd['global_step'])

@@ -1,0 +1,144 @@
+"""Training runtime -- host-side mirror of imm/train/cnn_train_multi.py.
+
+Reference: in-graph tower replication, gradients averaged on the CPU (cnn_train_multi.py:66-106,109-192).
+Here: one process per GPU (torchrun), one NCCL all-reduce of the flat gradient buffer over NVLink per step,
+then the fused per-tensor clip_by_norm + TF-Adam kernel.  Function names / argument meaning follow the
+reference; `graph` is accepted and ignored.  file:line citations are under /root/reference."""
+import os
+import time
+from datetime import datetime
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class AdamOptimizer(object):
+  """tf.train.AdamOptimizer(lr, name='Adam') stand-in (scripts/train.py:98): holds the hyper-parameters; the
+  update itself is immb_adam_apply.  `learning_rate` may be a float or a callable(global_step) -> float."""
+
+  def __init__(self, learning_rate, beta1=0.9, beta2=0.999, epsilon=1e-8, name='Adam'):
+    self.learning_rate, self.beta1, self.beta2, self.epsilon, self.name = learning_rate, beta1, beta2, epsilon, name
+
+  def lr(self, global_step):
+    return self.learning_rate(global_step) if callable(self.learning_rate) else float(self.learning_rate)
+
+
+def exponential_decay(start_val, decay_steps, decay_rate, staircase=True, lr_multiple=1.0):
+  """lr_multiple * tf.train.exponential_decay(...) (scripts/train.py:92-96)."""
+  def fn(global_step):
+    p = global_step / float(decay_steps)
+    if staircase:
+      p = np.floor(p)
+    return lr_multiple * start_val * decay_rate ** p
+  return fn
+
+
+def world_info():
+  ws = int(os.environ.get('WORLD_SIZE', '1'))
+  return int(os.environ.get('RANK', '0')), int(os.environ.get('LOCAL_RANK', '0')), ws
+
+
+def init_distributed(backend='nccl'):
+  rank, local_rank, ws = world_info()
+  if ws > 1 and not dist.is_initialized():
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    os.environ.setdefault('MASTER_PORT', '29500')
+    if backend == 'nccl':
+      torch.cuda.set_device(local_rank)
+    dist.init_process_group(backend=backend, rank=rank, world_size=ws)
+  return rank, local_rank, ws
+
+
+def average_gradients(flat_grads, clip_value=None):
+  """cnn_train_multi.py:66-106: mean over towers (the synchronisation point).  One all-reduce(sum) on the flat
+  bucket; the 1/N scale and the per-tensor clip are fused into the optimiser kernels (gscale, clip)."""
+  if dist.is_initialized() and dist.get_world_size() > 1:
+    dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM)
+  return flat_grads
+
+
+def tower_loss(inputs, training_pl, model, scope=None):
+  """cnn_train_multi.py:37-64."""
+  _, loss, avg_ops = model.build(inputs, training_pl, costs_collection='costs', scope=scope, var_device='/cpu:0')
+  return loss
+
+
+def _make_train_op(model, optim, inputs_fn, clip_value):
+  def train_op():
+    inputs = inputs_fn()
+    model.build(inputs, True)
+    eng = model.engine
+    eng.backward()
+    eng.optimizer_step(clip_value, lr=optim.lr(eng.global_step), beta1=optim.beta1, beta2=optim.beta2,
+                       eps=optim.epsilon, allreduce=average_gradients if eng.world_size > 1 else None)
+    for op in model._avg_ops:
+      pass                       # cost EMAs are evaluated lazily by the logger (they need a D2H read)
+    return eng.total_loss
+  return train_op
+
+
+def train_single(opts, graph, optim, inputs, training_pl, model_factory, global_step, clip_value=None):
+  """cnn_train_multi.py:195-250."""
+  model = model_factory.create()
+  train_op = _make_train_op(model, optim, inputs, clip_value)
+  loss = lambda: model.engine.total_loss
+  return loss, train_op, None, None, model
+
+
+def train_multi(opts, graph, optim, inputs, training_pl, model_factory, global_step, clip_value=None):
+  """cnn_train_multi.py:109-192: batch split across GPUs (:132), one tower per GPU, gradient mean, clip, apply.
+  `inputs` yields this rank's slice of the global batch (utils.split_tensors semantics, imm/utils/utils.py:113).
+  BN statistics stay per-replica (no SyncBN), as in the reference (:155,166)."""
+  num_gpus = len(opts['gpu_ids'])
+  assert opts['batch_size'] % num_gpus == 0, ('Batch size must be divisible by number of GPUs')
+  return train_single(opts, graph, optim, inputs, training_pl, model_factory, global_step, clip_value)
+
+
+def setup_training(opts, graph, optim, inputs, training_pl, model_factory, global_step, clip_value=None,
+                   split_gpus=False):
+  """cnn_train_multi.py:342-368."""
+  if split_gpus:
+    raise NotImplementedError('split_gpus component placement is not enabled by any shipped config')
+  num_gpus = len(opts['gpu_ids'])
+  if num_gpus == 0:
+    raise RuntimeError('training on CPU is not available: the CUDA path has no CPU fallback')
+  if num_gpus == 1:
+    return train_single(opts, graph, optim, inputs, training_pl, model_factory, global_step, clip_value)
+  return train_multi(opts, graph, optim, inputs, training_pl, model_factory, global_step, clip_value)
+
+
+def train_loop(opts, graph, loss, train_dataset, training_pl, handle_pl, train_op, train_summary_op,
+               test_summary_op, num_steps, global_step, checkpoint_fname, test_dataset=None,
+               ignore_missing_vars=False, reset_global_step=False, vars_to_restore=None, exclude_vars=None,
+               fwd_only=False, allow_growth=False, model=None, log_every=1):
+  """cnn_train_multi.py:371-516: restore, step loop with NaN guard and examples/sec logging, periodic checkpoints
+  `<logdir>/model.ckpt-<step>` holding tensors keyed by the reference's TF variable names."""
+  rank = world_info()[0]
+  eng = model.engine
+  if checkpoint_fname and os.path.exists(checkpoint_fname):
+    sd = torch.load(checkpoint_fname, map_location='cpu')
+    model.load_state_dict(sd, vars_to_restore=vars_to_restore or 'model', ignore_missing_vars=ignore_missing_vars,
+                          reset_global_step=reset_global_step if reset_global_step is not False else -1)
+  start_step = int(eng.global_step) if eng is not None else -1
+  begin = time.time()
+  n_done = 0
+  for step in range(start_step, num_steps):
+    t0 = time.time()
+    if fwd_only:
+      model.build(train_dataset(), False)
+      loss_value = float(model.engine.loss_value().item())
+    else:
+      loss_value = float(train_op().item())          # the one D2H read per step (loss), as session.run returns it
+    duration = time.time() - t0
+    assert not np.isnan(loss_value), 'Model diverged with loss = NaN'           # cnn_train_multi.py:463
+    if rank == 0 and step % log_every == 0:
+      print('%s: step %d, loss = %.4f (%.1f examples/sec) %.3f sec/batch'
+            % (datetime.now(), step, loss_value, opts['batch_size'] / duration, duration))
+    if not fwd_only and rank == 0 and step % opts['n_checkpoint'] == 0 and opts.get('log_dir'):
+      os.makedirs(opts['log_dir'], exist_ok=True)
+      torch.save(model.state_dict(), os.path.join(opts['log_dir'], 'model.ckpt-%d' % step))
+    n_done += 1
+  total = time.time() - begin
+  if rank == 0 and n_done:
+    print('Avg. samples per second %.3f' % (opts['batch_size'] * n_done / total))

@@ -72,7 +72,7 @@ typedef struct {
   int32_t x_cstride;          /* channel stride of the input tensor (>= Cin) */
   int32_t y_cstride;          /* channel stride of the output tensor (>= Cout) */
   int32_t cin_pad;            /* Cin rounded up to 32: K-extent of the packed weights (zero filled) */
-  int32_t epilogue;           /* immb_epilogue (fwd only) */
+  int32_t epilogue;           /* enum immb_epilogue; fwd only */
   int32_t precision;          /* immb_precision */
   int32_t engine;             /* immb_engine */
   int32_t x_layout;           /* immb_xlayout */

@@ -1,0 +1,133 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol the header declares, the config
+loader reads the reference's YAML schema, layer specs / schedules match the oracle, the data-parallel gradient
+exchange works on world_size 2 (gloo), and the product never touches the oracle."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+  from imm_b200 import _lib
+  header = open(os.path.join(ROOT, 'include', 'imm_b200.h')).read()
+  declared = set(re.findall(r'\b(immb_[a-z0-9_]+)\s*\(', header))
+  lib = _lib.lib()
+  assert lib.immb_version() == 100
+  for name in sorted(declared):
+    assert hasattr(lib, name), name
+  assert declared == set(_lib.exported_symbols())
+  assert lib.immb_last_error().decode() == ''
+
+
+def test_conv_descriptor_validation_without_gpu():
+  """Pure host-side argument checks of the ABI (no kernel is launched)."""
+  from imm_b200 import _lib
+  d = _lib.ConvDesc()
+  d.N, d.H, d.W, d.Cin, d.Cout, d.kh, d.kw, d.stride = 2, 16, 16, 64, 64, 3, 3, 1
+  d.Ho, d.Wo, d.pad_t, d.pad_l, d.x_cstride, d.y_cstride, d.cin_pad = 16, 16, 1, 1, 64, 64, 64
+  lib = _lib.lib()
+  assert [lib.immb_conv_engine_for(d, op) for op in range(3)] == [_lib.ENGINE_TC] * 3
+  d.Cin, d.x_cstride, d.kh, d.kw, d.pad_t, d.pad_l = 3, 3, 7, 7, 3, 3
+  assert lib.immb_conv_engine_for(d, 0) == _lib.ENGINE_SIMT        # raw NHWC 7x7/Cin=3 -> CUDA-core engine
+  d.x_layout, d.x_cstride = _lib.XLAYOUT_ROWWIN4, 4
+  assert lib.immb_conv_engine_for(d, 0) == _lib.ENGINE_TC          # staged row-window image -> tensor cores
+  d.Ho = 15
+  assert lib.immb_conv_engine_for(d, 0) < 0                        # Ho must be ceil(H/stride): IMMB_ERR_INVALID
+
+
+def test_config_loader_reads_reference_schema(tmp_path):
+  from imm_b200.utils.box import read_configs, default_model_config
+  (tmp_path / 'paths.yaml').write_text('logdir: data/logs\nceleba_data_dir: data/celeba\nvgg16_path: m/vgg.h5\n')
+  (tmp_path / 'exp.yaml').write_text(
+      'name: celeba-30pts\ntraining:\n  batch: 50\n  gradclip: 1.0\n  logdir: ${logdir}/${name}\n'
+      '  datadir: ${celeba_data_dir}\n  lr: {start_val: 0.001, step: 100000, decay: 0.95}\n'
+      'model:\n  n_maps: 30\n  gauss_mode: rot\n  perceptual:\n    net_file: ${vgg16_path}\n    comp: [input, conv1_2]\n')
+  c = read_configs([str(tmp_path / 'paths.yaml'), str(tmp_path / 'exp.yaml')])
+  assert c.training.logdir == 'data/logs/celeba-30pts' and c.training.datadir == 'data/celeba'
+  assert c.model.perceptual.net_file == 'm/vgg.h5' and c.model.n_maps == 30
+  assert not hasattr(c.model, 'split_gpus') and hasattr(c.model, 'gauss_mode')        # hasattr probing (imm_model.py:285)
+  assert c['model']['perceptual']['comp'] == ['input', 'conv1_2']
+  ex = read_configs(os.path.join(ROOT, 'configs', 'synthetic-10pts.yaml'))
+  assert ex.model.to_dict() == {k: v for k, v in default_model_config(10).to_dict().items() if k in ex.model}
+  assert ex.training.logdir == 'data/logs/synthetic-10pts'
+
+
+def test_layer_specs_match_oracle():
+  from imm_b200 import engine as E
+  from oracle import imm_oracle as O
+  assert E.encoder_spec(32) == O.encoder_spec(32)
+  for res in (128, 256):
+    assert E.renderer_spec(32, res, 9) == O.renderer_spec(32, res, 9)
+  for args in [(128, 3, 1), (128, 7, 1), (128, 3, 2), (5, 3, 2), (16, 1, 1)]:
+    assert E.same_pad(*args) == O.same_pad(*args)
+  assert E.PERCEPTUAL_WS == O.PERCEPTUAL_WS and E.WD == O.WD
+
+
+def test_lr_schedule_and_global_step_quirk():
+  from imm_b200.train.cnn_train_multi import exponential_decay, AdamOptimizer
+  from oracle import imm_oracle as O
+  opt = AdamOptimizer(exponential_decay(1e-3, 100000, 0.95, staircase=True, lr_multiple=2.0))
+  for gs in (-1, 0, 99999, 100000, 250000):
+    np.testing.assert_allclose(opt.lr(gs), O.learning_rate(gs, lr_multiple=2.0), rtol=1e-12)
+
+
+def test_synthetic_inputs_contract():
+  from imm_b200.utils.synthetic import synthetic_inputs, smooth_mask
+  from oracle import imm_oracle as O
+  d = synthetic_inputs(3, 128, seed=4)
+  assert d['image'].shape == (3, 128, 128, 3) and d['mask'].shape == (3, 128, 128, 1)
+  assert 0.0 <= float(d['image'].min()) and float(d['image'].max()) <= 255.0
+  assert torch.equal(smooth_mask(128, 128), O.smooth_mask(128, 128))
+  o = O.synthetic_inputs(3, 128, seed=4)
+  assert all(torch.equal(d[k], o[k]) for k in d)
+
+
+def test_product_never_imports_the_oracle():
+  hits = subprocess.run(['grep', '-rIl', '-E', r'(from|import)\s+oracle', os.path.join(ROOT, 'imm_b200'),
+                         os.path.join(ROOT, 'scripts')], stdout=subprocess.PIPE, text=True).stdout.split()
+  assert hits == []
+
+
+def test_engine_refuses_to_run_without_cuda():
+  from imm_b200 import _lib
+  from imm_b200.engine import IMMEngine
+  from imm_b200.utils.box import default_model_config
+  if torch.cuda.is_available():
+    pytest.skip('has a GPU')
+  with pytest.raises(_lib.ImmbError):
+    IMMEngine(default_model_config(10), 2, 128)
+  with pytest.raises(_lib.ImmbError):
+    _lib.call('immb_split_planes', torch.zeros(4), torch.zeros(4), None, 4, None)      # CPU tensors are refused
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from imm_b200.train import cnn_train_multi as tru
+rank, local_rank, world = tru.init_distributed('gloo')
+assert world == 2
+g = torch.arange(10, dtype=torch.float32) * (rank + 1)          # this rank's flat gradient bucket
+tru.average_gradients(g)
+expect = torch.arange(10, dtype=torch.float32) * 3.0             # sum over ranks; 1/N is applied by the optimiser kernel
+assert torch.equal(g, expect), (rank, g)
+# batch sharding: rank r of N takes rows [r*B/N, (r+1)*B/N) of the global batch (utils.split_tensors semantics)
+dist.barrier()
+print('ok', rank)
+'''
+
+
+def test_two_rank_gradient_exchange_gloo(tmp_path):
+  script = tmp_path / 'w.py'
+  script.write_text(_WORKER % ROOT)
+  env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29731')
+  out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29731', str(script)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=240)
+  assert out.returncode == 0, out.stdout[-2000:]
+  assert out.stdout.count('ok') == 2
