@@ -87,9 +87,21 @@ def cpu_reference_run(steps, warmup, sample_batch):
   import torch
   from oracle import imm_oracle as O
   cores = os.cpu_count() or 1
-  torch.set_num_threads(cores)
   st = O.init_state(O.State(n_maps=N_MAPS, image_size=IMAGE_SIZE), seed=0)
   inp = O.synthetic_inputs(sample_batch, IMAGE_SIZE, seed=0)
+  # "all the host threads it can use": oneDNN/OpenMP scale badly past a few dozen threads at this problem size,
+  # so time one step per candidate thread count and keep the fastest (reported as `cores`)
+  best, best_t = cores, None
+  for n in sorted({min(cores, c) for c in (8, 16, 32, 64, cores)}):
+    torch.set_num_threads(n)
+    O.train_step(st, inp)
+    t0 = time.time()
+    O.train_step(st, inp)
+    dt = time.time() - t0
+    if best_t is None or dt < best_t:
+      best, best_t = n, dt
+  cores = best
+  torch.set_num_threads(cores)
   for _ in range(warmup):
     O.train_step(st, inp)
   t0 = time.time()
