@@ -227,6 +227,360 @@ __global__ void split_planes_kernel(const float* __restrict__ v, float* hi, floa
     store_split(hi, lo, (size_t)i, __ldg(v + i));
 }
 
+
+// =====================================================================================================
+// float4-vectorised variants (C % 4 == 0, 16-byte aligned rows): one thread = 4 consecutive channels.
+// =====================================================================================================
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void store_split4(float* hi_p, float* lo_p, size_t i, float4 v) {
+  if (lo_p) {
+    float4 h, l;
+    split_tf32(v.x, h.x, l.x);
+    split_tf32(v.y, h.y, l.y);
+    split_tf32(v.z, h.z, l.z);
+    split_tf32(v.w, h.w, l.w);
+    st4(hi_p + i, h);
+    st4(lo_p + i, l);
+  } else {
+    st4(hi_p + i, v);
+  }
+}
+__device__ __forceinline__ float4 load_split4(const float* hi_p, const float* lo_p, size_t i) {
+  float4 v = ld4(hi_p + i);
+  if (lo_p) {
+    float4 l = ld4(lo_p + i);
+    v.x += l.x; v.y += l.y; v.z += l.z; v.w += l.w;
+  }
+  return v;
+}
+
+constexpr int kVRedPix = 512;       // pixels per block
+
+// per-channel reduction of NV quantities; f(p, c4, out[NV]) yields float4 per quantity for pixel p, channels c4*4..+3
+template <int NV, class F>
+__device__ __forceinline__ void channel_reduce4(int64_t npix, int C, double* out, int out_stride, F f) {
+  const int q = C >> 2;                       // channel quads
+  const int rows = blockDim.x / q;            // pixel rows handled concurrently by the block
+  const int cq = threadIdx.x % q, pr = threadIdx.x / q;
+  double acc[NV][4];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0;
+  int64_t p0 = (int64_t)blockIdx.x * kVRedPix;
+  int64_t p1 = p0 + kVRedPix;
+  if (p1 > npix) p1 = npix;
+  if (pr < rows) {
+    // 4 pixels in flight per thread (memory-level parallelism), fp32 partial over the 4, double across iterations
+    int64_t p = p0 + pr;
+    for (; p + 3 * (int64_t)rows < p1; p += 4 * (int64_t)rows) {
+      float4 v0[NV], v1[NV], v2[NV], v3[NV];
+      f(p, cq, v0);
+      f(p + rows, cq, v1);
+      f(p + 2 * (int64_t)rows, cq, v2);
+      f(p + 3 * (int64_t)rows, cq, v3);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        acc[i][0] += (double)((v0[i].x + v1[i].x) + (v2[i].x + v3[i].x));
+        acc[i][1] += (double)((v0[i].y + v1[i].y) + (v2[i].y + v3[i].y));
+        acc[i][2] += (double)((v0[i].z + v1[i].z) + (v2[i].z + v3[i].z));
+        acc[i][3] += (double)((v0[i].w + v1[i].w) + (v2[i].w + v3[i].w));
+      }
+    }
+    for (; p < p1; p += rows) {
+      float4 v[NV];
+      f(p, cq, v);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        acc[i][0] += (double)v[i].x; acc[i][1] += (double)v[i].y;
+        acc[i][2] += (double)v[i].z; acc[i][3] += (double)v[i].w;
+      }
+    }
+  }
+  extern __shared__ double vsm[];             // [NV*4][blockDim.x]
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) vsm[(i * 4 + j) * blockDim.x + threadIdx.x] = acc[i][j];
+  __syncthreads();
+  if (pr == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double sacc = 0.0;
+        for (int r = 0; r < rows; ++r) sacc += vsm[(i * 4 + j) * blockDim.x + r * q + cq];
+        atomicAdd(out + (size_t)i * out_stride + cq * 4 + j, sacc);
+      }
+  }
+}
+
+__global__ void bn_stats4_kernel(const float* __restrict__ y, int64_t npix, int C, int ycs, double* sums) {
+  channel_reduce4<2>(npix, C, sums, C, [&](int64_t p, int c4, float4* v) {
+    float4 t = ld4(y + p * ycs + c4 * 4);
+    v[0] = t;
+    v[1] = make_float4(t.x * t.x, t.y * t.y, t.z * t.z, t.w * t.w);
+  });
+}
+
+__device__ __forceinline__ float4 bn_act4(float4 y, float4 sc, float4 sh, int relu) {
+  return make_float4(bn_act(y.x, sc.x, sh.x, relu), bn_act(y.y, sc.y, sh.y, relu), bn_act(y.z, sc.z, sh.z, relu),
+                     bn_act(y.w, sc.w, sh.w, relu));
+}
+
+__global__ void bn_apply4_kernel(const float* __restrict__ y, int64_t npix, int C, int ycs,
+                                 const float* __restrict__ scale, const float* __restrict__ shift, int relu,
+                                 float* out_hi, float* out_lo, int ocs) {
+  const int q = C >> 2;
+  int64_t total = npix * q;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = i / q;
+    int c = (int)(i - p * q) * 4;
+    float4 v = bn_act4(ld4(y + p * ycs + c), ld4(scale + c), ld4(shift + c), relu);
+    store_split4(out_hi, out_lo, (size_t)(p * ocs + c), v);
+  }
+}
+
+__global__ void bn_apply_up2x4_kernel(const float* __restrict__ y, int N, int H, int W, int C, int ycs,
+                                      const float* __restrict__ scale, const float* __restrict__ shift,
+                                      int relu, float* out_hi, float* out_lo, int ocs) {
+  const int Ho = 2 * H, Wo = 2 * W, q = C >> 2;
+  int64_t total = (int64_t)N * Ho * Wo * q;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % q) * 4;
+    int64_t p = i / q;
+    int wo = (int)(p % Wo);
+    int64_t t = p / Wo;
+    int ho = (int)(t % Ho);
+    int n = (int)(t / Ho);
+    int h0 = ho >> 1, w0 = wo >> 1;
+    int h1 = min(h0 + 1, H - 1), w1 = min(w0 + 1, W - 1);
+    float fh = (ho & 1) ? 0.5f : 0.f, fw = (wo & 1) ? 0.5f : 0.f;
+    float4 sc = ld4(scale + c), sh = ld4(shift + c);
+    const float* base = y + (int64_t)n * H * W * ycs + c;
+    float4 a00 = bn_act4(ld4(base + ((int64_t)h0 * W + w0) * ycs), sc, sh, relu);
+    float4 a01 = bn_act4(ld4(base + ((int64_t)h0 * W + w1) * ycs), sc, sh, relu);
+    float4 a10 = bn_act4(ld4(base + ((int64_t)h1 * W + w0) * ycs), sc, sh, relu);
+    float4 a11 = bn_act4(ld4(base + ((int64_t)h1 * W + w1) * ycs), sc, sh, relu);
+    float4 v;
+#define IMMB_LERP(f)                                          \
+    {                                                         \
+      float top = a00.f + (a01.f - a00.f) * fw;               \
+      float bot = a10.f + (a11.f - a10.f) * fw;               \
+      v.f = top + (bot - top) * fh;                           \
+    }
+    IMMB_LERP(x) IMMB_LERP(y) IMMB_LERP(z) IMMB_LERP(w)
+#undef IMMB_LERP
+    store_split4(out_hi, out_lo, (size_t)(p * ocs + c), v);
+  }
+}
+
+__global__ void upsample2x_bwd4_kernel(const float* __restrict__ gup, int N, int H, int W, int C, int gcs,
+                                       float* g) {
+  const int Ho = 2 * H, Wo = 2 * W, q = C >> 2;
+  int64_t total = (int64_t)N * H * W * q;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % q) * 4;
+    int64_t p = i / q;
+    int w = (int)(p % W);
+    int64_t t = p / W;
+    int h = (int)(t % H);
+    int n = (int)(t / H);
+    const float* base = gup + (int64_t)n * Ho * Wo * gcs + c;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int dh = -1; dh <= 1; ++dh) {
+      int hh = 2 * h + dh;
+      if (hh < 0) continue;
+      float wh = dh == 0 ? 1.f : (dh < 0 ? 0.5f : (h == H - 1 ? 1.f : 0.5f));
+#pragma unroll
+      for (int dw = -1; dw <= 1; ++dw) {
+        int ww = 2 * w + dw;
+        if (ww < 0) continue;
+        float wt = wh * (dw == 0 ? 1.f : (dw < 0 ? 0.5f : (w == W - 1 ? 1.f : 0.5f)));
+        float4 gv = ld4(base + ((int64_t)hh * Wo + ww) * gcs);
+        acc.x += wt * gv.x; acc.y += wt * gv.y; acc.z += wt * gv.z; acc.w += wt * gv.w;
+      }
+    }
+    st4(g + p * C + c, acc);
+  }
+}
+
+struct BnBwdArgs {
+  const float *g, *y, *scale, *shift, *mean, *invstd;
+  int gcs, ycs, relu;
+};
+
+__device__ __forceinline__ void bn_bwd_elem4(const BnBwdArgs& a, int64_t p, int c, float4& dz, float4& xh) {
+  float4 yy = ld4(a.y + p * a.ycs + c), gg = ld4(a.g + p * a.gcs + c);
+  float4 sc = ld4(a.scale + c), sh = ld4(a.shift + c), mu = ld4(a.mean + c), is = ld4(a.invstd + c);
+#define IMMB_E(f)                                                        \
+  {                                                                      \
+    float z = fmaf(yy.f, sc.f, sh.f);                                    \
+    dz.f = (a.relu && !(z > 0.f)) ? 0.f : gg.f;                          \
+    xh.f = (yy.f - mu.f) * is.f;                                         \
+  }
+  IMMB_E(x) IMMB_E(y) IMMB_E(z) IMMB_E(w)
+#undef IMMB_E
+}
+
+__global__ void bn_bwd_reduce4_kernel(BnBwdArgs a, int64_t npix, int C, double* sums) {
+  channel_reduce4<2>(npix, C, sums, C, [&](int64_t p, int c4, float4* v) {
+    float4 dz, xh;
+    bn_bwd_elem4(a, p, c4 * 4, dz, xh);
+    v[0] = dz;
+    v[1] = make_float4(dz.x * xh.x, dz.y * xh.y, dz.z * xh.z, dz.w * xh.w);
+  });
+}
+
+__global__ void bn_bwd_apply4_kernel(BnBwdArgs a, int64_t npix, int C, const double* __restrict__ sums,
+                                     float* dy_hi, float* dy_lo, float* dgamma, float* dbeta, double* dbias_acc) {
+  const double inv_n = 1.0 / (double)npix;
+  if (blockIdx.x == 0 && threadIdx.x < C) {
+    dbeta[threadIdx.x] = (float)sums[threadIdx.x];
+    dgamma[threadIdx.x] = (float)sums[C + threadIdx.x];
+  }
+  channel_reduce4<1>(npix, C, dbias_acc, C, [&](int64_t p, int c4, float4* v) {
+    const int c = c4 * 4;
+    float4 dz, xh;
+    bn_bwd_elem4(a, p, c, dz, xh);
+    float4 sc = ld4(a.scale + c);
+    float4 dy;
+#define IMMB_E(f, j)                                                                 \
+    {                                                                                \
+      float mdz = (float)(sums[c + j] * inv_n), mdzx = (float)(sums[C + c + j] * inv_n); \
+      dy.f = sc.f * (dz.f - mdz - xh.f * mdzx);                                      \
+    }
+    IMMB_E(x, 0) IMMB_E(y, 1) IMMB_E(z, 2) IMMB_E(w, 3)
+#undef IMMB_E
+    store_split4(dy_hi, dy_lo, (size_t)(p * C + c), dy);
+    v[0] = dy;
+  });
+}
+
+__global__ void split_planes4_kernel(const float* __restrict__ v, float* hi, float* lo, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
+    store_split4(hi, lo, (size_t)i * 4, ld4(v + i * 4));
+}
+
+__global__ void maxpool2x2_fwd4_kernel(const float* __restrict__ x_hi, const float* __restrict__ x_lo, int N,
+                                       int H, int W, int C, float* o_hi, float* o_lo) {
+  int Ho = H / 2, Wo = W / 2, q = C >> 2;
+  int64_t total = (int64_t)N * Ho * Wo * q;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % q) * 4;
+    int64_t p = i / q;
+    int wo = (int)(p % Wo);
+    int64_t t = p / Wo;
+    int ho = (int)(t % Ho);
+    int n = (int)(t / Ho);
+    size_t base = (((size_t)n * H + 2 * ho) * W + 2 * wo) * C + c;
+    float4 a = load_split4(x_hi, x_lo, base), b = load_split4(x_hi, x_lo, base + C);
+    float4 d = load_split4(x_hi, x_lo, base + (size_t)W * C), e = load_split4(x_hi, x_lo, base + (size_t)W * C + C);
+    float4 v = make_float4(fmaxf(fmaxf(a.x, b.x), fmaxf(d.x, e.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(d.y, e.y)),
+                           fmaxf(fmaxf(a.z, b.z), fmaxf(d.z, e.z)), fmaxf(fmaxf(a.w, b.w), fmaxf(d.w, e.w)));
+    store_split4(o_hi, o_lo, (size_t)(p * C + c), v);
+  }
+}
+
+__global__ void maxpool2x2_bwd4_kernel(const float* __restrict__ g_out, const float* __restrict__ x_hi,
+                                       const float* __restrict__ x_lo, int N, int H, int W, int C, float* g_in) {
+  int Ho = H / 2, Wo = W / 2, q = C >> 2;
+  int64_t total = (int64_t)N * Ho * Wo * q;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % q) * 4;
+    int64_t p = i / q;
+    int wo = (int)(p % Wo);
+    int64_t t = p / Wo;
+    int ho = (int)(t % Ho);
+    int n = (int)(t / Ho);
+    size_t base = (((size_t)n * H + 2 * ho) * W + 2 * wo) * C + c;
+    size_t idx[4] = {base, base + C, base + (size_t)W * C, base + (size_t)W * C + C};
+    float4 xv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xv[k] = load_split4(x_hi, x_lo, idx[k]);
+    float4 gg = ld4(g_out + p * C + c);
+    float4 o[4];
+#define IMMB_E(f)                                                  \
+    {                                                              \
+      int best = 0;                                                \
+      float bv = xv[0].f;                                          \
+      _Pragma("unroll") for (int k = 1; k < 4; ++k) if (xv[k].f > bv) { bv = xv[k].f; best = k; } \
+      _Pragma("unroll") for (int k = 0; k < 4; ++k) o[k].f = (k == best) ? gg.f : 0.f;            \
+    }
+    IMMB_E(x) IMMB_E(y) IMMB_E(z) IMMB_E(w)
+#undef IMMB_E
+#pragma unroll
+    for (int k = 0; k < 4; ++k) st4(g_in + idx[k], o[k]);
+  }
+}
+
+__device__ __forceinline__ float mask_at(const float* __restrict__ mask, int64_t p, int h, int w, int R) {
+  if (!mask) return 1.f;
+  int s = R / h;
+  int ww = (int)(p % w);
+  int64_t t = p / w;
+  int hh = (int)(t % h);
+  int64_t b = t / h;
+  return __ldg(mask + (b * R + (int64_t)hh * s) * R + (int64_t)ww * s);
+}
+
+__global__ void perceptual_level_sum4_kernel(const float* __restrict__ fg_hi, const float* __restrict__ fg_lo,
+                                             int gcs, const float* __restrict__ fp_hi,
+                                             const float* __restrict__ fp_lo, int pcs, int B, int h, int w, int C,
+                                             const float* __restrict__ mask, int R, double* acc) {
+  const int q = C >> 2;
+  int64_t total = (int64_t)B * h * w * q;
+  double local = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % q) * 4;
+    int64_t p = i / q;
+    float4 a = load_split4(fg_hi, fg_lo, (size_t)(p * gcs + c)), b = load_split4(fp_hi, fp_lo, (size_t)(p * pcs + c));
+    float m = mask_at(mask, p, h, w, R);
+    float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z, dw = a.w - b.w;
+    local += (double)(m * (dx * dx)) + (double)(m * (dy * dy)) + (double)(m * (dz * dz)) + (double)(m * (dw * dw));
+  }
+  local = warp_sum(local);
+  __shared__ double sm[32];
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) sm[wid] = local;
+  __syncthreads();
+  if (wid == 0) {
+    double v = lane < (blockDim.x >> 5) ? sm[lane] : 0.0;
+    v = warp_sum(v);
+    if (lane == 0) atomicAdd(acc, v);
+  }
+}
+
+__global__ void vgg_bwd_combine4_kernel(const float* __restrict__ g_next, const float* __restrict__ fg_hi,
+                                        const float* __restrict__ fg_lo, const float* __restrict__ fp_hi,
+                                        const float* __restrict__ fp_lo, int B, int h, int w, int C,
+                                        const float* __restrict__ mask, int R, const float* __restrict__ coef,
+                                        float* dy_hi, float* dy_lo) {
+  const int q = C >> 2;
+  int64_t total = (int64_t)B * h * w * q;
+  float cf = coef ? __ldg(coef) : 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = i / q;
+    size_t e = (size_t)i * 4;
+    float4 fp = load_split4(fp_hi, fp_lo, e);
+    float4 g = g_next ? ld4(g_next + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (coef) {
+      float4 fg = load_split4(fg_hi, fg_lo, e);
+      float m = cf * mask_at(mask, p, h, w, R);
+      g.x += m * (fg.x - fp.x); g.y += m * (fg.y - fp.y); g.z += m * (fg.z - fp.z); g.w += m * (fg.w - fp.w);
+    }
+    g.x = fp.x > 0.f ? g.x : 0.f; g.y = fp.y > 0.f ? g.y : 0.f; g.z = fp.z > 0.f ? g.z : 0.f; g.w = fp.w > 0.f ? g.w : 0.f;
+    store_split4(dy_hi, dy_lo, e, g);
+  }
+}
+
 // =====================================================================================================
 // landmark bottleneck: one warp per (b, k)
 // =====================================================================================================
@@ -748,6 +1102,11 @@ static inline int ew_grid(int64_t total, int block = 256) {
   if (g < 1) g = 1;
   return (int)g;
 }
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+// vectorised per-channel kernels: C a multiple of 4 that divides 256*4 so that a 256-thread block covers whole rows
+static inline bool vec_ok(int C, int cs) { return C % 4 == 0 && cs % 4 == 0 && C <= 1024 && (1024 % C) == 0; }
+static inline int vred_grid(int64_t npix) { return (int)((npix + kVRedPix - 1) / kVRedPix); }
+static inline size_t vred_smem(int nv) { return sizeof(double) * nv * 4 * 256; }
 static inline dim3 red_grid(int64_t npix, int C) {
   return dim3((unsigned)((npix + kRedPixPerBlock - 1) / kRedPixPerBlock), (unsigned)((C + 31) / 32));
 }
@@ -760,13 +1119,19 @@ using namespace immb;
 extern "C" int immb_split_planes(const float* v, float* hi, float* lo, int64_t n, void* stream) {
   IMMB_REQUIRE(v && hi && n >= 0, "split_planes: bad args");
   if (n == 0) return IMMB_OK;
-  split_planes_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(v, hi, lo, n);
+  if ((n & 3) == 0 && aligned16(v) && aligned16(hi) && aligned16(lo))
+    split_planes4_kernel<<<ew_grid(n / 4), 256, 0, ST(stream)>>>(v, hi, lo, n / 4);
+  else
+    split_planes_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(v, hi, lo, n);
   return check_launch("split_planes");
 }
 
 extern "C" int immb_bn_stats(const float* y, int64_t npix, int C, int ycs, double* sums, void* stream) {
   IMMB_REQUIRE(y && sums && npix > 0 && C > 0 && ycs >= C, "bn_stats: bad args");
-  bn_stats_kernel<<<red_grid(npix, C), dim3(32, kRedRows), 0, ST(stream)>>>(y, npix, C, ycs, sums);
+  if (vec_ok(C, ycs) && aligned16(y))
+    bn_stats4_kernel<<<vred_grid(npix), 256, vred_smem(2), ST(stream)>>>(y, npix, C, ycs, sums);
+  else
+    bn_stats_kernel<<<red_grid(npix, C), dim3(32, kRedRows), 0, ST(stream)>>>(y, npix, C, ycs, sums);
   return check_launch("bn_stats");
 }
 
@@ -785,12 +1150,21 @@ extern "C" int immb_bn_apply(const float* y, int N, int H, int W, int C, int ycs
                              void* stream) {
   IMMB_REQUIRE(y && scale && shift && out_hi && ycs >= C && ocs >= C, "bn_apply: bad args");
   int64_t npix = (int64_t)N * H * W;
+  const bool v4 = vec_ok(C, ycs) && (ocs % 4 == 0) && aligned16(y) && aligned16(out_hi) && aligned16(out_lo);
   if (up2x) {
-    bn_apply_up2x_kernel<<<ew_grid(npix * 4 * C), 256, 0, ST(stream)>>>(y, N, H, W, C, ycs, scale, shift,
-                                                                         relu, out_hi, out_lo, ocs);
+    if (v4)
+      bn_apply_up2x4_kernel<<<ew_grid(npix * C), 256, 0, ST(stream)>>>(y, N, H, W, C, ycs, scale, shift, relu,
+                                                                       out_hi, out_lo, ocs);
+    else
+      bn_apply_up2x_kernel<<<ew_grid(npix * 4 * C), 256, 0, ST(stream)>>>(y, N, H, W, C, ycs, scale, shift,
+                                                                           relu, out_hi, out_lo, ocs);
   } else {
-    bn_apply_kernel<<<ew_grid(npix * C), 256, 0, ST(stream)>>>(y, npix, C, ycs, scale, shift, relu, out_hi,
-                                                                out_lo, ocs);
+    if (v4)
+      bn_apply4_kernel<<<ew_grid(npix * C / 4), 256, 0, ST(stream)>>>(y, npix, C, ycs, scale, shift, relu, out_hi,
+                                                                      out_lo, ocs);
+    else
+      bn_apply_kernel<<<ew_grid(npix * C), 256, 0, ST(stream)>>>(y, npix, C, ycs, scale, shift, relu, out_hi,
+                                                                  out_lo, ocs);
   }
   return check_launch("bn_apply");
 }
@@ -798,7 +1172,10 @@ extern "C" int immb_bn_apply(const float* y, int N, int H, int W, int C, int ycs
 extern "C" int immb_upsample2x_bwd(const float* g_up, int N, int H, int W, int C, int gcs, float* g,
                                    void* stream) {
   IMMB_REQUIRE(g_up && g && gcs >= C, "upsample2x_bwd: bad args");
-  upsample2x_bwd_kernel<<<ew_grid((int64_t)N * H * W * C), 256, 0, ST(stream)>>>(g_up, N, H, W, C, gcs, g);
+  if (vec_ok(C, gcs) && aligned16(g_up) && aligned16(g))
+    upsample2x_bwd4_kernel<<<ew_grid((int64_t)N * H * W * C / 4), 256, 0, ST(stream)>>>(g_up, N, H, W, C, gcs, g);
+  else
+    upsample2x_bwd_kernel<<<ew_grid((int64_t)N * H * W * C), 256, 0, ST(stream)>>>(g_up, N, H, W, C, gcs, g);
   return check_launch("upsample2x_bwd");
 }
 
@@ -806,8 +1183,13 @@ extern "C" int immb_bn_bwd_reduce(const float* g, int gcs, const float* y, int y
                                   const float* scale, const float* shift, const float* mean,
                                   const float* invstd, int relu, double* sums, void* stream) {
   IMMB_REQUIRE(g && y && sums && gcs >= C && ycs >= C, "bn_bwd_reduce: bad args");
-  bn_bwd_reduce_kernel<<<red_grid(npix, C), dim3(32, kRedRows), 0, ST(stream)>>>(
-      g, gcs, y, ycs, npix, C, scale, shift, mean, invstd, relu, sums);
+  if (vec_ok(C, gcs) && ycs % 4 == 0 && aligned16(g) && aligned16(y)) {
+    BnBwdArgs a{g, y, scale, shift, mean, invstd, gcs, ycs, relu};
+    bn_bwd_reduce4_kernel<<<vred_grid(npix), 256, vred_smem(2), ST(stream)>>>(a, npix, C, sums);
+  } else {
+    bn_bwd_reduce_kernel<<<red_grid(npix, C), dim3(32, kRedRows), 0, ST(stream)>>>(
+        g, gcs, y, ycs, npix, C, scale, shift, mean, invstd, relu, sums);
+  }
   return check_launch("bn_bwd_reduce");
 }
 
@@ -816,8 +1198,15 @@ extern "C" int immb_bn_bwd_apply(const float* g, int gcs, const float* y, int yc
                                  const float* invstd, int relu, const double* sums, float* dy_hi,
                                  float* dy_lo, float* dgamma, float* dbeta, double* dbias_acc, void* stream) {
   IMMB_REQUIRE(g && y && sums && dy_hi && dgamma && dbeta && dbias_acc, "bn_bwd_apply: bad args");
-  bn_bwd_apply_kernel<<<red_grid(npix, C), dim3(32, kRedRows), 0, ST(stream)>>>(
-      g, gcs, y, ycs, npix, C, scale, shift, mean, invstd, relu, sums, dy_hi, dy_lo, dgamma, dbeta, dbias_acc);
+  if (vec_ok(C, gcs) && ycs % 4 == 0 && C <= 256 && aligned16(g) && aligned16(y) && aligned16(dy_hi) &&
+      aligned16(dy_lo)) {
+    BnBwdArgs a{g, y, scale, shift, mean, invstd, gcs, ycs, relu};
+    bn_bwd_apply4_kernel<<<vred_grid(npix), 256, vred_smem(1), ST(stream)>>>(a, npix, C, sums, dy_hi, dy_lo, dgamma,
+                                                                            dbeta, dbias_acc);
+  } else {
+    bn_bwd_apply_kernel<<<red_grid(npix, C), dim3(32, kRedRows), 0, ST(stream)>>>(
+        g, gcs, y, ycs, npix, C, scale, shift, mean, invstd, relu, sums, dy_hi, dy_lo, dgamma, dbeta, dbias_acc);
+  }
   return check_launch("bn_bwd_apply");
 }
 
@@ -891,16 +1280,24 @@ extern "C" int immb_pack_weights_rowwin(const float* w, int Cout, float* wp_hi, 
 extern "C" int immb_maxpool2x2_fwd(const float* x_hi, const float* x_lo, int N, int H, int W, int C,
                                    float* o_hi, float* o_lo, void* stream) {
   IMMB_REQUIRE(x_hi && o_hi && (H % 2 == 0) && (W % 2 == 0), "maxpool_fwd: bad args (even sizes only)");
-  maxpool2x2_fwd_kernel<<<ew_grid((int64_t)N * (H / 2) * (W / 2) * C), 256, 0, ST(stream)>>>(x_hi, x_lo, N, H,
-                                                                                            W, C, o_hi, o_lo);
+  if (C % 4 == 0 && aligned16(x_hi) && aligned16(x_lo) && aligned16(o_hi) && aligned16(o_lo))
+    maxpool2x2_fwd4_kernel<<<ew_grid((int64_t)N * (H / 2) * (W / 2) * C / 4), 256, 0, ST(stream)>>>(x_hi, x_lo, N, H,
+                                                                                                  W, C, o_hi, o_lo);
+  else
+    maxpool2x2_fwd_kernel<<<ew_grid((int64_t)N * (H / 2) * (W / 2) * C), 256, 0, ST(stream)>>>(x_hi, x_lo, N, H,
+                                                                                              W, C, o_hi, o_lo);
   return check_launch("maxpool2x2_fwd");
 }
 
 extern "C" int immb_maxpool2x2_bwd(const float* g_out, const float* x_hi, const float* x_lo, int N, int H,
                                    int W, int C, float* g_in, void* stream) {
   IMMB_REQUIRE(g_out && x_hi && g_in && (H % 2 == 0) && (W % 2 == 0), "maxpool_bwd: bad args");
-  maxpool2x2_bwd_kernel<<<ew_grid((int64_t)N * (H / 2) * (W / 2) * C), 256, 0, ST(stream)>>>(g_out, x_hi, x_lo,
-                                                                                            N, H, W, C, g_in);
+  if (C % 4 == 0 && aligned16(g_out) && aligned16(x_hi) && aligned16(x_lo) && aligned16(g_in))
+    maxpool2x2_bwd4_kernel<<<ew_grid((int64_t)N * (H / 2) * (W / 2) * C / 4), 256, 0, ST(stream)>>>(g_out, x_hi, x_lo,
+                                                                                                  N, H, W, C, g_in);
+  else
+    maxpool2x2_bwd_kernel<<<ew_grid((int64_t)N * (H / 2) * (W / 2) * C), 256, 0, ST(stream)>>>(g_out, x_hi, x_lo,
+                                                                                              N, H, W, C, g_in);
   return check_launch("maxpool2x2_bwd");
 }
 
@@ -909,8 +1306,13 @@ extern "C" int immb_perceptual_level_sum(const float* fg_hi, const float* fg_lo,
                                          const float* mask, int R, double* acc, void* stream) {
   IMMB_REQUIRE(fg_hi && fp_hi && acc && gcs >= C && pcs >= C && h > 0 && (!mask || R % h == 0),
                "perceptual_level_sum: bad args");
-  perceptual_level_sum_kernel<<<ew_grid((int64_t)B * h * w * C), 256, 0, ST(stream)>>>(
-      fg_hi, fg_lo, gcs, fp_hi, fp_lo, pcs, B, h, w, C, mask, R, acc);
+  if (C % 4 == 0 && gcs % 4 == 0 && pcs % 4 == 0 && aligned16(fg_hi) && aligned16(fg_lo) && aligned16(fp_hi) &&
+      aligned16(fp_lo))
+    perceptual_level_sum4_kernel<<<ew_grid((int64_t)B * h * w * C / 4), 256, 0, ST(stream)>>>(
+        fg_hi, fg_lo, gcs, fp_hi, fp_lo, pcs, B, h, w, C, mask, R, acc);
+  else
+    perceptual_level_sum_kernel<<<ew_grid((int64_t)B * h * w * C), 256, 0, ST(stream)>>>(
+        fg_hi, fg_lo, gcs, fp_hi, fp_lo, pcs, B, h, w, C, mask, R, acc);
   return check_launch("perceptual_level_sum");
 }
 
@@ -928,8 +1330,13 @@ extern "C" int immb_vgg_bwd_combine(const float* g_next, const float* fg_hi, con
                                     const float* mask, int R, const float* coef, float* dy_hi, float* dy_lo,
                                     void* stream) {
   IMMB_REQUIRE(fp_hi && dy_hi && (g_next || coef) && (!coef || fg_hi), "vgg_bwd_combine: bad args");
-  vgg_bwd_combine_kernel<<<ew_grid((int64_t)B * h * w * C), 256, 0, ST(stream)>>>(
-      g_next, fg_hi, fg_lo, fp_hi, fp_lo, B, h, w, C, mask, R, coef, dy_hi, dy_lo);
+  if (C % 4 == 0 && aligned16(g_next) && aligned16(fg_hi) && aligned16(fg_lo) && aligned16(fp_hi) &&
+      aligned16(fp_lo) && aligned16(dy_hi) && aligned16(dy_lo))
+    vgg_bwd_combine4_kernel<<<ew_grid((int64_t)B * h * w * C / 4), 256, 0, ST(stream)>>>(
+        g_next, fg_hi, fg_lo, fp_hi, fp_lo, B, h, w, C, mask, R, coef, dy_hi, dy_lo);
+  else
+    vgg_bwd_combine_kernel<<<ew_grid((int64_t)B * h * w * C), 256, 0, ST(stream)>>>(
+        g_next, fg_hi, fg_lo, fp_hi, fp_lo, B, h, w, C, mask, R, coef, dy_hi, dy_lo);
   return check_launch("vgg_bwd_combine");
 }
 
