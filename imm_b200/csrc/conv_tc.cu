@@ -451,6 +451,20 @@ static int make_w_map(CUtensorMap* m, const float* base, int taps, int Nn, int K
   return make_map(m, base, 3, dims, str, box);
 }
 
+// exported to conv_tc2.cu
+int tc_make_act_map(CUtensorMap* m, const float* base, int N, int H, int W, int C, int cs, bool parity_split,
+                    int box_w, int box_h, int box_n, int swizzle_mn) {
+  return make_act_map(m, base, N, H, W, C, cs, parity_split, box_w, box_h, box_n,
+                      swizzle_mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
+}
+int tc_make_w_map(CUtensorMap* m, const float* base, int taps, int Nn, int Kd, int bn) {
+  return make_w_map(m, base, taps, Nn, Kd, bn);
+}
+bool conv_tc2_eligible(const immb_conv_desc* d, int op);
+int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const float* act_lo, int act_c, int act_cs,
+                 const float* w_hi, const float* w_lo, int w_rows, int kd, const float* bias, int relu,
+                 float* out_hi, float* out_lo, int ocs, int ncols, int n_store, cudaStream_t st);
+
 static bool pick_tile(int PH, int PW, int N, int* TW, int* TH, int* TN) {
   if (PW % 16 == 0 && PH % 8 == 0) { *TW = 16; *TH = 8; *TN = 1; return true; }
   if (PW == 8 && PH == 8) { *TW = 8; *TH = 8; *TN = 2; return true; }
@@ -521,6 +535,8 @@ static int dispatch_fwd(int bn, int passes, const CUtensorMap& a_hi, const CUten
   return set_error(IMMB_ERR_INVALID, "conv_tc: unsupported BN %d", bn);
 }
 
+static int pick_bn(int ncols);
+int tc_pick_bn(int ncols) { return pick_bn(ncols); }
 static int pick_bn(int ncols) {
   if (ncols % 128 == 0) return 128;
   if (ncols % 96 == 0) return 96;
@@ -535,6 +551,9 @@ static int pick_bn(int ncols) {
 
 int conv_tc_fwd(const immb_conv_desc* d, const float* x_hi, const float* x_lo, const float* wp_hi,
                 const float* wp_lo, const float* bias, float* y_hi, float* y_lo, cudaStream_t st) {
+  if (conv_tc2_eligible(d, 0))
+    return conv_tc2_run(d, 0, x_hi, x_lo, d->Cin, d->x_cstride, wp_hi, wp_lo, d->Cout, d->cin_pad, bias,
+                        d->epilogue == IMMB_EPI_BIAS_RELU, y_hi, y_lo, d->y_cstride, d->Cout, (d->Cout + 3) / 4 * 4, st);
   const int passes = d->precision == IMMB_PREC_TF32 ? 1 : 3;
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -583,6 +602,9 @@ int conv_tc_dgrad(const immb_conv_desc* d, const float* dy_hi, const float* dy_l
                   const float* wh_lo, float* dx, cudaStream_t st) {
   const int passes = d->precision == IMMB_PREC_TF32 ? 1 : 3;
   const int ncols = d->cin_pad < d->x_cstride ? d->cin_pad : d->x_cstride;   // channels of dx that get written
+  if (conv_tc2_eligible(d, 1))
+    return conv_tc2_run(d, 1, dy_hi, dy_lo, d->Cout, d->y_cstride, wh_hi, wh_lo, d->cin_pad, d->y_cstride, nullptr, 0,
+                        dx, nullptr, d->x_cstride, ncols, ncols, st);
   const int bn = pick_bn(ncols);
   const int classes = d->stride == 1 ? 1 : 4;
   for (int cls = 0; cls < classes; ++cls) {

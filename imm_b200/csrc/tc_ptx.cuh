@@ -22,6 +22,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -121,9 +124,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 // (+ k advance); lbo / sbo in bytes.
 // layout_type: 2 = SWIZZLE_128B (16-byte atoms; K-major operands), 1 = SWIZZLE_128B_BASE32B (32-byte atoms; the only
 // layout the hardware accepts for MN-major tf32 operands; pairs with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
+// base_offset: (start address >> 7) & 7 when the start is not aligned to the 1024-byte swizzle pattern.
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                                    uint32_t layout_type = 2) {
+                                                    uint32_t layout_type = 2, uint32_t base_offset = 0) {
   uint64_t d = 0;
+  d |= (uint64_t)(base_offset & 7u) << 49;               // matrix base offset [49,52)
   d |= (uint64_t)((addr & 0x3FFFFu) >> 4);               // start_address   [0,14)
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;     // leading_byte_offset [16,30)
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;     // stride_byte_offset  [32,46)
