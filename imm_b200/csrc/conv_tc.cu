@@ -461,6 +461,9 @@ int tc_make_w_map(CUtensorMap* m, const float* base, int taps, int Nn, int Kd, i
   return make_w_map(m, base, taps, Nn, Kd, bn);
 }
 bool conv_tc2_eligible(const immb_conv_desc* d, int op);
+bool conv_tc2_wgrad_eligible(const immb_conv_desc* d);
+int conv_tc2_wgrad_run(const immb_conv_desc* d, const float* x_hi, const float* x_lo, const float* dy_hi,
+                       const float* dy_lo, float* dw, cudaStream_t st);
 int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const float* act_lo, int act_c, int act_cs,
                  const float* w_hi, const float* w_lo, int w_rows, int kd, const float* bias, int relu,
                  float* out_hi, float* out_lo, int ocs, int ncols, int n_store, cudaStream_t st);
@@ -666,6 +669,7 @@ static int launch_wg(const CUtensorMap& x_hi, const CUtensorMap& x_lo, const CUt
 
 int conv_tc_wgrad(const immb_conv_desc* d, const float* x_hi, const float* x_lo, const float* dy_hi,
                   const float* dy_lo, float* dw, void*, size_t, cudaStream_t st) {
+  if (conv_tc2_wgrad_eligible(d)) return conv_tc2_wgrad_run(d, x_hi, x_lo, dy_hi, dy_lo, dw, st);
   const int passes = d->precision == IMMB_PREC_TF32 ? 1 : 3;
   WgParams p;
   memset(&p, 0, sizeof(p));

@@ -325,4 +325,214 @@ int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const flo
   return set_error(IMMB_ERR_INVALID, "conv_tc2: unsupported BN %d", bn);
 }
 
+
+// =============================================================================================================
+// Halo-reuse wgrad for the stride-1 3x3 layers.
+//   dW[r][s][ci][co] = sum_pixels X[h+r-1, w+s-1][ci] * dY[h, w][co]
+// One CTA owns a 32-input-channel chunk x BN output channels x a range of pixel tiles (split-K).  Per stage it
+// fetches ONE (4+2) x 16-pixel halo box of X (12 KB / plane) and the matching 4 x 8-pixel dY boxes, and issues, for
+// each filter row r and each image row of the tile, ONE MMA with M = 128 = 4 column taps (s = 0..3, the 4th is
+// ignored) x 32 channels: the four "MN groups" of the MN-major A descriptor are the SAME halo rows shifted by one
+// pixel each (LBO = 128 B), K = 8 pixels of one image row (two 4-row BASE32B atoms, SBO = 512 B).
+// Three TMEM accumulators (one per r).  Operand traffic per 32 pixels: 24 KB (X) + BN/32 * 8 KB (dY), versus
+// 9 x 8 KB + taps-tiles x dY in conv_tc_wgrad_kernel.
+// =============================================================================================================
+struct Wg2Params {
+  int tiles_w, tiles_h, n_img, total_tiles, tiles_per_split;
+  float* dw;
+  int Cin, Cout;
+};
+
+template <int BN, int PASSES, int STAGES>
+struct Wg2Cfg {
+  static constexpr uint32_t NPL = PASSES == 3 ? 2 : 1;
+  static constexpr uint32_t A_PLANE = 6 * 16 * 128;           // 12288 B halo box
+  static constexpr uint32_t B_PLANE = BN * 128;               // BN/32 boxes of 32 px x 128 B
+  static constexpr uint32_t STAGE_BYTES = (A_PLANE + B_PLANE) * NPL;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = 3 * BN <= 128 ? 128 : (3 * BN <= 256 ? 256 : 512);
+};
+
+template <int BN, int PASSES, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_constant__ CUtensorMap mapX_lo,
+                      const __grid_constant__ CUtensorMap mapY_hi, const __grid_constant__ CUtensorMap mapY_lo,
+                      const __grid_constant__ Wg2Params p) {
+  using Cfg = Wg2Cfg<BN, PASSES, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ci0 = blockIdx.x * 32;
+  const int n_off = blockIdx.y * BN;
+  const int t_begin = blockIdx.z * p.tiles_per_split;
+  int t_end = t_begin + p.tiles_per_split;
+  if (t_end > p.total_tiles) t_end = p.total_tiles;
+  const int num_k = t_end - t_begin;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kt = 0; kt < num_k; ++kt) {
+        const int s = kt % STAGES;
+        const uint32_t ph = (kt / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        const int tile = t_begin + kt;
+        const int twi = tile % p.tiles_w;
+        const int thi = (tile / p.tiles_w) % p.tiles_h;
+        const int n = tile / (p.tiles_w * p.tiles_h);
+        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+        mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+        tma_load_5d(st, &mapX_hi, &full[s], ci0, twi * 8 - 1, 0, thi * 4 - 1, n);
+        if (PASSES == 3) tma_load_5d(st + Cfg::A_PLANE, &mapX_lo, &full[s], ci0, twi * 8 - 1, 0, thi * 4 - 1, n);
+        uint8_t* sb = st + Cfg::A_PLANE * Cfg::NPL;
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j) {
+          tma_load_5d(sb + j * 4096, &mapY_hi, &full[s], n_off + j * 32, twi * 8, 0, thi * 4, n);
+          if (PASSES == 3) tma_load_5d(sb + Cfg::B_PLANE + j * 4096, &mapY_lo, &full[s], n_off + j * 32, twi * 8, 0, thi * 4, n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && num_k > 0) {
+      constexpr uint32_t idesc = idesc_tf32(128, BN, 1, 1);
+      for (int kt = 0; kt < num_k; ++kt) {
+        const int s = kt % STAGES;
+        const uint32_t ph = (kt / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint32_t a_lo = a_hi + Cfg::A_PLANE;
+        const uint32_t b_hi = a_hi + Cfg::A_PLANE * Cfg::NPL;
+        const uint32_t b_lo = b_hi + Cfg::B_PLANE;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const uint32_t tmem_d = tmem_base + (uint32_t)(r * BN);
+#pragma unroll
+          for (int hl = 0; hl < 4; ++hl) {
+            const uint32_t ao = (uint32_t)((hl + r) * 16) * 128u;        // halo row hl+r, column tap s via LBO
+            const uint32_t bo_ = (uint32_t)hl * 1024u;                    // dY rows hl*8 .. hl*8+7
+            const uint64_t da_hi = smem_desc_sw128(a_hi + ao, 128, 512, 1);
+            const uint64_t db_hi = smem_desc_sw128(b_hi + bo_, 4096, 512, 1);
+            mma_tf32(tmem_d, da_hi, db_hi, idesc, (kt > 0 || hl > 0) ? 1u : 0u);
+            if (PASSES == 3) {
+              const uint64_t da_lo = smem_desc_sw128(a_lo + ao, 128, 512, 1);
+              const uint64_t db_lo = smem_desc_sw128(b_lo + bo_, 4096, 512, 1);
+              mma_tf32(tmem_d, da_hi, db_lo, idesc, 1u);
+              mma_tf32(tmem_d, da_lo, db_hi, idesc, 1u);
+            }
+          }
+        }
+        mma_commit(&empty[s]);
+      }
+      mma_commit(tmem_full);
+    }
+  } else if (num_k > 0) {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int s = m >> 5;                 // column tap (0..3; 3 is the overhang group)
+    const int ci = ci0 + (m & 31);
+    const bool row_ok = (s < 3) && (ci < p.Cin);
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * BN + c0), v);
+        if (!row_ok) continue;
+        const int col0 = n_off + c0;
+        if (col0 >= p.Cout) continue;
+        float* o = p.dw + ((size_t)(r * 3 + s) * p.Cin + ci) * p.Cout + col0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.Cout) atomicAdd(o + j, v[j]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+bool conv_tc2_wgrad_eligible(const immb_conv_desc* d) {
+  if (!conv_tc2_enabled()) return false;
+  if (d->x_layout != IMMB_XLAYOUT_NHWC || d->kh != 3 || d->kw != 3 || d->stride != 1) return false;
+  if (d->H % 4 || d->W % 8 || d->pad_t != 1 || d->pad_l != 1) return false;
+  return true;
+}
+
+template <int BN, int PASSES>
+static int launch_wg2(const CUtensorMap& x_hi, const CUtensorMap& x_lo, const CUtensorMap& y_hi,
+                      const CUtensorMap& y_lo, const Wg2Params& p, dim3 grid, cudaStream_t st) {
+  constexpr int STAGES = PASSES == 3 ? (BN <= 64 ? 4 : 3) : 4;
+  using Cfg = Wg2Cfg<BN, PASSES, STAGES>;
+  auto kern = conv_tc2_wgrad_kernel<BN, PASSES, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "conv_tc2_wgrad smem attr: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  kern<<<grid, 192, Cfg::SMEM_BYTES, st>>>(x_hi, x_lo, y_hi, y_lo, p);
+  return check_launch("conv_tc2_wgrad_kernel");
+}
+
+int conv_tc2_wgrad_run(const immb_conv_desc* d, const float* x_hi, const float* x_lo, const float* dy_hi,
+                       const float* dy_lo, float* dw, cudaStream_t st) {
+  const int passes = d->precision == IMMB_PREC_TF32 ? 1 : 3;
+  Wg2Params p;
+  memset(&p, 0, sizeof(p));
+  p.tiles_w = d->W / 8; p.tiles_h = d->H / 4; p.n_img = d->N;
+  p.total_tiles = p.tiles_w * p.tiles_h * d->N;
+  p.dw = dw; p.Cin = d->Cin; p.Cout = d->Cout;
+  const int bn = d->Cout % 128 == 0 ? 128 : (d->Cout % 64 == 0 ? 64 : 32);
+  const int n_tiles = ceil_div(d->Cout, bn);
+  const int c_tiles = d->cin_pad / 32;
+  int splits = ceil_div(kNumSMs * 2, c_tiles * n_tiles);
+  if (splits > p.total_tiles) splits = p.total_tiles;
+  if (splits < 1) splits = 1;
+  p.tiles_per_split = ceil_div(p.total_tiles, splits);
+  splits = ceil_div(p.total_tiles, p.tiles_per_split);
+  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)9 * d->Cin * d->Cout, st);
+  if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "wgrad memset: %s", cudaGetErrorString(e));
+  CUtensorMap mx_hi, mx_lo, my_hi, my_lo;
+  int rc;
+  if ((rc = tc_make_act_map(&mx_hi, x_hi, d->N, d->H, d->W, d->Cin, d->x_cstride, false, 16, 6, 1, 1))) return rc;
+  if ((rc = tc_make_act_map(&my_hi, dy_hi, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, 8, 4, 1, 1))) return rc;
+  mx_lo = mx_hi; my_lo = my_hi;
+  if (passes == 3) {
+    if ((rc = tc_make_act_map(&mx_lo, x_lo, d->N, d->H, d->W, d->Cin, d->x_cstride, false, 16, 6, 1, 1))) return rc;
+    if ((rc = tc_make_act_map(&my_lo, dy_lo, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, 8, 4, 1, 1))) return rc;
+  }
+  dim3 grid(c_tiles, n_tiles, splits);
+#define IMMB_WG2(BN_)                                                                          \
+  if (bn == BN_)                                                                               \
+    return passes == 3 ? launch_wg2<BN_, 3>(mx_hi, mx_lo, my_hi, my_lo, p, grid, st)           \
+                       : launch_wg2<BN_, 1>(mx_hi, mx_lo, my_hi, my_lo, p, grid, st);
+  IMMB_WG2(32)
+  IMMB_WG2(64)
+  IMMB_WG2(128)
+#undef IMMB_WG2
+  return set_error(IMMB_ERR_INVALID, "conv_tc2_wgrad: bn");
+}
+
 }  // namespace immb
