@@ -736,6 +736,52 @@ __global__ void vgg_prologue_patch_kernel(const float* __restrict__ gt, const fl
   }
 }
 
+// VGG conv1_1 (Cin = 1) fused with the gray/normalise prologue.  block = 256 threads = 64 pixels x 4 channel groups;
+// each thread produces Cout/4 (= 16) channels of one pixel from its 9 gray taps; weights live in shared memory.
+template <int COUT>
+__global__ void __launch_bounds__(256) vgg_conv1_1_fused_kernel(const float* __restrict__ gt, const float* __restrict__ pred,
+                                                                int pcs, int B, int R, const float* __restrict__ w,
+                                                                const float* __restrict__ bias, float* out_hi,
+                                                                float* out_lo) {
+  constexpr int CG = COUT / 4;
+  __shared__ float ws[9][COUT];
+  __shared__ float bs[COUT];
+  for (int i = threadIdx.x; i < 9 * COUT; i += 256) ws[i / COUT][i % COUT] = __ldg(w + i);
+  for (int i = threadIdx.x; i < COUT; i += 256) bs[i] = __ldg(bias + i);
+  __syncthreads();
+  const int64_t per = (int64_t)B * R * R;
+  const int cg = threadIdx.x & 3;                  // channel group
+  for (int64_t p = (int64_t)blockIdx.x * 64 + (threadIdx.x >> 2); p < 2 * per; p += (int64_t)gridDim.x * 64) {
+    int wq = (int)(p % R);
+    int64_t q = p / R;
+    int h = (int)(q % R);
+    int64_t n = q / R;
+    float g[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      int hh = h + t / 3 - 1, ww = wq + t % 3 - 1;
+      float v = 0.f;
+      if (hh >= 0 && hh < R && ww >= 0 && ww < R) {
+        int64_t src = (n * R + hh) * R + ww;
+        v = src < per ? gray_norm(gt + src * 3) : gray_norm(pred + (src - per) * pcs);
+      }
+      g[t] = v;
+    }
+    float acc[CG];
+#pragma unroll
+    for (int j = 0; j < CG; ++j) acc[j] = bs[cg * CG + j];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int j = 0; j < CG; ++j) acc[j] = fmaf(g[t], ws[t][cg * CG + j], acc[j]);
+    size_t o = (size_t)p * COUT + cg * CG;
+#pragma unroll
+    for (int j = 0; j < CG; j += 4)
+      store_split4(out_hi, out_lo, o + j,
+                   make_float4(fmaxf(acc[j], 0.f), fmaxf(acc[j + 1], 0.f), fmaxf(acc[j + 2], 0.f), fmaxf(acc[j + 3], 0.f)));
+  }
+}
+
 // first-layer staging: image [N,H,W,3] -> [N,H,W+8,4] (3 zero columns left, 5 right, 4th channel zero)
 __global__ void stage_image_rowwin_kernel(const float* __restrict__ img, int N, int H, int W, float* x_hi,
                                           float* x_lo) {
@@ -1261,6 +1307,16 @@ extern "C" int immb_vgg_prologue(const float* gt, const float* pred, int pcs, in
     vgg_prologue_kernel<<<ew_grid((int64_t)2 * B * R * R), 256, 0, ST(stream)>>>(gt, pred, pcs, B, R, out_hi,
                                                                                 out_lo);
   return check_launch("vgg_prologue");
+}
+
+extern "C" int immb_vgg_conv1_1_fused(const float* gt, const float* pred, int pcs, int B, int R, const float* w,
+                                      const float* bias, int Cout, float* out_hi, float* out_lo, void* stream) {
+  IMMB_REQUIRE(gt && pred && w && bias && out_hi && pcs >= 3, "vgg_conv1_1_fused: bad args");
+  IMMB_REQUIRE(Cout == 64, "vgg_conv1_1_fused: Cout must be 64 (VGG16 conv1_1)");
+  int64_t blocks = ((int64_t)2 * B * R * R + 63) / 64;
+  if (blocks > (int64_t)kNumSMs * 32) blocks = (int64_t)kNumSMs * 32;
+  vgg_conv1_1_fused_kernel<64><<<(int)blocks, 256, 0, ST(stream)>>>(gt, pred, pcs, B, R, w, bias, out_hi, out_lo);
+  return check_launch("vgg_conv1_1_fused");
 }
 
 extern "C" int immb_stage_image_rowwin(const float* image, int N, int H, int W, float* x4_hi, float* x4_lo,

@@ -506,13 +506,20 @@ class IMMEngine(object):
       raise _lib.ImmbError('VGG16 weights not loaded (load_vgg_caffe_dict)')
     st = _lib.stream_ptr()
     B, R = self.B, self.R
-    call('immb_vgg_prologue', self.future_image, self.pred, self.pcs, B, R, 1, self.vgg_in.hi, self.vgg_in.lo, st)
+    fused_first = self.engine != _lib.ENGINE_SIMT
+    if not fused_first:
+      call('immb_vgg_prologue', self.future_image, self.pred, self.pcs, B, R, 1, self.vgg_in.hi, self.vgg_in.lo, st)
     X = self.vgg_in
     for kind, item, cin, size in self.vgg_seq:
       if kind == 'conv':
         item.x = X
         _lib.TAG = 'fwd:vgg/%s' % item.name
-        self._conv_fwd(item, X, item.out.hi, item.out.lo)
+        if item.name == 'conv1_1' and fused_first:
+          # Cin = 1: HBM-bound, exact-fp32 CUDA-core kernel straight from the RGB inputs (no patch tensor)
+          call('immb_vgg_conv1_1_fused', self.future_image, self.pred, self.pcs, B, R, item.w, item.b, item.cout,
+               item.out.hi, item.out.lo, st)
+        else:
+          self._conv_fwd(item, X, item.out.hi, item.out.lo)
         X = item.out
       else:
         O = self.vgg_act[item]

@@ -370,6 +370,22 @@ def test_vgg_patch_prologue_and_adjoint():
   assert rel_err((gh + gl)[..., :3], ims.grad[B:]) < 1e-5
 
 
+def test_vgg_conv1_1_fused():
+  B, R = 2, 16
+  g = torch.Generator().manual_seed(12)
+  gt = torch.rand(B, R, R, 3, generator=g) * 255
+  pred12 = torch.randn(B, R, R, 12, generator=g) * 60
+  w = torch.randn(3, 3, 1, 64, generator=g)
+  b = torch.randn(64, generator=g) * 0.1
+  ims = torch.cat([gt, pred12[..., :3]], 0).double()
+  gray = ims.mean(3, keepdim=True) / 255.0 - O.VGG_MEAN / 255.0
+  ref = torch.relu(O.conv2d_same(gray, w.double(), b.double(), 1))
+  dev = 'cuda'
+  oh, ol = torch.empty(2 * B, R, R, 64, device=dev), torch.empty(2 * B, R, R, 64, device=dev)
+  call('immb_vgg_conv1_1_fused', gt.to(dev), pred12.to(dev), 12, B, R, w.to(dev), b.to(dev), 64, oh, ol, ST())
+  assert rel_err(oh + ol, ref) < 1e-5
+
+
 def test_first_layer_rowwin_tcgen05():
   """7x7 / Cin=3 encoder conv_1 on the tensor cores via the staged row-window image (fwd + wgrad)."""
   N, R, Cout = 2, 32, 32

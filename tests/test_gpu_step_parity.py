@@ -76,6 +76,20 @@ def test_step_parity_k30_batch3():
   _check_step(eng, st64, st32, r64, r32)
 
 
+def test_step_parity_k50_batch2():
+  """AFLW-50pts model section (config 4 per-GPU model): 50 landmarks -> 52-stride heat-maps, Cj = 320."""
+  eng, st64, st32, r64, r32 = _run_step(2, 50, seed=2)
+  _check_step(eng, st64, st32, r64, r32)
+
+
+def test_step_parity_256px_batch1():
+  """Config 5 shape: 256x256 inputs -> 32x32 heat-maps, align_corners resize of the 32x32 encoder block to the
+  16x16 render size (imm_model.py:324-335), 10 renderer convs."""
+  eng, st64, st32, r64, r32 = _run_step(1, 10, image_size=256, seed=3)
+  assert eng.enc_out_size == 32 and len(eng.ren_layers) == 10
+  _check_step(eng, st64, st32, r64, r32)
+
+
 def test_param_update_matches_oracle():
   """After one step every parameter (except noise-gradient biases) moved as the oracle's TF-Adam says."""
   eng, st64, st32, inputs = make_pair(2, 10)
