@@ -61,6 +61,7 @@ _SIGS = {
   'immb_pred_grad': [_P, _P, _I, _P, _P, _P, _I, _I, _I, _P, _P, _P],
   'immb_resize_ac_fwd': [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P],
   'immb_resize_ac_bwd': [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+  'immb_tps_warp': [_P, _I, _I, _I, _I, _P, _I, _I, _P, _P],
   'immb_adam_norms': [_P, _P, _L, _P, _P, _P, _I, _P, _F, _P, _P, _P],
   'immb_adam_apply': [_P, _P, _P, _P, _L, _P, _P, _P, _I, _P, _F, _P, _F, _F, _F, _F, _F, _P],
   'immb_total_loss': [_P, _P, _P, _I, _P, _P, _P],

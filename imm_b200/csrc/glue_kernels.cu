@@ -1141,6 +1141,50 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int taps, int C
   }
 }
 
+// Thin-plate-spline warp: one thread per output pixel; the (Hc*Wc+3) x 2 parameters of the image are staged in
+// shared memory; U(|g-c|^2) is evaluated on the fly (no [H*W, M+3] matrix in HBM).
+__global__ void __launch_bounds__(256) tps_warp_kernel(const float* __restrict__ src, int H, int W, int C,
+                                                       const float* __restrict__ w_tps, int Hc, int Wc, float* dst) {
+  extern __shared__ float wsm[];                 // [(M+3)*2]
+  const int b = blockIdx.y;
+  const int M = Hc * Wc;
+  for (int i = threadIdx.x; i < (M + 3) * 2; i += blockDim.x) wsm[i] = __ldg(w_tps + (size_t)b * (M + 3) * 2 + i);
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= H * W) return;
+  const int ho = p / W, wo = p - ho * W;
+  const float gx = W > 1 ? -1.f + 2.f * (float)wo / (float)(W - 1) : -1.f;     // np.linspace(-1, 1, W)
+  const float gy = H > 1 ? -1.f + 2.f * (float)ho / (float)(H - 1) : -1.f;
+  float ox = wsm[M * 2] + gx * wsm[(M + 1) * 2] + gy * wsm[(M + 2) * 2];
+  float oy = wsm[M * 2 + 1] + gx * wsm[(M + 1) * 2 + 1] + gy * wsm[(M + 2) * 2 + 1];
+  for (int j = 0; j < M; ++j) {
+    const int cj = j % Wc, ci = j / Wc;
+    const float cx = Wc > 1 ? -1.f + 2.f * (float)cj / (float)(Wc - 1) : -1.f;
+    const float cy = Hc > 1 ? -1.f + 2.f * (float)ci / (float)(Hc - 1) : -1.f;
+    float d2 = (gx - cx) * (gx - cx) + (gy - cy) * (gy - cy);
+    d2 = fmaxf(d2, 1e-8f);
+    const float k = logf(d2) * d2;
+    ox = fmaf(k, wsm[j * 2], ox);
+    oy = fmaf(k, wsm[j * 2 + 1], oy);
+  }
+  // grid_sample, bilinear, zero padding, corner-aligned: pixel = (coord + 1) / 2 * (size - 1)
+  const float ix = (ox + 1.f) * 0.5f * (float)(W - 1), iy = (oy + 1.f) * 0.5f * (float)(H - 1);
+  const float fx = floorf(ix), fy = floorf(iy);
+  const int x0 = (int)fx, y0 = (int)fy;
+  const float ax = ix - fx, ay = iy - fy;
+  const float wts[4] = {(1.f - ax) * (1.f - ay), ax * (1.f - ay), (1.f - ax) * ay, ax * ay};
+  const int xs[4] = {x0, x0 + 1, x0, x0 + 1}, ys[4] = {y0, y0, y0 + 1, y0 + 1};
+  const float* sb = src + (size_t)b * H * W * C;
+  float* o = dst + ((size_t)b * H * W + p) * C;
+  for (int c = 0; c < C; ++c) {
+    float v = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (xs[t] >= 0 && xs[t] < W && ys[t] >= 0 && ys[t] < H) v += wts[t] * __ldg(sb + ((size_t)ys[t] * W + xs[t]) * C + c);
+    o[c] = v;
+  }
+}
+
 static inline int ew_grid(int64_t total, int block = 256) {
   int64_t g = (total + block - 1) / block;
   int64_t cap = (int64_t)kNumSMs * 16;
@@ -1421,6 +1465,17 @@ extern "C" int immb_resize_ac_bwd(const float* g_out, int gcs, int N, int H, int
   resize_ac_bwd_kernel<<<ew_grid((int64_t)N * Ho * Wo * C), 256, 0, ST(stream)>>>(g_out, gcs, N, H, W, C, Ho,
                                                                                  Wo, g_in);
   return check_launch("resize_ac_bwd");
+}
+
+extern "C" int immb_tps_warp(const float* src, int B, int H, int W, int C, const float* w_tps, int Hc, int Wc,
+                             float* dst, void* stream) {
+  IMMB_REQUIRE(src && w_tps && dst && B > 0 && H > 0 && W > 0 && C > 0 && C <= 8 && Hc > 0 && Wc > 0,
+               "tps_warp: bad args (C <= 8)");
+  IMMB_REQUIRE(src != dst, "tps_warp: in-place warp is not supported");
+  size_t smem = sizeof(float) * (size_t)(Hc * Wc + 3) * 2;
+  IMMB_REQUIRE(smem <= 40000, "tps_warp: too many control points");
+  tps_warp_kernel<<<dim3(ceil_div((int64_t)H * W, 256), B), 256, smem, ST(stream)>>>(src, H, W, C, w_tps, Hc, Wc, dst);
+  return check_launch("tps_warp");
 }
 
 extern "C" int immb_adam_norms(const float* p, const float* g, int64_t n, const int32_t* chunk_tensor,

@@ -299,6 +299,17 @@ class IMMEngine(object):
   def _alloc_buffers(self):
     dev, B, R, K = self.dev, self.B, self.R, self.K
     f32 = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+    # double accumulators live in two pools that are cleared with ONE memset per pass (fwd / bwd)
+    n_fwd = sum(2 * L.cout for L in self.layers.values() if L.bn) + len(self.comp)
+    n_bwd = sum((2 * L.cout if L.bn else 0) + L.cout for L in self.layers.values())
+    self.fwd_pool = torch.zeros(n_fwd, dtype=torch.float64, device=dev)
+    self.bwd_pool = torch.zeros(n_bwd, dtype=torch.float64, device=dev)
+    cur = {'f': 0, 'b': 0}
+
+    def take(pool, key, n):
+      v = pool[cur[key]:cur[key] + n]
+      cur[key] += n
+      return v
     f64z = lambda n: torch.zeros(n, dtype=torch.float64, device=dev)
     self.joint = Planes.alloc((B, 16, 16, self.Cj), dev, zero=True)     # pad channels stay zero
     ws_bytes = 0
@@ -306,9 +317,9 @@ class IMMEngine(object):
       self._alloc_weight_planes(L)
       L.y = torch.zeros((B, L.Ho, L.Wo, L.ycs), dtype=torch.float32, device=dev)
       L.dy = Planes.alloc((B, L.Ho, L.Wo, L.ycs), dev, zero=True)
-      L.dbias_acc = f64z(L.cout)
+      L.dbias_acc = take(self.bwd_pool, 'b', L.cout)
       if L.bn:
-        L.sums, L.bsums = f64z(2 * L.cout), f64z(2 * L.cout)
+        L.sums, L.bsums = take(self.fwd_pool, 'f', 2 * L.cout), take(self.bwd_pool, 'b', 2 * L.cout)
         L.scale, L.shift, L.mean, L.invstd = f32(L.cout), f32(L.cout), f32(L.cout), f32(L.cout)
         L.g_low = f32(B, L.Ho, L.Wo, L.cout) if L.up2x else None
       if L.needs_dgrad:
@@ -349,7 +360,7 @@ class IMMEngine(object):
       else:
         self.vgg_act[item] = Planes.alloc((2 * B, size // 2, size // 2, cin), dev)
     self.g_pool = {item: f32(B, size, size, cin) for kind, item, cin, size in self.vgg_seq if kind == 'pool'}
-    self.level_acc = f64z(len(self.comp))
+    self.level_acc = take(self.fwd_pool, 'f', len(self.comp))
     counts = []
     for nm in self.comp:
       if nm == 'input':
@@ -454,7 +465,6 @@ class IMMEngine(object):
       return None
     npix = L.N * L.Ho * L.Wo
     if training:
-      L.sums.zero_()
       call('immb_bn_stats', L.y, npix, L.cout, L.ycs, L.sums, st)
     call('immb_bn_finalize', L.sums, npix, L.cout, L.gamma, L.beta, L.mm, L.mv, 1 if training else 0,
          L.scale, L.shift, L.mean, L.invstd, st)
@@ -472,6 +482,7 @@ class IMMEngine(object):
     if self.use_mask and mask is None and build_loss:
       raise RuntimeError('No loss mask recieved but is required.')      # imm_model.py:363-367
     self.training = training
+    self.fwd_pool.zero_()
     # image encoder (imm_model.py:220-230) and pose encoder (:233-248)
     for enc, inp in (('image_encoder', image), ('pose_encoder', future_image)):
       X = Planes(inp, None)
@@ -525,7 +536,6 @@ class IMMEngine(object):
         O = self.vgg_act[item]
         call('immb_maxpool2x2_fwd', X.hi, X.lo, 2 * B, size, size, cin, O.hi, O.lo, st)
         X = O
-    self.level_acc.zero_()
     for k, nm in enumerate(self.comp):
       if nm == 'input':
         call('immb_perceptual_level_sum', self.future_image, None, 3, self.pred, None, self.pcs, B, R, R, 3,
@@ -562,8 +572,6 @@ class IMMEngine(object):
       if L.up2x:
         call('immb_upsample2x_bwd', g, L.N, L.Ho, L.Wo, L.cout, gcs, L.g_low, st)
         g, gcs = L.g_low, L.cout
-      L.bsums.zero_()
-      L.dbias_acc.zero_()
       relu = 1 if L.relu else 0
       call('immb_bn_bwd_reduce', g, gcs, L.y, L.cout, npix, L.cout, L.scale, L.shift, L.mean, L.invstd, relu,
            L.bsums, st)
@@ -576,7 +584,6 @@ class IMMEngine(object):
         assert gcs == L.ycs
         call('immb_split_planes', g, L.dy.hi, L.dy.lo, npix * L.ycs, st)
         dy = L.dy
-      L.dbias_acc.zero_()
       call('immb_bias_grad', dy.hi, dy.lo, L.ycs, npix, L.cout, L.dbias_acc, st)
     call('immb_cast_d2f', L.dbias_acc, L.db, L.cout, st)
     d = L.desc()
@@ -626,6 +633,7 @@ class IMMEngine(object):
     """Gradients of (reconstruction loss) wrt every trainable tensor; the L2 term is added in the optimiser."""
     st = _lib.stream_ptr()
     B, K = self.B, self.K
+    self.bwd_pool.zero_()
     g = self._loss_bwd()
     gcs = self.pcs
     for L in reversed(self.ren_layers):

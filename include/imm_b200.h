@@ -206,6 +206,13 @@ int immb_resize_ac_fwd(const float* x_hi, const float* x_lo, int x_cstride, int 
 int immb_resize_ac_bwd(const float* g_out, int g_cstride, int N, int H, int W, int C, int Ho, int Wo,
                        float* g_in, void* stream);
 
+/* ---- input pipeline: imm/utils/tps_sampler.py:77-165 + tps_dataset.py:70-96 ----------------
+ * dst[B,H,W,C] = grid_sample(src[B,H,W,C], TPSGridGen(H,W,Hc,Wc)(w_tps[B,Hc*Wc+3,2])): thin-plate-spline grid
+ * (U(d2) = d2 log d2 on a regular Hc x Wc control lattice in [-1,1]^2, affine rows last) evaluated per output pixel
+ * and sampled bilinearly with zero padding and corner-aligned coordinates (PyTorch-0.4 grid_sample), C <= 8. */
+int immb_tps_warp(const float* src, int B, int H, int W, int C, const float* w_tps, int Hc, int Wc, float* dst,
+                  void* stream);
+
 /* ---- optimiser: cnn_train_multi.py:93-98,232-241 + scripts/train.py:92-98 + nn_utils.py:44-46 ---- */
 /* Flat buffers of n floats hold every trainable tensor back to back.  The chunk table splits them into
  * chunks: chunk_tensor[i] = tensor id, chunk_off[i] = start offset, chunk_len[i] <= 1024*? elements.
