@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libimm_b200.so')
 
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
-PREC_TF32X3, PREC_TF32 = 0, 1
+PREC_TF32X3, PREC_TF32, PREC_TF32X2 = 0, 1, 2
 EPI_BIAS, EPI_BIAS_RELU = 0, 1
 XLAYOUT_NHWC, XLAYOUT_ROWWIN4 = 0, 1
 

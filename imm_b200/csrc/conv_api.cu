@@ -69,7 +69,8 @@ extern "C" int immb_conv2d_fwd(const immb_conv_desc* d, const float* x_hi, const
   if ((rc = pick_engine(d, 0, &engine))) return rc;
   if (engine == IMMB_ENGINE_TC) {
     IMMB_REQUIRE(wp_hi && (d->precision == IMMB_PREC_TF32 || (wp_lo && x_lo)),
-                 "conv2d_fwd: tcgen05 engine needs packed weights and (for TF32x3) lo planes");
+                 "conv2d_fwd: tcgen05 engine needs packed weights and (for TF32x3 / TF32x2) lo planes");
+    IMMB_REQUIRE(d->precision >= IMMB_PREC_TF32X3 && d->precision <= IMMB_PREC_TF32X2, "conv2d_fwd: bad precision");
     return conv_tc_fwd(d, x_hi, x_lo, wp_hi, wp_lo, bias, y_hi, y_lo, (cudaStream_t)stream);
   }
   IMMB_REQUIRE(w, "conv2d_fwd: SIMT engine needs the master weights");

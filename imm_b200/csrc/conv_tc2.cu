@@ -40,13 +40,15 @@ struct Tc2Params {
 
 template <int BN, int PASSES>
 struct Tc2Cfg {
-  static constexpr uint32_t NPL = PASSES == 3 ? 2 : 1;
+  // PASSES: 1 = hi*hi; 2 = hi*hi + lo*hi (weight operand exactly TF32); 3 = hi*hi + hi*lo + lo*hi
+  static constexpr uint32_t NPLA = PASSES >= 2 ? 2 : 1;       // activation planes
+  static constexpr uint32_t NPLB = PASSES == 3 ? 2 : 1;       // weight planes
   static constexpr uint32_t A_PLANE = 18 * 16 * 128;          // 36864 B: (16+2) halo rows x 16 pixels x 32 ch
-  static constexpr uint32_t A_SLOT = A_PLANE * NPL;
+  static constexpr uint32_t A_SLOT = A_PLANE * NPLA;
   static constexpr uint32_t A_SLOTS = 2;
   static constexpr uint32_t B_PLANE = BN * 128;
-  static constexpr uint32_t B_SLOT = B_PLANE * NPL;
-  static constexpr uint32_t B_SLOTS = BN <= 64 ? 4 : 2;
+  static constexpr uint32_t B_SLOT = B_PLANE * NPLB;
+  static constexpr uint32_t B_SLOTS = (B_SLOT <= 16384) ? 4 : ((A_SLOTS * A_SLOT + 3 * B_SLOT <= 225000) ? 3 : 2);
   static constexpr uint32_t SMEM_BYTES = A_SLOTS * A_SLOT + B_SLOTS * B_SLOT + 1024 + 256;
   static constexpr int ACC_COLS = (BN + 31) / 32 * 32;
   static constexpr int TMEM_COLS = 2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : 256);
@@ -82,7 +84,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapA_hi);
     prefetch_tmap(&mapB_hi);
-    if (PASSES == 3) { prefetch_tmap(&mapA_lo); prefetch_tmap(&mapB_lo); }
+    if (PASSES >= 2) prefetch_tmap(&mapA_lo);
+    if (PASSES == 3) prefetch_tmap(&mapB_lo);
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before();
@@ -107,7 +110,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
           uint8_t* sa = a_base + as * Cfg::A_SLOT;
           mbar_expect_tx(&a_full[as], Cfg::A_SLOT);
           tma_load_5d(sa, &mapA_hi, &a_full[as], kc * 32, tw * 8 - 1, 0, th * 16 - 1, img);
-          if (PASSES == 3) tma_load_5d(sa + Cfg::A_PLANE, &mapA_lo, &a_full[as], kc * 32, tw * 8 - 1, 0, th * 16 - 1, img);
+          if (PASSES >= 2) tma_load_5d(sa + Cfg::A_PLANE, &mapA_lo, &a_full[as], kc * 32, tw * 8 - 1, 0, th * 16 - 1, img);
           ++ai;
           for (int tap = 0; tap < 9; ++tap) {
             const uint32_t bs = bi % Cfg::B_SLOTS, bph = (bi / Cfg::B_SLOTS) & 1;
@@ -153,11 +156,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
               const uint64_t da_hi = smem_desc_sw128(a_hi + a_off + ko, 16, 2048, 2, bo);
               const uint64_t db_hi = smem_desc_sw128(b_hi + ko, 16, 1024);
               mma_tf32(tmem_d, da_hi, db_hi, idesc, (kc > 0 || tap > 0 || k4 > 0) ? 1u : 0u);
-              if (PASSES == 3) {
+              if (PASSES >= 2) {
                 const uint64_t da_lo = smem_desc_sw128(a_lo + a_off + ko, 16, 2048, 2, bo);
+                mma_tf32(tmem_d, da_lo, db_hi, idesc, 1u);
+              }
+              if (PASSES == 3) {
                 const uint64_t db_lo = smem_desc_sw128(b_lo + ko, 16, 1024);
                 mma_tf32(tmem_d, da_hi, db_lo, idesc, 1u);
-                mma_tf32(tmem_d, da_lo, db_hi, idesc, 1u);
               }
             }
             mma_commit(&b_empty[bs]);
@@ -285,7 +290,7 @@ static int launch_tc2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CU
 int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const float* act_lo, int act_c, int act_cs,
                  const float* w_hi, const float* w_lo, int w_rows, int kd, const float* bias, int relu,
                  float* out_hi, float* out_lo, int ocs, int ncols, int n_store, cudaStream_t st) {
-  const int passes = d->precision == IMMB_PREC_TF32 ? 1 : 3;
+  const int passes = d->precision == IMMB_PREC_TF32 ? 1 : (d->precision == IMMB_PREC_TF32X2 ? 2 : 3);
   Tc2Params p;
   memset(&p, 0, sizeof(p));
   p.tiles_w = d->W / 8; p.tiles_h = d->H / 16; p.n_img = d->N;
@@ -308,13 +313,16 @@ int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const flo
   if ((rc = tc_make_act_map(&a_hi, act_hi, d->N, d->H, d->W, act_c, act_cs, false, 16, 18, 1, 0))) return rc;
   if ((rc = tc_make_w_map(&b_hi, w_hi, 9, w_rows, kd, bn))) return rc;
   a_lo = a_hi; b_lo = b_hi;
-  if (passes == 3) {
+  if (passes >= 2) {
     if ((rc = tc_make_act_map(&a_lo, act_lo, d->N, d->H, d->W, act_c, act_cs, false, 16, 18, 1, 0))) return rc;
+  }
+  if (passes == 3) {
     if ((rc = tc_make_w_map(&b_lo, w_lo, 9, w_rows, kd, bn))) return rc;
   }
 #define IMMB_CASE(BN_)                                                                     \
   if (bn == BN_)                                                                           \
     return passes == 3 ? launch_tc2<BN_, 3>(a_hi, a_lo, b_hi, b_lo, p, st)                 \
+         : passes == 2 ? launch_tc2<BN_, 2>(a_hi, a_lo, b_hi, b_lo, p, st)                 \
                        : launch_tc2<BN_, 1>(a_hi, a_lo, b_hi, b_lo, p, st);
   IMMB_CASE(16)
   IMMB_CASE(32)

@@ -413,23 +413,30 @@ struct BnBwdArgs {
   int gcs, ycs, relu;
 };
 
-__device__ __forceinline__ void bn_bwd_elem4(const BnBwdArgs& a, int64_t p, int c, float4& dz, float4& xh) {
+// per-thread constants of the BN backward: the thread's channel quad is fixed for its whole pixel loop
+struct BnBwdRegs {
+  float4 sc, sh, mu, is;
+};
+
+__device__ __forceinline__ void bn_bwd_elem4(const BnBwdArgs& a, const BnBwdRegs& r, int64_t p, int c, float4& dz,
+                                             float4& xh) {
   float4 yy = ld4(a.y + p * a.ycs + c), gg = ld4(a.g + p * a.gcs + c);
-  float4 sc = ld4(a.scale + c), sh = ld4(a.shift + c), mu = ld4(a.mean + c), is = ld4(a.invstd + c);
 #define IMMB_E(f)                                                        \
   {                                                                      \
-    float z = fmaf(yy.f, sc.f, sh.f);                                    \
+    float z = fmaf(yy.f, r.sc.f, r.sh.f);                                \
     dz.f = (a.relu && !(z > 0.f)) ? 0.f : gg.f;                          \
-    xh.f = (yy.f - mu.f) * is.f;                                         \
+    xh.f = (yy.f - r.mu.f) * r.is.f;                                     \
   }
   IMMB_E(x) IMMB_E(y) IMMB_E(z) IMMB_E(w)
 #undef IMMB_E
 }
 
 __global__ void bn_bwd_reduce4_kernel(BnBwdArgs a, int64_t npix, int C, double* sums) {
-  channel_reduce4<2>(npix, C, sums, C, [&](int64_t p, int c4, float4* v) {
+  const int c = (threadIdx.x % (C >> 2)) * 4;
+  const BnBwdRegs r{ld4(a.scale + c), ld4(a.shift + c), ld4(a.mean + c), ld4(a.invstd + c)};
+  channel_reduce4<2>(npix, C, sums, C, [&](int64_t p, int, float4* v) {
     float4 dz, xh;
-    bn_bwd_elem4(a, p, c4 * 4, dz, xh);
+    bn_bwd_elem4(a, r, p, c, dz, xh);
     v[0] = dz;
     v[1] = make_float4(dz.x * xh.x, dz.y * xh.y, dz.z * xh.z, dz.w * xh.w);
   });
@@ -442,19 +449,20 @@ __global__ void bn_bwd_apply4_kernel(BnBwdArgs a, int64_t npix, int C, const dou
     dbeta[threadIdx.x] = (float)sums[threadIdx.x];
     dgamma[threadIdx.x] = (float)sums[C + threadIdx.x];
   }
-  channel_reduce4<1>(npix, C, dbias_acc, C, [&](int64_t p, int c4, float4* v) {
-    const int c = c4 * 4;
+  const int c = (threadIdx.x % (C >> 2)) * 4;
+  const BnBwdRegs r{ld4(a.scale + c), ld4(a.shift + c), ld4(a.mean + c), ld4(a.invstd + c)};
+  const float4 mdz = make_float4((float)(sums[c] * inv_n), (float)(sums[c + 1] * inv_n), (float)(sums[c + 2] * inv_n),
+                                 (float)(sums[c + 3] * inv_n));
+  const float4 mdzx = make_float4((float)(sums[C + c] * inv_n), (float)(sums[C + c + 1] * inv_n),
+                                  (float)(sums[C + c + 2] * inv_n), (float)(sums[C + c + 3] * inv_n));
+  channel_reduce4<1>(npix, C, dbias_acc, C, [&](int64_t p, int, float4* v) {
     float4 dz, xh;
-    bn_bwd_elem4(a, p, c, dz, xh);
-    float4 sc = ld4(a.scale + c);
+    bn_bwd_elem4(a, r, p, c, dz, xh);
     float4 dy;
-#define IMMB_E(f, j)                                                                 \
-    {                                                                                \
-      float mdz = (float)(sums[c + j] * inv_n), mdzx = (float)(sums[C + c + j] * inv_n); \
-      dy.f = sc.f * (dz.f - mdz - xh.f * mdzx);                                      \
-    }
-    IMMB_E(x, 0) IMMB_E(y, 1) IMMB_E(z, 2) IMMB_E(w, 3)
-#undef IMMB_E
+    dy.x = r.sc.x * (dz.x - mdz.x - xh.x * mdzx.x);
+    dy.y = r.sc.y * (dz.y - mdz.y - xh.y * mdzx.y);
+    dy.z = r.sc.z * (dz.z - mdz.z - xh.z * mdzx.z);
+    dy.w = r.sc.w * (dz.w - mdz.w - xh.w * mdzx.w);
     store_split4(dy_hi, dy_lo, (size_t)(p * C + c), dy);
     v[0] = dy;
   });

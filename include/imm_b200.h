@@ -47,7 +47,10 @@ typedef enum {
 
 typedef enum {
   IMMB_PREC_TF32X3 = 0,       /* error-compensated: hi*hi + hi*lo + lo*hi, fp32 accumulate (parity grade) */
-  IMMB_PREC_TF32 = 1          /* single pass on the hi planes (does NOT meet the 1e-3 parity bar) */
+  IMMB_PREC_TF32 = 1,         /* single pass on the hi planes (does NOT meet the 1e-3 parity bar) */
+  IMMB_PREC_TF32X2 = 2        /* hi*w + lo*w: exact 3xTF32 result when the WEIGHT operand is exactly representable in
+                                 TF32 (its lo plane is all zeros), e.g. the frozen VGG16 tower whose weights are rounded
+                                 to TF32 once at load; saves one of the three tensor-core passes */
 } immb_precision;
 
 typedef enum {
