@@ -28,6 +28,7 @@ struct Tc2Tap {
 
 struct Tc2Params {
   int tiles_w, tiles_h, n_img, n_tiles_n, total_tiles;
+  int m_tiles, total_pairs;      // cluster mode: ceil(m_tiles / 2) * n_tiles_n pair iterations
   int kchunks;
   Tc2Tap taps[9];
   float* out_hi;
@@ -54,12 +55,19 @@ struct Tc2Cfg {
   static constexpr int TMEM_COLS = 2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : 256);
 };
 
-template <int BN, int PASSES>
+// CL = 2: the CTA pair of a 2-CTA cluster works on two M tiles of the SAME N tile in lockstep; each CTA fetches half
+// of every weight slice and TMA-multicasts it into both CTAs' shared memory, which halves the L2 -> smem traffic of
+// the weight operand (the limiter of the big layers).  b_empty then counts 2 arrivals (own + peer MMA commits).
+template <int BN, int PASSES, int CL>
 __global__ void __launch_bounds__(192, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
                 const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
                 const __grid_constant__ Tc2Params p) {
   using Cfg = Tc2Cfg<BN, PASSES>;
+  const uint32_t crank = CL == 2 ? cluster_ctarank() : 0u;
+  const int tile0 = CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // first pair-tile / tile of this CTA
+  const int tstep = CL == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int n_iter_total = CL == 2 ? p.total_pairs : p.total_tiles;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_base = smem;
@@ -77,7 +85,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
 
   if (threadIdx.x == 0) {
     for (uint32_t i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (uint32_t i = 0; i < Cfg::B_SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (uint32_t i = 0; i < Cfg::B_SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], CL); }
     for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
     fence_mbar_init();
   }
@@ -90,20 +98,35 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();                   // peer barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  // iteration -> (m tile, n tile); with CL == 2 the pair shares the n tile and CTA `crank` takes m tile 2*jm + crank
+  // (clamped to the last m tile when the count is odd: that CTA recomputes it with stores disabled)
+  auto decode = [&](int it, int& img, int& th, int& tw, int& n_off, bool& live) {
+    const int nt = it % p.n_tiles_n;
+    int mt = it / p.n_tiles_n;
+    live = true;
+    if (CL == 2) {
+      mt = mt * 2 + (int)crank;
+      if (mt >= p.m_tiles) { mt = p.m_tiles - 1; live = false; }
+    }
+    tw = mt % p.tiles_w;
+    int r = mt / p.tiles_w;
+    th = r % p.tiles_h;
+    img = r / p.tiles_h;
+    n_off = nt * BN;
+  };
 
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
       uint32_t ai = 0, bi = 0;                       // running slot counters
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const int nt = t % p.n_tiles_n;
-        int r = t / p.n_tiles_n;
-        const int tw = r % p.tiles_w; r /= p.tiles_w;
-        const int th = r % p.tiles_h;
-        const int img = r / p.tiles_h;
-        const int n_off = nt * BN;
+      for (int t = tile0; t < n_iter_total; t += tstep) {
+        int img, th, tw, n_off;
+        bool live;
+        decode(t, img, th, tw, n_off, live);
         for (int kc = 0; kc < p.kchunks; ++kc) {
           const uint32_t as = ai % Cfg::A_SLOTS, aph = (ai / Cfg::A_SLOTS) & 1;
           mbar_wait(&a_empty[as], aph ^ 1);
@@ -117,8 +140,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
             mbar_wait(&b_empty[bs], bph ^ 1);
             uint8_t* sb = b_base + bs * Cfg::B_SLOT;
             mbar_expect_tx(&b_full[bs], Cfg::B_SLOT);
-            tma_load_3d(sb, &mapB_hi, &b_full[bs], kc * 32, n_off, p.taps[tap].b_tap);
-            if (PASSES == 3) tma_load_3d(sb + Cfg::B_PLANE, &mapB_lo, &b_full[bs], kc * 32, n_off, p.taps[tap].b_tap);
+            if (CL == 2) {
+              // my half of the rows, into both CTAs
+              const uint32_t ho = crank * (Cfg::B_PLANE / 2);
+              const int row0 = n_off + (int)crank * (BN / 2);
+              tma_load_3d_mc(sb + ho, &mapB_hi, &b_full[bs], kc * 32, row0, p.taps[tap].b_tap, (uint16_t)3);
+              if (PASSES == 3)
+                tma_load_3d_mc(sb + Cfg::B_PLANE + ho, &mapB_lo, &b_full[bs], kc * 32, row0, p.taps[tap].b_tap, (uint16_t)3);
+            } else {
+              tma_load_3d(sb, &mapB_hi, &b_full[bs], kc * 32, n_off, p.taps[tap].b_tap);
+              if (PASSES == 3) tma_load_3d(sb + Cfg::B_PLANE, &mapB_lo, &b_full[bs], kc * 32, n_off, p.taps[tap].b_tap);
+            }
             ++bi;
           }
         }
@@ -129,7 +161,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
       // ===== MMA issuer =====
       constexpr uint32_t idesc = idesc_tf32(128, BN, 0, 0);
       uint32_t ai = 0, bi = 0, ti = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = tile0; t < n_iter_total; t += tstep) {
         const uint32_t acc = ti & 1, tph = (ti >> 1) & 1;
         mbar_wait(&t_empty[acc], tph ^ 1);            // epilogue has drained this accumulator
         tc_fence_after();
@@ -165,7 +197,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
                 mma_tf32(tmem_d, da_hi, db_lo, idesc, 1u);
               }
             }
-            mma_commit(&b_empty[bs]);
+            if (CL == 2) mma_commit_mc(&b_empty[bs], (uint16_t)3);
+            else mma_commit(&b_empty[bs]);
             ++bi;
           }
           mma_commit(&a_empty[as]);
@@ -181,13 +214,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
     const int m = q * 32 + lane;
     const int hl = m >> 3, wl = m & 7;
     uint32_t ti = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      const int nt = t % p.n_tiles_n;
-      int r = t / p.n_tiles_n;
-      const int tw = r % p.tiles_w; r /= p.tiles_w;
-      const int th = r % p.tiles_h;
-      const int img = r / p.tiles_h;
-      const int n_off = nt * BN;
+    for (int t = tile0; t < n_iter_total; t += tstep) {
+      int img, th, tw, n_off;
+      bool live;
+      decode(t, img, th, tw, n_off, live);
       const uint32_t acc = ti & 1, tph = (ti >> 1) & 1;
       const int h = th * 16 + hl, w = tw * 8 + wl;
       const size_t pix = ((size_t)img * p.H + h) * p.W + w;
@@ -198,7 +228,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS + (uint32_t)c0, v);
         const int col0 = n_off + c0;
-        if (col0 >= p.n_cols) continue;
+        if (col0 >= p.n_cols || !live) continue;
         if (p.bias) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -239,6 +269,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();                   // nobody exits while the peer may still signal / write into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
@@ -270,20 +301,57 @@ bool conv_tc2_eligible(const immb_conv_desc* d, int op) {
   return true;
 }
 
+// IMMB_TC2_CLUSTER: 0 (default) = never, 1 = for wide N tiles on large problems, 2 = whenever the tile shape allows
+int conv_tc2_cluster_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("IMMB_TC2_CLUSTER");
+    mode = e ? atoi(e) : 0;      // measured on B200: no gain at batch 64 (the weight operand is not the limiter) -> off by default
+  }
+  return mode;
+}
+
 template <int BN, int PASSES>
 static int launch_tc2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
-                      const CUtensorMap& b_lo, const Tc2Params& p, cudaStream_t st) {
+                      const CUtensorMap& b_lo, const Tc2Params& p, bool cluster, cudaStream_t st) {
   using Cfg = Tc2Cfg<BN, PASSES>;
-  auto kern = conv_tc2_kernel<BN, PASSES>;
-  static bool configured = false;
-  if (!configured) {
+  if (!cluster) {
+    auto kern = conv_tc2_kernel<BN, PASSES, 1>;
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+      if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "conv_tc2 smem attr: %s", cudaGetErrorString(e));
+      configured = true;
+    }
+    int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+    kern<<<grid, 192, Cfg::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+    return check_launch("conv_tc2_kernel");
+  }
+  auto kern = conv_tc2_kernel<BN, PASSES, 2>;
+  static bool configured2 = false;
+  if (!configured2) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "conv_tc2 smem attr: %s", cudaGetErrorString(e));
-    configured = true;
+    configured2 = true;
   }
-  int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-  kern<<<grid, 192, Cfg::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, p);
-  return check_launch("conv_tc2_kernel");
+  int pairs = p.total_pairs < kNumSMs / 2 ? p.total_pairs : kNumSMs / 2;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a_hi, a_lo, b_hi, b_lo, p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "conv_tc2 cluster launch: %s", cudaGetErrorString(e));
+  return IMMB_OK;
 }
 
 // act: the tensor the halo boxes are read from ([N,H,W,act_cs], act_c valid channels); wts: [9][ncols_pad][kd]
@@ -297,6 +365,12 @@ int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const flo
   const int bn = tc_pick_bn(ncols);
   p.n_tiles_n = ceil_div(ncols, bn);
   p.total_tiles = p.tiles_w * p.tiles_h * p.n_img * p.n_tiles_n;
+  p.m_tiles = p.tiles_w * p.tiles_h * p.n_img;
+  p.total_pairs = ceil_div(p.m_tiles, 2) * p.n_tiles_n;
+  // cluster mode pays off when the weight slice dominates the operand traffic (wide N tiles) and there is enough work
+  const int cmode = conv_tc2_cluster_mode();
+  const bool cluster = cmode > 0 && bn >= 32 && (bn % 32 == 0 || bn == 96) && (cmode == 2 ? bn >= 32 : bn >= 64) &&
+                       (cmode == 2 || p.m_tiles >= 2 * kNumSMs);
   p.kchunks = ceil_div(kd, 32);
   for (int r = 0; r < 3; ++r)
     for (int s = 0; s < 3; ++s) {
@@ -311,19 +385,20 @@ int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const flo
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
   int rc;
   if ((rc = tc_make_act_map(&a_hi, act_hi, d->N, d->H, d->W, act_c, act_cs, false, 16, 18, 1, 0))) return rc;
-  if ((rc = tc_make_w_map(&b_hi, w_hi, 9, w_rows, kd, bn))) return rc;
+  const int b_box = cluster ? bn / 2 : bn;            // cluster mode: each CTA loads (and multicasts) half the rows
+  if ((rc = tc_make_w_map(&b_hi, w_hi, 9, w_rows, kd, b_box))) return rc;
   a_lo = a_hi; b_lo = b_hi;
   if (passes >= 2) {
     if ((rc = tc_make_act_map(&a_lo, act_lo, d->N, d->H, d->W, act_c, act_cs, false, 16, 18, 1, 0))) return rc;
   }
   if (passes == 3) {
-    if ((rc = tc_make_w_map(&b_lo, w_lo, 9, w_rows, kd, bn))) return rc;
+    if ((rc = tc_make_w_map(&b_lo, w_lo, 9, w_rows, kd, b_box))) return rc;
   }
 #define IMMB_CASE(BN_)                                                                     \
   if (bn == BN_)                                                                           \
-    return passes == 3 ? launch_tc2<BN_, 3>(a_hi, a_lo, b_hi, b_lo, p, st)                 \
-         : passes == 2 ? launch_tc2<BN_, 2>(a_hi, a_lo, b_hi, b_lo, p, st)                 \
-                       : launch_tc2<BN_, 1>(a_hi, a_lo, b_hi, b_lo, p, st);
+    return passes == 3 ? launch_tc2<BN_, 3>(a_hi, a_lo, b_hi, b_lo, p, cluster, st)        \
+         : passes == 2 ? launch_tc2<BN_, 2>(a_hi, a_lo, b_hi, b_lo, p, cluster, st)        \
+                       : launch_tc2<BN_, 1>(a_hi, a_lo, b_hi, b_lo, p, cluster, st);
   IMMB_CASE(16)
   IMMB_CASE(32)
   IMMB_CASE(64)

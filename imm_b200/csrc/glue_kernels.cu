@@ -255,19 +255,21 @@ __device__ __forceinline__ float4 load_split4(const float* hi_p, const float* lo
   return v;
 }
 
-constexpr int kVRedPix = 512;       // pixels per block
+// pixels per block: adaptive (vred_pix): enough blocks to fill the GPU, enough work per block to amortise the
+// cross-row reduction + atomics
 
 // per-channel reduction of NV quantities; f(p, c4, out[NV]) yields float4 per quantity for pixel p, channels c4*4..+3
 template <int NV, class F>
-__device__ __forceinline__ void channel_reduce4(int64_t npix, int C, double* out, int out_stride, F f) {
+__device__ __forceinline__ void channel_reduce4(int64_t npix, int C, double* out, int out_stride, int pix_per_block,
+                                                F f) {
   const int q = C >> 2;                       // channel quads
   const int rows = blockDim.x / q;            // pixel rows handled concurrently by the block
   const int cq = threadIdx.x % q, pr = threadIdx.x / q;
   double acc[NV][4];
 #pragma unroll
   for (int i = 0; i < NV; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0;
-  int64_t p0 = (int64_t)blockIdx.x * kVRedPix;
-  int64_t p1 = p0 + kVRedPix;
+  int64_t p0 = (int64_t)blockIdx.x * pix_per_block;
+  int64_t p1 = p0 + pix_per_block;
   if (p1 > npix) p1 = npix;
   if (pr < rows) {
     // 4 pixels in flight per thread (memory-level parallelism), fp32 partial over the 4, double across iterations
@@ -314,8 +316,8 @@ __device__ __forceinline__ void channel_reduce4(int64_t npix, int C, double* out
   }
 }
 
-__global__ void bn_stats4_kernel(const float* __restrict__ y, int64_t npix, int C, int ycs, double* sums) {
-  channel_reduce4<2>(npix, C, sums, C, [&](int64_t p, int c4, float4* v) {
+__global__ void bn_stats4_kernel(const float* __restrict__ y, int64_t npix, int C, int ycs, double* sums, int ppb) {
+  channel_reduce4<2>(npix, C, sums, C, ppb, [&](int64_t p, int c4, float4* v) {
     float4 t = ld4(y + p * ycs + c4 * 4);
     v[0] = t;
     v[1] = make_float4(t.x * t.x, t.y * t.y, t.z * t.z, t.w * t.w);
@@ -431,10 +433,10 @@ __device__ __forceinline__ void bn_bwd_elem4(const BnBwdArgs& a, const BnBwdRegs
 #undef IMMB_E
 }
 
-__global__ void bn_bwd_reduce4_kernel(BnBwdArgs a, int64_t npix, int C, double* sums) {
+__global__ void bn_bwd_reduce4_kernel(BnBwdArgs a, int64_t npix, int C, double* sums, int ppb) {
   const int c = (threadIdx.x % (C >> 2)) * 4;
   const BnBwdRegs r{ld4(a.scale + c), ld4(a.shift + c), ld4(a.mean + c), ld4(a.invstd + c)};
-  channel_reduce4<2>(npix, C, sums, C, [&](int64_t p, int, float4* v) {
+  channel_reduce4<2>(npix, C, sums, C, ppb, [&](int64_t p, int, float4* v) {
     float4 dz, xh;
     bn_bwd_elem4(a, r, p, c, dz, xh);
     v[0] = dz;
@@ -443,7 +445,8 @@ __global__ void bn_bwd_reduce4_kernel(BnBwdArgs a, int64_t npix, int C, double* 
 }
 
 __global__ void bn_bwd_apply4_kernel(BnBwdArgs a, int64_t npix, int C, const double* __restrict__ sums,
-                                     float* dy_hi, float* dy_lo, float* dgamma, float* dbeta, double* dbias_acc) {
+                                     float* dy_hi, float* dy_lo, float* dgamma, float* dbeta, double* dbias_acc,
+                                     int ppb) {
   const double inv_n = 1.0 / (double)npix;
   if (blockIdx.x == 0 && threadIdx.x < C) {
     dbeta[threadIdx.x] = (float)sums[threadIdx.x];
@@ -455,7 +458,7 @@ __global__ void bn_bwd_apply4_kernel(BnBwdArgs a, int64_t npix, int C, const dou
                                  (float)(sums[c + 3] * inv_n));
   const float4 mdzx = make_float4((float)(sums[C + c] * inv_n), (float)(sums[C + c + 1] * inv_n),
                                   (float)(sums[C + c + 2] * inv_n), (float)(sums[C + c + 3] * inv_n));
-  channel_reduce4<1>(npix, C, dbias_acc, C, [&](int64_t p, int, float4* v) {
+  channel_reduce4<1>(npix, C, dbias_acc, C, ppb, [&](int64_t p, int, float4* v) {
     float4 dz, xh;
     bn_bwd_elem4(a, r, p, c, dz, xh);
     float4 dy;
@@ -1203,7 +1206,14 @@ static inline int ew_grid(int64_t total, int block = 256) {
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 // vectorised per-channel kernels: C a multiple of 4 that divides 256*4 so that a 256-thread block covers whole rows
 static inline bool vec_ok(int C, int cs) { return C % 4 == 0 && cs % 4 == 0 && C <= 1024 && (1024 % C) == 0; }
-static inline int vred_grid(int64_t npix) { return (int)((npix + kVRedPix - 1) / kVRedPix); }
+static inline int vred_pix(int64_t npix) {
+  int64_t ppb = npix / ((int64_t)kNumSMs * 8);
+  ppb = (ppb + 255) / 256 * 256;
+  if (ppb < 256) ppb = 256;
+  if (ppb > 2048) ppb = 2048;
+  return (int)ppb;
+}
+static inline int vred_grid(int64_t npix) { int ppb = vred_pix(npix); return (int)((npix + ppb - 1) / ppb); }
 static inline size_t vred_smem(int nv) { return sizeof(double) * nv * 4 * 256; }
 static inline dim3 red_grid(int64_t npix, int C) {
   return dim3((unsigned)((npix + kRedPixPerBlock - 1) / kRedPixPerBlock), (unsigned)((C + 31) / 32));
@@ -1227,7 +1237,7 @@ extern "C" int immb_split_planes(const float* v, float* hi, float* lo, int64_t n
 extern "C" int immb_bn_stats(const float* y, int64_t npix, int C, int ycs, double* sums, void* stream) {
   IMMB_REQUIRE(y && sums && npix > 0 && C > 0 && ycs >= C, "bn_stats: bad args");
   if (vec_ok(C, ycs) && aligned16(y))
-    bn_stats4_kernel<<<vred_grid(npix), 256, vred_smem(2), ST(stream)>>>(y, npix, C, ycs, sums);
+    bn_stats4_kernel<<<vred_grid(npix), 256, vred_smem(2), ST(stream)>>>(y, npix, C, ycs, sums, vred_pix(npix));
   else
     bn_stats_kernel<<<red_grid(npix, C), dim3(32, kRedRows), 0, ST(stream)>>>(y, npix, C, ycs, sums);
   return check_launch("bn_stats");
@@ -1283,7 +1293,7 @@ extern "C" int immb_bn_bwd_reduce(const float* g, int gcs, const float* y, int y
   IMMB_REQUIRE(g && y && sums && gcs >= C && ycs >= C, "bn_bwd_reduce: bad args");
   if (vec_ok(C, gcs) && ycs % 4 == 0 && aligned16(g) && aligned16(y)) {
     BnBwdArgs a{g, y, scale, shift, mean, invstd, gcs, ycs, relu};
-    bn_bwd_reduce4_kernel<<<vred_grid(npix), 256, vred_smem(2), ST(stream)>>>(a, npix, C, sums);
+    bn_bwd_reduce4_kernel<<<vred_grid(npix), 256, vred_smem(2), ST(stream)>>>(a, npix, C, sums, vred_pix(npix));
   } else {
     bn_bwd_reduce_kernel<<<red_grid(npix, C), dim3(32, kRedRows), 0, ST(stream)>>>(
         g, gcs, y, ycs, npix, C, scale, shift, mean, invstd, relu, sums);
@@ -1300,7 +1310,7 @@ extern "C" int immb_bn_bwd_apply(const float* g, int gcs, const float* y, int yc
       aligned16(dy_lo)) {
     BnBwdArgs a{g, y, scale, shift, mean, invstd, gcs, ycs, relu};
     bn_bwd_apply4_kernel<<<vred_grid(npix), 256, vred_smem(1), ST(stream)>>>(a, npix, C, sums, dy_hi, dy_lo, dgamma,
-                                                                            dbeta, dbias_acc);
+                                                                            dbeta, dbias_acc, vred_pix(npix));
   } else {
     bn_bwd_apply_kernel<<<red_grid(npix, C), dim3(32, kRedRows), 0, ST(stream)>>>(
         g, gcs, y, ycs, npix, C, scale, shift, mean, invstd, relu, sums, dy_hi, dy_lo, dgamma, dbeta, dbias_acc);

@@ -161,6 +161,18 @@ def test_conv_tcgen05_engine(case, precision):
   assert rel_err((yh + yl)[..., :Cout], torch.relu(y_ref)) < tol
 
 
+def test_conv_tc2_cluster_multicast_mode():
+  """IMMB_TC2_CLUSTER=2 forces the 2-CTA-cluster variant of the halo kernel (each CTA TMA-multicasts half of every
+  weight slice into both CTAs' shared memory).  The mode is read once per process, so run a subset in a child."""
+  import os, subprocess, sys
+  env = dict(os.environ, IMMB_TC2_CLUSTER='2')
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  out = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(root, 'tests', 'test_gpu_ops.py'), '-m', 'gpu', '-q',
+                        '-k', 'tcgen05_engine and (case0 or case1 or case5 or case10)', '-p', 'no:cacheprovider'],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, cwd=root, timeout=600)
+  assert out.returncode == 0 and 'passed' in out.stdout and 'failed' not in out.stdout, out.stdout[-1500:]
+
+
 def test_pack_weights_layouts():
   w = torch.randn(3, 3, 5, 7)
   wp_h, wp_l = torch.empty(9, 7, 32, device='cuda'), torch.empty(9, 7, 32, device='cuda')
