@@ -27,7 +27,7 @@ class BaseModel(object):
 
   def _add_cost_summary(self, cost, name):
     """Raw + moving-average cost scalars (base_model.py:52-60); only for the first model instance."""
-    if self.__class__.num_instances == 1 or True:
+    if True:      # the reference only registers summaries for the first instance (num_instances == 1); EMAs are cheap here
       def update(cost=cost, name=name):
         v = float(cost() if callable(cost) else cost)
         self._cost_raw[name] = v
