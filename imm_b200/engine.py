@@ -698,6 +698,7 @@ class IMMEngine(object):
          float(clip_value) if clip_value is not None else 0.0, lr_t, beta1, beta2, eps, st)
     self.repack_weights()
     self.global_step += 1.0
+    self.last_lr = lr
     return lr
 
   def train_step(self, image, future_image, mask=None, clip_value=1.0, lr_multiple=1.0, allreduce=None):

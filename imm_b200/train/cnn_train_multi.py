@@ -121,6 +121,10 @@ def train_loop(opts, graph, loss, train_dataset, training_pl, handle_pl, train_o
     model.load_state_dict(sd, vars_to_restore=vars_to_restore or 'model', ignore_missing_vars=ignore_missing_vars,
                           reset_global_step=reset_global_step if reset_global_step is not False else -1)
   start_step = int(eng.global_step) if eng is not None else -1
+  summary = None
+  if rank == 0 and opts.get('log_dir') and opts.get('n_summary') and not fwd_only and opts.get('summaries', True):
+    from ..utils.summaries import SummaryLogger
+    summary = SummaryLogger(opts['log_dir'])            # tf.summary.FileWriter(opts['log_dir']) (cnn_train_multi.py:436)
   begin = time.time()
   n_done = 0
   for step in range(start_step, num_steps):
@@ -135,6 +139,8 @@ def train_loop(opts, graph, loss, train_dataset, training_pl, handle_pl, train_o
     if rank == 0 and step % log_every == 0:
       print('%s: step %d, loss = %.4f (%.1f examples/sec) %.3f sec/batch'
             % (datetime.now(), step, loss_value, opts['batch_size'] / duration, duration))
+    if summary is not None and step % opts['n_summary'] == 0:            # cnn_train_multi.py:452-457
+      summary.write(model, step, lr=getattr(model.engine, 'last_lr', None))
     if not fwd_only and rank == 0 and step % opts['n_checkpoint'] == 0 and opts.get('log_dir'):
       os.makedirs(opts['log_dir'], exist_ok=True)
       torch.save(model.state_dict(), os.path.join(opts['log_dir'], 'model.ckpt-%d' % step))

@@ -131,3 +131,20 @@ def test_two_rank_gradient_exchange_gloo(tmp_path):
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=240)
   assert out.returncode == 0, out.stdout[-2000:]
   assert out.stdout.count('ok') == 2
+
+
+def test_landmark_colourisation_matches_reference_semantics():
+  """colorize_landmark_maps (imm_model.py:81-91): per-landmark colour, max over landmarks; get_n_colors draws colours
+  in [0.9/1.9, 1] (pastel factor is hard-wired to 0.9 in the reference, utils.py:259-263)."""
+  import random
+  from imm_b200.utils.summaries import colorize_landmark_maps, get_n_colors
+  cols = get_n_colors(5, rnd=random.Random(0))
+  assert len(cols) == 5 and all(0.9 / 1.9 - 1e-9 <= c <= 1.0 for col in cols for c in col)
+  maps = torch.zeros(1, 2, 2, 2)
+  maps[0, 0, 0, 0] = 1.0
+  maps[0, 1, 1, 1] = 0.5
+  maps[0, 0, 1, :] = torch.tensor([0.2, 0.4])
+  out = colorize_landmark_maps(maps, [[1.0, 0.0, 0.5], [0.0, 1.0, 0.5]])
+  assert out.shape == (1, 2, 2, 3)
+  assert out[0, 0, 0].tolist() == [1.0, 0.0, 0.5] and out[0, 1, 1].tolist() == [0.0, 0.5, 0.25]
+  np.testing.assert_allclose(out[0, 0, 1].numpy(), [0.2, 0.4, 0.2], rtol=1e-6)      # max over landmarks per channel

@@ -50,6 +50,7 @@ def test_train_script_runs_checkpoints_and_restores(tmp_path):
   assert out.returncode == 0, out.stdout[-3000:]
   assert 'step -1, loss' in out.stdout and 'step 2, loss' in out.stdout       # global_step starts at -1 (train.py:87-89)
   assert 'Avg. samples per second' in out.stdout
+  assert any(f.startswith('events.out.tfevents') for f in os.listdir(str(tmp_path / 't')))      # train summaries
   ck = tmp_path / 't' / 'model.ckpt-2'
   assert ck.exists()
   sd = torch.load(str(ck), map_location='cpu')
