@@ -71,7 +71,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
   uint64_t* tmem_full = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int tw = blockIdx.x % p.tiles_w;
   const int th = (blockIdx.x / p.tiles_w) % p.tiles_h;
   const int tn = blockIdx.x / (p.tiles_w * p.tiles_h);
@@ -101,8 +101,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
+    {
+      // ===== TMA producer (whole warp runs the loop; one elected lane issues) =====
       for (int kt = 0; kt < num_k; ++kt) {
         const int s = kt % STAGES;
         const uint32_t ph = (kt / STAGES) & 1;
@@ -110,6 +110,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
         const int tap = kt / p.kchunks, kc = kt - tap * p.kchunks;
         const TapEntry t = p.taps[tap];
         uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+        if (elect_one()) {
         mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
         const int c = kc * 32 + t.dc, w = tw * p.TW + t.dw, h = th * p.TH + t.dh, n = tn * p.TN;
         tma_load_5d(st, &mapA_hi, &full[s], c, w, t.hp, h, n);
@@ -117,11 +118,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
         uint8_t* sb = st + Cfg::A_BYTES * Cfg::NPL;
         tma_load_3d(sb, &mapB_hi, &full[s], kc * 32, n_off, t.b_tap);
         if (PASSES == 3) tma_load_3d(sb + Cfg::B_BYTES, &mapB_lo, &full[s], kc * 32, n_off, t.b_tap);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
+    {
+      // ===== MMA issuer (whole warp, uniform values; one elected lane issues) =====
       constexpr uint32_t idesc = idesc_tf32(kTileM, BN, 0, 0);
       for (int kt = 0; kt < num_k; ++kt) {
         const int s = kt % STAGES;
@@ -132,6 +135,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
         const uint32_t a_lo = a_hi + Cfg::A_BYTES;
         const uint32_t b_hi = a_hi + Cfg::A_BYTES * Cfg::NPL;
         const uint32_t b_lo = b_hi + Cfg::B_BYTES;
+        if (elect_one()) {
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {
           const uint32_t ko = k4 * 32;    // 8 tf32 = 32 bytes along K inside the 128-byte swizzle row
@@ -146,8 +150,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
           }
         }
         mma_commit(&empty[s]);            // frees the smem stage once these MMAs have drained
+        if (kt == num_k - 1) mma_commit(tmem_full);
+        }
+        __syncwarp();
       }
-      mma_commit(tmem_full);
     }
   } else {
     // ===== epilogue: warps 2..5; warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
@@ -253,7 +259,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_c
   uint64_t* tmem_full = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   // M tile -> (first tap, channel offset)
   int tap0, ci0;
   if (p.cit == 128) {
@@ -285,7 +291,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_c
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0 && num_k > 0) {
+    if (num_k > 0) {
       for (int kt = 0; kt < num_k; ++kt) {
         const int s = kt % STAGES;
         const uint32_t ph = (kt / STAGES) & 1;
@@ -295,6 +301,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_c
         const int thi = (tile / p.tiles_w) % p.tiles_h;
         const int n = tile / (p.tiles_w * p.tiles_h);
         uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+        if (elect_one()) {
         mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
         // A: 4 boxes of 32 channels (taps beyond the filter are loaded with an out-of-range image index -> zeros)
 #pragma unroll
@@ -315,10 +322,12 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_c
           if (PASSES == 3)
             tma_load_5d(sb + Cfg::B_BYTES + j * 4096, &mapY_lo, &full[s], n_off + j * 32, twi * p.PW, 0, thi * p.PH, n);
         }
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && num_k > 0) {
+    if (num_k > 0) {
       constexpr uint32_t idesc = idesc_tf32(kTileM, BN, 1, 1);
       for (int kt = 0; kt < num_k; ++kt) {
         const int s = kt % STAGES;
@@ -329,6 +338,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_c
         const uint32_t a_lo = a_hi + Cfg::A_BYTES;
         const uint32_t b_hi = a_hi + Cfg::A_BYTES * Cfg::NPL;
         const uint32_t b_lo = b_hi + Cfg::B_BYTES;
+        if (elect_one()) {
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {
           const uint32_t ko = k4 * 1024;     // 8 pixels = 8 rows x 128 B
@@ -345,8 +355,10 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_c
           }
         }
         mma_commit(&empty[s]);
+        if (kt == num_k - 1) mma_commit(tmem_full);
+        }
+        __syncwarp();
       }
-      mma_commit(tmem_full);
     }
   } else if (num_k > 0) {
     const int q = warp & 3;

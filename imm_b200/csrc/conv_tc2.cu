@@ -81,7 +81,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
   uint64_t* t_empty = t_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (uint32_t i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
@@ -120,8 +120,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
   };
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
+    {
+      // ===== TMA producer (whole warp runs the loop; one elected lane issues) =====
       uint32_t ai = 0, bi = 0;                       // running slot counters
       for (int t = tile0; t < n_iter_total; t += tstep) {
         int img, th, tw, n_off;
@@ -131,14 +131,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
           const uint32_t as = ai % Cfg::A_SLOTS, aph = (ai / Cfg::A_SLOTS) & 1;
           mbar_wait(&a_empty[as], aph ^ 1);
           uint8_t* sa = a_base + as * Cfg::A_SLOT;
+          if (elect_one()) {
           mbar_expect_tx(&a_full[as], Cfg::A_SLOT);
           tma_load_5d(sa, &mapA_hi, &a_full[as], kc * 32, tw * 8 - 1, 0, th * 16 - 1, img);
           if (PASSES >= 2) tma_load_5d(sa + Cfg::A_PLANE, &mapA_lo, &a_full[as], kc * 32, tw * 8 - 1, 0, th * 16 - 1, img);
+          }
+          __syncwarp();
           ++ai;
           for (int tap = 0; tap < 9; ++tap) {
             const uint32_t bs = bi % Cfg::B_SLOTS, bph = (bi / Cfg::B_SLOTS) & 1;
             mbar_wait(&b_empty[bs], bph ^ 1);
             uint8_t* sb = b_base + bs * Cfg::B_SLOT;
+            if (elect_one()) {
             mbar_expect_tx(&b_full[bs], Cfg::B_SLOT);
             if (CL == 2) {
               // my half of the rows, into both CTAs
@@ -151,14 +155,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
               tma_load_3d(sb, &mapB_hi, &b_full[bs], kc * 32, n_off, p.taps[tap].b_tap);
               if (PASSES == 3) tma_load_3d(sb + Cfg::B_PLANE, &mapB_lo, &b_full[bs], kc * 32, n_off, p.taps[tap].b_tap);
             }
+            }
+            __syncwarp();
             ++bi;
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
+    {
+      // ===== MMA issuer (whole warp runs the loop with uniform values; one elected lane issues) =====
       constexpr uint32_t idesc = idesc_tf32(128, BN, 0, 0);
       uint32_t ai = 0, bi = 0, ti = 0;
       for (int t = tile0; t < n_iter_total; t += tstep) {
@@ -182,6 +188,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
             // measured on B200: the MMA unit applies the 128B swizzle to the absolute smem address, so a descriptor
             // that starts s rows into the 1024-byte pattern needs base_offset = 0 (setting it to s reads garbage)
             const uint32_t bo = p.bo_mode == 0 ? 0u : (uint32_t)tp.so;
+            if (elect_one()) {
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
               const uint32_t ko = k4 * 32;
@@ -199,12 +206,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
             }
             if (CL == 2) mma_commit_mc(&b_empty[bs], (uint16_t)3);
             else mma_commit(&b_empty[bs]);
+            if (tap == 8) mma_commit(&a_empty[as]);
+            if (tap == 8 && kc == p.kchunks - 1) mma_commit(&t_full[acc]);
+            }
+            __syncwarp();
             ++bi;
           }
-          mma_commit(&a_empty[as]);
           ++ai;
         }
-        mma_commit(&t_full[acc]);
         ++ti;
       }
     }
@@ -449,7 +458,7 @@ conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_
   uint64_t* tmem_full = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int ci0 = blockIdx.x * 32;
   const int n_off = blockIdx.y * BN;
   const int t_begin = blockIdx.z * p.tiles_per_split;
@@ -469,7 +478,7 @@ conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       for (int kt = 0; kt < num_k; ++kt) {
         const int s = kt % STAGES;
         const uint32_t ph = (kt / STAGES) & 1;
@@ -479,6 +488,7 @@ conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_
         const int thi = (tile / p.tiles_w) % p.tiles_h;
         const int n = tile / (p.tiles_w * p.tiles_h);
         uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+        if (elect_one()) {
         mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
         tma_load_5d(st, &mapX_hi, &full[s], ci0, twi * 8 - 1, 0, thi * 4 - 1, n);
         if (PASSES == 3) tma_load_5d(st + Cfg::A_PLANE, &mapX_lo, &full[s], ci0, twi * 8 - 1, 0, thi * 4 - 1, n);
@@ -488,10 +498,12 @@ conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_
           tma_load_5d(sb + j * 4096, &mapY_hi, &full[s], n_off + j * 32, twi * 8, 0, thi * 4, n);
           if (PASSES == 3) tma_load_5d(sb + Cfg::B_PLANE + j * 4096, &mapY_lo, &full[s], n_off + j * 32, twi * 8, 0, thi * 4, n);
         }
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && num_k > 0) {
+    if (num_k > 0) {
       constexpr uint32_t idesc = idesc_tf32(128, BN, 1, 1);
       for (int kt = 0; kt < num_k; ++kt) {
         const int s = kt % STAGES;
@@ -502,6 +514,7 @@ conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_
         const uint32_t a_lo = a_hi + Cfg::A_PLANE;
         const uint32_t b_hi = a_hi + Cfg::A_PLANE * Cfg::NPL;
         const uint32_t b_lo = b_hi + Cfg::B_PLANE;
+        if (elect_one()) {
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
           const uint32_t tmem_d = tmem_base + (uint32_t)(r * BN);
@@ -521,8 +534,10 @@ conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_
           }
         }
         mma_commit(&empty[s]);
+        if (kt == num_k - 1) mma_commit(tmem_full);
+        }
+        __syncwarp();
       }
-      mma_commit(tmem_full);
     }
   } else if (num_k > 0) {
     const int q = warp & 3;

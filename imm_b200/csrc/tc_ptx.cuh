@@ -11,6 +11,23 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a fully converged warp.  The tcgen05 / TMA issue loops are executed by ALL lanes of their warp with
+// warp-uniform values and only the instruction itself is predicated on this: descriptors then live in uniform
+// registers.  (Issuing from inside an `if (lane == 0)` branch makes ptxas wrap every UTCHMMA / UTMALDG in an
+// ELECT + 5x R2UR.BROADCAST loop, ~100 cycles per instruction: the issue thread, not the tensor pipe, set the pace.)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // ---- mbarrier -----------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
