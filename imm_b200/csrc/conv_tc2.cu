@@ -51,8 +51,13 @@ struct Tc2Cfg {
   static constexpr uint32_t B_SLOT = B_PLANE * NPLB;
   static constexpr uint32_t B_SLOTS = (B_SLOT <= 16384) ? 4 : ((A_SLOTS * A_SLOT + 3 * B_SLOT <= 225000) ? 3 : 2);
   static constexpr uint32_t SMEM_BYTES = A_SLOTS * A_SLOT + B_SLOTS * B_SLOT + 1024 + 256;
-  static constexpr int ACC_COLS = (BN + 31) / 32 * 32;
-  static constexpr int TMEM_COLS = 2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : 256);
+  // 3-pass: ONE MMA of N = 2*BN against the contiguous [w_hi ; w_lo] rows produces hi*hi in columns [0,BN) and
+  // hi*lo in [BN,2BN) (the A_hi tile is read from shared memory once instead of twice); lo*hi (N = BN) accumulates
+  // into [0,BN); the epilogue adds the two column blocks.
+  static constexpr int BNP = (BN + 31) / 32 * 32;
+  static constexpr int ACC_COLS = PASSES == 3 ? 2 * BNP : BNP;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512));
+  static_assert(PASSES != 3 || BN % 32 == 0 || BN == 16, "3-pass N-concatenation needs w_lo to start right after w_hi");
 };
 
 // CL = 2: the CTA pair of a 2-CTA cluster works on two M tiles of the SAME N tile in lockstep; each CTA fetches half
@@ -166,6 +171,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
     {
       // ===== MMA issuer (whole warp runs the loop with uniform values; one elected lane issues) =====
       constexpr uint32_t idesc = idesc_tf32(128, BN, 0, 0);
+      constexpr uint32_t idesc2 = idesc_tf32(128, 2 * BN, 0, 0);      // [w_hi ; w_lo]
       uint32_t ai = 0, bi = 0, ti = 0;
       for (int t = tile0; t < n_iter_total; t += tstep) {
         const uint32_t acc = ti & 1, tph = (ti >> 1) & 1;
@@ -194,14 +200,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
               const uint32_t ko = k4 * 32;
               const uint64_t da_hi = smem_desc_sw128(a_hi + a_off + ko, 16, 2048, 2, bo);
               const uint64_t db_hi = smem_desc_sw128(b_hi + ko, 16, 1024);
-              mma_tf32(tmem_d, da_hi, db_hi, idesc, (kc > 0 || tap > 0 || k4 > 0) ? 1u : 0u);
+              mma_tf32(tmem_d, da_hi, db_hi, PASSES == 3 ? idesc2 : idesc, (kc > 0 || tap > 0 || k4 > 0) ? 1u : 0u);
               if (PASSES >= 2) {
                 const uint64_t da_lo = smem_desc_sw128(a_lo + a_off + ko, 16, 2048, 2, bo);
                 mma_tf32(tmem_d, da_lo, db_hi, idesc, 1u);
-              }
-              if (PASSES == 3) {
-                const uint64_t db_lo = smem_desc_sw128(b_lo + ko, 16, 1024);
-                mma_tf32(tmem_d, da_hi, db_lo, idesc, 1u);
               }
             }
             if (CL == 2) mma_commit_mc(&b_empty[bs], (uint16_t)3);
@@ -236,6 +238,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS + (uint32_t)c0, v);
+        if (PASSES == 3) {
+          float v2[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS + (uint32_t)(BN + c0), v2);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += v2[j];
+        }
         const int col0 = n_off + c0;
         if (col0 >= p.n_cols || !live) continue;
         if (p.bias) {
