@@ -450,7 +450,10 @@ struct Wg2Cfg {
   static constexpr uint32_t B_PLANE = BN * 128;               // BN/32 boxes of 32 px x 128 B
   static constexpr uint32_t STAGE_BYTES = (A_PLANE + B_PLANE) * NPL;
   static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
-  static constexpr int TMEM_COLS = 3 * BN <= 128 ? 128 : (3 * BN <= 256 ? 256 : 512);
+  // 3-pass, BN <= 64: X_hi x [dY_hi | dY_lo] as ONE MMA of N = 2*BN (the lo plane follows the hi plane in the stage)
+  static constexpr bool CONCAT = PASSES == 3 && BN <= 64;
+  static constexpr int ACC = CONCAT ? 2 * BN : BN;            // columns per filter-row accumulator
+  static constexpr int TMEM_COLS = 3 * ACC <= 128 ? 128 : (3 * ACC <= 256 ? 256 : 512);
 };
 
 template <int BN, int PASSES, int STAGES>
@@ -513,6 +516,7 @@ conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_
   } else if (warp == 1) {
     if (num_k > 0) {
       constexpr uint32_t idesc = idesc_tf32(128, BN, 1, 1);
+      constexpr uint32_t idesc2 = idesc_tf32(128, 2 * BN <= 256 ? 2 * BN : BN, 1, 1);
       for (int kt = 0; kt < num_k; ++kt) {
         const int s = kt % STAGES;
         const uint32_t ph = (kt / STAGES) & 1;
@@ -525,18 +529,20 @@ conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_
         if (elect_one()) {
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-          const uint32_t tmem_d = tmem_base + (uint32_t)(r * BN);
+          const uint32_t tmem_d = tmem_base + (uint32_t)(r * Cfg::ACC);
 #pragma unroll
           for (int hl = 0; hl < 4; ++hl) {
             const uint32_t ao = (uint32_t)((hl + r) * 16) * 128u;        // halo row hl+r, column tap s via LBO
             const uint32_t bo_ = (uint32_t)hl * 1024u;                    // dY rows hl*8 .. hl*8+7
             const uint64_t da_hi = smem_desc_sw128(a_hi + ao, 128, 512, 1);
             const uint64_t db_hi = smem_desc_sw128(b_hi + bo_, 4096, 512, 1);
-            mma_tf32(tmem_d, da_hi, db_hi, idesc, (kt > 0 || hl > 0) ? 1u : 0u);
+            mma_tf32(tmem_d, da_hi, db_hi, Cfg::CONCAT ? idesc2 : idesc, (kt > 0 || hl > 0) ? 1u : 0u);
             if (PASSES == 3) {
               const uint64_t da_lo = smem_desc_sw128(a_lo + ao, 128, 512, 1);
-              const uint64_t db_lo = smem_desc_sw128(b_lo + bo_, 4096, 512, 1);
-              mma_tf32(tmem_d, da_hi, db_lo, idesc, 1u);
+              if (!Cfg::CONCAT) {
+                const uint64_t db_lo = smem_desc_sw128(b_lo + bo_, 4096, 512, 1);
+                mma_tf32(tmem_d, da_hi, db_lo, idesc, 1u);
+              }
               mma_tf32(tmem_d, da_lo, db_hi, idesc, 1u);
             }
           }
@@ -560,7 +566,13 @@ conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * BN + c0), v);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * Cfg::ACC + c0), v);
+        if (Cfg::CONCAT) {
+          float v2[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * Cfg::ACC + BN + c0), v2);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += v2[j];
+        }
         if (!row_ok) continue;
         const int col0 = n_off + c0;
         if (col0 >= p.Cout) continue;
