@@ -34,8 +34,13 @@ struct TapEntry {
 struct TcParams {
   int TW, TH, TN;             // tile box in pixels (TW*TH*TN == 128)
   int tiles_w, tiles_h;
-  int n_taps, kchunks;
+  int n_taps, kchunks;        // class 0 (and the only class of forward / stride-1 dgrad launches)
   TapEntry taps[kMaxTaps];
+  // stride-2 dgrad: the 4 output-parity classes run as blockIdx.z of ONE launch; classes 1..3 (<= 2 taps each... <= 4)
+  int n_classes;
+  int n_taps_c[3];
+  TapEntry taps_c[3][4];
+  int out_add_c[3][2];
   float* out_hi;
   float* out_lo;
   const float* bias;
@@ -55,7 +60,9 @@ struct FwdCfg {
   static constexpr uint32_t NPL = PASSES == 3 ? 2 : 1;      // planes per operand
   static constexpr uint32_t STAGE_BYTES = (A_BYTES + B_BYTES) * NPL;
   static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  // 3-pass: A_hi x [w_hi ; w_lo] is ONE MMA of N = 2*BN (hi*lo lands in columns [BN, 2BN), added in the epilogue)
+  static constexpr int ACC = PASSES == 3 ? 2 * ((BN + 31) / 32 * 32) : (BN + 31) / 32 * 32;
+  static constexpr int TMEM_COLS = ACC <= 32 ? 32 : (ACC <= 64 ? 64 : (ACC <= 128 ? 128 : 256));
 };
 
 template <int BN, int PASSES, int STAGES>
@@ -76,7 +83,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
   const int th = (blockIdx.x / p.tiles_w) % p.tiles_h;
   const int tn = blockIdx.x / (p.tiles_w * p.tiles_h);
   const int n_off = blockIdx.y * BN;
-  const int num_k = p.n_taps * p.kchunks;
+  const int cls = blockIdx.z;
+  const int n_taps = cls == 0 ? p.n_taps : p.n_taps_c[cls - 1];
+  const TapEntry* taps = cls == 0 ? p.taps : p.taps_c[cls - 1];
+  const int out_add_h = cls == 0 ? p.out_add_h : p.out_add_c[cls - 1][0];
+  const int out_add_w = cls == 0 ? p.out_add_w : p.out_add_c[cls - 1][1];
+  const int num_k = n_taps * p.kchunks;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -108,7 +120,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
         const uint32_t ph = (kt / STAGES) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         const int tap = kt / p.kchunks, kc = kt - tap * p.kchunks;
-        const TapEntry t = p.taps[tap];
+        const TapEntry t = taps[tap];
         uint8_t* st = smem + s * Cfg::STAGE_BYTES;
         if (elect_one()) {
         mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
@@ -126,6 +138,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
     {
       // ===== MMA issuer (whole warp, uniform values; one elected lane issues) =====
       constexpr uint32_t idesc = idesc_tf32(kTileM, BN, 0, 0);
+      constexpr uint32_t idesc2 = idesc_tf32(kTileM, 2 * BN, 0, 0);      // [w_hi ; w_lo] (contiguous in the stage)
       for (int kt = 0; kt < num_k; ++kt) {
         const int s = kt % STAGES;
         const uint32_t ph = (kt / STAGES) & 1;
@@ -134,18 +147,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
         const uint32_t a_hi = smem_u32(smem + s * Cfg::STAGE_BYTES);
         const uint32_t a_lo = a_hi + Cfg::A_BYTES;
         const uint32_t b_hi = a_hi + Cfg::A_BYTES * Cfg::NPL;
-        const uint32_t b_lo = b_hi + Cfg::B_BYTES;
         if (elect_one()) {
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {
           const uint32_t ko = k4 * 32;    // 8 tf32 = 32 bytes along K inside the 128-byte swizzle row
           const uint64_t da_hi = smem_desc_sw128(a_hi + ko, 16, 1024);
           const uint64_t db_hi = smem_desc_sw128(b_hi + ko, 16, 1024);
-          mma_tf32(tmem_base, da_hi, db_hi, idesc, (kt > 0 || k4 > 0) ? 1u : 0u);
+          mma_tf32(tmem_base, da_hi, db_hi, PASSES == 3 ? idesc2 : idesc, (kt > 0 || k4 > 0) ? 1u : 0u);
           if (PASSES == 3) {
             const uint64_t da_lo = smem_desc_sw128(a_lo + ko, 16, 1024);
-            const uint64_t db_lo = smem_desc_sw128(b_lo + ko, 16, 1024);
-            mma_tf32(tmem_base, da_hi, db_lo, idesc, 1u);
             mma_tf32(tmem_base, da_lo, db_hi, idesc, 1u);
           }
         }
@@ -162,14 +172,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
     const int wl = m % p.TW, hl = (m / p.TW) % p.TH, nl = m / (p.TW * p.TH);
     const int n = tn * p.TN + nl, h = th * p.TH + hl, w = tw * p.TW + wl;
     const bool row_ok = (n < p.N) && (h < p.PH) && (w < p.PW);
-    const size_t pix = ((size_t)n * p.OH + (size_t)(h * p.out_mul + p.out_add_h)) * p.OW +
-                       (size_t)(w * p.out_mul + p.out_add_w);
+    const size_t pix = ((size_t)n * p.OH + (size_t)(h * p.out_mul + out_add_h)) * p.OW +
+                       (size_t)(w * p.out_mul + out_add_w);
     mbar_wait(tmem_full, 0);
     tc_fence_after();
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (PASSES == 3) {
+        float v2[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c0), v2);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += v2[j];
+      }
       if (!row_ok) continue;
       const int col0 = n_off + c0;
       if (col0 >= p.n_cols) continue;
@@ -622,41 +638,44 @@ int conv_tc_dgrad(const immb_conv_desc* d, const float* dy_hi, const float* dy_l
                         dx, nullptr, d->x_cstride, ncols, ncols, st);
   const int bn = pick_bn(ncols);
   const int classes = d->stride == 1 ? 1 : 4;
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.PH = d->H / d->stride; p.PW = d->W / d->stride;
+  if (!pick_tile(p.PH, p.PW, d->N, &p.TW, &p.TH, &p.TN)) return set_error(IMMB_ERR_UNSUPPORTED, "conv_tc_dgrad: tile");
+  p.tiles_w = p.PW / p.TW; p.tiles_h = p.PH / p.TH;
+  p.kchunks = ceil_div(d->y_cstride, 32);
+  p.n_classes = classes;
   for (int cls = 0; cls < classes; ++cls) {
     const int phh = cls >> 1, pww = cls & 1;
-    TcParams p;
-    memset(&p, 0, sizeof(p));
-    p.PH = d->H / d->stride; p.PW = d->W / d->stride;
-    if (!pick_tile(p.PH, p.PW, d->N, &p.TW, &p.TH, &p.TN)) return set_error(IMMB_ERR_UNSUPPORTED, "conv_tc_dgrad: tile");
-    p.tiles_w = p.PW / p.TW; p.tiles_h = p.PH / p.TH;
-    p.kchunks = ceil_div(d->y_cstride, 32);
     int nt = 0;
     for (int r = 0; r < d->kh; ++r)
       for (int s = 0; s < d->kw; ++s) {
         int eh = phh + d->pad_t - r, ew = pww + d->pad_l - s;      // dy index = tile index + e/stride
         if (d->stride == 2 && ((eh & 1) || (ew & 1))) continue;
-        TapEntry& t = p.taps[nt++];
+        if (cls > 0 && nt >= 4) return set_error(IMMB_ERR_UNSUPPORTED, "conv_tc_dgrad: too many taps in a parity class");
+        TapEntry& t = cls == 0 ? p.taps[nt] : p.taps_c[cls - 1][nt];
+        ++nt;
         t.b_tap = r * d->kw + s; t.dc = 0; t.hp = 0;
         t.dh = d->stride == 1 ? eh : floordiv(eh, 2);
         t.dw = d->stride == 1 ? ew : floordiv(ew, 2);
       }
-    p.n_taps = nt;
-    p.out_hi = dx; p.out_lo = nullptr; p.bias = nullptr; p.relu = 0;
-    p.N = d->N; p.OH = d->H; p.OW = d->W; p.ocs = d->x_cstride;
-    p.out_mul = d->stride; p.out_add_h = phh; p.out_add_w = pww; p.n_cols = ncols; p.n_store = ncols;
-    CUtensorMap a_hi, a_lo, b_hi, b_lo;
-    int rc;
-    if ((rc = make_act_map(&a_hi, dy_hi, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, p.TW, p.TH, p.TN))) return rc;
-    if ((rc = make_w_map(&b_hi, wh_hi, d->kh * d->kw, d->cin_pad, d->y_cstride, bn))) return rc;
-    a_lo = a_hi; b_lo = b_hi;
-    if (passes == 3) {
-      if ((rc = make_act_map(&a_lo, dy_lo, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, p.TW, p.TH, p.TN))) return rc;
-      if ((rc = make_w_map(&b_lo, wh_lo, d->kh * d->kw, d->cin_pad, d->y_cstride, bn))) return rc;
-    }
-    dim3 grid(p.tiles_w * p.tiles_h * ceil_div(d->N, p.TN), ceil_div(ncols, bn));
-    if ((rc = dispatch_fwd(bn, passes, a_hi, a_lo, b_hi, b_lo, p, grid, st))) return rc;
+    if (cls == 0) { p.n_taps = nt; p.out_add_h = phh; p.out_add_w = pww; }
+    else { p.n_taps_c[cls - 1] = nt; p.out_add_c[cls - 1][0] = phh; p.out_add_c[cls - 1][1] = pww; }
   }
-  return IMMB_OK;
+  p.out_hi = dx; p.out_lo = nullptr; p.bias = nullptr; p.relu = 0;
+  p.N = d->N; p.OH = d->H; p.OW = d->W; p.ocs = d->x_cstride;
+  p.out_mul = d->stride; p.n_cols = ncols; p.n_store = ncols;
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  int rc;
+  if ((rc = make_act_map(&a_hi, dy_hi, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, p.TW, p.TH, p.TN))) return rc;
+  if ((rc = make_w_map(&b_hi, wh_hi, d->kh * d->kw, d->cin_pad, d->y_cstride, bn))) return rc;
+  a_lo = a_hi; b_lo = b_hi;
+  if (passes == 3) {
+    if ((rc = make_act_map(&a_lo, dy_lo, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, p.TW, p.TH, p.TN))) return rc;
+    if ((rc = make_w_map(&b_lo, wh_lo, d->kh * d->kw, d->cin_pad, d->y_cstride, bn))) return rc;
+  }
+  dim3 grid(p.tiles_w * p.tiles_h * ceil_div(d->N, p.TN), ceil_div(ncols, bn), classes);
+  return dispatch_fwd(bn, passes, a_hi, a_lo, b_hi, b_lo, p, grid, st);
 }
 
 size_t conv_tc_wgrad_workspace(const immb_conv_desc*) { return 0; }
