@@ -38,12 +38,13 @@ _SIGS = {
   'immb_conv2d_wgrad': [_D, _P, _P, _P, _P, _P, _P, _Z, _P],
   'immb_pack_weights': [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
   'immb_split_planes': [_P, _P, _P, _L, _P],
-  'immb_bn_stats': [_P, _L, _I, _I, _P, _P],
+  'immb_bn_scratch_elems': [_L, _I],
+  'immb_bn_stats': [_P, _L, _I, _I, _P, _P, _Z, _P],
   'immb_bn_finalize': [_P, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P],
   'immb_bn_apply': [_P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P],
   'immb_upsample2x_bwd': [_P, _I, _I, _I, _I, _I, _P, _P],
-  'immb_bn_bwd_reduce': [_P, _I, _P, _I, _L, _I, _P, _P, _P, _P, _I, _P, _P],
-  'immb_bn_bwd_apply': [_P, _I, _P, _I, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P],
+  'immb_bn_bwd_reduce': [_P, _I, _P, _I, _L, _I, _P, _P, _P, _P, _I, _P, _P, _Z, _P],
+  'immb_bn_bwd_apply': [_P, _I, _P, _I, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _Z, _P],
   'immb_bias_grad': [_P, _P, _I, _L, _I, _P, _P],
   'immb_cast_d2f': [_P, _P, _L, _P],
   'immb_softargmax_gauss_fwd': [_P, _I, _I, _I, _I, _F, _P, _P, _P, _I, _P, _P, _I, _I, _P],
@@ -66,7 +67,7 @@ _SIGS = {
   'immb_adam_apply': [_P, _P, _P, _P, _L, _P, _P, _P, _I, _P, _F, _P, _F, _F, _F, _F, _F, _P],
   'immb_total_loss': [_P, _P, _P, _I, _P, _P, _P],
 }
-_RESTYPES = {'immb_conv2d_wgrad_workspace': _Z}
+_RESTYPES = {'immb_conv2d_wgrad_workspace': _Z, 'immb_bn_scratch_elems': _Z}
 
 _lib = None
 

@@ -259,9 +259,11 @@ __device__ __forceinline__ float4 load_split4(const float* hi_p, const float* lo
 // cross-row reduction + atomics
 
 // per-channel reduction of NV quantities; f(p, c4, out[NV]) yields float4 per quantity for pixel p, channels c4*4..+3
+// partials != nullptr: block b writes its NV*C partial sums to partials[b*NV*C ...] (combined by reduce_partials_kernel
+// in block order: deterministic, no same-address atomics); else atomicAdd into out.
 template <int NV, class F>
 __device__ __forceinline__ void channel_reduce4(int64_t npix, int C, double* out, int out_stride, int pix_per_block,
-                                                F f) {
+                                                double* partials, F f) {
   const int q = C >> 2;                       // channel quads
   const int rows = blockDim.x / q;            // pixel rows handled concurrently by the block
   const int cq = threadIdx.x % q, pr = threadIdx.x / q;
@@ -311,13 +313,15 @@ __device__ __forceinline__ void channel_reduce4(int64_t npix, int C, double* out
       for (int j = 0; j < 4; ++j) {
         double sacc = 0.0;
         for (int r = 0; r < rows; ++r) sacc += vsm[(i * 4 + j) * blockDim.x + r * q + cq];
-        atomicAdd(out + (size_t)i * out_stride + cq * 4 + j, sacc);
+        if (partials) partials[((size_t)blockIdx.x * NV + i) * C + cq * 4 + j] = sacc;
+        else atomicAdd(out + (size_t)i * out_stride + cq * 4 + j, sacc);
       }
   }
 }
 
-__global__ void bn_stats4_kernel(const float* __restrict__ y, int64_t npix, int C, int ycs, double* sums, int ppb) {
-  channel_reduce4<2>(npix, C, sums, C, ppb, [&](int64_t p, int c4, float4* v) {
+__global__ void bn_stats4_kernel(const float* __restrict__ y, int64_t npix, int C, int ycs, double* sums, int ppb,
+                                 double* partials) {
+  channel_reduce4<2>(npix, C, sums, C, ppb, partials, [&](int64_t p, int c4, float4* v) {
     float4 t = ld4(y + p * ycs + c4 * 4);
     v[0] = t;
     v[1] = make_float4(t.x * t.x, t.y * t.y, t.z * t.z, t.w * t.w);
@@ -433,10 +437,10 @@ __device__ __forceinline__ void bn_bwd_elem4(const BnBwdArgs& a, const BnBwdRegs
 #undef IMMB_E
 }
 
-__global__ void bn_bwd_reduce4_kernel(BnBwdArgs a, int64_t npix, int C, double* sums, int ppb) {
+__global__ void bn_bwd_reduce4_kernel(BnBwdArgs a, int64_t npix, int C, double* sums, int ppb, double* partials) {
   const int c = (threadIdx.x % (C >> 2)) * 4;
   const BnBwdRegs r{ld4(a.scale + c), ld4(a.shift + c), ld4(a.mean + c), ld4(a.invstd + c)};
-  channel_reduce4<2>(npix, C, sums, C, ppb, [&](int64_t p, int, float4* v) {
+  channel_reduce4<2>(npix, C, sums, C, ppb, partials, [&](int64_t p, int, float4* v) {
     float4 dz, xh;
     bn_bwd_elem4(a, r, p, c, dz, xh);
     v[0] = dz;
@@ -446,7 +450,7 @@ __global__ void bn_bwd_reduce4_kernel(BnBwdArgs a, int64_t npix, int C, double* 
 
 __global__ void bn_bwd_apply4_kernel(BnBwdArgs a, int64_t npix, int C, const double* __restrict__ sums,
                                      float* dy_hi, float* dy_lo, float* dgamma, float* dbeta, double* dbias_acc,
-                                     int ppb) {
+                                     int ppb, double* partials) {
   const double inv_n = 1.0 / (double)npix;
   if (blockIdx.x == 0 && threadIdx.x < C) {
     dbeta[threadIdx.x] = (float)sums[threadIdx.x];
@@ -458,7 +462,7 @@ __global__ void bn_bwd_apply4_kernel(BnBwdArgs a, int64_t npix, int C, const dou
                                  (float)(sums[c + 3] * inv_n));
   const float4 mdzx = make_float4((float)(sums[C + c] * inv_n), (float)(sums[C + c + 1] * inv_n),
                                   (float)(sums[C + c + 2] * inv_n), (float)(sums[C + c + 3] * inv_n));
-  channel_reduce4<1>(npix, C, dbias_acc, C, ppb, [&](int64_t p, int, float4* v) {
+  channel_reduce4<1>(npix, C, dbias_acc, C, ppb, partials, [&](int64_t p, int, float4* v) {
     float4 dz, xh;
     bn_bwd_elem4(a, r, p, c, dz, xh);
     float4 dy;
@@ -469,6 +473,31 @@ __global__ void bn_bwd_apply4_kernel(BnBwdArgs a, int64_t npix, int C, const dou
     store_split4(dy_hi, dy_lo, (size_t)(p * C + c), dy);
     v[0] = dy;
   });
+}
+
+// out[v] += sum_b partials[b*nvals + v] in a fixed (deterministic) order: 32 partial-block lanes per value (strided
+// over b), then a fixed-order combine through shared memory.  block = (32 values, 32 lanes).
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const double* __restrict__ partials, int nblocks, int nvals,
+                                                                double* out) {
+  __shared__ double sm[32][33];
+  const int v = blockIdx.x * 32 + threadIdx.x;
+  double s0 = 0.0, s1 = 0.0;
+  if (v < nvals) {
+    int b = threadIdx.y;
+    for (; b + 32 < nblocks; b += 64) {
+      s0 += partials[(size_t)b * nvals + v];
+      s1 += partials[(size_t)(b + 32) * nvals + v];
+    }
+    if (b < nblocks) s0 += partials[(size_t)b * nvals + v];
+  }
+  sm[threadIdx.y][threadIdx.x] = s0 + s1;
+  __syncthreads();
+  if (threadIdx.y == 0 && v < nvals) {
+    double t = 0.0;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) t += sm[r][threadIdx.x];
+    out[v] += t;
+  }
 }
 
 __global__ void split_planes4_kernel(const float* __restrict__ v, float* hi, float* lo, int64_t n4) {
@@ -1206,14 +1235,27 @@ static inline int ew_grid(int64_t total, int block = 256) {
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 // vectorised per-channel kernels: C a multiple of 4 that divides 256*4 so that a 256-thread block covers whole rows
 static inline bool vec_ok(int C, int cs) { return C % 4 == 0 && cs % 4 == 0 && C <= 1024 && (1024 % C) == 0; }
-static inline int vred_pix(int64_t npix) {
-  int64_t ppb = npix / ((int64_t)kNumSMs * 8);
-  ppb = (ppb + 255) / 256 * 256;
-  if (ppb < 256) ppb = 256;
-  if (ppb > 2048) ppb = 2048;
+// pixels per block of the vectorised per-channel reductions.  With a scratch buffer (two-level reduction, no atomics)
+// small tensors get ~4 blocks per SM; without it blocks stay large because every block ends in 2*C same-address atomics.
+static inline int vred_pix(int64_t npix, int C, bool two_level) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("IMMB_VRED_PIX"); forced = e ? atoi(e) : 0; }
+  if (forced > 0) return forced;
+  if (!two_level) {
+    int64_t ppb = npix / ((int64_t)kNumSMs * 8);
+    ppb = (ppb + 255) / 256 * 256;
+    if (ppb < 256) ppb = 256;
+    if (ppb > 2048) ppb = 2048;
+    return (int)ppb;
+  }
+  const int64_t unit = (int64_t)(1024 / C) * 4;          // pixel rows per block (256 threads / (C/4) quads) x 4 in flight
+  int64_t ppb = npix / ((int64_t)kNumSMs * 6);
+  ppb = ppb / unit * unit;
+  if (ppb < unit) ppb = unit;
+  if (ppb > 1024) ppb = 1024 / unit * unit;
   return (int)ppb;
 }
-static inline int vred_grid(int64_t npix) { int ppb = vred_pix(npix); return (int)((npix + ppb - 1) / ppb); }
+static inline int vred_grid(int64_t npix, int ppb) { return (int)((npix + ppb - 1) / ppb); }
 static inline size_t vred_smem(int nv) { return sizeof(double) * nv * 4 * 256; }
 static inline dim3 red_grid(int64_t npix, int C) {
   return dim3((unsigned)((npix + kRedPixPerBlock - 1) / kRedPixPerBlock), (unsigned)((C + 31) / 32));
@@ -1234,12 +1276,30 @@ extern "C" int immb_split_planes(const float* v, float* hi, float* lo, int64_t n
   return check_launch("split_planes");
 }
 
-extern "C" int immb_bn_stats(const float* y, int64_t npix, int C, int ycs, double* sums, void* stream) {
+extern "C" size_t immb_bn_scratch_elems(int64_t npix, int C) {
+  if (npix <= 0 || C <= 0 || !vec_ok(C, C)) return 0;
+  int ppb = vred_pix(npix, C, true);
+  return (size_t)vred_grid(npix, ppb) * 2 * (size_t)C;
+}
+
+// launches the second level of a two-level reduction
+static int launch_reduce_partials(const double* partials, int nblocks, int nvals, double* out, cudaStream_t st) {
+  reduce_partials_kernel<<<ceil_div(nvals, 32), dim3(32, 32), 0, st>>>(partials, nblocks, nvals, out);
+  return check_launch("reduce_partials");
+}
+
+extern "C" int immb_bn_stats(const float* y, int64_t npix, int C, int ycs, double* sums, double* scratch,
+                             size_t scratch_elems, void* stream) {
   IMMB_REQUIRE(y && sums && npix > 0 && C > 0 && ycs >= C, "bn_stats: bad args");
-  if (vec_ok(C, ycs) && aligned16(y))
-    bn_stats4_kernel<<<vred_grid(npix), 256, vred_smem(2), ST(stream)>>>(y, npix, C, ycs, sums, vred_pix(npix));
-  else
-    bn_stats_kernel<<<red_grid(npix, C), dim3(32, kRedRows), 0, ST(stream)>>>(y, npix, C, ycs, sums);
+  if (vec_ok(C, ycs) && aligned16(y)) {
+    const bool two = scratch && scratch_elems >= immb_bn_scratch_elems(npix, C);
+    const int ppb = vred_pix(npix, C, two), grid = vred_grid(npix, ppb);
+    bn_stats4_kernel<<<grid, 256, vred_smem(2), ST(stream)>>>(y, npix, C, ycs, sums, ppb, two ? scratch : nullptr);
+    int rc = check_launch("bn_stats");
+    if (rc || !two) return rc;
+    return launch_reduce_partials(scratch, grid, 2 * C, sums, ST(stream));
+  }
+  bn_stats_kernel<<<red_grid(npix, C), dim3(32, kRedRows), 0, ST(stream)>>>(y, npix, C, ycs, sums);
   return check_launch("bn_stats");
 }
 
@@ -1289,11 +1349,17 @@ extern "C" int immb_upsample2x_bwd(const float* g_up, int N, int H, int W, int C
 
 extern "C" int immb_bn_bwd_reduce(const float* g, int gcs, const float* y, int ycs, int64_t npix, int C,
                                   const float* scale, const float* shift, const float* mean,
-                                  const float* invstd, int relu, double* sums, void* stream) {
+                                  const float* invstd, int relu, double* sums, double* scratch,
+                                  size_t scratch_elems, void* stream) {
   IMMB_REQUIRE(g && y && sums && gcs >= C && ycs >= C, "bn_bwd_reduce: bad args");
   if (vec_ok(C, gcs) && ycs % 4 == 0 && aligned16(g) && aligned16(y)) {
     BnBwdArgs a{g, y, scale, shift, mean, invstd, gcs, ycs, relu};
-    bn_bwd_reduce4_kernel<<<vred_grid(npix), 256, vred_smem(2), ST(stream)>>>(a, npix, C, sums, vred_pix(npix));
+    const bool two = scratch && scratch_elems >= immb_bn_scratch_elems(npix, C);
+    const int ppb = vred_pix(npix, C, two), grid = vred_grid(npix, ppb);
+    bn_bwd_reduce4_kernel<<<grid, 256, vred_smem(2), ST(stream)>>>(a, npix, C, sums, ppb, two ? scratch : nullptr);
+    int rc = check_launch("bn_bwd_reduce");
+    if (rc || !two) return rc;
+    return launch_reduce_partials(scratch, grid, 2 * C, sums, ST(stream));
   } else {
     bn_bwd_reduce_kernel<<<red_grid(npix, C), dim3(32, kRedRows), 0, ST(stream)>>>(
         g, gcs, y, ycs, npix, C, scale, shift, mean, invstd, relu, sums);
@@ -1304,13 +1370,19 @@ extern "C" int immb_bn_bwd_reduce(const float* g, int gcs, const float* y, int y
 extern "C" int immb_bn_bwd_apply(const float* g, int gcs, const float* y, int ycs, int64_t npix, int C,
                                  const float* scale, const float* shift, const float* mean,
                                  const float* invstd, int relu, const double* sums, float* dy_hi,
-                                 float* dy_lo, float* dgamma, float* dbeta, double* dbias_acc, void* stream) {
+                                 float* dy_lo, float* dgamma, float* dbeta, double* dbias_acc, double* scratch,
+                                 size_t scratch_elems, void* stream) {
   IMMB_REQUIRE(g && y && sums && dy_hi && dgamma && dbeta && dbias_acc, "bn_bwd_apply: bad args");
   if (vec_ok(C, gcs) && ycs % 4 == 0 && C <= 256 && aligned16(g) && aligned16(y) && aligned16(dy_hi) &&
       aligned16(dy_lo)) {
     BnBwdArgs a{g, y, scale, shift, mean, invstd, gcs, ycs, relu};
-    bn_bwd_apply4_kernel<<<vred_grid(npix), 256, vred_smem(1), ST(stream)>>>(a, npix, C, sums, dy_hi, dy_lo, dgamma,
-                                                                            dbeta, dbias_acc, vred_pix(npix));
+    const bool two = scratch && scratch_elems >= immb_bn_scratch_elems(npix, C);
+    const int ppb = vred_pix(npix, C, two), grid = vred_grid(npix, ppb);
+    bn_bwd_apply4_kernel<<<grid, 256, vred_smem(1), ST(stream)>>>(a, npix, C, sums, dy_hi, dy_lo, dgamma, dbeta,
+                                                                  dbias_acc, ppb, two ? scratch : nullptr);
+    int rc = check_launch("bn_bwd_apply");
+    if (rc || !two) return rc;
+    return launch_reduce_partials(scratch, grid, C, dbias_acc, ST(stream));
   } else {
     bn_bwd_apply_kernel<<<red_grid(npix, C), dim3(32, kRedRows), 0, ST(stream)>>>(
         g, gcs, y, ycs, npix, C, scale, shift, mean, invstd, relu, sums, dy_hi, dy_lo, dgamma, dbeta, dbias_acc);

@@ -382,6 +382,9 @@ class IMMEngine(object):
     self.pcs = self.ren_layers[-1].ycs      # channel stride of the renderer output / its gradient
     self.pred_dy = Planes.alloc((B, R, R, self.pcs), dev, zero=True)
     self.workspace = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+    # scratch of the two-level (deterministic, atomic-free) BN reductions
+    n_scr = max([int(call('immb_bn_scratch_elems', L.N * L.Ho * L.Wo, L.cout)) for L in self.layers.values() if L.bn] + [16])
+    self.bn_scratch = torch.empty(n_scr, dtype=torch.float64, device=dev)
 
   # ------------------------------------------------------------------------------------------------
   # parameters
@@ -478,7 +481,7 @@ class IMMEngine(object):
       return None
     npix = L.N * L.Ho * L.Wo
     if training:
-      call('immb_bn_stats', L.y, npix, L.cout, L.ycs, L.sums, st)
+      call('immb_bn_stats', L.y, npix, L.cout, L.ycs, L.sums, self.bn_scratch, self.bn_scratch.numel(), st)
     call('immb_bn_finalize', L.sums, npix, L.cout, L.gamma, L.beta, L.mm, L.mv, 1 if training else 0,
          L.scale, L.shift, L.mean, L.invstd, st)
     call('immb_bn_apply', L.y, L.N, L.Ho, L.Wo, L.cout, L.ycs, L.scale, L.shift, 1 if L.relu else 0,
@@ -586,10 +589,11 @@ class IMMEngine(object):
         call('immb_upsample2x_bwd', g, L.N, L.Ho, L.Wo, L.cout, gcs, L.g_low, st)
         g, gcs = L.g_low, L.cout
       relu = 1 if L.relu else 0
+      sc = self.bn_scratch
       call('immb_bn_bwd_reduce', g, gcs, L.y, L.cout, npix, L.cout, L.scale, L.shift, L.mean, L.invstd, relu,
-           L.bsums, st)
+           L.bsums, sc, sc.numel(), st)
       call('immb_bn_bwd_apply', g, gcs, L.y, L.cout, npix, L.cout, L.scale, L.shift, L.mean, L.invstd, relu,
-           L.bsums, L.dy.hi, L.dy.lo, L.dgamma, L.dbeta, L.dbias_acc, st)
+           L.bsums, L.dy.hi, L.dy.lo, L.dgamma, L.dbeta, L.dbias_acc, sc, sc.numel(), st)
       dy = L.dy
     else:
       dy = g if isinstance(g, Planes) else None

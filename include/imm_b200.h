@@ -116,8 +116,13 @@ int immb_pack_weights_rowwin(const float* w, int Cout, float* wp_hi, float* wp_l
 int immb_split_planes(const float* v, float* hi, float* lo, int64_t n, void* stream);
 
 /* ---- batch norm: nn_utils.py:201 tf.layers.batch_normalization(training=..., fused=True) ---------- */
-/* sums[2*C] (double, zeroed by the caller): sum(y), sum(y^2) per channel over npix pixels */
-int immb_bn_stats(const float* y, int64_t npix, int C, int y_cstride, double* sums, void* stream);
+/* sums[2*C] (double, zeroed by the caller): sum(y), sum(y^2) per channel over npix pixels.
+ * scratch (optional, caller-owned, scratch_elems doubles): when large enough (immb_bn_scratch_elems) the per-block
+ * partial sums are written there and combined by a second tiny kernel in a fixed order -- deterministic and free of
+ * same-address atomics; otherwise (NULL / too small) the blocks atomically add into sums. */
+size_t immb_bn_scratch_elems(int64_t npix, int C);
+int immb_bn_stats(const float* y, int64_t npix, int C, int y_cstride, double* sums, double* scratch,
+                  size_t scratch_elems, void* stream);
 /* training!=0: batch mean / biased var from sums; moving_mean/var updated in place (momentum .99, Bessel);
  * training==0: moving stats.  Outputs: scale = gamma*rsqrt(var+1e-3), shift = beta-mean*scale, mean, invstd. */
 int immb_bn_finalize(const double* sums, int64_t count, int C, const float* gamma, const float* beta,
@@ -134,13 +139,13 @@ int immb_upsample2x_bwd(const float* g_up, int N, int H, int W, int C, int gup_c
 /* sums[2*C] (double, zeroed): sum(dz), sum(dz*xhat) with dz = g * (relu ? (y*scale+shift > 0) : 1) */
 int immb_bn_bwd_reduce(const float* g, int g_cstride, const float* y, int y_cstride, int64_t npix, int C,
                        const float* scale, const float* shift, const float* mean, const float* invstd,
-                       int relu, double* sums, void* stream);
+                       int relu, double* sums, double* scratch, size_t scratch_elems, void* stream);
 /* dy = scale*(dz - mean(dz) - xhat*mean(dz*xhat)) as split planes; dgamma = sum(dz*xhat), dbeta = sum(dz),
  * dbias = sum(dy) (double accumulators dbias_acc[C], zeroed by the caller; finalised by immb_cast_d2f) */
 int immb_bn_bwd_apply(const float* g, int g_cstride, const float* y, int y_cstride, int64_t npix, int C,
                       const float* scale, const float* shift, const float* mean, const float* invstd,
                       int relu, const double* sums, float* dy_hi, float* dy_lo, float* dgamma, float* dbeta,
-                      double* dbias_acc, void* stream);
+                      double* dbias_acc, double* scratch, size_t scratch_elems, void* stream);
 /* column sums: acc[C] (double, zeroed) += sum over pixels of g[:, c] */
 int immb_bias_grad(const float* g_hi, const float* g_lo, int g_cstride, int64_t npix, int C, double* acc,
                    void* stream);

@@ -208,7 +208,9 @@ def test_bn_train_fwd_bwd(shape, up2x):
   mm, mv = mm0.to(dev), mv0.to(dev)
   scale, shift, mean, invstd = (torch.empty(C, device=dev) for _ in range(4))
   npix = N * H * W
-  call('immb_bn_stats', yc, npix, C, C, sums, ST())
+  scr = torch.empty(int(call('immb_bn_scratch_elems', npix, C)) if up2x else 0, dtype=torch.float64, device=dev)   # both paths
+  scr_p = scr if scr.numel() else None
+  call('immb_bn_stats', yc, npix, C, C, sums, scr_p, scr.numel(), ST())
   call('immb_bn_finalize', sums, npix, C, gamma.to(dev), beta.to(dev), mm, mv, 1, scale, shift, mean, invstd, ST())
   s = 2 if up2x else 1
   ocs = C + 8       # write into a wider (concat-style) buffer
@@ -228,8 +230,8 @@ def test_bn_train_fwd_bwd(shape, up2x):
   dbacc = torch.zeros(C, dtype=torch.float64, device=dev)
   dyh, dyl = torch.empty(N, H, W, C, device=dev), torch.empty(N, H, W, C, device=dev)
   dg, db_ = torch.empty(C, device=dev), torch.empty(C, device=dev)
-  call('immb_bn_bwd_reduce', gdev, C, yc, C, npix, C, scale, shift, mean, invstd, 1, bs, ST())
-  call('immb_bn_bwd_apply', gdev, C, yc, C, npix, C, scale, shift, mean, invstd, 1, bs, dyh, dyl, dg, db_, dbacc, ST())
+  call('immb_bn_bwd_reduce', gdev, C, yc, C, npix, C, scale, shift, mean, invstd, 1, bs, scr_p, scr.numel(), ST())
+  call('immb_bn_bwd_apply', gdev, C, yc, C, npix, C, scale, shift, mean, invstd, 1, bs, dyh, dyl, dg, db_, dbacc, scr_p, scr.numel(), ST())
   assert rel_err(dyh + dyl, yd.grad) < 1e-4
   assert rel_err(dg, gd.grad) < 1e-4 and rel_err(db_, bd.grad) < 1e-4
   assert float(dbacc.abs().max()) < 1e-3 * float(yd.grad.abs().sum())     # sum(dy) is analytically 0
