@@ -66,8 +66,9 @@ _SIGS = {
   'immb_adam_norms': [_P, _P, _L, _P, _P, _P, _I, _P, _F, _P, _P, _P],
   'immb_adam_apply': [_P, _P, _P, _P, _L, _P, _P, _P, _I, _P, _F, _P, _F, _F, _F, _F, _F, _P],
   'immb_total_loss': [_P, _P, _P, _I, _P, _P, _P],
+  'immb_crc32c': [_P, _Z, ctypes.c_uint32],
 }
-_RESTYPES = {'immb_conv2d_wgrad_workspace': _Z, 'immb_bn_scratch_elems': _Z}
+_RESTYPES = {'immb_conv2d_wgrad_workspace': _Z, 'immb_bn_scratch_elems': _Z, 'immb_crc32c': ctypes.c_uint32}
 
 _lib = None
 

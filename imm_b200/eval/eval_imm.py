@@ -31,12 +31,11 @@ def evaluate(dataset_instance, net, net_config, net_file, training_opts, batch_s
     start_time = time.time()
     if not restored:
       net_instance.build(inputs, False, output_tensors=True, build_loss=False)      # instantiates the engine
-      if not os.path.exists(ckpt):
+      if not (os.path.exists(ckpt) or os.path.exists(ckpt + '.index')):               # eval_imm.py:81
         raise Exception('model file does not exist at: ' + ckpt)                     # eval_imm.py:94-95
       print('RESTORING MODEL from: ' + ckpt)
-      sd = torch.load(ckpt, map_location='cpu')
       # every global variable present in the checkpoint is restored (eval_imm.py:81-94)
-      net_instance.load_state_dict(sd, vars_to_restore='all', ignore_missing_vars=True)
+      net_instance.restore_checkpoint(ckpt, vars_to_restore='all', ignore_missing_vars=True)
       restored = True
     _, loss, _, tensors = net_instance.build(inputs, False, output_tensors=True, build_loss=eval_loss)
     tensors.update(net_instance.get_collection('tensors'))

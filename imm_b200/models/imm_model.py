@@ -140,14 +140,43 @@ class IMMModel(BaseModel):
         sd[k + '/Adam_1'] = eng.adam_v[k].detach().cpu().clone()
     return sd
 
-  def load_state_dict(self, sd, vars_to_restore='model', ignore_missing_vars=False, reset_global_step=-1):
+  def save_checkpoint(self, prefix, include_optimizer=True):
+    """tf.train.Saver(tf.global_variables()).save (cnn_train_multi.py:439,511-513): writes `<prefix>.index` and
+    `<prefix>.data-00000-of-00001` in TensorFlow's TensorBundle format (imm_b200/utils/tf_checkpoint.py), variables
+    under the reference's names, float32, HWIO weights.  `__adam_t` is not a TF variable and is not written: the Adam
+    step count is recovered from `beta1_power` on restore."""
+    from ..utils import tf_checkpoint
+    sd = self.state_dict(include_optimizer)
+    sd.pop('__adam_t', None)
+    return tf_checkpoint.write_checkpoint(prefix, {k: v.numpy().astype('float32') for k, v in sd.items()})
+
+  def restore_checkpoint(self, fname, **kwargs):
+    """tf.train.Saver(var_list).restore(session, fname) (cnn_train_multi.py:404-433): fname is a TensorBundle prefix
+    (`model.ckpt-N`, with `.index` next to it) or a legacy torch.save file of state_dict()."""
+    import os
+    from ..utils import tf_checkpoint
+    if os.path.exists(fname + '.index'):
+      sd = {k: torch.from_numpy(v) for k, v in tf_checkpoint.CheckpointReader(fname).read_all().items()}
+    elif os.path.exists(fname):
+      sd = torch.load(fname, map_location='cpu')
+    else:
+      raise IOError('model file does not exist at: ' + fname)
+    self.load_state_dict(sd, **kwargs)
+    return sd
+
+  def load_state_dict(self, sd, vars_to_restore='model', ignore_missing_vars=False, reset_global_step=-1,
+                      exclude_vars=None):
     """cnn_train_multi.py:404-433 semantics: 'model' = MODEL_VARIABLES (w, b, *_agg, global_step -- NOT the
     tf.layers BN variables), 'all' = every global variable incl. BN and Adam slots (--restore-optim)."""
     eng = self.engine
     model_vars = [k for k in eng.params if k.endswith('/w') or k.endswith('/b')]
     model_vars += [k for k in eng.buffers if k.endswith('_agg')]
     all_vars = list(eng.params.keys()) + list(eng.buffers.keys())
-    names = all_vars if vars_to_restore == 'all' else model_vars
+    names = list(all_vars if vars_to_restore == 'all' else model_vars)
+    for ex in (exclude_vars or []):        # cnn_train_multi.py:425-430: drops the FIRST variable whose name contains ex
+      hit = [i for i, n in enumerate(names) if ex in n]
+      if hit:
+        names.pop(hit[0])
     missing = [k for k in names if k not in sd]
     if missing and not ignore_missing_vars:
       raise KeyError('variables missing from the checkpoint: %s' % missing[:5])
@@ -159,6 +188,15 @@ class IMMModel(BaseModel):
       adam_v = {k: sd[k + '/Adam_1'] for k in eng.params if k + '/Adam_1' in sd}
       if '__adam_t' in sd:
         eng.adam_t = int(sd['__adam_t'])
+      elif 'beta1_power' in sd:       # TF keeps beta1^(t+1) (AdamOptimizer._finish); t = steps applied so far
+        import math
+        b1p, b2p = float(sd['beta1_power']), float(sd.get('beta2_power', 0.0))
+        if b1p > 1e-30:
+          eng.adam_t = max(int(round(math.log(b1p) / math.log(0.9))) - 1, 0)
+        elif b2p > 1e-30:
+          eng.adam_t = max(int(round(math.log(b2p) / math.log(0.999))) - 1, 0)
+        else:                         # both powers underflowed in fp32 (> ~87k steps): the bias correction is 1 anyway
+          eng.adam_t = max(int(float(sd.get('global_step', 0))) + 1, 100000)
     eng.load_state(params, buffers, adam_m, adam_v)
     if reset_global_step >= 0:
       eng.global_step = float(reset_global_step)

@@ -12,6 +12,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from ..utils import tf_checkpoint
+
 
 class AdamOptimizer(object):
   """tf.train.AdamOptimizer(lr, name='Adam') stand-in (scripts/train.py:98): holds the hyper-parameters; the
@@ -113,13 +115,14 @@ def train_loop(opts, graph, loss, train_dataset, training_pl, handle_pl, train_o
                ignore_missing_vars=False, reset_global_step=False, vars_to_restore=None, exclude_vars=None,
                fwd_only=False, allow_growth=False, model=None, log_every=1):
   """cnn_train_multi.py:371-516: restore, step loop with NaN guard and examples/sec logging, periodic checkpoints
-  `<logdir>/model.ckpt-<step>` holding tensors keyed by the reference's TF variable names."""
+  `<logdir>/model.ckpt-<step>.{index,data-00000-of-00001}` (TensorFlow TensorBundle format, the reference's variable names)."""
   rank = world_info()[0]
   eng = model.engine
-  if checkpoint_fname and os.path.exists(checkpoint_fname):
-    sd = torch.load(checkpoint_fname, map_location='cpu')
-    model.load_state_dict(sd, vars_to_restore=vars_to_restore or 'model', ignore_missing_vars=ignore_missing_vars,
-                          reset_global_step=reset_global_step if reset_global_step is not False else -1)
+  if checkpoint_fname and tf_checkpoint.checkpoint_exists(checkpoint_fname):          # cnn_train_multi.py:404
+    print('RESTORING MODEL from: ' + checkpoint_fname)
+    model.restore_checkpoint(checkpoint_fname, vars_to_restore=vars_to_restore or 'model',
+                             ignore_missing_vars=ignore_missing_vars, exclude_vars=exclude_vars,
+                             reset_global_step=reset_global_step if reset_global_step is not False else -1)
   start_step = int(eng.global_step) if eng is not None else -1
   summary = None
   if rank == 0 and opts.get('log_dir') and opts.get('n_summary') and not fwd_only and opts.get('summaries', True):
@@ -142,8 +145,9 @@ def train_loop(opts, graph, loss, train_dataset, training_pl, handle_pl, train_o
     if summary is not None and step % opts['n_summary'] == 0:            # cnn_train_multi.py:452-457
       summary.write(model, step, lr=getattr(model.engine, 'last_lr', None))
     if not fwd_only and rank == 0 and step % opts['n_checkpoint'] == 0 and opts.get('log_dir'):
-      os.makedirs(opts['log_dir'], exist_ok=True)
-      torch.save(model.state_dict(), os.path.join(opts['log_dir'], 'model.ckpt-%d' % step))
+      # saver.save(session, <log_dir>/model.ckpt, global_step=step) (cnn_train_multi.py:511-513): TensorBundle files
+      prefix = model.save_checkpoint(os.path.join(opts['log_dir'], 'model.ckpt-%d' % step))
+      tf_checkpoint.update_checkpoint_state(opts['log_dir'], prefix)
     n_done += 1
   total = time.time() - begin
   if rank == 0 and n_done:

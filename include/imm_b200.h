@@ -238,6 +238,11 @@ int immb_adam_apply(float* p, const float* g, float* m, float* v, int64_t n, con
 int immb_total_loss(const float* rec_loss, const double* wsq, const float* tensor_wd, int n_tensors,
                     float* weights_loss, float* total, void* stream);
 
+/* ---- host utility: CRC-32C (Castagnoli) of n bytes continuing from `crc` (0 to start), as
+ * TensorFlow's lib/hash/crc32c used by the TensorBundle files behind tf.train.Saver (cnn_train_multi.py:432-439,
+ * 511-513).  Pure host code, no CUDA call. */
+uint32_t immb_crc32c(const void* data, size_t n, uint32_t crc);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,9 +51,14 @@ def test_train_script_runs_checkpoints_and_restores(tmp_path):
   assert 'step -1, loss' in out.stdout and 'step 2, loss' in out.stdout       # global_step starts at -1 (train.py:87-89)
   assert 'Avg. samples per second' in out.stdout
   assert any(f.startswith('events.out.tfevents') for f in os.listdir(str(tmp_path / 't')))      # train summaries
+  # saver.save(session, <logdir>/model.ckpt, global_step=step): TensorBundle files + the `checkpoint` state file
+  from imm_b200.utils import tf_checkpoint
   ck = tmp_path / 't' / 'model.ckpt-2'
-  assert ck.exists()
-  sd = torch.load(str(ck), map_location='cpu')
+  assert (tmp_path / 't' / 'model.ckpt-2.index').exists() and (tmp_path / 't' / 'model.ckpt-2.data-00000-of-00001').exists()
+  assert tf_checkpoint.latest_checkpoint(str(tmp_path / 't')) == str(ck)
+  reader = tf_checkpoint.CheckpointReader(str(ck))
+  sd = {k: torch.from_numpy(v) for k, v in reader.read_all().items()}
+  assert all(v.dtype == torch.float32 for v in sd.values()) and reader.get_variable_to_shape_map()['global_step'] == []
   for k in ('model/image_encoder/encoder/conv_1/conv_1/w', 'model/pose_encoder/conv_1/conv_1/b',
             'model/renderer/conv_7/batch_normalization/moving_variance', 'SelfSupReconstructionLoss/conv3_2_agg',
             'SelfSupReconstructionLoss/vgg16/conv5_2/weights', 'global_step', 'beta1_power',
@@ -74,4 +79,11 @@ def test_train_script_runs_checkpoints_and_restores(tmp_path):
   m.load_state_dict(sd, vars_to_restore='all')
   assert torch.equal(m.engine.params[g].cpu(), sd[g])
   assert torch.equal(m.engine.adam_v[k].cpu(), sd[k + '/Adam_1'])
-  assert m.engine.global_step == float(sd['global_step']) and m.engine.adam_t == int(sd['__adam_t'])
+  assert m.engine.global_step == float(sd['global_step']) == 3.0   # -1 + 4 applied steps; the FILE is named by the loop step (2)
+  assert m.engine.adam_t == 4          # steps -1..2 applied; recovered from beta1_power = 0.9^(t+1)
+  # --checkpoint restore through the CLI path (cnn_train_multi.py:404-433) continues from global_step + 0
+  out = subprocess.run([sys.executable, os.path.join(ROOT, 'scripts', 'train.py'), '--configs', str(cfg), '--num-steps', '4',
+                        '--checkpoint', str(ck), '--restore-optim'],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, cwd=ROOT, timeout=900)
+  assert out.returncode == 0, out.stdout[-3000:]
+  assert 'RESTORING MODEL from' in out.stdout and 'step 3, loss' in out.stdout and 'step 1, loss' not in out.stdout
