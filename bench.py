@@ -230,9 +230,13 @@ def main_cuda(args):
          'api': 'IMMModel.build(inputs from pinned host memory) + setup_training() train_op; loss.item() per step'}
 
   # ---- roofline of the dominant kernel family: one extra step with CUDA events around every C-ABI call --------
+  # (single-stream schedule for this one step, so that per-call durations are not inflated by overlapping kernels)
+  saved_streams = (eng.wgrad_stream, eng.pose_stream)
+  eng.wgrad_stream = eng.pose_stream = None
   _lib.PROFILE = []
   step_resident(0)
   torch.cuda.synchronize()
+  eng.wgrad_stream, eng.pose_stream = saved_streams
   fam = {}
   for name, tag, a, b in _lib.PROFILE:
     fam[name] = fam.get(name, 0.0) + a.elapsed_time(b)
@@ -244,7 +248,7 @@ def main_cuda(args):
   tj = os.path.join(ROOT, 'profiles', 'top_kernel.json')
   if os.path.exists(tj):
     traffic = json.load(open(tj)).get('dram_bytes_per_launch')
-  roofline = {'bound': 'tensor', 'kernel': 'conv_tc_kernel / conv_tc_wgrad_kernel (tcgen05 kind::tf32, 3xTF32)',
+  roofline = {'bound': 'tensor', 'kernel': 'conv engine: conv_tc2_kernel / conv_tc2_wgrad_kernel (persistent halo-reuse, 3x3 stride 1) + conv_tc_kernel / conv_tc_wgrad_kernel (other shapes); tcgen05 kind::tf32, 3xTF32 / 2-pass',
               'achieved': conv_tflops, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
               'frac': conv_tflops / peaks['bf16_tflops_sustained'], 'traffic': traffic,
               'peak_source': 'MEASURED_PEAKS.json bf16 sustained (%s); the TF32 pipe peaks at half of it and the engine '
@@ -270,7 +274,9 @@ def main_cuda(args):
                    'the frozen VGG16 tower uses weights rounded to TF32 at load and 2 passes)',
           'data': 'synthetic', 'config': workload_config(world), 'tflops_algorithmic': GFLOP_PER_PAIR * B * world / ms,
           'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks, 'e2e': e2e,
-          'gpu_launches': int(launches) * world, 'last_loss': loss_val}
+          'gpu_launches': int(launches) * world, 'last_loss': loss_val,
+          'streams': {'wgrad_side_stream': eng.wgrad_stream is not None, 'pose_branch_stream': eng.pose_stream is not None,
+                      'input_prefetch_stream': True}}
   print(json.dumps(line))
   sys.stdout.flush()
 

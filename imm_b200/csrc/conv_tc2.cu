@@ -293,6 +293,250 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
   }
 }
 
+// =============================================================================================================
+// CTA-pair variant (tcgen05 cta_group::2): the two CTAs of a 2-CTA cluster (one TPC) execute ONE MMA of
+// M = 256 pixels (two M tiles, CTA r owns tile 2*jm + r: its own halo box, its own 128 TMEM lanes) x N = BN2 output
+// channels.  The weight operand is SPLIT across the pair: CTA r fetches and keeps only rows [r*BN2/2, (r+1)*BN2/2) of
+// every weight slice, so per output the L2 -> SM weight traffic AND the per-SM shared-memory operand reads are half of
+// what two independent CTAs need, and N up to 256 fits (one activation halo serves 256 output channels).
+// Why: at M = 128 / N = 128 every SM has to ingest ~48-52 B/clk of operands to keep the TF32 pipe busy -- above the
+// ~42 B/clk/SM the L2 delivers chip-wide -- so the single-CTA kernel is L2-fed-bound on every wide layer.
+// Protocol: tc_ptx.cuh "CTA pair".  full barriers live in the leader (expect 2x the bytes: own + peer loads);
+// empty / accumulator-full barriers are per CTA and receive the leader's multicast commits; the accumulator-empty
+// barrier lives in the leader and counts the 4 epilogue warps of BOTH CTAs.
+// =============================================================================================================
+template <int BN2, int PASSES>
+struct Tc2PairCfg {
+  static constexpr uint32_t NPLA = PASSES >= 2 ? 2 : 1;
+  static constexpr uint32_t NPLB = PASSES == 3 ? 2 : 1;
+  static constexpr uint32_t A_PLANE = 18 * 16 * 128;
+  static constexpr uint32_t A_SLOT = A_PLANE * NPLA;
+  static constexpr uint32_t A_SLOTS = 2;
+  static constexpr uint32_t BH = BN2 / 2;                     // weight rows held by each CTA
+  static constexpr uint32_t B_PLANE = BH * 128;
+  static constexpr uint32_t B_SLOT = B_PLANE * NPLB;
+  static constexpr uint32_t ROOM = 232448 - 1024 - 512 - A_SLOTS * A_SLOT;
+  static constexpr uint32_t B_FIT = ROOM / B_SLOT;
+  static constexpr uint32_t B_SLOTS = B_FIT > 6 ? 6 : B_FIT;
+  static_assert(B_SLOTS >= 2, "weight ring needs two slots");
+  static constexpr uint32_t SMEM_BYTES = A_SLOTS * A_SLOT + B_SLOTS * B_SLOT + 1024 + 512;
+  static constexpr int ACC_COLS = BN2 < 32 ? 32 : BN2;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512));
+  static_assert(BN2 % 32 == 0 && BN2 <= 256, "pair N tile: multiple of 32 up to 256");
+};
+
+template <int BN2, int PASSES>
+__global__ void __launch_bounds__(192, 1)
+conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
+                     const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
+                     const __grid_constant__ Tc2Params p) {
+  using Cfg = Tc2PairCfg<BN2, PASSES>;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int tile0 = (int)(blockIdx.x >> 1);
+  const int tstep = (int)(gridDim.x >> 1);
+  const int n_iter_total = p.total_pairs;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_base = smem;
+  uint8_t* b_base = smem + Cfg::A_SLOTS * Cfg::A_SLOT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + Cfg::B_SLOTS * Cfg::B_SLOT);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + Cfg::A_SLOTS;
+  uint64_t* b_full = a_empty + Cfg::A_SLOTS;
+  uint64_t* b_empty = b_full + Cfg::B_SLOTS;
+  uint64_t* t_full = b_empty + Cfg::B_SLOTS;
+  uint64_t* t_empty = t_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (uint32_t i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (uint32_t i = 0; i < Cfg::B_SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 8); }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA_hi);
+    prefetch_tmap(&mapB_hi);
+    if (PASSES >= 2) prefetch_tmap(&mapA_lo);
+    if (PASSES == 3) prefetch_tmap(&mapB_lo);
+  }
+  if (warp == 1) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // both CTAs: barriers initialised and TMEM allocated before any load / MMA / arrive
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // pair iteration -> (n tile, the two m tiles); CTA `crank` owns m tile 2*jm + crank (clamped to the last m tile when
+  // the count is odd: that CTA recomputes it with stores disabled)
+  auto decode = [&](int it, int& img, int& th, int& tw, int& n_off, bool& live) {
+    const int nt = it % p.n_tiles_n;
+    int mt = (it / p.n_tiles_n) * 2 + (int)crank;
+    live = true;
+    if (mt >= p.m_tiles) { mt = p.m_tiles - 1; live = false; }
+    tw = mt % p.tiles_w;
+    int r = mt / p.tiles_w;
+    th = r % p.tiles_h;
+    img = r / p.tiles_h;
+    n_off = nt * BN2;
+  };
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs; every load signals the leader's full barrier) =====
+    uint32_t ai = 0, bi = 0;
+    for (int t = tile0; t < n_iter_total; t += tstep) {
+      int img, th, tw, n_off;
+      bool live;
+      decode(t, img, th, tw, n_off, live);
+      const int row0 = n_off + (int)crank * (int)Cfg::BH;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        const uint32_t as = ai % Cfg::A_SLOTS, aph = (ai / Cfg::A_SLOTS) & 1;
+        mbar_wait(&a_empty[as], aph ^ 1);
+        uint8_t* sa = a_base + as * Cfg::A_SLOT;
+        if (elect_one()) {
+          if (leader) mbar_expect_tx(&a_full[as], 2 * Cfg::A_SLOT);
+          tma_load_5d_pair(sa, &mapA_hi, &a_full[as], kc * 32, tw * 8 - 1, 0, th * 16 - 1, img);
+          if (PASSES >= 2)
+            tma_load_5d_pair(sa + Cfg::A_PLANE, &mapA_lo, &a_full[as], kc * 32, tw * 8 - 1, 0, th * 16 - 1, img);
+        }
+        __syncwarp();
+        ++ai;
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t bs = bi % Cfg::B_SLOTS, bph = (bi / Cfg::B_SLOTS) & 1;
+          mbar_wait(&b_empty[bs], bph ^ 1);
+          uint8_t* sb = b_base + bs * Cfg::B_SLOT;
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(&b_full[bs], 2 * Cfg::B_SLOT);
+            tma_load_3d_pair(sb, &mapB_hi, &b_full[bs], kc * 32, row0, p.taps[tap].b_tap);
+            if (PASSES == 3) tma_load_3d_pair(sb + Cfg::B_PLANE, &mapB_lo, &b_full[bs], kc * 32, row0, p.taps[tap].b_tap);
+          }
+          __syncwarp();
+          ++bi;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ===== MMA issuer (leader CTA only): M = 256 across the pair, N = BN2 =====
+      constexpr uint32_t idesc = idesc_tf32(256, BN2, 0, 0);
+      uint32_t ai = 0, bi = 0, ti = 0;
+      for (int t = tile0; t < n_iter_total; t += tstep) {
+        const uint32_t acc = ti & 1, tph = (ti >> 1) & 1;
+        mbar_wait(&t_empty[acc], tph ^ 1);            // the epilogues of BOTH CTAs have drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * Cfg::ACC_COLS;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          const uint32_t as = ai % Cfg::A_SLOTS, aph = (ai / Cfg::A_SLOTS) & 1;
+          mbar_wait(&a_full[as], aph);
+          const uint32_t a_hi = smem_u32(a_base + as * Cfg::A_SLOT);
+          const uint32_t a_lo = a_hi + Cfg::A_PLANE;
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint32_t bs = bi % Cfg::B_SLOTS, bph = (bi / Cfg::B_SLOTS) & 1;
+            mbar_wait(&b_full[bs], bph);
+            tc_fence_after();
+            const uint32_t b_hi = smem_u32(b_base + bs * Cfg::B_SLOT);
+            const uint32_t b_lo = b_hi + Cfg::B_PLANE;
+            const Tc2Tap tp = p.taps[tap];
+            const uint32_t a_off = (uint32_t)(tp.ro * 16 + tp.so) * 128u;
+            if (elect_one()) {
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const uint32_t ko = k4 * 32;
+                const uint64_t da_hi = smem_desc_sw128(a_hi + a_off + ko, 16, 2048, 2, 0);
+                const uint64_t db_hi = smem_desc_sw128(b_hi + ko, 16, 1024);
+                mma_tf32_pair(tmem_d, da_hi, db_hi, idesc, (kc > 0 || tap > 0 || k4 > 0) ? 1u : 0u);
+                if (PASSES == 3) {
+                  const uint64_t db_lo = smem_desc_sw128(b_lo + ko, 16, 1024);
+                  mma_tf32_pair(tmem_d, da_hi, db_lo, idesc, 1u);
+                }
+                if (PASSES >= 2) {
+                  const uint64_t da_lo = smem_desc_sw128(a_lo + a_off + ko, 16, 2048, 2, 0);
+                  mma_tf32_pair(tmem_d, da_lo, db_hi, idesc, 1u);
+                }
+              }
+              mma_commit_pair(&b_empty[bs], (uint16_t)3);
+              if (tap == 8) mma_commit_pair(&a_empty[as], (uint16_t)3);
+              if (tap == 8 && kc == p.kchunks - 1) mma_commit_pair(&t_full[acc], (uint16_t)3);
+            }
+            __syncwarp();
+            ++bi;
+          }
+          ++ai;
+        }
+        ++ti;
+      }
+    }
+  } else {
+    // ===== epilogue (warps 2..5 of both CTAs; each CTA drains its own 128 TMEM lanes) =====
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int hl = m >> 3, wl = m & 7;
+    uint32_t ti = 0;
+    for (int t = tile0; t < n_iter_total; t += tstep) {
+      int img, th, tw, n_off;
+      bool live;
+      decode(t, img, th, tw, n_off, live);
+      const uint32_t acc = ti & 1, tph = (ti >> 1) & 1;
+      const int h = th * 16 + hl, w = tw * 8 + wl;
+      const size_t pix = ((size_t)img * p.H + h) * p.W + w;
+      mbar_wait(&t_full[acc], tph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN2; c0 += 32) {
+        const int col0 = n_off + c0;
+        if (col0 >= p.n_cols) break;             // warp-uniform
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS + (uint32_t)c0, v);
+        if (!live) continue;
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.n_cols) v[j] += __ldg(p.bias + col0 + j);
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        float* o = p.out_hi + pix * p.ocs + col0;
+        if (p.out_lo) {
+          float* ol = p.out_lo + pix * p.ocs + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (col0 + j >= p.n_store) break;
+            float4 hi4, lo4;
+            split_tf32(v[j], hi4.x, lo4.x);
+            split_tf32(v[j + 1], hi4.y, lo4.y);
+            split_tf32(v[j + 2], hi4.z, lo4.z);
+            split_tf32(v[j + 3], hi4.w, lo4.w);
+            *reinterpret_cast<float4*>(o + j) = hi4;
+            *reinterpret_cast<float4*>(ol + j) = lo4;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (col0 + j >= p.n_store) break;
+            *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&t_empty[acc]);
+      ++ti;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // nobody exits (or frees TMEM) while the peer may still signal / compute into it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
 // ---- host ---------------------------------------------------------------------------------------------------
 int tc_make_act_map(CUtensorMap* m, const float* base, int N, int H, int W, int C, int cs, bool parity_split,
                     int box_w, int box_h, int box_n, int swizzle_mn);
@@ -371,6 +615,58 @@ static int launch_tc2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CU
   return IMMB_OK;
 }
 
+// IMMB_TC2_PAIR: 1 (default) = cta_group::2 pair kernel for every halo-conv, 0 = single-CTA kernel only,
+// N > 1 = pair kernel only when the layer has at least N output columns (development aid)
+int conv_tc2_pair_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("IMMB_TC2_PAIR");
+    mode = e ? atoi(e) : 1;
+  }
+  return mode;
+}
+// N tile of the pair kernel: as few N tiles as possible (one activation halo then serves up to 256 output channels),
+// each the smallest instantiated width that covers its share (288 columns -> 2 x 160, not 2 x 256)
+static int pair_bn(int ncols) {
+  const int nt = ceil_div(ncols, 256);
+  const int need = ceil_div(ncols, nt);
+  static const int kWidths[] = {32, 64, 96, 128, 160, 192, 256};
+  for (int w : kWidths)
+    if (w >= need) return w;
+  return 256;
+}
+
+template <int BN2, int PASSES>
+static int launch_tc2_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                           const CUtensorMap& b_lo, const Tc2Params& p, cudaStream_t st) {
+  using Cfg = Tc2PairCfg<BN2, PASSES>;
+  auto kern = conv_tc2_pair_kernel<BN2, PASSES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "conv_tc2_pair smem attr: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  int pairs = p.total_pairs < kNumSMs / 2 ? p.total_pairs : kNumSMs / 2;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a_hi, a_lo, b_hi, b_lo, p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "conv_tc2_pair launch: %s", cudaGetErrorString(e));
+  return IMMB_OK;
+}
+
 // act: the tensor the halo boxes are read from ([N,H,W,act_cs], act_c valid channels); wts: [9][ncols_pad][kd]
 int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const float* act_lo, int act_c, int act_cs,
                  const float* w_hi, const float* w_lo, int w_rows, int kd, const float* bias, int relu,
@@ -379,14 +675,16 @@ int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const flo
   Tc2Params p;
   memset(&p, 0, sizeof(p));
   p.tiles_w = d->W / 8; p.tiles_h = d->H / 16; p.n_img = d->N;
-  const int bn = tc_pick_bn(ncols);
+  const int pmode = conv_tc2_pair_mode();
+  const bool pair = pmode > 0 && ncols >= (pmode > 1 ? pmode : 1);
+  const int bn = pair ? pair_bn(ncols) : tc_pick_bn(ncols);
   p.n_tiles_n = ceil_div(ncols, bn);
   p.total_tiles = p.tiles_w * p.tiles_h * p.n_img * p.n_tiles_n;
   p.m_tiles = p.tiles_w * p.tiles_h * p.n_img;
   p.total_pairs = ceil_div(p.m_tiles, 2) * p.n_tiles_n;
   // cluster mode pays off when the weight slice dominates the operand traffic (wide N tiles) and there is enough work
   const int cmode = conv_tc2_cluster_mode();
-  const bool cluster = cmode > 0 && bn >= 32 && (bn % 32 == 0 || bn == 96) && (cmode == 2 ? bn >= 32 : bn >= 64) &&
+  const bool cluster = !pair && cmode > 0 && bn >= 32 && (bn % 32 == 0 || bn == 96) && (cmode == 2 ? bn >= 32 : bn >= 64) &&
                        (cmode == 2 || p.m_tiles >= 2 * kNumSMs);
   p.kchunks = ceil_div(kd, 32);
   for (int r = 0; r < 3; ++r)
@@ -402,7 +700,7 @@ int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const flo
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
   int rc;
   if ((rc = tc_make_act_map(&a_hi, act_hi, d->N, d->H, d->W, act_c, act_cs, false, 16, 18, 1, 0))) return rc;
-  const int b_box = cluster ? bn / 2 : bn;            // cluster mode: each CTA loads (and multicasts) half the rows
+  const int b_box = (cluster || pair) ? bn / 2 : bn;  // cluster / pair mode: each CTA loads half of the rows
   if ((rc = tc_make_w_map(&b_hi, w_hi, 9, w_rows, kd, b_box))) return rc;
   a_lo = a_hi; b_lo = b_hi;
   if (passes >= 2) {
@@ -410,6 +708,22 @@ int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const flo
   }
   if (passes == 3) {
     if ((rc = tc_make_w_map(&b_lo, w_lo, 9, w_rows, kd, b_box))) return rc;
+  }
+  if (pair) {
+#define IMMB_PCASE(BN_)                                                                  \
+  if (bn == BN_)                                                                         \
+    return passes == 3 ? launch_tc2_pair<BN_, 3>(a_hi, a_lo, b_hi, b_lo, p, st)          \
+         : passes == 2 ? launch_tc2_pair<BN_, 2>(a_hi, a_lo, b_hi, b_lo, p, st)          \
+                       : launch_tc2_pair<BN_, 1>(a_hi, a_lo, b_hi, b_lo, p, st);
+    IMMB_PCASE(32)
+    IMMB_PCASE(64)
+    IMMB_PCASE(96)
+    IMMB_PCASE(128)
+    IMMB_PCASE(160)
+    IMMB_PCASE(192)
+    IMMB_PCASE(256)
+#undef IMMB_PCASE
+    return set_error(IMMB_ERR_INVALID, "conv_tc2 pair: unsupported BN %d", bn);
   }
 #define IMMB_CASE(BN_)                                                                     \
   if (bn == BN_)                                                                           \

@@ -12,6 +12,7 @@ Data layout in HBM (per GPU, batch B, NHWC fp32):
   * raw conv outputs y (pre-BN) are kept for the BN backward; gradients wrt activations are single fp32.
 """
 import math
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -129,7 +130,7 @@ class IMMEngine(object):
   channels_bug_fix, perceptual.comp, reconstruction_loss, perceptual.l2."""
 
   def __init__(self, config, batch, image_size=128, device='cuda:0', precision=_lib.PREC_TF32X3,
-               engine=_lib.ENGINE_AUTO, world_size=1, vgg_tf32_weights=True):
+               engine=_lib.ENGINE_AUTO, world_size=1, vgg_tf32_weights=True, streams=None):
     if not torch.cuda.is_available():
       raise _lib.ImmbError('IMMEngine needs a CUDA device; there is no CPU fallback')
     _lib.lib()
@@ -162,6 +163,16 @@ class IMMEngine(object):
     self._alloc_params()
     self._alloc_buffers()
     self.vgg_loaded = False
+    # Stream-level concurrency of INDEPENDENT work (no arithmetic changes, same kernels, same results):
+    #   bit 0: every weight-gradient conv runs on a side stream (dw is only needed by the optimiser), so the HBM-bound
+    #          BN-backward kernels of the next layer overlap the tensor-bound wgrad kernels;
+    #   bit 1: the pose-encoder branch (forward and backward) runs on its own stream next to the image-encoder branch.
+    if streams is None:
+      streams = int(os.environ.get('IMMB_STREAMS', '3'))
+    self.streams = int(streams)
+    self.wgrad_stream = torch.cuda.Stream(device=self.dev) if self.streams & 1 else None
+    self.pose_stream = torch.cuda.Stream(device=self.dev) if self.streams & 2 else None
+    self._events = {}
 
   # ------------------------------------------------------------------------------------------------
   # construction
@@ -385,6 +396,7 @@ class IMMEngine(object):
     # scratch of the two-level (deterministic, atomic-free) BN reductions
     n_scr = max([int(call('immb_bn_scratch_elems', L.N * L.Ho * L.Wo, L.cout)) for L in self.layers.values() if L.bn] + [16])
     self.bn_scratch = torch.empty(n_scr, dtype=torch.float64, device=dev)
+    self.bn_scratch_pose = torch.empty(n_scr, dtype=torch.float64, device=dev)      # the pose-branch stream's own scratch
 
   # ------------------------------------------------------------------------------------------------
   # parameters
@@ -471,7 +483,25 @@ class IMMEngine(object):
   def _conv_fwd(self, L, X, y_hi, y_lo=None, N=None):
     call('immb_conv2d_fwd', L.desc(N), X.hi, X.lo, L.w, L.wp.hi, L.wp.lo, L.b, y_hi, y_lo, _lib.stream_ptr())
 
-  def _block_fwd(self, L, X, training):
+  def _event(self, key):
+    ev = self._events.get(key)
+    if ev is None:
+      ev = self._events[key] = torch.cuda.Event()
+    return ev
+
+  def _fork(self, side, key):
+    """side stream waits for everything enqueued so far on the current stream."""
+    ev = self._event(key)
+    ev.record()
+    side.wait_event(ev)
+
+  def _join(self, side, key):
+    """current stream waits for everything enqueued so far on the side stream."""
+    ev = self._event(key)
+    ev.record(side)
+    torch.cuda.current_stream().wait_event(ev)
+
+  def _block_fwd(self, L, X, training, scratch=None):
     """conv -> bias -> [BN] -> [ReLU] -> [x2 legacy bilinear]  (nn_utils.py:151-210, imm_model.py:175)."""
     st = _lib.stream_ptr()
     _lib.TAG = 'fwd:%s/%s' % (L.prefix.split('/')[-2] if L.prefix.endswith('encoder') else L.prefix.split('/')[-1], L.name)
@@ -481,7 +511,8 @@ class IMMEngine(object):
       return None
     npix = L.N * L.Ho * L.Wo
     if training:
-      call('immb_bn_stats', L.y, npix, L.cout, L.ycs, L.sums, self.bn_scratch, self.bn_scratch.numel(), st)
+      sc = self.bn_scratch if scratch is None else scratch
+      call('immb_bn_stats', L.y, npix, L.cout, L.ycs, L.sums, sc, sc.numel(), st)
     call('immb_bn_finalize', L.sums, npix, L.cout, L.gamma, L.beta, L.mm, L.mv, 1 if training else 0,
          L.scale, L.shift, L.mean, L.invstd, st)
     call('immb_bn_apply', L.y, L.N, L.Ho, L.Wo, L.cout, L.ycs, L.scale, L.shift, 1 if L.relu else 0,
@@ -500,24 +531,40 @@ class IMMEngine(object):
     self.training = training
     self.fwd_pool.zero_()
     # image encoder (imm_model.py:220-230) and pose encoder (:233-248)
-    for enc, inp in (('image_encoder', image), ('pose_encoder', future_image)):
+    def run_encoder(enc, inp, scratch):
+      st_ = _lib.stream_ptr()
       X = Planes(inp, None)
       L0 = self.enc_layers[enc][0]
       if L0.x_layout == _lib.XLAYOUT_ROWWIN4:
-        call('immb_stage_image_rowwin', inp, B, R, R, L0.stage.hi, L0.stage.lo, st)
+        call('immb_stage_image_rowwin', inp, B, R, R, L0.stage.hi, L0.stage.lo, st_)
         X = L0.stage
       for L in self.enc_layers[enc]:
-        X = self._block_fwd(L, X, training)
-    img_last, pose_last = self.enc_layers['image_encoder'][-1], self.enc_layers['pose_encoder'][-1]
+        X = self._block_fwd(L, X, training, scratch)
+
+    def run_pose_branch(scratch):
+      # pose encoder -> heatmaps -> (mu_y, mu_x) -> Gaussian maps into channels [enc_feat, enc_feat+K) of the concat
+      # buffer (imm_model.py:233-274,341-344); the image branch writes channels [0, enc_feat) of the same buffer
+      run_encoder('pose_encoder', future_image, scratch)
+      pose_last = self.enc_layers['pose_encoder'][-1]
+      self._block_fwd(self.pose_conv, pose_last.out, training, scratch)
+      S = self.enc_out_size
+      call('immb_softargmax_gauss_fwd', self.pose_conv.y, B, S, K, self.Kp, self.inv_std, self.mu, self.py, self.px, 16,
+           self.joint.hi, self.joint.lo, self.Cj, self.enc_feat, _lib.stream_ptr())
+
+    if self.pose_stream is not None:
+      self._fork(self.pose_stream, 'fwd_fork')
+      with torch.cuda.stream(self.pose_stream):
+        run_pose_branch(self.bn_scratch_pose)
+    run_encoder('image_encoder', image, None)
+    img_last = self.enc_layers['image_encoder'][-1]
     if self.enc_out_size != 16:     # imm_model.py:324-335: resize_bilinear(align_corners=True) to the render size
       S = self.enc_out_size
       call('immb_resize_ac_fwd', img_last.out.hi, img_last.out.lo, img_last.cout, B, S, S, self.enc_feat, 16, 16,
            self.joint.hi, self.joint.lo, self.Cj, st)
-    # heatmaps -> (mu_y, mu_x) -> Gaussian maps into the concat buffer (imm_model.py:247-274,341-344)
-    self._block_fwd(self.pose_conv, pose_last.out, training)
-    S = self.enc_out_size
-    call('immb_softargmax_gauss_fwd', self.pose_conv.y, B, S, K, self.Kp, self.inv_std, self.mu, self.py, self.px, 16,
-         self.joint.hi, self.joint.lo, self.Cj, self.enc_feat, st)
+    if self.pose_stream is not None:
+      self._join(self.pose_stream, 'fwd_join')
+    else:
+      run_pose_branch(None)
     # renderer (imm_model.py:154-179)
     X = self.joint
     for L in self.ren_layers:
@@ -578,7 +625,7 @@ class IMMEngine(object):
   # ------------------------------------------------------------------------------------------------
   # backward
   # ------------------------------------------------------------------------------------------------
-  def _block_bwd(self, L, g, gcs):
+  def _block_bwd(self, L, g, gcs, scratch=None):
     """g: gradient wrt the block output (after the optional x2 upsample), channel stride gcs.
     Returns the gradient wrt the block input [N,H,W,xcs] or None."""
     st = _lib.stream_ptr()
@@ -589,7 +636,7 @@ class IMMEngine(object):
         call('immb_upsample2x_bwd', g, L.N, L.Ho, L.Wo, L.cout, gcs, L.g_low, st)
         g, gcs = L.g_low, L.cout
       relu = 1 if L.relu else 0
-      sc = self.bn_scratch
+      sc = self.bn_scratch if scratch is None else scratch
       call('immb_bn_bwd_reduce', g, gcs, L.y, L.cout, npix, L.cout, L.scale, L.shift, L.mean, L.invstd, relu,
            L.bsums, sc, sc.numel(), st)
       call('immb_bn_bwd_apply', g, gcs, L.y, L.cout, npix, L.cout, L.scale, L.shift, L.mean, L.invstd, relu,
@@ -604,7 +651,14 @@ class IMMEngine(object):
       call('immb_bias_grad', dy.hi, dy.lo, L.ycs, npix, L.cout, L.dbias_acc, st)
     call('immb_cast_d2f', L.dbias_acc, L.db, L.cout, st)
     d = L.desc()
-    call('immb_conv2d_wgrad', d, L.x.hi, L.x.lo, dy.hi, dy.lo, L.dw, self.workspace, self.workspace.numel(), st)
+    if self.wgrad_stream is not None:
+      # dw is consumed by the optimiser only: the wgrad runs on its own stream behind the kernel that produced dy
+      self._fork(self.wgrad_stream, ('wg', id(L)))
+      with torch.cuda.stream(self.wgrad_stream):
+        call('immb_conv2d_wgrad', d, L.x.hi, L.x.lo, dy.hi, dy.lo, L.dw, self.workspace, self.workspace.numel(),
+             _lib.stream_ptr())
+    else:
+      call('immb_conv2d_wgrad', d, L.x.hi, L.x.lo, dy.hi, dy.lo, L.dw, self.workspace, self.workspace.numel(), st)
     if L.needs_dgrad:
       call('immb_conv2d_dgrad', d, dy.hi, dy.lo, L.w, L.wh.hi, L.wh.lo, L.dx, st)
       return L.dx
@@ -659,13 +713,21 @@ class IMMEngine(object):
     dJ = g                                             # [B,16,16,Cj]
     # pose branch: Gaussian maps -> mu -> softmax marginals -> heatmaps (imm_model.py:252-274)
     S = self.enc_out_size
-    call('immb_softargmax_gauss_bwd', dJ, self.Cj, self.enc_feat, self.mu, self.py, self.px, B, S, K, 16,
-         self.inv_std, self.g_heat, self.Kp, st)
-    gp = self._block_bwd(self.pose_conv, self.g_heat, self.Kp)
-    gcs_p = self.enc_feat
-    for L in reversed(self.enc_layers['pose_encoder']):
-      gp = self._block_bwd(L, gp, gcs_p)
-      gcs_p = L.xcs
+    def pose_branch_bwd(scratch):
+      call('immb_softargmax_gauss_bwd', dJ, self.Cj, self.enc_feat, self.mu, self.py, self.px, B, S, K, 16,
+           self.inv_std, self.g_heat, self.Kp, _lib.stream_ptr())
+      gp = self._block_bwd(self.pose_conv, self.g_heat, self.Kp, scratch)
+      gcs_p = self.enc_feat
+      for L in reversed(self.enc_layers['pose_encoder']):
+        gp = self._block_bwd(L, gp, gcs_p, scratch)
+        gcs_p = L.xcs
+
+    if self.pose_stream is not None:
+      self._fork(self.pose_stream, 'bwd_fork')
+      with torch.cuda.stream(self.pose_stream):
+        pose_branch_bwd(self.bn_scratch_pose)
+    else:
+      pose_branch_bwd(None)
     # image branch
     gi, gcs_i = dJ, self.Cj
     if self.enc_out_size != 16:
@@ -674,6 +736,10 @@ class IMMEngine(object):
     for L in reversed(self.enc_layers['image_encoder']):
       gi = self._block_bwd(L, gi, gcs_i)
       gcs_i = L.xcs
+    if self.pose_stream is not None:
+      self._join(self.pose_stream, 'bwd_join')
+    if self.wgrad_stream is not None:
+      self._join(self.wgrad_stream, 'wg_join')
 
   # ------------------------------------------------------------------------------------------------
   # optimiser  (cnn_train_multi.py:93-98,232-241; scripts/train.py:92-98)

@@ -66,14 +66,63 @@ def tower_loss(inputs, training_pl, model, scope=None):
   return loss
 
 
+class _InputPrefetcher(object):
+  """One-deep input prefetch, the role `dataset.prefetch` + the feedable iterator play in the reference
+  (tps_dataset.py:98-131, cnn_train_multi.py:445-450): the NEXT batch's host->device copies are enqueued on a copy
+  stream while the current step's kernels run, so H2D never sits on the critical path.  Host tensors should be pinned
+  (pageable memory makes the copy synchronous, which is still correct).  CUDA tensors pass through untouched."""
+
+  def __init__(self, inputs_fn, device):
+    self.inputs_fn, self.device = inputs_fn, torch.device(device)
+    self.stream = torch.cuda.Stream(device=self.device)
+    self.staged = None
+
+  def _stage(self):
+    inputs = self.inputs_fn()
+    if inputs is None:
+      self.staged = None
+      return
+    out = {}
+    with torch.cuda.stream(self.stream):
+      for k, v in inputs.items():
+        out[k] = v.to(self.device, non_blocking=True) if isinstance(v, torch.Tensor) and not v.is_cuda else v
+    ev = torch.cuda.Event()
+    ev.record(self.stream)
+    self.staged = (out, ev)
+
+  def next(self):
+    if self.staged is None:
+      self._stage()
+    if self.staged is None:
+      return None
+    out, ev = self.staged
+    cur = torch.cuda.current_stream(self.device)
+    cur.wait_event(ev)
+    for v in out.values():
+      if isinstance(v, torch.Tensor) and v.is_cuda:
+        v.record_stream(cur)          # allocated on the copy stream, consumed on the compute stream
+    self.staged = None
+    return out
+
+  def prefetch(self):
+    if self.staged is None:
+      self._stage()
+
+
 def _make_train_op(model, optim, inputs_fn, clip_value):
+  state = {}
+
   def train_op():
-    inputs = inputs_fn()
+    pf = state.get('pf')
+    if pf is None:
+      pf = state['pf'] = _InputPrefetcher(inputs_fn, model._device)
+    inputs = pf.next()
     model.build(inputs, True)
     eng = model.engine
     eng.backward()
     eng.optimizer_step(clip_value, lr=optim.lr(eng.global_step), beta1=optim.beta1, beta2=optim.beta2,
                        eps=optim.epsilon, allreduce=average_gradients if eng.world_size > 1 else None)
+    pf.prefetch()                  # next batch's H2D overlaps this step's kernels (the host is ahead of the GPU here)
     for op in model._avg_ops:
       pass                       # cost EMAs are evaluated lazily by the logger (they need a D2H read)
     return eng.total_loss

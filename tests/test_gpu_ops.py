@@ -100,6 +100,8 @@ TC_CASES = [
   (2, 16, 16, 256, 10, 1, 1, None),      # pose 1x1 -> 10 heatmaps (stride 12)
   (1, 16, 16, 256, 50, 1, 1, None),      # pose 1x1 -> 50 heatmaps (stride 52, BN=64 tile)
   (2, 32, 32, 9, 64, 1, 1, 12),          # vgg conv1_1 as a 1x1 conv over 3x3 patches (Cin=9, stride 12)
+  (3, 16, 16, 64, 96, 3, 1, None),       # CTA-pair N tile of 96 (48 weight rows per CTA), odd image count
+  (1, 16, 16, 320, 192, 3, 1, None),     # pair N tiles of 192 (fwd) and 2 x 160 (dgrad over 320 input channels)
 ]
 
 
@@ -165,10 +167,23 @@ def test_conv_tc2_cluster_multicast_mode():
   """IMMB_TC2_CLUSTER=2 forces the 2-CTA-cluster variant of the halo kernel (each CTA TMA-multicasts half of every
   weight slice into both CTAs' shared memory).  The mode is read once per process, so run a subset in a child."""
   import os, subprocess, sys
-  env = dict(os.environ, IMMB_TC2_CLUSTER='2')
+  env = dict(os.environ, IMMB_TC2_CLUSTER='2', IMMB_TC2_PAIR='0')
   root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
   out = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(root, 'tests', 'test_gpu_ops.py'), '-m', 'gpu', '-q',
                         '-k', 'tcgen05_engine and (case0 or case1 or case5 or case10)', '-p', 'no:cacheprovider'],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, cwd=root, timeout=600)
+  assert out.returncode == 0 and 'passed' in out.stdout and 'failed' not in out.stdout, out.stdout[-1500:]
+
+
+def test_conv_tc2_single_cta_mode():
+  """IMMB_TC2_PAIR=0 routes the stride-1 3x3 layers through the single-CTA halo kernel (cta_group::1) instead of the
+  default CTA-pair kernel (cta_group::2, M = 256); both must meet the same bars.  Read once per process -> child."""
+  import os, subprocess, sys
+  env = dict(os.environ, IMMB_TC2_PAIR='0')
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  out = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(root, 'tests', 'test_gpu_ops.py'), '-m', 'gpu', '-q',
+                        '-k', 'tcgen05_engine and (case0 or case1 or case5 or case8 or case10 or case11 or case15)',
+                        '-p', 'no:cacheprovider'],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, cwd=root, timeout=600)
   assert out.returncode == 0 and 'passed' in out.stdout and 'failed' not in out.stdout, out.stdout[-1500:]
 

@@ -31,7 +31,8 @@ print('fwd %.2f ms' % timed(lambda: eng.forward(inp['image'], inp['future_image'
 print('bwd %.2f ms' % timed(lambda: eng.backward()))
 print('opt %.2f ms' % timed(lambda: eng.optimizer_step()))
 
-# per-call attribution (CUDA events around every C-ABI call)
+# per-call attribution (CUDA events around every C-ABI call), single-stream schedule so that calls do not overlap
+eng.wgrad_stream = eng.pose_stream = None
 _lib.PROFILE = []
 eng.train_step(inp['image'], inp['future_image'], inp['mask'])
 torch.cuda.synchronize()
@@ -42,7 +43,7 @@ for name, tag, a, b in _lib.PROFILE:
 _lib.PROFILE = None
 tot = sum(by.values())
 print('sum of per-call times %.2f ms' % tot)
-for (tag, name), v in sorted(by.items(), key=lambda kv: -kv[1])[:45]:
+for (tag, name), v in sorted(by.items(), key=lambda kv: -kv[1])[:int(sys.argv[4]) if len(sys.argv) > 4 else 45]:
   print('  %-34s %-28s %7.3f ms' % (tag, name.replace('immb_', ''), v))
 print('by kernel family:')
 for name, v in sorted(by_k.items(), key=lambda kv: -kv[1])[:14]:
