@@ -488,6 +488,12 @@ int tc_make_act_map(CUtensorMap* m, const float* base, int N, int H, int W, int 
 int tc_make_w_map(CUtensorMap* m, const float* base, int taps, int Nn, int Kd, int bn) {
   return make_w_map(m, base, taps, Nn, Kd, bn);
 }
+int tc_make_rowwin_map(CUtensorMap* m, const float* base, int N, int H, int W, int box_w, int box_h, int box_n) {
+  return make_rowwin_map(m, base, N, H, W, box_w, box_h, box_n, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+bool conv_tc2_rowwin_eligible(const immb_conv_desc* d);
+int conv_tc2_rowwin_fwd(const immb_conv_desc* d, const float* x_hi, const float* x_lo, const float* wp_hi,
+                        const float* wp_lo, const float* bias, int relu, float* y_hi, float* y_lo, cudaStream_t st);
 bool conv_tc2_eligible(const immb_conv_desc* d, int op);
 bool conv_tc2_wgrad_eligible(const immb_conv_desc* d);
 int conv_tc2_wgrad_run(const immb_conv_desc* d, const float* x_hi, const float* x_lo, const float* dy_hi,
@@ -585,6 +591,8 @@ int conv_tc_fwd(const immb_conv_desc* d, const float* x_hi, const float* x_lo, c
   if (conv_tc2_eligible(d, 0))
     return conv_tc2_run(d, 0, x_hi, x_lo, d->Cin, d->x_cstride, wp_hi, wp_lo, d->Cout, d->cin_pad, bias,
                         d->epilogue == IMMB_EPI_BIAS_RELU, y_hi, y_lo, d->y_cstride, d->Cout, (d->Cout + 3) / 4 * 4, st);
+  if (conv_tc2_rowwin_eligible(d))
+    return conv_tc2_rowwin_fwd(d, x_hi, x_lo, wp_hi, wp_lo, bias, d->epilogue == IMMB_EPI_BIAS_RELU, y_hi, y_lo, st);
   const int passes = d->precision == IMMB_PREC_TF32 ? 1 : 3;
   TcParams p;
   memset(&p, 0, sizeof(p));

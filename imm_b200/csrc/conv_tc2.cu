@@ -37,6 +37,12 @@ struct Tc2Params {
   int relu;
   int H, W, ocs, n_cols, n_store;
   int bo_mode;               // debug (IMMB_TC2_BO): 0 = base_offset 0 (correct), 1 = base_offset s
+  // pair kernel only: geometry of the activation box (defaults = the 3x3 halo box)
+  int n_taps;                // 9 (3x3 halo) or 7 (filter rows of the 7x7 first layer on the row-window view)
+  int a_sbo;                 // bytes between the 8-row core-matrix groups of the A operand = box width * 128
+  int a_plane_bytes;         // bytes one TMA box deposits per plane (expect_tx)
+  int box_dw, box_dh;        // box origin relative to the tile origin (-1,-1 for 3x3 SAME; 0,-3 for the row-window view)
+  uint32_t a_off[9];         // byte offset of each tap's first row inside the box
 };
 
 template <int BN, int PASSES>
@@ -320,7 +326,13 @@ struct Tc2PairCfg {
   static constexpr uint32_t B_SLOTS = B_FIT > 6 ? 6 : B_FIT;
   static_assert(B_SLOTS >= 2, "weight ring needs two slots");
   static constexpr uint32_t SMEM_BYTES = A_SLOTS * A_SLOT + B_SLOTS * B_SLOT + 1024 + 512;
-  static constexpr int ACC_COLS = BN2 < 32 ? 32 : BN2;
+  // 3-pass: the two cross terms (hi*lo, lo*hi; ~2^-11 of the main term) accumulate in their OWN TMEM columns
+  // [BN2, 2*BN2) and are added to the main accumulator once, in the epilogue.  The tensor core truncates the fp32
+  // accumulator at every MMA, a biased error that grows linearly with the number of accumulating MMAs; keeping the
+  // small terms out of the main accumulator leaves it with ONE truncating add per K-step, like a plain TF32 GEMM
+  // (measured: all three products into one accumulator pushed the BN-beta gradients of config 1 from <1e-2 to 1.01e-2).
+  static constexpr int ACC_COLS = PASSES == 3 ? 2 * BN2 : BN2;
+  static_assert(2 * ACC_COLS <= 512, "two accumulator sets must fit the 512 TMEM columns (3-pass: BN2 <= 128)");
   static constexpr int TMEM_COLS = 2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512));
   static_assert(BN2 % 32 == 0 && BN2 <= 256, "pair N tile: multiple of 32 up to 256");
 };
@@ -397,14 +409,14 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
         mbar_wait(&a_empty[as], aph ^ 1);
         uint8_t* sa = a_base + as * Cfg::A_SLOT;
         if (elect_one()) {
-          if (leader) mbar_expect_tx(&a_full[as], 2 * Cfg::A_SLOT);
-          tma_load_5d_pair(sa, &mapA_hi, &a_full[as], kc * 32, tw * 8 - 1, 0, th * 16 - 1, img);
+          if (leader) mbar_expect_tx(&a_full[as], 2 * Cfg::NPLA * (uint32_t)p.a_plane_bytes);
+          tma_load_5d_pair(sa, &mapA_hi, &a_full[as], kc * 32, tw * 8 + p.box_dw, 0, th * 16 + p.box_dh, img);
           if (PASSES >= 2)
-            tma_load_5d_pair(sa + Cfg::A_PLANE, &mapA_lo, &a_full[as], kc * 32, tw * 8 - 1, 0, th * 16 - 1, img);
+            tma_load_5d_pair(sa + Cfg::A_PLANE, &mapA_lo, &a_full[as], kc * 32, tw * 8 + p.box_dw, 0, th * 16 + p.box_dh, img);
         }
         __syncwarp();
         ++ai;
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int tap = 0; tap < p.n_taps; ++tap) {
           const uint32_t bs = bi % Cfg::B_SLOTS, bph = (bi / Cfg::B_SLOTS) & 1;
           mbar_wait(&b_empty[bs], bph ^ 1);
           uint8_t* sb = b_base + bs * Cfg::B_SLOT;
@@ -433,33 +445,36 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
           mbar_wait(&a_full[as], aph);
           const uint32_t a_hi = smem_u32(a_base + as * Cfg::A_SLOT);
           const uint32_t a_lo = a_hi + Cfg::A_PLANE;
-          for (int tap = 0; tap < 9; ++tap) {
+          const int last_tap = p.n_taps - 1;
+          const uint32_t sbo = (uint32_t)p.a_sbo;
+          for (int tap = 0; tap <= last_tap; ++tap) {
             const uint32_t bs = bi % Cfg::B_SLOTS, bph = (bi / Cfg::B_SLOTS) & 1;
             mbar_wait(&b_full[bs], bph);
             tc_fence_after();
             const uint32_t b_hi = smem_u32(b_base + bs * Cfg::B_SLOT);
             const uint32_t b_lo = b_hi + Cfg::B_PLANE;
-            const Tc2Tap tp = p.taps[tap];
-            const uint32_t a_off = (uint32_t)(tp.ro * 16 + tp.so) * 128u;
+            const uint32_t a_off = p.a_off[tap];
             if (elect_one()) {
 #pragma unroll
               for (int k4 = 0; k4 < 4; ++k4) {
                 const uint32_t ko = k4 * 32;
-                const uint64_t da_hi = smem_desc_sw128(a_hi + a_off + ko, 16, 2048, 2, 0);
+                const uint64_t da_hi = smem_desc_sw128(a_hi + a_off + ko, 16, sbo, 2, 0);
                 const uint64_t db_hi = smem_desc_sw128(b_hi + ko, 16, 1024);
-                mma_tf32_pair(tmem_d, da_hi, db_hi, idesc, (kc > 0 || tap > 0 || k4 > 0) ? 1u : 0u);
+                const uint32_t first = (kc > 0 || tap > 0 || k4 > 0) ? 1u : 0u;
+                mma_tf32_pair(tmem_d, da_hi, db_hi, idesc, first);
                 if (PASSES == 3) {
                   const uint64_t db_lo = smem_desc_sw128(b_lo + ko, 16, 1024);
-                  mma_tf32_pair(tmem_d, da_hi, db_lo, idesc, 1u);
-                }
-                if (PASSES >= 2) {
-                  const uint64_t da_lo = smem_desc_sw128(a_lo + a_off + ko, 16, 2048, 2, 0);
+                  const uint64_t da_lo = smem_desc_sw128(a_lo + a_off + ko, 16, sbo, 2, 0);
+                  mma_tf32_pair(tmem_d + BN2, da_hi, db_lo, idesc, first);      // cross terms: own accumulator
+                  mma_tf32_pair(tmem_d + BN2, da_lo, db_hi, idesc, 1u);
+                } else if (PASSES == 2) {
+                  const uint64_t da_lo = smem_desc_sw128(a_lo + a_off + ko, 16, sbo, 2, 0);
                   mma_tf32_pair(tmem_d, da_lo, db_hi, idesc, 1u);
                 }
               }
               mma_commit_pair(&b_empty[bs], (uint16_t)3);
-              if (tap == 8) mma_commit_pair(&a_empty[as], (uint16_t)3);
-              if (tap == 8 && kc == p.kchunks - 1) mma_commit_pair(&t_full[acc], (uint16_t)3);
+              if (tap == last_tap) mma_commit_pair(&a_empty[as], (uint16_t)3);
+              if (tap == last_tap && kc == p.kchunks - 1) mma_commit_pair(&t_full[acc], (uint16_t)3);
             }
             __syncwarp();
             ++bi;
@@ -490,6 +505,12 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
         if (col0 >= p.n_cols) break;             // warp-uniform
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS + (uint32_t)c0, v);
+        if (PASSES == 3) {
+          float v2[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS + (uint32_t)(BN2 + c0), v2);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += v2[j];
+        }
         if (!live) continue;
         if (p.bias) {
 #pragma unroll
@@ -625,20 +646,25 @@ int conv_tc2_pair_mode() {
   }
   return mode;
 }
-// N tile of the pair kernel: as few N tiles as possible (one activation halo then serves up to 256 output channels),
-// each the smallest instantiated width that covers its share (288 columns -> 2 x 160, not 2 x 256)
-static int pair_bn(int ncols) {
-  const int nt = ceil_div(ncols, 256);
+// N tile of the pair kernel: as few N tiles as possible (one activation halo then serves up to 256 output channels;
+// 128 for the 3-pass product, whose cross-term accumulator doubles the TMEM columns), each the smallest instantiated
+// width that covers its share (288 columns -> 3 x 96 for 3 passes, 2 x 160 otherwise)
+static int pair_bn(int ncols, int passes) {
+  const int cap = passes == 3 ? 128 : 256;
+  const int nt = ceil_div(ncols, cap);
   const int need = ceil_div(ncols, nt);
   static const int kWidths[] = {32, 64, 96, 128, 160, 192, 256};
   for (int w : kWidths)
     if (w >= need) return w;
-  return 256;
+  return cap;
 }
 
 template <int BN2, int PASSES>
 static int launch_tc2_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                            const CUtensorMap& b_lo, const Tc2Params& p, cudaStream_t st) {
+  if constexpr (PASSES == 3 && BN2 > 128) {
+    return set_error(IMMB_ERR_INVALID, "conv_tc2 pair: 3-pass N tile %d > 128", BN2);
+  } else {
   using Cfg = Tc2PairCfg<BN2, PASSES>;
   auto kern = conv_tc2_pair_kernel<BN2, PASSES>;
   static bool configured = false;
@@ -665,6 +691,7 @@ static int launch_tc2_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, con
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "conv_tc2_pair launch: %s", cudaGetErrorString(e));
   return IMMB_OK;
+  }
 }
 
 // act: the tensor the halo boxes are read from ([N,H,W,act_cs], act_c valid channels); wts: [9][ncols_pad][kd]
@@ -677,7 +704,7 @@ int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const flo
   p.tiles_w = d->W / 8; p.tiles_h = d->H / 16; p.n_img = d->N;
   const int pmode = conv_tc2_pair_mode();
   const bool pair = pmode > 0 && ncols >= (pmode > 1 ? pmode : 1);
-  const int bn = pair ? pair_bn(ncols) : tc_pick_bn(ncols);
+  const int bn = pair ? pair_bn(ncols, passes) : tc_pick_bn(ncols);
   p.n_tiles_n = ceil_div(ncols, bn);
   p.total_tiles = p.tiles_w * p.tiles_h * p.n_img * p.n_tiles_n;
   p.m_tiles = p.tiles_w * p.tiles_h * p.n_img;
@@ -694,6 +721,8 @@ int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const flo
       t.ro = op == 0 ? r : 2 - r;
       t.so = op == 0 ? s : 2 - s;
     }
+  p.n_taps = 9; p.a_sbo = 2048; p.a_plane_bytes = 18 * 16 * 128; p.box_dw = -1; p.box_dh = -1;
+  for (int i = 0; i < 9; ++i) p.a_off[i] = (uint32_t)(p.taps[i].ro * 16 + p.taps[i].so) * 128u;
   p.out_hi = out_hi; p.out_lo = out_lo; p.bias = bias; p.relu = relu;
   p.H = d->H; p.W = d->W; p.ocs = ocs; p.n_cols = ncols; p.n_store = n_store;
   { const char* e = getenv("IMMB_TC2_BO"); p.bo_mode = e ? atoi(e) : 0; }
@@ -739,6 +768,60 @@ int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const flo
   return set_error(IMMB_ERR_INVALID, "conv_tc2: unsupported BN %d", bn);
 }
 
+
+// ---- 7x7 / Cin = 3 first encoder layer on the CTA-pair kernel --------------------------------------------------
+// The staged image [N,H,W+8,4] is read through the overlapping row-window view (conv_tc.cu make_rowwin_map): one
+// 128-byte smem row = the 8 pixels x 4 channels starting at a pixel, so filter row r is ONE K = 32 chunk and needs no
+// column halo.  Tile = 16 rows x 8 columns; ONE box of (16 + 6) window rows x 8 pixels per plane (22.5 KB) serves all
+// seven filter rows through descriptors that start r * 1024 bytes into it (conv_tc_kernel fetched one 16 KB tile per
+// filter row: 5x the L2 -> smem traffic, which was this layer's limiter).
+int tc_make_rowwin_map(CUtensorMap* m, const float* base, int N, int H, int W, int box_w, int box_h, int box_n);
+
+bool conv_tc2_rowwin_eligible(const immb_conv_desc* d) {
+  if (!conv_tc2_enabled() || conv_tc2_pair_mode() <= 0) return false;
+  if (d->x_layout != IMMB_XLAYOUT_ROWWIN4 || d->kh != 7 || d->kw != 7 || d->Cin != 3 || d->stride != 1) return false;
+  if (d->pad_t != 3 || d->pad_l != 3) return false;
+  return d->H % 16 == 0 && d->W % 8 == 0 && d->Cout % 32 == 0 && d->Cout <= 256 && d->y_cstride == d->Cout;
+}
+
+int conv_tc2_rowwin_fwd(const immb_conv_desc* d, const float* x_hi, const float* x_lo, const float* wp_hi,
+                        const float* wp_lo, const float* bias, int relu, float* y_hi, float* y_lo, cudaStream_t st) {
+  const int passes = d->precision == IMMB_PREC_TF32 ? 1 : (d->precision == IMMB_PREC_TF32X2 ? 2 : 3);
+  Tc2Params p;
+  memset(&p, 0, sizeof(p));
+  p.tiles_w = d->W / 8; p.tiles_h = d->H / 16; p.n_img = d->N;
+  const int bn = pair_bn(d->Cout, passes);
+  p.n_tiles_n = ceil_div(d->Cout, bn);
+  p.m_tiles = p.tiles_w * p.tiles_h * p.n_img;
+  p.total_tiles = p.m_tiles * p.n_tiles_n;
+  p.total_pairs = ceil_div(p.m_tiles, 2) * p.n_tiles_n;
+  p.kchunks = 1;
+  p.n_taps = 7; p.a_sbo = 1024; p.a_plane_bytes = 22 * 8 * 128; p.box_dw = 0; p.box_dh = -3;
+  for (int r = 0; r < 7; ++r) { p.taps[r].b_tap = r; p.a_off[r] = (uint32_t)r * 1024u; }
+  p.out_hi = y_hi; p.out_lo = y_lo; p.bias = bias; p.relu = relu;
+  p.H = d->H; p.W = d->W; p.ocs = d->y_cstride; p.n_cols = d->Cout; p.n_store = d->Cout;
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  int rc;
+  if ((rc = tc_make_rowwin_map(&a_hi, x_hi, d->N, d->H, d->W, 8, 22, 1))) return rc;
+  if ((rc = tc_make_w_map(&b_hi, wp_hi, 7, d->Cout, 32, bn / 2))) return rc;
+  a_lo = a_hi; b_lo = b_hi;
+  if (passes >= 2 && (rc = tc_make_rowwin_map(&a_lo, x_lo, d->N, d->H, d->W, 8, 22, 1))) return rc;
+  if (passes == 3 && (rc = tc_make_w_map(&b_lo, wp_lo, 7, d->Cout, 32, bn / 2))) return rc;
+#define IMMB_PCASE(BN_)                                                                  \
+  if (bn == BN_)                                                                         \
+    return passes == 3 ? launch_tc2_pair<BN_, 3>(a_hi, a_lo, b_hi, b_lo, p, st)          \
+         : passes == 2 ? launch_tc2_pair<BN_, 2>(a_hi, a_lo, b_hi, b_lo, p, st)          \
+                       : launch_tc2_pair<BN_, 1>(a_hi, a_lo, b_hi, b_lo, p, st);
+  IMMB_PCASE(32)
+  IMMB_PCASE(64)
+  IMMB_PCASE(96)
+  IMMB_PCASE(128)
+  IMMB_PCASE(160)
+  IMMB_PCASE(192)
+  IMMB_PCASE(256)
+#undef IMMB_PCASE
+  return set_error(IMMB_ERR_INVALID, "conv_tc2 rowwin: unsupported BN %d", bn);
+}
 
 // =============================================================================================================
 // Halo-reuse wgrad for the stride-1 3x3 layers.

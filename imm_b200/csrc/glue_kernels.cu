@@ -476,27 +476,39 @@ __global__ void bn_bwd_apply4_kernel(BnBwdArgs a, int64_t npix, int C, const dou
 }
 
 // out[v] += sum_b partials[b*nvals + v] in a fixed (deterministic) order: 32 partial-block lanes per value (strided
-// over b), then a fixed-order combine through shared memory.  block = (32 values, 32 lanes).
+// over b) with EIGHT independent loads in flight per thread (the kernel is a dependent-L2-load chain otherwise: 69
+// launches per step used to cost 1.1 ms), then a fixed-order combine through shared memory.
+// block = (32 values, 32 lanes).
 __global__ void __launch_bounds__(1024) reduce_partials_kernel(const double* __restrict__ partials, int nblocks, int nvals,
                                                                 double* out) {
   __shared__ double sm[32][33];
   const int v = blockIdx.x * 32 + threadIdx.x;
-  double s0 = 0.0, s1 = 0.0;
+  double s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.0;
   if (v < nvals) {
+    const double* pv = partials + v;
     int b = threadIdx.y;
-    for (; b + 32 < nblocks; b += 64) {
-      s0 += partials[(size_t)b * nvals + v];
-      s1 += partials[(size_t)(b + 32) * nvals + v];
+    for (; b + 7 * 32 < nblocks; b += 8 * 32) {
+      double t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] = __ldcg(pv + (size_t)(b + 32 * j) * nvals);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += t[j];
     }
-    if (b < nblocks) s0 += partials[(size_t)b * nvals + v];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (b + 32 * j < nblocks) s[j] += __ldcg(pv + (size_t)(b + 32 * j) * nvals);
   }
-  sm[threadIdx.y][threadIdx.x] = s0 + s1;
+  sm[threadIdx.y][threadIdx.x] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
   __syncthreads();
   if (threadIdx.y == 0 && v < nvals) {
-    double t = 0.0;
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
 #pragma unroll
-    for (int r = 0; r < 32; ++r) t += sm[r][threadIdx.x];
-    out[v] += t;
+    for (int r = 0; r < 32; r += 4) {
+      t0 += sm[r][threadIdx.x]; t1 += sm[r + 1][threadIdx.x]; t2 += sm[r + 2][threadIdx.x]; t3 += sm[r + 3][threadIdx.x];
+    }
+    out[v] += (t0 + t1) + (t2 + t3);
   }
 }
 
