@@ -231,12 +231,12 @@ def main_cuda(args):
 
   # ---- roofline of the dominant kernel family: one extra step with CUDA events around every C-ABI call --------
   # (single-stream schedule for this one step, so that per-call durations are not inflated by overlapping kernels)
-  saved_streams = (eng.wgrad_stream, eng.pose_stream)
-  eng.wgrad_stream = eng.pose_stream = None
+  saved_streams = (eng.wgrad_stream, eng.pose_stream, eng.gt_stream)
+  eng.wgrad_stream = eng.pose_stream = eng.gt_stream = None
   _lib.PROFILE = []
   step_resident(0)
   torch.cuda.synchronize()
-  eng.wgrad_stream, eng.pose_stream = saved_streams
+  eng.wgrad_stream, eng.pose_stream, eng.gt_stream = saved_streams
   fam = {}
   for name, tag, a, b in _lib.PROFILE:
     fam[name] = fam.get(name, 0.0) + a.elapsed_time(b)
@@ -275,7 +275,7 @@ def main_cuda(args):
           'data': 'synthetic', 'config': workload_config(world), 'tflops_algorithmic': GFLOP_PER_PAIR * B * world / ms,
           'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks, 'e2e': e2e,
           'gpu_launches': int(launches) * world, 'last_loss': loss_val,
-          'streams': {'wgrad_side_stream': eng.wgrad_stream is not None, 'pose_branch_stream': eng.pose_stream is not None,
+          'streams': {'wgrad_side_stream': eng.wgrad_stream is not None, 'pose_branch_stream': eng.pose_stream is not None, 'vgg_gt_half_stream': eng.gt_stream is not None,
                       'input_prefetch_stream': True}}
   print(json.dumps(line))
   sys.stdout.flush()

@@ -51,7 +51,7 @@ _SIGS = {
   'immb_softargmax_gauss_bwd': [_P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _F, _P, _I, _P],
   'immb_gaussian_maps': [_P, _I, _I, _I, _F, _P, _P],
   'immb_vgg_prologue': [_P, _P, _I, _I, _I, _I, _P, _P, _P],
-  'immb_vgg_conv1_1_fused': [_P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _P],
+  'immb_vgg_conv1_1_fused': [_P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P],
   'immb_stage_image_rowwin': [_P, _I, _I, _I, _P, _P, _P],
   'immb_pack_weights_rowwin': [_P, _I, _P, _P, _P],
   'immb_maxpool2x2_fwd': [_P, _P, _I, _I, _I, _I, _P, _P, _P],

@@ -489,6 +489,8 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const int hl = m >> 3, wl = m & 7;
+    const bool vec8 = (p.ocs % 8 == 0) && (p.n_store % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.out_hi) & 31) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(p.out_lo) & 31) == 0);
     uint32_t ti = 0;
     for (int t = tile0; t < n_iter_total; t += tstep) {
       int img, th, tw, n_off;
@@ -522,7 +524,27 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         float* o = p.out_hi + pix * p.ocs + col0;
-        if (p.out_lo) {
+        if (vec8) {
+          // one full 32-byte sector per store
+          if (p.out_lo) {
+            float* ol = p.out_lo + pix * p.ocs + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (col0 + j >= p.n_store) break;
+              float h[8], l[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) split_tf32(v[j + u], h[u], l[u]);
+              st_global_v8(o + j, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+              st_global_v8(ol + j, l[0], l[1], l[2], l[3], l[4], l[5], l[6], l[7]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (col0 + j >= p.n_store) break;
+              st_global_v8(o + j, v[j], v[j + 1], v[j + 2], v[j + 3], v[j + 4], v[j + 5], v[j + 6], v[j + 7]);
+            }
+          }
+        } else if (p.out_lo) {
           float* ol = p.out_lo + pix * p.ocs + col0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -721,19 +743,25 @@ int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const flo
       t.ro = op == 0 ? r : 2 - r;
       t.so = op == 0 ? s : 2 - s;
     }
-  p.n_taps = 9; p.a_sbo = 2048; p.a_plane_bytes = 18 * 16 * 128; p.box_dw = -1; p.box_dh = -1;
-  for (int i = 0; i < 9; ++i) p.a_off[i] = (uint32_t)(p.taps[i].ro * 16 + p.taps[i].so) * 128u;
+  // halo box width: the pair kernel fetches exactly the 8 + 2 columns a tile needs (the descriptors' group stride is
+  // then 10 * 128 B; groups may start anywhere on a 128-byte boundary because both TMA and the MMA unit swizzle on
+  // absolute shared-memory address bits); the single-CTA kernel keeps its 16-pixel box (SBO = 2048 B).
+  static int pair_box_w = -1;
+  if (pair_box_w < 0) { const char* e = getenv("IMMB_TC2_BOXW"); pair_box_w = e ? atoi(e) : 10; }
+  const int box_w = pair ? pair_box_w : 16;
+  p.n_taps = 9; p.a_sbo = box_w * 128; p.a_plane_bytes = 18 * box_w * 128; p.box_dw = -1; p.box_dh = -1;
+  for (int i = 0; i < 9; ++i) p.a_off[i] = (uint32_t)(p.taps[i].ro * box_w + p.taps[i].so) * 128u;
   p.out_hi = out_hi; p.out_lo = out_lo; p.bias = bias; p.relu = relu;
   p.H = d->H; p.W = d->W; p.ocs = ocs; p.n_cols = ncols; p.n_store = n_store;
   { const char* e = getenv("IMMB_TC2_BO"); p.bo_mode = e ? atoi(e) : 0; }
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
   int rc;
-  if ((rc = tc_make_act_map(&a_hi, act_hi, d->N, d->H, d->W, act_c, act_cs, false, 16, 18, 1, 0))) return rc;
+  if ((rc = tc_make_act_map(&a_hi, act_hi, d->N, d->H, d->W, act_c, act_cs, false, box_w, 18, 1, 0))) return rc;
   const int b_box = (cluster || pair) ? bn / 2 : bn;  // cluster / pair mode: each CTA loads half of the rows
   if ((rc = tc_make_w_map(&b_hi, w_hi, 9, w_rows, kd, b_box))) return rc;
   a_lo = a_hi; b_lo = b_hi;
   if (passes >= 2) {
-    if ((rc = tc_make_act_map(&a_lo, act_lo, d->N, d->H, d->W, act_c, act_cs, false, 16, 18, 1, 0))) return rc;
+    if ((rc = tc_make_act_map(&a_lo, act_lo, d->N, d->H, d->W, act_c, act_cs, false, box_w, 18, 1, 0))) return rc;
   }
   if (passes == 3) {
     if ((rc = tc_make_w_map(&b_lo, w_lo, 9, w_rows, kd, b_box))) return rc;

@@ -794,7 +794,7 @@ template <int COUT>
 __global__ void __launch_bounds__(256) vgg_conv1_1_fused_kernel(const float* __restrict__ gt, const float* __restrict__ pred,
                                                                 int pcs, int B, int R, const float* __restrict__ w,
                                                                 const float* __restrict__ bias, float* out_hi,
-                                                                float* out_lo) {
+                                                                float* out_lo, int64_t p_begin, int64_t p_end) {
   constexpr int CG = COUT / 4;
   __shared__ float ws[9][COUT];
   __shared__ float bs[COUT];
@@ -803,7 +803,7 @@ __global__ void __launch_bounds__(256) vgg_conv1_1_fused_kernel(const float* __r
   __syncthreads();
   const int64_t per = (int64_t)B * R * R;
   const int cg = threadIdx.x & 3;                  // channel group
-  for (int64_t p = (int64_t)blockIdx.x * 64 + (threadIdx.x >> 2); p < 2 * per; p += (int64_t)gridDim.x * 64) {
+  for (int64_t p = p_begin + (int64_t)blockIdx.x * 64 + (threadIdx.x >> 2); p < p_end; p += (int64_t)gridDim.x * 64) {
     int wq = (int)(p % R);
     int64_t q = p / R;
     int h = (int)(q % R);
@@ -1456,12 +1456,16 @@ extern "C" int immb_vgg_prologue(const float* gt, const float* pred, int pcs, in
 }
 
 extern "C" int immb_vgg_conv1_1_fused(const float* gt, const float* pred, int pcs, int B, int R, const float* w,
-                                      const float* bias, int Cout, float* out_hi, float* out_lo, void* stream) {
-  IMMB_REQUIRE(gt && pred && w && bias && out_hi && pcs >= 3, "vgg_conv1_1_fused: bad args");
+                                      const float* bias, int Cout, float* out_hi, float* out_lo, int which,
+                                      void* stream) {
+  IMMB_REQUIRE(w && bias && out_hi && pcs >= 3 && which >= 0 && which <= 2, "vgg_conv1_1_fused: bad args");
+  IMMB_REQUIRE((which == 2 || gt) && (which == 1 || pred), "vgg_conv1_1_fused: missing input for the requested half");
   IMMB_REQUIRE(Cout == 64, "vgg_conv1_1_fused: Cout must be 64 (VGG16 conv1_1)");
-  int64_t blocks = ((int64_t)2 * B * R * R + 63) / 64;
+  const int64_t per = (int64_t)B * R * R;
+  const int64_t p0 = which == 2 ? per : 0, p1 = which == 1 ? per : 2 * per;
+  int64_t blocks = (p1 - p0 + 63) / 64;
   if (blocks > (int64_t)kNumSMs * 32) blocks = (int64_t)kNumSMs * 32;
-  vgg_conv1_1_fused_kernel<64><<<(int)blocks, 256, 0, ST(stream)>>>(gt, pred, pcs, B, R, w, bias, out_hi, out_lo);
+  vgg_conv1_1_fused_kernel<64><<<(int)blocks, 256, 0, ST(stream)>>>(gt, pred, pcs, B, R, w, bias, out_hi, out_lo, p0, p1);
   return check_launch("vgg_conv1_1_fused");
 }
 

@@ -226,6 +226,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 256-bit global store (sm_100+, SASS STG.E.ENL2.256): one full 32-byte sector per thread.  The conv epilogues own
+// one pixel row per thread (lanes are a whole pixel apart), so a 128-bit store fills only half a sector per lane and
+// L2 sees twice the write transactions.
+__device__ __forceinline__ void st_global_v8(float* p, float a0, float a1, float a2, float a3, float a4, float a5,
+                                             float a6, float a7) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a0), "f"(a1), "f"(a2), "f"(a3),
+               "f"(a4), "f"(a5), "f"(a6), "f"(a7)
+               : "memory");
+}
+
 // ---- descriptors (bit layouts: cute/arch/mma_sm100_desc.hpp) ---------------------------------------------
 // Shared-memory matrix descriptor, SWIZZLE_128B.  addr: smem byte address of the (1024B-aligned) tile start
 // (+ k advance); lbo / sbo in bytes.

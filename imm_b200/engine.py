@@ -166,12 +166,15 @@ class IMMEngine(object):
     # Stream-level concurrency of INDEPENDENT work (no arithmetic changes, same kernels, same results):
     #   bit 0: every weight-gradient conv runs on a side stream (dw is only needed by the optimiser), so the HBM-bound
     #          BN-backward kernels of the next layer overlap the tensor-bound wgrad kernels;
-    #   bit 1: the pose-encoder branch (forward and backward) runs on its own stream next to the image-encoder branch.
+    #   bit 1: the pose-encoder branch (forward and backward) runs on its own stream next to the image-encoder branch;
+    #   bit 2: the ground-truth half of the frozen VGG16 tower (features of future_image, which depend on the input
+    #          batch alone) runs on its own stream next to the encoders / renderer; the predicted half follows the renderer.
     if streams is None:
-      streams = int(os.environ.get('IMMB_STREAMS', '3'))
+      streams = int(os.environ.get('IMMB_STREAMS', '3'))   # bit 2 measured: no gain at batch 64 (20.19 vs 20.15 ms) -> off by default
     self.streams = int(streams)
     self.wgrad_stream = torch.cuda.Stream(device=self.dev) if self.streams & 1 else None
     self.pose_stream = torch.cuda.Stream(device=self.dev) if self.streams & 2 else None
+    self.gt_stream = torch.cuda.Stream(device=self.dev) if self.streams & 4 else None
     self._events = {}
 
   # ------------------------------------------------------------------------------------------------
@@ -530,6 +533,12 @@ class IMMEngine(object):
       raise RuntimeError('No loss mask recieved but is required.')      # imm_model.py:363-367
     self.training = training
     self.fwd_pool.zero_()
+    self._gt_tower_forked = False
+    if self.gt_stream is not None and build_loss and self.vgg_loaded and self.engine != _lib.ENGINE_SIMT:
+      self._fork(self.gt_stream, 'gt_fork')
+      with torch.cuda.stream(self.gt_stream):
+        self._vgg_tower(0)
+      self._gt_tower_forked = True
     # image encoder (imm_model.py:220-230) and pose encoder (:233-248)
     def run_encoder(enc, inp, scratch):
       st_ = _lib.stream_ptr()
@@ -574,31 +583,46 @@ class IMMEngine(object):
       self._loss_fwd(training)
     return self.pred
 
+  def _vgg_tower(self, which):
+    """build_vgg16 (build_vgg16.py:14-35) + vgg16.build_network (vgg16.py:289-375) on [future_image ; pred].
+    which: None = both halves as one batch of 2B, 0 = ground-truth half only, 1 = predicted half only."""
+    st = _lib.stream_ptr()
+    B, R = self.B, self.R
+    n = 2 * B if which is None else B
+    sel = (lambda P: P) if which is None else (lambda P: P.half(which, B))
+    fused_first = self.engine != _lib.ENGINE_SIMT
+    if not fused_first:
+      assert which is None
+      call('immb_vgg_prologue', self.future_image, self.pred, self.pcs, B, R, 1, self.vgg_in.hi, self.vgg_in.lo, st)
+    X = self.vgg_in
+    for kind, item, cin, size in self.vgg_seq:
+      if kind == 'conv':
+        _lib.TAG = 'fwd:vgg/%s' % item.name
+        out = sel(item.out)
+        if item.name == 'conv1_1' and fused_first:
+          # Cin = 1: HBM-bound, exact-fp32 CUDA-core kernel straight from the RGB inputs (no patch tensor)
+          call('immb_vgg_conv1_1_fused', self.future_image, None if which == 0 else self.pred, self.pcs, B, R,
+               item.w, item.b, item.cout, item.out.hi, item.out.lo, 0 if which is None else which + 1, st)
+        else:
+          self._conv_fwd(item, X, out.hi, out.lo, N=n)
+        X = out
+      else:
+        O = sel(self.vgg_act[item])
+        call('immb_maxpool2x2_fwd', X.hi, X.lo, n, size, size, cin, O.hi, O.lo, st)
+        X = O
+
   def _loss_fwd(self, training):
     """_colorization_reconstruction_loss (imm_model.py:111-151) + build_vgg16 (build_vgg16.py:14-35)."""
     if not self.vgg_loaded:
       raise _lib.ImmbError('VGG16 weights not loaded (load_vgg_caffe_dict)')
     st = _lib.stream_ptr()
     B, R = self.B, self.R
-    fused_first = self.engine != _lib.ENGINE_SIMT
-    if not fused_first:
-      call('immb_vgg_prologue', self.future_image, self.pred, self.pcs, B, R, 1, self.vgg_in.hi, self.vgg_in.lo, st)
-    X = self.vgg_in
-    for kind, item, cin, size in self.vgg_seq:
-      if kind == 'conv':
-        item.x = X
-        _lib.TAG = 'fwd:vgg/%s' % item.name
-        if item.name == 'conv1_1' and fused_first:
-          # Cin = 1: HBM-bound, exact-fp32 CUDA-core kernel straight from the RGB inputs (no patch tensor)
-          call('immb_vgg_conv1_1_fused', self.future_image, self.pred, self.pcs, B, R, item.w, item.b, item.cout,
-               item.out.hi, item.out.lo, st)
-        else:
-          self._conv_fwd(item, X, item.out.hi, item.out.lo)
-        X = item.out
-      else:
-        O = self.vgg_act[item]
-        call('immb_maxpool2x2_fwd', X.hi, X.lo, 2 * B, size, size, cin, O.hi, O.lo, st)
-        X = O
+    if self._gt_tower_forked:
+      self._vgg_tower(1)                               # predicted half; the gt half was forked at the top of forward()
+      self._join(self.gt_stream, 'gt_join')
+      self._gt_tower_forked = False
+    else:
+      self._vgg_tower(None)
     for k, nm in enumerate(self.comp):
       if nm == 'input':
         call('immb_perceptual_level_sum', self.future_image, None, 3, self.pred, None, self.pcs, B, R, R, 3,

@@ -174,9 +174,11 @@ int immb_vgg_prologue(const float* gt, const float* pred, int pred_cstride, int 
                       float* out_hi, float* out_lo, void* stream);
 /* VGG conv1_1 fused with the prologue (vgg16.py:182-230 on build_vgg16.py:22-26): out[2B,R,R,Cout] split planes =
  * relu(conv3x3_SAME(gray([gt ; pred])) + b), w [3,3,1,Cout] HWIO.  Cin = 1 makes this layer HBM-bound (it writes
- * 2*Cout*4 bytes per pixel), so it runs on the CUDA cores in exact fp32 straight from the RGB inputs. */
+ * 2*Cout*4 bytes per pixel), so it runs on the CUDA cores in exact fp32 straight from the RGB inputs.
+ * which: 0 = both halves, 1 = only the gt half (images [0,B) of out; pred may be NULL), 2 = only the pred half
+ * (images [B,2B) of out; gt may be NULL) -- the gt half depends on the input batch alone and can run on its own stream. */
 int immb_vgg_conv1_1_fused(const float* gt, const float* pred, int pred_cstride, int B, int R, const float* w,
-                           const float* bias, int Cout, float* out_hi, float* out_lo, void* stream);
+                           const float* bias, int Cout, float* out_hi, float* out_lo, int which, void* stream);
 /* 2x2/2 max pool on split planes [N,H,W,C] -> [N,H/2,W/2,C] split planes */
 int immb_maxpool2x2_fwd(const float* x_hi, const float* x_lo, int N, int H, int W, int C, float* o_hi,
                         float* o_lo, void* stream);

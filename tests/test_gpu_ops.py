@@ -411,8 +411,14 @@ def test_vgg_conv1_1_fused():
   ref = torch.relu(O.conv2d_same(gray, w.double(), b.double(), 1))
   dev = 'cuda'
   oh, ol = torch.empty(2 * B, R, R, 64, device=dev), torch.empty(2 * B, R, R, 64, device=dev)
-  call('immb_vgg_conv1_1_fused', gt.to(dev), pred12.to(dev), 12, B, R, w.to(dev), b.to(dev), 64, oh, ol, ST())
+  call('immb_vgg_conv1_1_fused', gt.to(dev), pred12.to(dev), 12, B, R, w.to(dev), b.to(dev), 64, oh, ol, 0, ST())
   assert rel_err(oh + ol, ref) < 1e-5
+  # the two halves separately (the gt half runs on its own stream in the engine) write the same bits
+  oh2, ol2 = torch.full_like(oh, float('nan')), torch.full_like(ol, float('nan'))
+  call('immb_vgg_conv1_1_fused', gt.to(dev), None, 12, B, R, w.to(dev), b.to(dev), 64, oh2, ol2, 1, ST())
+  assert torch.equal(oh2[:B], oh[:B]) and bool(torch.isnan(oh2[B:]).all())
+  call('immb_vgg_conv1_1_fused', None, pred12.to(dev), 12, B, R, w.to(dev), b.to(dev), 64, oh2, ol2, 2, ST())
+  assert torch.equal(oh2, oh) and torch.equal(ol2, ol)
 
 
 def test_first_layer_rowwin_tcgen05():

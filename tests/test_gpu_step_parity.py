@@ -150,16 +150,17 @@ def test_two_steps_track_oracle():
 
 
 def test_stream_overlap_does_not_change_results():
-  """IMMEngine(streams=3) runs the weight-gradient convs and the pose-encoder branch on side streams; the kernels
-  and their inputs are the same, so two steps must give the same state as the single-stream schedule (everything
+  """IMMEngine(streams=7) runs the weight-gradient convs, the pose-encoder branch and the ground-truth half of the VGG
+  tower on side streams; the kernels and their inputs are the same, so two steps must give the same state as the single-stream schedule (everything
   except the split-K `red.add` accumulated weight gradients is bit-identical)."""
   from imm_b200.engine import IMMEngine
   from imm_b200.utils.box import default_model_config
   from imm_b200.utils.synthetic import synthetic_inputs, synthetic_vgg_caffe_dict
   res = []
-  for streams in (0, 3):
+  for streams in (0, 7):
     eng = IMMEngine(default_model_config(10), 4, 128, 'cuda:0', streams=streams)
     assert (eng.wgrad_stream is not None) == bool(streams & 1) and (eng.pose_stream is not None) == bool(streams & 2)
+    assert (eng.gt_stream is not None) == bool(streams & 4)
     eng.init_parameters(3)
     eng.load_vgg_caffe_dict(synthetic_vgg_caffe_dict(1))
     for i in range(2):

@@ -32,7 +32,7 @@ print('bwd %.2f ms' % timed(lambda: eng.backward()))
 print('opt %.2f ms' % timed(lambda: eng.optimizer_step()))
 
 # per-call attribution (CUDA events around every C-ABI call), single-stream schedule so that calls do not overlap
-eng.wgrad_stream = eng.pose_stream = None
+eng.wgrad_stream = eng.pose_stream = eng.gt_stream = None
 _lib.PROFILE = []
 eng.train_step(inp['image'], inp['future_image'], inp['mask'])
 torch.cuda.synchronize()
