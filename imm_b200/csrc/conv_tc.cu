@@ -199,7 +199,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
       }
       float* o = p.out_hi + pix * p.ocs + col0;
-      if (p.out_lo) {
+      const bool vec8 = (p.ocs % 8 == 0) && (p.n_store % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.out_hi) & 31) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.out_lo) & 31) == 0);
+      if (vec8) {
+        // one full 32-byte sector per store (thread = pixel row: 128-bit stores fill half a sector per lane)
+        float* ol = p.out_lo ? p.out_lo + pix * p.ocs + col0 : nullptr;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          if (col0 + j >= p.n_store) break;
+          if (ol) {
+            float h[8], l[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) split_tf32(v[j + u], h[u], l[u]);
+            st_global_v8(o + j, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+            st_global_v8(ol + j, l[0], l[1], l[2], l[3], l[4], l[5], l[6], l[7]);
+          } else {
+            st_global_v8(o + j, v[j], v[j + 1], v[j + 2], v[j + 3], v[j + 4], v[j + 5], v[j + 6], v[j + 7]);
+          }
+        }
+      } else if (p.out_lo) {
         float* ol = p.out_lo + pix * p.ocs + col0;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -398,9 +416,15 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_c
       const int col0 = n_off + c0;
       if (col0 >= p.Cout) continue;
       float* o = p.dw + row_off + col0;
+if ((p.Cout & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dw) & 15) == 0) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < p.Cout) atomicAdd(o + j, v[j]);
+          for (int j = 0; j < 32; j += 4)
+            if (col0 + j < p.Cout) red_add_v4(o + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.Cout) atomicAdd(o + j, v[j]);
+        }
     }
   }
   tc_fence_before();

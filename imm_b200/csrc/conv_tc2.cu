@@ -1002,9 +1002,15 @@ conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_
         const int col0 = n_off + c0;
         if (col0 >= p.Cout) continue;
         float* o = p.dw + ((size_t)(r * 3 + s) * p.Cin + ci) * p.Cout + col0;
+if ((p.Cout & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dw) & 15) == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < p.Cout) atomicAdd(o + j, v[j]);
+          for (int j = 0; j < 32; j += 4)
+            if (col0 + j < p.Cout) red_add_v4(o + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.Cout) atomicAdd(o + j, v[j]);
+        }
       }
     }
   }
@@ -1050,7 +1056,11 @@ int conv_tc2_wgrad_run(const immb_conv_desc* d, const float* x_hi, const float* 
   const int bn = d->Cout % 128 == 0 ? 128 : (d->Cout % 64 == 0 ? 64 : 32);
   const int n_tiles = ceil_div(d->Cout, bn);
   const int c_tiles = d->cin_pad / 32;
-  int splits = ceil_div(kNumSMs * 2, c_tiles * n_tiles);
+  // split-K factor: the grid must not exceed a whole number of waves (1 CTA per SM: 19 splits x 16 tiles = 304 CTAs
+  // used to run as 148 + 148 + 8, a third round for 3 % of the work)
+  static int wg_waves = -1;
+  if (wg_waves < 0) { const char* e = getenv("IMMB_WG_WAVES"); wg_waves = e ? atoi(e) : 1; if (wg_waves < 1) wg_waves = 1; }
+  int splits = (kNumSMs * wg_waves) / (c_tiles * n_tiles);
   if (splits > p.total_tiles) splits = p.total_tiles;
   if (splits < 1) splits = 1;
   p.tiles_per_split = ceil_div(p.total_tiles, splits);

@@ -236,6 +236,12 @@ __device__ __forceinline__ void st_global_v8(float* p, float a0, float a1, float
                : "memory");
 }
 
+// 128-bit reduction (sm_90+, SASS REDG.E.ADD.F32x4): four fp32 adds in ONE L2 atomic transaction -- the split-K wgrad
+// epilogues issue a quarter of the reduction traffic of scalar atomicAdd.  16-byte aligned address.
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // ---- descriptors (bit layouts: cute/arch/mma_sm100_desc.hpp) ---------------------------------------------
 // Shared-memory matrix descriptor, SWIZZLE_128B.  addr: smem byte address of the (1024B-aligned) tile start
 // (+ k advance); lbo / sbo in bytes.
