@@ -65,6 +65,7 @@ _SIGS = {
   'immb_tps_warp': [_P, _I, _I, _I, _I, _P, _I, _I, _P, _P],
   'immb_adam_norms': [_P, _P, _L, _P, _P, _P, _I, _P, _F, _P, _P, _P],
   'immb_adam_apply': [_P, _P, _P, _P, _L, _P, _P, _P, _I, _P, _F, _P, _F, _F, _F, _F, _F, _P],
+  'immb_adam_apply_dev': [_P, _P, _P, _P, _L, _P, _P, _P, _I, _P, _F, _P, _F, _P, _F, _F, _F, _P],
   'immb_total_loss': [_P, _P, _P, _I, _P, _P, _P],
   'immb_crc32c': [_P, _Z, ctypes.c_uint32],
 }

@@ -1138,7 +1138,8 @@ __global__ void adam_apply_kernel(float* p, const float* __restrict__ g, float* 
                                   const int32_t* __restrict__ chunk_tensor, const int64_t* __restrict__ chunk_off,
                                   const int32_t* __restrict__ chunk_len, const float* __restrict__ tensor_wd,
                                   float gscale, const double* __restrict__ sq, float clip, float lr_t,
-                                  float beta1, float beta2, float eps) {
+                                  float beta1, float beta2, float eps, const float* __restrict__ lr_t_dev) {
+  if (lr_t_dev) lr_t = __ldg(lr_t_dev);          // CUDA-graph replays: the step-dependent scalar lives in device memory
   int ch = blockIdx.x;
   int t = chunk_tensor[ch];
   int64_t off = chunk_off[ch];
@@ -1601,8 +1602,19 @@ extern "C" int immb_adam_apply(float* p, const float* g, float* m, float* v, int
   IMMB_REQUIRE(p && g && m && v && chunk_tensor && chunk_off && chunk_len && tensor_wd && sq && n_chunks > 0,
                "adam_apply: bad args");
   adam_apply_kernel<<<n_chunks, 256, 0, ST(stream)>>>(p, g, m, v, chunk_tensor, chunk_off, chunk_len,
-                                                      tensor_wd, gscale, sq, clip, lr_t, beta1, beta2, eps);
+                                                      tensor_wd, gscale, sq, clip, lr_t, beta1, beta2, eps, nullptr);
   return check_launch("adam_apply");
+}
+
+extern "C" int immb_adam_apply_dev(float* p, const float* g, float* m, float* v, int64_t n,
+                                   const int32_t* chunk_tensor, const int64_t* chunk_off, const int32_t* chunk_len,
+                                   int n_chunks, const float* tensor_wd, float gscale, const double* sq, float clip,
+                                   const float* lr_t_dev, float beta1, float beta2, float eps, void* stream) {
+  IMMB_REQUIRE(p && g && m && v && chunk_tensor && chunk_off && chunk_len && tensor_wd && sq && n_chunks > 0 && lr_t_dev,
+               "adam_apply_dev: bad args");
+  adam_apply_kernel<<<n_chunks, 256, 0, ST(stream)>>>(p, g, m, v, chunk_tensor, chunk_off, chunk_len,
+                                                      tensor_wd, gscale, sq, clip, 0.f, beta1, beta2, eps, lr_t_dev);
+  return check_launch("adam_apply_dev");
 }
 
 extern "C" int immb_total_loss(const float* rec_loss, const double* wsq, const float* tensor_wd, int n_tensors,

@@ -130,7 +130,7 @@ class IMMEngine(object):
   channels_bug_fix, perceptual.comp, reconstruction_loss, perceptual.l2."""
 
   def __init__(self, config, batch, image_size=128, device='cuda:0', precision=_lib.PREC_TF32X3,
-               engine=_lib.ENGINE_AUTO, world_size=1, vgg_tf32_weights=True, streams=None):
+               engine=_lib.ENGINE_AUTO, world_size=1, vgg_tf32_weights=True, streams=None, use_graph=None):
     if not torch.cuda.is_available():
       raise _lib.ImmbError('IMMEngine needs a CUDA device; there is no CPU fallback')
     _lib.lib()
@@ -175,6 +175,10 @@ class IMMEngine(object):
     self.wgrad_stream = torch.cuda.Stream(device=self.dev) if self.streams & 1 else None
     self.pose_stream = torch.cuda.Stream(device=self.dev) if self.streams & 2 else None
     self.gt_stream = torch.cuda.Stream(device=self.dev) if self.streams & 4 else None
+    # CUDA-graph replay of the training step (train_step only; forward / backward / optimizer_step stay eager)
+    self.use_graph = bool(int(os.environ.get('IMMB_GRAPH', '1'))) if use_graph is None else bool(use_graph)
+    self._graphs, self._graph_key, self._graph_warm = None, None, 0
+    self.graph_replays, self.graph_launches_per_step = 0, 0
     self._events = {}
 
   # ------------------------------------------------------------------------------------------------
@@ -771,36 +775,109 @@ class IMMEngine(object):
   def learning_rate(self, start_val=1e-3, step=100000, decay=0.95, lr_multiple=1.0):
     return lr_multiple * start_val * decay ** math.floor(self.global_step / float(step))
 
-  def optimizer_step(self, clip_value=1.0, lr=None, beta1=0.9, beta2=0.999, eps=1e-8, allreduce=None):
-    """mean over replicas (one all-reduce on the flat gradient buffer) -> +wd*w -> per-tensor clip_by_norm
-    -> TF Adam -> repack the tensor-core weight planes.  Also produces the total loss value."""
+  def _optimizer_kernels(self, clip_value, lr_t, beta1, beta2, eps, lr_t_dev=None):
+    """+wd*w -> per-tensor clip_by_norm -> TF Adam -> repack the tensor-core weight planes; total loss value."""
     st = _lib.stream_ptr()
-    if allreduce is not None:
-      allreduce(self.flat_g)
     gscale = 1.0 / float(self.world_size)
-    if lr is None:
-      lr = self.learning_rate()
-    self.adam_t += 1
-    lr_t = lr * math.sqrt(1.0 - beta2 ** self.adam_t) / (1.0 - beta1 ** self.adam_t)
+    clip = float(clip_value) if clip_value is not None else 0.0
     self.sq.zero_()
     nt = self.n_tensors
     call('immb_adam_norms', self.flat_p, self.flat_g, self.n_flat, self.chunk_tensor, self.chunk_off,
          self.chunk_len, self.n_chunks, self.tensor_wd, gscale, self.sq, self.sq[nt:], st)
     call('immb_total_loss', self.rec_loss, self.sq[nt:], self.tensor_wd, nt, self.weights_loss, self.total_loss, st)
-    call('immb_adam_apply', self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.n_flat, self.chunk_tensor,
-         self.chunk_off, self.chunk_len, self.n_chunks, self.tensor_wd, gscale, self.sq,
-         float(clip_value) if clip_value is not None else 0.0, lr_t, beta1, beta2, eps, st)
+    if lr_t_dev is None:
+      call('immb_adam_apply', self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.n_flat, self.chunk_tensor,
+           self.chunk_off, self.chunk_len, self.n_chunks, self.tensor_wd, gscale, self.sq, clip, lr_t, beta1, beta2,
+           eps, st)
+    else:
+      call('immb_adam_apply_dev', self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.n_flat, self.chunk_tensor,
+           self.chunk_off, self.chunk_len, self.n_chunks, self.tensor_wd, gscale, self.sq, clip, lr_t_dev, beta1,
+           beta2, eps, st)
     self.repack_weights()
-    self.global_step += 1.0
-    self.last_lr = lr
-    return lr
 
-  def train_step(self, image, future_image, mask=None, clip_value=1.0, lr_multiple=1.0, allreduce=None):
-    """One iteration of train_loop's hot loop (cnn_train_multi.py:445-460): fwd + loss + bwd + update."""
+  def _next_lr_t(self, lr, beta1, beta2):
+    if lr is None:
+      lr = self.learning_rate()
+    self.adam_t += 1
+    self.last_lr = lr
+    return lr * math.sqrt(1.0 - beta2 ** self.adam_t) / (1.0 - beta1 ** self.adam_t)
+
+  def optimizer_step(self, clip_value=1.0, lr=None, beta1=0.9, beta2=0.999, eps=1e-8, allreduce=None):
+    """mean over replicas (one all-reduce on the flat gradient buffer) -> +wd*w -> per-tensor clip_by_norm
+    -> TF Adam -> repack the tensor-core weight planes.  Also produces the total loss value."""
+    if allreduce is not None:
+      allreduce(self.flat_g)
+    lr_t = self._next_lr_t(lr, beta1, beta2)
+    self._optimizer_kernels(clip_value, lr_t, beta1, beta2, eps)
+    self.global_step += 1.0
+    return self.last_lr
+
+  def train_step(self, image, future_image, mask=None, clip_value=1.0, lr_multiple=1.0, allreduce=None, lr=None,
+                 beta1=0.9, beta2=0.999, eps=1e-8):
+    """One iteration of train_loop's hot loop (cnn_train_multi.py:445-460): fwd + loss + bwd + update.
+    With use_graph the whole step (3 streams, ~370 launches) is captured once into CUDA graphs and replayed: inputs are
+    copied into static buffers, the step-dependent Adam scalar is refreshed in device memory, and (N > 1) the NCCL
+    all-reduce runs between the forward+backward graph and the optimiser graph."""
+    if lr is None:
+      lr = self.learning_rate(lr_multiple=lr_multiple)
+    if self.use_graph:
+      key = (None if clip_value is None else float(clip_value), beta1, beta2, eps, allreduce is not None,
+             mask is not None)
+      if self._graphs is not None and self._graph_key != key:
+        self._graphs = None                                     # hyper-parameters baked into the graph changed
+      if self._graphs is None and self._graph_warm >= 2:
+        self._capture_graphs(key, image, future_image, mask)
+      if self._graphs is not None:
+        self.g_image.copy_(image, non_blocking=True)
+        self.g_future.copy_(future_image, non_blocking=True)
+        if mask is not None:
+          self.g_mask.copy_(mask, non_blocking=True)
+        self.d_lr_t.fill_(self._next_lr_t(lr, beta1, beta2))    # by-value upload: no host buffer to race with
+        g_fb, g_opt = self._graphs
+        g_fb.replay()
+        if g_opt is not None:
+          allreduce(self.flat_g)
+          g_opt.replay()
+        self.global_step += 1.0
+        self.graph_replays += 1
+        return self.total_loss
+      self._graph_warm += 1          # eager warm-up steps: kernel attributes configured, events created
     self.forward(image, future_image, mask, training=True, build_loss=True)
     self.backward()
-    self.optimizer_step(clip_value, lr=self.learning_rate(lr_multiple=lr_multiple), allreduce=allreduce)
+    self.optimizer_step(clip_value, lr=lr, beta1=beta1, beta2=beta2, eps=eps, allreduce=allreduce)
     return self.total_loss
+
+  def _capture_graphs(self, key, image, future_image, mask):
+    clip_value, beta1, beta2, eps, has_allreduce, has_mask = key
+    dev = self.dev
+    self.g_image = torch.empty_like(image, device=dev)
+    self.g_future = torch.empty_like(future_image, device=dev)
+    self.g_mask = torch.empty_like(mask, device=dev) if has_mask else None
+    self.g_image.copy_(image)
+    self.g_future.copy_(future_image)
+    if has_mask:
+      self.g_mask.copy_(mask)
+    self.d_lr_t = torch.zeros(1, dtype=torch.float32, device=dev)
+    torch.cuda.synchronize(dev)
+    saved = (self.flat_p.clone(), self.flat_m.clone(), self.flat_v.clone(), self.flat_bn.clone(), self.agg.clone())
+    cap = torch.cuda.Stream(device=dev)
+    g_fb, g_opt = torch.cuda.CUDAGraph(), None
+    n0 = _lib.launch_count()
+    with torch.cuda.graph(g_fb, stream=cap):
+      self.forward(self.g_image, self.g_future, self.g_mask, training=True, build_loss=True)
+      self.backward()
+      if not has_allreduce:
+        self._optimizer_kernels(clip_value, 0.0, beta1, beta2, eps, lr_t_dev=self.d_lr_t)
+    if has_allreduce:
+      g_opt = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(g_opt, stream=cap):
+        self._optimizer_kernels(clip_value, 0.0, beta1, beta2, eps, lr_t_dev=self.d_lr_t)
+    torch.cuda.synchronize(dev)
+    # capture does not execute anything, but be explicit that model state is exactly what it was
+    for dst, src in zip((self.flat_p, self.flat_m, self.flat_v, self.flat_bn, self.agg), saved):
+      dst.copy_(src)
+    self._graphs, self._graph_key = (g_fb, g_opt), key
+    self.graph_launches_per_step = _lib.launch_count() - n0     # kernels recorded into the graphs (= launched per replay)
 
   # ------------------------------------------------------------------------------------------------
   # introspection

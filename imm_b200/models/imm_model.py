@@ -120,6 +120,26 @@ class IMMModel(BaseModel):
       return None, loss, self._avg_ops, tensors
     return None, loss, self._avg_ops
 
+  def train_step(self, inputs, clip_value=None, lr=None, beta1=0.9, beta2=0.999, eps=1e-8, allreduce=None):
+    """build(inputs, training_pl=True) + backward + clip/Adam as ONE engine call (what session.run(train_op) executes,
+    cnn_train_multi.py:445-460), so that the engine can replay it as a CUDA graph.  Returns the loss (CUDA scalar)."""
+    im, future_im = inputs['image'], inputs['future_image']
+    B, R = int(future_im.shape[0]), int(future_im.shape[1])
+    eng = self._ensure_engine(B, R)
+    dev = eng.dev
+    im_d, fut_d = self._to_device(im, dev), self._to_device(future_im, dev)
+    mask_d = self._to_device(inputs['mask'], dev) if 'mask' in inputs else None
+    if bool(self._config.loss_mask) and mask_d is None:
+      raise RuntimeError('No loss mask recieved but is required.')     # imm_model.py:363-367
+    loss = eng.train_step(im_d, fut_d, mask_d, clip_value=clip_value, lr=lr, beta1=beta1, beta2=beta2, eps=eps,
+                          allreduce=allreduce)
+    if not self._avg_ops:
+      self._add_cost_summary(lambda: eng.rec_loss.item(), 'reconstruction_loss')     # imm_model.py:390
+      self._add_cost_summary(lambda: eng.weights_loss.item(), 'weights_loss')        # :396
+      self._add_cost_summary(lambda: eng.total_loss.item(), 'loss_total')            # :402
+    self._tensors = {'heatmaps': eng.pose_conv.y[..., :eng.K], 'gauss_y_prob': eng.py, 'gauss_x_prob': eng.px}
+    return loss.view(())
+
   def get_collection(self, name='tensors'):
     return dict(self._tensors)
 

@@ -117,15 +117,12 @@ def _make_train_op(model, optim, inputs_fn, clip_value):
     if pf is None:
       pf = state['pf'] = _InputPrefetcher(inputs_fn, model._device)
     inputs = pf.next()
-    model.build(inputs, True)
-    eng = model.engine
-    eng.backward()
-    eng.optimizer_step(clip_value, lr=optim.lr(eng.global_step), beta1=optim.beta1, beta2=optim.beta2,
-                       eps=optim.epsilon, allreduce=average_gradients if eng.world_size > 1 else None)
+    gs = model.engine.global_step if model.engine is not None else float(model._global_step if model._global_step is not None else -1)
+    world = model.engine.world_size if model.engine is not None else model._world
+    loss = model.train_step(inputs, clip_value, lr=optim.lr(gs), beta1=optim.beta1, beta2=optim.beta2, eps=optim.epsilon,
+                            allreduce=average_gradients if world > 1 else None)
     pf.prefetch()                  # next batch's H2D overlaps this step's kernels (the host is ahead of the GPU here)
-    for op in model._avg_ops:
-      pass                       # cost EMAs are evaluated lazily by the logger (they need a D2H read)
-    return eng.total_loss
+    return loss        # cost EMAs (model._avg_ops) are evaluated lazily by the logger: they need a D2H read
   return train_op
 
 

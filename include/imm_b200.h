@@ -236,6 +236,13 @@ int immb_adam_apply(float* p, const float* g, float* m, float* v, int64_t n, con
                     const int64_t* chunk_off, const int32_t* chunk_len, int n_chunks, const float* tensor_wd,
                     float gscale, const double* sq, float clip, float lr_t, float beta1, float beta2,
                     float eps, void* stream);
+/* Same update with the step-dependent scalar lr_t = lr*sqrt(1-beta2^t)/(1-beta1^t) read from device memory, so that a
+ * captured CUDA graph of the whole training step can be replayed every iteration (the host refreshes lr_t_dev[0] with
+ * one 4-byte async copy before each replay). */
+int immb_adam_apply_dev(float* p, const float* g, float* m, float* v, int64_t n, const int32_t* chunk_tensor,
+                        const int64_t* chunk_off, const int32_t* chunk_len, int n_chunks, const float* tensor_wd,
+                        float gscale, const double* sq, float clip, const float* lr_t_dev, float beta1, float beta2,
+                        float eps, void* stream);
 /* total = rec_loss[0] + sum_t 0.5*wd_t*wsq[t]  (imm_model.py:395-400, base_model.py:33-37) */
 int immb_total_loss(const float* rec_loss, const double* wsq, const float* tensor_wd, int n_tensors,
                     float* weights_loss, float* total, void* stream);

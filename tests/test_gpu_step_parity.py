@@ -180,3 +180,39 @@ def test_stream_overlap_does_not_change_results():
   # second step: the first TF-Adam update is lr * sign(g) (m/sqrt(v) = +-1), so summation-order noise on near-zero
   # gradient components legitimately flips a few updates by 2*lr; the loss agrees to the level that implies
   assert abs(float(l0) - float(l1)) <= 1e-3 * abs(float(l0))
+
+
+def test_cuda_graph_replay_matches_eager_steps():
+  """IMMEngine.train_step captures the whole step (3 streams) into CUDA graphs after two eager steps and replays it;
+  the learning-rate scalar is refreshed in device memory.  Five steps with changing inputs and a changing learning rate
+  must track the eager engine (bit-identical forward on the first replayed step given identical parameters is not
+  expected because split-K `red.add` weight gradients differ in summation order from run to run)."""
+  from imm_b200.engine import IMMEngine
+  from imm_b200.utils.box import default_model_config
+  from imm_b200.utils.synthetic import synthetic_inputs, synthetic_vgg_caffe_dict
+  res = []
+  for use_graph in (False, True):
+    eng = IMMEngine(default_model_config(10), 4, 128, 'cuda:0', use_graph=use_graph)
+    eng.init_parameters(5)
+    eng.load_vgg_caffe_dict(synthetic_vgg_caffe_dict(1))
+    losses = []
+    for i in range(5):
+      d = to_dev(synthetic_inputs(4, 128, seed=i))
+      loss = eng.train_step(d['image'], d['future_image'], d['mask'], clip_value=1.0, lr=1e-3 * (0.5 ** i))
+      losses.append(float(loss.item()))
+    assert (eng._graphs is not None) == use_graph
+    if use_graph:
+      assert eng.graph_replays == 3 and eng.graph_launches_per_step > 300
+    assert eng.adam_t == 5 and eng.global_step == 4.0
+    res.append((losses, eng.flat_p.clone(), eng.flat_bn.clone(), eng.mu.clone()))
+  (l0, p0, bn0, mu0), (l1, p1, bn1, mu1) = res
+  assert l0[0] == l1[0]                                   # step 1 is eager in both
+  np.testing.assert_allclose(l1, l0, rtol=5e-3)          # later steps: Adam's sign-like first updates amplify atomics noise
+  assert rel_err(p1, p0) < 2e-2 and rel_err(bn1, bn0) < 1e-3
+  assert float((mu1 - mu0).abs().max()) < 5e-2
+  # a different learning rate must take effect through the device scalar: lr = 0 leaves the parameters unchanged
+  before = eng.flat_p.clone()
+  d = to_dev(synthetic_inputs(4, 128, seed=9))
+  eng.train_step(d['image'], d['future_image'], d['mask'], clip_value=1.0, lr=0.0)
+  torch.cuda.synchronize()
+  assert torch.equal(eng.flat_p, before)
