@@ -14,6 +14,9 @@ int conv_tc_fwd(const immb_conv_desc*, const float* x_hi, const float* x_lo, con
                 const float* wp_lo, const float* bias, float* y_hi, float* y_lo, cudaStream_t);
 int conv_tc_dgrad(const immb_conv_desc*, const float* dy_hi, const float* dy_lo, const float* wh_hi,
                   const float* wh_lo, float* dx, cudaStream_t);
+bool conv_tc_dgrad_relu_eligible(const immb_conv_desc* d);
+int conv_tc_dgrad_relu(const immb_conv_desc* d, const float* dy_hi, const float* dy_lo, const float* wh_hi,
+                       const float* wh_lo, const float* act_hi, int act_cs, float* out_hi, float* out_lo, cudaStream_t);
 size_t conv_tc_wgrad_workspace(const immb_conv_desc*);
 int conv_tc_wgrad(const immb_conv_desc*, const float* x_hi, const float* x_lo, const float* dy_hi,
                   const float* dy_lo, float* dw, void* ws, size_t ws_bytes, cudaStream_t);
@@ -92,6 +95,23 @@ extern "C" int immb_conv2d_dgrad(const immb_conv_desc* d, const float* dy_hi, co
   }
   IMMB_REQUIRE(w, "conv2d_dgrad: SIMT engine needs the master weights");
   return conv_simt_dgrad(d, dy_hi, dy_lo, w, dx, (cudaStream_t)stream);
+}
+
+extern "C" int immb_conv2d_dgrad_relu(const immb_conv_desc* d, const float* dy_hi, const float* dy_lo,
+                                      const float* wh_hi, const float* wh_lo, const float* act_hi, int act_cstride,
+                                      float* out_hi, float* out_lo, void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  IMMB_REQUIRE(dy_hi && wh_hi && act_hi && out_hi && out_lo && act_cstride >= d->Cin, "conv2d_dgrad_relu: null tensors");
+  IMMB_REQUIRE(d->precision == IMMB_PREC_TF32 || (dy_lo && (d->precision == IMMB_PREC_TF32X2 || wh_lo)),
+               "conv2d_dgrad_relu: lo planes missing");
+  if (!conv_tc_dgrad_relu_eligible(d))
+    return immb::set_error(IMMB_ERR_UNSUPPORTED, "conv2d_dgrad_relu: shape not covered by the halo pair kernel");
+  return conv_tc_dgrad_relu(d, dy_hi, dy_lo, wh_hi, wh_lo, act_hi, act_cstride, out_hi, out_lo, (cudaStream_t)stream);
+}
+
+extern "C" int immb_conv2d_dgrad_relu_supported(const immb_conv_desc* d) {
+  return (validate(d) == IMMB_OK && conv_tc_dgrad_relu_eligible(d)) ? 1 : 0;
 }
 
 extern "C" size_t immb_conv2d_wgrad_workspace(const immb_conv_desc* d) {

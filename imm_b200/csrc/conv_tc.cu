@@ -524,7 +524,9 @@ int conv_tc2_wgrad_run(const immb_conv_desc* d, const float* x_hi, const float* 
                        const float* dy_lo, float* dw, cudaStream_t st);
 int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const float* act_lo, int act_c, int act_cs,
                  const float* w_hi, const float* w_lo, int w_rows, int kd, const float* bias, int relu,
-                 float* out_hi, float* out_lo, int ocs, int ncols, int n_store, cudaStream_t st);
+                 float* out_hi, float* out_lo, int ocs, int ncols, int n_store, cudaStream_t st,
+                 const float* relu_src = nullptr, int relu_cs = 0);
+int conv_tc2_pair_mode();
 
 static bool pick_tile(int PH, int PW, int N, int* TW, int* TH, int* TN) {
   if (PW % 16 == 0 && PH % 8 == 0) { *TW = 16; *TH = 8; *TN = 1; return true; }
@@ -659,6 +661,19 @@ int conv_tc_fwd(const immb_conv_desc* d, const float* x_hi, const float* x_lo, c
   }
   dim3 grid(p.tiles_w * p.tiles_h * ceil_div(d->N, p.TN), ceil_div(d->Cout, bn));
   return dispatch_fwd(bn, passes, a_hi, a_lo, b_hi, b_lo, p, grid, st);
+}
+
+// dgrad fused with the backward of the ReLU that produced the conv's input and with the TF32 split of the result:
+// out = split(dgrad(dy) * [act_hi > 0]).  Halo pair kernel only (stride-1 3x3, H % 16 == 0, W % 16 == 0).
+bool conv_tc_dgrad_relu_eligible(const immb_conv_desc* d) {
+  return conv_tc_eligible(d, 1) && conv_tc2_eligible(d, 1) && conv_tc2_pair_mode() == 1 && d->x_cstride % 8 == 0;
+}
+int conv_tc_dgrad_relu(const immb_conv_desc* d, const float* dy_hi, const float* dy_lo, const float* wh_hi,
+                       const float* wh_lo, const float* act_hi, int act_cs, float* out_hi, float* out_lo,
+                       cudaStream_t st) {
+  const int ncols = d->cin_pad < d->x_cstride ? d->cin_pad : d->x_cstride;
+  return conv_tc2_run(d, 1, dy_hi, dy_lo, d->Cout, d->y_cstride, wh_hi, wh_lo, d->cin_pad, d->y_cstride, nullptr, 0,
+                      out_hi, out_lo, d->x_cstride, ncols, ncols, st, act_hi, act_cs);
 }
 
 int conv_tc_dgrad(const immb_conv_desc* d, const float* dy_hi, const float* dy_lo, const float* wh_hi,

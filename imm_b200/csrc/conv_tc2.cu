@@ -43,6 +43,8 @@ struct Tc2Params {
   int a_plane_bytes;         // bytes one TMA box deposits per plane (expect_tx)
   int box_dw, box_dh;        // box origin relative to the tile origin (-1,-1 for 3x3 SAME; 0,-3 for the row-window view)
   uint32_t a_off[9];         // byte offset of each tap's first row inside the box
+  const float* relu_src;     // optional [.., relu_cs] tensor laid out like the output: out = (relu_src > 0) ? out : 0
+  int relu_cs;               // (backward of the ReLU of the layer that produced the dgrad's input, fused)
 };
 
 template <int BN, int PASSES>
@@ -523,6 +525,18 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
+        if (p.relu_src) {
+          const float* a = p.relu_src + pix * p.relu_cs + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (col0 + j >= p.n_store) break;
+            const float4 t = __ldg(reinterpret_cast<const float4*>(a + j));
+            v[j] = t.x > 0.f ? v[j] : 0.f;
+            v[j + 1] = t.y > 0.f ? v[j + 1] : 0.f;
+            v[j + 2] = t.z > 0.f ? v[j + 2] : 0.f;
+            v[j + 3] = t.w > 0.f ? v[j + 3] : 0.f;
+          }
+        }
         float* o = p.out_hi + pix * p.ocs + col0;
         if (vec8) {
           // one full 32-byte sector per store
@@ -719,7 +733,8 @@ static int launch_tc2_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, con
 // act: the tensor the halo boxes are read from ([N,H,W,act_cs], act_c valid channels); wts: [9][ncols_pad][kd]
 int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const float* act_lo, int act_c, int act_cs,
                  const float* w_hi, const float* w_lo, int w_rows, int kd, const float* bias, int relu,
-                 float* out_hi, float* out_lo, int ocs, int ncols, int n_store, cudaStream_t st) {
+                 float* out_hi, float* out_lo, int ocs, int ncols, int n_store, cudaStream_t st,
+                 const float* relu_src, int relu_cs) {
   const int passes = d->precision == IMMB_PREC_TF32 ? 1 : (d->precision == IMMB_PREC_TF32X2 ? 2 : 3);
   Tc2Params p;
   memset(&p, 0, sizeof(p));
@@ -753,6 +768,8 @@ int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const flo
   for (int i = 0; i < 9; ++i) p.a_off[i] = (uint32_t)(p.taps[i].ro * box_w + p.taps[i].so) * 128u;
   p.out_hi = out_hi; p.out_lo = out_lo; p.bias = bias; p.relu = relu;
   p.H = d->H; p.W = d->W; p.ocs = ocs; p.n_cols = ncols; p.n_store = n_store;
+  p.relu_src = relu_src; p.relu_cs = relu_cs;
+  if (relu_src && !pair) return set_error(IMMB_ERR_UNSUPPORTED, "conv_tc2: the fused ReLU-backward epilogue needs the pair kernel");
   { const char* e = getenv("IMMB_TC2_BO"); p.bo_mode = e ? atoi(e) : 0; }
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
   int rc;

@@ -827,10 +827,18 @@ __global__ void __launch_bounds__(256) vgg_conv1_1_fused_kernel(const float* __r
 #pragma unroll
       for (int j = 0; j < CG; ++j) acc[j] = fmaf(g[t], ws[t][cg * CG + j], acc[j]);
     size_t o = (size_t)p * COUT + cg * CG;
+    // 256-bit stores: a thread owns 16 consecutive channels (64 B per plane); 128-bit stores would fill only half of
+    // each 32-byte sector per instruction (this layer is pure HBM write traffic: 2 planes x 64 ch x 4 B per pixel)
 #pragma unroll
-    for (int j = 0; j < CG; j += 4)
-      store_split4(out_hi, out_lo, o + j,
-                   make_float4(fmaxf(acc[j], 0.f), fmaxf(acc[j + 1], 0.f), fmaxf(acc[j + 2], 0.f), fmaxf(acc[j + 3], 0.f)));
+    for (int j = 0; j < CG; j += 8) {
+      float h[8], l[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) split_tf32(fmaxf(acc[j + u], 0.f), h[u], l[u]);
+      asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out_hi + o + j), "f"(h[0]), "f"(h[1]),
+                   "f"(h[2]), "f"(h[3]), "f"(h[4]), "f"(h[5]), "f"(h[6]), "f"(h[7]) : "memory");
+      asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out_lo + o + j), "f"(l[0]), "f"(l[1]),
+                   "f"(l[2]), "f"(l[3]), "f"(l[4]), "f"(l[5]), "f"(l[6]), "f"(l[7]) : "memory");
+    }
   }
 }
 
@@ -1246,6 +1254,7 @@ static inline int ew_grid(int64_t total, int block = 256) {
   return (int)g;
 }
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
 // vectorised per-channel kernels: C a multiple of 4 that divides 256*4 so that a 256-thread block covers whole rows
 static inline bool vec_ok(int C, int cs) { return C % 4 == 0 && cs % 4 == 0 && C <= 1024 && (1024 % C) == 0; }
 // pixels per block of the vectorised per-channel reductions.  With a scratch buffer (two-level reduction, no atomics)
@@ -1462,6 +1471,7 @@ extern "C" int immb_vgg_conv1_1_fused(const float* gt, const float* pred, int pc
   IMMB_REQUIRE(w && bias && out_hi && pcs >= 3 && which >= 0 && which <= 2, "vgg_conv1_1_fused: bad args");
   IMMB_REQUIRE((which == 2 || gt) && (which == 1 || pred), "vgg_conv1_1_fused: missing input for the requested half");
   IMMB_REQUIRE(Cout == 64, "vgg_conv1_1_fused: Cout must be 64 (VGG16 conv1_1)");
+  IMMB_REQUIRE(out_lo && aligned32(out_hi) && aligned32(out_lo), "vgg_conv1_1_fused: split output planes must be 32-byte aligned");
   const int64_t per = (int64_t)B * R * R;
   const int64_t p0 = which == 2 ? per : 0, p1 = which == 1 ? per : 2 * per;
   int64_t blocks = (p1 - p0 + 63) / 64;

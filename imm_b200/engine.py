@@ -698,26 +698,40 @@ class IMMEngine(object):
     B, R = self.B, self.R
     level_of = {nm: k for k, nm in enumerate(self.comp)}
     g = None                       # gradient wrt the current activation (pred half), fp32 [B,h,w,C]
-    for kind, item, cin, size in reversed(self.vgg_seq):
+    fused_dy = None                # layer whose dy planes were already produced by the consumer's fused dgrad epilogue
+    seq = self.vgg_seq
+    for idx in range(len(seq) - 1, -1, -1):
+      kind, item, cin, size = seq[idx]
       if kind == 'conv':
         L = item
         P = L.out
         coef = self.coef[level_of[L.name]:] if L.name in level_of else None
-        if g is None and coef is None:
+        if g is None and coef is None and fused_dy is not L:
           continue                  # above the deepest level used by the loss
         fg, fp = P.half(0, B), P.half(1, B)
         _lib.TAG = 'bwd:vgg/%s' % L.name
-        call('immb_vgg_bwd_combine', g, fg.hi, fg.lo, fp.hi, fp.lo, B, size, size, L.cout, self.mask, R, coef,
-             L.dy.hi, L.dy.lo, st)
-        call('immb_conv2d_dgrad', L.desc(B), L.dy.hi, L.dy.lo, L.w, L.wh.hi, L.wh.lo, L.dx, st)
-        g = L.dx
+        if fused_dy is not L:
+          call('immb_vgg_bwd_combine', g, fg.hi, fg.lo, fp.hi, fp.lo, B, size, size, L.cout, self.mask, R, coef,
+               L.dy.hi, L.dy.lo, st)
+        fused_dy = None
+        # producer of this conv's input: when it is a conv without a loss level, its dy = dgrad * [act > 0] is written
+        # by this dgrad's epilogue (no fp32 gradient round trip, no combine launch)
+        prev = seq[idx - 1] if idx > 0 else None
+        d = L.desc(B)
+        if (prev is not None and prev[0] == 'conv' and prev[1].name not in level_of
+                and _lib.lib().immb_conv2d_dgrad_relu_supported(d)):
+          Lp = prev[1]
+          call('immb_conv2d_dgrad_relu', d, L.dy.hi, L.dy.lo, L.wh.hi, L.wh.lo, Lp.out.half(1, B).hi, Lp.cout,
+               Lp.dy.hi, Lp.dy.lo, st)
+          fused_dy, g = Lp, None
+        else:
+          call('immb_conv2d_dgrad', d, L.dy.hi, L.dy.lo, L.w, L.wh.hi, L.wh.lo, L.dx, st)
+          g = L.dx
       else:
         if g is None:
           continue
-        xin = None
         # input of the pool = previous conv's activation (pred half)
-        idx = [i for i, v in enumerate(self.vgg_seq) if v[1] == item][0]
-        prev = self.vgg_seq[idx - 1][1]
+        prev = seq[idx - 1][1]
         xin = prev.out.half(1, B)
         call('immb_maxpool2x2_bwd', g, xin.hi, xin.lo, B, size, size, cin, self.g_pool[item], st)
         g = self.g_pool[item]

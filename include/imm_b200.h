@@ -101,6 +101,14 @@ int immb_conv2d_fwd(const immb_conv_desc* d, const float* x_hi, const float* x_l
 int immb_conv2d_dgrad(const immb_conv_desc* d, const float* dy_hi, const float* dy_lo, const float* w,
                       const float* wh_hi, const float* wh_lo, float* dx, void* stream);
 /* dw[kh,kw,Cin,Cout] = conv2d_backprop_filter(x, dy).  workspace: split-K partials (query size first). */
+/* dgrad fused with the backward of the ReLU that produced the conv's input (vgg16.py:229-236: activations are stored
+ * post-ReLU) and with the TF32 split of the result: out_{hi,lo}[N,H,W,x_cstride] = split(dgrad(dy) * [act_hi > 0]),
+ * act_hi = hi plane of the conv's (post-ReLU) input, channel stride act_cstride.  Only shapes served by the halo pair
+ * kernel (immb_conv2d_dgrad_relu_supported); saves one write + one read of the fp32 gradient and one launch per layer. */
+int immb_conv2d_dgrad_relu_supported(const immb_conv_desc* d);
+int immb_conv2d_dgrad_relu(const immb_conv_desc* d, const float* dy_hi, const float* dy_lo, const float* wh_hi,
+                           const float* wh_lo, const float* act_hi, int act_cstride, float* out_hi, float* out_lo,
+                           void* stream);
 size_t immb_conv2d_wgrad_workspace(const immb_conv_desc* d);
 int immb_conv2d_wgrad(const immb_conv_desc* d, const float* x_hi, const float* x_lo, const float* dy_hi,
                       const float* dy_lo, float* dw, void* workspace, size_t ws_bytes, void* stream);

@@ -175,6 +175,42 @@ def test_conv_tc2_cluster_multicast_mode():
   assert out.returncode == 0 and 'passed' in out.stdout and 'failed' not in out.stdout, out.stdout[-1500:]
 
 
+def test_conv_dgrad_fused_relu_backward():
+  """immb_conv2d_dgrad_relu = dgrad * [act > 0] written as TF32 split planes (VGG backward: the producer's ReLU
+  backward and the operand split folded into the consumer's dgrad epilogue) vs the two separate ops."""
+  N, H, W, Cin, Cout = 2, 32, 32, 64, 128
+  g = torch.Generator().manual_seed(21)
+  w = torch.randn(3, 3, Cin, Cout, generator=g) * 0.1
+  gy = torch.randn(N, H, W, Cout, generator=g)
+  act = torch.relu(torch.randn(N, H, W, Cin, generator=g))          # post-ReLU activation that fed the conv
+  dev = 'cuda'
+  d = conv_desc(N, H, W, Cin, Cout, 3, 1, None, engine=_lib.ENGINE_TC, precision=_lib.PREC_TF32X2)
+  assert _lib.lib().immb_conv2d_dgrad_relu_supported(d) == 1
+  wq = O.round_tf32(w)                                               # 2-pass product: weights exactly TF32
+  wp_h, wp_l = torch.empty(9, Cout, Cin, device=dev), torch.empty(9, Cout, Cin, device=dev)
+  wh_h, wh_l = torch.empty(9, Cin, Cout, device=dev), torch.empty(9, Cin, Cout, device=dev)
+  call('immb_pack_weights', wq.to(dev), 3, 3, Cin, Cout, Cin, Cout, wp_h, wp_l, wh_h, wh_l, ST())
+  gh, gl = split(gy)
+  gh, gl = gh.to(dev), gl.to(dev)
+  dx = torch.empty(N, H, W, Cin, device=dev)
+  call('immb_conv2d_dgrad', d, gh, gl, None, wh_h, wh_l, dx, ST())
+  ah, _ = split(act)
+  oh, ol = torch.full((N, H, W, Cin), float('nan'), device=dev), torch.full((N, H, W, Cin), float('nan'), device=dev)
+  call('immb_conv2d_dgrad_relu', d, gh, gl, wh_h, wh_l, ah.to(dev), Cin, oh, ol, ST())
+  torch.cuda.synchronize()
+  want = dx.cpu() * (act > 0).float()
+  got = (oh + ol).cpu()
+  assert rel_err(got, want) < 1e-6                                   # same kernel, same accumulation; only the split differs
+  assert float((oh.cpu() - O.round_tf32(oh.cpu())).abs().max()) == 0.0     # hi plane is exactly TF32
+  assert float(got[act <= 0].abs().max()) == 0.0                      # the ReLU backward mask is exact
+  xd = torch.zeros(N, H, W, Cin, dtype=torch.float64, requires_grad=True)
+  O.conv2d_same(xd, wq.double(), None, 1).backward(gy.double())
+  assert rel_err(oh + ol, xd.grad * (act > 0).double()) < 2e-5
+  # shapes outside the halo pair kernel are refused, not silently routed elsewhere
+  d8 = conv_desc(N, 8, 8, Cin, Cout, 3, 1, None, engine=_lib.ENGINE_TC, precision=_lib.PREC_TF32X2)
+  assert _lib.lib().immb_conv2d_dgrad_relu_supported(d8) == 0
+
+
 def test_conv_tc2_single_cta_mode():
   """IMMB_TC2_PAIR=0 routes the stride-1 3x3 layers through the single-CTA halo kernel (cta_group::1) instead of the
   default CTA-pair kernel (cta_group::2, M = 256); both must meet the same bars.  Read once per process -> child."""

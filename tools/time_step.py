@@ -21,7 +21,7 @@ for _ in range(K): eng.train_step(inp['image'], inp['future_image'], inp['mask']
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
 print('B=%d prec=%d: %.2f ms/step  %.1f pairs/s  %.1f TFLOP/s algorithmic; launches/step %d; wall %.2f ms; loss %.3f'
-      % (B, prec, ms, B / ms * 1e3, B * 48.98e9 / ms / 1e9, (_lib.launch_count() - n0) // K, (time.time() - t0) / K * 1e3, float(eng.total_loss)))
+      % (B, prec, ms, B / ms * 1e3, B * 48.98e9 / ms / 1e9, (_lib.launch_count() - n0) // K if not eng.graph_replays else eng.graph_launches_per_step, (time.time() - t0) / K * 1e3, float(eng.total_loss)))
 def timed(fn, n=3):
   torch.cuda.synchronize(); a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   a.record()
@@ -33,6 +33,7 @@ print('opt %.2f ms' % timed(lambda: eng.optimizer_step()))
 
 # per-call attribution (CUDA events around every C-ABI call), single-stream schedule so that calls do not overlap
 eng.wgrad_stream = eng.pose_stream = eng.gt_stream = None
+eng.use_graph = False
 _lib.PROFILE = []
 eng.train_step(inp['image'], inp['future_image'], inp['mask'])
 torch.cuda.synchronize()
