@@ -232,7 +232,8 @@ def main_cuda(args):
   h2d = sum(v.numel() * v.element_size() for v in host[0].values()) * world
   e2e = {'value': B * world / (ms_e2e * 1e-3), 'unit': 'pairs/s', 'ms_per_step': ms_e2e,
          'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4 * world,
-         'api': 'IMMModel.build(inputs from pinned host memory) + setup_training() train_op; loss.item() per step'}
+         'api': 'setup_training() train_op on IMMModel (inputs in pinned host memory, one-deep H2D prefetch on a copy stream, '
+                'CUDA-graph replay of the step) + loss.item() per step'}
 
   # ---- roofline of the dominant kernel family: one extra step with CUDA events around every C-ABI call --------
   # (single-stream schedule for this one step, so that per-call durations are not inflated by overlapping kernels)
@@ -242,25 +243,50 @@ def main_cuda(args):
   step_resident(0, eager=True)
   torch.cuda.synchronize()
   eng.wgrad_stream, eng.pose_stream, eng.gt_stream = saved_streams
-  fam = {}
-  for name, tag, a, b in _lib.PROFILE:
-    fam[name] = fam.get(name, 0.0) + a.elapsed_time(b)
+  fam, kern = {}, {}
+  for name, tag, a, b, info in _lib.PROFILE:
+    t = a.elapsed_time(b)
+    fam[name] = fam.get(name, 0.0) + t
+    if info is not None:
+      k = kern.setdefault(info['kernel'], {'ms': 0.0, 'flops': 0.0, 'mma_flops': 0.0, 'launches': 0})
+      k['ms'] += t
+      k['flops'] += info['flops']
+      k['mma_flops'] += info['flops'] * info['passes']
+      k['launches'] += 1
   _lib.PROFILE = None
-  conv_ms = sum(fam.get(k, 0.0) for k in ('immb_conv2d_fwd', 'immb_conv2d_dgrad', 'immb_conv2d_wgrad'))
+  conv_ms = sum(k['ms'] for k in kern.values())
   peaks = load_peaks()
   conv_tflops = GFLOP_PER_PAIR * B / conv_ms            # GFLOP / ms == TFLOP/s
+  top_name = max(kern, key=lambda n: kern[n]['ms'])
+  top = kern[top_name]
+  top_tflops = top['flops'] / top['ms'] * 1e-9          # algorithmic FLOP per launch / average launch duration
+  top_mma_tflops = top['mma_flops'] / top['ms'] * 1e-9
   traffic = None
   tj = os.path.join(ROOT, 'profiles', 'top_kernel.json')
   if os.path.exists(tj):
     traffic = json.load(open(tj)).get('dram_bytes_per_launch')
-  roofline = {'bound': 'tensor', 'kernel': 'conv engine: conv_tc2_kernel / conv_tc2_wgrad_kernel (persistent halo-reuse, 3x3 stride 1) + conv_tc_kernel / conv_tc_wgrad_kernel (other shapes); tcgen05 kind::tf32, 3xTF32 / 2-pass',
-              'achieved': conv_tflops, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-              'frac': conv_tflops / peaks['bf16_tflops_sustained'], 'traffic': traffic,
-              'peak_source': 'MEASURED_PEAKS.json bf16 sustained (%s); the TF32 pipe peaks at half of it and the engine '
-                             'issues %.2f TF32 MMAs per algorithmic MAC (3 on the trainable stack, 2 on the frozen '
-                             'tower), so frac is capped near %.3f' % (peaks['source'], MMA_PASSES, 0.5 / MMA_PASSES),
-              'tensor_pipe_frac_tf32': MMA_PASSES * conv_tflops / (0.5 * peaks['bf16_tflops_sustained']),
-              'conv_ms_per_step': conv_ms, 'step_share': conv_ms / ms,
+  tf32_peak = 0.5 * peaks['bf16_tflops_sustained']
+  roofline = {'bound': 'tensor',
+              'kernel': '%s (persistent CTA-pair halo conv: tcgen05 cta_group::2 kind::tf32, M=256, TMA halo boxes; forward and '
+                        'dgrad of every stride-1 3x3 layer and the 7x7 first layer) -- %d launches, %.1f%% of the step'
+                        % (top_name, top['launches'], 100.0 * top['ms'] / ms),
+              'achieved': top_tflops, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
+              'frac': top_tflops / peaks['bf16_tflops_sustained'], 'traffic': traffic,
+              'algorithmic_gflop_per_launch': top['flops'] / top['launches'] * 1e-9,
+              'ms_per_launch': top['ms'] / top['launches'],
+              'peak_source': 'MEASURED_PEAKS.json bf16 sustained (%s).  The kernel runs kind::tf32 (half the bf16 rate) and issues '
+                             '3 MMAs per algorithmic MAC on the trainable stack (error-compensated 3xTF32) or 2 on the frozen VGG '
+                             'tower, so `frac` is capped near %.3f; `tensor_pipe_frac_tf32` = issued TF32 MMA FLOP/s / (peak/2) is '
+                             'the figure to compare with ncu sm__pipe_tensor_cycles_active (profiles/top_kernel.json)'
+                             % (peaks['source'], 0.5 / MMA_PASSES),
+              'tensor_pipe_frac_tf32': top_mma_tflops / tf32_peak,
+              'conv_engine': {'flops_accounted_vs_survey': sum(k['flops'] for k in kern.values()) * 1e-9 / (GFLOP_PER_PAIR * B),
+                              'ms_per_step': conv_ms, 'step_share': conv_ms / ms, 'achieved_tflops_algorithmic': conv_tflops,
+                              'tensor_pipe_frac_tf32': MMA_PASSES * conv_tflops / tf32_peak,
+                              'by_kernel': {n: {'ms': round(k['ms'], 3), 'launches': k['launches'],
+                                                'tflops_algorithmic': round(k['flops'] / k['ms'] * 1e-9, 1),
+                                                'tensor_pipe_frac_tf32': round(k['mma_flops'] / k['ms'] * 1e-9 / tf32_peak, 3)}
+                                            for n, k in sorted(kern.items(), key=lambda kv: -kv[1]['ms'])}},
               'per_family_ms': {k.replace('immb_', ''): round(v, 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1])[:10]}}
 
   if world > 1:

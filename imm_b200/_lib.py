@@ -123,9 +123,25 @@ def call(name, *args):
     e0.record()
     rc = _call(name, *args)
     e1.record()
-    PROFILE.append((name, TAG, e0, e1))
+    PROFILE.append((name, TAG, e0, e1, conv_info(name, args[0]) if args and isinstance(args[0], ConvDesc) else None))
     return rc
   return _call(name, *args)
+
+
+def conv_info(name, d):
+  """Algorithmic work of one conv call (2*MACs) and which kernel family serves it (development /
+  bench.py roofline attribution; mirrors conv_tc2_eligible / conv_tc2_rowwin_eligible in csrc/conv_tc2.cu)."""
+  flops = 2.0 * d.N * d.Ho * d.Wo * d.Cout * d.kh * d.kw * d.Cin
+  halo = d.kh == 3 and d.stride == 1 and d.H % 16 == 0 and d.W % 16 == 0 and d.x_layout == XLAYOUT_NHWC
+  first = d.x_layout == XLAYOUT_ROWWIN4 and d.H % 16 == 0 and d.W % 8 == 0
+  wgrad = name.endswith('wgrad')
+  if wgrad:
+    kernel = 'conv_tc2_wgrad_kernel' if (d.kh == 3 and d.stride == 1 and d.H % 4 == 0 and d.W % 8 == 0
+                                         and d.x_layout == XLAYOUT_NHWC) else 'conv_tc_wgrad_kernel'
+  else:
+    kernel = 'conv_tc2_pair_kernel' if (halo or (first and name.endswith('fwd'))) else 'conv_tc_kernel'
+  passes = {PREC_TF32X3: 3, PREC_TF32: 1, PREC_TF32X2: 2}[d.precision]
+  return {'flops': flops, 'kernel': kernel, 'passes': passes}
 
 
 def _call(name, *args):

@@ -39,7 +39,7 @@ eng.train_step(inp['image'], inp['future_image'], inp['mask'])
 torch.cuda.synchronize()
 import collections
 by = collections.defaultdict(float); by_k = collections.defaultdict(float)
-for name, tag, a, b in _lib.PROFILE:
+for name, tag, a, b, _info in _lib.PROFILE:
   ms_ = a.elapsed_time(b); by[(tag, name)] += ms_; by_k[name] += ms_
 _lib.PROFILE = None
 tot = sum(by.values())
