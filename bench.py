@@ -277,7 +277,9 @@ def main_cuda(args):
               'peak_source': 'MEASURED_PEAKS.json bf16 sustained (%s).  The kernel runs kind::tf32 (half the bf16 rate) and issues '
                              '3 MMAs per algorithmic MAC on the trainable stack (error-compensated 3xTF32) or 2 on the frozen VGG '
                              'tower, so `frac` is capped near %.3f; `tensor_pipe_frac_tf32` = issued TF32 MMA FLOP/s / (peak/2) is '
-                             'the figure to compare with ncu sm__pipe_tensor_cycles_active (profiles/top_kernel.json)'
+                             'the issue-rate view of the same thing; the sustained bf16 GEMM that sets `peak` runs power-capped near 1.3 GHz while this '
+                             'kernel holds 1.85-1.97 GHz, so the ratio can exceed ncu sm__pipe_tensor_cycles_active (70.6 %% '
+                             'time-weighted over 21 launches, profiles/top_kernel.json), which is the utilisation figure'
                              % (peaks['source'], 0.5 / MMA_PASSES),
               'tensor_pipe_frac_tf32': top_mma_tflops / tf32_peak,
               'conv_engine': {'flops_accounted_vs_survey': sum(k['flops'] for k in kern.values()) * 1e-9 / (GFLOP_PER_PAIR * B),

@@ -34,6 +34,9 @@ _SIGS = {
   'immb_conv_engine_for': [_D, _I],
   'immb_conv2d_fwd': [_D, _P, _P, _P, _P, _P, _P, _P, _P, _P],
   'immb_conv2d_dgrad': [_D, _P, _P, _P, _P, _P, _P, _P],
+  'immb_conv2d_fwd_stats_rows': [_D],
+  'immb_conv2d_fwd_bnstats': [_D, _P, _P, _P, _P, _P, _P, _P, _Z, _P],
+  'immb_bn_stats_from_partials': [_P, _I, _I, _P, _P],
   'immb_conv2d_dgrad_relu': [_D, _P, _P, _P, _P, _P, _I, _P, _P, _P],
   'immb_conv2d_dgrad_relu_supported': [_D],
   'immb_conv2d_wgrad_workspace': [_D],

@@ -11,7 +11,8 @@ int conv_simt_wgrad(const immb_conv_desc*, const float*, const float*, const flo
 // tcgen05 engine (conv_tc.cu)
 bool conv_tc_eligible(const immb_conv_desc* d, int op);
 int conv_tc_fwd(const immb_conv_desc*, const float* x_hi, const float* x_lo, const float* wp_hi,
-                const float* wp_lo, const float* bias, float* y_hi, float* y_lo, cudaStream_t);
+                const float* wp_lo, const float* bias, float* y_hi, float* y_lo, cudaStream_t, double* stats = nullptr);
+int conv_tc_fwd_stats_rows(const immb_conv_desc* d);
 int conv_tc_dgrad(const immb_conv_desc*, const float* dy_hi, const float* dy_lo, const float* wh_hi,
                   const float* wh_lo, float* dx, cudaStream_t);
 bool conv_tc_dgrad_relu_eligible(const immb_conv_desc* d);
@@ -78,6 +79,25 @@ extern "C" int immb_conv2d_fwd(const immb_conv_desc* d, const float* x_hi, const
   }
   IMMB_REQUIRE(w, "conv2d_fwd: SIMT engine needs the master weights");
   return conv_simt_fwd(d, x_hi, x_lo, w, bias, y_hi, y_lo, (cudaStream_t)stream);
+}
+
+extern "C" int immb_conv2d_fwd_stats_rows(const immb_conv_desc* d) {
+  if (validate(d) != IMMB_OK) return 0;
+  int engine = IMMB_ENGINE_SIMT;
+  if (pick_engine(d, 0, &engine) || engine != IMMB_ENGINE_TC) return 0;
+  return conv_tc_fwd_stats_rows(d);
+}
+
+extern "C" int immb_conv2d_fwd_bnstats(const immb_conv_desc* d, const float* x_hi, const float* x_lo,
+                                       const float* wp_hi, const float* wp_lo, const float* bias, float* y,
+                                       double* partials, size_t partial_elems, void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  IMMB_REQUIRE(x_hi && x_lo && wp_hi && wp_lo && y && partials, "conv2d_fwd_bnstats: null tensors");
+  const int rows = immb_conv2d_fwd_stats_rows(d);
+  if (rows <= 0) return immb::set_error(IMMB_ERR_UNSUPPORTED, "conv2d_fwd_bnstats: shape not served by the 3-pass pair kernel");
+  IMMB_REQUIRE(partial_elems >= (size_t)rows * 2 * (size_t)d->Cout, "conv2d_fwd_bnstats: partials buffer too small");
+  return conv_tc_fwd(d, x_hi, x_lo, wp_hi, wp_lo, bias, y, nullptr, (cudaStream_t)stream, partials);
 }
 
 extern "C" int immb_conv2d_dgrad(const immb_conv_desc* d, const float* dy_hi, const float* dy_lo,

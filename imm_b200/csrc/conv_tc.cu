@@ -517,7 +517,8 @@ int tc_make_rowwin_map(CUtensorMap* m, const float* base, int N, int H, int W, i
 }
 bool conv_tc2_rowwin_eligible(const immb_conv_desc* d);
 int conv_tc2_rowwin_fwd(const immb_conv_desc* d, const float* x_hi, const float* x_lo, const float* wp_hi,
-                        const float* wp_lo, const float* bias, int relu, float* y_hi, float* y_lo, cudaStream_t st);
+                        const float* wp_lo, const float* bias, int relu, float* y_hi, float* y_lo, cudaStream_t st,
+                        double* stats = nullptr);
 bool conv_tc2_eligible(const immb_conv_desc* d, int op);
 bool conv_tc2_wgrad_eligible(const immb_conv_desc* d);
 int conv_tc2_wgrad_run(const immb_conv_desc* d, const float* x_hi, const float* x_lo, const float* dy_hi,
@@ -525,7 +526,8 @@ int conv_tc2_wgrad_run(const immb_conv_desc* d, const float* x_hi, const float* 
 int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const float* act_lo, int act_c, int act_cs,
                  const float* w_hi, const float* w_lo, int w_rows, int kd, const float* bias, int relu,
                  float* out_hi, float* out_lo, int ocs, int ncols, int n_store, cudaStream_t st,
-                 const float* relu_src = nullptr, int relu_cs = 0);
+                 const float* relu_src = nullptr, int relu_cs = 0, double* stats = nullptr);
+int conv_tc2_fwd_stats_rows(const immb_conv_desc* d);
 int conv_tc2_pair_mode();
 
 static bool pick_tile(int PH, int PW, int N, int* TW, int* TH, int* TN) {
@@ -612,13 +614,18 @@ static int pick_bn(int ncols) {
   return 128;
 }
 
+int conv_tc_fwd_stats_rows(const immb_conv_desc* d) { return conv_tc2_fwd_stats_rows(d); }
+
 int conv_tc_fwd(const immb_conv_desc* d, const float* x_hi, const float* x_lo, const float* wp_hi,
-                const float* wp_lo, const float* bias, float* y_hi, float* y_lo, cudaStream_t st) {
+                const float* wp_lo, const float* bias, float* y_hi, float* y_lo, cudaStream_t st, double* stats) {
+  if (stats && conv_tc2_fwd_stats_rows(d) == 0)
+    return set_error(IMMB_ERR_UNSUPPORTED, "conv_tc_fwd: fused BN statistics are not available for this shape");
   if (conv_tc2_eligible(d, 0))
     return conv_tc2_run(d, 0, x_hi, x_lo, d->Cin, d->x_cstride, wp_hi, wp_lo, d->Cout, d->cin_pad, bias,
-                        d->epilogue == IMMB_EPI_BIAS_RELU, y_hi, y_lo, d->y_cstride, d->Cout, (d->Cout + 3) / 4 * 4, st);
+                        d->epilogue == IMMB_EPI_BIAS_RELU, y_hi, y_lo, d->y_cstride, d->Cout, (d->Cout + 3) / 4 * 4, st,
+                        nullptr, 0, stats);
   if (conv_tc2_rowwin_eligible(d))
-    return conv_tc2_rowwin_fwd(d, x_hi, x_lo, wp_hi, wp_lo, bias, d->epilogue == IMMB_EPI_BIAS_RELU, y_hi, y_lo, st);
+    return conv_tc2_rowwin_fwd(d, x_hi, x_lo, wp_hi, wp_lo, bias, d->epilogue == IMMB_EPI_BIAS_RELU, y_hi, y_lo, st, stats);
   const int passes = d->precision == IMMB_PREC_TF32 ? 1 : 3;
   TcParams p;
   memset(&p, 0, sizeof(p));

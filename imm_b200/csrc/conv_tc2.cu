@@ -45,6 +45,7 @@ struct Tc2Params {
   uint32_t a_off[9];         // byte offset of each tap's first row inside the box
   const float* relu_src;     // optional [.., relu_cs] tensor laid out like the output: out = (relu_src > 0) ? out : 0
   int relu_cs;               // (backward of the ReLU of the layer that produced the dgrad's input, fused)
+  double* stats;             // optional BN batch-statistics partials: row (cta*4 + epilogue warp) of [2][n_cols] doubles
 };
 
 template <int BN, int PASSES>
@@ -323,11 +324,14 @@ struct Tc2PairCfg {
   static constexpr uint32_t BH = BN2 / 2;                     // weight rows held by each CTA
   static constexpr uint32_t B_PLANE = BH * 128;
   static constexpr uint32_t B_SLOT = B_PLANE * NPLB;
-  static constexpr uint32_t ROOM = 232448 - 1024 - 512 - A_SLOTS * A_SLOT;
+  // fused BN statistics (3-pass layers only: the frozen 2-pass tower has no BN): per epilogue warp, per N tile (<= 2),
+  // sum and sum of squares of BN2 channels in double
+  static constexpr uint32_t STATS_BYTES = PASSES == 3 ? 4 * 2 * 2 * BN2 * 8 : 0;
+  static constexpr uint32_t ROOM = 232448 - 1024 - 512 - A_SLOTS * A_SLOT - STATS_BYTES;
   static constexpr uint32_t B_FIT = ROOM / B_SLOT;
   static constexpr uint32_t B_SLOTS = B_FIT > 6 ? 6 : B_FIT;
   static_assert(B_SLOTS >= 2, "weight ring needs two slots");
-  static constexpr uint32_t SMEM_BYTES = A_SLOTS * A_SLOT + B_SLOTS * B_SLOT + 1024 + 512;
+  static constexpr uint32_t SMEM_BYTES = A_SLOTS * A_SLOT + B_SLOTS * B_SLOT + STATS_BYTES + 1024 + 512;
   // 3-pass: the two cross terms (hi*lo, lo*hi; ~2^-11 of the main term) accumulate in their OWN TMEM columns
   // [BN2, 2*BN2) and are added to the main accumulator once, in the epilogue.  The tensor core truncates the fp32
   // accumulator at every MMA, a biased error that grows linearly with the number of accumulating MMAs; keeping the
@@ -362,6 +366,7 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
   uint64_t* t_full = b_empty + Cfg::B_SLOTS;
   uint64_t* t_empty = t_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  double* stats_sm = reinterpret_cast<double*>(b_base + Cfg::B_SLOTS * Cfg::B_SLOT + 512);     // [4 warps][2 n tiles][2][BN2]
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
 
@@ -493,6 +498,10 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
     const int hl = m >> 3, wl = m & 7;
     const bool vec8 = (p.ocs % 8 == 0) && (p.n_store % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.out_hi) & 31) == 0) &&
                       ((reinterpret_cast<uintptr_t>(p.out_lo) & 31) == 0);
+    const bool do_stats = PASSES == 3 && p.stats != nullptr;
+    double* my_stats = stats_sm + (size_t)q * (2 * 2 * BN2);      // this warp's private rows: no cross-warp races
+    if (do_stats)
+      for (int i = lane; i < 2 * 2 * BN2; i += 32) my_stats[i] = 0.0;
     uint32_t ti = 0;
     for (int t = tile0; t < n_iter_total; t += tstep) {
       int img, th, tw, n_off;
@@ -520,6 +529,32 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (col0 + j < p.n_cols) v[j] += __ldg(p.bias + col0 + j);
+        }
+        if (do_stats) {
+          // per-channel sum / sum of squares of this warp's 32 pixel rows: butterfly transpose-reduce (31 shuffles per
+          // quantity; lane j ends up with channel col0 + j), accumulated in double in the warp's own smem rows
+          float s1[32], s2[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float t = (col0 + j < p.n_cols) ? v[j] : 0.f;
+            s1[j] = t;
+            s2[j] = t * t;
+          }
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              const float send1 = up ? s1[i] : s1[i + off], keep1 = up ? s1[i + off] : s1[i];
+              const float send2 = up ? s2[i] : s2[i + off], keep2 = up ? s2[i + off] : s2[i];
+              s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
+              s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+            }
+          }
+          const int nt = (n_off / BN2) & 1;
+          double* row = my_stats + (size_t)nt * (2 * BN2);
+          row[c0 + lane] += (double)s1[0];
+          row[BN2 + c0 + lane] += (double)s2[0];
         }
         if (p.relu) {
 #pragma unroll
@@ -583,6 +618,20 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&t_empty[acc]);
       ++ti;
+    }
+    if (do_stats) {
+      // one partial row per (CTA, epilogue warp): [sum over n_cols | sum of squares over n_cols]; summed in a fixed
+      // order by the second level (immb_bn_stats_from_partials): deterministic, no atomics
+      __syncwarp();
+      double* out = p.stats + ((size_t)blockIdx.x * 4 + q) * (size_t)(2 * p.n_cols);
+      for (int nt = 0; nt < p.n_tiles_n && nt < 2; ++nt)
+        for (int c = lane; c < BN2; c += 32) {
+          const int col = nt * BN2 + c;
+          if (col < p.n_cols) {
+            out[col] = my_stats[(size_t)nt * (2 * BN2) + c];
+            out[p.n_cols + col] = my_stats[(size_t)nt * (2 * BN2) + BN2 + c];
+          }
+        }
     }
   }
   tc_fence_before();
@@ -734,7 +783,7 @@ static int launch_tc2_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, con
 int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const float* act_lo, int act_c, int act_cs,
                  const float* w_hi, const float* w_lo, int w_rows, int kd, const float* bias, int relu,
                  float* out_hi, float* out_lo, int ocs, int ncols, int n_store, cudaStream_t st,
-                 const float* relu_src, int relu_cs) {
+                 const float* relu_src, int relu_cs, double* stats) {
   const int passes = d->precision == IMMB_PREC_TF32 ? 1 : (d->precision == IMMB_PREC_TF32X2 ? 2 : 3);
   Tc2Params p;
   memset(&p, 0, sizeof(p));
@@ -768,7 +817,9 @@ int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const flo
   for (int i = 0; i < 9; ++i) p.a_off[i] = (uint32_t)(p.taps[i].ro * box_w + p.taps[i].so) * 128u;
   p.out_hi = out_hi; p.out_lo = out_lo; p.bias = bias; p.relu = relu;
   p.H = d->H; p.W = d->W; p.ocs = ocs; p.n_cols = ncols; p.n_store = n_store;
-  p.relu_src = relu_src; p.relu_cs = relu_cs;
+  p.relu_src = relu_src; p.relu_cs = relu_cs; p.stats = stats;
+  if (stats && (!pair || passes != 3 || p.n_tiles_n > 2))
+    return set_error(IMMB_ERR_UNSUPPORTED, "conv_tc2: fused BN statistics need the 3-pass pair kernel and <= 2 N tiles");
   if (relu_src && !pair) return set_error(IMMB_ERR_UNSUPPORTED, "conv_tc2: the fused ReLU-backward epilogue needs the pair kernel");
   { const char* e = getenv("IMMB_TC2_BO"); p.bo_mode = e ? atoi(e) : 0; }
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
@@ -829,8 +880,23 @@ bool conv_tc2_rowwin_eligible(const immb_conv_desc* d) {
   return d->H % 16 == 0 && d->W % 8 == 0 && d->Cout % 32 == 0 && d->Cout <= 256 && d->y_cstride == d->Cout;
 }
 
+// rows of BN-statistics partials the pair kernel writes for this forward conv (4 per CTA), 0 = not served by it
+int conv_tc2_fwd_stats_rows(const immb_conv_desc* d) {
+  const bool rowwin = conv_tc2_rowwin_eligible(d);
+  if (!rowwin && !(conv_tc2_eligible(d, 0) && conv_tc2_pair_mode() == 1)) return 0;
+  if (d->precision != IMMB_PREC_TF32X3) return 0;
+  const int m_tiles = (d->W / 8) * (d->H / 16) * d->N;
+  const int bn = pair_bn(d->Cout, 3);
+  const int n_tiles_n = ceil_div(d->Cout, bn);
+  if (n_tiles_n > 2) return 0;
+  const int total_pairs = ceil_div(m_tiles, 2) * n_tiles_n;
+  const int pairs = total_pairs < kNumSMs / 2 ? total_pairs : kNumSMs / 2;
+  return 2 * pairs * 4;
+}
+
 int conv_tc2_rowwin_fwd(const immb_conv_desc* d, const float* x_hi, const float* x_lo, const float* wp_hi,
-                        const float* wp_lo, const float* bias, int relu, float* y_hi, float* y_lo, cudaStream_t st) {
+                        const float* wp_lo, const float* bias, int relu, float* y_hi, float* y_lo, cudaStream_t st,
+                        double* stats) {
   const int passes = d->precision == IMMB_PREC_TF32 ? 1 : (d->precision == IMMB_PREC_TF32X2 ? 2 : 3);
   Tc2Params p;
   memset(&p, 0, sizeof(p));
@@ -845,6 +911,9 @@ int conv_tc2_rowwin_fwd(const immb_conv_desc* d, const float* x_hi, const float*
   for (int r = 0; r < 7; ++r) { p.taps[r].b_tap = r; p.a_off[r] = (uint32_t)r * 1024u; }
   p.out_hi = y_hi; p.out_lo = y_lo; p.bias = bias; p.relu = relu;
   p.H = d->H; p.W = d->W; p.ocs = d->y_cstride; p.n_cols = d->Cout; p.n_store = d->Cout;
+  p.stats = stats;
+  if (stats && (passes != 3 || p.n_tiles_n > 2))
+    return set_error(IMMB_ERR_UNSUPPORTED, "conv_tc2 rowwin: fused BN statistics need the 3-pass kernel and <= 2 N tiles");
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
   int rc;
   if ((rc = tc_make_rowwin_map(&a_hi, x_hi, d->N, d->H, d->W, 8, 22, 1))) return rc;

@@ -1325,6 +1325,11 @@ extern "C" int immb_bn_stats(const float* y, int64_t npix, int C, int ycs, doubl
   return check_launch("bn_stats");
 }
 
+extern "C" int immb_bn_stats_from_partials(const double* partials, int rows, int C, double* sums, void* stream) {
+  IMMB_REQUIRE(partials && sums && rows > 0 && C > 0, "bn_stats_from_partials: bad args");
+  return launch_reduce_partials(partials, rows, 2 * C, sums, ST(stream));
+}
+
 extern "C" int immb_bn_finalize(const double* sums, int64_t count, int C, const float* gamma,
                                 const float* beta, float* mm, float* mv, int training, float* scale,
                                 float* shift, float* mean, float* invstd, void* stream) {

@@ -177,6 +177,7 @@ class IMMEngine(object):
     self.gt_stream = torch.cuda.Stream(device=self.dev) if self.streams & 4 else None
     # CUDA-graph replay of the training step (train_step only; forward / backward / optimizer_step stay eager)
     self.use_graph = bool(int(os.environ.get('IMMB_GRAPH', '1'))) if use_graph is None else bool(use_graph)
+    self.fuse_bn_stats = bool(int(os.environ.get('IMMB_FUSE_BN_STATS', '1')))
     self._graphs, self._graph_key, self._graph_warm = None, None, 0
     self.graph_replays, self.graph_launches_per_step = 0, 0
     self._events = {}
@@ -402,6 +403,9 @@ class IMMEngine(object):
     self.workspace = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
     # scratch of the two-level (deterministic, atomic-free) BN reductions
     n_scr = max([int(call('immb_bn_scratch_elems', L.N * L.Ho * L.Wo, L.cout)) for L in self.layers.values() if L.bn] + [16])
+    for L in self.layers.values():
+      L.stats_rows = int(_lib.lib().immb_conv2d_fwd_stats_rows(L.desc())) if (L.bn and L.ycs == L.cout) else 0
+      n_scr = max(n_scr, L.stats_rows * 2 * L.cout)
     self.bn_scratch = torch.empty(n_scr, dtype=torch.float64, device=dev)
     self.bn_scratch_pose = torch.empty(n_scr, dtype=torch.float64, device=dev)      # the pose-branch stream's own scratch
 
@@ -513,12 +517,18 @@ class IMMEngine(object):
     st = _lib.stream_ptr()
     _lib.TAG = 'fwd:%s/%s' % (L.prefix.split('/')[-2] if L.prefix.endswith('encoder') else L.prefix.split('/')[-1], L.name)
     L.x = X
-    self._conv_fwd(L, X, L.y)
+    sc = self.bn_scratch if scratch is None else scratch
+    fused_stats = bool(L.bn and training and self.fuse_bn_stats and L.stats_rows > 0)
+    if fused_stats:
+      # batch statistics accumulated in the conv epilogue (per-CTA partial rows -> fixed-order second level)
+      call('immb_conv2d_fwd_bnstats', L.desc(), X.hi, X.lo, L.wp.hi, L.wp.lo, L.b, L.y, sc, sc.numel(), st)
+      call('immb_bn_stats_from_partials', sc, L.stats_rows, L.cout, L.sums, st)
+    else:
+      self._conv_fwd(L, X, L.y)
     if not L.bn:
       return None
     npix = L.N * L.Ho * L.Wo
-    if training:
-      sc = self.bn_scratch if scratch is None else scratch
+    if training and not fused_stats:
       call('immb_bn_stats', L.y, npix, L.cout, L.ycs, L.sums, sc, sc.numel(), st)
     call('immb_bn_finalize', L.sums, npix, L.cout, L.gamma, L.beta, L.mm, L.mv, 1 if training else 0,
          L.scale, L.shift, L.mean, L.invstd, st)

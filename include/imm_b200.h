@@ -101,6 +101,17 @@ int immb_conv2d_fwd(const immb_conv_desc* d, const float* x_hi, const float* x_l
 int immb_conv2d_dgrad(const immb_conv_desc* d, const float* dy_hi, const float* dy_lo, const float* w,
                       const float* wh_hi, const float* wh_lo, float* dx, void* stream);
 /* dw[kh,kw,Cin,Cout] = conv2d_backprop_filter(x, dy).  workspace: split-K partials (query size first). */
+/* Forward conv with the batch-normalisation statistics of its output (tf.layers.batch_normalization(fused=True),
+ * nn_utils.py:201: per-channel sum and sum of squares over N*Ho*Wo) accumulated in the epilogue, so the raw output is
+ * not re-read by immb_bn_stats.  y[N,Ho,Wo,y_cstride] = conv + bias (single fp32 plane);  partials = rows x [2][Cout]
+ * doubles, rows = immb_conv2d_fwd_stats_rows(d) (4 per CTA; 0 when the shape is not served by the 3-pass pair kernel),
+ * one row per (CTA, epilogue warp) accumulated in a fixed order;  immb_bn_stats_from_partials adds them, in a fixed
+ * order, to sums[2*Cout] (zeroed by the caller): deterministic, no atomics. */
+int immb_conv2d_fwd_stats_rows(const immb_conv_desc* d);
+int immb_conv2d_fwd_bnstats(const immb_conv_desc* d, const float* x_hi, const float* x_lo, const float* wp_hi,
+                            const float* wp_lo, const float* bias, float* y, double* partials, size_t partial_elems,
+                            void* stream);
+int immb_bn_stats_from_partials(const double* partials, int rows, int C, double* sums, void* stream);
 /* dgrad fused with the backward of the ReLU that produced the conv's input (vgg16.py:229-236: activations are stored
  * post-ReLU) and with the TF32 split of the result: out_{hi,lo}[N,H,W,x_cstride] = split(dgrad(dy) * [act_hi > 0]),
  * act_hi = hi plane of the conv's (post-ReLU) input, channel stride act_cstride.  Only shapes served by the halo pair

@@ -552,3 +552,49 @@ def test_error_reporting_no_throw():
   assert 'kernel size' in str(e.value)
   with pytest.raises(_lib.ImmbError):
     call('immb_split_planes', torch.zeros(4), torch.zeros(4), None, 4, ST())       # CPU tensors are refused
+
+
+@pytest.mark.parametrize('case', [(2, 32, 32, 32, 32, 3), (1, 16, 16, 288, 256, 3), (3, 16, 16, 64, 96, 3), (2, 32, 32, 3, 32, 7)])
+def test_conv_fwd_fused_bn_statistics(case):
+  """immb_conv2d_fwd_bnstats: the conv output is bit-identical to immb_conv2d_fwd and the per-channel sum / sum of
+  squares accumulated in the epilogue match the oracle's batch moments of that output (nn_utils.py:201)."""
+  N, H, W, Cin, Cout, k = case
+  g = torch.Generator().manual_seed(sum(case))
+  dev = 'cuda'
+  first = k == 7
+  w = torch.randn(k, k, Cin, Cout, generator=g) * 0.05
+  b = torch.randn(Cout, generator=g)
+  if first:
+    img = torch.rand(N, H, W, 3, generator=g) * 255
+    d = conv_desc(N, H, W, 3, Cout, 7, 1, xcs=4, engine=_lib.ENGINE_TC)
+    d.x_layout = _lib.XLAYOUT_ROWWIN4
+    xh, xl = torch.empty(N, H, W + 8, 4, device=dev), torch.empty(N, H, W + 8, 4, device=dev)
+    call('immb_stage_image_rowwin', img.to(dev), N, H, W, xh, xl, ST())
+    wph, wpl = torch.empty(7, Cout, 32, device=dev), torch.empty(7, Cout, 32, device=dev)
+    call('immb_pack_weights_rowwin', w.to(dev), Cout, wph, wpl, ST())
+  else:
+    x = torch.randn(N, H, W, Cin, generator=g)
+    d = conv_desc(N, H, W, Cin, Cout, 3, 1, None, engine=_lib.ENGINE_TC)
+    xh, xl = (t.to(dev) for t in split(x))
+    cp = d.cin_pad
+    wph, wpl = torch.empty(9, Cout, cp, device=dev), torch.empty(9, Cout, cp, device=dev)
+    whh, whl = torch.empty(9, cp, Cout, device=dev), torch.empty(9, cp, Cout, device=dev)
+    call('immb_pack_weights', w.to(dev), 3, 3, Cin, Cout, cp, Cout, wph, wpl, whh, whl, ST())
+  rows = int(_lib.lib().immb_conv2d_fwd_stats_rows(d))
+  assert rows > 0 and rows % 8 == 0
+  y0 = torch.empty(N, H, W, Cout, device=dev)
+  call('immb_conv2d_fwd', d, xh, xl, None, wph, wpl, b.to(dev), y0, None, ST())
+  y1 = torch.full_like(y0, float('nan'))
+  part = torch.full((rows * 2 * Cout,), float('nan'), dtype=torch.float64, device=dev)
+  call('immb_conv2d_fwd_bnstats', d, xh, xl, wph, wpl, b.to(dev), y1, part, part.numel(), ST())
+  sums = torch.zeros(2 * Cout, dtype=torch.float64, device=dev)
+  call('immb_bn_stats_from_partials', part, rows, Cout, sums, ST())
+  torch.cuda.synchronize()
+  assert torch.equal(y0, y1)
+  yd = y0.double().reshape(-1, Cout)
+  ref = torch.cat([yd.sum(0), (yd * yd).sum(0)])
+  assert bool(torch.isfinite(part).all())
+  np.testing.assert_allclose(sums.cpu().numpy(), ref.cpu().numpy(), rtol=2e-6, atol=1e-6 * float(ref.abs().max()))
+  # single-pass TF32 / shapes outside the pair kernel: not offered
+  d1 = conv_desc(N, 8, 8, 32, 32, 3, 1, None, engine=_lib.ENGINE_TC)
+  assert int(_lib.lib().immb_conv2d_fwd_stats_rows(d1)) == 0
