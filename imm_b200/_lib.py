@@ -142,7 +142,7 @@ def conv_info(name, d):
     kernel = 'conv_tc2_wgrad_kernel' if (d.kh == 3 and d.stride == 1 and d.H % 4 == 0 and d.W % 8 == 0
                                          and d.x_layout == XLAYOUT_NHWC) else 'conv_tc_wgrad_kernel'
   else:
-    kernel = 'conv_tc2_pair_kernel' if (halo or (first and name.endswith('fwd'))) else 'conv_tc_kernel'
+    kernel = 'conv_tc2_pair_kernel' if (halo or (first and 'fwd' in name)) else 'conv_tc_kernel'
   passes = {PREC_TF32X3: 3, PREC_TF32: 1, PREC_TF32X2: 2}[d.precision]
   return {'flops': flops, 'kernel': kernel, 'passes': passes}
 
