@@ -8,7 +8,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libimm_b200.so')
+LIB_PATH = os.environ.get('IMMB_LIB', os.path.join(_HERE, 'lib', 'libimm_b200.so'))     # IMMB_LIB: A/B builds (development)
 
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
 PREC_TF32X3, PREC_TF32, PREC_TF32X2 = 0, 1, 2
@@ -37,6 +37,8 @@ _SIGS = {
   'immb_conv2d_fwd_stats_rows': [_D],
   'immb_conv2d_fwd_bnstats': [_D, _P, _P, _P, _P, _P, _P, _P, _Z, _P],
   'immb_bn_stats_from_partials': [_P, _I, _I, _P, _P],
+  'immb_conv2d_dgrad_stats_rows': [_D],
+  'immb_conv2d_dgrad_bnreduce': [_D, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _P, _Z, _P],
   'immb_conv2d_dgrad_relu': [_D, _P, _P, _P, _P, _P, _I, _P, _P, _P],
   'immb_conv2d_dgrad_relu_supported': [_D],
   'immb_conv2d_wgrad_workspace': [_D],

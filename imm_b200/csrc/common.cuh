@@ -62,6 +62,14 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// BN-backward reduction fused into a dgrad epilogue (conv_tc2_pair_kernel, stats_mode 2): the raw conv output and the
+// BN constants of the layer that produced the dgrad's input
+struct Tc2BnReduce {
+  const float* y;
+  int ycs, relu;
+  const float *scale, *shift, *mean, *invstd;
+};
+
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 constexpr int kNumSMs = 148;

@@ -15,6 +15,11 @@ int conv_tc_fwd(const immb_conv_desc*, const float* x_hi, const float* x_lo, con
 int conv_tc_fwd_stats_rows(const immb_conv_desc* d);
 int conv_tc_dgrad(const immb_conv_desc*, const float* dy_hi, const float* dy_lo, const float* wh_hi,
                   const float* wh_lo, float* dx, cudaStream_t);
+int conv_tc_dgrad_stats_rows(const immb_conv_desc* d);
+int conv_tc_dgrad_bnreduce(const immb_conv_desc* d, const float* dy_hi, const float* dy_lo, const float* wh_hi,
+                           const float* wh_lo, float* dx, const float* y_prev, int y_prev_cs, const float* scale,
+                           const float* shift, const float* mean, const float* invstd, int relu, double* partials,
+                           cudaStream_t st);
 bool conv_tc_dgrad_relu_eligible(const immb_conv_desc* d);
 int conv_tc_dgrad_relu(const immb_conv_desc* d, const float* dy_hi, const float* dy_lo, const float* wh_hi,
                        const float* wh_lo, const float* act_hi, int act_cs, float* out_hi, float* out_lo, cudaStream_t);
@@ -115,6 +120,30 @@ extern "C" int immb_conv2d_dgrad(const immb_conv_desc* d, const float* dy_hi, co
   }
   IMMB_REQUIRE(w, "conv2d_dgrad: SIMT engine needs the master weights");
   return conv_simt_dgrad(d, dy_hi, dy_lo, w, dx, (cudaStream_t)stream);
+}
+
+extern "C" int immb_conv2d_dgrad_stats_rows(const immb_conv_desc* d) {
+  if (validate(d) != IMMB_OK) return 0;
+  int engine = IMMB_ENGINE_SIMT;
+  if (pick_engine(d, 1, &engine) || engine != IMMB_ENGINE_TC) return 0;
+  return conv_tc_dgrad_stats_rows(d);
+}
+
+extern "C" int immb_conv2d_dgrad_bnreduce(const immb_conv_desc* d, const float* dy_hi, const float* dy_lo,
+                                          const float* wh_hi, const float* wh_lo, float* dx, const float* y_prev,
+                                          int y_prev_cstride, const float* scale, const float* shift, const float* mean,
+                                          const float* invstd, int relu, double* partials, size_t partial_elems,
+                                          void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  IMMB_REQUIRE(dy_hi && dy_lo && wh_hi && wh_lo && dx && y_prev && scale && shift && mean && invstd && partials,
+               "conv2d_dgrad_bnreduce: null tensors");
+  IMMB_REQUIRE(y_prev_cstride >= d->Cin && y_prev_cstride % 4 == 0, "conv2d_dgrad_bnreduce: bad y stride");
+  const int rows = immb_conv2d_dgrad_stats_rows(d);
+  if (rows <= 0) return immb::set_error(IMMB_ERR_UNSUPPORTED, "conv2d_dgrad_bnreduce: shape not served by the 3-pass pair kernel");
+  IMMB_REQUIRE(partial_elems >= (size_t)rows * 2 * (size_t)d->Cin, "conv2d_dgrad_bnreduce: partials buffer too small");
+  return conv_tc_dgrad_bnreduce(d, dy_hi, dy_lo, wh_hi, wh_lo, dx, y_prev, y_prev_cstride, scale, shift, mean, invstd, relu,
+                                partials, (cudaStream_t)stream);
 }
 
 extern "C" int immb_conv2d_dgrad_relu(const immb_conv_desc* d, const float* dy_hi, const float* dy_lo,

@@ -526,8 +526,10 @@ int conv_tc2_wgrad_run(const immb_conv_desc* d, const float* x_hi, const float* 
 int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const float* act_lo, int act_c, int act_cs,
                  const float* w_hi, const float* w_lo, int w_rows, int kd, const float* bias, int relu,
                  float* out_hi, float* out_lo, int ocs, int ncols, int n_store, cudaStream_t st,
-                 const float* relu_src = nullptr, int relu_cs = 0, double* stats = nullptr);
+                 const float* relu_src = nullptr, int relu_cs = 0, double* stats = nullptr,
+                 const Tc2BnReduce* bnr = nullptr);
 int conv_tc2_fwd_stats_rows(const immb_conv_desc* d);
+int conv_tc2_dgrad_stats_rows(const immb_conv_desc* d);
 int conv_tc2_pair_mode();
 
 static bool pick_tile(int PH, int PW, int N, int* TW, int* TH, int* TN) {
@@ -681,6 +683,18 @@ int conv_tc_dgrad_relu(const immb_conv_desc* d, const float* dy_hi, const float*
   const int ncols = d->cin_pad < d->x_cstride ? d->cin_pad : d->x_cstride;
   return conv_tc2_run(d, 1, dy_hi, dy_lo, d->Cout, d->y_cstride, wh_hi, wh_lo, d->cin_pad, d->y_cstride, nullptr, 0,
                       out_hi, out_lo, d->x_cstride, ncols, ncols, st, act_hi, act_cs);
+}
+
+// dgrad that also accumulates, in its epilogue, the BN-backward sums of the layer that produced its input
+int conv_tc_dgrad_stats_rows(const immb_conv_desc* d) { return conv_tc_eligible(d, 1) ? conv_tc2_dgrad_stats_rows(d) : 0; }
+int conv_tc_dgrad_bnreduce(const immb_conv_desc* d, const float* dy_hi, const float* dy_lo, const float* wh_hi,
+                           const float* wh_lo, float* dx, const float* y_prev, int y_prev_cs, const float* scale,
+                           const float* shift, const float* mean, const float* invstd, int relu, double* partials,
+                           cudaStream_t st) {
+  const int ncols = d->cin_pad < d->x_cstride ? d->cin_pad : d->x_cstride;
+  Tc2BnReduce b{y_prev, y_prev_cs, relu, scale, shift, mean, invstd};
+  return conv_tc2_run(d, 1, dy_hi, dy_lo, d->Cout, d->y_cstride, wh_hi, wh_lo, d->cin_pad, d->y_cstride, nullptr, 0,
+                      dx, nullptr, d->x_cstride, ncols, ncols, st, nullptr, 0, partials, &b);
 }
 
 int conv_tc_dgrad(const immb_conv_desc* d, const float* dy_hi, const float* dy_lo, const float* wh_hi,

@@ -45,7 +45,12 @@ struct Tc2Params {
   uint32_t a_off[9];         // byte offset of each tap's first row inside the box
   const float* relu_src;     // optional [.., relu_cs] tensor laid out like the output: out = (relu_src > 0) ? out : 0
   int relu_cs;               // (backward of the ReLU of the layer that produced the dgrad's input, fused)
-  double* stats;             // optional BN batch-statistics partials: row (cta*4 + epilogue warp) of [2][n_cols] doubles
+  double* stats;             // optional per-channel reduction partials: row (cta*4 + epilogue warp) of [2][n_cols] doubles
+  int stats_mode;            // 1: forward BN moments (sum y, sum y^2);  2: BN-backward sums of the layer that produced
+                             // this dgrad's input (sum dz, sum dz*xhat), dz = g * relu'(z), xhat = (y - mean) * invstd
+  const float* bnr_y;        // mode 2: that layer's raw conv output y [.., bnr_ycs] and its BN constants [n_cols]
+  int bnr_ycs, bnr_relu;
+  const float *bnr_scale, *bnr_shift, *bnr_mean, *bnr_invstd;
 };
 
 template <int BN, int PASSES>
@@ -318,15 +323,20 @@ template <int BN2, int PASSES>
 struct Tc2PairCfg {
   static constexpr uint32_t NPLA = PASSES >= 2 ? 2 : 1;
   static constexpr uint32_t NPLB = PASSES == 3 ? 2 : 1;
-  static constexpr uint32_t A_PLANE = 18 * 16 * 128;
+  // one activation plane of a slot: the 18 x 10-pixel halo box (23040 B) or the first layer's 22 x 8 row-window box
+  // (22528 B), rounded up to the 1024-byte swizzle pattern
+  static constexpr uint32_t A_PLANE = 23 * 1024;
   static constexpr uint32_t A_SLOT = A_PLANE * NPLA;
-  static constexpr uint32_t A_SLOTS = 2;
+#ifndef IMMB_PAIR_A_SLOTS
+#define IMMB_PAIR_A_SLOTS 3
+#endif
+  static constexpr uint32_t A_SLOTS = IMMB_PAIR_A_SLOTS;
   static constexpr uint32_t BH = BN2 / 2;                     // weight rows held by each CTA
   static constexpr uint32_t B_PLANE = BH * 128;
   static constexpr uint32_t B_SLOT = B_PLANE * NPLB;
   // fused BN statistics (3-pass layers only: the frozen 2-pass tower has no BN): per epilogue warp, per N tile (<= 2),
   // sum and sum of squares of BN2 channels in double
-  static constexpr uint32_t STATS_BYTES = PASSES == 3 ? 4 * 2 * 2 * BN2 * 8 : 0;
+  static constexpr uint32_t STATS_BYTES = PASSES == 3 ? 4 * 2 * 2 * BN2 * 8 + 4 * 256 * 4 : 0;     // + BN constants [4][256]
   static constexpr uint32_t ROOM = 232448 - 1024 - 512 - A_SLOTS * A_SLOT - STATS_BYTES;
   static constexpr uint32_t B_FIT = ROOM / B_SLOT;
   static constexpr uint32_t B_SLOTS = B_FIT > 6 ? 6 : B_FIT;
@@ -343,7 +353,9 @@ struct Tc2PairCfg {
   static_assert(BN2 % 32 == 0 && BN2 <= 256, "pair N tile: multiple of 32 up to 256");
 };
 
-template <int BN2, int PASSES>
+// BNR: the BN-backward-sums epilogue (stats_mode 2) is a separate instantiation so that its registers do not weigh on
+// the forward / plain-dgrad variants (a high register count squeezes the glue kernels that co-run on the side streams)
+template <int BN2, int PASSES, bool BNR>
 __global__ void __launch_bounds__(192, 1)
 conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
                      const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
@@ -500,8 +512,20 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
                       ((reinterpret_cast<uintptr_t>(p.out_lo) & 31) == 0);
     const bool do_stats = PASSES == 3 && p.stats != nullptr;
     double* my_stats = stats_sm + (size_t)q * (2 * 2 * BN2);      // this warp's private rows: no cross-warp races
-    if (do_stats)
+    float* bn_const = reinterpret_cast<float*>(stats_sm + 4 * 2 * 2 * BN2);     // [scale | shift | mean | invstd][256]
+    if (do_stats) {
       for (int i = lane; i < 2 * 2 * BN2; i += 32) my_stats[i] = 0.0;
+      if (BNR) {
+        // every epilogue warp stages the full table itself (identical values: benign), so no cross-warp barrier is needed
+        for (int c = lane; c < p.n_cols && c < 256; c += 32) {
+          bn_const[c] = __ldg(p.bnr_scale + c);
+          bn_const[256 + c] = __ldg(p.bnr_shift + c);
+          bn_const[512 + c] = __ldg(p.bnr_mean + c);
+          bn_const[768 + c] = __ldg(p.bnr_invstd + c);
+        }
+      }
+      __syncwarp();
+    }
     uint32_t ti = 0;
     for (int t = tile0; t < n_iter_total; t += tstep) {
       int img, th, tw, n_off;
@@ -534,11 +558,28 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
           // per-channel sum / sum of squares of this warp's 32 pixel rows: butterfly transpose-reduce (31 shuffles per
           // quantity; lane j ends up with channel col0 + j), accumulated in double in the warp's own smem rows
           float s1[32], s2[32];
+          if (BNR) {
+            const float* yp = p.bnr_y + pix * p.bnr_ycs + col0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float t = (col0 + j < p.n_cols) ? v[j] : 0.f;
-            s1[j] = t;
-            s2[j] = t * t;
+            for (int j = 0; j < 32; j += 4) {
+              const float4 yy = __ldg(reinterpret_cast<const float4*>(yp + j));       // n_cols % 32 == 0 in this mode
+              const float ya[4] = {yy.x, yy.y, yy.z, yy.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int c = col0 + j + u;
+                const float z = fmaf(ya[u], bn_const[c], bn_const[256 + c]);
+                const float dz = (p.bnr_relu && !(z > 0.f)) ? 0.f : v[j + u];
+                s1[j + u] = dz;
+                s2[j + u] = dz * ((ya[u] - bn_const[512 + c]) * bn_const[768 + c]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float t = (col0 + j < p.n_cols) ? v[j] : 0.f;
+              s1[j] = t;
+              s2[j] = t * t;
+            }
           }
 #pragma unroll
           for (int off = 16; off >= 1; off >>= 1) {
@@ -744,14 +785,17 @@ static int pair_bn(int ncols, int passes) {
   return cap;
 }
 
-template <int BN2, int PASSES>
+template <int BN2, int PASSES, bool BNR = false>
 static int launch_tc2_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                            const CUtensorMap& b_lo, const Tc2Params& p, cudaStream_t st) {
   if constexpr (PASSES == 3 && BN2 > 128) {
     return set_error(IMMB_ERR_INVALID, "conv_tc2 pair: 3-pass N tile %d > 128", BN2);
+  } else if constexpr (BNR && PASSES != 3) {
+    return set_error(IMMB_ERR_INVALID, "conv_tc2 pair: the BN-backward epilogue exists for the 3-pass product only");
   } else {
+  if (!BNR && p.stats_mode == 2) return launch_tc2_pair<BN2, PASSES, true>(a_hi, a_lo, b_hi, b_lo, p, st);
   using Cfg = Tc2PairCfg<BN2, PASSES>;
-  auto kern = conv_tc2_pair_kernel<BN2, PASSES>;
+  auto kern = conv_tc2_pair_kernel<BN2, PASSES, BNR>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
@@ -783,7 +827,7 @@ static int launch_tc2_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, con
 int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const float* act_lo, int act_c, int act_cs,
                  const float* w_hi, const float* w_lo, int w_rows, int kd, const float* bias, int relu,
                  float* out_hi, float* out_lo, int ocs, int ncols, int n_store, cudaStream_t st,
-                 const float* relu_src, int relu_cs, double* stats) {
+                 const float* relu_src, int relu_cs, double* stats, const Tc2BnReduce* bnr) {
   const int passes = d->precision == IMMB_PREC_TF32 ? 1 : (d->precision == IMMB_PREC_TF32X2 ? 2 : 3);
   Tc2Params p;
   memset(&p, 0, sizeof(p));
@@ -810,14 +854,19 @@ int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const flo
   // halo box width: the pair kernel fetches exactly the 8 + 2 columns a tile needs (the descriptors' group stride is
   // then 10 * 128 B; groups may start anywhere on a 128-byte boundary because both TMA and the MMA unit swizzle on
   // absolute shared-memory address bits); the single-CTA kernel keeps its 16-pixel box (SBO = 2048 B).
-  static int pair_box_w = -1;
-  if (pair_box_w < 0) { const char* e = getenv("IMMB_TC2_BOXW"); pair_box_w = e ? atoi(e) : 10; }
-  const int box_w = pair ? pair_box_w : 16;
+  const int box_w = pair ? 10 : 16;        // (a 16-pixel box for the pair kernel measured 0.6 % slower and needs 60 % more smem)
   p.n_taps = 9; p.a_sbo = box_w * 128; p.a_plane_bytes = 18 * box_w * 128; p.box_dw = -1; p.box_dh = -1;
   for (int i = 0; i < 9; ++i) p.a_off[i] = (uint32_t)(p.taps[i].ro * box_w + p.taps[i].so) * 128u;
   p.out_hi = out_hi; p.out_lo = out_lo; p.bias = bias; p.relu = relu;
   p.H = d->H; p.W = d->W; p.ocs = ocs; p.n_cols = ncols; p.n_store = n_store;
-  p.relu_src = relu_src; p.relu_cs = relu_cs; p.stats = stats;
+  p.relu_src = relu_src; p.relu_cs = relu_cs; p.stats = stats; p.stats_mode = stats ? 1 : 0;
+  if (bnr) {
+    if (!stats || ncols % 32 || ncols > 256)
+      return set_error(IMMB_ERR_UNSUPPORTED, "conv_tc2: fused BN-backward sums need a partials buffer and 32 | channels <= 256");
+    p.stats_mode = 2;
+    p.bnr_y = bnr->y; p.bnr_ycs = bnr->ycs; p.bnr_relu = bnr->relu;
+    p.bnr_scale = bnr->scale; p.bnr_shift = bnr->shift; p.bnr_mean = bnr->mean; p.bnr_invstd = bnr->invstd;
+  }
   if (stats && (!pair || passes != 3 || p.n_tiles_n > 2))
     return set_error(IMMB_ERR_UNSUPPORTED, "conv_tc2: fused BN statistics need the 3-pass pair kernel and <= 2 N tiles");
   if (relu_src && !pair) return set_error(IMMB_ERR_UNSUPPORTED, "conv_tc2: the fused ReLU-backward epilogue needs the pair kernel");
@@ -894,6 +943,20 @@ int conv_tc2_fwd_stats_rows(const immb_conv_desc* d) {
   return 2 * pairs * 4;
 }
 
+// rows of BN-backward partials the pair kernel writes for this dgrad (4 per CTA), 0 = not served
+int conv_tc2_dgrad_stats_rows(const immb_conv_desc* d) {
+  if (!(conv_tc2_eligible(d, 1) && conv_tc2_pair_mode() == 1) || d->precision != IMMB_PREC_TF32X3) return 0;
+  const int ncols = d->cin_pad < d->x_cstride ? d->cin_pad : d->x_cstride;
+  if (ncols != d->Cin || ncols % 32 || ncols > 256) return 0;
+  const int m_tiles = (d->W / 8) * (d->H / 16) * d->N;
+  const int bn = pair_bn(ncols, 3);
+  const int n_tiles_n = ceil_div(ncols, bn);
+  if (n_tiles_n > 2) return 0;
+  const int total_pairs = ceil_div(m_tiles, 2) * n_tiles_n;
+  const int pairs = total_pairs < kNumSMs / 2 ? total_pairs : kNumSMs / 2;
+  return 2 * pairs * 4;
+}
+
 int conv_tc2_rowwin_fwd(const immb_conv_desc* d, const float* x_hi, const float* x_lo, const float* wp_hi,
                         const float* wp_lo, const float* bias, int relu, float* y_hi, float* y_lo, cudaStream_t st,
                         double* stats) {
@@ -911,7 +974,7 @@ int conv_tc2_rowwin_fwd(const immb_conv_desc* d, const float* x_hi, const float*
   for (int r = 0; r < 7; ++r) { p.taps[r].b_tap = r; p.a_off[r] = (uint32_t)r * 1024u; }
   p.out_hi = y_hi; p.out_lo = y_lo; p.bias = bias; p.relu = relu;
   p.H = d->H; p.W = d->W; p.ocs = d->y_cstride; p.n_cols = d->Cout; p.n_store = d->Cout;
-  p.stats = stats;
+  p.stats = stats; p.stats_mode = stats ? 1 : 0;
   if (stats && (passes != 3 || p.n_tiles_n > 2))
     return set_error(IMMB_ERR_UNSUPPORTED, "conv_tc2 rowwin: fused BN statistics need the 3-pass kernel and <= 2 N tiles");
   CUtensorMap a_hi, a_lo, b_hi, b_lo;

@@ -219,6 +219,12 @@ class IMMEngine(object):
       cin, xcs = cout, cout
       if up:
         size *= 2
+    # producer of each conv's input when that producer's BN-backward sums can ride in this conv's dgrad epilogue
+    for lst in list(self.enc_layers.values()) + [self.ren_layers]:
+      for i, L in enumerate(lst):
+        P = lst[i - 1] if i > 0 else None
+        L.producer = P if (P is not None and P.bn and not P.up2x and P.cout == L.cin and L.xcs == L.cin) else None
+    self.pose_conv.producer = None
     # frozen VGG16 up to the deepest level the loss reads (conv3_3 / conv4_3 feed pools)
     needed = [c for c in self.comp if c != 'input']
     last = max((i for i, it in enumerate(VGG_ORDER) if not isinstance(it, str) and it[0] in needed), default=-1)
@@ -406,6 +412,10 @@ class IMMEngine(object):
     for L in self.layers.values():
       L.stats_rows = int(_lib.lib().immb_conv2d_fwd_stats_rows(L.desc())) if (L.bn and L.ycs == L.cout) else 0
       n_scr = max(n_scr, L.stats_rows * 2 * L.cout)
+      L.bwd_rows = 0                   # > 0 while this layer's BN-backward partials sit in the scratch buffer
+      L.dgrad_stats_rows = (int(_lib.lib().immb_conv2d_dgrad_stats_rows(L.desc()))
+                            if (L.needs_dgrad and getattr(L, 'producer', None) is not None) else 0)
+      n_scr = max(n_scr, L.dgrad_stats_rows * 2 * L.cin)
     self.bn_scratch = torch.empty(n_scr, dtype=torch.float64, device=dev)
     self.bn_scratch_pose = torch.empty(n_scr, dtype=torch.float64, device=dev)      # the pose-branch stream's own scratch
 
@@ -675,8 +685,13 @@ class IMMEngine(object):
         g, gcs = L.g_low, L.cout
       relu = 1 if L.relu else 0
       sc = self.bn_scratch if scratch is None else scratch
-      call('immb_bn_bwd_reduce', g, gcs, L.y, L.cout, npix, L.cout, L.scale, L.shift, L.mean, L.invstd, relu,
-           L.bsums, sc, sc.numel(), st)
+      if L.bwd_rows > 0:
+        # sum(dz), sum(dz * xhat) were accumulated by the consumer's dgrad epilogue: fixed-order second level only
+        call('immb_bn_stats_from_partials', sc, L.bwd_rows, L.cout, L.bsums, st)
+        L.bwd_rows = 0
+      else:
+        call('immb_bn_bwd_reduce', g, gcs, L.y, L.cout, npix, L.cout, L.scale, L.shift, L.mean, L.invstd, relu,
+             L.bsums, sc, sc.numel(), st)
       call('immb_bn_bwd_apply', g, gcs, L.y, L.cout, npix, L.cout, L.scale, L.shift, L.mean, L.invstd, relu,
            L.bsums, L.dy.hi, L.dy.lo, L.dgamma, L.dbeta, L.dbias_acc, sc, sc.numel(), st)
       dy = L.dy
@@ -698,7 +713,14 @@ class IMMEngine(object):
     else:
       call('immb_conv2d_wgrad', d, L.x.hi, L.x.lo, dy.hi, dy.lo, L.dw, self.workspace, self.workspace.numel(), st)
     if L.needs_dgrad:
-      call('immb_conv2d_dgrad', d, dy.hi, dy.lo, L.w, L.wh.hi, L.wh.lo, L.dx, st)
+      P = L.producer
+      if P is not None and L.dgrad_stats_rows > 0 and self.fuse_bn_stats and self.training:
+        sc = self.bn_scratch if scratch is None else scratch
+        call('immb_conv2d_dgrad_bnreduce', d, dy.hi, dy.lo, L.wh.hi, L.wh.lo, L.dx, P.y, P.ycs, P.scale, P.shift,
+             P.mean, P.invstd, 1 if P.relu else 0, sc, sc.numel(), st)
+        P.bwd_rows = L.dgrad_stats_rows
+      else:
+        call('immb_conv2d_dgrad', d, dy.hi, dy.lo, L.w, L.wh.hi, L.wh.lo, L.dx, st)
       return L.dx
     return None
 

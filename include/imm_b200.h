@@ -112,6 +112,17 @@ int immb_conv2d_fwd_bnstats(const immb_conv_desc* d, const float* x_hi, const fl
                             const float* wp_lo, const float* bias, float* y, double* partials, size_t partial_elems,
                             void* stream);
 int immb_bn_stats_from_partials(const double* partials, int rows, int C, double* sums, void* stream);
+/* dgrad that also accumulates, in its epilogue, the two per-channel sums of the BN backward of the layer that produced
+ * the conv's input (tf.layers.batch_normalization gradient, nn_utils.py:201-209): sum(dz) and sum(dz * xhat) with
+ * dz = dx * [relu ? y*scale+shift > 0 : 1], xhat = (y - mean) * invstd, y = that layer's raw conv output
+ * [N,H,W,y_prev_cstride].  dx is written as by immb_conv2d_dgrad; partials = rows x [2][Cin] doubles
+ * (rows = immb_conv2d_dgrad_stats_rows(d), 0 when not served), reduced by immb_bn_stats_from_partials into the
+ * `sums` immb_bn_bwd_apply reads -- replaces the immb_bn_bwd_reduce pass over dx and y. */
+int immb_conv2d_dgrad_stats_rows(const immb_conv_desc* d);
+int immb_conv2d_dgrad_bnreduce(const immb_conv_desc* d, const float* dy_hi, const float* dy_lo, const float* wh_hi,
+                               const float* wh_lo, float* dx, const float* y_prev, int y_prev_cstride,
+                               const float* scale, const float* shift, const float* mean, const float* invstd,
+                               int relu, double* partials, size_t partial_elems, void* stream);
 /* dgrad fused with the backward of the ReLU that produced the conv's input (vgg16.py:229-236: activations are stored
  * post-ReLU) and with the TF32 split of the result: out_{hi,lo}[N,H,W,x_cstride] = split(dgrad(dy) * [act_hi > 0]),
  * act_hi = hi plane of the conv's (post-ReLU) input, channel stride act_cstride.  Only shapes served by the halo pair

@@ -598,3 +598,48 @@ def test_conv_fwd_fused_bn_statistics(case):
   # single-pass TF32 / shapes outside the pair kernel: not offered
   d1 = conv_desc(N, 8, 8, 32, 32, 3, 1, None, engine=_lib.ENGINE_TC)
   assert int(_lib.lib().immb_conv2d_fwd_stats_rows(d1)) == 0
+
+
+@pytest.mark.parametrize('case', [(2, 32, 32, 32, 32, 1), (1, 16, 16, 256, 256, 1), (3, 16, 16, 64, 128, 0)])
+def test_conv_dgrad_fused_bn_backward_sums(case):
+  """immb_conv2d_dgrad_bnreduce: dx is bit-identical to immb_conv2d_dgrad, and the per-channel sums of the producing
+  layer's BN backward (sum dz, sum dz*xhat; nn_utils.py:201-209) accumulated in the epilogue match immb_bn_bwd_reduce
+  run on that dx."""
+  N, H, W, Cin, Cout, relu = case
+  g = torch.Generator().manual_seed(sum(case) + 5)
+  dev = 'cuda'
+  w = torch.randn(3, 3, Cin, Cout, generator=g) * 0.05
+  gy = torch.randn(N, H, W, Cout, generator=g)
+  y_prev = torch.randn(N, H, W, Cin, generator=g) * 3 + 1          # raw conv output of the producing layer
+  scale, shift = torch.rand(Cin, generator=g) + 0.5, torch.randn(Cin, generator=g)
+  mean, invstd = torch.randn(Cin, generator=g), torch.rand(Cin, generator=g) + 0.2
+  d = conv_desc(N, H, W, Cin, Cout, 3, 1, None, engine=_lib.ENGINE_TC)
+  rows = int(_lib.lib().immb_conv2d_dgrad_stats_rows(d))
+  assert rows > 0
+  cp = d.cin_pad
+  wph, wpl = torch.empty(9, Cout, cp, device=dev), torch.empty(9, Cout, cp, device=dev)
+  whh, whl = torch.empty(9, cp, Cout, device=dev), torch.empty(9, cp, Cout, device=dev)
+  call('immb_pack_weights', w.to(dev), 3, 3, Cin, Cout, cp, Cout, wph, wpl, whh, whl, ST())
+  gh, gl = (t.to(dev) for t in split(gy))
+  dx0 = torch.empty(N, H, W, Cin, device=dev)
+  call('immb_conv2d_dgrad', d, gh, gl, None, whh, whl, dx0, ST())
+  dx1 = torch.full_like(dx0, float('nan'))
+  part = torch.full((rows * 2 * Cin,), float('nan'), dtype=torch.float64, device=dev)
+  args = [t.to(dev) for t in (y_prev, scale, shift, mean, invstd)]
+  call('immb_conv2d_dgrad_bnreduce', d, gh, gl, whh, whl, dx1, args[0], Cin, args[1], args[2], args[3], args[4], relu,
+       part, part.numel(), ST())
+  sums = torch.zeros(2 * Cin, dtype=torch.float64, device=dev)
+  call('immb_bn_stats_from_partials', part, rows, Cin, sums, ST())
+  ref = torch.zeros(2 * Cin, dtype=torch.float64, device=dev)
+  call('immb_bn_bwd_reduce', dx0, Cin, args[0], Cin, N * H * W, Cin, args[1], args[2], args[3], args[4], relu, ref,
+       None, 0, ST())
+  torch.cuda.synchronize()
+  assert torch.equal(dx0, dx1) and bool(torch.isfinite(part).all())
+  dz = dx0.double().cpu()
+  if relu:
+    dz = dz * ((y_prev.double() * scale.double() + shift.double()) > 0)
+  xh = (y_prev.double() - mean.double()) * invstd.double()
+  want = torch.cat([dz.reshape(-1, Cin).sum(0), (dz * xh).reshape(-1, Cin).sum(0)])
+  tol = 1e-5 * float(want.abs().max())
+  np.testing.assert_allclose(sums.cpu().numpy(), want.numpy(), rtol=1e-4, atol=tol)
+  np.testing.assert_allclose(sums.cpu().numpy(), ref.cpu().numpy(), rtol=1e-4, atol=tol)
