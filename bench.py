@@ -38,18 +38,21 @@ def load_peaks():
 
 
 class ClockSampler(object):
-  """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-  Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+  """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md).  The sampler is started
+  before the warm-up steps (nvidia-smi needs a few hundred ms to come up) and only the rows whose timestamp falls inside
+  [mark_begin, mark_end] are reported."""
+  Q = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
        'clocks_event_reasons.sw_power_cap')
 
   def __init__(self, gpu_index=0):
     self.rows, self.proc, self.gpu = [], None, gpu_index
+    self.t0 = self.t1 = None
 
   def start(self):
     try:
       self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
-                                    '--format=csv,noheader,nounits', '-lms', '100'],
+                                    '--format=csv,noheader,nounits', '-lms', '20'],
                                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
       self.t = threading.Thread(target=self._read, daemon=True)
       self.t.start()
@@ -58,18 +61,29 @@ class ClockSampler(object):
 
   def _read(self):
     for line in self.proc.stdout:
-      self.rows.append([x.strip() for x in line.split(',')])
+      self.rows.append((time.time(), [x.strip() for x in line.split(',')]))
+
+  def mark_begin(self):
+    self.t0 = time.time()
+
+  def mark_end(self):
+    self.t1 = time.time()
 
   def stop(self):
     if self.proc is None:
       return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+    time.sleep(0.05)
     self.proc.terminate()
     try:
       self.proc.wait(timeout=2)
     except Exception:
       self.proc.kill()
+    inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t)]
+    window = 'timed region'
+    if len(inside) < 3:           # very short timed regions: fall back to every sample taken under load (warm-up + timed)
+      inside, window = [r for _, r in self.rows], 'warm-up + timed region'
     sm, mx, reasons, power = [], [], set(), []
-    for r in self.rows:
+    for r in inside:
       try:
         sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
         for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
@@ -79,7 +93,8 @@ class ClockSampler(object):
         pass
     sm.sort()
     return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-            'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+            'power_w_max': max(power) if power else None, 'samples': len(sm), 'window': window,
+            'reasons': sorted(reasons)}
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -190,12 +205,13 @@ def main_cuda(args):
       eng.train_step(d['image'], d['future_image'], d['mask'], clip_value=1.0, lr=optim.lr(eng.global_step),
                      allreduce=allreduce)
 
-  for i in range(args.warmup):
-    step_resident(i)
-  barrier()
   sampler = ClockSampler(local_rank)
   if rank == 0:
     sampler.start()
+  for i in range(args.warmup):
+    step_resident(i)
+  barrier()
+  sampler.mark_begin()
   n0, r0 = _lib.launch_count(), eng.graph_replays
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   e0.record()
@@ -203,6 +219,7 @@ def main_cuda(args):
     step_resident(i)
   e1.record()
   barrier()
+  sampler.mark_end()
   # kernels launched in the timed region: eager launches + (graph replays x kernels recorded per graph)
   launches = _lib.launch_count() - n0 + (eng.graph_replays - r0) * eng.graph_launches_per_step
   ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
