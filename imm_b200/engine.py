@@ -472,20 +472,40 @@ class IMMEngine(object):
         mu = np.asarray(bn['0']) / np.asarray(bn['2'])
         W = W / sigma
         bias = (bias - mu) / sigma
-      cin_true = 1 if L.name == 'conv1_1' else L.cin
-      assert tuple(W.shape) == (3, 3, cin_true, L.cout), 'Incorrect weights shape for %s' % L.name   # vgg16.py:171
-      W = np.ascontiguousarray(W, dtype=np.float32)
-      if self.vgg_tf32_weights and L.name != 'conv1_1':      # conv1_1 runs in exact fp32 on the CUDA cores
-        bits = W.view(np.uint32).astype(np.uint64)
-        bits = (bits + 0x0FFF + ((bits >> 13) & 1)) & 0xFFFFE000          # round-to-nearest-even to 10 mantissa bits
-        W = bits.astype(np.uint32).view(np.float32)
-        L.precision_override = _lib.PREC_TF32X2
-      L.w.copy_(torch.from_numpy(W).reshape(L.w.shape))
-      L.b.copy_(torch.from_numpy(np.ascontiguousarray(bias, dtype=np.float32)))
-      self.vgg_params['SelfSupReconstructionLoss/vgg16/%s/weights' % L.name] = L.w.view(3, 3, cin_true, L.cout)
-      self.vgg_params['SelfSupReconstructionLoss/vgg16/%s/biases' % L.name] = L.b
-      self._pack(L)
+      self._set_vgg_layer(L, W, bias)
     self.vgg_loaded = True
+
+  def load_vgg_hwio(self, variables):
+    """Frozen tower from already-prepared TF variables {'SelfSupReconstructionLoss/vgg16/<conv>/weights': HWIO,
+    '.../biases': [Cout]} -- the form the reference's checkpoints hold them in (tf.global_variables() are all saved,
+    cnn_train_multi.py:439; vgg16.py:175-179), BN already folded.  Returns False if a needed layer is missing."""
+    pre = 'SelfSupReconstructionLoss/vgg16/'
+    convs = [item for kind, item, cin, size in self.vgg_seq if kind == 'conv']
+    if not all((pre + L.name + '/weights') in variables and (pre + L.name + '/biases') in variables for L in convs):
+      return False
+    self.vgg_params = OrderedDict()
+    for L in convs:
+      W = np.ascontiguousarray(np.asarray(variables[pre + L.name + '/weights'], dtype=np.float32))
+      bias = np.asarray(variables[pre + L.name + '/biases'], dtype=np.float32)
+      self._set_vgg_layer(L, W, bias)
+    self.vgg_loaded = True
+    return True
+
+  def _set_vgg_layer(self, L, W, bias):
+    """W: HWIO float32 (BN folded), bias [Cout]."""
+    cin_true = 1 if L.name == 'conv1_1' else L.cin
+    assert tuple(W.shape) == (3, 3, cin_true, L.cout), 'Incorrect weights shape for %s' % L.name   # vgg16.py:171
+    W = np.ascontiguousarray(W, dtype=np.float32)
+    if self.vgg_tf32_weights and L.name != 'conv1_1':      # conv1_1 runs in exact fp32 on the CUDA cores
+      bits = W.view(np.uint32).astype(np.uint64)
+      bits = (bits + 0x0FFF + ((bits >> 13) & 1)) & 0xFFFFE000          # round-to-nearest-even to 10 mantissa bits
+      W = bits.astype(np.uint32).view(np.float32)
+      L.precision_override = _lib.PREC_TF32X2
+    L.w.copy_(torch.from_numpy(W).reshape(L.w.shape))
+    L.b.copy_(torch.from_numpy(np.ascontiguousarray(bias, dtype=np.float32)))
+    self.vgg_params['SelfSupReconstructionLoss/vgg16/%s/weights' % L.name] = L.w.view(3, 3, cin_true, L.cout)
+    self.vgg_params['SelfSupReconstructionLoss/vgg16/%s/biases' % L.name] = L.b
+    self._pack(L)
 
   def _pack(self, L):
     if L.x_layout == _lib.XLAYOUT_ROWWIN4:
@@ -872,7 +892,12 @@ class IMMEngine(object):
       if self._graphs is not None and self._graph_key != key:
         self._graphs = None                                     # hyper-parameters baked into the graph changed
       if self._graphs is None and self._graph_warm >= 2:
-        self._capture_graphs(key, image, future_image, mask)
+        try:
+          self._capture_graphs(key, image, future_image, mask)
+        except Exception as e:      # e.g. a foreign thread touching CUDA during capture: keep training, eagerly
+          import warnings
+          warnings.warn('CUDA-graph capture of the training step failed (%s); continuing with eager launches' % (e,))
+          self.use_graph, self._graphs = False, None
       if self._graphs is not None:
         self.g_image.copy_(image, non_blocking=True)
         self.g_future.copy_(future_image, non_blocking=True)
@@ -909,14 +934,14 @@ class IMMEngine(object):
     cap = torch.cuda.Stream(device=dev)
     g_fb, g_opt = torch.cuda.CUDAGraph(), None
     n0 = _lib.launch_count()
-    with torch.cuda.graph(g_fb, stream=cap):
+    with torch.cuda.graph(g_fb, stream=cap, capture_error_mode='thread_local'):
       self.forward(self.g_image, self.g_future, self.g_mask, training=True, build_loss=True)
       self.backward()
       if not has_allreduce:
         self._optimizer_kernels(clip_value, 0.0, beta1, beta2, eps, lr_t_dev=self.d_lr_t)
     if has_allreduce:
       g_opt = torch.cuda.CUDAGraph()
-      with torch.cuda.graph(g_opt, stream=cap):
+      with torch.cuda.graph(g_opt, stream=cap, capture_error_mode='thread_local'):
         self._optimizer_kernels(clip_value, 0.0, beta1, beta2, eps, lr_t_dev=self.d_lr_t)
     torch.cuda.synchronize(dev)
     # capture does not execute anything, but be explicit that model state is exactly what it was

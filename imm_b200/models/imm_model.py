@@ -218,6 +218,13 @@ class IMMModel(BaseModel):
         else:                         # both powers underflowed in fp32 (> ~87k steps): the bias correction is 1 anyway
           eng.adam_t = max(int(float(sd.get('global_step', 0))) + 1, 100000)
     eng.load_state(params, buffers, adam_m, adam_v)
+    if vars_to_restore == 'all':
+      # the frozen tower's weights/biases are global variables too: a full checkpoint (the reference's own included)
+      # carries them, so a run can start from a checkpoint alone when the Caffe HDF5 file is not at hand
+      np_vars = {k: (v.numpy() if isinstance(v, torch.Tensor) else v) for k, v in sd.items()
+                 if k.startswith('SelfSupReconstructionLoss/vgg16/')}
+      if np_vars:
+        eng.load_vgg_hwio(np_vars)
     if reset_global_step >= 0:
       eng.global_step = float(reset_global_step)
     elif 'global_step' in sd:

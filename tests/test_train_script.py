@@ -79,6 +79,12 @@ def test_train_script_runs_checkpoints_and_restores(tmp_path):
   m.load_state_dict(sd, vars_to_restore='all')
   assert torch.equal(m.engine.params[g].cpu(), sd[g])
   assert torch.equal(m.engine.adam_v[k].cpu(), sd[k + '/Adam_1'])
+  # a full restore also takes the frozen tower from the checkpoint (its weights are global variables too): the fresh
+  # model above was built with VGG seed 1 like the training run, so perturb it first to see the restore act
+  vk = 'SelfSupReconstructionLoss/vgg16/conv3_2/weights'
+  m.engine.vgg_params[vk].mul_(0.5)
+  m.load_state_dict(sd, vars_to_restore='all')
+  assert torch.equal(m.engine.vgg_params[vk].cpu(), sd[vk])
   assert m.engine.global_step == float(sd['global_step']) == 3.0   # -1 + 4 applied steps; the FILE is named by the loop step (2)
   assert m.engine.adam_t == 4          # steps -1..2 applied; recovered from beta1_power = 0.9^(t+1)
   # --checkpoint restore through the CLI path (cnn_train_multi.py:404-433) continues from global_step + 0
