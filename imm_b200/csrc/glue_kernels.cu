@@ -609,6 +609,54 @@ __global__ void perceptual_level_sum4_kernel(const float* __restrict__ fg_hi, co
   }
 }
 
+// 2x2/2 max pool of BOTH halves of a perceptual level ([gt ; pred] stacked on the batch axis) fused with that level's
+// masked squared-difference sum (imm_model.py:143-147): the pool reads every element of the level anyway, so the
+// separate perceptual_level_sum pass (4 more planes) disappears.  acc[0] += sum mask * (f_gt - f_pred)^2.
+__global__ void maxpool2x2_fwd_levelsum4_kernel(const float* __restrict__ x_hi, const float* __restrict__ x_lo, int B,
+                                                int H, int W, int C, float* o_hi, float* o_lo,
+                                                const float* __restrict__ mask, int R, double* acc) {
+  const int Ho = H / 2, Wo = W / 2, q = C >> 2;
+  const int64_t total = (int64_t)B * Ho * Wo * q;
+  const size_t half_in = (size_t)B * H * W * C, half_out = (size_t)B * Ho * Wo * C;
+  const int s = R / H;
+  double local = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % q) * 4;
+    int64_t p = i / q;
+    int wo = (int)(p % Wo);
+    int64_t t = p / Wo;
+    int ho = (int)(t % Ho);
+    int n = (int)(t / Ho);
+    size_t base = (((size_t)n * H + 2 * ho) * W + 2 * wo) * C + c;
+    const size_t off[4] = {0, (size_t)C, (size_t)W * C, (size_t)W * C + C};
+    float4 vg = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), vp = vg;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 g = load_split4(x_hi, x_lo, base + off[k]);
+      const float4 pr = load_split4(x_hi, x_lo, half_in + base + off[k]);
+      vg = make_float4(fmaxf(vg.x, g.x), fmaxf(vg.y, g.y), fmaxf(vg.z, g.z), fmaxf(vg.w, g.w));
+      vp = make_float4(fmaxf(vp.x, pr.x), fmaxf(vp.y, pr.y), fmaxf(vp.z, pr.z), fmaxf(vp.w, pr.w));
+      const int hh = 2 * ho + (k >> 1), ww = 2 * wo + (k & 1);
+      const float m = mask ? __ldg(mask + ((int64_t)n * R + (int64_t)hh * s) * R + (int64_t)ww * s) : 1.f;
+      const float dx = g.x - pr.x, dy = g.y - pr.y, dz = g.z - pr.z, dw = g.w - pr.w;
+      local += (double)(m * (dx * dx)) + (double)(m * (dy * dy)) + (double)(m * (dz * dz)) + (double)(m * (dw * dw));
+    }
+    store_split4(o_hi, o_lo, (size_t)(p * C + c), vg);
+    store_split4(o_hi, o_lo, half_out + (size_t)(p * C + c), vp);
+  }
+  local = warp_sum(local);
+  __shared__ double sm[32];
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) sm[wid] = local;
+  __syncthreads();
+  if (wid == 0) {
+    double v = lane < (blockDim.x >> 5) ? sm[lane] : 0.0;
+    v = warp_sum(v);
+    if (lane == 0) atomicAdd(acc, v);
+  }
+}
+
 __global__ void vgg_bwd_combine4_kernel(const float* __restrict__ g_next, const float* __restrict__ fg_hi,
                                         const float* __restrict__ fg_lo, const float* __restrict__ fp_hi,
                                         const float* __restrict__ fp_lo, int B, int h, int w, int C,
@@ -1509,6 +1557,18 @@ extern "C" int immb_maxpool2x2_fwd(const float* x_hi, const float* x_lo, int N, 
     maxpool2x2_fwd_kernel<<<ew_grid((int64_t)N * (H / 2) * (W / 2) * C), 256, 0, ST(stream)>>>(x_hi, x_lo, N, H,
                                                                                               W, C, o_hi, o_lo);
   return check_launch("maxpool2x2_fwd");
+}
+
+extern "C" int immb_maxpool2x2_fwd_levelsum(const float* x_hi, const float* x_lo, int B, int H, int W, int C,
+                                            float* o_hi, float* o_lo, const float* mask, int R, double* acc,
+                                            void* stream) {
+  IMMB_REQUIRE(x_hi && x_lo && o_hi && o_lo && acc && B > 0 && (H % 2 == 0) && (W % 2 == 0) && C % 4 == 0,
+               "maxpool_fwd_levelsum: bad args (even sizes, split planes, 4 | C)");
+  IMMB_REQUIRE(!mask || (R >= H && R % H == 0), "maxpool_fwd_levelsum: mask resolution must be a multiple of the level's");
+  IMMB_REQUIRE(aligned16(x_hi) && aligned16(x_lo) && aligned16(o_hi) && aligned16(o_lo), "maxpool_fwd_levelsum: alignment");
+  maxpool2x2_fwd_levelsum4_kernel<<<ew_grid((int64_t)B * (H / 2) * (W / 2) * C / 4), 256, 0, ST(stream)>>>(
+      x_hi, x_lo, B, H, W, C, o_hi, o_lo, mask, R, acc);
+  return check_launch("maxpool2x2_fwd_levelsum");
 }
 
 extern "C" int immb_maxpool2x2_bwd(const float* g_out, const float* x_hi, const float* x_lo, int N, int H,

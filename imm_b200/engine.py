@@ -178,6 +178,7 @@ class IMMEngine(object):
     # CUDA-graph replay of the training step (train_step only; forward / backward / optimizer_step stay eager)
     self.use_graph = bool(int(os.environ.get('IMMB_GRAPH', '1'))) if use_graph is None else bool(use_graph)
     self.fuse_bn_stats = bool(int(os.environ.get('IMMB_FUSE_BN_STATS', '1')))
+    self.fuse_level_sums = bool(int(os.environ.get('IMMB_FUSE_LEVEL_SUMS', '1')))
     self._graphs, self._graph_key, self._graph_warm = None, None, 0
     self.graph_replays, self.graph_launches_per_step = 0, 0
     self._events = {}
@@ -639,6 +640,8 @@ class IMMEngine(object):
       assert which is None
       call('immb_vgg_prologue', self.future_image, self.pred, self.pcs, B, R, 1, self.vgg_in.hi, self.vgg_in.lo, st)
     X = self.vgg_in
+    prev_conv = None
+    self._level_of = {nm: k for k, nm in enumerate(self.comp)}
     for kind, item, cin, size in self.vgg_seq:
       if kind == 'conv':
         _lib.TAG = 'fwd:vgg/%s' % item.name
@@ -650,9 +653,17 @@ class IMMEngine(object):
         else:
           self._conv_fwd(item, X, out.hi, out.lo, N=n)
         X = out
+        prev_conv = item.name
       else:
         O = sel(self.vgg_act[item])
-        call('immb_maxpool2x2_fwd', X.hi, X.lo, n, size, size, cin, O.hi, O.lo, st)
+        lvl = self._level_of.get(prev_conv) if (which is None and self.fuse_level_sums) else None
+        if lvl is not None and cin % 4 == 0:
+          # this level feeds a pool: its masked squared-difference sum rides in the pool kernel
+          call('immb_maxpool2x2_fwd_levelsum', X.hi, X.lo, B, size, size, cin, O.hi, O.lo, self.mask, R,
+               self.level_acc[lvl:], st)
+          self._levels_done.add(lvl)
+        else:
+          call('immb_maxpool2x2_fwd', X.hi, X.lo, n, size, size, cin, O.hi, O.lo, st)
         X = O
 
   def _loss_fwd(self, training):
@@ -661,6 +672,7 @@ class IMMEngine(object):
       raise _lib.ImmbError('VGG16 weights not loaded (load_vgg_caffe_dict)')
     st = _lib.stream_ptr()
     B, R = self.B, self.R
+    self._levels_done = set()
     if self._gt_tower_forked:
       self._vgg_tower(1)                               # predicted half; the gt half was forked at the top of forward()
       self._join(self.gt_stream, 'gt_join')
@@ -668,6 +680,8 @@ class IMMEngine(object):
     else:
       self._vgg_tower(None)
     for k, nm in enumerate(self.comp):
+      if k in self._levels_done:
+        continue
       if nm == 'input':
         call('immb_perceptual_level_sum', self.future_image, None, 3, self.pred, None, self.pcs, B, R, R, 3,
              self.mask, R, self.level_acc[k:], st)

@@ -212,6 +212,11 @@ int immb_vgg_conv1_1_fused(const float* gt, const float* pred, int pred_cstride,
 /* 2x2/2 max pool on split planes [N,H,W,C] -> [N,H/2,W/2,C] split planes */
 int immb_maxpool2x2_fwd(const float* x_hi, const float* x_lo, int N, int H, int W, int C, float* o_hi,
                         float* o_lo, void* stream);
+/* The same pool on a perceptual level x = [gt ; pred] ([2B,H,W,C] split planes, B images each) fused with that level's
+ * masked squared-difference sum (imm_model.py:143-147, _loss_mask :408-410): acc[0] += sum mask[b, y*R/H, x*R/H] *
+ * (x[b] - x[B+b])^2 (mask [B,R,R,1] or NULL).  Replaces immb_perceptual_level_sum for levels that feed a pool. */
+int immb_maxpool2x2_fwd_levelsum(const float* x_hi, const float* x_lo, int B, int H, int W, int C, float* o_hi,
+                                 float* o_lo, const float* mask, int R, double* acc, void* stream);
 /* g_in[N,H,W,C] from g_out[N,H/2,W/2,C]; first-max-wins tie rule of TF's CPU MaxPoolGrad */
 int immb_maxpool2x2_bwd(const float* g_out, const float* x_hi, const float* x_lo, int N, int H, int W,
                         int C, float* g_in, void* stream);

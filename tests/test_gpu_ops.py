@@ -643,3 +643,30 @@ def test_conv_dgrad_fused_bn_backward_sums(case):
   tol = 1e-5 * float(want.abs().max())
   np.testing.assert_allclose(sums.cpu().numpy(), want.numpy(), rtol=1e-4, atol=tol)
   np.testing.assert_allclose(sums.cpu().numpy(), ref.cpu().numpy(), rtol=1e-4, atol=tol)
+
+
+@pytest.mark.parametrize('use_mask', [True, False])
+def test_maxpool_fused_level_sum(use_mask):
+  """immb_maxpool2x2_fwd_levelsum = immb_maxpool2x2_fwd on [gt ; pred] + immb_perceptual_level_sum of the level
+  (imm_model.py:143-147 with _loss_mask's subsampled mask) in one pass."""
+  B, H, C, R = 3, 16, 8, 64
+  g = torch.Generator().manual_seed(31 + use_mask)
+  x = torch.relu(torch.randn(2 * B, H, H, C, generator=g))
+  mask = torch.rand(B, R, R, 1, generator=g)
+  dev = 'cuda'
+  xh, xl = (t.to(dev) for t in split(x))
+  md = mask.to(dev) if use_mask else None
+  o0h, o0l = torch.empty(2 * B, H // 2, H // 2, C, device=dev), torch.empty(2 * B, H // 2, H // 2, C, device=dev)
+  call('immb_maxpool2x2_fwd', xh, xl, 2 * B, H, H, C, o0h, o0l, ST())
+  acc0 = torch.zeros(1, dtype=torch.float64, device=dev)
+  call('immb_perceptual_level_sum', xh[:B], xl[:B], C, xh[B:], xl[B:], C, B, H, H, C, md, R, acc0, ST())
+  o1h, o1l = torch.full_like(o0h, float('nan')), torch.full_like(o0l, float('nan'))
+  acc1 = torch.zeros(1, dtype=torch.float64, device=dev)
+  call('immb_maxpool2x2_fwd_levelsum', xh, xl, B, H, H, C, o1h, o1l, md, R, acc1, ST())
+  torch.cuda.synchronize()
+  assert torch.equal(o0h, o1h) and torch.equal(o0l, o1l)
+  assert abs(float(acc0) - float(acc1)) <= 1e-12 * abs(float(acc0))
+  xs = (xh + xl).double().cpu()
+  m = mask[:, ::R // H, ::R // H].double() if use_mask else 1.0
+  want = float((m * (xs[:B] - xs[B:]) ** 2).sum())
+  assert abs(float(acc1) - want) <= 1e-6 * want
