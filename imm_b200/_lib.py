@@ -63,6 +63,7 @@ _SIGS = {
   'immb_pack_weights_rowwin': [_P, _I, _P, _P, _P],
   'immb_maxpool2x2_fwd': [_P, _P, _I, _I, _I, _I, _P, _P, _P],
   'immb_maxpool2x2_fwd_levelsum': [_P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P],
+  'immb_maxpool2x2_bwd_combine': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P],
   'immb_maxpool2x2_bwd': [_P, _P, _P, _I, _I, _I, _I, _P, _P],
   'immb_perceptual_level_sum': [_P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P, _P],
   'immb_perceptual_finalize': [_P, _P, _I, _P, _I, _P, _P, _P, _P],

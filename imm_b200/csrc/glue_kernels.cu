@@ -681,6 +681,59 @@ __global__ void vgg_bwd_combine4_kernel(const float* __restrict__ g_next, const 
   }
 }
 
+// max-pool backward fused with the loss-term / ReLU-backward combine of the layer that fed the pool (the pred half of
+// a VGG activation): dy = split( [x > 0] * ( [x is the window's first max] * g_out  +  coef * mask * (f_gt - x) ) ),
+// i.e. maxpool2x2_bwd4_kernel followed by vgg_bwd_combine4_kernel without the fp32 gradient round trip and without
+// re-reading x.  coef == nullptr: no loss term at this layer (fg_* unused).
+__global__ void maxpool2x2_bwd_combine4_kernel(const float* __restrict__ g_out, const float* __restrict__ fg_hi,
+                                               const float* __restrict__ fg_lo, const float* __restrict__ x_hi,
+                                               const float* __restrict__ x_lo, int N, int H, int W, int C,
+                                               const float* __restrict__ mask, int R, const float* __restrict__ coef,
+                                               float* dy_hi, float* dy_lo) {
+  const int Ho = H / 2, Wo = W / 2, q = C >> 2;
+  const int64_t total = (int64_t)N * Ho * Wo * q;
+  const float cf = coef ? __ldg(coef) : 0.f;
+  const int s = R / H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % q) * 4;
+    int64_t p = i / q;
+    int wo = (int)(p % Wo);
+    int64_t t = p / Wo;
+    int ho = (int)(t % Ho);
+    int n = (int)(t / Ho);
+    size_t base = (((size_t)n * H + 2 * ho) * W + 2 * wo) * C + c;
+    size_t idx[4] = {base, base + C, base + (size_t)W * C, base + (size_t)W * C + C};
+    float4 xv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xv[k] = load_split4(x_hi, x_lo, idx[k]);
+    float4 gg = ld4(g_out + p * C + c);
+    float4 o[4];
+#define IMMB_E(f)                                                  \
+    {                                                              \
+      int best = 0;                                                \
+      float bv = xv[0].f;                                          \
+      _Pragma("unroll") for (int k = 1; k < 4; ++k) if (xv[k].f > bv) { bv = xv[k].f; best = k; } \
+      _Pragma("unroll") for (int k = 0; k < 4; ++k) o[k].f = (k == best) ? gg.f : 0.f;            \
+    }
+    IMMB_E(x) IMMB_E(y) IMMB_E(z) IMMB_E(w)
+#undef IMMB_E
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float4 g = o[k];
+      if (coef) {
+        const float4 fg = load_split4(fg_hi, fg_lo, idx[k]);
+        const int hh = 2 * ho + (k >> 1), ww = 2 * wo + (k & 1);
+        const float m = cf * (mask ? __ldg(mask + ((int64_t)n * R + (int64_t)hh * s) * R + (int64_t)ww * s) : 1.f);
+        g.x += m * (fg.x - xv[k].x); g.y += m * (fg.y - xv[k].y); g.z += m * (fg.z - xv[k].z); g.w += m * (fg.w - xv[k].w);
+      }
+      g.x = xv[k].x > 0.f ? g.x : 0.f; g.y = xv[k].y > 0.f ? g.y : 0.f;
+      g.z = xv[k].z > 0.f ? g.z : 0.f; g.w = xv[k].w > 0.f ? g.w : 0.f;
+      store_split4(dy_hi, dy_lo, idx[k], g);
+    }
+  }
+}
+
 // =====================================================================================================
 // landmark bottleneck: one warp per (b, k)
 // =====================================================================================================
@@ -1581,6 +1634,20 @@ extern "C" int immb_maxpool2x2_bwd(const float* g_out, const float* x_hi, const 
     maxpool2x2_bwd_kernel<<<ew_grid((int64_t)N * (H / 2) * (W / 2) * C), 256, 0, ST(stream)>>>(g_out, x_hi, x_lo,
                                                                                               N, H, W, C, g_in);
   return check_launch("maxpool2x2_bwd");
+}
+
+extern "C" int immb_maxpool2x2_bwd_combine(const float* g_out, const float* fg_hi, const float* fg_lo,
+                                           const float* fp_hi, const float* fp_lo, int B, int H, int W, int C,
+                                           const float* mask, int R, const float* coef, float* dy_hi, float* dy_lo,
+                                           void* stream) {
+  IMMB_REQUIRE(g_out && fp_hi && fp_lo && dy_hi && dy_lo && (H % 2 == 0) && (W % 2 == 0) && C % 4 == 0 &&
+               (!coef || (fg_hi && fg_lo)), "maxpool_bwd_combine: bad args");
+  IMMB_REQUIRE(!mask || (R >= H && R % H == 0), "maxpool_bwd_combine: mask resolution must be a multiple of the level's");
+  IMMB_REQUIRE(aligned16(g_out) && aligned16(fg_hi) && aligned16(fg_lo) && aligned16(fp_hi) && aligned16(fp_lo) &&
+               aligned16(dy_hi) && aligned16(dy_lo), "maxpool_bwd_combine: alignment");
+  maxpool2x2_bwd_combine4_kernel<<<ew_grid((int64_t)B * (H / 2) * (W / 2) * C / 4), 256, 0, ST(stream)>>>(
+      g_out, fg_hi, fg_lo, fp_hi, fp_lo, B, H, W, C, mask, R, coef, dy_hi, dy_lo);
+  return check_launch("maxpool2x2_bwd_combine");
 }
 
 extern "C" int immb_perceptual_level_sum(const float* fg_hi, const float* fg_lo, int gcs, const float* fp_hi,

@@ -799,8 +799,17 @@ class IMMEngine(object):
         # input of the pool = previous conv's activation (pred half)
         prev = seq[idx - 1][1]
         xin = prev.out.half(1, B)
-        call('immb_maxpool2x2_bwd', g, xin.hi, xin.lo, B, size, size, cin, self.g_pool[item], st)
-        g = self.g_pool[item]
+        if self.fuse_level_sums and cin % 4 == 0:
+          # pool backward + the producer's loss term / ReLU backward / operand split in one pass: dy of `prev` directly
+          _lib.TAG = 'bwd:vgg/%s' % prev.name
+          fgp = prev.out.half(0, B)
+          coef_p = self.coef[level_of[prev.name]:] if prev.name in level_of else None
+          call('immb_maxpool2x2_bwd_combine', g, fgp.hi, fgp.lo, xin.hi, xin.lo, B, size, size, cin, self.mask, R,
+               coef_p, prev.dy.hi, prev.dy.lo, st)
+          fused_dy, g = prev, None
+        else:
+          call('immb_maxpool2x2_bwd', g, xin.hi, xin.lo, B, size, size, cin, self.g_pool[item], st)
+          g = self.g_pool[item]
     coef_in = self.coef[level_of['input']:] if 'input' in level_of else None
     if coef_in is None:
       raise _lib.ImmbError("perceptual.comp without 'input' is not built")

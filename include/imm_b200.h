@@ -238,6 +238,13 @@ int immb_perceptual_finalize(const double* acc, const double* counts, int n_leve
 int immb_vgg_bwd_combine(const float* g_next, const float* fg_hi, const float* fg_lo, const float* fp_hi,
                          const float* fp_lo, int B, int h, int w, int C, const float* mask, int R,
                          const float* coef, float* dy_hi, float* dy_lo, void* stream);
+/* immb_maxpool2x2_bwd followed by immb_vgg_bwd_combine in one pass, for a VGG activation that feeds a pool (ops.py:16-26
+ * backward + imm_model.py:143-147 backward + ReLU backward): dy = split([fp > 0] * ([fp is the first max of its 2x2
+ * window] * g_out + coef * mask * (fg - fp))), g_out [B,H/2,W/2,C], fg / fp the gt / pred halves [B,H,W,C] of the
+ * activation; coef NULL = no loss term at this layer.  No fp32 gradient round trip, fp read once. */
+int immb_maxpool2x2_bwd_combine(const float* g_out, const float* fg_hi, const float* fg_lo, const float* fp_hi,
+                                const float* fp_lo, int B, int H, int W, int C, const float* mask, int R,
+                                const float* coef, float* dy_hi, float* dy_lo, void* stream);
 /* gradient wrt the renderer output [B,R,R,pred_cstride] (channels >=3 get 0) as split planes:
  *   g_pred_c = coef_input * m * (gt_c - pred_c) + g_gray / (3*255)
  * g_vggin (may be NULL): gradient wrt the VGG input; [B,R,R,1] when g_is_patch == 0, else the gradient wrt the

@@ -670,3 +670,27 @@ def test_maxpool_fused_level_sum(use_mask):
   m = mask[:, ::R // H, ::R // H].double() if use_mask else 1.0
   want = float((m * (xs[:B] - xs[B:]) ** 2).sum())
   assert abs(float(acc1) - want) <= 1e-6 * want
+
+
+@pytest.mark.parametrize('with_loss', [True, False])
+def test_maxpool_bwd_fused_combine(with_loss):
+  """immb_maxpool2x2_bwd_combine = immb_maxpool2x2_bwd followed by immb_vgg_bwd_combine (bit-identical planes)."""
+  B, H, C, R = 2, 16, 8, 32
+  g = torch.Generator().manual_seed(41 + with_loss)
+  f = torch.relu(torch.randn(2 * B, H, H, C, generator=g))
+  f[B:, ::2, ::2] = f[B:, 1::2, ::2]                       # ties inside pooling windows: first-max-wins must hold
+  g_out = torch.randn(B, H // 2, H // 2, C, generator=g)
+  mask = torch.rand(B, R, R, 1, generator=g)
+  coef = torch.tensor([0.37])
+  dev = 'cuda'
+  fh, fl = (t.to(dev) for t in split(f))
+  cd = coef.to(dev) if with_loss else None
+  g_in = torch.empty(B, H, H, C, device=dev)
+  call('immb_maxpool2x2_bwd', g_out.to(dev), fh[B:], fl[B:], B, H, H, C, g_in, ST())
+  d0h, d0l = torch.empty(B, H, H, C, device=dev), torch.empty(B, H, H, C, device=dev)
+  call('immb_vgg_bwd_combine', g_in, fh[:B], fl[:B], fh[B:], fl[B:], B, H, H, C, mask.to(dev), R, cd, d0h, d0l, ST())
+  d1h, d1l = torch.full_like(d0h, float('nan')), torch.full_like(d0l, float('nan'))
+  call('immb_maxpool2x2_bwd_combine', g_out.to(dev), fh[:B], fl[:B], fh[B:], fl[B:], B, H, H, C, mask.to(dev), R, cd,
+       d1h, d1l, ST())
+  torch.cuda.synchronize()
+  assert torch.equal(d0h, d1h) and torch.equal(d0l, d1l)
