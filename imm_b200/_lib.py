@@ -68,6 +68,7 @@ _SIGS = {
   'immb_perceptual_level_sum': [_P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P, _P],
   'immb_perceptual_finalize': [_P, _P, _I, _P, _I, _P, _P, _P, _P],
   'immb_vgg_bwd_combine': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P],
+  'immb_vgg_conv1_1_bwd_fused': [_P, _P, _P, _I, _P, _P, _I, _P, _P, _I, _I, _P, _P, _P],
   'immb_pred_grad': [_P, _P, _I, _P, _P, _P, _I, _I, _I, _P, _P, _P],
   'immb_resize_ac_fwd': [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P],
   'immb_resize_ac_bwd': [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P],

@@ -1144,6 +1144,69 @@ __global__ void pred_grad_kernel(const float* __restrict__ gt, const float* __re
   }
 }
 
+// Backward of the whole VGG input stage in one kernel: dgrad of conv1_1 (3x3, Cin = 1) + adjoint of the gray /
+// normalise prologue + the 'input' level's loss term = the gradient wrt the renderer output (split planes):
+//   g_pred[c<3] = coef_in * mask * (gt_c - pred_c) + (1/(3*255)) * sum_t sum_co dy[q - off_t][co] * w[t][co]
+// One block = one 16x16-pixel tile: phase 1 contracts the 64 channels of dy for the 18x18 halo pixels and the nine taps
+// (4 threads per pixel, 16 channels each, exact fp32) into shared memory, phase 2 gathers the nine shifted values.
+// Replaces conv2d_dgrad (1x1 over the [.,12] patch tensor on the tensor cores) + pred_grad and their 48 B/pixel tensor.
+__global__ void __launch_bounds__(256) vgg_conv1_1_bwd_fused_kernel(
+    const float* __restrict__ dy_hi, const float* __restrict__ dy_lo, const float* __restrict__ w,
+    const float* __restrict__ gt, const float* __restrict__ pred, int pcs, const float* __restrict__ mask,
+    const float* __restrict__ coef_in, int R, float* g_hi, float* g_lo) {
+  constexpr int COUT = 64, T = 16, HW = T + 2;
+  __shared__ float ws[9][COUT];
+  __shared__ float patch[HW * HW][9];
+  for (int i = threadIdx.x; i < 9 * COUT; i += 256) ws[i / COUT][i % COUT] = __ldg(w + i);
+  const int tiles = R / T;
+  const int tw = blockIdx.x % tiles, th = (blockIdx.x / tiles) % tiles;
+  const int64_t n = blockIdx.x / (tiles * tiles);
+  __syncthreads();
+  const int part = threadIdx.x & 3;                       // 16-channel quarter of a pixel
+  for (int it = 0; it < (HW * HW + 63) / 64; ++it) {        // uniform trip count: the shuffles below need whole warps
+    const int q = it * 64 + (threadIdx.x >> 2);
+    const bool valid = q < HW * HW;
+    const int hh = th * T + q / HW - 1, ww = tw * T + q % HW - 1;
+    float acc[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+    if (valid && hh >= 0 && hh < R && ww >= 0 && ww < R) {
+      const size_t base = (((size_t)n * R + hh) * R + ww) * COUT + part * 16;
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 v = load_split4(dy_hi, dy_lo, base + j);
+        const int c = part * 16 + j;
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+          acc[t] += v.x * ws[t][c] + v.y * ws[t][c + 1] + v.z * ws[t][c + 2] + v.w * ws[t][c + 3];
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], 1);
+      acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], 2);
+    }
+    if (valid && part == 0) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) patch[q][t] = acc[t];
+    }
+  }
+  __syncthreads();
+  const int hl = threadIdx.x / T, wl = threadIdx.x % T;
+  const int h = th * T + hl, wq = tw * T + wl;
+  float gg = 0.f;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) gg += patch[(hl + 1 - (t / 3 - 1)) * HW + (wl + 1 - (t % 3 - 1))][t];
+  gg *= (1.0f / 3.0f) * (1.0f / 255.0f);
+  const size_t p = ((size_t)n * R + h) * R + wq;
+  const float cm = __ldg(coef_in) * (mask ? __ldg(mask + p) : 1.f);
+  for (int c = 0; c < pcs; ++c) {
+    float g = 0.f;
+    if (c < 3) g = cm * (__ldg(gt + p * 3 + c) - __ldg(pred + p * pcs + c)) + gg;
+    store_split(g_hi, g_lo, p * pcs + c, g);
+  }
+}
+
 __device__ __forceinline__ void ac_src(int o, int n_in, int n_out, int& lo, int& hi, float& f) {
   float scale = n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.f;
   float s = (float)o * scale;
@@ -1696,6 +1759,19 @@ extern "C" int immb_pred_grad(const float* gt, const float* pred, int pcs, const
   pred_grad_kernel<<<ew_grid((int64_t)B * R * R * pcs), 256, 0, ST(stream)>>>(
       gt, pred, pcs, mask, coef_input, g_vggin, g_is_patch, B, R, g_hi, g_lo);
   return check_launch("pred_grad");
+}
+
+extern "C" int immb_vgg_conv1_1_bwd_fused(const float* dy_hi, const float* dy_lo, const float* w, int Cout,
+                                          const float* gt, const float* pred, int pcs, const float* mask,
+                                          const float* coef_input, int B, int R, float* g_hi, float* g_lo,
+                                          void* stream) {
+  IMMB_REQUIRE(dy_hi && dy_lo && w && gt && pred && coef_input && g_hi && g_lo && pcs >= 3 && B > 0,
+               "vgg_conv1_1_bwd_fused: bad args");
+  IMMB_REQUIRE(Cout == 64 && R % 16 == 0, "vgg_conv1_1_bwd_fused: Cout must be 64 and 16 | R");
+  IMMB_REQUIRE(aligned16(dy_hi) && aligned16(dy_lo), "vgg_conv1_1_bwd_fused: alignment");
+  vgg_conv1_1_bwd_fused_kernel<<<B * (R / 16) * (R / 16), 256, 0, ST(stream)>>>(dy_hi, dy_lo, w, gt, pred, pcs, mask,
+                                                                                coef_input, R, g_hi, g_lo);
+  return check_launch("vgg_conv1_1_bwd_fused");
 }
 
 extern "C" int immb_resize_ac_fwd(const float* x_hi, const float* x_lo, int xcs, int N, int H, int W, int C,

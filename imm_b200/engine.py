@@ -784,6 +784,12 @@ class IMMEngine(object):
         # by this dgrad's epilogue (no fp32 gradient round trip, no combine launch)
         prev = seq[idx - 1] if idx > 0 else None
         d = L.desc(B)
+        if (L.name == 'conv1_1' and self.fuse_level_sums and self.engine != _lib.ENGINE_SIMT and R % 16 == 0
+                and L.cout == 64 and 'input' in level_of):
+          # conv1_1 dgrad + gray/normalise adjoint + the 'input' level's term: the renderer-output gradient in one kernel
+          call('immb_vgg_conv1_1_bwd_fused', L.dy.hi, L.dy.lo, L.w, L.cout, self.future_image, self.pred, self.pcs,
+               self.mask, self.coef[level_of['input']:], B, R, self.pred_dy.hi, self.pred_dy.lo, st)
+          return self.pred_dy
         if (prev is not None and prev[0] == 'conv' and prev[1].name not in level_of
                 and _lib.lib().immb_conv2d_dgrad_relu_supported(d)):
           Lp = prev[1]

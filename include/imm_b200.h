@@ -252,6 +252,14 @@ int immb_maxpool2x2_bwd_combine(const float* g_out, const float* fg_hi, const fl
 int immb_pred_grad(const float* gt, const float* pred, int pred_cstride, const float* mask,
                    const float* coef_input, const float* g_vggin, int g_is_patch, int B, int R, float* g_hi,
                    float* g_lo, void* stream);
+/* Backward of the VGG input stage in one kernel (vgg16.py:182-230 backward for conv1_1, build_vgg16.py:22-26 adjoint,
+ * imm_model.py:143-147 'input' level): the gradient wrt the renderer output from the split gradient dy[B,R,R,64] wrt
+ * conv1_1's raw output (ReLU backward already applied), w [3,3,1,64] HWIO:
+ *   g_pred_c = coef_input * m * (gt_c - pred_c) + (1/(3*255)) * sum_{r,s,co} dy[h-r+1, w-s+1, co] * w[r,s,0,co]  (c < 3)
+ * Equals immb_conv2d_dgrad on the patch form + immb_pred_grad(g_is_patch = 1), in exact fp32. */
+int immb_vgg_conv1_1_bwd_fused(const float* dy_hi, const float* dy_lo, const float* w, int Cout, const float* gt,
+                               const float* pred, int pred_cstride, const float* mask, const float* coef_input,
+                               int B, int R, float* g_hi, float* g_lo, void* stream);
 /* tf.image.resize_bilinear(align_corners=True) (imm_model.py:334) on split planes, and its adjoint */
 int immb_resize_ac_fwd(const float* x_hi, const float* x_lo, int x_cstride, int N, int H, int W, int C,
                        int Ho, int Wo, float* o_hi, float* o_lo, int o_cstride, void* stream);

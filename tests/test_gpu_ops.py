@@ -694,3 +694,40 @@ def test_maxpool_bwd_fused_combine(with_loss):
        d1h, d1l, ST())
   torch.cuda.synchronize()
   assert torch.equal(d0h, d1h) and torch.equal(d0l, d1l)
+
+
+def test_vgg_conv1_1_backward_fused():
+  """immb_vgg_conv1_1_bwd_fused (conv1_1 dgrad + gray/normalise adjoint + 'input' level term in one exact-fp32 kernel)
+  vs autograd through the oracle's prologue + conv1_1, and vs the two-kernel path it replaces."""
+  B, R, pcs = 2, 32, 12
+  g = torch.Generator().manual_seed(51)
+  gt = torch.rand(B, R, R, 3, generator=g) * 255
+  pred12 = torch.randn(B, R, R, pcs, generator=g) * 60
+  w = torch.randn(3, 3, 1, 64, generator=g)
+  dy = torch.randn(B, R, R, 64, generator=g)
+  mask = torch.rand(B, R, R, 1, generator=g)
+  coef = torch.tensor([0.013])
+  dev = 'cuda'
+  pd = pred12[..., :3].double().clone().requires_grad_(True)
+  gray = pd.mean(3, keepdim=True) / 255.0 - O.VGG_MEAN / 255.0
+  y = O.conv2d_same(gray, w.double(), None, 1)
+  y.backward(dy.double())
+  want = pd.grad + float(coef) * mask.double() * (gt.double() - pred12[..., :3].double())
+  dh, dl = (t.to(dev) for t in split(dy))
+  gh, gl = torch.full((B, R, R, pcs), float('nan'), device=dev), torch.full((B, R, R, pcs), float('nan'), device=dev)
+  call('immb_vgg_conv1_1_bwd_fused', dh, dl, w.to(dev), 64, gt.to(dev), pred12.to(dev), pcs, mask.to(dev), coef.to(dev),
+       B, R, gh, gl, ST())
+  torch.cuda.synchronize()
+  got = (gh + gl).cpu()
+  assert rel_err(got[..., :3], want) < 1e-5
+  assert float(got[..., 3:].abs().max()) == 0.0
+  # the path it replaces: 1x1 dgrad over the patch tensor on the tensor cores + pred_grad
+  d = conv_desc(B, R, R, 9, 64, 1, 1, xcs=12, engine=_lib.ENGINE_TC)
+  wp_h, wp_l = torch.empty(1, 64, 32, device=dev), torch.empty(1, 64, 32, device=dev)
+  wh_h, wh_l = torch.empty(1, 32, 64, device=dev), torch.empty(1, 32, 64, device=dev)
+  call('immb_pack_weights', w.reshape(1, 1, 9, 64).contiguous().to(dev), 1, 1, 9, 64, 32, 64, wp_h, wp_l, wh_h, wh_l, ST())
+  dx = torch.zeros(B, R, R, 12, device=dev)
+  call('immb_conv2d_dgrad', d, dh, dl, None, wh_h, wh_l, dx, ST())
+  g2h, g2l = torch.empty_like(gh), torch.empty_like(gl)
+  call('immb_pred_grad', gt.to(dev), pred12.to(dev), pcs, mask.to(dev), coef.to(dev), dx, 1, B, R, g2h, g2l, ST())
+  assert rel_err(got, (g2h + g2l).cpu()) < 2e-5
