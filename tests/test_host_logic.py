@@ -148,3 +148,57 @@ def test_landmark_colourisation_matches_reference_semantics():
   assert out.shape == (1, 2, 2, 3)
   assert out[0, 0, 0].tolist() == [1.0, 0.0, 0.5] and out[0, 1, 1].tolist() == [0.0, 0.5, 0.25]
   np.testing.assert_allclose(out[0, 0, 1].numpy(), [0.2, 0.4, 0.2], rtol=1e-6)      # max over landmarks per channel
+
+
+def test_conv_call_attribution_matches_engine_routing():
+  """bench.py's roofline attributes each conv call to the kernel that serves it (_lib.conv_info mirrors the C
+  eligibility rules) and counts its algorithmic 2*MACs; the per-step total must reproduce SURVEY 8d's 48.98 GFLOP/pair."""
+  from imm_b200 import _lib
+  from imm_b200.engine import encoder_spec, renderer_spec, same_pad, VGG_ORDER
+  def desc(N, H, Cin, Cout, k, s, prec=_lib.PREC_TF32X3, layout=_lib.XLAYOUT_NHWC):
+    d = _lib.ConvDesc()
+    d.N, d.H, d.W, d.Cin, d.Cout, d.kh, d.kw, d.stride = N, H, H, Cin, Cout, k, k, s
+    d.Ho = d.Wo = -(-H // s)
+    d.pad_t = d.pad_l = same_pad(H, k, s)[0]
+    d.precision, d.x_layout = prec, layout
+    return d
+  total, kernels = 0.0, {}
+  def add(name, d, times=1):
+    nonlocal total
+    info = _lib.conv_info(name, d)
+    total += times * info['flops']
+    kernels.setdefault(info['kernel'], 0)
+    kernels[info['kernel']] += times
+  B = 1
+  for _enc in range(2):
+    cin, size = 3, 128
+    for i, (nm, k, s, cout) in enumerate(encoder_spec(32)):
+      d = desc(B, size, cin, cout, k, s, layout=_lib.XLAYOUT_ROWWIN4 if i == 0 else _lib.XLAYOUT_NHWC)
+      add('immb_conv2d_fwd', d); add('immb_conv2d_wgrad', d)
+      if i > 0:
+        add('immb_conv2d_dgrad', d)
+      cin, size = cout, d.Ho
+  d = desc(B, 16, 256, 10, 1, 1)
+  add('immb_conv2d_fwd', d); add('immb_conv2d_wgrad', d); add('immb_conv2d_dgrad', d)
+  cin, size = 266, 16
+  for nm, cout, bn, relu, up in renderer_spec(32, 128, 9):
+    d = desc(B, size, cin, cout, 3, 1)
+    add('immb_conv2d_fwd', d); add('immb_conv2d_wgrad', d); add('immb_conv2d_dgrad', d)
+    cin, size = cout, size * (2 if up else 1)
+  cin, size = 1, 128
+  for it in VGG_ORDER:
+    if isinstance(it, str):
+      size //= 2
+      continue
+    nm, cout = it
+    if nm == 'conv5_3':
+      break
+    d = desc(B, size, cin, cout, 3, 1, prec=_lib.PREC_TF32X2)
+    add('immb_conv2d_fwd', d, 2); add('immb_conv2d_dgrad', d, 1)
+    cin = cout
+  assert abs(total * 1e-9 - 48.98) < 0.05, total * 1e-9          # SURVEY 8(d)
+  assert set(kernels) == {'conv_tc2_pair_kernel', 'conv_tc2_wgrad_kernel', 'conv_tc_kernel', 'conv_tc_wgrad_kernel'}
+  first = desc(B, 128, 3, 32, 7, 1, layout=_lib.XLAYOUT_ROWWIN4)
+  assert _lib.conv_info('immb_conv2d_fwd_bnstats', first)['kernel'] == 'conv_tc2_pair_kernel'
+  assert _lib.conv_info('immb_conv2d_wgrad', first)['kernel'] == 'conv_tc_wgrad_kernel'
+  assert _lib.conv_info('immb_conv2d_fwd', desc(B, 8, 512, 512, 3, 1))['kernel'] == 'conv_tc_kernel'

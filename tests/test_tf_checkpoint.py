@@ -142,3 +142,31 @@ def test_reader_accepts_foreign_writer_choices(tmp_path):
   r = T.CheckpointReader(str(tmp_path / 'f'))
   assert r.get_variable_to_shape_map() == {'w': [2, 3]}
   assert np.array_equal(r.get_tensor('w'), data.reshape(2, 3))
+
+
+def test_round_trip_property_random_variable_sets(tmp_path):
+  """Randomised round trips (names with shared prefixes, scalars, empty tensors, several dtypes, enough entries to
+  cross restart intervals): what is written is what is read, for any variable set."""
+  from hypothesis import given, settings, strategies as st, HealthCheck
+  dtypes = [np.float32, np.float64, np.int32, np.int64, np.uint8, np.bool_]
+  name = st.text(alphabet='abcxyz/_01', min_size=1, max_size=24)
+  shape = st.lists(st.integers(0, 5), min_size=0, max_size=3)
+  counter = {'n': 0}
+
+  @settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+  @given(st.dictionaries(name, st.tuples(shape, st.integers(0, len(dtypes) - 1), st.integers(0, 2 ** 31 - 1)),
+                         min_size=1, max_size=40))
+  def run(spec):
+    counter['n'] += 1
+    tens = {}
+    for k, (shp, di, seed) in spec.items():
+      rng = np.random.default_rng(seed)
+      tens[k] = (rng.integers(0, 2, size=shp).astype(dtypes[di]) if dtypes[di] in (np.bool_, np.uint8)
+                 else (rng.normal(size=shp) * 100).astype(dtypes[di]))
+    p = T.write_checkpoint(str(tmp_path / ('c%d' % counter['n'])), tens)
+    r = T.CheckpointReader(p)
+    assert list(r.entries) == sorted(tens, key=lambda s: s.encode())
+    for k, v in tens.items():
+      got = r.get_tensor(k)
+      assert got.dtype == v.dtype and got.shape == v.shape and np.array_equal(got, v)
+  run()
