@@ -149,7 +149,7 @@ def conv_info(name, d):
   else:
     kernel = 'conv_tc2_pair_kernel' if (halo or (first and 'fwd' in name)) else 'conv_tc_kernel'
   passes = {PREC_TF32X3: 3, PREC_TF32: 1, PREC_TF32X2: 2}[d.precision]
-  return {'flops': flops, 'kernel': kernel, 'passes': passes}
+  return {'flops': flops, 'kernel': kernel, 'passes': passes, 'kind': 'tf32'}
 
 
 def _call(name, *args):

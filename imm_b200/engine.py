@@ -982,6 +982,13 @@ class IMMEngine(object):
   # ------------------------------------------------------------------------------------------------
   # introspection
   # ------------------------------------------------------------------------------------------------
+  def dtype_string(self):
+    """The arithmetic the conv engine computes in (bench.py's `dtype`)."""
+    if self.precision == _lib.PREC_TF32:
+      return 'tf32 (single pass; does not meet the parity bar)'
+    return ('tf32x3 (fp32 storage; error-compensated TF32 tensor-core products hi*hi+hi*lo+lo*hi, fp32 accumulate; '
+            'the frozen VGG16 tower uses weights rounded to TF32 at load and 2 passes)')
+
   def engine_table(self):
     out = OrderedDict()
     for key, L in self.layers.items():

@@ -156,6 +156,38 @@ def setup_training(opts, graph, optim, inputs, training_pl, model_factory, globa
   return train_multi(opts, graph, optim, inputs, training_pl, model_factory, global_step, clip_value)
 
 
+def run_test_pass(opts, model, test_dataset, step, summary=None):
+  """The periodic test pass of train_loop (cnn_train_multi.py:472-506): one full pass over the (finite) test set with
+  training_pl = False -- BN uses the moving statistics, no state is updated -- logging the loss of every batch; the
+  streaming `loss` metric (imm_model.py:392, op_utils.py:80-91: mean over the pass) goes to the summary writer.
+  test_dataset: a callable yielding input dicts and None when exhausted, or a zero-argument factory returning one (the
+  re-initialisable iterator of the reference)."""
+  it = test_dataset
+  first = it()
+  if callable(first):               # factory -> fresh iterator for this pass
+    it, first = first, first()
+  total, n, test_iter, inputs = 0.0, 0, 0, first
+  while inputs is not None:
+    t0 = time.time()
+    _, loss, _ = model.build(inputs, False, costs_collection='costs')
+    loss_value = float(loss.item())
+    duration = time.time() - t0
+    if world_info()[0] == 0:
+      print('test: %s: step %d, loss = %.4f (%.1f examples/sec) %.3f sec/batch'
+            % (datetime.now(), step, loss_value, opts['batch_size'] / float(duration), duration))
+    total, n, test_iter = total + loss_value, n + 1, test_iter + 1
+    try:
+      inputs = it()
+    except StopIteration:
+      inputs = None
+  print('iteration through test set finished')
+  mean_loss = total / max(n, 1)
+  if summary is not None and n:
+    summary.writer.add_scalar('test/loss', mean_loss, step)
+    summary.writer.flush()
+  return mean_loss
+
+
 def train_loop(opts, graph, loss, train_dataset, training_pl, handle_pl, train_op, train_summary_op,
                test_summary_op, num_steps, global_step, checkpoint_fname, test_dataset=None,
                ignore_missing_vars=False, reset_global_step=False, vars_to_restore=None, exclude_vars=None,
@@ -176,6 +208,7 @@ def train_loop(opts, graph, loss, train_dataset, training_pl, handle_pl, train_o
     summary = SummaryLogger(opts['log_dir'])            # tf.summary.FileWriter(opts['log_dir']) (cnn_train_multi.py:436)
   begin = time.time()
   n_done = 0
+  world = world_info()[2]
   for step in range(start_step, num_steps):
     t0 = time.time()
     if fwd_only:
@@ -183,13 +216,24 @@ def train_loop(opts, graph, loss, train_dataset, training_pl, handle_pl, train_o
       loss_value = float(model.engine.loss_value().item())
     else:
       loss_value = float(train_op().item())          # the one D2H read per step (loss), as session.run returns it
+      # the cost moving averages advance every step, as the reference's avg_ops inside train_op do (base_model.py:52-60;
+      # rank-local values; the scalars were produced by this step's kernels and the loss read above already synchronised)
+      for op in model._avg_ops:
+        op()
     duration = time.time() - t0
+    if world > 1 and dist.is_initialized() and step % log_every == 0:
+      # the reference's loss is the tower MEAN (cnn_train_multi.py:177): average the rank-local values for the log line
+      t = torch.tensor([loss_value], dtype=torch.float64, device=model.engine.dev)
+      dist.all_reduce(t)
+      loss_value = float(t.item()) / world
     assert not np.isnan(loss_value), 'Model diverged with loss = NaN'           # cnn_train_multi.py:463
     if rank == 0 and step % log_every == 0:
       print('%s: step %d, loss = %.4f (%.1f examples/sec) %.3f sec/batch'
             % (datetime.now(), step, loss_value, opts['batch_size'] / duration, duration))
     if summary is not None and step % opts['n_summary'] == 0:            # cnn_train_multi.py:452-457
-      summary.write(model, step, lr=getattr(model.engine, 'last_lr', None))
+      summary.write(model, step, lr=getattr(model.engine, 'last_lr', None), advance_avgs=fwd_only)
+    if not fwd_only and test_dataset is not None and opts.get('n_test') and step % opts['n_test'] == 0:
+      run_test_pass(opts, model, test_dataset, step, summary if rank == 0 else None)       # cnn_train_multi.py:472-506
     if not fwd_only and rank == 0 and step % opts['n_checkpoint'] == 0 and opts.get('log_dir'):
       # saver.save(session, <log_dir>/model.ckpt, global_step=step) (cnn_train_multi.py:511-513): TensorBundle files
       prefix = model.save_checkpoint(os.path.join(opts['log_dir'], 'model.ckpt-%d' % step))

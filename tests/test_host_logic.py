@@ -140,6 +140,7 @@ def test_landmark_colourisation_matches_reference_semantics():
   from imm_b200.utils.summaries import colorize_landmark_maps, get_n_colors
   cols = get_n_colors(5, rnd=random.Random(0))
   assert len(cols) == 5 and all(0.9 / 1.9 - 1e-9 <= c <= 1.0 for col in cols for c in col)
+  assert min(sum(abs(a - b) for a, b in zip(cols[i], cols[j])) for i in range(5) for j in range(i)) > 0.2   # distinct
   maps = torch.zeros(1, 2, 2, 2)
   maps[0, 0, 0, 0] = 1.0
   maps[0, 1, 1, 1] = 0.5

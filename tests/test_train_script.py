@@ -45,7 +45,7 @@ model:
 def test_train_script_runs_checkpoints_and_restores(tmp_path):
   cfg = tmp_path / 'exp.yaml'
   cfg.write_text(CFG % str(tmp_path))
-  out = subprocess.run([sys.executable, os.path.join(ROOT, 'scripts', 'train.py'), '--configs', str(cfg), '--num-steps', '3'],
+  out = subprocess.run([sys.executable, os.path.join(ROOT, 'scripts', 'train.py'), '--configs', str(cfg), '--num-steps', '3', '--synthetic'],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, cwd=ROOT, timeout=900)
   assert out.returncode == 0, out.stdout[-3000:]
   assert 'step -1, loss' in out.stdout and 'step 2, loss' in out.stdout       # global_step starts at -1 (train.py:87-89)
@@ -88,7 +88,7 @@ def test_train_script_runs_checkpoints_and_restores(tmp_path):
   assert m.engine.global_step == float(sd['global_step']) == 3.0   # -1 + 4 applied steps; the FILE is named by the loop step (2)
   assert m.engine.adam_t == 4          # steps -1..2 applied; recovered from beta1_power = 0.9^(t+1)
   # --checkpoint restore through the CLI path (cnn_train_multi.py:404-433) continues from global_step + 0
-  out = subprocess.run([sys.executable, os.path.join(ROOT, 'scripts', 'train.py'), '--configs', str(cfg), '--num-steps', '4',
+  out = subprocess.run([sys.executable, os.path.join(ROOT, 'scripts', 'train.py'), '--configs', str(cfg), '--num-steps', '4', '--synthetic',
                         '--checkpoint', str(ck), '--restore-optim'],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, cwd=ROOT, timeout=900)
   assert out.returncode == 0, out.stdout[-3000:]
