@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('IMMB_LIB', os.path.join(_HERE, 'lib', 'libimm_b200.so'))     # IMMB_LIB: A/B builds (development)
 
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
-PREC_TF32X3, PREC_TF32, PREC_TF32X2 = 0, 1, 2
+PREC_TF32X3, PREC_TF32, PREC_TF32X2, PREC_F16X3, PREC_F16X2 = 0, 1, 2, 3, 4
 EPI_BIAS, EPI_BIAS_RELU = 0, 1
 XLAYOUT_NHWC, XLAYOUT_ROWWIN4 = 0, 1
 
@@ -21,9 +21,10 @@ class ImmbError(RuntimeError):
 
 
 class ConvDesc(ctypes.Structure):
-  _fields_ = [(n, ctypes.c_int32) for n in
-              ('N', 'H', 'W', 'Cin', 'Cout', 'kh', 'kw', 'stride', 'Ho', 'Wo', 'pad_t', 'pad_l',
-               'x_cstride', 'y_cstride', 'cin_pad', 'epilogue', 'precision', 'engine', 'x_layout')]
+  _fields_ = ([(n, ctypes.c_int32) for n in
+               ('N', 'H', 'W', 'Cin', 'Cout', 'kh', 'kw', 'stride', 'Ho', 'Wo', 'pad_t', 'pad_l',
+                'x_cstride', 'y_cstride', 'cin_pad', 'epilogue', 'precision', 'engine', 'x_layout', 'reserved_')] +
+              [(n, ctypes.c_void_p) for n in ('x_scale', 'y_scale', 'w_scale')])     # H16 scale records (NULL: TF32)
 
 
 _P, _I, _L, _F, _Z = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
@@ -39,46 +40,55 @@ _SIGS = {
   'immb_bn_stats_from_partials': [_P, _I, _I, _P, _P],
   'immb_conv2d_dgrad_stats_rows': [_D],
   'immb_conv2d_dgrad_bnreduce': [_D, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _P, _Z, _P],
-  'immb_conv2d_dgrad_relu': [_D, _P, _P, _P, _P, _P, _I, _P, _P, _P],
+  'immb_conv2d_dgrad_relu': [_D, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P],
   'immb_conv2d_dgrad_relu_supported': [_D],
   'immb_conv2d_wgrad_workspace': [_D],
   'immb_conv2d_wgrad': [_D, _P, _P, _P, _P, _P, _P, _Z, _P],
-  'immb_pack_weights': [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
-  'immb_split_planes': [_P, _P, _P, _L, _P],
+  'immb_pack_weights': [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+  'immb_split_planes': [_P, _P, _P, _L, _P, _P],
   'immb_bn_scratch_elems': [_L, _I],
   'immb_bn_stats': [_P, _L, _I, _I, _P, _P, _Z, _P],
   'immb_bn_finalize': [_P, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P],
-  'immb_bn_apply': [_P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P],
+  'immb_bn_apply': [_P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P, _P],
   'immb_upsample2x_bwd': [_P, _I, _I, _I, _I, _I, _P, _P],
   'immb_bn_bwd_reduce': [_P, _I, _P, _I, _L, _I, _P, _P, _P, _P, _I, _P, _P, _Z, _P],
-  'immb_bn_bwd_apply': [_P, _I, _P, _I, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _Z, _P],
-  'immb_bias_grad': [_P, _P, _I, _L, _I, _P, _P],
+  'immb_bn_bwd_apply': [_P, _I, _P, _I, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _Z, _P, _P],
+  'immb_bias_grad': [_P, _P, _I, _L, _I, _P, _P, _P],
   'immb_cast_d2f': [_P, _P, _L, _P],
-  'immb_softargmax_gauss_fwd': [_P, _I, _I, _I, _I, _F, _P, _P, _P, _I, _P, _P, _I, _I, _P],
+  'immb_softargmax_gauss_fwd': [_P, _I, _I, _I, _I, _F, _P, _P, _P, _I, _P, _P, _I, _I, _P, _P],
   'immb_softargmax_gauss_bwd': [_P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _F, _P, _I, _P],
   'immb_gaussian_maps': [_P, _I, _I, _I, _F, _P, _P],
   'immb_vgg_prologue': [_P, _P, _I, _I, _I, _I, _P, _P, _P],
-  'immb_vgg_conv1_1_fused': [_P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P],
+  'immb_vgg_conv1_1_fused': [_P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P],
   'immb_stage_image_rowwin': [_P, _I, _I, _I, _P, _P, _P],
   'immb_pack_weights_rowwin': [_P, _I, _P, _P, _P],
-  'immb_maxpool2x2_fwd': [_P, _P, _I, _I, _I, _I, _P, _P, _P],
-  'immb_maxpool2x2_fwd_levelsum': [_P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P],
-  'immb_maxpool2x2_bwd_combine': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P],
+  'immb_maxpool2x2_fwd': [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+  'immb_maxpool2x2_fwd_levelsum': [_P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P],
+  'immb_maxpool2x2_bwd_combine': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P],
   'immb_maxpool2x2_bwd': [_P, _P, _P, _I, _I, _I, _I, _P, _P],
-  'immb_perceptual_level_sum': [_P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P, _P],
+  'immb_perceptual_level_sum': [_P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P],
   'immb_perceptual_finalize': [_P, _P, _I, _P, _I, _P, _P, _P, _P],
-  'immb_vgg_bwd_combine': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P],
-  'immb_vgg_conv1_1_bwd_fused': [_P, _P, _P, _I, _P, _P, _I, _P, _P, _I, _I, _P, _P, _P],
+  'immb_vgg_bwd_combine': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P],
+  'immb_vgg_conv1_1_bwd_fused': [_P, _P, _P, _I, _P, _P, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P],
   'immb_pred_grad': [_P, _P, _I, _P, _P, _P, _I, _I, _I, _P, _P, _P],
-  'immb_resize_ac_fwd': [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P],
+  'immb_resize_ac_fwd': [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P],
   'immb_resize_ac_bwd': [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
   'immb_tps_warp': [_P, _I, _I, _I, _I, _P, _I, _I, _P, _P],
   'immb_adam_norms': [_P, _P, _L, _P, _P, _P, _I, _P, _F, _P, _P, _P],
-  'immb_adam_apply': [_P, _P, _P, _P, _L, _P, _P, _P, _I, _P, _F, _P, _F, _F, _F, _F, _F, _P],
-  'immb_adam_apply_dev': [_P, _P, _P, _P, _L, _P, _P, _P, _I, _P, _F, _P, _F, _P, _F, _F, _F, _P],
-  'immb_total_loss': [_P, _P, _P, _I, _P, _P, _P],
+  'immb_adam_apply': [_P, _P, _P, _P, _L, _P, _P, _P, _I, _P, _F, _P, _F, _F, _F, _F, _F, _P, _P],
+  'immb_adam_apply_dev': [_P, _P, _P, _P, _L, _P, _P, _P, _I, _P, _F, _P, _F, _P, _F, _F, _F, _P, _P],
+  'immb_total_loss': [_P, _P, _P, _I, _P, _P, _P, _P],
+  'immb_scale_update': [_P, _I, _P, _P],
+  'immb_multi_amax': [_P, _P, _P, _P, _I, _P, _P],
   'immb_crc32c': [_P, _Z, ctypes.c_uint32],
 }
+# trailing H16 scale-record / amax arguments (just before `stream`): callers that work on fp32 TF32 planes may omit
+# them -- call() fills them with NULL
+_OPTIONAL_TAIL = {'immb_conv2d_dgrad_relu': 1, 'immb_pack_weights': 2, 'immb_split_planes': 1, 'immb_bn_apply': 1,
+                  'immb_bn_bwd_apply': 1, 'immb_bias_grad': 1, 'immb_softargmax_gauss_fwd': 1, 'immb_vgg_conv1_1_fused': 1,
+                  'immb_maxpool2x2_fwd': 2, 'immb_maxpool2x2_fwd_levelsum': 2, 'immb_maxpool2x2_bwd_combine': 2,
+                  'immb_perceptual_level_sum': 1, 'immb_vgg_bwd_combine': 2, 'immb_vgg_conv1_1_bwd_fused': 2,
+                  'immb_resize_ac_fwd': 2, 'immb_adam_apply': 1, 'immb_adam_apply_dev': 1, 'immb_total_loss': 1}
 _RESTYPES = {'immb_conv2d_wgrad_workspace': _Z, 'immb_bn_scratch_elems': _Z, 'immb_crc32c': ctypes.c_uint32}
 
 _lib = None
@@ -148,8 +158,13 @@ def conv_info(name, d):
                                          and d.x_layout == XLAYOUT_NHWC) else 'conv_tc_wgrad_kernel'
   else:
     kernel = 'conv_tc2_pair_kernel' if (halo or (first and 'fwd' in name)) else 'conv_tc_kernel'
-  passes = {PREC_TF32X3: 3, PREC_TF32: 1, PREC_TF32X2: 2}[d.precision]
-  return {'flops': flops, 'kernel': kernel, 'passes': passes, 'kind': 'tf32'}
+  passes = {PREC_TF32X3: 3, PREC_TF32: 1, PREC_TF32X2: 2, PREC_F16X3: 3, PREC_F16X2: 2}[d.precision]
+  f16 = d.precision in (PREC_F16X3, PREC_F16X2)
+  if not (kernel == 'conv_tc2_pair_kernel') and passes == 2:
+    passes = 3                      # only the pair kernel has a 2-pass variant
+  if f16 and wgrad:
+    kernel = 'conv_tc2_wgrad16_kernel'
+  return {'flops': flops, 'kernel': kernel, 'passes': passes, 'kind': 'f16' if f16 else 'tf32'}
 
 
 def _call(name, *args):
@@ -164,6 +179,9 @@ def _call(name, *args):
       conv.append(ctypes.byref(a))
     else:
       conv.append(a)
+  k = _OPTIONAL_TAIL.get(name, 0)
+  if k and len(conv) == len(_SIGS[name]) - k:
+    conv = conv[:-1] + [None] * k + conv[-1:]
   rc = getattr(l, name)(*conv)
   if name in _RESTYPES:
     return rc

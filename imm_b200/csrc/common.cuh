@@ -51,6 +51,50 @@ __device__ __forceinline__ float load_split(const float* hi_p, const float* lo_p
   return v;
 }
 
+// ---- scaled fp16 split ("H16" planes): the operands of the kind::f16 tensor-core convolutions --------------------
+// A tensor v is stored as two fp16 planes and ONE power-of-two scale 2^e (exact):
+//   t = v * 2^e;  hi = rn_f16(t);  lo = rn_f16((t - hi) * 2^11);      v ~= (hi + lo * 2^-11) * 2^-e
+// hi carries 11 significant bits, lo the next 11 (the residual t - hi is exact in fp32 and at most half an ulp of hi,
+// so lo * 2^-11 never underflows before hi does): 22 bits, the same as the TF32 pair.  A product of two such tensors
+// is hi*hi (main accumulator) + (hi*lo + lo*hi) * 2^-11 (cross accumulator), both exact fp16 x fp16 products
+// accumulated in fp32 by the tensor core; the dropped lo*lo term is 2^-22 relative.  Since the scale is a power of
+// two the result does not depend on e as long as hi neither saturates (|t| <= 65504) nor leaves the normal range
+// (|t| >= 2^-14) for the elements that matter: e is chosen so that the tensor's largest magnitude sits near 2^12
+// (16x headroom above, 26 binades below).  Scale record in device memory: int32 {e, amax_bits}: producers read e and
+// atomicMax the bit pattern of the largest |v| they wrote; immb_scale_update turns amax into the next step's e.
+constexpr int kH16TargetExp = 12;
+constexpr float kH16LoScale = 2048.f;               // 2^11
+constexpr float kH16LoInv = 1.f / 2048.f;
+
+__device__ __forceinline__ uint16_t f16_sat(float t) {      // round-to-nearest-even, saturating to +-65504
+  uint16_t r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(t));
+  return r;
+}
+__device__ __forceinline__ float f16_to_f32(uint16_t h) {
+  float f;
+  asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"(h));
+  return f;
+}
+// t = v * 2^e (already scaled) -> (hi, lo) fp16 bit patterns
+__device__ __forceinline__ void split_h16(float t, uint16_t& hi, uint16_t& lo) {
+  hi = f16_sat(t);
+  lo = f16_sat((t - f16_to_f32(hi)) * kH16LoScale);
+}
+__device__ __forceinline__ float join_h16(uint16_t hi, uint16_t lo) {      // scaled value t
+  return fmaf(f16_to_f32(lo), kH16LoInv, f16_to_f32(hi));
+}
+__device__ __forceinline__ uint32_t pack2(uint16_t a, uint16_t b) { return (uint32_t)a | ((uint32_t)b << 16); }
+__device__ __forceinline__ float exp2i(int e) { return scalbnf(1.f, e); }      // exact 2^e
+
+// warp-wide maximum of non-negative floats -> one atomicMax on the tensor's amax record (bit patterns of non-negative
+// floats order like unsigned integers)
+__device__ __forceinline__ void h16_track_amax(int32_t* scale_rec, float amax) {
+  uint32_t b = __float_as_uint(amax);
+  b = __reduce_max_sync(0xffffffffu, b);
+  if ((threadIdx.x & 31) == 0 && b != 0) atomicMax(reinterpret_cast<unsigned int*>(scale_rec + 1), b);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -68,6 +112,14 @@ struct Tc2BnReduce {
   const float* y;
   int ycs, relu;
   const float *scale, *shift, *mean, *invstd;
+};
+
+// scale records ({e, amax bits}, common.cuh "H16 planes") of a conv's activation operand, weight operand and -- when
+// the result is written as H16 planes -- output tensor
+struct Tc2Scales {
+  const int32_t* a;
+  const int32_t* b;
+  int32_t* o;
 };
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -10,22 +10,25 @@ int conv_simt_wgrad(const immb_conv_desc*, const float*, const float*, const flo
                     cudaStream_t);
 // tcgen05 engine (conv_tc.cu)
 bool conv_tc_eligible(const immb_conv_desc* d, int op);
-int conv_tc_fwd(const immb_conv_desc*, const float* x_hi, const float* x_lo, const float* wp_hi,
-                const float* wp_lo, const float* bias, float* y_hi, float* y_lo, cudaStream_t, double* stats = nullptr);
+int conv_tc_fwd(const immb_conv_desc*, const void* x_hi, const void* x_lo, const void* wp_hi,
+                const void* wp_lo, const float* bias, void* y_hi, void* y_lo, cudaStream_t, double* stats = nullptr);
 int conv_tc_fwd_stats_rows(const immb_conv_desc* d);
-int conv_tc_dgrad(const immb_conv_desc*, const float* dy_hi, const float* dy_lo, const float* wh_hi,
-                  const float* wh_lo, float* dx, cudaStream_t);
+int conv_tc_dgrad(const immb_conv_desc*, const void* dy_hi, const void* dy_lo, const void* wh_hi,
+                  const void* wh_lo, float* dx, cudaStream_t);
 int conv_tc_dgrad_stats_rows(const immb_conv_desc* d);
-int conv_tc_dgrad_bnreduce(const immb_conv_desc* d, const float* dy_hi, const float* dy_lo, const float* wh_hi,
-                           const float* wh_lo, float* dx, const float* y_prev, int y_prev_cs, const float* scale,
+int conv_tc_dgrad_bnreduce(const immb_conv_desc* d, const void* dy_hi, const void* dy_lo, const void* wh_hi,
+                           const void* wh_lo, float* dx, const float* y_prev, int y_prev_cs, const float* scale,
                            const float* shift, const float* mean, const float* invstd, int relu, double* partials,
                            cudaStream_t st);
 bool conv_tc_dgrad_relu_eligible(const immb_conv_desc* d);
-int conv_tc_dgrad_relu(const immb_conv_desc* d, const float* dy_hi, const float* dy_lo, const float* wh_hi,
-                       const float* wh_lo, const float* act_hi, int act_cs, float* out_hi, float* out_lo, cudaStream_t);
+int conv_tc_dgrad_relu(const immb_conv_desc* d, const void* dy_hi, const void* dy_lo, const void* wh_hi,
+                       const void* wh_lo, const void* act_hi, int act_cs, void* out_hi, void* out_lo, int32_t* out_scale,
+                       cudaStream_t);
 size_t conv_tc_wgrad_workspace(const immb_conv_desc*);
-int conv_tc_wgrad(const immb_conv_desc*, const float* x_hi, const float* x_lo, const float* dy_hi,
-                  const float* dy_lo, float* dw, void* ws, size_t ws_bytes, cudaStream_t);
+int conv_tc_wgrad(const immb_conv_desc*, const void* x_hi, const void* x_lo, const void* dy_hi,
+                  const void* dy_lo, float* dw, void* ws, size_t ws_bytes, cudaStream_t);
+
+static inline bool is_f16_prec(int p) { return p == IMMB_PREC_F16X3 || p == IMMB_PREC_F16X2; }
 
 static int validate(const immb_conv_desc* d) {
   IMMB_REQUIRE(d, "conv: null descriptor");
@@ -38,6 +41,9 @@ static int validate(const immb_conv_desc* d) {
   IMMB_REQUIRE(d->pad_t >= 0 && d->pad_l >= 0 && d->pad_t < d->kh && d->pad_l < d->kw, "conv: bad padding");
   IMMB_REQUIRE(d->x_layout == IMMB_XLAYOUT_NHWC || d->engine != IMMB_ENGINE_SIMT,
                "conv: the SIMT engine reads plain NHWC only");
+  IMMB_REQUIRE(d->precision >= IMMB_PREC_TF32X3 && d->precision <= IMMB_PREC_F16X2, "conv: bad precision");
+  IMMB_REQUIRE(!is_f16_prec(d->precision) || d->engine != IMMB_ENGINE_SIMT,
+               "conv: fp16 planes are read by the tcgen05 engine only");
   return IMMB_OK;
 }
 
@@ -52,6 +58,8 @@ static int pick_engine(const immb_conv_desc* d, int op, int* engine) {
     *engine = ok ? IMMB_ENGINE_TC : IMMB_ENGINE_SIMT;
     if (!ok && d->x_layout != IMMB_XLAYOUT_NHWC)
       return set_error(IMMB_ERR_UNSUPPORTED, "conv: x_layout ROWWIN4 needs the tcgen05 engine");
+    if (!ok && is_f16_prec(d->precision))
+      return set_error(IMMB_ERR_UNSUPPORTED, "conv: this shape / op has no fp16-plane kernel (use a TF32 precision)");
   }
   return IMMB_OK;
 }
@@ -68,9 +76,9 @@ extern "C" int immb_conv_engine_for(const immb_conv_desc* d, int op) {
   return e;
 }
 
-extern "C" int immb_conv2d_fwd(const immb_conv_desc* d, const float* x_hi, const float* x_lo, const float* w,
-                               const float* wp_hi, const float* wp_lo, const float* bias, float* y_hi,
-                               float* y_lo, void* stream) {
+extern "C" int immb_conv2d_fwd(const immb_conv_desc* d, const void* x_hi, const void* x_lo, const float* w,
+                               const void* wp_hi, const void* wp_lo, const float* bias, void* y_hi,
+                               void* y_lo, void* stream) {
   int rc = validate(d);
   if (rc) return rc;
   IMMB_REQUIRE(x_hi && y_hi, "conv2d_fwd: null tensors");
@@ -79,11 +87,10 @@ extern "C" int immb_conv2d_fwd(const immb_conv_desc* d, const float* x_hi, const
   if (engine == IMMB_ENGINE_TC) {
     IMMB_REQUIRE(wp_hi && (d->precision == IMMB_PREC_TF32 || (wp_lo && x_lo)),
                  "conv2d_fwd: tcgen05 engine needs packed weights and (for TF32x3 / TF32x2) lo planes");
-    IMMB_REQUIRE(d->precision >= IMMB_PREC_TF32X3 && d->precision <= IMMB_PREC_TF32X2, "conv2d_fwd: bad precision");
     return conv_tc_fwd(d, x_hi, x_lo, wp_hi, wp_lo, bias, y_hi, y_lo, (cudaStream_t)stream);
   }
   IMMB_REQUIRE(w, "conv2d_fwd: SIMT engine needs the master weights");
-  return conv_simt_fwd(d, x_hi, x_lo, w, bias, y_hi, y_lo, (cudaStream_t)stream);
+  return conv_simt_fwd(d, (const float*)x_hi, (const float*)x_lo, w, bias, (float*)y_hi, (float*)y_lo, (cudaStream_t)stream);
 }
 
 extern "C" int immb_conv2d_fwd_stats_rows(const immb_conv_desc* d) {
@@ -93,8 +100,8 @@ extern "C" int immb_conv2d_fwd_stats_rows(const immb_conv_desc* d) {
   return conv_tc_fwd_stats_rows(d);
 }
 
-extern "C" int immb_conv2d_fwd_bnstats(const immb_conv_desc* d, const float* x_hi, const float* x_lo,
-                                       const float* wp_hi, const float* wp_lo, const float* bias, float* y,
+extern "C" int immb_conv2d_fwd_bnstats(const immb_conv_desc* d, const void* x_hi, const void* x_lo,
+                                       const void* wp_hi, const void* wp_lo, const float* bias, float* y,
                                        double* partials, size_t partial_elems, void* stream) {
   int rc = validate(d);
   if (rc) return rc;
@@ -105,8 +112,8 @@ extern "C" int immb_conv2d_fwd_bnstats(const immb_conv_desc* d, const float* x_h
   return conv_tc_fwd(d, x_hi, x_lo, wp_hi, wp_lo, bias, y, nullptr, (cudaStream_t)stream, partials);
 }
 
-extern "C" int immb_conv2d_dgrad(const immb_conv_desc* d, const float* dy_hi, const float* dy_lo,
-                                 const float* w, const float* wh_hi, const float* wh_lo, float* dx,
+extern "C" int immb_conv2d_dgrad(const immb_conv_desc* d, const void* dy_hi, const void* dy_lo,
+                                 const float* w, const void* wh_hi, const void* wh_lo, float* dx,
                                  void* stream) {
   int rc = validate(d);
   if (rc) return rc;
@@ -119,7 +126,7 @@ extern "C" int immb_conv2d_dgrad(const immb_conv_desc* d, const float* dy_hi, co
     return conv_tc_dgrad(d, dy_hi, dy_lo, wh_hi, wh_lo, dx, (cudaStream_t)stream);
   }
   IMMB_REQUIRE(w, "conv2d_dgrad: SIMT engine needs the master weights");
-  return conv_simt_dgrad(d, dy_hi, dy_lo, w, dx, (cudaStream_t)stream);
+  return conv_simt_dgrad(d, (const float*)dy_hi, (const float*)dy_lo, w, dx, (cudaStream_t)stream);
 }
 
 extern "C" int immb_conv2d_dgrad_stats_rows(const immb_conv_desc* d) {
@@ -129,8 +136,8 @@ extern "C" int immb_conv2d_dgrad_stats_rows(const immb_conv_desc* d) {
   return conv_tc_dgrad_stats_rows(d);
 }
 
-extern "C" int immb_conv2d_dgrad_bnreduce(const immb_conv_desc* d, const float* dy_hi, const float* dy_lo,
-                                          const float* wh_hi, const float* wh_lo, float* dx, const float* y_prev,
+extern "C" int immb_conv2d_dgrad_bnreduce(const immb_conv_desc* d, const void* dy_hi, const void* dy_lo,
+                                          const void* wh_hi, const void* wh_lo, float* dx, const float* y_prev,
                                           int y_prev_cstride, const float* scale, const float* shift, const float* mean,
                                           const float* invstd, int relu, double* partials, size_t partial_elems,
                                           void* stream) {
@@ -146,17 +153,20 @@ extern "C" int immb_conv2d_dgrad_bnreduce(const immb_conv_desc* d, const float* 
                                 partials, (cudaStream_t)stream);
 }
 
-extern "C" int immb_conv2d_dgrad_relu(const immb_conv_desc* d, const float* dy_hi, const float* dy_lo,
-                                      const float* wh_hi, const float* wh_lo, const float* act_hi, int act_cstride,
-                                      float* out_hi, float* out_lo, void* stream) {
+extern "C" int immb_conv2d_dgrad_relu(const immb_conv_desc* d, const void* dy_hi, const void* dy_lo,
+                                      const void* wh_hi, const void* wh_lo, const void* act_hi, int act_cstride,
+                                      void* out_hi, void* out_lo, int32_t* out_scale, void* stream) {
   int rc = validate(d);
   if (rc) return rc;
   IMMB_REQUIRE(dy_hi && wh_hi && act_hi && out_hi && out_lo && act_cstride >= d->Cin, "conv2d_dgrad_relu: null tensors");
-  IMMB_REQUIRE(d->precision == IMMB_PREC_TF32 || (dy_lo && (d->precision == IMMB_PREC_TF32X2 || wh_lo)),
+  IMMB_REQUIRE(d->precision == IMMB_PREC_TF32 ||
+                   (dy_lo && (d->precision == IMMB_PREC_TF32X2 || d->precision == IMMB_PREC_F16X2 || wh_lo)),
                "conv2d_dgrad_relu: lo planes missing");
+  IMMB_REQUIRE(!is_f16_prec(d->precision) || out_scale, "conv2d_dgrad_relu: fp16 output planes need their scale record");
   if (!conv_tc_dgrad_relu_eligible(d))
     return immb::set_error(IMMB_ERR_UNSUPPORTED, "conv2d_dgrad_relu: shape not covered by the halo pair kernel");
-  return conv_tc_dgrad_relu(d, dy_hi, dy_lo, wh_hi, wh_lo, act_hi, act_cstride, out_hi, out_lo, (cudaStream_t)stream);
+  return conv_tc_dgrad_relu(d, dy_hi, dy_lo, wh_hi, wh_lo, act_hi, act_cstride, out_hi, out_lo, out_scale,
+                            (cudaStream_t)stream);
 }
 
 extern "C" int immb_conv2d_dgrad_relu_supported(const immb_conv_desc* d) {
@@ -170,8 +180,8 @@ extern "C" size_t immb_conv2d_wgrad_workspace(const immb_conv_desc* d) {
   return engine == IMMB_ENGINE_TC ? conv_tc_wgrad_workspace(d) : 0;
 }
 
-extern "C" int immb_conv2d_wgrad(const immb_conv_desc* d, const float* x_hi, const float* x_lo,
-                                 const float* dy_hi, const float* dy_lo, float* dw, void* workspace,
+extern "C" int immb_conv2d_wgrad(const immb_conv_desc* d, const void* x_hi, const void* x_lo,
+                                 const void* dy_hi, const void* dy_lo, float* dw, void* workspace,
                                  size_t ws_bytes, void* stream) {
   int rc = validate(d);
   if (rc) return rc;
@@ -182,5 +192,6 @@ extern "C" int immb_conv2d_wgrad(const immb_conv_desc* d, const float* x_hi, con
     IMMB_REQUIRE(d->precision == IMMB_PREC_TF32 || (x_lo && dy_lo), "conv2d_wgrad: TF32x3 needs lo planes");
     return conv_tc_wgrad(d, x_hi, x_lo, dy_hi, dy_lo, dw, workspace, ws_bytes, (cudaStream_t)stream);
   }
-  return conv_simt_wgrad(d, x_hi, x_lo, dy_hi, dy_lo, dw, (cudaStream_t)stream);
+  return conv_simt_wgrad(d, (const float*)x_hi, (const float*)x_lo, (const float*)dy_hi, (const float*)dy_lo, dw,
+                         (cudaStream_t)stream);
 }

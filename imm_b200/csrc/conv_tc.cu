@@ -50,6 +50,12 @@ struct TcParams {
   int out_mul, out_add_h, out_add_w;
   int n_cols;                 // valid output channels
   int n_store;                // channels written (n_cols rounded up to 4, <= ocs; the excess is exact zeros)
+  // scaled-fp16 operands (F16 kernels): scale records of the A / B operands and of H16 output planes; 32-byte k-steps
+  // to issue in the last K chunk
+  const int32_t* a_scale;
+  const int32_t* b_scale;
+  int32_t* o_scale;
+  int k_last;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -65,12 +71,15 @@ struct FwdCfg {
   static constexpr int TMEM_COLS = ACC <= 32 ? 32 : (ACC <= 64 ? 64 : (ACC <= 128 ? 128 : 256));
 };
 
-template <int BN, int PASSES, int STAGES>
+// F16: scaled fp16 split planes (common.cuh), kind::f16: a K chunk of 128 bytes holds 64 channels; PASSES 3 = hi*hi into
+// columns [0,BN), hi*lo (same N-concatenated MMA) and lo*hi into the cross columns [BN,2BN), which carry 2^-11.
+template <int BN, int PASSES, int STAGES, bool F16>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
                const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
                const __grid_constant__ TcParams p) {
   using Cfg = FwdCfg<BN, PASSES, STAGES>;
+  constexpr int KC = F16 ? 64 : 32;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
@@ -124,12 +133,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
         uint8_t* st = smem + s * Cfg::STAGE_BYTES;
         if (elect_one()) {
         mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
-        const int c = kc * 32 + t.dc, w = tw * p.TW + t.dw, h = th * p.TH + t.dh, n = tn * p.TN;
+        const int c = kc * KC + t.dc, w = tw * p.TW + t.dw, h = th * p.TH + t.dh, n = tn * p.TN;
         tma_load_5d(st, &mapA_hi, &full[s], c, w, t.hp, h, n);
         if (PASSES == 3) tma_load_5d(st + Cfg::A_BYTES, &mapA_lo, &full[s], c, w, t.hp, h, n);
         uint8_t* sb = st + Cfg::A_BYTES * Cfg::NPL;
-        tma_load_3d(sb, &mapB_hi, &full[s], kc * 32, n_off, t.b_tap);
-        if (PASSES == 3) tma_load_3d(sb + Cfg::B_BYTES, &mapB_lo, &full[s], kc * 32, n_off, t.b_tap);
+        tma_load_3d(sb, &mapB_hi, &full[s], kc * KC, n_off, t.b_tap);
+        if (PASSES == 3) tma_load_3d(sb + Cfg::B_BYTES, &mapB_lo, &full[s], kc * KC, n_off, t.b_tap);
         }
         __syncwarp();
       }
@@ -137,8 +146,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
   } else if (warp == 1) {
     {
       // ===== MMA issuer (whole warp, uniform values; one elected lane issues) =====
-      constexpr uint32_t idesc = idesc_tf32(kTileM, BN, 0, 0);
-      constexpr uint32_t idesc2 = idesc_tf32(kTileM, 2 * BN, 0, 0);      // [w_hi ; w_lo] (contiguous in the stage)
+      constexpr uint32_t idesc = idesc_kind<F16>(kTileM, BN, 0, 0);
+      constexpr uint32_t idesc2 = idesc_kind<F16>(kTileM, 2 * BN, 0, 0);      // [w_hi ; w_lo] (contiguous in the stage)
       for (int kt = 0; kt < num_k; ++kt) {
         const int s = kt % STAGES;
         const uint32_t ph = (kt / STAGES) & 1;
@@ -147,16 +156,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
         const uint32_t a_hi = smem_u32(smem + s * Cfg::STAGE_BYTES);
         const uint32_t a_lo = a_hi + Cfg::A_BYTES;
         const uint32_t b_hi = a_hi + Cfg::A_BYTES * Cfg::NPL;
+        const int kc_ = kt % p.kchunks;
+        const int nk = (F16 && kc_ == p.kchunks - 1) ? p.k_last : 4;
         if (elect_one()) {
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {
-          const uint32_t ko = k4 * 32;    // 8 tf32 = 32 bytes along K inside the 128-byte swizzle row
+          if (k4 < nk) {
+          const uint32_t ko = k4 * 32;    // 8 tf32 / 16 fp16 = 32 bytes along K inside the 128-byte swizzle row
           const uint64_t da_hi = smem_desc_sw128(a_hi + ko, 16, 1024);
           const uint64_t db_hi = smem_desc_sw128(b_hi + ko, 16, 1024);
-          mma_tf32(tmem_base, da_hi, db_hi, PASSES == 3 ? idesc2 : idesc, (kt > 0 || k4 > 0) ? 1u : 0u);
+          mma_kind<F16>(tmem_base, da_hi, db_hi, PASSES == 3 ? idesc2 : idesc, (kt > 0 || k4 > 0) ? 1u : 0u);
           if (PASSES == 3) {
             const uint64_t da_lo = smem_desc_sw128(a_lo + ko, 16, 1024);
-            mma_tf32(tmem_base, da_lo, db_hi, idesc, 1u);
+            // TF32: lo*hi joins the main columns; F16: the lo plane carries 2^11, so it joins hi*lo in the cross columns
+            mma_kind<F16>(F16 ? tmem_base + BN : tmem_base, da_lo, db_hi, idesc, 1u);
+          }
           }
         }
         mma_commit(&empty[s]);            // frees the smem stage once these MMAs have drained
@@ -174,6 +188,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
     const bool row_ok = (n < p.N) && (h < p.PH) && (w < p.PW);
     const size_t pix = ((size_t)n * p.OH + (size_t)(h * p.out_mul + out_add_h)) * p.OW +
                        (size_t)(w * p.out_mul + out_add_w);
+    float s_main = 1.f, s_cross = 1.f, s_out = 1.f, amax = 0.f;
+    if (F16) {
+      const int e = __ldg(p.a_scale) + __ldg(p.b_scale);
+      s_main = exp2i(-e);
+      s_cross = exp2i(-e - 11);
+      if (p.out_lo) s_out = exp2i(__ldg(p.o_scale));
+    }
     mbar_wait(tmem_full, 0);
     tc_fence_after();
 #pragma unroll 1
@@ -184,7 +205,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
         float v2[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c0), v2);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += v2[j];
+        for (int j = 0; j < 32; ++j) v[j] = F16 ? fmaf(v2[j], s_cross, v[j] * s_main) : v[j] + v2[j];
+      } else if (F16) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= s_main;
       }
       if (!row_ok) continue;
       const int col0 = n_off + c0;
@@ -197,6 +221,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
       if (p.relu) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (F16 && p.out_lo) {
+        // H16 output planes (ocs % 8 == 0, n_store % 8 == 0): 16-byte stores
+        uint16_t* oh = reinterpret_cast<uint16_t*>(p.out_hi) + pix * p.ocs + col0;
+        uint16_t* ol = reinterpret_cast<uint16_t*>(p.out_lo) + pix * p.ocs + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          if (col0 + j >= p.n_store) break;
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint16_t h0, l0, h1, l1;
+            amax = fmaxf(amax, fmaxf(fabsf(v[j + 2 * u]), fabsf(v[j + 2 * u + 1])));
+            split_h16(v[j + 2 * u] * s_out, h0, l0);
+            split_h16(v[j + 2 * u + 1] * s_out, h1, l1);
+            hw[u] = pack2(h0, h1);
+            lw[u] = pack2(l0, l1);
+          }
+          *reinterpret_cast<uint4*>(oh + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(ol + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+        continue;
       }
       float* o = p.out_hi + pix * p.ocs + col0;
       const bool vec8 = (p.ocs % 8 == 0) && (p.n_store % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.out_hi) & 31) == 0) &&
@@ -237,6 +283,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
           *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
       }
+    }
+    if (F16 && p.out_lo) {
+      __syncwarp();
+      h16_track_amax(p.o_scale, amax);
     }
   }
   tc_fence_before();
@@ -451,12 +501,13 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   return fn;
 }
 
-static int make_map(CUtensorMap* m, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
-                    const uint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
+                    const uint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, int esize = 4) {
   auto fn = get_encode_fn();
   if (!fn) return set_error(IMMB_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
   uint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base),
+  CUresult r = fn(m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                  const_cast<void*>(base),
                   reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_b),
                   reinterpret_cast<const cuuint32_t*>(box), reinterpret_cast<const cuuint32_t*>(estr),
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -467,20 +518,22 @@ static int make_map(CUtensorMap* m, const float* base, int rank, const uint64_t*
 
 // 5-D activation view (c, w, hpar, h, n) of an NHWC tensor [N,H,W,cs] with `C` valid channels.
 // parity_split: (c + wpar*C, w/2, hpar, h/2, n) view used by stride-2 convolutions (needs cs == C, even H, W).
-static int make_act_map(CUtensorMap* m, const float* base, int N, int H, int W, int C, int cs, bool parity_split,
-                        int box_w, int box_h, int box_n, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+static int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int cs, bool parity_split,
+                        int box_w, int box_h, int box_n, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B,
+                        int esize = 4) {
   uint64_t dims[5], str[4];
-  uint32_t box[5] = {32, (uint32_t)box_w, 1, (uint32_t)box_h, (uint32_t)box_n};
+  const uint64_t es = (uint64_t)esize;
+  uint32_t box[5] = {(uint32_t)(128 / esize), (uint32_t)box_w, 1, (uint32_t)box_h, (uint32_t)box_n};
   if (!parity_split) {
     dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = N;
-    str[0] = (uint64_t)cs * 4; str[1] = (uint64_t)W * cs * 4; str[2] = (uint64_t)W * cs * 4;
-    str[3] = (uint64_t)H * W * cs * 4;
+    str[0] = (uint64_t)cs * es; str[1] = (uint64_t)W * cs * es; str[2] = (uint64_t)W * cs * es;
+    str[3] = (uint64_t)H * W * cs * es;
   } else {
     dims[0] = 2 * (uint64_t)C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = N;
-    str[0] = (uint64_t)2 * C * 4; str[1] = (uint64_t)W * C * 4; str[2] = (uint64_t)2 * W * C * 4;
-    str[3] = (uint64_t)H * W * C * 4;
+    str[0] = (uint64_t)2 * C * es; str[1] = (uint64_t)W * C * es; str[2] = (uint64_t)2 * W * C * es;
+    str[3] = (uint64_t)H * W * C * es;
   }
-  return make_map(m, base, 5, dims, str, box, swz);
+  return make_map(m, base, 5, dims, str, box, swz, esize);
 }
 
 // Row-window view of the staged first-layer image [N,H,W+8,4]: element (j, w, 0, h, n) = x4[n, h, w + j/4, j%4],
@@ -496,21 +549,23 @@ static int make_rowwin_map(CUtensorMap* m, const float* base, int N, int H, int 
 }
 
 // 3-D weight view (k, n, tap) of [taps][Nn][Kd] with box (32, BN, 1)
-static int make_w_map(CUtensorMap* m, const float* base, int taps, int Nn, int Kd, int bn) {
+static int make_w_map(CUtensorMap* m, const void* base, int taps, int Nn, int Kd, int bn, int esize = 4) {
   uint64_t dims[3] = {(uint64_t)Kd, (uint64_t)Nn, (uint64_t)taps};
-  uint64_t str[2] = {(uint64_t)Kd * 4, (uint64_t)Nn * Kd * 4};
-  uint32_t box[3] = {32, (uint32_t)bn, 1};
-  return make_map(m, base, 3, dims, str, box);
+  uint64_t str[2] = {(uint64_t)Kd * esize, (uint64_t)Nn * Kd * esize};
+  uint32_t box[3] = {(uint32_t)(128 / esize), (uint32_t)bn, 1};
+  return make_map(m, base, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, esize);
 }
 
 // exported to conv_tc2.cu
-int tc_make_act_map(CUtensorMap* m, const float* base, int N, int H, int W, int C, int cs, bool parity_split,
-                    int box_w, int box_h, int box_n, int swizzle_mn) {
+// swizzle_mn: MN-major operands of the wgrad kernels: the TF32 path needs the 32-byte-atom variant; fp16 planes use
+// the standard 128-byte swizzle for both majors
+int tc_make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int cs, bool parity_split,
+                    int box_w, int box_h, int box_n, int swizzle_mn, int esize) {
   return make_act_map(m, base, N, H, W, C, cs, parity_split, box_w, box_h, box_n,
-                      swizzle_mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
+                      (swizzle_mn && esize == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, esize);
 }
-int tc_make_w_map(CUtensorMap* m, const float* base, int taps, int Nn, int Kd, int bn) {
-  return make_w_map(m, base, taps, Nn, Kd, bn);
+int tc_make_w_map(CUtensorMap* m, const void* base, int taps, int Nn, int Kd, int bn, int esize) {
+  return make_w_map(m, base, taps, Nn, Kd, bn, esize);
 }
 int tc_make_rowwin_map(CUtensorMap* m, const float* base, int N, int H, int W, int box_w, int box_h, int box_n) {
   return make_rowwin_map(m, base, N, H, W, box_w, box_h, box_n, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -521,16 +576,20 @@ int conv_tc2_rowwin_fwd(const immb_conv_desc* d, const float* x_hi, const float*
                         double* stats = nullptr);
 bool conv_tc2_eligible(const immb_conv_desc* d, int op);
 bool conv_tc2_wgrad_eligible(const immb_conv_desc* d);
-int conv_tc2_wgrad_run(const immb_conv_desc* d, const float* x_hi, const float* x_lo, const float* dy_hi,
-                       const float* dy_lo, float* dw, cudaStream_t st);
-int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const float* act_lo, int act_c, int act_cs,
-                 const float* w_hi, const float* w_lo, int w_rows, int kd, const float* bias, int relu,
-                 float* out_hi, float* out_lo, int ocs, int ncols, int n_store, cudaStream_t st,
-                 const float* relu_src = nullptr, int relu_cs = 0, double* stats = nullptr,
-                 const Tc2BnReduce* bnr = nullptr);
+int conv_tc2_wgrad_run(const immb_conv_desc* d, const void* x_hi, const void* x_lo, const void* dy_hi,
+                       const void* dy_lo, float* dw, cudaStream_t st);
+int conv_tc2_run(const immb_conv_desc* d, int op, const void* act_hi, const void* act_lo, int act_c, int act_cs,
+                 const void* w_hi, const void* w_lo, int w_rows, int kd, const float* bias, int relu,
+                 void* out_hi, void* out_lo, int ocs, int ncols, int n_store, cudaStream_t st,
+                 const void* relu_src = nullptr, int relu_cs = 0, double* stats = nullptr,
+                 const Tc2BnReduce* bnr = nullptr, const Tc2Scales* sc = nullptr);
 int conv_tc2_fwd_stats_rows(const immb_conv_desc* d);
 int conv_tc2_dgrad_stats_rows(const immb_conv_desc* d);
 int conv_tc2_pair_mode();
+
+static inline bool is_f16(const immb_conv_desc* d) {
+  return d->precision == IMMB_PREC_F16X3 || d->precision == IMMB_PREC_F16X2;
+}
 
 static bool pick_tile(int PH, int PW, int N, int* TW, int* TH, int* TN) {
   if (PW % 16 == 0 && PH % 8 == 0) { *TW = 16; *TH = 8; *TN = 1; return true; }
@@ -544,6 +603,11 @@ static int pymod(int a, int b) { return a - floordiv(a, b) * b; }
 
 bool conv_tc_eligible(const immb_conv_desc* d, int op) {
   int TW, TH, TN;
+  if (is_f16(d)) {
+    // fp16 planes: 16-byte pixel strides, no row-window first layer, weight gradients through the halo wgrad kernel only
+    if (d->x_layout != IMMB_XLAYOUT_NHWC || d->x_cstride % 8 || d->y_cstride % 8) return false;
+    if (op == 2 && !conv_tc2_wgrad_eligible(d)) return false;
+  }
   if (d->x_layout == IMMB_XLAYOUT_ROWWIN4) {
     // first encoder layer: 7x7, Cin = 3, stride 1 on the staged [N,H,W+8,4] image (no dgrad: the input is data)
     if (d->kh != 7 || d->kw != 7 || d->Cin != 3 || d->stride != 1 || op == 1) return false;
@@ -570,12 +634,12 @@ bool conv_tc_eligible(const immb_conv_desc* d, int op) {
   }
 }
 
-template <int BN, int PASSES>
+template <int BN, int PASSES, bool F16 = false>
 static int launch_fwd(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                       const CUtensorMap& b_lo, const TcParams& p, dim3 grid, cudaStream_t st) {
   constexpr int STAGES = PASSES == 3 ? (BN <= 64 ? 4 : 3) : (BN <= 64 ? 6 : 4);
   using Cfg = FwdCfg<BN, PASSES, STAGES>;
-  auto kern = conv_tc_kernel<BN, PASSES, STAGES>;
+  auto kern = conv_tc_kernel<BN, PASSES, STAGES, F16>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
@@ -588,7 +652,19 @@ static int launch_fwd(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CU
 
 static int dispatch_fwd(int bn, int passes, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
                         const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcParams& p, dim3 grid,
-                        cudaStream_t st) {
+                        cudaStream_t st, bool f16 = false) {
+  if (f16) {
+    if (passes != 3) return set_error(IMMB_ERR_INVALID, "conv_tc: single-pass fp16 is not built");
+#define IMMB_CASE16(BN_) \
+  if (bn == BN_) return launch_fwd<BN_, 3, true>(a_hi, a_lo, b_hi, b_lo, p, grid, st);
+    IMMB_CASE16(16)
+    IMMB_CASE16(32)
+    IMMB_CASE16(64)
+    IMMB_CASE16(96)
+    IMMB_CASE16(128)
+#undef IMMB_CASE16
+    return set_error(IMMB_ERR_INVALID, "conv_tc (fp16): unsupported BN %d", bn);
+  }
 #define IMMB_CASE(BN_)                                                                         \
   if (bn == BN_)                                                                               \
     return passes == 3 ? launch_fwd<BN_, 3>(a_hi, a_lo, b_hi, b_lo, p, grid, st)               \
@@ -618,16 +694,29 @@ static int pick_bn(int ncols) {
 
 int conv_tc_fwd_stats_rows(const immb_conv_desc* d) { return conv_tc2_fwd_stats_rows(d); }
 
-int conv_tc_fwd(const immb_conv_desc* d, const float* x_hi, const float* x_lo, const float* wp_hi,
-                const float* wp_lo, const float* bias, float* y_hi, float* y_lo, cudaStream_t st, double* stats) {
+// number of 32-byte k-steps of the last 128-byte K chunk that hold weights (fp16: 16 channels per k-step)
+static inline int k_last_steps(int kd, bool f16) {
+  if (!f16) return 4;
+  const int rem = kd - (ceil_div(kd, 64) - 1) * 64;
+  return ceil_div(rem, 16);
+}
+
+int conv_tc_fwd(const immb_conv_desc* d, const void* x_hi, const void* x_lo, const void* wp_hi,
+                const void* wp_lo, const float* bias, void* y_hi, void* y_lo, cudaStream_t st, double* stats) {
+  const bool f16 = is_f16(d);
+  const int esize = f16 ? 2 : 4, kchunk = f16 ? 64 : 32;
+  const Tc2Scales sc{d->x_scale, d->w_scale, d->y_scale};
+  if (f16 && (!sc.a || !sc.b || (y_lo && !sc.o)))
+    return set_error(IMMB_ERR_INVALID, "conv_tc_fwd: fp16 planes need x_scale / w_scale (and y_scale for plane outputs)");
   if (stats && conv_tc2_fwd_stats_rows(d) == 0)
     return set_error(IMMB_ERR_UNSUPPORTED, "conv_tc_fwd: fused BN statistics are not available for this shape");
   if (conv_tc2_eligible(d, 0))
     return conv_tc2_run(d, 0, x_hi, x_lo, d->Cin, d->x_cstride, wp_hi, wp_lo, d->Cout, d->cin_pad, bias,
-                        d->epilogue == IMMB_EPI_BIAS_RELU, y_hi, y_lo, d->y_cstride, d->Cout, (d->Cout + 3) / 4 * 4, st,
-                        nullptr, 0, stats);
+                        d->epilogue == IMMB_EPI_BIAS_RELU, y_hi, y_lo, d->y_cstride, d->Cout,
+                        f16 ? (d->Cout + 7) / 8 * 8 : (d->Cout + 3) / 4 * 4, st, nullptr, 0, stats, nullptr, &sc);
   if (conv_tc2_rowwin_eligible(d))
-    return conv_tc2_rowwin_fwd(d, x_hi, x_lo, wp_hi, wp_lo, bias, d->epilogue == IMMB_EPI_BIAS_RELU, y_hi, y_lo, st, stats);
+    return conv_tc2_rowwin_fwd(d, (const float*)x_hi, (const float*)x_lo, (const float*)wp_hi, (const float*)wp_lo, bias,
+                               d->epilogue == IMMB_EPI_BIAS_RELU, (float*)y_hi, (float*)y_lo, st, stats);
   const int passes = d->precision == IMMB_PREC_TF32 ? 1 : 3;
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -638,7 +727,7 @@ int conv_tc_fwd(const immb_conv_desc* d, const float* x_hi, const float* x_lo, c
     p.n_taps = 7; p.kchunks = 1;
     for (int r = 0; r < 7; ++r) { TapEntry& t = p.taps[r]; t.b_tap = r; t.dc = 0; t.dw = 0; t.hp = 0; t.dh = r - d->pad_t; }
   } else {
-    p.n_taps = d->kh * d->kw; p.kchunks = d->cin_pad / 32;
+    p.n_taps = d->kh * d->kw; p.kchunks = ceil_div(d->cin_pad, kchunk);
     for (int r = 0; r < d->kh; ++r)
       for (int s = 0; s < d->kw; ++s) {
         TapEntry& t = p.taps[r * d->kw + s];
@@ -648,62 +737,71 @@ int conv_tc_fwd(const immb_conv_desc* d, const float* x_hi, const float* x_lo, c
         else { t.dh = floordiv(th, 2); t.hp = pymod(th, 2); t.dw = floordiv(tw, 2); t.dc = pymod(tw, 2) * d->Cin; }
       }
   }
-  p.out_hi = y_hi; p.out_lo = y_lo; p.bias = bias; p.relu = d->epilogue == IMMB_EPI_BIAS_RELU;
+  p.out_hi = (float*)y_hi; p.out_lo = (float*)y_lo; p.bias = bias; p.relu = d->epilogue == IMMB_EPI_BIAS_RELU;
   p.N = d->N; p.PH = d->Ho; p.PW = d->Wo; p.OH = d->Ho; p.OW = d->Wo; p.ocs = d->y_cstride;
   p.out_mul = 1; p.out_add_h = 0; p.out_add_w = 0; p.n_cols = d->Cout;
-  p.n_store = (d->Cout + 3) / 4 * 4;
+  p.n_store = f16 ? (d->Cout + 7) / 8 * 8 : (d->Cout + 3) / 4 * 4;      // fp16 layers: 8-channel output strides
+  p.a_scale = sc.a; p.b_scale = sc.b; p.o_scale = sc.o;
   const int bn = pick_bn(d->Cout);
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
   int rc;
   const bool split = d->stride == 2;
   const int kd = rowwin ? 32 : d->cin_pad;
-  auto amap = [&](CUtensorMap* m, const float* base) {
-    return rowwin ? make_rowwin_map(m, base, d->N, d->H, d->W, p.TW, p.TH, p.TN, CU_TENSOR_MAP_SWIZZLE_128B)
-                  : make_act_map(m, base, d->N, d->H, d->W, d->Cin, d->x_cstride, split, p.TW, p.TH, p.TN);
+  p.k_last = k_last_steps(kd, f16);
+  auto amap = [&](CUtensorMap* m, const void* base) {
+    return rowwin ? make_rowwin_map(m, (const float*)base, d->N, d->H, d->W, p.TW, p.TH, p.TN, CU_TENSOR_MAP_SWIZZLE_128B)
+                  : make_act_map(m, base, d->N, d->H, d->W, d->Cin, d->x_cstride, split, p.TW, p.TH, p.TN,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, esize);
   };
   if ((rc = amap(&a_hi, x_hi))) return rc;
-  if ((rc = make_w_map(&b_hi, wp_hi, p.n_taps, d->Cout, kd, bn))) return rc;
+  if ((rc = make_w_map(&b_hi, wp_hi, p.n_taps, d->Cout, kd, bn, esize))) return rc;
   a_lo = a_hi; b_lo = b_hi;
   if (passes == 3) {
     if ((rc = amap(&a_lo, x_lo))) return rc;
-    if ((rc = make_w_map(&b_lo, wp_lo, p.n_taps, d->Cout, kd, bn))) return rc;
+    if ((rc = make_w_map(&b_lo, wp_lo, p.n_taps, d->Cout, kd, bn, esize))) return rc;
   }
   dim3 grid(p.tiles_w * p.tiles_h * ceil_div(d->N, p.TN), ceil_div(d->Cout, bn));
-  return dispatch_fwd(bn, passes, a_hi, a_lo, b_hi, b_lo, p, grid, st);
+  return dispatch_fwd(bn, passes, a_hi, a_lo, b_hi, b_lo, p, grid, st, f16);
 }
 
-// dgrad fused with the backward of the ReLU that produced the conv's input and with the TF32 split of the result:
+// dgrad fused with the backward of the ReLU that produced the conv's input and with the operand split of the result:
 // out = split(dgrad(dy) * [act_hi > 0]).  Halo pair kernel only (stride-1 3x3, H % 16 == 0, W % 16 == 0).
 bool conv_tc_dgrad_relu_eligible(const immb_conv_desc* d) {
   return conv_tc_eligible(d, 1) && conv_tc2_eligible(d, 1) && conv_tc2_pair_mode() == 1 && d->x_cstride % 8 == 0;
 }
-int conv_tc_dgrad_relu(const immb_conv_desc* d, const float* dy_hi, const float* dy_lo, const float* wh_hi,
-                       const float* wh_lo, const float* act_hi, int act_cs, float* out_hi, float* out_lo,
-                       cudaStream_t st) {
+int conv_tc_dgrad_relu(const immb_conv_desc* d, const void* dy_hi, const void* dy_lo, const void* wh_hi,
+                       const void* wh_lo, const void* act_hi, int act_cs, void* out_hi, void* out_lo,
+                       int32_t* out_scale, cudaStream_t st) {
   const int ncols = d->cin_pad < d->x_cstride ? d->cin_pad : d->x_cstride;
+  const Tc2Scales sc{d->y_scale, d->w_scale, out_scale};
   return conv_tc2_run(d, 1, dy_hi, dy_lo, d->Cout, d->y_cstride, wh_hi, wh_lo, d->cin_pad, d->y_cstride, nullptr, 0,
-                      out_hi, out_lo, d->x_cstride, ncols, ncols, st, act_hi, act_cs);
+                      out_hi, out_lo, d->x_cstride, ncols, ncols, st, act_hi, act_cs, nullptr, nullptr, &sc);
 }
 
 // dgrad that also accumulates, in its epilogue, the BN-backward sums of the layer that produced its input
 int conv_tc_dgrad_stats_rows(const immb_conv_desc* d) { return conv_tc_eligible(d, 1) ? conv_tc2_dgrad_stats_rows(d) : 0; }
-int conv_tc_dgrad_bnreduce(const immb_conv_desc* d, const float* dy_hi, const float* dy_lo, const float* wh_hi,
-                           const float* wh_lo, float* dx, const float* y_prev, int y_prev_cs, const float* scale,
+int conv_tc_dgrad_bnreduce(const immb_conv_desc* d, const void* dy_hi, const void* dy_lo, const void* wh_hi,
+                           const void* wh_lo, float* dx, const float* y_prev, int y_prev_cs, const float* scale,
                            const float* shift, const float* mean, const float* invstd, int relu, double* partials,
                            cudaStream_t st) {
   const int ncols = d->cin_pad < d->x_cstride ? d->cin_pad : d->x_cstride;
   Tc2BnReduce b{y_prev, y_prev_cs, relu, scale, shift, mean, invstd};
+  const Tc2Scales sc{d->y_scale, d->w_scale, nullptr};
   return conv_tc2_run(d, 1, dy_hi, dy_lo, d->Cout, d->y_cstride, wh_hi, wh_lo, d->cin_pad, d->y_cstride, nullptr, 0,
-                      dx, nullptr, d->x_cstride, ncols, ncols, st, nullptr, 0, partials, &b);
+                      dx, nullptr, d->x_cstride, ncols, ncols, st, nullptr, 0, partials, &b, &sc);
 }
 
-int conv_tc_dgrad(const immb_conv_desc* d, const float* dy_hi, const float* dy_lo, const float* wh_hi,
-                  const float* wh_lo, float* dx, cudaStream_t st) {
+int conv_tc_dgrad(const immb_conv_desc* d, const void* dy_hi, const void* dy_lo, const void* wh_hi,
+                  const void* wh_lo, float* dx, cudaStream_t st) {
+  const bool f16 = is_f16(d);
+  const int esize = f16 ? 2 : 4, kchunk = f16 ? 64 : 32;
+  const Tc2Scales sc{d->y_scale, d->w_scale, nullptr};
+  if (f16 && (!sc.a || !sc.b)) return set_error(IMMB_ERR_INVALID, "conv_tc_dgrad: fp16 planes need y_scale / w_scale");
   const int passes = d->precision == IMMB_PREC_TF32 ? 1 : 3;
   const int ncols = d->cin_pad < d->x_cstride ? d->cin_pad : d->x_cstride;   // channels of dx that get written
   if (conv_tc2_eligible(d, 1))
     return conv_tc2_run(d, 1, dy_hi, dy_lo, d->Cout, d->y_cstride, wh_hi, wh_lo, d->cin_pad, d->y_cstride, nullptr, 0,
-                        dx, nullptr, d->x_cstride, ncols, ncols, st);
+                        dx, nullptr, d->x_cstride, ncols, ncols, st, nullptr, 0, nullptr, nullptr, &sc);
   const int bn = pick_bn(ncols);
   const int classes = d->stride == 1 ? 1 : 4;
   TcParams p;
@@ -711,7 +809,9 @@ int conv_tc_dgrad(const immb_conv_desc* d, const float* dy_hi, const float* dy_l
   p.PH = d->H / d->stride; p.PW = d->W / d->stride;
   if (!pick_tile(p.PH, p.PW, d->N, &p.TW, &p.TH, &p.TN)) return set_error(IMMB_ERR_UNSUPPORTED, "conv_tc_dgrad: tile");
   p.tiles_w = p.PW / p.TW; p.tiles_h = p.PH / p.TH;
-  p.kchunks = ceil_div(d->y_cstride, 32);
+  p.kchunks = ceil_div(d->y_cstride, kchunk);
+  p.k_last = k_last_steps(d->y_cstride, f16);
+  p.a_scale = sc.a; p.b_scale = sc.b; p.o_scale = nullptr;
   p.n_classes = classes;
   for (int cls = 0; cls < classes; ++cls) {
     const int phh = cls >> 1, pww = cls & 1;
@@ -735,15 +835,16 @@ int conv_tc_dgrad(const immb_conv_desc* d, const float* dy_hi, const float* dy_l
   p.out_mul = d->stride; p.n_cols = ncols; p.n_store = ncols;
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
   int rc;
-  if ((rc = make_act_map(&a_hi, dy_hi, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, p.TW, p.TH, p.TN))) return rc;
-  if ((rc = make_w_map(&b_hi, wh_hi, d->kh * d->kw, d->cin_pad, d->y_cstride, bn))) return rc;
+  const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  if ((rc = make_act_map(&a_hi, dy_hi, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, p.TW, p.TH, p.TN, sw, esize))) return rc;
+  if ((rc = make_w_map(&b_hi, wh_hi, d->kh * d->kw, d->cin_pad, d->y_cstride, bn, esize))) return rc;
   a_lo = a_hi; b_lo = b_hi;
   if (passes == 3) {
-    if ((rc = make_act_map(&a_lo, dy_lo, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, p.TW, p.TH, p.TN))) return rc;
-    if ((rc = make_w_map(&b_lo, wh_lo, d->kh * d->kw, d->cin_pad, d->y_cstride, bn))) return rc;
+    if ((rc = make_act_map(&a_lo, dy_lo, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, p.TW, p.TH, p.TN, sw, esize))) return rc;
+    if ((rc = make_w_map(&b_lo, wh_lo, d->kh * d->kw, d->cin_pad, d->y_cstride, bn, esize))) return rc;
   }
   dim3 grid(p.tiles_w * p.tiles_h * ceil_div(d->N, p.TN), ceil_div(ncols, bn), classes);
-  return dispatch_fwd(bn, passes, a_hi, a_lo, b_hi, b_lo, p, grid, st);
+  return dispatch_fwd(bn, passes, a_hi, a_lo, b_hi, b_lo, p, grid, st, f16);
 }
 
 size_t conv_tc_wgrad_workspace(const immb_conv_desc*) { return 0; }
@@ -766,9 +867,11 @@ static int launch_wg(const CUtensorMap& x_hi, const CUtensorMap& x_lo, const CUt
   return check_launch("conv_tc_wgrad_kernel");
 }
 
-int conv_tc_wgrad(const immb_conv_desc* d, const float* x_hi, const float* x_lo, const float* dy_hi,
-                  const float* dy_lo, float* dw, void*, size_t, cudaStream_t st) {
-  if (conv_tc2_wgrad_eligible(d)) return conv_tc2_wgrad_run(d, x_hi, x_lo, dy_hi, dy_lo, dw, st);
+int conv_tc_wgrad(const immb_conv_desc* d, const void* x_hi_, const void* x_lo_, const void* dy_hi_,
+                  const void* dy_lo_, float* dw, void*, size_t, cudaStream_t st) {
+  if (conv_tc2_wgrad_eligible(d)) return conv_tc2_wgrad_run(d, x_hi_, x_lo_, dy_hi_, dy_lo_, dw, st);
+  if (is_f16(d)) return set_error(IMMB_ERR_UNSUPPORTED, "conv_tc_wgrad: fp16 planes are served by the halo wgrad kernel only");
+  const float *x_hi = (const float*)x_hi_, *x_lo = (const float*)x_lo_, *dy_hi = (const float*)dy_hi_, *dy_lo = (const float*)dy_lo_;
   const int passes = d->precision == IMMB_PREC_TF32 ? 1 : 3;
   WgParams p;
   memset(&p, 0, sizeof(p));

@@ -51,6 +51,12 @@ struct Tc2Params {
   const float* bnr_y;        // mode 2: that layer's raw conv output y [.., bnr_ycs] and its BN constants [n_cols]
   int bnr_ycs, bnr_relu;
   const float *bnr_scale, *bnr_shift, *bnr_mean, *bnr_invstd;
+  // scaled-fp16 operands (F16 kernels): scale records {e, amax bits} of the activation / weight operands and, when the
+  // output is written as H16 planes, of the output tensor; k-steps (of 32 bytes) to issue in the LAST K chunk
+  const int32_t* a_scale;
+  const int32_t* b_scale;
+  int32_t* o_scale;
+  int k_last;
 };
 
 template <int BN, int PASSES>
@@ -319,7 +325,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
 // empty / accumulator-full barriers are per CTA and receive the leader's multicast commits; the accumulator-empty
 // barrier lives in the leader and counts the 4 epilogue warps of BOTH CTAs.
 // =============================================================================================================
-template <int BN2, int PASSES>
+template <int BN2, int PASSES, bool F16 = false>
 struct Tc2PairCfg {
   static constexpr uint32_t NPLA = PASSES >= 2 ? 2 : 1;
   static constexpr uint32_t NPLB = PASSES == 3 ? 2 : 1;
@@ -347,20 +353,24 @@ struct Tc2PairCfg {
   // accumulator at every MMA, a biased error that grows linearly with the number of accumulating MMAs; keeping the
   // small terms out of the main accumulator leaves it with ONE truncating add per K-step, like a plain TF32 GEMM
   // (measured: all three products into one accumulator pushed the BN-beta gradients of config 1 from <1e-2 to 1.01e-2).
-  static constexpr int ACC_COLS = PASSES == 3 ? 2 * BN2 : BN2;
-  static_assert(2 * ACC_COLS <= 512, "two accumulator sets must fit the 512 TMEM columns (3-pass: BN2 <= 128)");
+  // F16: the lo planes carry an extra factor 2^11, so every product with a lo operand (also the single one of the
+  // 2-pass frozen-weight product) goes to the cross accumulator and is scaled by 2^-11 when the epilogue adds it.
+  static constexpr bool CROSS = PASSES == 3 || (F16 && PASSES == 2);
+  static constexpr int ACC_COLS = CROSS ? 2 * BN2 : BN2;
+  static_assert(2 * ACC_COLS <= 512, "two accumulator sets must fit the 512 TMEM columns (cross accumulator: BN2 <= 128)");
   static constexpr int TMEM_COLS = 2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512));
   static_assert(BN2 % 32 == 0 && BN2 <= 256, "pair N tile: multiple of 32 up to 256");
 };
 
 // BNR: the BN-backward-sums epilogue (stats_mode 2) is a separate instantiation so that its registers do not weigh on
 // the forward / plain-dgrad variants (a high register count squeezes the glue kernels that co-run on the side streams)
-template <int BN2, int PASSES, bool BNR>
+template <int BN2, int PASSES, bool BNR, bool F16>
 __global__ void __launch_bounds__(192, 1)
 conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
                      const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
                      const __grid_constant__ Tc2Params p) {
-  using Cfg = Tc2PairCfg<BN2, PASSES>;
+  using Cfg = Tc2PairCfg<BN2, PASSES, F16>;
+  constexpr int KC = F16 ? 64 : 32;                 // channels per 128-byte K chunk
   const uint32_t crank = cluster_ctarank();
   const bool leader = crank == 0;
   const int tile0 = (int)(blockIdx.x >> 1);
@@ -429,9 +439,9 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
         uint8_t* sa = a_base + as * Cfg::A_SLOT;
         if (elect_one()) {
           if (leader) mbar_expect_tx(&a_full[as], 2 * Cfg::NPLA * (uint32_t)p.a_plane_bytes);
-          tma_load_5d_pair(sa, &mapA_hi, &a_full[as], kc * 32, tw * 8 + p.box_dw, 0, th * 16 + p.box_dh, img);
+          tma_load_5d_pair(sa, &mapA_hi, &a_full[as], kc * KC, tw * 8 + p.box_dw, 0, th * 16 + p.box_dh, img);
           if (PASSES >= 2)
-            tma_load_5d_pair(sa + Cfg::A_PLANE, &mapA_lo, &a_full[as], kc * 32, tw * 8 + p.box_dw, 0, th * 16 + p.box_dh, img);
+            tma_load_5d_pair(sa + Cfg::A_PLANE, &mapA_lo, &a_full[as], kc * KC, tw * 8 + p.box_dw, 0, th * 16 + p.box_dh, img);
         }
         __syncwarp();
         ++ai;
@@ -441,8 +451,8 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
           uint8_t* sb = b_base + bs * Cfg::B_SLOT;
           if (elect_one()) {
             if (leader) mbar_expect_tx(&b_full[bs], 2 * Cfg::B_SLOT);
-            tma_load_3d_pair(sb, &mapB_hi, &b_full[bs], kc * 32, row0, p.taps[tap].b_tap);
-            if (PASSES == 3) tma_load_3d_pair(sb + Cfg::B_PLANE, &mapB_lo, &b_full[bs], kc * 32, row0, p.taps[tap].b_tap);
+            tma_load_3d_pair(sb, &mapB_hi, &b_full[bs], kc * KC, row0, p.taps[tap].b_tap);
+            if (PASSES == 3) tma_load_3d_pair(sb + Cfg::B_PLANE, &mapB_lo, &b_full[bs], kc * KC, row0, p.taps[tap].b_tap);
           }
           __syncwarp();
           ++bi;
@@ -452,7 +462,7 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
   } else if (warp == 1) {
     if (leader) {
       // ===== MMA issuer (leader CTA only): M = 256 across the pair, N = BN2 =====
-      constexpr uint32_t idesc = idesc_tf32(256, BN2, 0, 0);
+      constexpr uint32_t idesc = idesc_kind<F16>(256, BN2, 0, 0);
       uint32_t ai = 0, bi = 0, ti = 0;
       for (int t = tile0; t < n_iter_total; t += tstep) {
         const uint32_t acc = ti & 1, tph = (ti >> 1) & 1;
@@ -466,6 +476,7 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
           const uint32_t a_lo = a_hi + Cfg::A_PLANE;
           const int last_tap = p.n_taps - 1;
           const uint32_t sbo = (uint32_t)p.a_sbo;
+          const int nk = (kc == p.kchunks - 1) ? p.k_last : 4;       // 32-byte k-steps holding real channels
           for (int tap = 0; tap <= last_tap; ++tap) {
             const uint32_t bs = bi % Cfg::B_SLOTS, bph = (bi / Cfg::B_SLOTS) & 1;
             mbar_wait(&b_full[bs], bph);
@@ -476,19 +487,22 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
             if (elect_one()) {
 #pragma unroll
               for (int k4 = 0; k4 < 4; ++k4) {
-                const uint32_t ko = k4 * 32;
-                const uint64_t da_hi = smem_desc_sw128(a_hi + a_off + ko, 16, sbo, 2, 0);
-                const uint64_t db_hi = smem_desc_sw128(b_hi + ko, 16, 1024);
-                const uint32_t first = (kc > 0 || tap > 0 || k4 > 0) ? 1u : 0u;
-                mma_tf32_pair(tmem_d, da_hi, db_hi, idesc, first);
-                if (PASSES == 3) {
-                  const uint64_t db_lo = smem_desc_sw128(b_lo + ko, 16, 1024);
-                  const uint64_t da_lo = smem_desc_sw128(a_lo + a_off + ko, 16, sbo, 2, 0);
-                  mma_tf32_pair(tmem_d + BN2, da_hi, db_lo, idesc, first);      // cross terms: own accumulator
-                  mma_tf32_pair(tmem_d + BN2, da_lo, db_hi, idesc, 1u);
-                } else if (PASSES == 2) {
-                  const uint64_t da_lo = smem_desc_sw128(a_lo + a_off + ko, 16, sbo, 2, 0);
-                  mma_tf32_pair(tmem_d, da_lo, db_hi, idesc, 1u);
+                if (k4 < nk) {
+                  const uint32_t ko = k4 * 32;
+                  const uint64_t da_hi = smem_desc_sw128(a_hi + a_off + ko, 16, sbo, 2, 0);
+                  const uint64_t db_hi = smem_desc_sw128(b_hi + ko, 16, 1024);
+                  const uint32_t first = (kc > 0 || tap > 0 || k4 > 0) ? 1u : 0u;
+                  mma_kind_pair<F16>(tmem_d, da_hi, db_hi, idesc, first);
+                  if (PASSES == 3) {
+                    const uint64_t db_lo = smem_desc_sw128(b_lo + ko, 16, 1024);
+                    const uint64_t da_lo = smem_desc_sw128(a_lo + a_off + ko, 16, sbo, 2, 0);
+                    mma_kind_pair<F16>(tmem_d + BN2, da_hi, db_lo, idesc, first);      // cross terms: own accumulator
+                    mma_kind_pair<F16>(tmem_d + BN2, da_lo, db_hi, idesc, 1u);
+                  } else if (PASSES == 2) {
+                    const uint64_t da_lo = smem_desc_sw128(a_lo + a_off + ko, 16, sbo, 2, 0);
+                    if (F16) mma_kind_pair<F16>(tmem_d + BN2, da_lo, db_hi, idesc, first);   // lo carries 2^11: cross accumulator
+                    else mma_kind_pair<F16>(tmem_d, da_lo, db_hi, idesc, 1u);
+                  }
                 }
               }
               mma_commit_pair(&b_empty[bs], (uint16_t)3);
@@ -511,6 +525,16 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
     const bool vec8 = (p.ocs % 8 == 0) && (p.n_store % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.out_hi) & 31) == 0) &&
                       ((reinterpret_cast<uintptr_t>(p.out_lo) & 31) == 0);
     const bool do_stats = PASSES == 3 && p.stats != nullptr;
+    // F16: result = (main + cross * 2^-11) * 2^-(e_a + e_b); H16 output planes are written with the output tensor's 2^e_o
+    float s_main = 1.f, s_cross = 1.f, s_out = 1.f, amax = 0.f;
+    if (F16) {
+      const int e = __ldg(p.a_scale) + __ldg(p.b_scale);
+      s_main = exp2i(-e);
+      s_cross = exp2i(-e - 11);
+      if (p.out_lo) s_out = exp2i(__ldg(p.o_scale));
+    }
+    const bool vec16h = F16 && p.out_lo && (p.ocs % 16 == 0) && (p.n_store % 16 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.out_hi) & 31) == 0) && ((reinterpret_cast<uintptr_t>(p.out_lo) & 31) == 0);
     double* my_stats = stats_sm + (size_t)q * (2 * 2 * BN2);      // this warp's private rows: no cross-warp races
     float* bn_const = reinterpret_cast<float*>(stats_sm + 4 * 2 * 2 * BN2);     // [scale | shift | mean | invstd][256]
     if (do_stats) {
@@ -542,11 +566,14 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
         if (col0 >= p.n_cols) break;             // warp-uniform
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS + (uint32_t)c0, v);
-        if (PASSES == 3) {
+        if (Cfg::CROSS) {
           float v2[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS + (uint32_t)(BN2 + c0), v2);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += v2[j];
+          for (int j = 0; j < 32; ++j) v[j] = F16 ? fmaf(v2[j], s_cross, v[j] * s_main) : v[j] + v2[j];
+        } else if (F16) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= s_main;
         }
         if (!live) continue;
         if (p.bias) {
@@ -601,7 +628,22 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
-        if (p.relu_src) {
+        if (p.relu_src && F16) {
+          // hi plane (fp16) of the post-ReLU activation: positive <=> sign clear and magnitude non-zero
+          const uint16_t* a = reinterpret_cast<const uint16_t*>(p.relu_src) + pix * p.relu_cs + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (col0 + j >= p.n_store) break;
+            const uint4 t = __ldg(reinterpret_cast<const uint4*>(a + j));
+            const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const uint32_t h0 = w[u] & 0xFFFFu, h1 = w[u] >> 16;
+              v[j + 2 * u] = (h0 != 0u && h0 < 0x8000u) ? v[j + 2 * u] : 0.f;
+              v[j + 2 * u + 1] = (h1 != 0u && h1 < 0x8000u) ? v[j + 2 * u + 1] : 0.f;
+            }
+          }
+        } else if (p.relu_src) {
           const float* a = p.relu_src + pix * p.relu_cs + col0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -612,6 +654,37 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
             v[j + 2] = t.z > 0.f ? v[j + 2] : 0.f;
             v[j + 3] = t.w > 0.f ? v[j + 3] : 0.f;
           }
+        }
+        if (F16 && p.out_lo) {
+          // H16 output planes: 16 channels = one 32-byte sector per plane per store
+          uint16_t* oh = reinterpret_cast<uint16_t*>(p.out_hi) + pix * p.ocs + col0;
+          uint16_t* ol = reinterpret_cast<uint16_t*>(p.out_lo) + pix * p.ocs + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 16) {
+            if (col0 + j >= p.n_store) break;
+            uint32_t hw[8], lw[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              uint16_t h0, l0, h1, l1;
+              amax = fmaxf(amax, fmaxf(fabsf(v[j + 2 * u]), fabsf(v[j + 2 * u + 1])));
+              split_h16(v[j + 2 * u] * s_out, h0, l0);
+              split_h16(v[j + 2 * u + 1] * s_out, h1, l1);
+              hw[u] = pack2(h0, h1);
+              lw[u] = pack2(l0, l1);
+            }
+            if (vec16h) {
+              st_global_v8u(oh + j, hw[0], hw[1], hw[2], hw[3], hw[4], hw[5], hw[6], hw[7]);
+              st_global_v8u(ol + j, lw[0], lw[1], lw[2], lw[3], lw[4], lw[5], lw[6], lw[7]);
+            } else {
+              *reinterpret_cast<uint4*>(oh + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              *reinterpret_cast<uint4*>(ol + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+              if (col0 + j + 8 < p.n_store) {
+                *reinterpret_cast<uint4*>(oh + j + 8) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+                *reinterpret_cast<uint4*>(ol + j + 8) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+              }
+            }
+          }
+          continue;
         }
         float* o = p.out_hi + pix * p.ocs + col0;
         if (vec8) {
@@ -660,6 +733,10 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
       if (lane == 0) mbar_arrive_leader(&t_empty[acc]);
       ++ti;
     }
+    if (F16 && p.out_lo) {
+      __syncwarp();
+      h16_track_amax(p.o_scale, amax);
+    }
     if (do_stats) {
       // one partial row per (CTA, epilogue warp): [sum over n_cols | sum of squares over n_cols]; summed in a fixed
       // order by the second level (immb_bn_stats_from_partials): deterministic, no atomics
@@ -685,9 +762,11 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
 }
 
 // ---- host ---------------------------------------------------------------------------------------------------
-int tc_make_act_map(CUtensorMap* m, const float* base, int N, int H, int W, int C, int cs, bool parity_split,
-                    int box_w, int box_h, int box_n, int swizzle_mn);
-int tc_make_w_map(CUtensorMap* m, const float* base, int taps, int Nn, int Kd, int bn);
+// esize: bytes per element of the planes (4 = TF32 pairs in fp32 storage, 2 = scaled fp16); the box is always 128 bytes
+// of channels wide (32 fp32 / 64 fp16 elements)
+int tc_make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int cs, bool parity_split,
+                    int box_w, int box_h, int box_n, int swizzle_mn, int esize = 4);
+int tc_make_w_map(CUtensorMap* m, const void* base, int taps, int Nn, int Kd, int bn, int esize = 4);
 int tc_pick_bn(int ncols);
 
 bool conv_tc2_enabled() {
@@ -775,8 +854,8 @@ int conv_tc2_pair_mode() {
 // N tile of the pair kernel: as few N tiles as possible (one activation halo then serves up to 256 output channels;
 // 128 for the 3-pass product, whose cross-term accumulator doubles the TMEM columns), each the smallest instantiated
 // width that covers its share (288 columns -> 3 x 96 for 3 passes, 2 x 160 otherwise)
-static int pair_bn(int ncols, int passes) {
-  const int cap = passes == 3 ? 128 : 256;
+static int pair_bn(int ncols, int passes, bool f16 = false) {
+  const int cap = (passes == 3 || (f16 && passes == 2)) ? 128 : 256;      // a cross accumulator doubles the TMEM columns
   const int nt = ceil_div(ncols, cap);
   const int need = ceil_div(ncols, nt);
   static const int kWidths[] = {32, 64, 96, 128, 160, 192, 256};
@@ -785,17 +864,19 @@ static int pair_bn(int ncols, int passes) {
   return cap;
 }
 
-template <int BN2, int PASSES, bool BNR = false>
+template <int BN2, int PASSES, bool BNR = false, bool F16 = false>
 static int launch_tc2_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                            const CUtensorMap& b_lo, const Tc2Params& p, cudaStream_t st) {
-  if constexpr (PASSES == 3 && BN2 > 128) {
-    return set_error(IMMB_ERR_INVALID, "conv_tc2 pair: 3-pass N tile %d > 128", BN2);
+  if constexpr ((PASSES == 3 || (F16 && PASSES == 2)) && BN2 > 128) {
+    return set_error(IMMB_ERR_INVALID, "conv_tc2 pair: N tile %d > 128 with a cross accumulator", BN2);
   } else if constexpr (BNR && PASSES != 3) {
     return set_error(IMMB_ERR_INVALID, "conv_tc2 pair: the BN-backward epilogue exists for the 3-pass product only");
+  } else if constexpr (F16 && PASSES == 1) {
+    return set_error(IMMB_ERR_INVALID, "conv_tc2 pair: single-pass fp16 is not built");
   } else {
-  if (!BNR && p.stats_mode == 2) return launch_tc2_pair<BN2, PASSES, true>(a_hi, a_lo, b_hi, b_lo, p, st);
-  using Cfg = Tc2PairCfg<BN2, PASSES>;
-  auto kern = conv_tc2_pair_kernel<BN2, PASSES, BNR>;
+  if (!BNR && p.stats_mode == 2) return launch_tc2_pair<BN2, PASSES, true, F16>(a_hi, a_lo, b_hi, b_lo, p, st);
+  using Cfg = Tc2PairCfg<BN2, PASSES, F16>;
+  auto kern = conv_tc2_pair_kernel<BN2, PASSES, BNR, F16>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
@@ -823,18 +904,31 @@ static int launch_tc2_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, con
   }
 }
 
+static inline bool prec_is_f16(int precision) { return precision == IMMB_PREC_F16X3 || precision == IMMB_PREC_F16X2; }
+static inline int prec_passes(int precision) {
+  return precision == IMMB_PREC_TF32 ? 1 : ((precision == IMMB_PREC_TF32X2 || precision == IMMB_PREC_F16X2) ? 2 : 3);
+}
+
 // act: the tensor the halo boxes are read from ([N,H,W,act_cs], act_c valid channels); wts: [9][ncols_pad][kd]
-int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const float* act_lo, int act_c, int act_cs,
-                 const float* w_hi, const float* w_lo, int w_rows, int kd, const float* bias, int relu,
-                 float* out_hi, float* out_lo, int ocs, int ncols, int n_store, cudaStream_t st,
-                 const float* relu_src, int relu_cs, double* stats, const Tc2BnReduce* bnr) {
-  const int passes = d->precision == IMMB_PREC_TF32 ? 1 : (d->precision == IMMB_PREC_TF32X2 ? 2 : 3);
+// F16 precisions: planes are scaled fp16 (common.cuh); `sc` = scale records of act / weights / output planes
+int conv_tc2_run(const immb_conv_desc* d, int op, const void* act_hi, const void* act_lo, int act_c, int act_cs,
+                 const void* w_hi, const void* w_lo, int w_rows, int kd, const float* bias, int relu,
+                 void* out_hi, void* out_lo, int ocs, int ncols, int n_store, cudaStream_t st,
+                 const void* relu_src, int relu_cs, double* stats, const Tc2BnReduce* bnr, const Tc2Scales* sc) {
+  const int passes = prec_passes(d->precision);
+  const bool f16 = prec_is_f16(d->precision);
+  const int esize = f16 ? 2 : 4, kchunk = f16 ? 64 : 32;
   Tc2Params p;
   memset(&p, 0, sizeof(p));
   p.tiles_w = d->W / 8; p.tiles_h = d->H / 16; p.n_img = d->N;
   const int pmode = conv_tc2_pair_mode();
   const bool pair = pmode > 0 && ncols >= (pmode > 1 ? pmode : 1);
-  const int bn = pair ? pair_bn(ncols, passes) : tc_pick_bn(ncols);
+  if (f16 && !pair) return set_error(IMMB_ERR_UNSUPPORTED, "conv_tc2: the fp16 product needs the pair kernel");
+  if (f16 && (!sc || !sc->a || !sc->b || (out_lo && !sc->o)))
+    return set_error(IMMB_ERR_INVALID, "conv_tc2: fp16 planes need their scale records");
+  if (f16 && (act_cs % 8 || (out_lo && (ocs % 8 || n_store % 8))))
+    return set_error(IMMB_ERR_UNSUPPORTED, "conv_tc2: fp16 planes need channel strides that are multiples of 8");
+  const int bn = pair ? pair_bn(ncols, passes, f16) : tc_pick_bn(ncols);
   p.n_tiles_n = ceil_div(ncols, bn);
   p.total_tiles = p.tiles_w * p.tiles_h * p.n_img * p.n_tiles_n;
   p.m_tiles = p.tiles_w * p.tiles_h * p.n_img;
@@ -843,7 +937,9 @@ int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const flo
   const int cmode = conv_tc2_cluster_mode();
   const bool cluster = !pair && cmode > 0 && bn >= 32 && (bn % 32 == 0 || bn == 96) && (cmode == 2 ? bn >= 32 : bn >= 64) &&
                        (cmode == 2 || p.m_tiles >= 2 * kNumSMs);
-  p.kchunks = ceil_div(kd, 32);
+  p.kchunks = ceil_div(kd, kchunk);
+  // k-steps (32 bytes: 8 tf32 / 16 fp16 channels) of the last chunk that hold real (or zero-padded) weights
+  p.k_last = f16 ? ceil_div(kd - (p.kchunks - 1) * kchunk, 16) : 4;
   for (int r = 0; r < 3; ++r)
     for (int s = 0; s < 3; ++s) {
       Tc2Tap& t = p.taps[r * 3 + s];
@@ -857,9 +953,10 @@ int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const flo
   const int box_w = pair ? 10 : 16;        // (a 16-pixel box for the pair kernel measured 0.6 % slower and needs 60 % more smem)
   p.n_taps = 9; p.a_sbo = box_w * 128; p.a_plane_bytes = 18 * box_w * 128; p.box_dw = -1; p.box_dh = -1;
   for (int i = 0; i < 9; ++i) p.a_off[i] = (uint32_t)(p.taps[i].ro * box_w + p.taps[i].so) * 128u;
-  p.out_hi = out_hi; p.out_lo = out_lo; p.bias = bias; p.relu = relu;
+  p.out_hi = reinterpret_cast<float*>(out_hi); p.out_lo = reinterpret_cast<float*>(out_lo); p.bias = bias; p.relu = relu;
   p.H = d->H; p.W = d->W; p.ocs = ocs; p.n_cols = ncols; p.n_store = n_store;
-  p.relu_src = relu_src; p.relu_cs = relu_cs; p.stats = stats; p.stats_mode = stats ? 1 : 0;
+  p.relu_src = reinterpret_cast<const float*>(relu_src); p.relu_cs = relu_cs; p.stats = stats; p.stats_mode = stats ? 1 : 0;
+  if (sc) { p.a_scale = sc->a; p.b_scale = sc->b; p.o_scale = sc->o; }
   if (bnr) {
     if (!stats || ncols % 32 || ncols > 256)
       return set_error(IMMB_ERR_UNSUPPORTED, "conv_tc2: fused BN-backward sums need a partials buffer and 32 | channels <= 256");
@@ -873,15 +970,27 @@ int conv_tc2_run(const immb_conv_desc* d, int op, const float* act_hi, const flo
   { const char* e = getenv("IMMB_TC2_BO"); p.bo_mode = e ? atoi(e) : 0; }
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
   int rc;
-  if ((rc = tc_make_act_map(&a_hi, act_hi, d->N, d->H, d->W, act_c, act_cs, false, box_w, 18, 1, 0))) return rc;
+  if ((rc = tc_make_act_map(&a_hi, act_hi, d->N, d->H, d->W, act_c, act_cs, false, box_w, 18, 1, 0, esize))) return rc;
   const int b_box = (cluster || pair) ? bn / 2 : bn;  // cluster / pair mode: each CTA loads half of the rows
-  if ((rc = tc_make_w_map(&b_hi, w_hi, 9, w_rows, kd, b_box))) return rc;
+  if ((rc = tc_make_w_map(&b_hi, w_hi, 9, w_rows, kd, b_box, esize))) return rc;
   a_lo = a_hi; b_lo = b_hi;
   if (passes >= 2) {
-    if ((rc = tc_make_act_map(&a_lo, act_lo, d->N, d->H, d->W, act_c, act_cs, false, box_w, 18, 1, 0))) return rc;
+    if ((rc = tc_make_act_map(&a_lo, act_lo, d->N, d->H, d->W, act_c, act_cs, false, box_w, 18, 1, 0, esize))) return rc;
   }
   if (passes == 3) {
-    if ((rc = tc_make_w_map(&b_lo, w_lo, 9, w_rows, kd, b_box))) return rc;
+    if ((rc = tc_make_w_map(&b_lo, w_lo, 9, w_rows, kd, b_box, esize))) return rc;
+  }
+  if (pair && f16) {
+#define IMMB_PCASE(BN_)                                                                        \
+  if (bn == BN_)                                                                               \
+    return passes == 3 ? launch_tc2_pair<BN_, 3, false, true>(a_hi, a_lo, b_hi, b_lo, p, st)   \
+                       : launch_tc2_pair<BN_, 2, false, true>(a_hi, a_lo, b_hi, b_lo, p, st);
+    IMMB_PCASE(32)
+    IMMB_PCASE(64)
+    IMMB_PCASE(96)
+    IMMB_PCASE(128)
+#undef IMMB_PCASE
+    return set_error(IMMB_ERR_INVALID, "conv_tc2 pair (fp16): unsupported BN %d", bn);
   }
   if (pair) {
 #define IMMB_PCASE(BN_)                                                                  \
@@ -933,7 +1042,8 @@ bool conv_tc2_rowwin_eligible(const immb_conv_desc* d) {
 int conv_tc2_fwd_stats_rows(const immb_conv_desc* d) {
   const bool rowwin = conv_tc2_rowwin_eligible(d);
   if (!rowwin && !(conv_tc2_eligible(d, 0) && conv_tc2_pair_mode() == 1)) return 0;
-  if (d->precision != IMMB_PREC_TF32X3) return 0;
+  if (d->precision != IMMB_PREC_TF32X3 && d->precision != IMMB_PREC_F16X3) return 0;
+  if (rowwin && d->precision != IMMB_PREC_TF32X3) return 0;
   const int m_tiles = (d->W / 8) * (d->H / 16) * d->N;
   const int bn = pair_bn(d->Cout, 3);
   const int n_tiles_n = ceil_div(d->Cout, bn);
@@ -945,7 +1055,8 @@ int conv_tc2_fwd_stats_rows(const immb_conv_desc* d) {
 
 // rows of BN-backward partials the pair kernel writes for this dgrad (4 per CTA), 0 = not served
 int conv_tc2_dgrad_stats_rows(const immb_conv_desc* d) {
-  if (!(conv_tc2_eligible(d, 1) && conv_tc2_pair_mode() == 1) || d->precision != IMMB_PREC_TF32X3) return 0;
+  if (!(conv_tc2_eligible(d, 1) && conv_tc2_pair_mode() == 1) ||
+      (d->precision != IMMB_PREC_TF32X3 && d->precision != IMMB_PREC_F16X3)) return 0;
   const int ncols = d->cin_pad < d->x_cstride ? d->cin_pad : d->x_cstride;
   if (ncols != d->Cin || ncols % 32 || ncols > 256) return 0;
   const int m_tiles = (d->W / 8) * (d->H / 16) * d->N;
@@ -969,7 +1080,7 @@ int conv_tc2_rowwin_fwd(const immb_conv_desc* d, const float* x_hi, const float*
   p.m_tiles = p.tiles_w * p.tiles_h * p.n_img;
   p.total_tiles = p.m_tiles * p.n_tiles_n;
   p.total_pairs = ceil_div(p.m_tiles, 2) * p.n_tiles_n;
-  p.kchunks = 1;
+  p.kchunks = 1; p.k_last = 4;
   p.n_taps = 7; p.a_sbo = 1024; p.a_plane_bytes = 22 * 8 * 128; p.box_dw = 0; p.box_dh = -3;
   for (int r = 0; r < 7; ++r) { p.taps[r].b_tap = r; p.a_off[r] = (uint32_t)r * 1024u; }
   p.out_hi = y_hi; p.out_lo = y_lo; p.bias = bias; p.relu = relu;
@@ -1171,6 +1282,225 @@ if ((p.Cout & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dw) & 15) == 0) {
   }
 }
 
+// =============================================================================================================
+// Halo wgrad on scaled fp16 planes (kind::f16, both operands MN-major, standard 128-byte swizzle).
+//   dW[r][s][ci][co] = sum_pixels X[h+r-1, w+s-1][ci] * dY[h, w][co]
+// One CTA owns ONE filter row r, a 64-input-channel chunk (one 128-byte smem row = 64 fp16 channels), BN output
+// channels and a range of 4x8-pixel tiles (split-K).  Per stage it fetches the 4 x 16-pixel window of X rows
+// h + r - 1 (8 KB / plane) and the 4 x 8-pixel dY boxes (4 KB per 64 channels / plane).  One MMA has M = 128 = two
+// column taps x 64 channels -- the two MN atoms of the A descriptor are the SAME window rows one pixel apart
+// (LBO = 128 B) -- and K = 16 = the 8 pixels of two consecutive image rows (two K atoms, SBO = the 2048-byte row
+// pitch of the window / the 1024-byte row pitch of a dY box).  Taps s = 0,1 share one MMA, tap s = 2 takes a second
+// one whose upper MN atom is ignored.  The lo planes carry 2^11 (common.cuh), so hi*hi accumulates in "main" columns
+// and hi*lo + lo*hi in "cross" columns: four accumulators of BN columns ([s01 | s2] x [main | cross]).
+// Grid: (64-channel chunks, BN tiles, 3 * splits).  Epilogue: (main + cross * 2^-11) * 2^-(e_x + e_dy), vector red.
+// =============================================================================================================
+struct Wg16Params {
+  int tiles_w, tiles_h, n_img, total_tiles, tiles_per_split, splits;
+  float* dw;
+  int Cin, Cout;
+  const int32_t* x_scale;
+  const int32_t* dy_scale;
+};
+
+template <int BN, int STAGES>
+struct Wg16Cfg {
+  static constexpr uint32_t A_PLANE = 4 * 16 * 128;                       // 8192 B window
+  static constexpr uint32_t NB = (BN + 63) / 64;                          // dY boxes of 64 channels
+  static constexpr uint32_t B_PLANE = NB * 4096;
+  static constexpr uint32_t STAGE_BYTES = (A_PLANE + B_PLANE) * 2;        // hi + lo planes of both operands
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = 4 * BN <= 64 ? 64 : (4 * BN <= 128 ? 128 : (4 * BN <= 256 ? 256 : 512));
+  static_assert(4 * BN <= 512, "four accumulators of BN columns");
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv_tc2_wgrad16_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_constant__ CUtensorMap mapX_lo,
+                        const __grid_constant__ CUtensorMap mapY_hi, const __grid_constant__ CUtensorMap mapY_lo,
+                        const __grid_constant__ Wg16Params p) {
+  using Cfg = Wg16Cfg<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const int ci0 = blockIdx.x * 64;
+  const int n_off = blockIdx.y * BN;
+  const int r = blockIdx.z / p.splits;                 // filter row of this CTA
+  const int split = blockIdx.z - r * p.splits;
+  const int t_begin = split * p.tiles_per_split;
+  int t_end = t_begin + p.tiles_per_split;
+  if (t_end > p.total_tiles) t_end = p.total_tiles;
+  const int num_k = t_end - t_begin;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    for (int kt = 0; kt < num_k; ++kt) {
+      const int s = kt % STAGES;
+      const uint32_t ph = (kt / STAGES) & 1;
+      mbar_wait(&empty[s], ph ^ 1);
+      const int tile = t_begin + kt;
+      const int twi = tile % p.tiles_w;
+      const int thi = (tile / p.tiles_w) % p.tiles_h;
+      const int n = tile / (p.tiles_w * p.tiles_h);
+      uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+      if (elect_one()) {
+        mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+        tma_load_5d(st, &mapX_hi, &full[s], ci0, twi * 8 - 1, 0, thi * 4 + r - 1, n);
+        tma_load_5d(st + Cfg::A_PLANE, &mapX_lo, &full[s], ci0, twi * 8 - 1, 0, thi * 4 + r - 1, n);
+        uint8_t* sb = st + Cfg::A_PLANE * 2;
+#pragma unroll
+        for (uint32_t j = 0; j < Cfg::NB; ++j) {
+          tma_load_5d(sb + j * 4096, &mapY_hi, &full[s], n_off + (int)j * 64, twi * 8, 0, thi * 4, n);
+          tma_load_5d(sb + Cfg::B_PLANE + j * 4096, &mapY_lo, &full[s], n_off + (int)j * 64, twi * 8, 0, thi * 4, n);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    if (num_k > 0) {
+      constexpr uint32_t idesc = idesc_f16(128, BN, 1, 1);
+      for (int kt = 0; kt < num_k; ++kt) {
+        const int s = kt % STAGES;
+        const uint32_t ph = (kt / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint32_t a_lo = a_hi + Cfg::A_PLANE;
+        const uint32_t b_hi = a_hi + Cfg::A_PLANE * 2;
+        const uint32_t b_lo = b_hi + Cfg::B_PLANE;
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {                                   // image rows 2j, 2j+1 of the tile = K 16
+            const uint32_t acc = (kt > 0 || j > 0) ? 1u : 0u;
+            const uint64_t db_hi = smem_desc_sw128(b_hi + (uint32_t)j * 2048u, 4096, 1024, 2);
+            const uint64_t db_lo = smem_desc_sw128(b_lo + (uint32_t)j * 2048u, 4096, 1024, 2);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {                                 // g = 0: taps s = 0,1;  g = 1: tap s = 2 (+ ignored)
+              const uint32_t ao = ((uint32_t)(2 * j) * 16u + (uint32_t)(2 * g)) * 128u;
+              const uint64_t da_hi = smem_desc_sw128(a_hi + ao, 128, 2048, 2);
+              const uint64_t da_lo = smem_desc_sw128(a_lo + ao, 128, 2048, 2);
+              const uint32_t d_main = tmem_base + (uint32_t)(g * 2 * BN);
+              const uint32_t d_cross = d_main + (uint32_t)BN;
+              mma_f16(d_main, da_hi, db_hi, idesc, acc);
+              mma_f16(d_cross, da_hi, db_lo, idesc, acc);
+              mma_f16(d_cross, da_lo, db_hi, idesc, 1u);
+            }
+          }
+          mma_commit(&empty[s]);
+          if (kt == num_k - 1) mma_commit(tmem_full);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (num_k > 0) {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int g_row = m >> 6;                  // MN atom of this TMEM lane: column tap s = 2*g + g_row
+    const int ci = ci0 + (m & 63);
+    const int e = __ldg(p.x_scale) + __ldg(p.dy_scale);
+    const float s_main = exp2i(-e), s_cross = exp2i(-e - 11);
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int g = 0; g < 2; ++g) {
+      const int s_tap = 2 * g + g_row;
+      const bool row_ok = (s_tap < 3) && (ci < p.Cin);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32], v2[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 2 * BN + c0), v);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 2 * BN + BN + c0), v2);
+        if (!row_ok) continue;
+        const int col0 = n_off + c0;
+        if (col0 >= p.Cout) continue;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(v2[j], s_cross, v[j] * s_main);
+        float* o = p.dw + ((size_t)(r * 3 + s_tap) * p.Cin + ci) * p.Cout + col0;
+        if ((p.Cout & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dw) & 15) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (col0 + j < p.Cout) red_add_v4(o + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.Cout) atomicAdd(o + j, v[j]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN>
+static int launch_wg16(const CUtensorMap& x_hi, const CUtensorMap& x_lo, const CUtensorMap& y_hi,
+                       const CUtensorMap& y_lo, const Wg16Params& p, dim3 grid, cudaStream_t st) {
+  constexpr int STAGES = BN <= 64 ? 6 : 5;
+  using Cfg = Wg16Cfg<BN, STAGES>;
+  auto kern = conv_tc2_wgrad16_kernel<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "conv_tc2_wgrad16 smem attr: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  kern<<<grid, 192, Cfg::SMEM_BYTES, st>>>(x_hi, x_lo, y_hi, y_lo, p);
+  return check_launch("conv_tc2_wgrad16_kernel");
+}
+
+static int conv_tc2_wgrad16_run(const immb_conv_desc* d, const void* x_hi, const void* x_lo, const void* dy_hi,
+                                const void* dy_lo, float* dw, cudaStream_t st) {
+  if (!d->x_scale || !d->y_scale) return set_error(IMMB_ERR_INVALID, "conv_tc2_wgrad: fp16 planes need x_scale / y_scale");
+  if (d->x_cstride % 8 || d->y_cstride % 8)
+    return set_error(IMMB_ERR_UNSUPPORTED, "conv_tc2_wgrad: fp16 planes need channel strides that are multiples of 8");
+  Wg16Params p;
+  memset(&p, 0, sizeof(p));
+  p.tiles_w = d->W / 8; p.tiles_h = d->H / 4; p.n_img = d->N;
+  p.total_tiles = p.tiles_w * p.tiles_h * d->N;
+  p.dw = dw; p.Cin = d->Cin; p.Cout = d->Cout;
+  p.x_scale = d->x_scale; p.dy_scale = d->y_scale;
+  const int bn = d->Cout > 64 ? 128 : (d->Cout > 32 ? 64 : 32);      // (narrower tiles would read past their TMEM columns)
+  const int n_tiles = ceil_div(d->Cout, bn);
+  const int c_tiles = ceil_div(d->Cin, 64);
+  int splits = kNumSMs / (c_tiles * n_tiles * 3);
+  if (splits > p.total_tiles) splits = p.total_tiles;
+  if (splits < 1) splits = 1;
+  p.tiles_per_split = ceil_div(p.total_tiles, splits);
+  splits = ceil_div(p.total_tiles, p.tiles_per_split);
+  p.splits = splits;
+  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)9 * d->Cin * d->Cout, st);
+  if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "wgrad memset: %s", cudaGetErrorString(e));
+  CUtensorMap mx_hi, mx_lo, my_hi, my_lo;
+  int rc;
+  if ((rc = tc_make_act_map(&mx_hi, x_hi, d->N, d->H, d->W, d->Cin, d->x_cstride, false, 16, 4, 1, 1, 2))) return rc;
+  if ((rc = tc_make_act_map(&mx_lo, x_lo, d->N, d->H, d->W, d->Cin, d->x_cstride, false, 16, 4, 1, 1, 2))) return rc;
+  if ((rc = tc_make_act_map(&my_hi, dy_hi, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, 8, 4, 1, 1, 2))) return rc;
+  if ((rc = tc_make_act_map(&my_lo, dy_lo, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, 8, 4, 1, 1, 2))) return rc;
+  dim3 grid(c_tiles, n_tiles, 3 * splits);
+  if (bn == 128) return launch_wg16<128>(mx_hi, mx_lo, my_hi, my_lo, p, grid, st);
+  if (bn == 64) return launch_wg16<64>(mx_hi, mx_lo, my_hi, my_lo, p, grid, st);
+  return launch_wg16<32>(mx_hi, mx_lo, my_hi, my_lo, p, grid, st);
+}
+
 bool conv_tc2_wgrad_eligible(const immb_conv_desc* d) {
   if (!conv_tc2_enabled()) return false;
   if (d->x_layout != IMMB_XLAYOUT_NHWC || d->kh != 3 || d->kw != 3 || d->stride != 1) return false;
@@ -1194,8 +1524,10 @@ static int launch_wg2(const CUtensorMap& x_hi, const CUtensorMap& x_lo, const CU
   return check_launch("conv_tc2_wgrad_kernel");
 }
 
-int conv_tc2_wgrad_run(const immb_conv_desc* d, const float* x_hi, const float* x_lo, const float* dy_hi,
-                       const float* dy_lo, float* dw, cudaStream_t st) {
+int conv_tc2_wgrad_run(const immb_conv_desc* d, const void* x_hi_, const void* x_lo_, const void* dy_hi_,
+                       const void* dy_lo_, float* dw, cudaStream_t st) {
+  if (prec_is_f16(d->precision)) return conv_tc2_wgrad16_run(d, x_hi_, x_lo_, dy_hi_, dy_lo_, dw, st);
+  const float *x_hi = (const float*)x_hi_, *x_lo = (const float*)x_lo_, *dy_hi = (const float*)dy_hi_, *dy_lo = (const float*)dy_lo_;
   const int passes = d->precision == IMMB_PREC_TF32 ? 1 : 3;
   Wg2Params p;
   memset(&p, 0, sizeof(p));

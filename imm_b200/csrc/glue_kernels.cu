@@ -209,13 +209,6 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ g, int gcs, const 
   });
 }
 
-__global__ void bias_grad_kernel(const float* __restrict__ g_hi, const float* __restrict__ g_lo, int gcs,
-                                 int64_t npix, int C, double* acc) {
-  channel_reduce<1>(npix, C, acc, C, [&](int64_t p, int c, float* v) {
-    v[0] = load_split(g_hi, g_lo, (size_t)(p * gcs + c));
-  });
-}
-
 __global__ void cast_d2f_kernel(const double* s, float* d, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) d[i] = (float)s[i];
@@ -253,6 +246,76 @@ __device__ __forceinline__ float4 load_split4(const float* hi_p, const float* lo
     v.x += l.x; v.y += l.y; v.z += l.z; v.w += l.w;
   }
   return v;
+}
+
+// -----------------------------------------------------------------------------------------------------
+// Split-plane accessors.  Every kernel that reads or writes conv operands is a template on the plane format:
+//   Pl<false>: fp32 storage, TF32 pair (hi, lo); lo == nullptr means a plain fp32 tensor in `hi`;
+//   Pl<true> : scaled fp16 pair ("H16 planes", common.cuh) with the tensor's scale record {e, amax bits}.
+// load*: the real value (planes joined, scale removed).  store*: split + write, tracking max |v| in `amax`, which the
+// kernel hands to finish() once, at its end, with whole warps converged.
+// -----------------------------------------------------------------------------------------------------
+template <bool H16>
+struct Pl;
+template <>
+struct Pl<false> {
+  float* hi;
+  float* lo;
+  __device__ __forceinline__ void init() {}
+  __device__ __forceinline__ float load(size_t i) const { return load_split(hi, lo, i); }
+  __device__ __forceinline__ float4 load4(size_t i) const { return load_split4(hi, lo, i); }
+  __device__ __forceinline__ void store(size_t i, float v, float&) const { store_split(hi, lo, i, v); }
+  __device__ __forceinline__ void store4(size_t i, float4 v, float&) const { store_split4(hi, lo, i, v); }
+  __device__ __forceinline__ void finish(float) const {}
+};
+template <>
+struct Pl<true> {
+  uint16_t* hi;
+  uint16_t* lo;
+  int32_t* rec;
+  float mul, inv;
+  __device__ __forceinline__ void init() {
+    const int e = __ldg(rec);
+    mul = exp2i(e);
+    inv = exp2i(-e);
+  }
+  __device__ __forceinline__ float load(size_t i) const { return join_h16(__ldg(hi + i), __ldg(lo + i)) * inv; }
+  __device__ __forceinline__ float4 load4(size_t i) const {
+    const uint2 h = __ldg(reinterpret_cast<const uint2*>(hi + i)), l = __ldg(reinterpret_cast<const uint2*>(lo + i));
+    return make_float4(join_h16((uint16_t)(h.x & 0xFFFFu), (uint16_t)(l.x & 0xFFFFu)) * inv,
+                       join_h16((uint16_t)(h.x >> 16), (uint16_t)(l.x >> 16)) * inv,
+                       join_h16((uint16_t)(h.y & 0xFFFFu), (uint16_t)(l.y & 0xFFFFu)) * inv,
+                       join_h16((uint16_t)(h.y >> 16), (uint16_t)(l.y >> 16)) * inv);
+  }
+  __device__ __forceinline__ void store(size_t i, float v, float& amax) const {
+    uint16_t h, l;
+    amax = fmaxf(amax, fabsf(v));
+    split_h16(v * mul, h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+  __device__ __forceinline__ void store4(size_t i, float4 v, float& amax) const {
+    uint16_t h0, l0, h1, l1, h2, l2, h3, l3;
+    amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    split_h16(v.x * mul, h0, l0);
+    split_h16(v.y * mul, h1, l1);
+    split_h16(v.z * mul, h2, l2);
+    split_h16(v.w * mul, h3, l3);
+    *reinterpret_cast<uint2*>(hi + i) = make_uint2(pack2(h0, h1), pack2(h2, h3));
+    *reinterpret_cast<uint2*>(lo + i) = make_uint2(pack2(l0, l1), pack2(l2, l3));
+  }
+  __device__ __forceinline__ void finish(float amax) const { h16_track_amax(rec, amax); }
+};
+template <bool H16>
+static inline Pl<H16> make_pl(const void* hi, const void* lo, const int32_t* rec);
+template <>
+inline Pl<false> make_pl<false>(const void* hi, const void* lo, const int32_t*) {
+  return Pl<false>{const_cast<float*>(static_cast<const float*>(hi)), const_cast<float*>(static_cast<const float*>(lo))};
+}
+template <>
+inline Pl<true> make_pl<true>(const void* hi, const void* lo, const int32_t* rec) {
+  return Pl<true>{const_cast<uint16_t*>(static_cast<const uint16_t*>(hi)), const_cast<uint16_t*>(static_cast<const uint16_t*>(lo)),
+                  const_cast<int32_t*>(rec), 1.f, 1.f};
 }
 
 // pixels per block: adaptive (vred_pix): enough blocks to fill the GPU, enough work per block to amortise the
@@ -333,25 +396,32 @@ __device__ __forceinline__ float4 bn_act4(float4 y, float4 sc, float4 sh, int re
                      bn_act(y.w, sc.w, sh.w, relu));
 }
 
+template <bool H16>
 __global__ void bn_apply4_kernel(const float* __restrict__ y, int64_t npix, int C, int ycs,
                                  const float* __restrict__ scale, const float* __restrict__ shift, int relu,
-                                 float* out_hi, float* out_lo, int ocs) {
+                                 Pl<H16> out, int ocs) {
   const int q = C >> 2;
   int64_t total = npix * q;
+  out.init();
+  float amax = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     int64_t p = i / q;
     int c = (int)(i - p * q) * 4;
     float4 v = bn_act4(ld4(y + p * ycs + c), ld4(scale + c), ld4(shift + c), relu);
-    store_split4(out_hi, out_lo, (size_t)(p * ocs + c), v);
+    out.store4((size_t)(p * ocs + c), v, amax);
   }
+  out.finish(amax);
 }
 
+template <bool H16>
 __global__ void bn_apply_up2x4_kernel(const float* __restrict__ y, int N, int H, int W, int C, int ycs,
                                       const float* __restrict__ scale, const float* __restrict__ shift,
-                                      int relu, float* out_hi, float* out_lo, int ocs) {
+                                      int relu, Pl<H16> out, int ocs) {
   const int Ho = 2 * H, Wo = 2 * W, q = C >> 2;
   int64_t total = (int64_t)N * Ho * Wo * q;
+  out.init();
+  float amax = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % q) * 4;
@@ -378,8 +448,9 @@ __global__ void bn_apply_up2x4_kernel(const float* __restrict__ y, int N, int H,
     }
     IMMB_LERP(x) IMMB_LERP(y) IMMB_LERP(z) IMMB_LERP(w)
 #undef IMMB_LERP
-    store_split4(out_hi, out_lo, (size_t)(p * ocs + c), v);
+    out.store4((size_t)(p * ocs + c), v, amax);
   }
+  out.finish(amax);
 }
 
 __global__ void upsample2x_bwd4_kernel(const float* __restrict__ gup, int N, int H, int W, int C, int gcs,
@@ -448,10 +519,13 @@ __global__ void bn_bwd_reduce4_kernel(BnBwdArgs a, int64_t npix, int C, double* 
   });
 }
 
+template <bool H16>
 __global__ void bn_bwd_apply4_kernel(BnBwdArgs a, int64_t npix, int C, const double* __restrict__ sums,
-                                     float* dy_hi, float* dy_lo, float* dgamma, float* dbeta, double* dbias_acc,
+                                     Pl<H16> dyp, float* dgamma, float* dbeta, double* dbias_acc,
                                      int ppb, double* partials) {
   const double inv_n = 1.0 / (double)npix;
+  dyp.init();
+  float amax = 0.f;
   if (blockIdx.x == 0 && threadIdx.x < C) {
     dbeta[threadIdx.x] = (float)sums[threadIdx.x];
     dgamma[threadIdx.x] = (float)sums[C + threadIdx.x];
@@ -470,9 +544,11 @@ __global__ void bn_bwd_apply4_kernel(BnBwdArgs a, int64_t npix, int C, const dou
     dy.y = r.sc.y * (dz.y - mdz.y - xh.y * mdzx.y);
     dy.z = r.sc.z * (dz.z - mdz.z - xh.z * mdzx.z);
     dy.w = r.sc.w * (dz.w - mdz.w - xh.w * mdzx.w);
-    store_split4(dy_hi, dy_lo, (size_t)(p * C + c), dy);
+    dyp.store4((size_t)(p * C + c), dy, amax);
     v[0] = dy;
   });
+  __syncwarp();
+  dyp.finish(amax);
 }
 
 // out[v] += sum_b partials[b*nvals + v] in a fixed (deterministic) order: 32 partial-block lanes per value (strided
@@ -512,15 +588,30 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const double* __r
   }
 }
 
-__global__ void split_planes4_kernel(const float* __restrict__ v, float* hi, float* lo, int64_t n4) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
-    store_split4(hi, lo, (size_t)i * 4, ld4(v + i * 4));
+template <bool H16>
+__global__ void bias_grad_kernel(Pl<H16> g, int gcs, int64_t npix, int C, double* acc) {
+  g.init();
+  channel_reduce<1>(npix, C, acc, C, [&](int64_t p, int c, float* v) {
+    v[0] = g.load((size_t)(p * gcs + c));
+  });
 }
 
-__global__ void maxpool2x2_fwd4_kernel(const float* __restrict__ x_hi, const float* __restrict__ x_lo, int N,
-                                       int H, int W, int C, float* o_hi, float* o_lo) {
+template <bool H16>
+__global__ void split_planes4_kernel(const float* __restrict__ v, Pl<H16> out, int64_t n4) {
+  out.init();
+  float amax = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
+    out.store4((size_t)i * 4, ld4(v + i * 4), amax);
+  out.finish(amax);
+}
+
+template <bool HI, bool HO>
+__global__ void maxpool2x2_fwd4_kernel(Pl<HI> x, int N, int H, int W, int C, Pl<HO> o) {
   int Ho = H / 2, Wo = W / 2, q = C >> 2;
   int64_t total = (int64_t)N * Ho * Wo * q;
+  x.init();
+  o.init();
+  float amax = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % q) * 4;
@@ -530,12 +621,13 @@ __global__ void maxpool2x2_fwd4_kernel(const float* __restrict__ x_hi, const flo
     int ho = (int)(t % Ho);
     int n = (int)(t / Ho);
     size_t base = (((size_t)n * H + 2 * ho) * W + 2 * wo) * C + c;
-    float4 a = load_split4(x_hi, x_lo, base), b = load_split4(x_hi, x_lo, base + C);
-    float4 d = load_split4(x_hi, x_lo, base + (size_t)W * C), e = load_split4(x_hi, x_lo, base + (size_t)W * C + C);
+    float4 a = x.load4(base), b = x.load4(base + C);
+    float4 d = x.load4(base + (size_t)W * C), e = x.load4(base + (size_t)W * C + C);
     float4 v = make_float4(fmaxf(fmaxf(a.x, b.x), fmaxf(d.x, e.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(d.y, e.y)),
                            fmaxf(fmaxf(a.z, b.z), fmaxf(d.z, e.z)), fmaxf(fmaxf(a.w, b.w), fmaxf(d.w, e.w)));
-    store_split4(o_hi, o_lo, (size_t)(p * C + c), v);
+    o.store4((size_t)(p * C + c), v, amax);
   }
+  o.finish(amax);
 }
 
 __global__ void maxpool2x2_bwd4_kernel(const float* __restrict__ g_out, const float* __restrict__ x_hi,
@@ -581,18 +673,19 @@ __device__ __forceinline__ float mask_at(const float* __restrict__ mask, int64_t
   return __ldg(mask + (b * R + (int64_t)hh * s) * R + (int64_t)ww * s);
 }
 
-__global__ void perceptual_level_sum4_kernel(const float* __restrict__ fg_hi, const float* __restrict__ fg_lo,
-                                             int gcs, const float* __restrict__ fp_hi,
-                                             const float* __restrict__ fp_lo, int pcs, int B, int h, int w, int C,
+template <bool H16>
+__global__ void perceptual_level_sum4_kernel(Pl<H16> fg, int gcs, Pl<H16> fp, int pcs, int B, int h, int w, int C,
                                              const float* __restrict__ mask, int R, double* acc) {
   const int q = C >> 2;
   int64_t total = (int64_t)B * h * w * q;
   double local = 0.0;
+  fg.init();
+  fp.init();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % q) * 4;
     int64_t p = i / q;
-    float4 a = load_split4(fg_hi, fg_lo, (size_t)(p * gcs + c)), b = load_split4(fp_hi, fp_lo, (size_t)(p * pcs + c));
+    float4 a = fg.load4((size_t)(p * gcs + c)), b = fp.load4((size_t)(p * pcs + c));
     float m = mask_at(mask, p, h, w, R);
     float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z, dw = a.w - b.w;
     local += (double)(m * (dx * dx)) + (double)(m * (dy * dy)) + (double)(m * (dz * dz)) + (double)(m * (dw * dw));
@@ -612,9 +705,12 @@ __global__ void perceptual_level_sum4_kernel(const float* __restrict__ fg_hi, co
 // 2x2/2 max pool of BOTH halves of a perceptual level ([gt ; pred] stacked on the batch axis) fused with that level's
 // masked squared-difference sum (imm_model.py:143-147): the pool reads every element of the level anyway, so the
 // separate perceptual_level_sum pass (4 more planes) disappears.  acc[0] += sum mask * (f_gt - f_pred)^2.
-__global__ void maxpool2x2_fwd_levelsum4_kernel(const float* __restrict__ x_hi, const float* __restrict__ x_lo, int B,
-                                                int H, int W, int C, float* o_hi, float* o_lo,
+template <bool HI, bool HO>
+__global__ void maxpool2x2_fwd_levelsum4_kernel(Pl<HI> x, int B, int H, int W, int C, Pl<HO> o,
                                                 const float* __restrict__ mask, int R, double* acc) {
+  x.init();
+  o.init();
+  float amax = 0.f;
   const int Ho = H / 2, Wo = W / 2, q = C >> 2;
   const int64_t total = (int64_t)B * Ho * Wo * q;
   const size_t half_in = (size_t)B * H * W * C, half_out = (size_t)B * Ho * Wo * C;
@@ -633,8 +729,8 @@ __global__ void maxpool2x2_fwd_levelsum4_kernel(const float* __restrict__ x_hi, 
     float4 vg = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), vp = vg;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float4 g = load_split4(x_hi, x_lo, base + off[k]);
-      const float4 pr = load_split4(x_hi, x_lo, half_in + base + off[k]);
+      const float4 g = x.load4(base + off[k]);
+      const float4 pr = x.load4(half_in + base + off[k]);
       vg = make_float4(fmaxf(vg.x, g.x), fmaxf(vg.y, g.y), fmaxf(vg.z, g.z), fmaxf(vg.w, g.w));
       vp = make_float4(fmaxf(vp.x, pr.x), fmaxf(vp.y, pr.y), fmaxf(vp.z, pr.z), fmaxf(vp.w, pr.w));
       const int hh = 2 * ho + (k >> 1), ww = 2 * wo + (k & 1);
@@ -642,9 +738,10 @@ __global__ void maxpool2x2_fwd_levelsum4_kernel(const float* __restrict__ x_hi, 
       const float dx = g.x - pr.x, dy = g.y - pr.y, dz = g.z - pr.z, dw = g.w - pr.w;
       local += (double)(m * (dx * dx)) + (double)(m * (dy * dy)) + (double)(m * (dz * dz)) + (double)(m * (dw * dw));
     }
-    store_split4(o_hi, o_lo, (size_t)(p * C + c), vg);
-    store_split4(o_hi, o_lo, half_out + (size_t)(p * C + c), vp);
+    o.store4((size_t)(p * C + c), vg, amax);
+    o.store4(half_out + (size_t)(p * C + c), vp, amax);
   }
+  o.finish(amax);
   local = warp_sum(local);
   __shared__ double sm[32];
   int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -657,39 +754,46 @@ __global__ void maxpool2x2_fwd_levelsum4_kernel(const float* __restrict__ x_hi, 
   }
 }
 
-__global__ void vgg_bwd_combine4_kernel(const float* __restrict__ g_next, const float* __restrict__ fg_hi,
-                                        const float* __restrict__ fg_lo, const float* __restrict__ fp_hi,
-                                        const float* __restrict__ fp_lo, int B, int h, int w, int C,
+template <bool HI, bool HO>
+__global__ void vgg_bwd_combine4_kernel(const float* __restrict__ g_next, Pl<HI> fgp, Pl<HI> fpp, int B, int h, int w, int C,
                                         const float* __restrict__ mask, int R, const float* __restrict__ coef,
-                                        float* dy_hi, float* dy_lo) {
+                                        Pl<HO> dyp) {
   const int q = C >> 2;
   int64_t total = (int64_t)B * h * w * q;
   float cf = coef ? __ldg(coef) : 0.f;
+  fgp.init();
+  fpp.init();
+  dyp.init();
+  float amax = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     int64_t p = i / q;
     size_t e = (size_t)i * 4;
-    float4 fp = load_split4(fp_hi, fp_lo, e);
+    float4 fp = fpp.load4(e);
     float4 g = g_next ? ld4(g_next + e) : make_float4(0.f, 0.f, 0.f, 0.f);
     if (coef) {
-      float4 fg = load_split4(fg_hi, fg_lo, e);
+      float4 fg = fgp.load4(e);
       float m = cf * mask_at(mask, p, h, w, R);
       g.x += m * (fg.x - fp.x); g.y += m * (fg.y - fp.y); g.z += m * (fg.z - fp.z); g.w += m * (fg.w - fp.w);
     }
     g.x = fp.x > 0.f ? g.x : 0.f; g.y = fp.y > 0.f ? g.y : 0.f; g.z = fp.z > 0.f ? g.z : 0.f; g.w = fp.w > 0.f ? g.w : 0.f;
-    store_split4(dy_hi, dy_lo, e, g);
+    dyp.store4(e, g, amax);
   }
+  dyp.finish(amax);
 }
 
 // max-pool backward fused with the loss-term / ReLU-backward combine of the layer that fed the pool (the pred half of
 // a VGG activation): dy = split( [x > 0] * ( [x is the window's first max] * g_out  +  coef * mask * (f_gt - x) ) ),
 // i.e. maxpool2x2_bwd4_kernel followed by vgg_bwd_combine4_kernel without the fp32 gradient round trip and without
 // re-reading x.  coef == nullptr: no loss term at this layer (fg_* unused).
-__global__ void maxpool2x2_bwd_combine4_kernel(const float* __restrict__ g_out, const float* __restrict__ fg_hi,
-                                               const float* __restrict__ fg_lo, const float* __restrict__ x_hi,
-                                               const float* __restrict__ x_lo, int N, int H, int W, int C,
-                                               const float* __restrict__ mask, int R, const float* __restrict__ coef,
-                                               float* dy_hi, float* dy_lo) {
+template <bool HI, bool HO>
+__global__ void maxpool2x2_bwd_combine4_kernel(const float* __restrict__ g_out, Pl<HI> fgp, Pl<HI> xp, int N, int H, int W,
+                                               int C, const float* __restrict__ mask, int R,
+                                               const float* __restrict__ coef, Pl<HO> dyp) {
+  fgp.init();
+  xp.init();
+  dyp.init();
+  float amax = 0.f;
   const int Ho = H / 2, Wo = W / 2, q = C >> 2;
   const int64_t total = (int64_t)N * Ho * Wo * q;
   const float cf = coef ? __ldg(coef) : 0.f;
@@ -706,7 +810,7 @@ __global__ void maxpool2x2_bwd_combine4_kernel(const float* __restrict__ g_out, 
     size_t idx[4] = {base, base + C, base + (size_t)W * C, base + (size_t)W * C + C};
     float4 xv[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) xv[k] = load_split4(x_hi, x_lo, idx[k]);
+    for (int k = 0; k < 4; ++k) xv[k] = xp.load4(idx[k]);
     float4 gg = ld4(g_out + p * C + c);
     float4 o[4];
 #define IMMB_E(f)                                                  \
@@ -722,16 +826,17 @@ __global__ void maxpool2x2_bwd_combine4_kernel(const float* __restrict__ g_out, 
     for (int k = 0; k < 4; ++k) {
       float4 g = o[k];
       if (coef) {
-        const float4 fg = load_split4(fg_hi, fg_lo, idx[k]);
+        const float4 fg = fgp.load4(idx[k]);
         const int hh = 2 * ho + (k >> 1), ww = 2 * wo + (k & 1);
         const float m = cf * (mask ? __ldg(mask + ((int64_t)n * R + (int64_t)hh * s) * R + (int64_t)ww * s) : 1.f);
         g.x += m * (fg.x - xv[k].x); g.y += m * (fg.y - xv[k].y); g.z += m * (fg.z - xv[k].z); g.w += m * (fg.w - xv[k].w);
       }
       g.x = xv[k].x > 0.f ? g.x : 0.f; g.y = xv[k].y > 0.f ? g.y : 0.f;
       g.z = xv[k].z > 0.f ? g.z : 0.f; g.w = xv[k].w > 0.f ? g.w : 0.f;
-      store_split4(dy_hi, dy_lo, idx[k], g);
+      dyp.store4(idx[k], g, amax);
     }
   }
+  dyp.finish(amax);
 }
 
 // =====================================================================================================
@@ -742,12 +847,15 @@ __device__ __forceinline__ float lin_coord(int i, int S) {
   return S > 1 ? -1.0f + (float)i * (2.0f / (float)(S - 1)) : -1.0f;
 }
 
+template <bool H16>
 __global__ void softargmax_gauss_fwd_kernel(const float* __restrict__ heat, int B, int S, int K, int hcs,
                                             float inv_std, float* mu, float* py, float* px, int Sg,
-                                            float* maps_hi, float* maps_lo, int ocs, int c_off) {
+                                            Pl<H16> maps, int ocs, int c_off) {
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
-  if (warp >= B * K) return;
+  if (warp >= B * K) return;                 // whole warps leave together
+  maps.init();
+  float amax = 0.f;
   int b = warp / K, k = warp - b * K;
   const float* hb = heat + (int64_t)b * S * S * hcs + k;
   float ly = 0.f, lx = 0.f;
@@ -783,14 +891,16 @@ __global__ void softargmax_gauss_fwd_kernel(const float* __restrict__ heat, int 
     mu[((int64_t)b * K + k) * 2 + 0] = muy;
     mu[((int64_t)b * K + k) * 2 + 1] = mux;
   }
-  if (maps_hi) {
+  if (maps.hi) {
     float inv2 = inv_std * inv_std;
     for (int t = lane; t < Sg * Sg; t += 32) {
       int i = t / Sg, j = t - i * Sg;
       float dy = lin_coord(i, Sg) - muy, dx = lin_coord(j, Sg) - mux;
       float gval = expf(-(dy * dy + dx * dx) * inv2);
-      store_split(maps_hi, maps_lo, (size_t)(((int64_t)b * Sg * Sg + t) * ocs + c_off + k), gval);
+      maps.store((size_t)(((int64_t)b * Sg * Sg + t) * ocs + c_off + k), gval, amax);
     }
+    __syncwarp();
+    maps.finish(amax);
   }
 }
 
@@ -891,12 +1001,14 @@ __global__ void vgg_prologue_patch_kernel(const float* __restrict__ gt, const fl
 
 // VGG conv1_1 (Cin = 1) fused with the gray/normalise prologue.  block = 256 threads = 64 pixels x 4 channel groups;
 // each thread produces Cout/4 (= 16) channels of one pixel from its 9 gray taps; weights live in shared memory.
-template <int COUT>
+template <int COUT, bool H16>
 __global__ void __launch_bounds__(256) vgg_conv1_1_fused_kernel(const float* __restrict__ gt, const float* __restrict__ pred,
                                                                 int pcs, int B, int R, const float* __restrict__ w,
-                                                                const float* __restrict__ bias, float* out_hi,
-                                                                float* out_lo, int64_t p_begin, int64_t p_end) {
+                                                                const float* __restrict__ bias, Pl<H16> out,
+                                                                int64_t p_begin, int64_t p_end) {
   constexpr int CG = COUT / 4;
+  out.init();
+  float amax = 0.f;
   __shared__ float ws[9][COUT];
   __shared__ float bs[COUT];
   for (int i = threadIdx.x; i < 9 * COUT; i += 256) ws[i / COUT][i % COUT] = __ldg(w + i);
@@ -930,17 +1042,38 @@ __global__ void __launch_bounds__(256) vgg_conv1_1_fused_kernel(const float* __r
     size_t o = (size_t)p * COUT + cg * CG;
     // 256-bit stores: a thread owns 16 consecutive channels (64 B per plane); 128-bit stores would fill only half of
     // each 32-byte sector per instruction (this layer is pure HBM write traffic: 2 planes x 64 ch x 4 B per pixel)
+    if constexpr (H16) {
+      // 16 consecutive channels = 32 bytes per plane: one full sector per store
+      static_assert(CG == 16, "fp16 planes: a thread owns 16 channels");
+      uint32_t hw[8], lw[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float v0 = fmaxf(acc[2 * u], 0.f), v1 = fmaxf(acc[2 * u + 1], 0.f);
+        uint16_t h0, l0, h1, l1;
+        amax = fmaxf(amax, fmaxf(v0, v1));
+        split_h16(v0 * out.mul, h0, l0);
+        split_h16(v1 * out.mul, h1, l1);
+        hw[u] = pack2(h0, h1);
+        lw[u] = pack2(l0, l1);
+      }
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out.hi + o), "r"(hw[0]), "r"(hw[1]),
+                   "r"(hw[2]), "r"(hw[3]), "r"(hw[4]), "r"(hw[5]), "r"(hw[6]), "r"(hw[7]) : "memory");
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out.lo + o), "r"(lw[0]), "r"(lw[1]),
+                   "r"(lw[2]), "r"(lw[3]), "r"(lw[4]), "r"(lw[5]), "r"(lw[6]), "r"(lw[7]) : "memory");
+    } else {
 #pragma unroll
     for (int j = 0; j < CG; j += 8) {
       float h[8], l[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) split_tf32(fmaxf(acc[j + u], 0.f), h[u], l[u]);
-      asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out_hi + o + j), "f"(h[0]), "f"(h[1]),
+      asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out.hi + o + j), "f"(h[0]), "f"(h[1]),
                    "f"(h[2]), "f"(h[3]), "f"(h[4]), "f"(h[5]), "f"(h[6]), "f"(h[7]) : "memory");
-      asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out_lo + o + j), "f"(l[0]), "f"(l[1]),
+      asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out.lo + o + j), "f"(l[0]), "f"(l[1]),
                    "f"(l[2]), "f"(l[3]), "f"(l[4]), "f"(l[5]), "f"(l[6]), "f"(l[7]) : "memory");
     }
+    }
   }
+  out.finish(amax);
 }
 
 // first-layer staging: image [N,H,W,3] -> [N,H,W+8,4] (3 zero columns left, 5 right, 4th channel zero)
@@ -1150,11 +1283,15 @@ __global__ void pred_grad_kernel(const float* __restrict__ gt, const float* __re
 // One block = one 16x16-pixel tile: phase 1 contracts the 64 channels of dy for the 18x18 halo pixels and the nine taps
 // (4 threads per pixel, 16 channels each, exact fp32) into shared memory, phase 2 gathers the nine shifted values.
 // Replaces conv2d_dgrad (1x1 over the [.,12] patch tensor on the tensor cores) + pred_grad and their 48 B/pixel tensor.
+template <bool HI, bool HO>
 __global__ void __launch_bounds__(256) vgg_conv1_1_bwd_fused_kernel(
-    const float* __restrict__ dy_hi, const float* __restrict__ dy_lo, const float* __restrict__ w,
+    Pl<HI> dyp, const float* __restrict__ w,
     const float* __restrict__ gt, const float* __restrict__ pred, int pcs, const float* __restrict__ mask,
-    const float* __restrict__ coef_in, int R, float* g_hi, float* g_lo) {
+    const float* __restrict__ coef_in, int R, Pl<HO> gp) {
   constexpr int COUT = 64, T = 16, HW = T + 2;
+  dyp.init();
+  gp.init();
+  float amax = 0.f;
   __shared__ float ws[9][COUT];
   __shared__ float patch[HW * HW][9];
   for (int i = threadIdx.x; i < 9 * COUT; i += 256) ws[i / COUT][i % COUT] = __ldg(w + i);
@@ -1174,7 +1311,7 @@ __global__ void __launch_bounds__(256) vgg_conv1_1_bwd_fused_kernel(
       const size_t base = (((size_t)n * R + hh) * R + ww) * COUT + part * 16;
 #pragma unroll
       for (int j = 0; j < 16; j += 4) {
-        const float4 v = load_split4(dy_hi, dy_lo, base + j);
+        const float4 v = dyp.load4(base + j);
         const int c = part * 16 + j;
 #pragma unroll
         for (int t = 0; t < 9; ++t)
@@ -1203,8 +1340,9 @@ __global__ void __launch_bounds__(256) vgg_conv1_1_bwd_fused_kernel(
   for (int c = 0; c < pcs; ++c) {
     float g = 0.f;
     if (c < 3) g = cm * (__ldg(gt + p * 3 + c) - __ldg(pred + p * pcs + c)) + gg;
-    store_split(g_hi, g_lo, p * pcs + c, g);
+    gp.store(p * pcs + c, g, amax);
   }
+  gp.finish(amax);
 }
 
 __device__ __forceinline__ void ac_src(int o, int n_in, int n_out, int& lo, int& hi, float& f) {
@@ -1215,10 +1353,12 @@ __device__ __forceinline__ void ac_src(int o, int n_in, int n_out, int& lo, int&
   f = s - (float)lo;
 }
 
-__global__ void resize_ac_fwd_kernel(const float* __restrict__ x_hi, const float* __restrict__ x_lo, int xcs,
-                                     int N, int H, int W, int C, int Ho, int Wo, float* o_hi, float* o_lo,
-                                     int ocs) {
+template <bool HI, bool HO>
+__global__ void resize_ac_fwd_kernel(Pl<HI> x, int xcs, int N, int H, int W, int C, int Ho, int Wo, Pl<HO> o, int ocs) {
   int64_t total = (int64_t)N * Ho * Wo * C;
+  x.init();
+  o.init();
+  float amax = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % C);
@@ -1232,13 +1372,14 @@ __global__ void resize_ac_fwd_kernel(const float* __restrict__ x_hi, const float
     ac_src(ho, H, Ho, h0, h1, fh);
     ac_src(wo, W, Wo, w0, w1, fw);
     size_t nb = (size_t)n * H * W;
-    float a00 = load_split(x_hi, x_lo, (nb + (size_t)h0 * W + w0) * xcs + c);
-    float a01 = load_split(x_hi, x_lo, (nb + (size_t)h0 * W + w1) * xcs + c);
-    float a10 = load_split(x_hi, x_lo, (nb + (size_t)h1 * W + w0) * xcs + c);
-    float a11 = load_split(x_hi, x_lo, (nb + (size_t)h1 * W + w1) * xcs + c);
+    float a00 = x.load((nb + (size_t)h0 * W + w0) * xcs + c);
+    float a01 = x.load((nb + (size_t)h0 * W + w1) * xcs + c);
+    float a10 = x.load((nb + (size_t)h1 * W + w0) * xcs + c);
+    float a11 = x.load((nb + (size_t)h1 * W + w1) * xcs + c);
     float top = a00 + (a01 - a00) * fw, bot = a10 + (a11 - a10) * fw;
-    store_split(o_hi, o_lo, (size_t)(p * ocs + c), top + (bot - top) * fh);
+    o.store((size_t)(p * ocs + c), top + (bot - top) * fh, amax);
   }
+  o.finish(amax);
 }
 
 // adjoint by scatter; g_in must be zeroed by the caller
@@ -1310,8 +1451,10 @@ __global__ void adam_apply_kernel(float* p, const float* __restrict__ g, float* 
                                   const int32_t* __restrict__ chunk_tensor, const int64_t* __restrict__ chunk_off,
                                   const int32_t* __restrict__ chunk_len, const float* __restrict__ tensor_wd,
                                   float gscale, const double* __restrict__ sq, float clip, float lr_t,
-                                  float beta1, float beta2, float eps, const float* __restrict__ lr_t_dev) {
+                                  float beta1, float beta2, float eps, const float* __restrict__ lr_t_dev,
+                                  float* amax) {
   if (lr_t_dev) lr_t = __ldg(lr_t_dev);          // CUDA-graph replays: the step-dependent scalar lives in device memory
+  float pmax = 0.f;
   int ch = blockIdx.x;
   int t = chunk_tensor[ch];
   int64_t off = chunk_off[ch];
@@ -1328,17 +1471,27 @@ __global__ void adam_apply_kernel(float* p, const float* __restrict__ g, float* 
     float vv = beta2 * v[j] + (1.f - beta2) * gv * gv;
     m[j] = mv;
     v[j] = vv;
-    p[j] = pv - lr_t * mv / (sqrtf(vv) + eps);
+    const float pn = pv - lr_t * mv / (sqrtf(vv) + eps);
+    p[j] = pn;
+    pmax = fmaxf(pmax, fabsf(pn));
+  }
+  if (amax) {       // per-tensor max |p| of the UPDATED parameters (zeroed by the caller): scale of the fp16 weight planes
+    __syncwarp();
+    const uint32_t b = __reduce_max_sync(0xffffffffu, __float_as_uint(pmax));
+    if ((threadIdx.x & 31) == 0 && b != 0) atomicMax(reinterpret_cast<unsigned int*>(amax + t), b);
   }
 }
 
 __global__ void total_loss_kernel(const float* rec_loss, const double* wsq, const float* tensor_wd,
-                                  int n_tensors, float* weights_loss, float* total) {
+                                  int n_tensors, float* weights_loss, float* total, const int32_t* overflow) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   double s = 0.0;
   for (int t = 0; t < n_tensors; ++t) s += 0.5 * (double)tensor_wd[t] * wsq[t];
   weights_loss[0] = (float)s;
   total[0] = rec_loss[0] + (float)s;
+  // an fp16 operand plane saturated (immb_scale_update counted it): the step is not trustworthy -> fail loudly through
+  // the caller's NaN guard (cnn_train_multi.py:463) instead of training on clipped values
+  if (overflow && overflow[0] > 0) total[0] = __int_as_float(0x7fc00000);
 }
 
 // HWIO master -> packed [tap][Cout][cin_pad] and split [tap][cin_pad][cout_pad], both as (hi, lo) planes
@@ -1364,6 +1517,73 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int taps, int C
       if (wp_lo) wp_lo[j] = lo;
     }
   }
+}
+
+// H16 variant: the same two layouts as scaled fp16 pairs.  The tensor's scale exponent is derived here from its largest
+// magnitude (amax[0], produced by the optimiser / immb_multi_amax in the same step: weights need no delayed scaling)
+// and published in rec[0] for the convolutions that consume the planes.
+__device__ __forceinline__ int h16_exp_for(float amax) {
+  if (!(amax > 0.f) || !isfinite(amax)) return 0;
+  int ex;
+  frexpf(amax, &ex);                    // amax = m * 2^ex, m in [0.5, 1)  ->  amax * 2^(target - ex) < 2^target
+  int e = kH16TargetExp - ex;
+  return e > 100 ? 100 : (e < -100 ? -100 : e);
+}
+__global__ void pack_weights_h16_kernel(const float* __restrict__ w, int taps, int Cin, int Cout, int cin_pad,
+                                        int cout_pad, uint16_t* wp_hi, uint16_t* wp_lo, uint16_t* wh_hi, uint16_t* wh_lo,
+                                        const float* __restrict__ amax, int32_t* rec) {
+  const int e = h16_exp_for(__ldg(amax));
+  const float mul = exp2i(e);
+  if (blockIdx.x == 0 && threadIdx.x == 0) rec[0] = e;
+  int64_t total = (int64_t)taps * cin_pad * cout_pad;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int co = (int)(i % cout_pad);
+    int64_t q = i / cout_pad;
+    int ci = (int)(q % cin_pad);
+    int tap = (int)(q / cin_pad);
+    float val = (ci < Cin && co < Cout) ? __ldg(w + ((int64_t)tap * Cin + ci) * Cout + co) : 0.f;
+    uint16_t hi, lo;
+    split_h16(val * mul, hi, lo);
+    if (wh_hi) {
+      wh_hi[i] = hi;
+      if (wh_lo) wh_lo[i] = lo;
+    }
+    if (wp_hi && co < Cout) {
+      size_t j = ((size_t)tap * Cout + co) * cin_pad + ci;
+      wp_hi[j] = hi;
+      if (wp_lo) wp_lo[j] = lo;
+    }
+  }
+}
+
+// per-tensor max |p| over the chunk table of the flat parameter buffer (amax[t] zeroed by the caller; bit patterns of
+// non-negative floats order like unsigned integers)
+__global__ void multi_amax_kernel(const float* __restrict__ p, const int32_t* __restrict__ chunk_tensor,
+                                  const int64_t* __restrict__ chunk_off, const int32_t* __restrict__ chunk_len,
+                                  float* amax) {
+  const int ch = blockIdx.x;
+  const int64_t off = chunk_off[ch];
+  const int len = chunk_len[ch];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) m = fmaxf(m, fabsf(__ldg(p + off + i)));
+  uint32_t b = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+  if ((threadIdx.x & 31) == 0 && b != 0) atomicMax(reinterpret_cast<unsigned int*>(amax + chunk_tensor[ch]), b);
+}
+
+// Delayed scaling of the activation / gradient planes: rec[i] = {e, amax bits}.  For every tensor that was written
+// since the last update: count a saturation if its largest magnitude did not fit fp16 under the exponent it was
+// written with, choose the next exponent from the observed maximum, clear the maximum.
+__global__ void scale_update_kernel(int32_t* recs, int n, int32_t* overflow) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t bits = (uint32_t)recs[2 * i + 1];
+  if (bits == 0) return;
+  const float a = __uint_as_float(bits);
+  const int e_old = recs[2 * i];
+  if (!isfinite(a) || a * exp2i(e_old) > 65504.f) atomicAdd(overflow, 1);
+  if (isfinite(a)) recs[2 * i] = h16_exp_for(a);
+  recs[2 * i + 1] = 0;
 }
 
 // Thin-plate-spline warp: one thread per output pixel; the (Hc*Wc+3) x 2 parameters of the image are staged in
@@ -1452,13 +1672,16 @@ static inline dim3 red_grid(int64_t npix, int C) {
 using namespace immb;
 #define ST(s) ((cudaStream_t)(s))
 
-extern "C" int immb_split_planes(const float* v, float* hi, float* lo, int64_t n, void* stream) {
+extern "C" int immb_split_planes(const float* v, void* hi, void* lo, int64_t n, int32_t* scale, void* stream) {
   IMMB_REQUIRE(v && hi && n >= 0, "split_planes: bad args");
   if (n == 0) return IMMB_OK;
-  if ((n & 3) == 0 && aligned16(v) && aligned16(hi) && aligned16(lo))
-    split_planes4_kernel<<<ew_grid(n / 4), 256, 0, ST(stream)>>>(v, hi, lo, n / 4);
+  if (scale) {
+    IMMB_REQUIRE(lo && (n & 3) == 0 && aligned16(v) && aligned16(hi) && aligned16(lo), "split_planes: fp16 planes need n % 4 == 0");
+    split_planes4_kernel<true><<<ew_grid(n / 4), 256, 0, ST(stream)>>>(v, make_pl<true>(hi, lo, scale), n / 4);
+  } else if ((n & 3) == 0 && aligned16(v) && aligned16(hi) && aligned16(lo))
+    split_planes4_kernel<false><<<ew_grid(n / 4), 256, 0, ST(stream)>>>(v, make_pl<false>(hi, lo, nullptr), n / 4);
   else
-    split_planes_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(v, hi, lo, n);
+    split_planes_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(v, (float*)hi, (float*)lo, n);
   return check_launch("split_planes");
 }
 
@@ -1505,25 +1728,33 @@ extern "C" int immb_bn_finalize(const double* sums, int64_t count, int C, const 
 }
 
 extern "C" int immb_bn_apply(const float* y, int N, int H, int W, int C, int ycs, const float* scale,
-                             const float* shift, int relu, int up2x, float* out_hi, float* out_lo, int ocs,
-                             void* stream) {
+                             const float* shift, int relu, int up2x, void* out_hi, void* out_lo, int ocs,
+                             int32_t* out_scale, void* stream) {
   IMMB_REQUIRE(y && scale && shift && out_hi && ycs >= C && ocs >= C, "bn_apply: bad args");
   int64_t npix = (int64_t)N * H * W;
   const bool v4 = vec_ok(C, ycs) && (ocs % 4 == 0) && aligned16(y) && aligned16(out_hi) && aligned16(out_lo);
+  if (out_scale) {
+    IMMB_REQUIRE(v4 && out_lo, "bn_apply: fp16 planes need the vectorised path (C % 4 == 0, aligned rows)");
+    const Pl<true> o = make_pl<true>(out_hi, out_lo, out_scale);
+    if (up2x)
+      bn_apply_up2x4_kernel<true><<<ew_grid(npix * C), 256, 0, ST(stream)>>>(y, N, H, W, C, ycs, scale, shift, relu, o, ocs);
+    else
+      bn_apply4_kernel<true><<<ew_grid(npix * C / 4), 256, 0, ST(stream)>>>(y, npix, C, ycs, scale, shift, relu, o, ocs);
+    return check_launch("bn_apply");
+  }
+  float *ohi = (float*)out_hi, *olo = (float*)out_lo;
+  const Pl<false> o = make_pl<false>(out_hi, out_lo, nullptr);
   if (up2x) {
     if (v4)
-      bn_apply_up2x4_kernel<<<ew_grid(npix * C), 256, 0, ST(stream)>>>(y, N, H, W, C, ycs, scale, shift, relu,
-                                                                       out_hi, out_lo, ocs);
+      bn_apply_up2x4_kernel<false><<<ew_grid(npix * C), 256, 0, ST(stream)>>>(y, N, H, W, C, ycs, scale, shift, relu, o, ocs);
     else
       bn_apply_up2x_kernel<<<ew_grid(npix * 4 * C), 256, 0, ST(stream)>>>(y, N, H, W, C, ycs, scale, shift,
-                                                                           relu, out_hi, out_lo, ocs);
+                                                                           relu, ohi, olo, ocs);
   } else {
     if (v4)
-      bn_apply4_kernel<<<ew_grid(npix * C / 4), 256, 0, ST(stream)>>>(y, npix, C, ycs, scale, shift, relu, out_hi,
-                                                                      out_lo, ocs);
+      bn_apply4_kernel<false><<<ew_grid(npix * C / 4), 256, 0, ST(stream)>>>(y, npix, C, ycs, scale, shift, relu, o, ocs);
     else
-      bn_apply_kernel<<<ew_grid(npix * C), 256, 0, ST(stream)>>>(y, npix, C, ycs, scale, shift, relu, out_hi,
-                                                                  out_lo, ocs);
+      bn_apply_kernel<<<ew_grid(npix * C), 256, 0, ST(stream)>>>(y, npix, C, ycs, scale, shift, relu, ohi, olo, ocs);
   }
   return check_launch("bn_apply");
 }
@@ -1560,31 +1791,40 @@ extern "C" int immb_bn_bwd_reduce(const float* g, int gcs, const float* y, int y
 
 extern "C" int immb_bn_bwd_apply(const float* g, int gcs, const float* y, int ycs, int64_t npix, int C,
                                  const float* scale, const float* shift, const float* mean,
-                                 const float* invstd, int relu, const double* sums, float* dy_hi,
-                                 float* dy_lo, float* dgamma, float* dbeta, double* dbias_acc, double* scratch,
-                                 size_t scratch_elems, void* stream) {
+                                 const float* invstd, int relu, const double* sums, void* dy_hi,
+                                 void* dy_lo, float* dgamma, float* dbeta, double* dbias_acc, double* scratch,
+                                 size_t scratch_elems, int32_t* dy_scale, void* stream) {
   IMMB_REQUIRE(g && y && sums && dy_hi && dgamma && dbeta && dbias_acc, "bn_bwd_apply: bad args");
-  if (vec_ok(C, gcs) && ycs % 4 == 0 && C <= 256 && aligned16(g) && aligned16(y) && aligned16(dy_hi) &&
-      aligned16(dy_lo)) {
+  const bool v4 = vec_ok(C, gcs) && ycs % 4 == 0 && C <= 256 && aligned16(g) && aligned16(y) && aligned16(dy_hi) &&
+                  aligned16(dy_lo);
+  IMMB_REQUIRE(!dy_scale || (v4 && dy_lo), "bn_bwd_apply: fp16 planes need the vectorised path");
+  if (v4) {
     BnBwdArgs a{g, y, scale, shift, mean, invstd, gcs, ycs, relu};
     const bool two = scratch && scratch_elems >= immb_bn_scratch_elems(npix, C);
     const int ppb = vred_pix(npix, C, two), grid = vred_grid(npix, ppb);
-    bn_bwd_apply4_kernel<<<grid, 256, vred_smem(1), ST(stream)>>>(a, npix, C, sums, dy_hi, dy_lo, dgamma, dbeta,
-                                                                  dbias_acc, ppb, two ? scratch : nullptr);
+    if (dy_scale)
+      bn_bwd_apply4_kernel<true><<<grid, 256, vred_smem(1), ST(stream)>>>(a, npix, C, sums, make_pl<true>(dy_hi, dy_lo, dy_scale),
+                                                                          dgamma, dbeta, dbias_acc, ppb, two ? scratch : nullptr);
+    else
+      bn_bwd_apply4_kernel<false><<<grid, 256, vred_smem(1), ST(stream)>>>(a, npix, C, sums, make_pl<false>(dy_hi, dy_lo, nullptr),
+                                                                           dgamma, dbeta, dbias_acc, ppb, two ? scratch : nullptr);
     int rc = check_launch("bn_bwd_apply");
     if (rc || !two) return rc;
     return launch_reduce_partials(scratch, grid, C, dbias_acc, ST(stream));
   } else {
     bn_bwd_apply_kernel<<<red_grid(npix, C), dim3(32, kRedRows), 0, ST(stream)>>>(
-        g, gcs, y, ycs, npix, C, scale, shift, mean, invstd, relu, sums, dy_hi, dy_lo, dgamma, dbeta, dbias_acc);
+        g, gcs, y, ycs, npix, C, scale, shift, mean, invstd, relu, sums, (float*)dy_hi, (float*)dy_lo, dgamma, dbeta, dbias_acc);
   }
   return check_launch("bn_bwd_apply");
 }
 
-extern "C" int immb_bias_grad(const float* g_hi, const float* g_lo, int gcs, int64_t npix, int C, double* acc,
-                              void* stream) {
+extern "C" int immb_bias_grad(const void* g_hi, const void* g_lo, int gcs, int64_t npix, int C, double* acc,
+                              const int32_t* g_scale, void* stream) {
   IMMB_REQUIRE(g_hi && acc && gcs >= C, "bias_grad: bad args");
-  bias_grad_kernel<<<red_grid(npix, C), dim3(32, kRedRows), 0, ST(stream)>>>(g_hi, g_lo, gcs, npix, C, acc);
+  if (g_scale)
+    bias_grad_kernel<true><<<red_grid(npix, C), dim3(32, kRedRows), 0, ST(stream)>>>(make_pl<true>(g_hi, g_lo, g_scale), gcs, npix, C, acc);
+  else
+    bias_grad_kernel<false><<<red_grid(npix, C), dim3(32, kRedRows), 0, ST(stream)>>>(make_pl<false>(g_hi, g_lo, nullptr), gcs, npix, C, acc);
   return check_launch("bias_grad");
 }
 
@@ -1595,13 +1835,18 @@ extern "C" int immb_cast_d2f(const double* src, float* dst, int64_t n, void* str
 }
 
 extern "C" int immb_softargmax_gauss_fwd(const float* heat, int B, int S, int K, int hcs, float inv_std,
-                                         float* mu, float* py, float* px, int Sg, float* maps_hi,
-                                         float* maps_lo, int ocs, int c_off, void* stream) {
+                                         float* mu, float* py, float* px, int Sg, void* maps_hi,
+                                         void* maps_lo, int ocs, int c_off, int32_t* maps_scale, void* stream) {
   IMMB_REQUIRE(heat && mu && py && px && S >= 1 && S <= 32 && K >= 1 && hcs >= K, "softargmax_fwd: bad args (S<=32)");
   IMMB_REQUIRE(!maps_hi || (Sg >= 1 && ocs >= c_off + K), "softargmax_fwd: bad map args");
+  IMMB_REQUIRE(!maps_scale || (maps_hi && maps_lo), "softargmax_fwd: fp16 map planes need both planes");
   int warps = B * K;
-  softargmax_gauss_fwd_kernel<<<ceil_div((int64_t)warps * 32, 128), 128, 0, ST(stream)>>>(
-      heat, B, S, K, hcs, inv_std, mu, py, px, Sg, maps_hi, maps_lo, ocs, c_off);
+  if (maps_scale)
+    softargmax_gauss_fwd_kernel<true><<<ceil_div((int64_t)warps * 32, 128), 128, 0, ST(stream)>>>(
+        heat, B, S, K, hcs, inv_std, mu, py, px, Sg, make_pl<true>(maps_hi, maps_lo, maps_scale), ocs, c_off);
+  else
+    softargmax_gauss_fwd_kernel<false><<<ceil_div((int64_t)warps * 32, 128), 128, 0, ST(stream)>>>(
+        heat, B, S, K, hcs, inv_std, mu, py, px, Sg, make_pl<false>(maps_hi, maps_lo, nullptr), ocs, c_off);
   return check_launch("softargmax_gauss_fwd");
 }
 
@@ -1635,8 +1880,8 @@ extern "C" int immb_vgg_prologue(const float* gt, const float* pred, int pcs, in
 }
 
 extern "C" int immb_vgg_conv1_1_fused(const float* gt, const float* pred, int pcs, int B, int R, const float* w,
-                                      const float* bias, int Cout, float* out_hi, float* out_lo, int which,
-                                      void* stream) {
+                                      const float* bias, int Cout, void* out_hi, void* out_lo, int which,
+                                      int32_t* out_scale, void* stream) {
   IMMB_REQUIRE(w && bias && out_hi && pcs >= 3 && which >= 0 && which <= 2, "vgg_conv1_1_fused: bad args");
   IMMB_REQUIRE((which == 2 || gt) && (which == 1 || pred), "vgg_conv1_1_fused: missing input for the requested half");
   IMMB_REQUIRE(Cout == 64, "vgg_conv1_1_fused: Cout must be 64 (VGG16 conv1_1)");
@@ -1645,7 +1890,12 @@ extern "C" int immb_vgg_conv1_1_fused(const float* gt, const float* pred, int pc
   const int64_t p0 = which == 2 ? per : 0, p1 = which == 1 ? per : 2 * per;
   int64_t blocks = (p1 - p0 + 63) / 64;
   if (blocks > (int64_t)kNumSMs * 32) blocks = (int64_t)kNumSMs * 32;
-  vgg_conv1_1_fused_kernel<64><<<(int)blocks, 256, 0, ST(stream)>>>(gt, pred, pcs, B, R, w, bias, out_hi, out_lo, p0, p1);
+  if (out_scale)
+    vgg_conv1_1_fused_kernel<64, true><<<(int)blocks, 256, 0, ST(stream)>>>(gt, pred, pcs, B, R, w, bias,
+                                                                            make_pl<true>(out_hi, out_lo, out_scale), p0, p1);
+  else
+    vgg_conv1_1_fused_kernel<64, false><<<(int)blocks, 256, 0, ST(stream)>>>(gt, pred, pcs, B, R, w, bias,
+                                                                             make_pl<false>(out_hi, out_lo, nullptr), p0, p1);
   return check_launch("vgg_conv1_1_fused");
 }
 
@@ -1663,27 +1913,48 @@ extern "C" int immb_pack_weights_rowwin(const float* w, int Cout, float* wp_hi, 
   return check_launch("pack_weights_rowwin");
 }
 
-extern "C" int immb_maxpool2x2_fwd(const float* x_hi, const float* x_lo, int N, int H, int W, int C,
-                                   float* o_hi, float* o_lo, void* stream) {
+template <bool H>
+static inline Pl<H> pl_of(const void* hi, const void* lo, const int32_t* rec) { return make_pl<H>(hi, lo, rec); }
+
+extern "C" int immb_maxpool2x2_fwd(const void* x_hi, const void* x_lo, int N, int H, int W, int C,
+                                   void* o_hi, void* o_lo, const int32_t* x_scale, int32_t* o_scale, void* stream) {
   IMMB_REQUIRE(x_hi && o_hi && (H % 2 == 0) && (W % 2 == 0), "maxpool_fwd: bad args (even sizes only)");
-  if (C % 4 == 0 && aligned16(x_hi) && aligned16(x_lo) && aligned16(o_hi) && aligned16(o_lo))
-    maxpool2x2_fwd4_kernel<<<ew_grid((int64_t)N * (H / 2) * (W / 2) * C / 4), 256, 0, ST(stream)>>>(x_hi, x_lo, N, H,
-                                                                                                  W, C, o_hi, o_lo);
+  const bool v4 = C % 4 == 0 && aligned16(x_hi) && aligned16(x_lo) && aligned16(o_hi) && aligned16(o_lo);
+  IMMB_REQUIRE((!x_scale && !o_scale) || (v4 && x_lo && o_lo), "maxpool_fwd: fp16 planes need 4 | C and both planes");
+  const int grid = ew_grid((int64_t)N * (H / 2) * (W / 2) * C / 4);
+  if (x_scale && o_scale)
+    maxpool2x2_fwd4_kernel<true, true><<<grid, 256, 0, ST(stream)>>>(pl_of<true>(x_hi, x_lo, x_scale), N, H, W, C, pl_of<true>(o_hi, o_lo, o_scale));
+  else if (x_scale)
+    maxpool2x2_fwd4_kernel<true, false><<<grid, 256, 0, ST(stream)>>>(pl_of<true>(x_hi, x_lo, x_scale), N, H, W, C, pl_of<false>(o_hi, o_lo, nullptr));
+  else if (o_scale)
+    return set_error(IMMB_ERR_UNSUPPORTED, "maxpool_fwd: fp32 -> fp16 planes is not built");
+  else if (v4)
+    maxpool2x2_fwd4_kernel<false, false><<<grid, 256, 0, ST(stream)>>>(pl_of<false>(x_hi, x_lo, nullptr), N, H, W, C, pl_of<false>(o_hi, o_lo, nullptr));
   else
-    maxpool2x2_fwd_kernel<<<ew_grid((int64_t)N * (H / 2) * (W / 2) * C), 256, 0, ST(stream)>>>(x_hi, x_lo, N, H,
-                                                                                              W, C, o_hi, o_lo);
+    maxpool2x2_fwd_kernel<<<ew_grid((int64_t)N * (H / 2) * (W / 2) * C), 256, 0, ST(stream)>>>(
+        (const float*)x_hi, (const float*)x_lo, N, H, W, C, (float*)o_hi, (float*)o_lo);
   return check_launch("maxpool2x2_fwd");
 }
 
-extern "C" int immb_maxpool2x2_fwd_levelsum(const float* x_hi, const float* x_lo, int B, int H, int W, int C,
-                                            float* o_hi, float* o_lo, const float* mask, int R, double* acc,
-                                            void* stream) {
+extern "C" int immb_maxpool2x2_fwd_levelsum(const void* x_hi, const void* x_lo, int B, int H, int W, int C,
+                                            void* o_hi, void* o_lo, const float* mask, int R, double* acc,
+                                            const int32_t* x_scale, int32_t* o_scale, void* stream) {
   IMMB_REQUIRE(x_hi && x_lo && o_hi && o_lo && acc && B > 0 && (H % 2 == 0) && (W % 2 == 0) && C % 4 == 0,
                "maxpool_fwd_levelsum: bad args (even sizes, split planes, 4 | C)");
   IMMB_REQUIRE(!mask || (R >= H && R % H == 0), "maxpool_fwd_levelsum: mask resolution must be a multiple of the level's");
   IMMB_REQUIRE(aligned16(x_hi) && aligned16(x_lo) && aligned16(o_hi) && aligned16(o_lo), "maxpool_fwd_levelsum: alignment");
-  maxpool2x2_fwd_levelsum4_kernel<<<ew_grid((int64_t)B * (H / 2) * (W / 2) * C / 4), 256, 0, ST(stream)>>>(
-      x_hi, x_lo, B, H, W, C, o_hi, o_lo, mask, R, acc);
+  const int grid = ew_grid((int64_t)B * (H / 2) * (W / 2) * C / 4);
+  if (x_scale && o_scale)
+    maxpool2x2_fwd_levelsum4_kernel<true, true><<<grid, 256, 0, ST(stream)>>>(pl_of<true>(x_hi, x_lo, x_scale), B, H, W, C,
+                                                                              pl_of<true>(o_hi, o_lo, o_scale), mask, R, acc);
+  else if (x_scale)
+    maxpool2x2_fwd_levelsum4_kernel<true, false><<<grid, 256, 0, ST(stream)>>>(pl_of<true>(x_hi, x_lo, x_scale), B, H, W, C,
+                                                                               pl_of<false>(o_hi, o_lo, nullptr), mask, R, acc);
+  else if (o_scale)
+    return set_error(IMMB_ERR_UNSUPPORTED, "maxpool_fwd_levelsum: fp32 -> fp16 planes is not built");
+  else
+    maxpool2x2_fwd_levelsum4_kernel<false, false><<<grid, 256, 0, ST(stream)>>>(pl_of<false>(x_hi, x_lo, nullptr), B, H, W, C,
+                                                                                pl_of<false>(o_hi, o_lo, nullptr), mask, R, acc);
   return check_launch("maxpool2x2_fwd_levelsum");
 }
 
@@ -1699,32 +1970,45 @@ extern "C" int immb_maxpool2x2_bwd(const float* g_out, const float* x_hi, const 
   return check_launch("maxpool2x2_bwd");
 }
 
-extern "C" int immb_maxpool2x2_bwd_combine(const float* g_out, const float* fg_hi, const float* fg_lo,
-                                           const float* fp_hi, const float* fp_lo, int B, int H, int W, int C,
-                                           const float* mask, int R, const float* coef, float* dy_hi, float* dy_lo,
-                                           void* stream) {
+extern "C" int immb_maxpool2x2_bwd_combine(const float* g_out, const void* fg_hi, const void* fg_lo,
+                                           const void* fp_hi, const void* fp_lo, int B, int H, int W, int C,
+                                           const float* mask, int R, const float* coef, void* dy_hi, void* dy_lo,
+                                           const int32_t* f_scale, int32_t* dy_scale, void* stream) {
   IMMB_REQUIRE(g_out && fp_hi && fp_lo && dy_hi && dy_lo && (H % 2 == 0) && (W % 2 == 0) && C % 4 == 0 &&
                (!coef || (fg_hi && fg_lo)), "maxpool_bwd_combine: bad args");
   IMMB_REQUIRE(!mask || (R >= H && R % H == 0), "maxpool_bwd_combine: mask resolution must be a multiple of the level's");
   IMMB_REQUIRE(aligned16(g_out) && aligned16(fg_hi) && aligned16(fg_lo) && aligned16(fp_hi) && aligned16(fp_lo) &&
                aligned16(dy_hi) && aligned16(dy_lo), "maxpool_bwd_combine: alignment");
-  maxpool2x2_bwd_combine4_kernel<<<ew_grid((int64_t)B * (H / 2) * (W / 2) * C / 4), 256, 0, ST(stream)>>>(
-      g_out, fg_hi, fg_lo, fp_hi, fp_lo, B, H, W, C, mask, R, coef, dy_hi, dy_lo);
+  IMMB_REQUIRE((f_scale != nullptr) == (dy_scale != nullptr), "maxpool_bwd_combine: activation and dy planes share a format");
+  const int grid = ew_grid((int64_t)B * (H / 2) * (W / 2) * C / 4);
+  if (f_scale)
+    maxpool2x2_bwd_combine4_kernel<true, true><<<grid, 256, 0, ST(stream)>>>(
+        g_out, pl_of<true>(fg_hi, fg_lo, f_scale), pl_of<true>(fp_hi, fp_lo, f_scale), B, H, W, C, mask, R, coef,
+        pl_of<true>(dy_hi, dy_lo, dy_scale));
+  else
+    maxpool2x2_bwd_combine4_kernel<false, false><<<grid, 256, 0, ST(stream)>>>(
+        g_out, pl_of<false>(fg_hi, fg_lo, nullptr), pl_of<false>(fp_hi, fp_lo, nullptr), B, H, W, C, mask, R, coef,
+        pl_of<false>(dy_hi, dy_lo, nullptr));
   return check_launch("maxpool2x2_bwd_combine");
 }
 
-extern "C" int immb_perceptual_level_sum(const float* fg_hi, const float* fg_lo, int gcs, const float* fp_hi,
-                                         const float* fp_lo, int pcs, int B, int h, int w, int C,
-                                         const float* mask, int R, double* acc, void* stream) {
+extern "C" int immb_perceptual_level_sum(const void* fg_hi, const void* fg_lo, int gcs, const void* fp_hi,
+                                         const void* fp_lo, int pcs, int B, int h, int w, int C,
+                                         const float* mask, int R, double* acc, const int32_t* f_scale, void* stream) {
   IMMB_REQUIRE(fg_hi && fp_hi && acc && gcs >= C && pcs >= C && h > 0 && (!mask || R % h == 0),
                "perceptual_level_sum: bad args");
-  if (C % 4 == 0 && gcs % 4 == 0 && pcs % 4 == 0 && aligned16(fg_hi) && aligned16(fg_lo) && aligned16(fp_hi) &&
-      aligned16(fp_lo))
-    perceptual_level_sum4_kernel<<<ew_grid((int64_t)B * h * w * C / 4), 256, 0, ST(stream)>>>(
-        fg_hi, fg_lo, gcs, fp_hi, fp_lo, pcs, B, h, w, C, mask, R, acc);
+  const bool v4 = C % 4 == 0 && gcs % 4 == 0 && pcs % 4 == 0 && aligned16(fg_hi) && aligned16(fg_lo) && aligned16(fp_hi) &&
+                  aligned16(fp_lo);
+  IMMB_REQUIRE(!f_scale || (v4 && fg_lo && fp_lo), "perceptual_level_sum: fp16 planes need 4 | C and both planes");
+  if (f_scale)
+    perceptual_level_sum4_kernel<true><<<ew_grid((int64_t)B * h * w * C / 4), 256, 0, ST(stream)>>>(
+        pl_of<true>(fg_hi, fg_lo, f_scale), gcs, pl_of<true>(fp_hi, fp_lo, f_scale), pcs, B, h, w, C, mask, R, acc);
+  else if (v4)
+    perceptual_level_sum4_kernel<false><<<ew_grid((int64_t)B * h * w * C / 4), 256, 0, ST(stream)>>>(
+        pl_of<false>(fg_hi, fg_lo, nullptr), gcs, pl_of<false>(fp_hi, fp_lo, nullptr), pcs, B, h, w, C, mask, R, acc);
   else
     perceptual_level_sum_kernel<<<ew_grid((int64_t)B * h * w * C), 256, 0, ST(stream)>>>(
-        fg_hi, fg_lo, gcs, fp_hi, fp_lo, pcs, B, h, w, C, mask, R, acc);
+        (const float*)fg_hi, (const float*)fg_lo, gcs, (const float*)fp_hi, (const float*)fp_lo, pcs, B, h, w, C, mask, R, acc);
   return check_launch("perceptual_level_sum");
 }
 
@@ -1737,18 +2021,28 @@ extern "C" int immb_perceptual_finalize(const double* acc, const double* counts,
   return check_launch("perceptual_finalize");
 }
 
-extern "C" int immb_vgg_bwd_combine(const float* g_next, const float* fg_hi, const float* fg_lo,
-                                    const float* fp_hi, const float* fp_lo, int B, int h, int w, int C,
-                                    const float* mask, int R, const float* coef, float* dy_hi, float* dy_lo,
-                                    void* stream) {
+extern "C" int immb_vgg_bwd_combine(const float* g_next, const void* fg_hi, const void* fg_lo,
+                                    const void* fp_hi, const void* fp_lo, int B, int h, int w, int C,
+                                    const float* mask, int R, const float* coef, void* dy_hi, void* dy_lo,
+                                    const int32_t* f_scale, int32_t* dy_scale, void* stream) {
   IMMB_REQUIRE(fp_hi && dy_hi && (g_next || coef) && (!coef || fg_hi), "vgg_bwd_combine: bad args");
-  if (C % 4 == 0 && aligned16(g_next) && aligned16(fg_hi) && aligned16(fg_lo) && aligned16(fp_hi) &&
-      aligned16(fp_lo) && aligned16(dy_hi) && aligned16(dy_lo))
-    vgg_bwd_combine4_kernel<<<ew_grid((int64_t)B * h * w * C / 4), 256, 0, ST(stream)>>>(
-        g_next, fg_hi, fg_lo, fp_hi, fp_lo, B, h, w, C, mask, R, coef, dy_hi, dy_lo);
+  const bool v4 = C % 4 == 0 && aligned16(g_next) && aligned16(fg_hi) && aligned16(fg_lo) && aligned16(fp_hi) &&
+                  aligned16(fp_lo) && aligned16(dy_hi) && aligned16(dy_lo);
+  IMMB_REQUIRE((f_scale != nullptr) == (dy_scale != nullptr), "vgg_bwd_combine: activation and dy planes share a format");
+  IMMB_REQUIRE(!f_scale || (v4 && fp_lo && dy_lo), "vgg_bwd_combine: fp16 planes need 4 | C and both planes");
+  const int grid = ew_grid((int64_t)B * h * w * C / 4);
+  if (f_scale)
+    vgg_bwd_combine4_kernel<true, true><<<grid, 256, 0, ST(stream)>>>(g_next, pl_of<true>(fg_hi, fg_lo, f_scale),
+                                                                      pl_of<true>(fp_hi, fp_lo, f_scale), B, h, w, C, mask, R,
+                                                                      coef, pl_of<true>(dy_hi, dy_lo, dy_scale));
+  else if (v4)
+    vgg_bwd_combine4_kernel<false, false><<<grid, 256, 0, ST(stream)>>>(g_next, pl_of<false>(fg_hi, fg_lo, nullptr),
+                                                                        pl_of<false>(fp_hi, fp_lo, nullptr), B, h, w, C, mask,
+                                                                        R, coef, pl_of<false>(dy_hi, dy_lo, nullptr));
   else
     vgg_bwd_combine_kernel<<<ew_grid((int64_t)B * h * w * C), 256, 0, ST(stream)>>>(
-        g_next, fg_hi, fg_lo, fp_hi, fp_lo, B, h, w, C, mask, R, coef, dy_hi, dy_lo);
+        g_next, (const float*)fg_hi, (const float*)fg_lo, (const float*)fp_hi, (const float*)fp_lo, B, h, w, C, mask, R, coef,
+        (float*)dy_hi, (float*)dy_lo);
   return check_launch("vgg_bwd_combine");
 }
 
@@ -1761,24 +2055,48 @@ extern "C" int immb_pred_grad(const float* gt, const float* pred, int pcs, const
   return check_launch("pred_grad");
 }
 
-extern "C" int immb_vgg_conv1_1_bwd_fused(const float* dy_hi, const float* dy_lo, const float* w, int Cout,
+extern "C" int immb_vgg_conv1_1_bwd_fused(const void* dy_hi, const void* dy_lo, const float* w, int Cout,
                                           const float* gt, const float* pred, int pcs, const float* mask,
-                                          const float* coef_input, int B, int R, float* g_hi, float* g_lo,
-                                          void* stream) {
+                                          const float* coef_input, int B, int R, void* g_hi, void* g_lo,
+                                          const int32_t* dy_scale, int32_t* g_scale, void* stream) {
   IMMB_REQUIRE(dy_hi && dy_lo && w && gt && pred && coef_input && g_hi && g_lo && pcs >= 3 && B > 0,
                "vgg_conv1_1_bwd_fused: bad args");
   IMMB_REQUIRE(Cout == 64 && R % 16 == 0, "vgg_conv1_1_bwd_fused: Cout must be 64 and 16 | R");
   IMMB_REQUIRE(aligned16(dy_hi) && aligned16(dy_lo), "vgg_conv1_1_bwd_fused: alignment");
-  vgg_conv1_1_bwd_fused_kernel<<<B * (R / 16) * (R / 16), 256, 0, ST(stream)>>>(dy_hi, dy_lo, w, gt, pred, pcs, mask,
-                                                                                coef_input, R, g_hi, g_lo);
+  const int grid = B * (R / 16) * (R / 16);
+  if (dy_scale && g_scale)
+    vgg_conv1_1_bwd_fused_kernel<true, true><<<grid, 256, 0, ST(stream)>>>(pl_of<true>(dy_hi, dy_lo, dy_scale), w, gt, pred, pcs,
+                                                                           mask, coef_input, R, pl_of<true>(g_hi, g_lo, g_scale));
+  else if (dy_scale)
+    vgg_conv1_1_bwd_fused_kernel<true, false><<<grid, 256, 0, ST(stream)>>>(pl_of<true>(dy_hi, dy_lo, dy_scale), w, gt, pred, pcs,
+                                                                            mask, coef_input, R, pl_of<false>(g_hi, g_lo, nullptr));
+  else if (g_scale)
+    vgg_conv1_1_bwd_fused_kernel<false, true><<<grid, 256, 0, ST(stream)>>>(pl_of<false>(dy_hi, dy_lo, nullptr), w, gt, pred, pcs,
+                                                                            mask, coef_input, R, pl_of<true>(g_hi, g_lo, g_scale));
+  else
+    vgg_conv1_1_bwd_fused_kernel<false, false><<<grid, 256, 0, ST(stream)>>>(pl_of<false>(dy_hi, dy_lo, nullptr), w, gt, pred, pcs,
+                                                                             mask, coef_input, R, pl_of<false>(g_hi, g_lo, nullptr));
   return check_launch("vgg_conv1_1_bwd_fused");
 }
 
-extern "C" int immb_resize_ac_fwd(const float* x_hi, const float* x_lo, int xcs, int N, int H, int W, int C,
-                                  int Ho, int Wo, float* o_hi, float* o_lo, int ocs, void* stream) {
+extern "C" int immb_resize_ac_fwd(const void* x_hi, const void* x_lo, int xcs, int N, int H, int W, int C,
+                                  int Ho, int Wo, void* o_hi, void* o_lo, int ocs, const int32_t* x_scale,
+                                  int32_t* o_scale, void* stream) {
   IMMB_REQUIRE(x_hi && o_hi && xcs >= C && ocs >= C, "resize_ac_fwd: bad args");
-  resize_ac_fwd_kernel<<<ew_grid((int64_t)N * Ho * Wo * C), 256, 0, ST(stream)>>>(x_hi, x_lo, xcs, N, H, W, C,
-                                                                                 Ho, Wo, o_hi, o_lo, ocs);
+  IMMB_REQUIRE((!x_scale || x_lo) && (!o_scale || o_lo), "resize_ac_fwd: fp16 planes need both planes");
+  const int grid = ew_grid((int64_t)N * Ho * Wo * C);
+  if (x_scale && o_scale)
+    resize_ac_fwd_kernel<true, true><<<grid, 256, 0, ST(stream)>>>(pl_of<true>(x_hi, x_lo, x_scale), xcs, N, H, W, C, Ho, Wo,
+                                                                   pl_of<true>(o_hi, o_lo, o_scale), ocs);
+  else if (x_scale)
+    resize_ac_fwd_kernel<true, false><<<grid, 256, 0, ST(stream)>>>(pl_of<true>(x_hi, x_lo, x_scale), xcs, N, H, W, C, Ho, Wo,
+                                                                    pl_of<false>(o_hi, o_lo, nullptr), ocs);
+  else if (o_scale)
+    resize_ac_fwd_kernel<false, true><<<grid, 256, 0, ST(stream)>>>(pl_of<false>(x_hi, x_lo, nullptr), xcs, N, H, W, C, Ho, Wo,
+                                                                    pl_of<true>(o_hi, o_lo, o_scale), ocs);
+  else
+    resize_ac_fwd_kernel<false, false><<<grid, 256, 0, ST(stream)>>>(pl_of<false>(x_hi, x_lo, nullptr), xcs, N, H, W, C, Ho, Wo,
+                                                                     pl_of<false>(o_hi, o_lo, nullptr), ocs);
   return check_launch("resize_ac_fwd");
 }
 
@@ -1816,36 +2134,57 @@ extern "C" int immb_adam_norms(const float* p, const float* g, int64_t n, const 
 extern "C" int immb_adam_apply(float* p, const float* g, float* m, float* v, int64_t n,
                                const int32_t* chunk_tensor, const int64_t* chunk_off, const int32_t* chunk_len,
                                int n_chunks, const float* tensor_wd, float gscale, const double* sq, float clip,
-                               float lr_t, float beta1, float beta2, float eps, void* stream) {
+                               float lr_t, float beta1, float beta2, float eps, float* amax, void* stream) {
   IMMB_REQUIRE(p && g && m && v && chunk_tensor && chunk_off && chunk_len && tensor_wd && sq && n_chunks > 0,
                "adam_apply: bad args");
   adam_apply_kernel<<<n_chunks, 256, 0, ST(stream)>>>(p, g, m, v, chunk_tensor, chunk_off, chunk_len,
-                                                      tensor_wd, gscale, sq, clip, lr_t, beta1, beta2, eps, nullptr);
+                                                      tensor_wd, gscale, sq, clip, lr_t, beta1, beta2, eps, nullptr, amax);
   return check_launch("adam_apply");
 }
 
 extern "C" int immb_adam_apply_dev(float* p, const float* g, float* m, float* v, int64_t n,
                                    const int32_t* chunk_tensor, const int64_t* chunk_off, const int32_t* chunk_len,
                                    int n_chunks, const float* tensor_wd, float gscale, const double* sq, float clip,
-                                   const float* lr_t_dev, float beta1, float beta2, float eps, void* stream) {
+                                   const float* lr_t_dev, float beta1, float beta2, float eps, float* amax,
+                                   void* stream) {
   IMMB_REQUIRE(p && g && m && v && chunk_tensor && chunk_off && chunk_len && tensor_wd && sq && n_chunks > 0 && lr_t_dev,
                "adam_apply_dev: bad args");
   adam_apply_kernel<<<n_chunks, 256, 0, ST(stream)>>>(p, g, m, v, chunk_tensor, chunk_off, chunk_len,
-                                                      tensor_wd, gscale, sq, clip, 0.f, beta1, beta2, eps, lr_t_dev);
+                                                      tensor_wd, gscale, sq, clip, 0.f, beta1, beta2, eps, lr_t_dev, amax);
   return check_launch("adam_apply_dev");
 }
 
 extern "C" int immb_total_loss(const float* rec_loss, const double* wsq, const float* tensor_wd, int n_tensors,
-                               float* weights_loss, float* total, void* stream) {
+                               float* weights_loss, float* total, const int32_t* overflow, void* stream) {
   IMMB_REQUIRE(rec_loss && wsq && tensor_wd && weights_loss && total, "total_loss: bad args");
-  total_loss_kernel<<<1, 32, 0, ST(stream)>>>(rec_loss, wsq, tensor_wd, n_tensors, weights_loss, total);
+  total_loss_kernel<<<1, 32, 0, ST(stream)>>>(rec_loss, wsq, tensor_wd, n_tensors, weights_loss, total, overflow);
   return check_launch("total_loss");
 }
 
+extern "C" int immb_multi_amax(const float* p, const int32_t* chunk_tensor, const int64_t* chunk_off,
+                               const int32_t* chunk_len, int n_chunks, float* amax, void* stream) {
+  IMMB_REQUIRE(p && chunk_tensor && chunk_off && chunk_len && amax && n_chunks > 0, "multi_amax: bad args");
+  multi_amax_kernel<<<n_chunks, 256, 0, ST(stream)>>>(p, chunk_tensor, chunk_off, chunk_len, amax);
+  return check_launch("multi_amax");
+}
+
+extern "C" int immb_scale_update(int32_t* recs, int n, int32_t* overflow, void* stream) {
+  IMMB_REQUIRE(recs && overflow && n > 0, "scale_update: bad args");
+  scale_update_kernel<<<ceil_div(n, 128), 128, 0, ST(stream)>>>(recs, n, overflow);
+  return check_launch("scale_update");
+}
+
 extern "C" int immb_pack_weights(const float* w, int kh, int kw, int Cin, int Cout, int cin_pad, int cout_pad,
-                                 float* wp_hi, float* wp_lo, float* wh_hi, float* wh_lo, void* stream) {
+                                 void* wp_hi, void* wp_lo, void* wh_hi, void* wh_lo, const float* amax,
+                                 int32_t* w_scale, void* stream) {
   IMMB_REQUIRE(w && (wp_hi || wh_hi) && cin_pad >= Cin && cout_pad >= Cout, "pack_weights: bad args");
-  pack_weights_kernel<<<ew_grid((int64_t)kh * kw * cin_pad * cout_pad), 256, 0, ST(stream)>>>(
-      w, kh * kw, Cin, Cout, cin_pad, cout_pad, wp_hi, wp_lo, wh_hi, wh_lo);
+  IMMB_REQUIRE((amax != nullptr) == (w_scale != nullptr), "pack_weights: fp16 planes need both the tensor's amax and its scale record");
+  if (w_scale)
+    pack_weights_h16_kernel<<<ew_grid((int64_t)kh * kw * cin_pad * cout_pad), 256, 0, ST(stream)>>>(
+        w, kh * kw, Cin, Cout, cin_pad, cout_pad, (uint16_t*)wp_hi, (uint16_t*)wp_lo, (uint16_t*)wh_hi, (uint16_t*)wh_lo,
+        amax, w_scale);
+  else
+    pack_weights_kernel<<<ew_grid((int64_t)kh * kw * cin_pad * cout_pad), 256, 0, ST(stream)>>>(
+        w, kh * kw, Cin, Cout, cin_pad, cout_pad, (float*)wp_hi, (float*)wp_lo, (float*)wh_hi, (float*)wh_lo);
   return check_launch("pack_weights");
 }

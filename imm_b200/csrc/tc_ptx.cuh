@@ -136,6 +136,25 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same, kind::f16 (fp16 / bf16 operands, K = 16 per instruction, twice the kind::tf32 rate)
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// kind selected at compile time: F16 = scaled fp16 split planes, else TF32 split planes
+template <bool F16>
+__device__ __forceinline__ void mma_kind(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  if (F16) mma_f16(tmem_d, adesc, bdesc, idesc, accumulate);
+  else mma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
+}
 // mbarrier arrive when all previously issued MMAs of this thread have completed (implies fence::before)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -196,6 +215,23 @@ __device__ __forceinline__ void mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, u
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+__device__ __forceinline__ void mma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <bool F16>
+__device__ __forceinline__ void mma_kind_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  if (F16) mma_f16_pair(tmem_d, adesc, bdesc, idesc, accumulate);
+  else mma_tf32_pair(tmem_d, adesc, bdesc, idesc, accumulate);
 }
 __device__ __forceinline__ void mma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
   asm volatile(
@@ -268,6 +304,29 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn, int b_
          | ((uint32_t)b_mn << 16)        // b_major
          | ((uint32_t)(N >> 3) << 17)    // n_dim
          | ((uint32_t)(M >> 4) << 24);   // m_dim
+}
+
+// Instruction descriptor for kind::f16 with fp16 operands (a_format = b_format = 0 = F16), fp32 accumulate.
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4)                       // c_format = F32
+         | (0u << 7)                     // a_format = F16
+         | (0u << 10)                    // b_format = F16
+         | ((uint32_t)a_mn << 15)        // a_major
+         | ((uint32_t)b_mn << 16)        // b_major
+         | ((uint32_t)(N >> 3) << 17)    // n_dim
+         | ((uint32_t)(M >> 4) << 24);   // m_dim
+}
+template <bool F16>
+__host__ __device__ constexpr uint32_t idesc_kind(int M, int N, int a_mn, int b_mn) {
+  return F16 ? idesc_f16(M, N, a_mn, b_mn) : idesc_tf32(M, N, a_mn, b_mn);
+}
+
+// 256-bit global store of 8 x 32-bit words (16 fp16 values)
+__device__ __forceinline__ void st_global_v8u(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
+                                              uint32_t a5, uint32_t a6, uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3),
+               "r"(a4), "r"(a5), "r"(a6), "r"(a7)
+               : "memory");
 }
 
 }  // namespace ptx

@@ -67,23 +67,33 @@ def renderer_spec(n_filters_render, final_res, n_final_out, start_res=16):
 
 
 class Planes(object):
-  """A split tensor: hi (+ optional lo) fp32 planes of identical shape [N,H,W,Cs]."""
+  """A split tensor: hi (+ optional lo) planes of identical shape [N,H,W,Cs].
+  fp32 planes = TF32 pair; fp16 planes ("H16", include/imm_b200.h) carry `scale`, a view of the tensor's scale record
+  (int32 {e, amax bits}): value = (hi + lo * 2^-11) * 2^-e."""
 
-  def __init__(self, hi, lo=None):
-    self.hi, self.lo = hi, lo
+  def __init__(self, hi, lo=None, scale=None):
+    self.hi, self.lo, self.scale = hi, lo, scale
+
+  @property
+  def h16(self):
+    return self.scale is not None
 
   @staticmethod
-  def alloc(shape, device, lo=True, zero=False):
+  def alloc(shape, device, lo=True, zero=False, scale=None):
     f = torch.zeros if zero else torch.empty
-    return Planes(f(shape, dtype=torch.float32, device=device),
-                  f(shape, dtype=torch.float32, device=device) if lo else None)
+    dt = torch.float16 if scale is not None else torch.float32
+    return Planes(f(shape, dtype=dt, device=device), f(shape, dtype=dt, device=device) if lo else None, scale)
 
   def value(self):
+    """The tensor the planes represent, as fp32 (host-side convenience: eval outputs, sub-builders, tests)."""
+    if self.scale is not None:
+      e = int(self.scale[0].item())
+      return (self.hi.float() + self.lo.float() * (2.0 ** -11)) * (2.0 ** -e)
     return self.hi if self.lo is None else self.hi + self.lo
 
   def half(self, i, B):
     """i-th batch half of a [2B,...] tensor."""
-    return Planes(self.hi[i * B:(i + 1) * B], None if self.lo is None else self.lo[i * B:(i + 1) * B])
+    return Planes(self.hi[i * B:(i + 1) * B], None if self.lo is None else self.lo[i * B:(i + 1) * B], self.scale)
 
 
 class ConvLayer(object):
@@ -97,7 +107,9 @@ class ConvLayer(object):
     self.Ho, self.Wo = -(-H // stride), -(-W // stride)
     self.bn, self.relu, self.up2x, self.needs_dgrad, self.trainable = bn, relu, up2x, needs_dgrad, trainable
     self.cin_pad = round_up(cin, 32)
-    self.ycs = round_up(cout, 4)          # channel stride of y / dy (TMA needs 16-byte pixel strides)
+    self.ycs = round_up(cout, 4)          # channel stride of y / dy (TMA needs 16-byte pixel strides; 8 channels for fp16 planes)
+    self.h16 = False                      # operands (x, dy, packed weights) are scaled fp16 planes (IMMEngine._pick_formats)
+    self.w_scale = self.w_amax = None
     self.pad_t = same_pad(H, k, stride)[0]
     self.pad_l = same_pad(W, k, stride)[0]
     self.epilogue = epilogue
@@ -105,16 +117,31 @@ class ConvLayer(object):
     self.precision_override = None
     self.x_layout = _lib.XLAYOUT_NHWC
 
-  def desc(self, N=None):
+  def precision(self):
+    if self.precision_override is not None:
+      return self.precision_override
+    if self.eng.h16 and not self.h16:
+      return _lib.PREC_TF32X3               # a layer without fp16-plane kernels inside an fp16 engine
+    return self.eng.precision
+
+  def desc(self, N=None, x=None, y=None):
+    """x / y: the Planes this call reads as input activations / touches as output-side planes (y of a forward call
+    that writes planes, dy of dgrad / wgrad); their scale records travel in the descriptor (H16 layers only)."""
     d = ConvDesc()
     d.N, d.H, d.W, d.Cin = (self.N if N is None else N), self.H, self.W, self.cin
     d.Cout, d.kh, d.kw, d.stride = self.cout, self.k, self.k, self.stride
     d.Ho, d.Wo, d.pad_t, d.pad_l = self.Ho, self.Wo, self.pad_t, self.pad_l
     d.x_cstride, d.y_cstride, d.cin_pad = self.xcs, self.ycs, self.cin_pad
     d.epilogue = self.epilogue
-    d.precision = self.eng.precision if self.precision_override is None else self.precision_override
+    d.precision = self.precision()
     d.engine = self.eng.engine if self.engine_override is None else self.engine_override
     d.x_layout = self.x_layout
+    if self.h16:
+      d.w_scale = self.w_scale.data_ptr()
+      if x is not None and x.scale is not None:
+        d.x_scale = x.scale.data_ptr()
+      if y is not None and y.scale is not None:
+        d.y_scale = y.scale.data_ptr()
     return d
 
   def engines(self):
@@ -129,7 +156,7 @@ class IMMEngine(object):
   n_maps, n_filters, n_filters_render, gauss_std, gauss_mode, renderer_stride, min_res, loss_mask,
   channels_bug_fix, perceptual.comp, reconstruction_loss, perceptual.l2."""
 
-  def __init__(self, config, batch, image_size=128, device='cuda:0', precision=_lib.PREC_TF32X3,
+  def __init__(self, config, batch, image_size=128, device='cuda:0', precision=None,
                engine=_lib.ENGINE_AUTO, world_size=1, vgg_tf32_weights=True, streams=None, use_graph=None):
     if not torch.cuda.is_available():
       raise _lib.ImmbError('IMMEngine needs a CUDA device; there is no CPU fallback')
@@ -137,13 +164,24 @@ class IMMEngine(object):
     self.cfg = config
     self.B, self.R = int(batch), int(image_size)
     self.dev = torch.device(device)
+    if precision is None:
+      # default: scaled fp16 split operands on the tensor cores (IMMB_PREC_F16X3; every layer without an fp16-plane
+      # kernel stays on 3xTF32); IMMB_PRECISION=tf32x3 selects the all-TF32 engine.  The SIMT cross-check engine reads
+      # fp32 planes only.
+      name = os.environ.get('IMMB_PRECISION', 'f16x3').lower()
+      precision = {'f16x3': _lib.PREC_F16X3, 'tf32x3': _lib.PREC_TF32X3, 'tf32': _lib.PREC_TF32}[name]
+      if engine == _lib.ENGINE_SIMT:
+        precision = _lib.PREC_TF32X3
+    if precision == _lib.PREC_F16X3 and engine == _lib.ENGINE_SIMT:
+      raise _lib.ImmbError('the SIMT engine reads fp32 planes: use a TF32 precision with it')
     self.precision, self.engine = precision, engine
+    self.h16 = precision == _lib.PREC_F16X3
     self.world_size = world_size
     # The frozen VGG16 weights are rounded to TF32 (round-to-nearest-even) once at load: their lo plane is then
     # exactly zero and the tower runs the 2-pass IMMB_PREC_TF32X2 product (hi*w + lo*w) instead of 3 passes.
     # Effect of the rounding, measured against the fp64 oracle with exact weights: loss 1e-7, level losses <= 1.6e-4,
     # weight gradients 1.7e-4 (median) -- below fp32's own rounding noise on this problem.
-    self.vgg_tf32_weights = bool(vgg_tf32_weights) and precision == _lib.PREC_TF32X3
+    self.vgg_tf32_weights = bool(vgg_tf32_weights) and precision in (_lib.PREC_TF32X3, _lib.PREC_F16X3)
     self.K = int(config.n_maps)
     if config.gauss_mode != 'rot':
       raise _lib.ImmbError("only gauss_mode 'rot' (used by every shipped config) is built; got %r" % config.gauss_mode)
@@ -159,7 +197,13 @@ class IMMEngine(object):
     self.inv_std = 1.0 / float(config.gauss_std)
     self.global_step = -1.0           # scripts/train.py:87-89,192: initialised to --reset-global-step (default -1)
     self.adam_t = 0
+    # H16 scale records (include/imm_b200.h "H16 planes"): one int32 {e, amax bits} per fp16 tensor
+    self.scale_recs = torch.zeros((768, 2), dtype=torch.int32, device=self.dev)
+    self.n_scale_recs = 0
+    self.h16_overflow = torch.zeros(1, dtype=torch.int32, device=self.dev)
+    self._scale_mode, self._mode_scales, self._calibrating = None, {}, False
     self._build_layers()
+    self._pick_formats()
     self._alloc_params()
     self._alloc_buffers()
     self.vgg_loaded = False
@@ -247,6 +291,43 @@ class IMMEngine(object):
         self.vgg_seq.append(('conv', L, cin, size))
         cin = cout
 
+  def _new_scale(self, enable=True):
+    """A fresh scale record (view of two int32) or None."""
+    if not enable:
+      return None
+    i = self.n_scale_recs
+    self.n_scale_recs += 1
+    assert i < self.scale_recs.shape[0]
+    return self.scale_recs[i]
+
+  def _vgg_convs(self):
+    return [item for kind, item, cin, size in self.vgg_seq if kind == 'conv']
+
+  def _pick_formats(self):
+    """Which layers run on scaled fp16 planes: every conv whose forward, dgrad (if needed) and wgrad (if trainable) all
+    have an fp16-plane tensor-core kernel (the stride-1 3x3 layers and the frozen tower); the 7x7 first layers, the
+    stride-2 layers and the 1x1 heat-map conv stay on 3xTF32.  The planes BETWEEN two layers take the consumer's format."""
+    if not self.h16:
+      return
+    lib = _lib.lib()
+
+    def eligible(L):
+      if L.x_layout != _lib.XLAYOUT_NHWC or L.xcs % 8:
+        return False
+      d = L.desc()
+      d.precision, d.y_cstride = _lib.PREC_F16X3, round_up(L.cout, 8)
+      ops = [0] + ([1] if L.needs_dgrad else []) + ([2] if L.trainable else [])
+      return all(lib.immb_conv_engine_for(d, op) == _lib.ENGINE_TC for op in ops)
+
+    for L in list(self.layers.values()) + self._vgg_convs():
+      if L.name == 'conv1_1' and not L.trainable:
+        continue
+      if eligible(L):
+        L.h16, L.ycs = True, round_up(L.cout, 8)
+    convs = self._vgg_convs()
+    if len(convs) > 1 and convs[0].name == 'conv1_1':
+      convs[0].h16 = convs[1].h16            # conv1_1 has its own CUDA-core kernels: only its planes follow conv1_2
+
   def _alloc_params(self):
     dev = self.dev
     names, shapes, wds = [], [], []
@@ -288,6 +369,7 @@ class IMMEngine(object):
     self.tensor_wd = torch.tensor(wds, dtype=torch.float32, device=dev)
     self.n_tensors = len(names)
     self.sq = torch.zeros(2 * self.n_tensors, dtype=torch.float64, device=dev)     # [sq ; wsq]
+    self.w_amax = torch.zeros(self.n_tensors, dtype=torch.float32, device=dev)     # per-tensor max |p| (fp16 weight scaling)
     # non-trainable state: BN moving stats + loss normalisers
     bnames, bshapes = [], []
     for key, L in self.layers.items():
@@ -309,6 +391,8 @@ class IMMEngine(object):
     # per-layer handles
     for key, L in self.layers.items():
       L.w, L.b = self.params['%s/%s/w' % (key, L.name)], self.params['%s/%s/b' % (key, L.name)]
+      t = names.index('%s/%s/w' % (key, L.name))
+      L.w_amax = self.w_amax[t:t + 1]
       L.dw, L.db = self.grads['%s/%s/w' % (key, L.name)], self.grads['%s/%s/b' % (key, L.name)]
       if L.bn:
         pre = '%s/batch_normalization/' % key
@@ -324,10 +408,10 @@ class IMMEngine(object):
       L.wh = Planes(None, None)
       L.stage = Planes.alloc((L.N, L.H, L.W + 8, 4), dev)
       return
-    L.wp = Planes(e((taps, L.cout, L.cin_pad), dtype=torch.float32, device=dev),
-                  e((taps, L.cout, L.cin_pad), dtype=torch.float32, device=dev))
-    L.wh = Planes(e((taps, L.cin_pad, L.ycs), dtype=torch.float32, device=dev),
-                  e((taps, L.cin_pad, L.ycs), dtype=torch.float32, device=dev))
+    dt = torch.float16 if L.h16 else torch.float32
+    L.w_scale = self._new_scale(L.h16)
+    L.wp = Planes(e((taps, L.cout, L.cin_pad), dtype=dt, device=dev), e((taps, L.cout, L.cin_pad), dtype=dt, device=dev))
+    L.wh = Planes(e((taps, L.cin_pad, L.ycs), dtype=dt, device=dev), e((taps, L.cin_pad, L.ycs), dtype=dt, device=dev))
 
   def _alloc_buffers(self):
     dev, B, R, K = self.dev, self.B, self.R, self.K
@@ -344,12 +428,13 @@ class IMMEngine(object):
       cur[key] += n
       return v
     f64z = lambda n: torch.zeros(n, dtype=torch.float64, device=dev)
-    self.joint = Planes.alloc((B, 16, 16, self.Cj), dev, zero=True)     # pad channels stay zero
+    ns = self._new_scale
+    self.joint = Planes.alloc((B, 16, 16, self.Cj), dev, zero=True, scale=ns(self.ren_layers[0].h16))     # pad channels stay zero
     ws_bytes = 0
     for key, L in self.layers.items():
       self._alloc_weight_planes(L)
       L.y = torch.zeros((B, L.Ho, L.Wo, L.ycs), dtype=torch.float32, device=dev)
-      L.dy = Planes.alloc((B, L.Ho, L.Wo, L.ycs), dev, zero=True)
+      L.dy = Planes.alloc((B, L.Ho, L.Wo, L.ycs), dev, zero=True, scale=ns(L.h16))
       L.dbias_acc = take(self.bwd_pool, 'b', L.cout)
       if L.bn:
         L.sums, L.bsums = take(self.fwd_pool, 'f', 2 * L.cout), take(self.bwd_pool, 'b', 2 * L.cout)
@@ -359,39 +444,46 @@ class IMMEngine(object):
         L.dx = torch.zeros((B, L.H, L.W, L.xcs), dtype=torch.float32, device=dev)
       ws_bytes = max(ws_bytes, int(call('immb_conv2d_wgrad_workspace', L.desc())))
     # activation planes: output of each trainable block
+    # activation planes take the CONSUMER's format
     for enc in ('image_encoder', 'pose_encoder'):
-      for i, L in enumerate(self.enc_layers[enc]):
-        last = i == len(self.enc_layers[enc]) - 1
+      lst = self.enc_layers[enc]
+      for i, L in enumerate(lst):
+        last = i == len(lst) - 1
         if enc == 'image_encoder' and last and L.Ho == 16:
           L.out, L.ocs = self.joint, self.Cj               # written straight into the concat buffer
         else:
-          L.out, L.ocs = Planes.alloc((B, L.Ho, L.Wo, L.cout), dev), L.cout
+          consumer = lst[i + 1] if not last else (self.pose_conv if enc == 'pose_encoder' else self.ren_layers[0])
+          L.out, L.ocs = Planes.alloc((B, L.Ho, L.Wo, L.cout), dev, scale=ns(consumer.h16)), L.cout
     if self.enc_out_size != 16:
       self.g_enc_resized = f32(B, self.enc_out_size, self.enc_out_size, self.enc_feat)
-    for L in self.ren_layers:
+    for i, L in enumerate(self.ren_layers):
       if L.bn:
         s = 2 if L.up2x else 1
-        L.out, L.ocs = Planes.alloc((B, L.Ho * s, L.Wo * s, L.cout), dev), L.cout
+        L.out, L.ocs = Planes.alloc((B, L.Ho * s, L.Wo * s, L.cout), dev, scale=ns(self.ren_layers[i + 1].h16)), L.cout
     S = self.enc_out_size
     self.mu, self.py, self.px = f32(B, K, 2), f32(B, S, K), f32(B, S, K)
     self.Kp = self.pose_conv.ycs
     self.g_heat = torch.zeros((B, S, S, self.Kp), dtype=torch.float32, device=dev)
     # perceptual tower
-    self.vgg_in = Planes.alloc((2 * B, R, R, 12), dev)        # 3x3 patches of the normalised gray image
+    self.vgg_in = Planes.alloc((2 * B, R, R, 12), dev)        # 3x3 patches of the normalised gray image (SIMT engine only)
     self.vgg_act = OrderedDict()
-    for kind, item, cin, size in self.vgg_seq:
+    for idx, (kind, item, cin, size) in enumerate(self.vgg_seq):
+      later = [it for k, it, _, _ in self.vgg_seq[idx + 1:] if k == 'conv']
       if kind == 'conv':
         L = item
         self._alloc_weight_planes(L)
         L.w = f32(L.k, L.k, L.cin, L.cout)
         L.b = f32(L.cout)
-        L.out = Planes.alloc((2 * B, size, size, L.cout), dev)
-        L.dy = Planes.alloc((B, size, size, L.cout), dev)        # pred half only
+        L.w_amax = torch.zeros(1, dtype=torch.float32, device=dev)
+        consumer = later[0] if later else L
+        L.out = Planes.alloc((2 * B, size, size, L.cout), dev, scale=ns(consumer.h16))
+        L.dy = Planes.alloc((B, size, size, L.cout), dev, scale=ns(L.h16))        # pred half only
         L.dx = torch.zeros((B, size, size, L.xcs), dtype=torch.float32, device=dev)
         self.vgg_act[L.name] = L.out
         ws_bytes = max(ws_bytes, 0)
       else:
-        self.vgg_act[item] = Planes.alloc((2 * B, size // 2, size // 2, cin), dev)
+        fmt = later[0].h16 if later else False
+        self.vgg_act[item] = Planes.alloc((2 * B, size // 2, size // 2, cin), dev, scale=ns(fmt))
     self.g_pool = {item: f32(B, size, size, cin) for kind, item, cin, size in self.vgg_seq if kind == 'pool'}
     self.level_acc = take(self.fwd_pool, 'f', len(self.comp))
     counts = []
@@ -406,7 +498,7 @@ class IMMEngine(object):
     self.coef = f32(len(self.comp))
     self.rec_loss, self.weights_loss, self.total_loss = f32(1), f32(1), f32(1)
     self.pcs = self.ren_layers[-1].ycs      # channel stride of the renderer output / its gradient
-    self.pred_dy = Planes.alloc((B, R, R, self.pcs), dev, zero=True)
+    self.pred_dy = Planes.alloc((B, R, R, self.pcs), dev, zero=True, scale=ns(self.ren_layers[-1].h16))
     self.workspace = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
     # scratch of the two-level (deterministic, atomic-free) BN reductions
     n_scr = max([int(call('immb_bn_scratch_elems', L.N * L.Ho * L.Wo, L.cout)) for L in self.layers.values() if L.bn] + [16])
@@ -442,6 +534,7 @@ class IMMEngine(object):
     self.flat_v.zero_()
     self.adam_t = 0
     self.global_step = -1.0
+    self._invalidate_scales()
     self.repack_weights()
 
   def load_state(self, params=None, buffers=None, adam_m=None, adam_v=None):
@@ -452,6 +545,7 @@ class IMMEngine(object):
       for k, v in src.items():
         if k in dst:
           dst[k].copy_(torch.as_tensor(v, dtype=torch.float32).reshape(dst[k].shape))
+    self._invalidate_scales()
     self.repack_weights()
 
   def load_vgg_caffe_dict(self, data):
@@ -498,11 +592,18 @@ class IMMEngine(object):
     assert tuple(W.shape) == (3, 3, cin_true, L.cout), 'Incorrect weights shape for %s' % L.name   # vgg16.py:171
     W = np.ascontiguousarray(W, dtype=np.float32)
     if self.vgg_tf32_weights and L.name != 'conv1_1':      # conv1_1 runs in exact fp32 on the CUDA cores
-      bits = W.view(np.uint32).astype(np.uint64)
-      bits = (bits + 0x0FFF + ((bits >> 13) & 1)) & 0xFFFFE000          # round-to-nearest-even to 10 mantissa bits
-      W = bits.astype(np.uint32).view(np.float32)
-      L.precision_override = _lib.PREC_TF32X2
+      if L.h16:
+        # scaled fp16 planes: the pair kernel's 2-pass product reads the hi weight plane only, i.e. the weights rounded
+        # to fp16's 11 significant bits (the same width as TF32) -- the rounding happens in immb_pack_weights
+        L.precision_override = _lib.PREC_F16X2
+      else:
+        bits = W.view(np.uint32).astype(np.uint64)
+        bits = (bits + 0x0FFF + ((bits >> 13) & 1)) & 0xFFFFE000          # round-to-nearest-even to 10 mantissa bits
+        W = bits.astype(np.uint32).view(np.float32)
+        L.precision_override = _lib.PREC_TF32X2
     L.w.copy_(torch.from_numpy(W).reshape(L.w.shape))
+    L.w_amax.fill_(float(np.abs(W).max()))
+    self._invalidate_scales()
     L.b.copy_(torch.from_numpy(np.ascontiguousarray(bias, dtype=np.float32)))
     self.vgg_params['SelfSupReconstructionLoss/vgg16/%s/weights' % L.name] = L.w.view(3, 3, cin_true, L.cout)
     self.vgg_params['SelfSupReconstructionLoss/vgg16/%s/biases' % L.name] = L.b
@@ -513,17 +614,78 @@ class IMMEngine(object):
       call('immb_pack_weights_rowwin', L.w, L.cout, L.wp.hi, L.wp.lo, _lib.stream_ptr())
       return
     call('immb_pack_weights', L.w, L.k, L.k, L.cin, L.cout, L.cin_pad, L.ycs, L.wp.hi, L.wp.lo, L.wh.hi, L.wh.lo,
-         _lib.stream_ptr())
+         L.w_amax if L.h16 else None, L.w_scale if L.h16 else None, _lib.stream_ptr())
 
-  def repack_weights(self):
+  def repack_weights(self, amax_current=False):
+    """Rebuilds the tensor-core weight planes from the master weights.  fp16 planes are scaled by each tensor's largest
+    magnitude: the optimiser kernel leaves it in w_amax (amax_current), otherwise it is measured here."""
+    if self.h16 and not amax_current:
+      self.w_amax.zero_()
+      call('immb_multi_amax', self.flat_p, self.chunk_tensor, self.chunk_off, self.chunk_len, self.n_chunks, self.w_amax,
+           _lib.stream_ptr())
     for L in self.layers.values():
       self._pack(L)
 
   # ------------------------------------------------------------------------------------------------
+  # H16 scale records: delayed scaling + calibration
+  # ------------------------------------------------------------------------------------------------
+  def _invalidate_scales(self):
+    self._scale_mode, self._mode_scales = None, {}
+
+  def _scale_update(self):
+    """Turns the maxima observed since the last update into the next exponents (include/imm_b200.h).  Runs at the START of
+    a forward pass, when no fp16 activation / gradient tensor of the previous step is live any more."""
+    if self.h16 and self.n_scale_recs:
+      call('immb_scale_update', self.scale_recs, self.n_scale_recs, self.h16_overflow, _lib.stream_ptr())
+
+  def _enter_scale_mode(self, image, future_image, mask, training, build_loss):
+    """The exponents of the activation planes depend on what flows through the network: training-mode batch statistics
+    vs inference-mode moving statistics, with or without a backward pass.  Each mode keeps its own set of exponents:
+    switching modes (the periodic test pass of train_loop) stashes / restores them; a mode seen for the first time is
+    calibrated by dry passes over the given inputs (model state is restored afterwards), repeated until the exponents
+    stop moving, because a tensor written with a far-off exponent is only approximately right and so is everything
+    computed from it."""
+    mode = (bool(training), bool(build_loss))
+    with_backward = mode == (True, True)          # a training forward with the loss is followed by backward()
+    if self._scale_mode == mode or self._calibrating:
+      return
+    if self._scale_mode is not None:
+      self._mode_scales[self._scale_mode] = self.scale_recs.clone()
+    if mode in self._mode_scales:
+      self.scale_recs.copy_(self._mode_scales[mode])
+      self._scale_mode = mode
+      return
+    if (mode[0], True) in self._mode_scales:     # same statistics mode without the loss: a subset of a calibrated mode
+      self.scale_recs.copy_(self._mode_scales[(mode[0], True)])
+      self._scale_mode = mode
+      return
+    self._calibrating = True
+    try:
+      saved = (self.flat_bn.clone(), self.agg.clone())
+      prev = None
+      for it in range(8):
+        self.forward(image, future_image, mask, training=training, build_loss=build_loss)
+        if with_backward:
+          self.backward()
+        self._scale_update()
+        cur = self.scale_recs[:self.n_scale_recs, 0].clone()
+        self.flat_bn.copy_(saved[0])
+        self.agg.copy_(saved[1])
+        if prev is not None and int((cur - prev).abs().max().item()) <= 1:
+          break
+        prev = cur
+      self.h16_overflow.zero_()
+      self.calibration_passes = it + 1
+    finally:
+      self._calibrating = False
+    self._scale_mode = mode
+
+  # ------------------------------------------------------------------------------------------------
   # forward
   # ------------------------------------------------------------------------------------------------
-  def _conv_fwd(self, L, X, y_hi, y_lo=None, N=None):
-    call('immb_conv2d_fwd', L.desc(N), X.hi, X.lo, L.w, L.wp.hi, L.wp.lo, L.b, y_hi, y_lo, _lib.stream_ptr())
+  def _conv_fwd(self, L, X, y_hi, y_lo=None, N=None, Y=None):
+    """Y: the output Planes when the result is written as split planes (their scale record goes into the descriptor)."""
+    call('immb_conv2d_fwd', L.desc(N, x=X, y=Y), X.hi, X.lo, L.w, L.wp.hi, L.wp.lo, L.b, y_hi, y_lo, _lib.stream_ptr())
 
   def _event(self, key):
     ev = self._events.get(key)
@@ -552,7 +714,7 @@ class IMMEngine(object):
     fused_stats = bool(L.bn and training and self.fuse_bn_stats and L.stats_rows > 0)
     if fused_stats:
       # batch statistics accumulated in the conv epilogue (per-CTA partial rows -> fixed-order second level)
-      call('immb_conv2d_fwd_bnstats', L.desc(), X.hi, X.lo, L.wp.hi, L.wp.lo, L.b, L.y, sc, sc.numel(), st)
+      call('immb_conv2d_fwd_bnstats', L.desc(x=X), X.hi, X.lo, L.wp.hi, L.wp.lo, L.b, L.y, sc, sc.numel(), st)
       call('immb_bn_stats_from_partials', sc, L.stats_rows, L.cout, L.sums, st)
     else:
       self._conv_fwd(L, X, L.y)
@@ -564,7 +726,7 @@ class IMMEngine(object):
     call('immb_bn_finalize', L.sums, npix, L.cout, L.gamma, L.beta, L.mm, L.mv, 1 if training else 0,
          L.scale, L.shift, L.mean, L.invstd, st)
     call('immb_bn_apply', L.y, L.N, L.Ho, L.Wo, L.cout, L.ycs, L.scale, L.shift, 1 if L.relu else 0,
-         1 if L.up2x else 0, L.out.hi, L.out.lo, L.ocs, st)
+         1 if L.up2x else 0, L.out.hi, L.out.lo, L.ocs, L.out.scale, st)
     return L.out
 
   def forward(self, image, future_image, mask=None, training=True, build_loss=True):
@@ -577,6 +739,9 @@ class IMMEngine(object):
     if self.use_mask and mask is None and build_loss:
       raise RuntimeError('No loss mask recieved but is required.')      # imm_model.py:363-367
     self.training = training
+    if self.h16:
+      self._enter_scale_mode(image, future_image, mask, training, build_loss)
+      self._scale_update()
     self.fwd_pool.zero_()
     self._gt_tower_forked = False
     if self.gt_stream is not None and build_loss and self.vgg_loaded and self.engine != _lib.ENGINE_SIMT:
@@ -603,7 +768,7 @@ class IMMEngine(object):
       self._block_fwd(self.pose_conv, pose_last.out, training, scratch)
       S = self.enc_out_size
       call('immb_softargmax_gauss_fwd', self.pose_conv.y, B, S, K, self.Kp, self.inv_std, self.mu, self.py, self.px, 16,
-           self.joint.hi, self.joint.lo, self.Cj, self.enc_feat, _lib.stream_ptr())
+           self.joint.hi, self.joint.lo, self.Cj, self.enc_feat, self.joint.scale, _lib.stream_ptr())
 
     if self.pose_stream is not None:
       self._fork(self.pose_stream, 'fwd_fork')
@@ -614,7 +779,7 @@ class IMMEngine(object):
     if self.enc_out_size != 16:     # imm_model.py:324-335: resize_bilinear(align_corners=True) to the render size
       S = self.enc_out_size
       call('immb_resize_ac_fwd', img_last.out.hi, img_last.out.lo, img_last.cout, B, S, S, self.enc_feat, 16, 16,
-           self.joint.hi, self.joint.lo, self.Cj, st)
+           self.joint.hi, self.joint.lo, self.Cj, img_last.out.scale, self.joint.scale, st)
     if self.pose_stream is not None:
       self._join(self.pose_stream, 'fwd_join')
     else:
@@ -649,9 +814,9 @@ class IMMEngine(object):
         if item.name == 'conv1_1' and fused_first:
           # Cin = 1: HBM-bound, exact-fp32 CUDA-core kernel straight from the RGB inputs (no patch tensor)
           call('immb_vgg_conv1_1_fused', self.future_image, None if which == 0 else self.pred, self.pcs, B, R,
-               item.w, item.b, item.cout, item.out.hi, item.out.lo, 0 if which is None else which + 1, st)
+               item.w, item.b, item.cout, item.out.hi, item.out.lo, 0 if which is None else which + 1, item.out.scale, st)
         else:
-          self._conv_fwd(item, X, out.hi, out.lo, N=n)
+          self._conv_fwd(item, X, out.hi, out.lo, N=n, Y=out)
         X = out
         prev_conv = item.name
       else:
@@ -660,10 +825,10 @@ class IMMEngine(object):
         if lvl is not None and cin % 4 == 0:
           # this level feeds a pool: its masked squared-difference sum rides in the pool kernel
           call('immb_maxpool2x2_fwd_levelsum', X.hi, X.lo, B, size, size, cin, O.hi, O.lo, self.mask, R,
-               self.level_acc[lvl:], st)
+               self.level_acc[lvl:], X.scale, O.scale, st)
           self._levels_done.add(lvl)
         else:
-          call('immb_maxpool2x2_fwd', X.hi, X.lo, n, size, size, cin, O.hi, O.lo, st)
+          call('immb_maxpool2x2_fwd', X.hi, X.lo, n, size, size, cin, O.hi, O.lo, X.scale, O.scale, st)
         X = O
 
   def _loss_fwd(self, training):
@@ -684,13 +849,13 @@ class IMMEngine(object):
         continue
       if nm == 'input':
         call('immb_perceptual_level_sum', self.future_image, None, 3, self.pred, None, self.pcs, B, R, R, 3,
-             self.mask, R, self.level_acc[k:], st)
+             self.mask, R, self.level_acc[k:], None, st)
       else:
         P = self.vgg_act[nm]
         h, w, C = P.hi.shape[1], P.hi.shape[2], P.hi.shape[3]
         g, p = P.half(0, B), P.half(1, B)
         call('immb_perceptual_level_sum', g.hi, g.lo, C, p.hi, p.lo, C, B, h, w, C, self.mask, R,
-             self.level_acc[k:], st)
+             self.level_acc[k:], P.scale, st)
     call('immb_perceptual_finalize', self.level_acc, self.level_counts, len(self.comp), self.agg,
          1 if training else 0, self.levels, self.rec_loss, self.coef, st)
 
@@ -701,7 +866,7 @@ class IMMEngine(object):
     call('immb_adam_norms', self.flat_p, self.flat_g, self.n_flat, self.chunk_tensor, self.chunk_off,
          self.chunk_len, self.n_chunks, self.tensor_wd, 1.0, self.sq, self.sq[self.n_tensors:], st)
     call('immb_total_loss', self.rec_loss, self.sq[self.n_tensors:], self.tensor_wd, self.n_tensors,
-         self.weights_loss, self.total_loss, st)
+         self.weights_loss, self.total_loss, self.h16_overflow if self.h16 else None, st)
     return self.total_loss
 
   # ------------------------------------------------------------------------------------------------
@@ -727,17 +892,17 @@ class IMMEngine(object):
         call('immb_bn_bwd_reduce', g, gcs, L.y, L.cout, npix, L.cout, L.scale, L.shift, L.mean, L.invstd, relu,
              L.bsums, sc, sc.numel(), st)
       call('immb_bn_bwd_apply', g, gcs, L.y, L.cout, npix, L.cout, L.scale, L.shift, L.mean, L.invstd, relu,
-           L.bsums, L.dy.hi, L.dy.lo, L.dgamma, L.dbeta, L.dbias_acc, sc, sc.numel(), st)
+           L.bsums, L.dy.hi, L.dy.lo, L.dgamma, L.dbeta, L.dbias_acc, sc, sc.numel(), L.dy.scale, st)
       dy = L.dy
     else:
       dy = g if isinstance(g, Planes) else None
       if dy is None:
         assert gcs == L.ycs
-        call('immb_split_planes', g, L.dy.hi, L.dy.lo, npix * L.ycs, st)
+        call('immb_split_planes', g, L.dy.hi, L.dy.lo, npix * L.ycs, L.dy.scale, st)
         dy = L.dy
-      call('immb_bias_grad', dy.hi, dy.lo, L.ycs, npix, L.cout, L.dbias_acc, st)
+      call('immb_bias_grad', dy.hi, dy.lo, L.ycs, npix, L.cout, L.dbias_acc, dy.scale, st)
     call('immb_cast_d2f', L.dbias_acc, L.db, L.cout, st)
-    d = L.desc()
+    d = L.desc(x=L.x, y=dy)
     if self.wgrad_stream is not None:
       # dw is consumed by the optimiser only: the wgrad runs on its own stream behind the kernel that produced dy
       self._fork(self.wgrad_stream, ('wg', id(L)))
@@ -778,23 +943,24 @@ class IMMEngine(object):
         _lib.TAG = 'bwd:vgg/%s' % L.name
         if fused_dy is not L:
           call('immb_vgg_bwd_combine', g, fg.hi, fg.lo, fp.hi, fp.lo, B, size, size, L.cout, self.mask, R, coef,
-               L.dy.hi, L.dy.lo, st)
+               L.dy.hi, L.dy.lo, P.scale, L.dy.scale, st)
         fused_dy = None
         # producer of this conv's input: when it is a conv without a loss level, its dy = dgrad * [act > 0] is written
         # by this dgrad's epilogue (no fp32 gradient round trip, no combine launch)
         prev = seq[idx - 1] if idx > 0 else None
-        d = L.desc(B)
+        d = L.desc(B, y=L.dy)
         if (L.name == 'conv1_1' and self.fuse_level_sums and self.engine != _lib.ENGINE_SIMT and R % 16 == 0
                 and L.cout == 64 and 'input' in level_of):
           # conv1_1 dgrad + gray/normalise adjoint + the 'input' level's term: the renderer-output gradient in one kernel
           call('immb_vgg_conv1_1_bwd_fused', L.dy.hi, L.dy.lo, L.w, L.cout, self.future_image, self.pred, self.pcs,
-               self.mask, self.coef[level_of['input']:], B, R, self.pred_dy.hi, self.pred_dy.lo, st)
+               self.mask, self.coef[level_of['input']:], B, R, self.pred_dy.hi, self.pred_dy.lo, L.dy.scale,
+               self.pred_dy.scale, st)
           return self.pred_dy
         if (prev is not None and prev[0] == 'conv' and prev[1].name not in level_of
                 and _lib.lib().immb_conv2d_dgrad_relu_supported(d)):
           Lp = prev[1]
           call('immb_conv2d_dgrad_relu', d, L.dy.hi, L.dy.lo, L.wh.hi, L.wh.lo, Lp.out.half(1, B).hi, Lp.cout,
-               Lp.dy.hi, Lp.dy.lo, st)
+               Lp.dy.hi, Lp.dy.lo, Lp.dy.scale, st)
           fused_dy, g = Lp, None
         else:
           call('immb_conv2d_dgrad', d, L.dy.hi, L.dy.lo, L.w, L.wh.hi, L.wh.lo, L.dx, st)
@@ -811,7 +977,7 @@ class IMMEngine(object):
           fgp = prev.out.half(0, B)
           coef_p = self.coef[level_of[prev.name]:] if prev.name in level_of else None
           call('immb_maxpool2x2_bwd_combine', g, fgp.hi, fgp.lo, xin.hi, xin.lo, B, size, size, cin, self.mask, R,
-               coef_p, prev.dy.hi, prev.dy.lo, st)
+               coef_p, prev.dy.hi, prev.dy.lo, xin.scale, prev.dy.scale, st)
           fused_dy, g = prev, None
         else:
           call('immb_maxpool2x2_bwd', g, xin.hi, xin.lo, B, size, size, cin, self.g_pool[item], st)
@@ -879,16 +1045,21 @@ class IMMEngine(object):
     nt = self.n_tensors
     call('immb_adam_norms', self.flat_p, self.flat_g, self.n_flat, self.chunk_tensor, self.chunk_off,
          self.chunk_len, self.n_chunks, self.tensor_wd, gscale, self.sq, self.sq[nt:], st)
-    call('immb_total_loss', self.rec_loss, self.sq[nt:], self.tensor_wd, nt, self.weights_loss, self.total_loss, st)
+    call('immb_total_loss', self.rec_loss, self.sq[nt:], self.tensor_wd, nt, self.weights_loss, self.total_loss,
+         self.h16_overflow if self.h16 else None, st)
+    amax = None
+    if self.h16:
+      self.w_amax.zero_()
+      amax = self.w_amax                 # max |p| of the updated tensors: the scale of their fp16 weight planes
     if lr_t_dev is None:
       call('immb_adam_apply', self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.n_flat, self.chunk_tensor,
            self.chunk_off, self.chunk_len, self.n_chunks, self.tensor_wd, gscale, self.sq, clip, lr_t, beta1, beta2,
-           eps, st)
+           eps, amax, st)
     else:
       call('immb_adam_apply_dev', self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.n_flat, self.chunk_tensor,
            self.chunk_off, self.chunk_len, self.n_chunks, self.tensor_wd, gscale, self.sq, clip, lr_t_dev, beta1,
-           beta2, eps, st)
-    self.repack_weights()
+           beta2, eps, amax, st)
+    self.repack_weights(amax_current=True)
 
   def _next_lr_t(self, lr, beta1, beta2):
     if lr is None:
@@ -915,6 +1086,10 @@ class IMMEngine(object):
     all-reduce runs between the forward+backward graph and the optimiser graph."""
     if lr is None:
       lr = self.learning_rate(lr_multiple=lr_multiple)
+    if self.h16:
+      # exponents of the training mode (calibrated on first use; restored after an interleaved evaluation pass) -- done
+      # here, eagerly, so that neither graph capture nor graph replay ever contains a mode switch
+      self._enter_scale_mode(image, future_image, mask, True, True)
     if self.use_graph:
       key = (None if clip_value is None else float(clip_value), beta1, beta2, eps, allreduce is not None,
              mask is not None)
@@ -984,6 +1159,12 @@ class IMMEngine(object):
   # ------------------------------------------------------------------------------------------------
   def dtype_string(self):
     """The arithmetic the conv engine computes in (bench.py's `dtype`)."""
+    if self.h16:
+      n16 = sum(1 for L in list(self.layers.values()) + self._vgg_convs() if L.h16)
+      return ('f16x3 (scaled fp16 split operands hi + lo*2^-11 with one power-of-two scale per tensor; tensor-core products '
+              'hi*hi + (hi*lo + lo*hi)*2^-11 at kind::f16, fp32 accumulate: 22 significant bits per operand; %d of %d convs -- '
+              'the stride-1 3x3 layers and the frozen VGG16 tower (2 passes: weights rounded to fp16 planes) -- the 7x7 / '
+              'stride-2 / 1x1 layers run error-compensated 3xTF32)' % (n16, len(self.layers) + len(self._vgg_convs())))
     if self.precision == _lib.PREC_TF32:
       return 'tf32 (single pass; does not meet the parity bar)'
     return ('tf32x3 (fp32 storage; error-compensated TF32 tensor-core products hi*hi+hi*lo+lo*hi, fp32 accumulate; '

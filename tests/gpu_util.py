@@ -15,7 +15,7 @@ def rel_err(a, b):
   return float((a - b).norm()) / (n if n > 0 else 1.0)
 
 
-def make_pair(batch=2, n_maps=10, image_size=128, seed=0, precision=_lib.PREC_TF32X3, engine=_lib.ENGINE_AUTO,
+def make_pair(batch=2, n_maps=10, image_size=128, seed=0, precision=None, engine=_lib.ENGINE_AUTO,
               world_size=1):
   """Returns (engine on cuda:0, fp64 oracle state, fp32 oracle state, cpu inputs) with identical parameters."""
   st32 = O.init_state(O.State(n_maps=n_maps, image_size=image_size), seed=seed)
