@@ -729,6 +729,55 @@ class IMMEngine(object):
          1 if L.up2x else 0, L.out.hi, L.out.lo, L.ocs, L.out.scale, st)
     return L.out
 
+  # sections of the forward pass (also the bodies of IMMModel's sub-builders image_encoder / pose_encoder / simple_renderer)
+  def run_encoder(self, enc, inp, training, scratch=None):
+    """IMMModel.encoder (imm_model.py:182-217) of branch `enc` on inp [B,R,R,3]."""
+    B, R = self.B, self.R
+    X = Planes(inp, None)
+    L0 = self.enc_layers[enc][0]
+    if L0.x_layout == _lib.XLAYOUT_ROWWIN4:
+      call('immb_stage_image_rowwin', inp, B, R, R, L0.stage.hi, L0.stage.lo, _lib.stream_ptr())
+      X = L0.stage
+    for L in self.enc_layers[enc]:
+      X = self._block_fwd(L, X, training, scratch)
+    return X
+
+  def run_image_encoder(self, image, training):
+    """image_encoder (imm_model.py:220-230); the 16x16 block lands in channels [0, enc_feat) of the concat buffer
+    (resize_bilinear(align_corners=True) first when the encoder ends above the render size, :324-335)."""
+    self.run_encoder('image_encoder', image, training, None)
+    img_last = self.enc_layers['image_encoder'][-1]
+    if self.enc_out_size != 16:
+      S = self.enc_out_size
+      call('immb_resize_ac_fwd', img_last.out.hi, img_last.out.lo, img_last.cout, self.B, S, S, self.enc_feat, 16, 16,
+           self.joint.hi, self.joint.lo, self.Cj, img_last.out.scale, self.joint.scale, _lib.stream_ptr())
+
+  def run_pose_branch(self, future_image, training, scratch=None):
+    """pose encoder -> heatmaps -> (mu_y, mu_x) -> Gaussian maps into channels [enc_feat, enc_feat+K) of the concat
+    buffer (imm_model.py:233-274,341-344)."""
+    self.run_encoder('pose_encoder', future_image, training, scratch)
+    pose_last = self.enc_layers['pose_encoder'][-1]
+    self._block_fwd(self.pose_conv, pose_last.out, training, scratch)
+    S = self.enc_out_size
+    call('immb_softargmax_gauss_fwd', self.pose_conv.y, self.B, S, self.K, self.Kp, self.inv_std, self.mu, self.py,
+         self.px, 16, self.joint.hi, self.joint.lo, self.Cj, self.enc_feat, self.joint.scale, _lib.stream_ptr())
+
+  def run_renderer(self, training):
+    """simple_renderer (imm_model.py:154-179) on the concat buffer -> self.pred [B,R,R,pcs]."""
+    X = self.joint
+    for L in self.ren_layers:
+      X = self._block_fwd(L, X, training)
+    self.pred = self.ren_layers[-1].y
+    return self.pred
+
+  def load_joint(self, feat16):
+    """Fills the renderer's concat buffer from an explicit [B,16,16,enc_feat+K] tensor (simple_renderer called on its own)."""
+    B, C = self.B, self.enc_feat + self.K
+    assert tuple(feat16.shape) == (B, 16, 16, C), 'renderer input must be [B,16,16,%d]' % C
+    padded = torch.zeros((B, 16, 16, self.Cj), dtype=torch.float32, device=self.dev)
+    padded[..., :C] = feat16.to(self.dev, torch.float32)
+    call('immb_split_planes', padded, self.joint.hi, self.joint.lo, padded.numel(), self.joint.scale, _lib.stream_ptr())
+
   def forward(self, image, future_image, mask=None, training=True, build_loss=True):
     """IMMModel.build (imm_model.py:413-490).  image / future_image [B,R,R,3] fp32 in [0,255]; mask [B,R,R,1]."""
     st = _lib.stream_ptr()
@@ -749,45 +798,17 @@ class IMMEngine(object):
       with torch.cuda.stream(self.gt_stream):
         self._vgg_tower(0)
       self._gt_tower_forked = True
-    # image encoder (imm_model.py:220-230) and pose encoder (:233-248)
-    def run_encoder(enc, inp, scratch):
-      st_ = _lib.stream_ptr()
-      X = Planes(inp, None)
-      L0 = self.enc_layers[enc][0]
-      if L0.x_layout == _lib.XLAYOUT_ROWWIN4:
-        call('immb_stage_image_rowwin', inp, B, R, R, L0.stage.hi, L0.stage.lo, st_)
-        X = L0.stage
-      for L in self.enc_layers[enc]:
-        X = self._block_fwd(L, X, training, scratch)
-
-    def run_pose_branch(scratch):
-      # pose encoder -> heatmaps -> (mu_y, mu_x) -> Gaussian maps into channels [enc_feat, enc_feat+K) of the concat
-      # buffer (imm_model.py:233-274,341-344); the image branch writes channels [0, enc_feat) of the same buffer
-      run_encoder('pose_encoder', future_image, scratch)
-      pose_last = self.enc_layers['pose_encoder'][-1]
-      self._block_fwd(self.pose_conv, pose_last.out, training, scratch)
-      S = self.enc_out_size
-      call('immb_softargmax_gauss_fwd', self.pose_conv.y, B, S, K, self.Kp, self.inv_std, self.mu, self.py, self.px, 16,
-           self.joint.hi, self.joint.lo, self.Cj, self.enc_feat, self.joint.scale, _lib.stream_ptr())
-
+    # image encoder (imm_model.py:220-230) next to the pose branch (:233-274), then the renderer (:154-179)
     if self.pose_stream is not None:
       self._fork(self.pose_stream, 'fwd_fork')
       with torch.cuda.stream(self.pose_stream):
-        run_pose_branch(self.bn_scratch_pose)
-    run_encoder('image_encoder', image, None)
-    img_last = self.enc_layers['image_encoder'][-1]
-    if self.enc_out_size != 16:     # imm_model.py:324-335: resize_bilinear(align_corners=True) to the render size
-      S = self.enc_out_size
-      call('immb_resize_ac_fwd', img_last.out.hi, img_last.out.lo, img_last.cout, B, S, S, self.enc_feat, 16, 16,
-           self.joint.hi, self.joint.lo, self.Cj, img_last.out.scale, self.joint.scale, st)
+        self.run_pose_branch(future_image, training, self.bn_scratch_pose)
+    self.run_image_encoder(image, training)
     if self.pose_stream is not None:
       self._join(self.pose_stream, 'fwd_join')
     else:
-      run_pose_branch(None)
-    # renderer (imm_model.py:154-179)
-    X = self.joint
-    for L in self.ren_layers:
-      X = self._block_fwd(L, X, training)
+      self.run_pose_branch(future_image, training, None)
+    self.run_renderer(training)
     self.pred = self.ren_layers[-1].y           # [B,R,R,pcs]; first 3 channels = future_im_pred (:348-355)
     if build_loss:
       self._loss_fwd(training)

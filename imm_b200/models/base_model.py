@@ -14,6 +14,7 @@ class BaseModel(object):
     self._opts = None
     self._cost_avgs = {}        # name -> EMA value (tf.train.ExponentialMovingAverage(0.99), base_model.py:56-60)
     self._cost_raw = {}
+    self._running = {}          # name -> value of the host-side _exp_running_avg helper
     self.__class__.num_instances += 1
 
   def _decay(self, scope=None):
@@ -21,9 +22,14 @@ class BaseModel(object):
     raise NotImplementedError
 
   def _exp_running_avg(self, x, training_pl, init_val=0.0, rho=0.99, name='x'):
-    """base_model.py:39-50.  The perceptual-loss normalisers `<name>_agg` live in the engine (engine.agg) and
-    are updated by immb_perceptual_finalize when training_pl is True."""
-    raise NotImplementedError('handled on device: immb_perceptual_finalize')
+    """base_model.py:39-50: x_new = agg + (1 - rho) (x - agg); agg <- x_new when training_pl; returns x_new.  Host-side
+    scalar version for callers of the helper; the perceptual-loss normalisers `<level>_agg` of the hot path live in the
+    engine (engine.agg) and are advanced on device by immb_perceptual_finalize."""
+    agg = self._running.get(name + '_agg', float(init_val))
+    x_new = agg + (1.0 - rho) * (float(x) - agg)
+    if training_pl:
+      self._running[name + '_agg'] = x_new
+    return x_new
 
   def _add_cost_summary(self, cost, name):
     """Raw + moving-average cost scalars (base_model.py:52-60); only for the first model instance."""
@@ -48,7 +54,11 @@ class BaseModel(object):
     return lambda: None
 
   def conv_block(self, *args, **kwargs):
-    raise NotImplementedError('conv blocks are scheduled by IMMEngine (nn_utils.py:151-210 semantics)')
+    """base_model.py:96-117 creates the variables of ONE conv block inside a TF graph.  Here every block of the path
+    (shape, packed weight planes, BN scratch) is created by IMMEngine at construction from the reference's layer specs;
+    a free-standing block has no buffers to run on -- documented as graph-only in INTEGRATION.md."""
+    raise NotImplementedError('graph-only helper: conv blocks are instantiated by IMMEngine from the layer specs '
+                              '(nn_utils.py:151-210 semantics); see IMMModel.encoder / simple_renderer for runnable sections')
 
   def build(self, inputs, training_pl):
     raise NotImplementedError

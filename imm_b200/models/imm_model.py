@@ -32,13 +32,14 @@ class IMMModel(BaseModel):
   Extra keyword-only knobs select the device-side execution: `device`, `precision`, `engine`, `world_size`."""
 
   def __init__(self, config, global_step=None, dtype=torch.float32, name='IMMModel', device='cuda:0',
-               precision=_lib.PREC_TF32X3, engine=_lib.ENGINE_AUTO, world_size=1, vgg_data=None, seed=0):
+               precision=None, engine=_lib.ENGINE_AUTO, world_size=1, vgg_data=None, seed=0):
     super(IMMModel, self).__init__(dtype, name)
     self._config = config
     self._global_step = global_step
     self._device, self._precision, self._engine_sel, self._world = device, precision, engine, world_size
     self._vgg_data, self._seed = vgg_data, seed
     self.engine = None
+    self._colors = None
     self._tensors = {}            # the reference's 'tensors' collection (imm_model.py:250,266-267)
 
   # -- construction -----------------------------------------------------------------------------------
@@ -73,11 +74,94 @@ class IMMModel(BaseModel):
       return t.contiguous()
     return t.to(dev, non_blocking=True).contiguous()
 
-  # -- sub-builders kept for API parity; they run the corresponding engine section ------------------------
-  def encoder(self, x, training_pl, var_device='/cpu:0'):
-    raise NotImplementedError('use build(); the encoder stack is scheduled by IMMEngine.forward')
+  # -- sub-builders: each runs the engine section of the same name on its own ---------------------------------
+  # They exist for callers that assemble the model piecewise (imm_model.py:279-357 `model` takes them as callables).
+  # The engine has static shapes and one set of buffers: outputs are views / fresh fp32 copies of engine buffers and
+  # stay valid until the next call.  On an fp16-plane engine the activation exponents must have been calibrated by one
+  # full build() in the same training_pl mode before a section is run on its own.
+  def _section_engine(self, x, training_pl):
+    B, R = int(x.shape[0]), int(x.shape[1])
+    eng = self._ensure_engine(B, R) if x.shape[-1] == 3 else self.engine
+    if eng is None:
+      raise _lib.ImmbError('run build() once before calling a sub-builder on intermediate features')
+    if eng.h16 and eng._scale_mode is None:
+      raise _lib.ImmbError('fp16-plane engine: run one full build() (same training_pl) before a stand-alone sub-builder, '
+                           'so that the activation exponents are calibrated')
+    return eng
 
-  image_encoder = pose_encoder = simple_renderer = encoder
+  @staticmethod
+  def _block_outputs(layers):
+    """The four block outputs of an encoder (after conv_2 / conv_4 / conv_6 / conv_8, imm_model.py:195-216), fp32."""
+    return [L.out.value()[..., :L.cout] for L in layers[1::2]]
+
+  def encoder(self, x, training_pl, var_device='/cpu:0', _branch='image_encoder'):
+    """imm_model.py:182-217 -> [f(R), f(R/2), f(R/4), f(R/8)] block features of x [B,R,R,3]."""
+    eng = self._section_engine(x, training_pl)
+    eng.run_encoder(_branch, self._to_device(x, eng.dev), bool(training_pl))
+    return self._block_outputs(eng.enc_layers[_branch])
+
+  def image_encoder(self, x, training_pl, filters=64, var_device='/cpu:0'):
+    """imm_model.py:220-230: [x] + encoder(x)."""
+    eng = self._section_engine(x, training_pl)
+    eng.run_image_encoder(self._to_device(x, eng.dev), bool(training_pl))
+    return [x] + self._block_outputs(eng.enc_layers['image_encoder'])
+
+  def pose_encoder(self, x, training_pl, n_maps=1, filters=32, gauss_mode='ankush', map_sizes=None, reuse=False,
+                   var_device='/cpu:0'):
+    """imm_model.py:233-276 -> (gauss_mu [B,K,2] (y,x) in [-1,1], [Gaussian maps per size in map_sizes])."""
+    eng = self._section_engine(x, training_pl)
+    if n_maps not in (1, eng.K) or gauss_mode not in ('ankush', 'rot'):
+      raise ValueError('the engine was built for n_maps=%d, gauss_mode=rot' % eng.K)
+    eng.run_pose_branch(self._to_device(x, eng.dev), bool(training_pl))
+    self._tensors = {'heatmaps': eng.pose_conv.y[..., :eng.K], 'gauss_y_prob': eng.py, 'gauss_x_prob': eng.px}
+    maps = [get_gaussian_maps(eng.mu, [sz, sz], eng.inv_std, 'rot') for sz in (map_sizes or [])]
+    return eng.mu, maps
+
+  def simple_renderer(self, feat_heirarchy, training_pl, n_final_out=3, final_res=128, var_device='/cpu:0'):
+    """imm_model.py:154-179: renders feat_heirarchy[16] = [B,16,16,enc_feat+K] -> [B,final_res,final_res,n_final_out]."""
+    eng = self._section_engine(feat_heirarchy[16], training_pl)
+    if final_res != eng.R or n_final_out > eng.n_out:
+      raise ValueError('the engine renders %dx%d images with %d channels' % (eng.R, eng.R, eng.n_out))
+    eng.load_joint(feat_heirarchy[16])
+    return eng.run_renderer(bool(training_pl))[..., :n_final_out]
+
+  def model(self, im, future_im, image_encoder=None, pose_encoder=None, renderer=None):
+    """imm_model.py:279-357 -> (future_im_pred [B,R,R,3], gauss_yx [B,K,2], [pose embedding maps per render size]).
+    The three callables of the reference signature are accepted; the wiring (concat, optional align_corners resize,
+    first three renderer channels) is the engine's forward pass."""
+    B, R = int(future_im.shape[0]), int(future_im.shape[1])
+    eng = self._ensure_engine(B, R)
+    training = bool(self._opts['training_pl']) if self._opts else False
+    eng.forward(self._to_device(im, eng.dev), self._to_device(future_im, eng.dev), None, training=training,
+                build_loss=False)
+    sizes, size = [], R
+    while size >= int(self._config.min_res):            # imm_model.py:296-303
+      sizes.append(size)
+      size //= int(self._config.renderer_stride)
+    return eng.pred[..., :3], eng.mu, [get_gaussian_maps(eng.mu, [sz, sz], eng.inv_std, 'rot') for sz in sizes]
+
+  def loss(self, future_im_pred, future_im, future_yx, future_yx_gmaps, costs_collection, training_pl,
+           loss_mask=None):
+    """imm_model.py:360-405 on the engine's current prediction (future_im_pred must be the tensor model() / build()
+    returned): reconstruction + weight decay, cost summaries registered once."""
+    eng = self.engine
+    if eng is None or future_im_pred.data_ptr() != eng.pred.data_ptr():
+      raise _lib.ImmbError('loss(): future_im_pred must be the prediction the engine just produced')
+    if bool(self._config.loss_mask) and loss_mask is None:
+      raise RuntimeError('No loss mask recieved but is required.')
+    eng.future_image = self._to_device(future_im, eng.dev)
+    eng.mask = self._to_device(loss_mask, eng.dev) if (eng.use_mask and loss_mask is not None) else None
+    eng._gt_tower_forked = False
+    eng.fwd_pool[-len(eng.comp):].zero_()
+    eng._loss_fwd(bool(training_pl))
+    return eng.loss_value().view(())
+
+  def _decay(self, scope=None):
+    """base_model.py:33-37: the sum of the L2 weight-decay terms (device scalar; refreshed by loss_value())."""
+    if self.engine is None:
+      raise _lib.ImmbError('_decay(): the model has not been built')
+    self.engine.loss_value()
+    return self.engine.weights_loss.view(())
 
   def _loss_mask(self, map, mask):
     """imm_model.py:408-410: map * resize_images(mask, map.shape) -- at the integer scales used by the loss the TF1
@@ -113,10 +197,14 @@ class IMMModel(BaseModel):
     if output_tensors:
       tensors = {}
       tensors.update(inputs)
+      from ..utils.summaries import colorize_landmark_maps, get_n_colors
+      if self._colors is None:
+        self._colors = get_n_colors(eng.K)
+      pose_embedding = colorize_landmark_maps(get_gaussian_maps(eng.mu, [R, R], eng.inv_std, 'rot'), self._colors)
       tensors.update({'future_im': fut_d, 'im': im_d,
+                      'pose_embedding': pose_embedding,                     # imm_model.py:463-465,480-485
                       'future_im_pred': eng.pred[..., :3],
-                      'gauss_yx': eng.mu,
-                      'pose_embedding_maps': lambda: get_gaussian_maps(eng.mu, [R, R], eng.inv_std, 'rot')})
+                      'gauss_yx': eng.mu})
       return None, loss, self._avg_ops, tensors
     return None, loss, self._avg_ops
 

@@ -203,3 +203,9 @@ def test_conv_call_attribution_matches_engine_routing():
   assert _lib.conv_info('immb_conv2d_fwd_bnstats', first)['kernel'] == 'conv_tc2_pair_kernel'
   assert _lib.conv_info('immb_conv2d_wgrad', first)['kernel'] == 'conv_tc_wgrad_kernel'
   assert _lib.conv_info('immb_conv2d_fwd', desc(B, 8, 512, 512, 3, 1))['kernel'] == 'conv_tc_kernel'
+  # fp16-plane layers: kind::f16 MMAs; the frozen tower's 2-pass product exists on the pair kernel only
+  h = _lib.conv_info('immb_conv2d_wgrad', desc(B, 64, 64, 64, 3, 1, prec=_lib.PREC_F16X3))
+  assert (h['kernel'], h['kind'], h['passes']) == ('conv_tc2_wgrad16_kernel', 'f16', 3)
+  v = _lib.conv_info('immb_conv2d_fwd', desc(B, 32, 256, 256, 3, 1, prec=_lib.PREC_F16X2))
+  assert (v['kernel'], v['kind'], v['passes']) == ('conv_tc2_pair_kernel', 'f16', 2)
+  assert _lib.conv_info('immb_conv2d_fwd', desc(B, 8, 512, 512, 3, 1, prec=_lib.PREC_F16X2))['passes'] == 3

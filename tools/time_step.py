@@ -6,7 +6,7 @@ from imm_b200.engine import IMMEngine
 from imm_b200.utils.box import default_model_config
 from imm_b200.utils import synthetic as S
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-prec = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+prec = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 engine = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 eng = IMMEngine(default_model_config(10), B, 128, 'cuda:0', precision=prec, engine=engine)
 eng.init_parameters(0); eng.load_vgg_caffe_dict(S.synthetic_vgg_caffe_dict(1))
