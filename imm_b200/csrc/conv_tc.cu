@@ -634,16 +634,20 @@ bool conv_tc_eligible(const immb_conv_desc* d, int op) {
   }
 }
 
-template <int BN, int PASSES, bool F16 = false>
+// SHORT: launches whose CTAs run only a handful of K iterations (the stride-2 dgrad parity classes: <= 4 taps x 1-2
+// chunks, thousands of CTAs) are bound by per-CTA set-up latency, not by the pipeline depth: two stages leave room for
+// two resident CTAs per SM, which overlap each other's prologue / epilogue
+template <int BN, int PASSES, bool F16 = false, bool SHORT = false>
 static int launch_fwd(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                       const CUtensorMap& b_lo, const TcParams& p, dim3 grid, cudaStream_t st) {
-  constexpr int STAGES = PASSES == 3 ? (BN <= 64 ? 4 : 3) : (BN <= 64 ? 6 : 4);
+  constexpr int STAGES = SHORT ? 2 : (PASSES == 3 ? (BN <= 64 ? 4 : 3) : (BN <= 64 ? 6 : 4));
   using Cfg = FwdCfg<BN, PASSES, STAGES>;
   auto kern = conv_tc_kernel<BN, PASSES, STAGES, F16>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "conv_tc smem attr: %s", cudaGetErrorString(e));
+    if (SHORT) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
   kern<<<grid, 192, Cfg::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, p);
@@ -653,6 +657,14 @@ static int launch_fwd(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CU
 static int dispatch_fwd(int bn, int passes, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
                         const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcParams& p, dim3 grid,
                         cudaStream_t st, bool f16 = false) {
+  // longest K loop of any CTA of this launch
+  int max_k = p.n_taps * p.kchunks;
+  for (int c = 1; c < p.n_classes; ++c) max_k = p.n_taps_c[c - 1] * p.kchunks > max_k ? p.n_taps_c[c - 1] * p.kchunks : max_k;
+  if (!f16 && passes == 3 && max_k <= 18 && bn <= 64) {
+    if (bn == 16) return launch_fwd<16, 3, false, true>(a_hi, a_lo, b_hi, b_lo, p, grid, st);
+    if (bn == 32) return launch_fwd<32, 3, false, true>(a_hi, a_lo, b_hi, b_lo, p, grid, st);
+    if (bn == 64) return launch_fwd<64, 3, false, true>(a_hi, a_lo, b_hi, b_lo, p, grid, st);
+  }
   if (f16) {
     if (passes != 3) return set_error(IMMB_ERR_INVALID, "conv_tc: single-pass fp16 is not built");
 #define IMMB_CASE16(BN_) \

@@ -356,7 +356,12 @@ struct Tc2PairCfg {
   // F16: the lo planes carry an extra factor 2^11, so every product with a lo operand (also the single one of the
   // 2-pass frozen-weight product) goes to the cross accumulator and is scaled by 2^-11 when the epilogue adds it.
   static constexpr bool CROSS = PASSES == 3 || (F16 && PASSES == 2);
-  static constexpr int ACC_COLS = CROSS ? 2 * BN2 : BN2;
+  // Narrow N tiles of the 3-pass product are bound by the shared-memory reads of the A operand (4 KB per MMA that lasts
+  // 16-32 cycles), not by the tensor pipe: there A_hi is read ONCE per k-step by an MMA of N = 2*BN2 against each CTA's
+  // contiguous [w_hi half ; w_lo half] rows (columns per CTA half h: [h*2*BH, h*2*BH + BH) = main, the next BH = hi*lo),
+  // and A_lo * w_hi accumulates in a third block of BN2 columns: 2 A reads and 2 MMAs per k-step instead of 3.
+  static constexpr bool CONCAT = PASSES == 3 && BN2 <= 64;
+  static constexpr int ACC_COLS = CONCAT ? 3 * BN2 : (CROSS ? 2 * BN2 : BN2);
   static_assert(2 * ACC_COLS <= 512, "two accumulator sets must fit the 512 TMEM columns (cross accumulator: BN2 <= 128)");
   static constexpr int TMEM_COLS = 2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512));
   static_assert(BN2 % 32 == 0 && BN2 <= 256, "pair N tile: multiple of 32 up to 256");
@@ -463,6 +468,7 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
     if (leader) {
       // ===== MMA issuer (leader CTA only): M = 256 across the pair, N = BN2 =====
       constexpr uint32_t idesc = idesc_kind<F16>(256, BN2, 0, 0);
+      constexpr uint32_t idesc2 = idesc_kind<F16>(256, 2 * BN2 <= 256 ? 2 * BN2 : BN2, 0, 0);      // [w_hi ; w_lo] rows of both CTAs
       uint32_t ai = 0, bi = 0, ti = 0;
       for (int t = tile0; t < n_iter_total; t += tstep) {
         const uint32_t acc = ti & 1, tph = (ti >> 1) & 1;
@@ -492,16 +498,23 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
                   const uint64_t da_hi = smem_desc_sw128(a_hi + a_off + ko, 16, sbo, 2, 0);
                   const uint64_t db_hi = smem_desc_sw128(b_hi + ko, 16, 1024);
                   const uint32_t first = (kc > 0 || tap > 0 || k4 > 0) ? 1u : 0u;
-                  mma_kind_pair<F16>(tmem_d, da_hi, db_hi, idesc, first);
-                  if (PASSES == 3) {
+                  if (Cfg::CONCAT) {
+                    const uint64_t da_lo = smem_desc_sw128(a_lo + a_off + ko, 16, sbo, 2, 0);
+                    mma_kind_pair<F16>(tmem_d, da_hi, db_hi, idesc2, first);               // hi*hi and hi*lo in one pass over A_hi
+                    mma_kind_pair<F16>(tmem_d + 2 * BN2, da_lo, db_hi, idesc, first);      // lo*hi: third column block
+                  } else if (PASSES == 3) {
+                    mma_kind_pair<F16>(tmem_d, da_hi, db_hi, idesc, first);
                     const uint64_t db_lo = smem_desc_sw128(b_lo + ko, 16, 1024);
                     const uint64_t da_lo = smem_desc_sw128(a_lo + a_off + ko, 16, sbo, 2, 0);
                     mma_kind_pair<F16>(tmem_d + BN2, da_hi, db_lo, idesc, first);      // cross terms: own accumulator
                     mma_kind_pair<F16>(tmem_d + BN2, da_lo, db_hi, idesc, 1u);
                   } else if (PASSES == 2) {
+                    mma_kind_pair<F16>(tmem_d, da_hi, db_hi, idesc, first);
                     const uint64_t da_lo = smem_desc_sw128(a_lo + a_off + ko, 16, sbo, 2, 0);
                     if (F16) mma_kind_pair<F16>(tmem_d + BN2, da_lo, db_hi, idesc, first);   // lo carries 2^11: cross accumulator
                     else mma_kind_pair<F16>(tmem_d, da_lo, db_hi, idesc, 1u);
+                  } else {
+                    mma_kind_pair<F16>(tmem_d, da_hi, db_hi, idesc, first);
                   }
                 }
               }
@@ -565,8 +578,34 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
         const int col0 = n_off + c0;
         if (col0 >= p.n_cols) break;             // warp-uniform
         float v[32];
+        if (Cfg::CONCAT) {
+          // columns: CTA-half h of the N tile holds [main | hi*lo] for its BH channels; lo*hi follows at 2*BN2 in channel order
+          const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS;
+          float va[32], vb[32], vc[32];
+          tmem_ld32(tb + (uint32_t)(2 * BN2 + c0), vc);
+          if (Cfg::BH == 16) {                  // BN2 = 32: 16 main + 16 cross columns per half
+            tmem_ld32(tb, va);
+            tmem_ld32(tb + 32u, vb);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float c_lo = va[16 + j] + vc[j], c_hi = vb[16 + j] + vc[16 + j];
+              v[j] = F16 ? fmaf(c_lo, s_cross, va[j] * s_main) : va[j] + c_lo;
+              v[16 + j] = F16 ? fmaf(c_hi, s_cross, vb[j] * s_main) : vb[j] + c_hi;
+            }
+          } else {                              // BN2 = 64: a 32-channel chunk is one CTA half
+            tmem_ld32(tb + (uint32_t)(2 * c0), va);
+            tmem_ld32(tb + (uint32_t)(2 * c0 + 32), vb);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float c = vb[j] + vc[j];
+              v[j] = F16 ? fmaf(c, s_cross, va[j] * s_main) : va[j] + c;
+            }
+          }
+        } else {
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS + (uint32_t)c0, v);
-        if (Cfg::CROSS) {
+        }
+        if (Cfg::CONCAT) {
+        } else if (Cfg::CROSS) {
           float v2[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS + (uint32_t)(BN2 + c0), v2);
 #pragma unroll
@@ -1303,23 +1342,27 @@ struct Wg16Params {
   const int32_t* dy_scale;
 };
 
-template <int BN, int STAGES>
+// RPC = filter rows per CTA: 1 (the CTA's row comes from blockIdx.z) or 3 (narrow N tiles: the twelve accumulators of all
+// three rows fit TMEM, X and dY are streamed once instead of three times; the window then carries the 2 halo rows)
+template <int BN, int STAGES, int RPC = 1>
 struct Wg16Cfg {
-  static constexpr uint32_t A_PLANE = 4 * 16 * 128;                       // 8192 B window
+  static constexpr uint32_t A_ROWS = 4 + RPC - 1;
+  static constexpr uint32_t A_PLANE = A_ROWS * 16 * 128;                  // 8192 B window (12288 B with the halo rows)
   static constexpr uint32_t NB = (BN + 63) / 64;                          // dY boxes of 64 channels
   static constexpr uint32_t B_PLANE = NB * 4096;
   static constexpr uint32_t STAGE_BYTES = (A_PLANE + B_PLANE) * 2;        // hi + lo planes of both operands
   static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
-  static constexpr int TMEM_COLS = 4 * BN <= 64 ? 64 : (4 * BN <= 128 ? 128 : (4 * BN <= 256 ? 256 : 512));
-  static_assert(4 * BN <= 512, "four accumulators of BN columns");
+  static constexpr int ACC_COLS = RPC * 4 * BN;
+  static constexpr int TMEM_COLS = ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512));
+  static_assert(ACC_COLS <= 512, "four accumulators of BN columns per filter row");
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int RPC>
 __global__ void __launch_bounds__(192, 1)
 conv_tc2_wgrad16_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_constant__ CUtensorMap mapX_lo,
                         const __grid_constant__ CUtensorMap mapY_hi, const __grid_constant__ CUtensorMap mapY_lo,
                         const __grid_constant__ Wg16Params p) {
-  using Cfg = Wg16Cfg<BN, STAGES>;
+  using Cfg = Wg16Cfg<BN, STAGES, RPC>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
@@ -1330,8 +1373,8 @@ conv_tc2_wgrad16_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __gri
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int ci0 = blockIdx.x * 64;
   const int n_off = blockIdx.y * BN;
-  const int r = blockIdx.z / p.splits;                 // filter row of this CTA
-  const int split = blockIdx.z - r * p.splits;
+  const int r = RPC == 3 ? 0 : blockIdx.z / p.splits;       // first filter row of this CTA
+  const int split = RPC == 3 ? blockIdx.z : blockIdx.z - r * p.splits;
   const int t_begin = split * p.tiles_per_split;
   int t_end = t_begin + p.tiles_per_split;
   if (t_end > p.total_tiles) t_end = p.total_tiles;
@@ -1390,15 +1433,18 @@ conv_tc2_wgrad16_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __gri
             const uint64_t db_hi = smem_desc_sw128(b_hi + (uint32_t)j * 2048u, 4096, 1024, 2);
             const uint64_t db_lo = smem_desc_sw128(b_lo + (uint32_t)j * 2048u, 4096, 1024, 2);
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {                                 // g = 0: taps s = 0,1;  g = 1: tap s = 2 (+ ignored)
-              const uint32_t ao = ((uint32_t)(2 * j) * 16u + (uint32_t)(2 * g)) * 128u;
-              const uint64_t da_hi = smem_desc_sw128(a_hi + ao, 128, 2048, 2);
-              const uint64_t da_lo = smem_desc_sw128(a_lo + ao, 128, 2048, 2);
-              const uint32_t d_main = tmem_base + (uint32_t)(g * 2 * BN);
-              const uint32_t d_cross = d_main + (uint32_t)BN;
-              mma_f16(d_main, da_hi, db_hi, idesc, acc);
-              mma_f16(d_cross, da_hi, db_lo, idesc, acc);
-              mma_f16(d_cross, da_lo, db_hi, idesc, 1u);
+            for (int rr = 0; rr < RPC; ++rr) {
+#pragma unroll
+              for (int g = 0; g < 2; ++g) {                               // g = 0: taps s = 0,1;  g = 1: tap s = 2 (+ ignored)
+                const uint32_t ao = ((uint32_t)(2 * j + rr) * 16u + (uint32_t)(2 * g)) * 128u;
+                const uint64_t da_hi = smem_desc_sw128(a_hi + ao, 128, 2048, 2);
+                const uint64_t da_lo = smem_desc_sw128(a_lo + ao, 128, 2048, 2);
+                const uint32_t d_main = tmem_base + (uint32_t)((rr * 2 + g) * 2 * BN);
+                const uint32_t d_cross = d_main + (uint32_t)BN;
+                mma_f16(d_main, da_hi, db_hi, idesc, acc);
+                mma_f16(d_cross, da_hi, db_lo, idesc, acc);
+                mma_f16(d_cross, da_lo, db_hi, idesc, 1u);
+              }
             }
           }
           mma_commit(&empty[s]);
@@ -1417,20 +1463,21 @@ conv_tc2_wgrad16_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __gri
     mbar_wait(tmem_full, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int g = 0; g < 2; ++g) {
+    for (int rg = 0; rg < 2 * RPC; ++rg) {
+      const int rr = rg >> 1, g = rg & 1;
       const int s_tap = 2 * g + g_row;
       const bool row_ok = (s_tap < 3) && (ci < p.Cin);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32], v2[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 2 * BN + c0), v);
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 2 * BN + BN + c0), v2);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(rg * 2 * BN + c0), v);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(rg * 2 * BN + BN + c0), v2);
         if (!row_ok) continue;
         const int col0 = n_off + c0;
         if (col0 >= p.Cout) continue;
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaf(v2[j], s_cross, v[j] * s_main);
-        float* o = p.dw + ((size_t)(r * 3 + s_tap) * p.Cin + ci) * p.Cout + col0;
+        float* o = p.dw + ((size_t)((r + rr) * 3 + s_tap) * p.Cin + ci) * p.Cout + col0;
         if ((p.Cout & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dw) & 15) == 0) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
@@ -1451,12 +1498,12 @@ conv_tc2_wgrad16_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __gri
   }
 }
 
-template <int BN>
+template <int BN, int RPC>
 static int launch_wg16(const CUtensorMap& x_hi, const CUtensorMap& x_lo, const CUtensorMap& y_hi,
                        const CUtensorMap& y_lo, const Wg16Params& p, dim3 grid, cudaStream_t st) {
   constexpr int STAGES = BN <= 64 ? 6 : 5;
-  using Cfg = Wg16Cfg<BN, STAGES>;
-  auto kern = conv_tc2_wgrad16_kernel<BN, STAGES>;
+  using Cfg = Wg16Cfg<BN, STAGES, RPC>;
+  auto kern = conv_tc2_wgrad16_kernel<BN, STAGES, RPC>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
@@ -1481,7 +1528,8 @@ static int conv_tc2_wgrad16_run(const immb_conv_desc* d, const void* x_hi, const
   const int bn = d->Cout > 64 ? 128 : (d->Cout > 32 ? 64 : 32);      // (narrower tiles would read past their TMEM columns)
   const int n_tiles = ceil_div(d->Cout, bn);
   const int c_tiles = ceil_div(d->Cin, 64);
-  int splits = kNumSMs / (c_tiles * n_tiles * 3);
+  const int rpc = bn == 32 ? 3 : 1;                                  // all three filter rows in one CTA when TMEM allows
+  int splits = kNumSMs / (c_tiles * n_tiles * (rpc == 3 ? 1 : 3));
   if (splits > p.total_tiles) splits = p.total_tiles;
   if (splits < 1) splits = 1;
   p.tiles_per_split = ceil_div(p.total_tiles, splits);
@@ -1491,14 +1539,15 @@ static int conv_tc2_wgrad16_run(const immb_conv_desc* d, const void* x_hi, const
   if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "wgrad memset: %s", cudaGetErrorString(e));
   CUtensorMap mx_hi, mx_lo, my_hi, my_lo;
   int rc;
-  if ((rc = tc_make_act_map(&mx_hi, x_hi, d->N, d->H, d->W, d->Cin, d->x_cstride, false, 16, 4, 1, 1, 2))) return rc;
-  if ((rc = tc_make_act_map(&mx_lo, x_lo, d->N, d->H, d->W, d->Cin, d->x_cstride, false, 16, 4, 1, 1, 2))) return rc;
+  const int box_h = 4 + rpc - 1;
+  if ((rc = tc_make_act_map(&mx_hi, x_hi, d->N, d->H, d->W, d->Cin, d->x_cstride, false, 16, box_h, 1, 1, 2))) return rc;
+  if ((rc = tc_make_act_map(&mx_lo, x_lo, d->N, d->H, d->W, d->Cin, d->x_cstride, false, 16, box_h, 1, 1, 2))) return rc;
   if ((rc = tc_make_act_map(&my_hi, dy_hi, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, 8, 4, 1, 1, 2))) return rc;
   if ((rc = tc_make_act_map(&my_lo, dy_lo, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, 8, 4, 1, 1, 2))) return rc;
-  dim3 grid(c_tiles, n_tiles, 3 * splits);
-  if (bn == 128) return launch_wg16<128>(mx_hi, mx_lo, my_hi, my_lo, p, grid, st);
-  if (bn == 64) return launch_wg16<64>(mx_hi, mx_lo, my_hi, my_lo, p, grid, st);
-  return launch_wg16<32>(mx_hi, mx_lo, my_hi, my_lo, p, grid, st);
+  dim3 grid(c_tiles, n_tiles, (rpc == 3 ? 1 : 3) * splits);
+  if (bn == 128) return launch_wg16<128, 1>(mx_hi, mx_lo, my_hi, my_lo, p, grid, st);
+  if (bn == 64) return launch_wg16<64, 1>(mx_hi, mx_lo, my_hi, my_lo, p, grid, st);
+  return launch_wg16<32, 3>(mx_hi, mx_lo, my_hi, my_lo, p, grid, st);
 }
 
 bool conv_tc2_wgrad_eligible(const immb_conv_desc* d) {

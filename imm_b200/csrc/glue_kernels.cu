@@ -57,15 +57,26 @@ __global__ void bn_stats_kernel(const float* __restrict__ y, int64_t npix, int C
 
 // sumsq in fp32 of a single value is exact enough; accumulation is in double.  (t*t rounds once.)
 
+__device__ __forceinline__ void bn_finalize_channel(int c, int training, double sum, double sumsq, double count,
+                                                    const float* gamma, const float* beta, float* mm, float* mv,
+                                                    float* scale, float* shift, float* mean_o, float* invstd_o);
+
 __global__ void bn_finalize_kernel(const double* sums, double count, int C, const float* gamma,
                                    const float* beta, float* mm, float* mv, int training, float* scale,
                                    float* shift, float* mean_o, float* invstd_o) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  bn_finalize_channel(c, training, training ? sums[c] : 0.0, training ? sums[C + c] : 0.0, count, gamma, beta, mm, mv,
+                      scale, shift, mean_o, invstd_o);
+}
+
+__device__ __forceinline__ void bn_finalize_channel(int c, int training, double sum, double sumsq, double count,
+                                                    const float* gamma, const float* beta, float* mm, float* mv,
+                                                    float* scale, float* shift, float* mean_o, float* invstd_o) {
   float mean, var;
   if (training) {
-    double m = sums[c] / count;
-    double v = sums[C + c] / count - m * m;
+    double m = sum / count;
+    double v = sumsq / count - m * m;
     if (v < 0.0) v = 0.0;
     mean = (float)m;
     var = (float)v;
@@ -555,8 +566,10 @@ __global__ void bn_bwd_apply4_kernel(BnBwdArgs a, int64_t npix, int C, const dou
 // over b) with EIGHT independent loads in flight per thread (the kernel is a dependent-L2-load chain otherwise: 69
 // launches per step used to cost 1.1 ms), then a fixed-order combine through shared memory.
 // block = (32 values, 32 lanes).
+// (also: out_f != nullptr writes the float value of the sum there instead of accumulating into `out`: the bias gradient
+// needs no double accumulator and no cast kernel)
 __global__ void __launch_bounds__(1024) reduce_partials_kernel(const double* __restrict__ partials, int nblocks, int nvals,
-                                                                double* out) {
+                                                                double* out, float* out_f) {
   __shared__ double sm[32][33];
   const int v = blockIdx.x * 32 + threadIdx.x;
   double s[8];
@@ -584,7 +597,55 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const double* __r
     for (int r = 0; r < 32; r += 4) {
       t0 += sm[r][threadIdx.x]; t1 += sm[r + 1][threadIdx.x]; t2 += sm[r + 2][threadIdx.x]; t3 += sm[r + 3][threadIdx.x];
     }
-    out[v] += (t0 + t1) + (t2 + t3);
+    if (out_f) out_f[v] = (float)((t0 + t1) + (t2 + t3));
+    else out[v] += (t0 + t1) + (t2 + t3);
+  }
+}
+
+// Second level of the conv-epilogue BN statistics fused with bn_finalize: block = 32 channels x 32 row lanes sums the
+// partial rows of sum(y) and sum(y^2) in the same fixed order as reduce_partials_kernel, then lane row 0 finalises its
+// channel (one launch instead of two per BN layer; deterministic, no atomics).
+__global__ void __launch_bounds__(1024) bn_finalize_partials_kernel(const double* __restrict__ partials, int nblocks, int C,
+                                                                     double count, const float* gamma, const float* beta,
+                                                                     float* mm, float* mv, float* scale, float* shift,
+                                                                     float* mean_o, float* invstd_o) {
+  __shared__ double sm[2][32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int nvals = 2 * C;
+#pragma unroll
+  for (int qn = 0; qn < 2; ++qn) {
+    double s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = 0.0;
+    if (c < C) {
+      const double* pv = partials + qn * C + c;
+      int b = threadIdx.y;
+      for (; b + 7 * 32 < nblocks; b += 8 * 32) {
+        double t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = __ldcg(pv + (size_t)(b + 32 * j) * nvals);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += t[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (b + 32 * j < nblocks) s[j] += __ldcg(pv + (size_t)(b + 32 * j) * nvals);
+    }
+    sm[qn][threadIdx.y][threadIdx.x] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+  }
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    double tot[2];
+#pragma unroll
+    for (int qn = 0; qn < 2; ++qn) {
+      double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+#pragma unroll
+      for (int r = 0; r < 32; r += 4) {
+        t0 += sm[qn][r][threadIdx.x]; t1 += sm[qn][r + 1][threadIdx.x]; t2 += sm[qn][r + 2][threadIdx.x]; t3 += sm[qn][r + 3][threadIdx.x];
+      }
+      tot[qn] = (t0 + t1) + (t2 + t3);
+    }
+    bn_finalize_channel(c, 1, tot[0], tot[1], count, gamma, beta, mm, mv, scale, shift, mean_o, invstd_o);
   }
 }
 
@@ -1557,6 +1618,59 @@ __global__ void pack_weights_h16_kernel(const float* __restrict__ w, int taps, i
   }
 }
 
+// All weight tensors of the model in ONE launch (the 25 per-layer pack launches sat back to back on the critical path at
+// the end of every step): `items` is a device table (immb_pack_item), block b works on the item whose [block0, block0 +
+// nblocks) range contains it, 2048 elements per block.  kind 0 = fp32 TF32 planes, 1 = scaled fp16 planes, 2 = the 7x7
+// first layer's row-window layout (TF32 planes).
+__global__ void pack_weights_multi_kernel(const immb_pack_item* __restrict__ items, int n_items) {
+  int it = 0;
+  while (it + 1 < n_items && (int)blockIdx.x >= items[it + 1].block0) ++it;
+  const immb_pack_item m = items[it];
+  const int64_t base = (int64_t)((int)blockIdx.x - m.block0) * 2048;
+  const float* w = m.w;
+  if (m.kind == 2) {
+    const int total = 7 * m.Cout * 32;
+    float* wp_hi = (float*)m.wp_hi;
+    float* wp_lo = (float*)m.wp_lo;
+    for (int64_t i = base + threadIdx.x; i < base + 2048 && i < total; i += blockDim.x) {
+      int k = (int)i & 31;
+      int co = ((int)i >> 5) % m.Cout;
+      int r = ((int)i >> 5) / m.Cout;
+      int sx = k >> 2, c = k & 3;
+      float v = (sx < 7 && c < 3) ? __ldg(w + ((size_t)(r * 7 + sx) * 3 + c) * m.Cout + co) : 0.f;
+      store_split(wp_hi, wp_lo, (size_t)i, v);
+    }
+    return;
+  }
+  const int64_t total = (int64_t)m.taps * m.cin_pad * m.cout_pad;
+  int e = 0;
+  float mul = 1.f;
+  if (m.kind == 1) {
+    e = h16_exp_for(__ldg(m.amax));
+    mul = exp2i(e);
+    if ((int)blockIdx.x == m.block0 && threadIdx.x == 0) m.rec[0] = e;
+  }
+  for (int64_t i = base + threadIdx.x; i < base + 2048 && i < total; i += blockDim.x) {
+    int co = (int)(i % m.cout_pad);
+    int64_t q = i / m.cout_pad;
+    int ci = (int)(q % m.cin_pad);
+    int tap = (int)(q / m.cin_pad);
+    float val = (ci < m.Cin && co < m.Cout) ? __ldg(w + ((int64_t)tap * m.Cin + ci) * m.Cout + co) : 0.f;
+    const size_t j = ((size_t)tap * m.Cout + co) * m.cin_pad + ci;
+    if (m.kind == 1) {
+      uint16_t hi, lo;
+      split_h16(val * mul, hi, lo);
+      if (m.wh_hi) { ((uint16_t*)m.wh_hi)[i] = hi; ((uint16_t*)m.wh_lo)[i] = lo; }
+      if (m.wp_hi && co < m.Cout) { ((uint16_t*)m.wp_hi)[j] = hi; ((uint16_t*)m.wp_lo)[j] = lo; }
+    } else {
+      float hi, lo;
+      split_tf32(val, hi, lo);
+      if (m.wh_hi) { ((float*)m.wh_hi)[i] = hi; ((float*)m.wh_lo)[i] = lo; }
+      if (m.wp_hi && co < m.Cout) { ((float*)m.wp_hi)[j] = hi; ((float*)m.wp_lo)[j] = lo; }
+    }
+  }
+}
+
 // per-tensor max |p| over the chunk table of the flat parameter buffer (amax[t] zeroed by the caller; bit patterns of
 // non-negative floats order like unsigned integers)
 __global__ void multi_amax_kernel(const float* __restrict__ p, const int32_t* __restrict__ chunk_tensor,
@@ -1692,8 +1806,9 @@ extern "C" size_t immb_bn_scratch_elems(int64_t npix, int C) {
 }
 
 // launches the second level of a two-level reduction
-static int launch_reduce_partials(const double* partials, int nblocks, int nvals, double* out, cudaStream_t st) {
-  reduce_partials_kernel<<<ceil_div(nvals, 32), dim3(32, 32), 0, st>>>(partials, nblocks, nvals, out);
+static int launch_reduce_partials(const double* partials, int nblocks, int nvals, double* out, cudaStream_t st,
+                                  float* out_f = nullptr) {
+  reduce_partials_kernel<<<ceil_div(nvals, 32), dim3(32, 32), 0, st>>>(partials, nblocks, nvals, out, out_f);
   return check_launch("reduce_partials");
 }
 
@@ -1715,6 +1830,16 @@ extern "C" int immb_bn_stats(const float* y, int64_t npix, int C, int ycs, doubl
 extern "C" int immb_bn_stats_from_partials(const double* partials, int rows, int C, double* sums, void* stream) {
   IMMB_REQUIRE(partials && sums && rows > 0 && C > 0, "bn_stats_from_partials: bad args");
   return launch_reduce_partials(partials, rows, 2 * C, sums, ST(stream));
+}
+
+extern "C" int immb_bn_finalize_partials(const double* partials, int rows, int64_t count, int C, const float* gamma,
+                                         const float* beta, float* mm, float* mv, float* scale, float* shift,
+                                         float* mean, float* invstd, void* stream) {
+  IMMB_REQUIRE(partials && rows > 0 && gamma && beta && mm && mv && scale && shift && mean && invstd && C > 0,
+               "bn_finalize_partials: bad args");
+  bn_finalize_partials_kernel<<<ceil_div(C, 32), dim3(32, 32), 0, ST(stream)>>>(partials, rows, C, (double)count, gamma, beta,
+                                                                                mm, mv, scale, shift, mean, invstd);
+  return check_launch("bn_finalize_partials");
 }
 
 extern "C" int immb_bn_finalize(const double* sums, int64_t count, int C, const float* gamma,
@@ -1793,7 +1918,7 @@ extern "C" int immb_bn_bwd_apply(const float* g, int gcs, const float* y, int yc
                                  const float* scale, const float* shift, const float* mean,
                                  const float* invstd, int relu, const double* sums, void* dy_hi,
                                  void* dy_lo, float* dgamma, float* dbeta, double* dbias_acc, double* scratch,
-                                 size_t scratch_elems, int32_t* dy_scale, void* stream) {
+                                 size_t scratch_elems, int32_t* dy_scale, float* dbias_out, void* stream) {
   IMMB_REQUIRE(g && y && sums && dy_hi && dgamma && dbeta && dbias_acc, "bn_bwd_apply: bad args");
   const bool v4 = vec_ok(C, gcs) && ycs % 4 == 0 && C <= 256 && aligned16(g) && aligned16(y) && aligned16(dy_hi) &&
                   aligned16(dy_lo);
@@ -1809,8 +1934,12 @@ extern "C" int immb_bn_bwd_apply(const float* g, int gcs, const float* y, int yc
       bn_bwd_apply4_kernel<false><<<grid, 256, vred_smem(1), ST(stream)>>>(a, npix, C, sums, make_pl<false>(dy_hi, dy_lo, nullptr),
                                                                            dgamma, dbeta, dbias_acc, ppb, two ? scratch : nullptr);
     int rc = check_launch("bn_bwd_apply");
-    if (rc || !two) return rc;
-    return launch_reduce_partials(scratch, grid, C, dbias_acc, ST(stream));
+    if (rc) return rc;
+    if (!two) {
+      IMMB_REQUIRE(!dbias_out, "bn_bwd_apply: the float bias-gradient output needs the two-level (scratch) path");
+      return rc;
+    }
+    return launch_reduce_partials(scratch, grid, C, dbias_acc, ST(stream), dbias_out);
   } else {
     bn_bwd_apply_kernel<<<red_grid(npix, C), dim3(32, kRedRows), 0, ST(stream)>>>(
         g, gcs, y, ycs, npix, C, scale, shift, mean, invstd, relu, sums, (float*)dy_hi, (float*)dy_lo, dgamma, dbeta, dbias_acc);
@@ -2159,6 +2288,12 @@ extern "C" int immb_total_loss(const float* rec_loss, const double* wsq, const f
   IMMB_REQUIRE(rec_loss && wsq && tensor_wd && weights_loss && total, "total_loss: bad args");
   total_loss_kernel<<<1, 32, 0, ST(stream)>>>(rec_loss, wsq, tensor_wd, n_tensors, weights_loss, total, overflow);
   return check_launch("total_loss");
+}
+
+extern "C" int immb_pack_weights_multi(const immb_pack_item* items, int n_items, int total_blocks, void* stream) {
+  IMMB_REQUIRE(items && n_items > 0 && total_blocks > 0, "pack_weights_multi: bad args");
+  pack_weights_multi_kernel<<<total_blocks, 256, 0, ST(stream)>>>(items, n_items);
+  return check_launch("pack_weights_multi");
 }
 
 extern "C" int immb_multi_amax(const float* p, const int32_t* chunk_tensor, const int64_t* chunk_off,

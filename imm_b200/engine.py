@@ -224,6 +224,12 @@ class IMMEngine(object):
     self.fuse_bn_stats = bool(int(os.environ.get('IMMB_FUSE_BN_STATS', '1')))
     self.fuse_level_sums = bool(int(os.environ.get('IMMB_FUSE_LEVEL_SUMS', '1')))
     self._graphs, self._graph_key, self._graph_warm = None, None, 0
+    # N > 1: bucketed all-reduce overlapped with the encoders' backward (IMMB_AR_OVERLAP=0: one all-reduce after backward)
+    # and captured into the step graph (IMMB_GRAPH_NCCL=0: eager all-reduce between a fwd+bwd graph and an optimiser graph)
+    self.overlap_allreduce = bool(int(os.environ.get('IMMB_AR_OVERLAP', '1')))
+    self.graph_nccl = bool(int(os.environ.get('IMMB_GRAPH_NCCL', '1')))
+    self.comm_stream, self._allreduce_fn = None, None
+    self._pack_table = None
     self.graph_replays, self.graph_launches_per_step = 0, 0
     self._events = {}
 
@@ -349,6 +355,8 @@ class IMMEngine(object):
       offs.append(off)
       off += round_up(int(np.prod(s)), 4)
     self.param_offsets, self.n_flat = offs, off
+    self.ren_grad_offset = offs[names.index('model/renderer/conv_1/conv_1/w')]      # renderer tensors are the tail of the buffer
+    assert all(n.startswith('model/renderer/') for n in names[names.index('model/renderer/conv_1/conv_1/w'):])
     z = lambda: torch.zeros(off, dtype=torch.float32, device=dev)
     self.flat_p, self.flat_g, self.flat_m, self.flat_v = z(), z(), z(), z()
     view = lambda flat: OrderedDict((n, flat[o:o + int(np.prod(s))].view(s)) for n, o, s in zip(names, offs, shapes))
@@ -623,8 +631,34 @@ class IMMEngine(object):
       self.w_amax.zero_()
       call('immb_multi_amax', self.flat_p, self.chunk_tensor, self.chunk_off, self.chunk_len, self.n_chunks, self.w_amax,
            _lib.stream_ptr())
+    if self._pack_table is None:
+      self._build_pack_table()
+    call('immb_pack_weights_multi', self._pack_table, self._pack_n, self._pack_blocks, _lib.stream_ptr())
+
+  def _build_pack_table(self):
+    """Device table of immb_pack_item records: every trainable weight tensor is repacked by ONE launch per step."""
+    import ctypes
+    items, block0 = [], 0
+    ptr = lambda t: (t.data_ptr() if t is not None else None)
     for L in self.layers.values():
-      self._pack(L)
+      it = _lib.PackItem()
+      it.w = L.w.data_ptr()
+      it.wp_hi, it.wp_lo = ptr(L.wp.hi), ptr(L.wp.lo)
+      it.wh_hi, it.wh_lo = ptr(L.wh.hi), ptr(L.wh.lo)
+      it.taps, it.Cin, it.Cout, it.cin_pad, it.cout_pad = L.k * L.k, L.cin, L.cout, L.cin_pad, L.ycs
+      if L.x_layout == _lib.XLAYOUT_ROWWIN4:
+        it.kind, n = 2, 7 * L.cout * 32
+      else:
+        it.kind, n = (1 if L.h16 else 0), L.k * L.k * L.cin_pad * L.ycs
+        if L.h16:
+          it.amax, it.rec = L.w_amax.data_ptr(), L.w_scale.data_ptr()
+      it.block0, it.nblocks = block0, (n + 2047) // 2048
+      block0 += it.nblocks
+      items.append(it)
+    arr = (_lib.PackItem * len(items))(*items)
+    raw = torch.frombuffer(bytearray(ctypes.string_at(ctypes.addressof(arr), ctypes.sizeof(arr))), dtype=torch.uint8)
+    self._pack_table = raw.to(self.dev)
+    self._pack_n, self._pack_blocks = len(items), block0
 
   # ------------------------------------------------------------------------------------------------
   # H16 scale records: delayed scaling + calibration
@@ -715,16 +749,20 @@ class IMMEngine(object):
     if fused_stats:
       # batch statistics accumulated in the conv epilogue (per-CTA partial rows -> fixed-order second level)
       call('immb_conv2d_fwd_bnstats', L.desc(x=X), X.hi, X.lo, L.wp.hi, L.wp.lo, L.b, L.y, sc, sc.numel(), st)
-      call('immb_bn_stats_from_partials', sc, L.stats_rows, L.cout, L.sums, st)
     else:
       self._conv_fwd(L, X, L.y)
     if not L.bn:
       return None
     npix = L.N * L.Ho * L.Wo
-    if training and not fused_stats:
-      call('immb_bn_stats', L.y, npix, L.cout, L.ycs, L.sums, sc, sc.numel(), st)
-    call('immb_bn_finalize', L.sums, npix, L.cout, L.gamma, L.beta, L.mm, L.mv, 1 if training else 0,
-         L.scale, L.shift, L.mean, L.invstd, st)
+    if fused_stats:
+      # second level of the epilogue statistics + finalize in one launch
+      call('immb_bn_finalize_partials', sc, L.stats_rows, npix, L.cout, L.gamma, L.beta, L.mm, L.mv, L.scale, L.shift,
+           L.mean, L.invstd, st)
+    else:
+      if training:
+        call('immb_bn_stats', L.y, npix, L.cout, L.ycs, L.sums, sc, sc.numel(), st)
+      call('immb_bn_finalize', L.sums, npix, L.cout, L.gamma, L.beta, L.mm, L.mv, 1 if training else 0,
+           L.scale, L.shift, L.mean, L.invstd, st)
     call('immb_bn_apply', L.y, L.N, L.Ho, L.Wo, L.cout, L.ycs, L.scale, L.shift, 1 if L.relu else 0,
          1 if L.up2x else 0, L.out.hi, L.out.lo, L.ocs, L.out.scale, st)
     return L.out
@@ -912,8 +950,11 @@ class IMMEngine(object):
       else:
         call('immb_bn_bwd_reduce', g, gcs, L.y, L.cout, npix, L.cout, L.scale, L.shift, L.mean, L.invstd, relu,
              L.bsums, sc, sc.numel(), st)
+      # the bias gradient comes out of the second-level reduction as float (no accumulator, no cast launch)
+      direct_db = sc.numel() >= int(call('immb_bn_scratch_elems', npix, L.cout)) > 0
       call('immb_bn_bwd_apply', g, gcs, L.y, L.cout, npix, L.cout, L.scale, L.shift, L.mean, L.invstd, relu,
-           L.bsums, L.dy.hi, L.dy.lo, L.dgamma, L.dbeta, L.dbias_acc, sc, sc.numel(), L.dy.scale, st)
+           L.bsums, L.dy.hi, L.dy.lo, L.dgamma, L.dbeta, L.dbias_acc, sc, sc.numel(), L.dy.scale,
+           L.db if direct_db else None, st)
       dy = L.dy
     else:
       dy = g if isinstance(g, Planes) else None
@@ -922,7 +963,9 @@ class IMMEngine(object):
         call('immb_split_planes', g, L.dy.hi, L.dy.lo, npix * L.ycs, L.dy.scale, st)
         dy = L.dy
       call('immb_bias_grad', dy.hi, dy.lo, L.ycs, npix, L.cout, L.dbias_acc, dy.scale, st)
-    call('immb_cast_d2f', L.dbias_acc, L.db, L.cout, st)
+      direct_db = False
+    if not direct_db:
+      call('immb_cast_d2f', L.dbias_acc, L.db, L.cout, st)
     d = L.desc(x=L.x, y=dy)
     if self.wgrad_stream is not None:
       # dw is consumed by the optimiser only: the wgrad runs on its own stream behind the kernel that produced dy
@@ -1010,8 +1053,12 @@ class IMMEngine(object):
          self.pred_dy.hi, self.pred_dy.lo, st)
     return self.pred_dy
 
-  def backward(self):
-    """Gradients of (reconstruction loss) wrt every trainable tensor; the L2 term is added in the optimiser."""
+  def backward(self, allreduce=None):
+    """Gradients of (reconstruction loss) wrt every trainable tensor; the L2 term is added in the optimiser.
+    allreduce (N > 1): callable(flat tensor) = sum over replicas (cnn_train_multi.py:66-106).  The flat gradient buffer is
+    reduced in two buckets in backward order: the renderer's gradients (the tail of the buffer, complete after the
+    renderer's backward) go out on a communication stream while the two encoders are still running their backward; the
+    encoders' bucket follows the last weight-gradient kernel.  The optimiser waits for both."""
     st = _lib.stream_ptr()
     B, K = self.B, self.K
     self.bwd_pool.zero_()
@@ -1020,6 +1067,18 @@ class IMMEngine(object):
     for L in reversed(self.ren_layers):
       g = self._block_bwd(L, g, gcs)
       gcs = L.xcs
+    comm = None
+    if allreduce is not None and self.overlap_allreduce:
+      if self.comm_stream is None:
+        self.comm_stream = torch.cuda.Stream(device=self.dev)
+      comm = self.comm_stream
+      self._fork(comm, 'ar_fork_main')                       # renderer db / dgamma / dbeta (main stream)
+      if self.wgrad_stream is not None:
+        ev = self._event('ar_fork_wg')
+        ev.record(self.wgrad_stream)                         # renderer dw (weight-gradient stream)
+        comm.wait_event(ev)
+      with torch.cuda.stream(comm):
+        allreduce(self.flat_g[self.ren_grad_offset:])
     dJ = g                                             # [B,16,16,Cj]
     # pose branch: Gaussian maps -> mu -> softmax marginals -> heatmaps (imm_model.py:252-274)
     S = self.enc_out_size
@@ -1050,6 +1109,12 @@ class IMMEngine(object):
       self._join(self.pose_stream, 'bwd_join')
     if self.wgrad_stream is not None:
       self._join(self.wgrad_stream, 'wg_join')
+    if allreduce is not None:
+      if comm is not None:
+        allreduce(self.flat_g[:self.ren_grad_offset])
+        self._join(comm, 'ar_join')
+      else:
+        allreduce(self.flat_g)
 
   # ------------------------------------------------------------------------------------------------
   # optimiser  (cnn_train_multi.py:93-98,232-241; scripts/train.py:92-98)
@@ -1090,8 +1155,8 @@ class IMMEngine(object):
     return lr * math.sqrt(1.0 - beta2 ** self.adam_t) / (1.0 - beta1 ** self.adam_t)
 
   def optimizer_step(self, clip_value=1.0, lr=None, beta1=0.9, beta2=0.999, eps=1e-8, allreduce=None):
-    """mean over replicas (one all-reduce on the flat gradient buffer) -> +wd*w -> per-tensor clip_by_norm
-    -> TF Adam -> repack the tensor-core weight planes.  Also produces the total loss value."""
+    """mean over replicas (all-reduce of the flat gradient buffer, unless backward(allreduce=...) already did it) ->
+    +wd*w -> per-tensor clip_by_norm -> TF Adam -> repack the tensor-core weight planes.  Also produces the total loss."""
     if allreduce is not None:
       allreduce(self.flat_g)
     lr_t = self._next_lr_t(lr, beta1, beta2)
@@ -1118,6 +1183,7 @@ class IMMEngine(object):
         self._graphs = None                                     # hyper-parameters baked into the graph changed
       if self._graphs is None and self._graph_warm >= 2:
         try:
+          self._allreduce_fn = allreduce
           self._capture_graphs(key, image, future_image, mask)
         except Exception as e:      # e.g. a foreign thread touching CUDA during capture: keep training, eagerly
           import warnings
@@ -1131,7 +1197,7 @@ class IMMEngine(object):
         self.d_lr_t.fill_(self._next_lr_t(lr, beta1, beta2))    # by-value upload: no host buffer to race with
         g_fb, g_opt = self._graphs
         g_fb.replay()
-        if g_opt is not None:
+        if g_opt is not None:                                   # NCCL could not be captured: all-reduce between two graphs
           allreduce(self.flat_g)
           g_opt.replay()
         self.global_step += 1.0
@@ -1139,8 +1205,8 @@ class IMMEngine(object):
         return self.total_loss
       self._graph_warm += 1          # eager warm-up steps: kernel attributes configured, events created
     self.forward(image, future_image, mask, training=True, build_loss=True)
-    self.backward()
-    self.optimizer_step(clip_value, lr=lr, beta1=beta1, beta2=beta2, eps=eps, allreduce=allreduce)
+    self.backward(allreduce=allreduce)
+    self.optimizer_step(clip_value, lr=lr, beta1=beta1, beta2=beta2, eps=eps)
     return self.total_loss
 
   def _capture_graphs(self, key, image, future_image, mask):
@@ -1159,15 +1225,31 @@ class IMMEngine(object):
     cap = torch.cuda.Stream(device=dev)
     g_fb, g_opt = torch.cuda.CUDAGraph(), None
     n0 = _lib.launch_count()
-    with torch.cuda.graph(g_fb, stream=cap, capture_error_mode='thread_local'):
-      self.forward(self.g_image, self.g_future, self.g_mask, training=True, build_loss=True)
-      self.backward()
-      if not has_allreduce:
-        self._optimizer_kernels(clip_value, 0.0, beta1, beta2, eps, lr_t_dev=self.d_lr_t)
-    if has_allreduce:
-      g_opt = torch.cuda.CUDAGraph()
-      with torch.cuda.graph(g_opt, stream=cap, capture_error_mode='thread_local'):
-        self._optimizer_kernels(clip_value, 0.0, beta1, beta2, eps, lr_t_dev=self.d_lr_t)
+    one_graph = has_allreduce and self.graph_nccl
+    if one_graph:
+      # the whole step incl. the two bucketed NCCL all-reduces as ONE graph (NCCL >= 2.9 collectives are capturable)
+      try:
+        with torch.cuda.graph(g_fb, stream=cap, capture_error_mode='thread_local'):
+          self.forward(self.g_image, self.g_future, self.g_mask, training=True, build_loss=True)
+          self.backward(allreduce=self._allreduce_fn)
+          self._optimizer_kernels(clip_value, 0.0, beta1, beta2, eps, lr_t_dev=self.d_lr_t)
+      except Exception as e:
+        import warnings
+        warnings.warn('capturing the NCCL all-reduce into the step graph failed (%s); using two graphs' % (e,))
+        one_graph, self.graph_nccl = False, False
+        g_fb = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        torch.cuda.synchronize(dev)
+    if not one_graph:
+      with torch.cuda.graph(g_fb, stream=cap, capture_error_mode='thread_local'):
+        self.forward(self.g_image, self.g_future, self.g_mask, training=True, build_loss=True)
+        self.backward()
+        if not has_allreduce:
+          self._optimizer_kernels(clip_value, 0.0, beta1, beta2, eps, lr_t_dev=self.d_lr_t)
+      if has_allreduce:
+        g_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_opt, stream=cap, capture_error_mode='thread_local'):
+          self._optimizer_kernels(clip_value, 0.0, beta1, beta2, eps, lr_t_dev=self.d_lr_t)
     torch.cuda.synchronize(dev)
     # capture does not execute anything, but be explicit that model state is exactly what it was
     for dst, src in zip((self.flat_p, self.flat_m, self.flat_v, self.flat_bn, self.agg), saved):

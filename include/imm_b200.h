@@ -126,6 +126,12 @@ int immb_conv2d_fwd_bnstats(const immb_conv_desc* d, const void* x_hi, const voi
                             const void* wp_lo, const float* bias, float* y, double* partials, size_t partial_elems,
                             void* stream);
 int immb_bn_stats_from_partials(const double* partials, int rows, int C, double* sums, void* stream);
+/* immb_bn_stats_from_partials + immb_bn_finalize(training = 1) in ONE launch: sums the partial rows of the conv epilogue
+ * in the same fixed order and finalises every channel (batch mean / biased variance, moving statistics updated in
+ * place, scale / shift / mean / invstd written). */
+int immb_bn_finalize_partials(const double* partials, int rows, int64_t count, int C, const float* gamma,
+                              const float* beta, float* moving_mean, float* moving_var, float* scale, float* shift,
+                              float* mean, float* invstd, void* stream);
 /* dgrad that also accumulates, in its epilogue, the two per-channel sums of the BN backward of the layer that produced
  * the conv's input (tf.layers.batch_normalization gradient, nn_utils.py:201-209): sum(dz) and sum(dz * xhat) with
  * dz = dx * [relu ? y*scale+shift > 0 : 1], xhat = (y - mean) * invstd, y = that layer's raw conv output
@@ -157,6 +163,20 @@ int immb_pack_weights(const float* w, int kh, int kw, int Cin, int Cout, int cin
                       void* wp_lo, void* wh_hi, void* wh_lo, const float* amax, int32_t* w_scale, void* stream);
 /* first-layer staging for IMMB_XLAYOUT_ROWWIN4: image [N,H,W,3] -> x4 split planes [N,H,W+8,4];
  * weights [7,7,3,Cout] -> wp_{hi,lo} [7][Cout][32] with k = s*4 + c (zero for c == 3 and s == 7) */
+/* Every weight tensor in ONE launch: `items` = device array of n_items records, block ranges assigned by the caller
+ * (item i owns blocks [block0, block0 + nblocks), nblocks = ceil(elements / 2048), elements = taps*cin_pad*cout_pad or
+ * 7*Cout*32 for kind 2); total_blocks = sum of nblocks.  Same results as the per-tensor calls. */
+typedef struct {
+  const float* w;             /* master HWIO weights */
+  void *wp_hi, *wp_lo;        /* packed [taps][Cout][cin_pad] planes (kind 2: [7][Cout][32]) */
+  void *wh_hi, *wh_lo;        /* split  [taps][cin_pad][cout_pad] planes (may be NULL) */
+  const float* amax;          /* kind 1: the tensor's largest |w| */
+  int32_t* rec;               /* kind 1: its scale record */
+  int32_t taps, Cin, Cout, cin_pad, cout_pad;
+  int32_t kind;               /* 0 fp32 TF32 planes, 1 scaled fp16 planes, 2 row-window first layer (TF32 planes) */
+  int32_t block0, nblocks;
+} immb_pack_item;
+int immb_pack_weights_multi(const immb_pack_item* items, int n_items, int total_blocks, void* stream);
 int immb_stage_image_rowwin(const float* image, int N, int H, int W, float* x4_hi, float* x4_lo, void* stream);
 int immb_pack_weights_rowwin(const float* w, int Cout, float* wp_hi, float* wp_lo, void* stream);
 /* v -> (hi, lo) planes, contiguous n elements */
@@ -207,11 +227,14 @@ int immb_bn_bwd_reduce(const float* g, int g_cstride, const float* y, int y_cstr
                        const float* scale, const float* shift, const float* mean, const float* invstd,
                        int relu, double* sums, double* scratch, size_t scratch_elems, void* stream);
 /* dy = scale*(dz - mean(dz) - xhat*mean(dz*xhat)) as split planes; dgamma = sum(dz*xhat), dbeta = sum(dz),
- * dbias = sum(dy) (double accumulators dbias_acc[C], zeroed by the caller; finalised by immb_cast_d2f) */
+ * dbias = sum(dy) (double accumulators dbias_acc[C], zeroed by the caller; finalised by immb_cast_d2f).
+ * dbias_out (optional, needs the scratch path): the bias gradient is written there as float by the second-level
+ * reduction and dbias_acc is left untouched -- no accumulator clearing, no cast launch. */
 int immb_bn_bwd_apply(const float* g, int g_cstride, const float* y, int y_cstride, int64_t npix, int C,
                       const float* scale, const float* shift, const float* mean, const float* invstd,
                       int relu, const double* sums, void* dy_hi, void* dy_lo, float* dgamma, float* dbeta,
-                      double* dbias_acc, double* scratch, size_t scratch_elems, int32_t* dy_scale, void* stream);
+                      double* dbias_acc, double* scratch, size_t scratch_elems, int32_t* dy_scale, float* dbias_out,
+                      void* stream);
 /* column sums: acc[C] (double, zeroed) += sum over pixels of g[:, c] */
 int immb_bias_grad(const void* g_hi, const void* g_lo, int g_cstride, int64_t npix, int C, double* acc,
                    const int32_t* g_scale, void* stream);

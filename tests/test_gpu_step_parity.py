@@ -143,7 +143,7 @@ def test_two_tower_gradient_scale_single_gpu():
     flat_g.mul_(2.0)
   eng.train_step(d['image'], d['future_image'], d['mask'], allreduce=fake_allreduce)
   torch.cuda.synchronize()
-  assert calls == [eng.n_flat]
+  assert sum(calls) == eng.n_flat and len(calls) in (1, 2)      # one bucket, or renderer + encoders (overlapped)
   assert abs(float(eng.total_loss.item()) - float(r64['loss'])) / float(r64['loss']) < 1e-4
   for k, v in st64.params.items():
     g = r64['grads'][k]

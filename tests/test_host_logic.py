@@ -122,6 +122,60 @@ print('ok', rank)
 '''
 
 
+_WORKER_TOWERS = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from collections import OrderedDict
+from imm_b200.train import cnn_train_multi as tru
+from oracle import imm_oracle as O
+torch.set_num_threads(2)
+rank, local_rank, world = tru.init_distributed('gloo')
+assert world == 2
+# every rank = one tower of train_multi (cnn_train_multi.py:109-192) on ITS slice of the global batch; the gradient
+# exchange follows IMMEngine.backward: the flat bucket goes out in two pieces (renderer tail first, encoders second),
+# each through tru.average_gradients (sum); the 1/N of the tower mean is applied afterwards like the optimiser kernels do
+st = O.init_state(O.State(n_maps=10, image_size=128), seed=0)
+inputs = O.synthetic_inputs(2, 128, seed=0)
+mine = {k: v[rank:rank + 1] for k, v in inputs.items()}
+for p in st.params.values():
+  p.requires_grad_(True)
+out = O.forward(st, mine, training=True, build_loss=True)
+grads = torch.autograd.grad(out['loss'], list(st.params.values()), allow_unused=True)
+grads = [torch.zeros_like(p) if g is None else g for g, p in zip(grads, st.params.values())]
+names = list(st.params.keys())
+flat = torch.cat([g.reshape(-1) for g in grads])
+split = sum(g.numel() for g, n in zip(grads, names) if not n.startswith('model/renderer/'))
+assert all(n.startswith('model/renderer/') for n in names[[n.startswith('model/renderer/') for n in names].index(True):])
+tru.average_gradients(flat[split:])          # bucket 1: renderer (ready first in the backward pass)
+tru.average_gradients(flat[:split])          # bucket 2: encoders
+flat /= world
+ref_state = O.init_state(O.State(n_maps=10, image_size=128), seed=0)
+ref = O.train_step(ref_state, inputs, n_towers=2)
+ref_flat = torch.cat([ref['grads'][n].reshape(-1) for n in names])
+err = float((flat - ref_flat).norm() / ref_flat.norm())
+assert err < 1e-5, err
+# replicas hold identical reduced buckets
+other = flat.clone()
+dist.broadcast(other, src=0)
+assert torch.equal(other, flat)
+dist.barrier()
+print('ok', rank, err)
+'''
+
+
+def test_two_rank_tower_step_matches_two_tower_oracle_gloo(tmp_path):
+  """world_size 2 over gloo on CPU: two ranks, each computing one tower of the reference's train_multi on its slice of
+  the batch, exchange gradients with the engine's bucketed protocol; the mean equals oracle.train_step(n_towers=2)."""
+  script = tmp_path / 'towers.py'
+  script.write_text(_WORKER_TOWERS % ROOT)
+  env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29741')
+  out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29741', str(script)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=600)
+  assert out.returncode == 0, out.stdout[-3000:]
+  assert out.stdout.count('ok') == 2
+
+
 def test_two_rank_gradient_exchange_gloo(tmp_path):
   script = tmp_path / 'w.py'
   script.write_text(_WORKER % ROOT)
