@@ -287,7 +287,7 @@ def test_cuda_graph_replay_matches_eager_steps():
       losses.append(float(loss.item()))
     assert (eng._graphs is not None) == use_graph
     if use_graph:
-      assert eng.graph_replays == 3 and eng.graph_launches_per_step > 300
+      assert eng.graph_replays == 3 and eng.graph_launches_per_step > 200
     assert eng.adam_t == 5 and eng.global_step == 4.0
     res.append((losses, eng.flat_p.clone(), eng.flat_bn.clone(), eng.mu.clone()))
   (l0, p0, bn0, mu0), (l1, p1, bn1, mu1) = res
