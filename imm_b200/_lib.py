@@ -27,6 +27,12 @@ class ConvDesc(ctypes.Structure):
               [(n, ctypes.c_void_p) for n in ('x_scale', 'y_scale', 'w_scale')])     # H16 scale records (NULL: TF32)
 
 
+class ReduceItem(ctypes.Structure):
+  """immb_reduce_item (include/imm_b200.h)."""
+  _fields_ = ([(n, ctypes.c_void_p) for n in ('partials', 'out_f')] +
+              [(n, ctypes.c_int32) for n in ('nblocks', 'nvals', 'block0', 'reserved_')])
+
+
 class PackItem(ctypes.Structure):
   """immb_pack_item (include/imm_b200.h)."""
   _fields_ = ([(n, ctypes.c_void_p) for n in ('w', 'wp_hi', 'wp_lo', 'wh_hi', 'wh_lo', 'amax', 'rec')] +
@@ -58,7 +64,9 @@ _SIGS = {
   'immb_bn_apply': [_P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P, _P],
   'immb_upsample2x_bwd': [_P, _I, _I, _I, _I, _I, _P, _P],
   'immb_bn_bwd_reduce': [_P, _I, _P, _I, _L, _I, _P, _P, _P, _P, _I, _P, _P, _Z, _P],
-  'immb_bn_bwd_apply': [_P, _I, _P, _I, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _Z, _P, _P, _P],
+  'immb_bn_bwd_apply': [_P, _I, _P, _I, _L, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _Z, _P, _P, _I, _P],
+  'immb_bn_bwd_apply_blocks': [_L, _I],
+  'immb_reduce_partials_multi': [_P, _I, _I, _P],
   'immb_bn_finalize_partials': [_P, _I, _L, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
   'immb_bias_grad': [_P, _P, _I, _L, _I, _P, _P, _P],
   'immb_cast_d2f': [_P, _P, _L, _P],
@@ -93,11 +101,11 @@ _SIGS = {
 # trailing H16 scale-record / amax arguments (just before `stream`): callers that work on fp32 TF32 planes may omit
 # them -- call() fills them with NULL
 _OPTIONAL_TAIL = {'immb_conv2d_dgrad_relu': 1, 'immb_pack_weights': 2, 'immb_split_planes': 1, 'immb_bn_apply': 1,
-                  'immb_bn_bwd_apply': 2, 'immb_bias_grad': 1, 'immb_softargmax_gauss_fwd': 1, 'immb_vgg_conv1_1_fused': 1,
+                  'immb_bn_bwd_apply': 3, 'immb_bias_grad': 1, 'immb_softargmax_gauss_fwd': 1, 'immb_vgg_conv1_1_fused': 1,
                   'immb_maxpool2x2_fwd': 2, 'immb_maxpool2x2_fwd_levelsum': 2, 'immb_maxpool2x2_bwd_combine': 2,
                   'immb_perceptual_level_sum': 1, 'immb_vgg_bwd_combine': 2, 'immb_vgg_conv1_1_bwd_fused': 2,
                   'immb_resize_ac_fwd': 2, 'immb_adam_apply': 1, 'immb_adam_apply_dev': 1, 'immb_total_loss': 1}
-_RESTYPES = {'immb_conv2d_wgrad_workspace': _Z, 'immb_bn_scratch_elems': _Z, 'immb_crc32c': ctypes.c_uint32}
+_RESTYPES = {'immb_bn_bwd_apply_blocks': ctypes.c_int, 'immb_conv2d_wgrad_workspace': _Z, 'immb_bn_scratch_elems': _Z, 'immb_crc32c': ctypes.c_uint32}
 
 _lib = None
 
@@ -190,7 +198,9 @@ def _call(name, *args):
   k = _OPTIONAL_TAIL.get(name, 0)
   missing = len(_SIGS[name]) - len(conv) if name in _SIGS else 0
   if k and 0 < missing <= k:
-    conv = conv[:-1] + [None] * missing + conv[-1:]
+    sig = _SIGS[name]
+    fill = [None if sig[len(conv) - 1 + j] is _P else 0 for j in range(missing)]
+    conv = conv[:-1] + fill + conv[-1:]
   rc = getattr(l, name)(*conv)
   if name in _RESTYPES:
     return rc

@@ -57,6 +57,9 @@ struct Tc2Params {
   const int32_t* b_scale;
   int32_t* o_scale;
   int k_last;
+  // pair kernel: the whole weight operand of the layer (n_taps x kchunks slices of this CTA's rows) fits the weight
+  // ring and there is a single N tile: it is loaded ONCE per CTA and stays resident for all of the CTA's tiles
+  int b_resident;
 };
 
 template <int BN, int PASSES>
@@ -345,7 +348,9 @@ struct Tc2PairCfg {
   static constexpr uint32_t STATS_BYTES = PASSES == 3 ? 4 * 2 * 2 * BN2 * 8 + 4 * 256 * 4 : 0;     // + BN constants [4][256]
   static constexpr uint32_t ROOM = 232448 - 1024 - 512 - A_SLOTS * A_SLOT - STATS_BYTES;
   static constexpr uint32_t B_FIT = ROOM / B_SLOT;
-  static constexpr uint32_t B_SLOTS = B_FIT > 6 ? 6 : B_FIT;
+  // ring depth 6 for streaming; layers whose whole weight operand fits (narrow layers: 9 taps x 1-2 chunks of <= 8 KB)
+  // use the region as resident storage (Tc2Params::b_resident), so take what the budget gives up to 18 slots
+  static constexpr uint32_t B_SLOTS = B_FIT > 18 ? 18 : B_FIT;
   static_assert(B_SLOTS >= 2, "weight ring needs two slots");
   static constexpr uint32_t SMEM_BYTES = A_SLOTS * A_SLOT + B_SLOTS * B_SLOT + STATS_BYTES + 1024 + 512;
   // 3-pass: the two cross terms (hi*lo, lo*hi; ~2^-11 of the main term) accumulate in their OWN TMEM columns
@@ -433,6 +438,20 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
   if (warp == 0) {
     // ===== TMA producer (both CTAs; every load signals the leader's full barrier) =====
     uint32_t ai = 0, bi = 0;
+    if (p.b_resident && tile0 < n_iter_total) {
+      // the layer's whole weight operand (this CTA's rows of every slice), once: slot = kc * n_taps + tap
+      const int row0r = (int)crank * (int)Cfg::BH;
+      if (elect_one()) {
+        if (leader) mbar_expect_tx(&b_full[0], 2u * (uint32_t)(p.kchunks * p.n_taps) * Cfg::B_SLOT);
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          for (int tap = 0; tap < p.n_taps; ++tap) {
+            uint8_t* sb = b_base + (uint32_t)(kc * p.n_taps + tap) * Cfg::B_SLOT;
+            tma_load_3d_pair(sb, &mapB_hi, &b_full[0], kc * KC, row0r, p.taps[tap].b_tap);
+            if (PASSES == 3) tma_load_3d_pair(sb + Cfg::B_PLANE, &mapB_lo, &b_full[0], kc * KC, row0r, p.taps[tap].b_tap);
+          }
+      }
+      __syncwarp();
+    }
     for (int t = tile0; t < n_iter_total; t += tstep) {
       int img, th, tw, n_off;
       bool live;
@@ -450,6 +469,7 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
         }
         __syncwarp();
         ++ai;
+        if (p.b_resident) continue;
         for (int tap = 0; tap < p.n_taps; ++tap) {
           const uint32_t bs = bi % Cfg::B_SLOTS, bph = (bi / Cfg::B_SLOTS) & 1;
           mbar_wait(&b_empty[bs], bph ^ 1);
@@ -470,6 +490,11 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
       constexpr uint32_t idesc = idesc_kind<F16>(256, BN2, 0, 0);
       constexpr uint32_t idesc2 = idesc_kind<F16>(256, 2 * BN2 <= 256 ? 2 * BN2 : BN2, 0, 0);      // [w_hi ; w_lo] rows of both CTAs
       uint32_t ai = 0, bi = 0, ti = 0;
+      const bool resident = p.b_resident != 0;
+      if (resident && tile0 < n_iter_total) {
+        mbar_wait(&b_full[0], 0);                     // the whole weight operand of both CTAs has landed
+        tc_fence_after();
+      }
       for (int t = tile0; t < n_iter_total; t += tstep) {
         const uint32_t acc = ti & 1, tph = (ti >> 1) & 1;
         mbar_wait(&t_empty[acc], tph ^ 1);            // the epilogues of BOTH CTAs have drained this accumulator
@@ -484,9 +509,14 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
           const uint32_t sbo = (uint32_t)p.a_sbo;
           const int nk = (kc == p.kchunks - 1) ? p.k_last : 4;       // 32-byte k-steps holding real channels
           for (int tap = 0; tap <= last_tap; ++tap) {
-            const uint32_t bs = bi % Cfg::B_SLOTS, bph = (bi / Cfg::B_SLOTS) & 1;
-            mbar_wait(&b_full[bs], bph);
-            tc_fence_after();
+            const uint32_t bs = resident ? (uint32_t)(kc * p.n_taps + tap) : bi % Cfg::B_SLOTS;
+            const uint32_t bph = (bi / Cfg::B_SLOTS) & 1;
+            if (!resident) {
+              mbar_wait(&b_full[bs], bph);
+              tc_fence_after();
+            } else if (tap == 0) {
+              tc_fence_after();                       // (the a_full wait above ordered this chunk's activation box)
+            }
             const uint32_t b_hi = smem_u32(b_base + bs * Cfg::B_SLOT);
             const uint32_t b_lo = b_hi + Cfg::B_PLANE;
             const uint32_t a_off = p.a_off[tap];
@@ -518,7 +548,7 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
                   }
                 }
               }
-              mma_commit_pair(&b_empty[bs], (uint16_t)3);
+              if (!resident) mma_commit_pair(&b_empty[bs], (uint16_t)3);
               if (tap == last_tap) mma_commit_pair(&a_empty[as], (uint16_t)3);
               if (tap == last_tap && kc == p.kchunks - 1) mma_commit_pair(&t_full[acc], (uint16_t)3);
             }
@@ -936,7 +966,12 @@ static int launch_tc2_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, con
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a_hi, a_lo, b_hi, b_lo, p);
+  // resident weight operand: single N tile and every slice of the layer fits the weight region (IMMB_B_RESIDENT=0: off)
+  static int resident_on = -1;
+  if (resident_on < 0) { const char* ev = getenv("IMMB_B_RESIDENT"); resident_on = (ev && atoi(ev) == 0) ? 0 : 1; }
+  Tc2Params pp = p;
+  pp.b_resident = (resident_on && p.n_tiles_n == 1 && p.n_taps * p.kchunks <= (int)Cfg::B_SLOTS) ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a_hi, a_lo, b_hi, b_lo, pp);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "conv_tc2_pair launch: %s", cudaGetErrorString(e));
   return IMMB_OK;

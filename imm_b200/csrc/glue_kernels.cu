@@ -622,6 +622,45 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const double* __r
   }
 }
 
+// Many second-level reductions in one launch (the bias gradients of all BN layers, deferred to the end of the backward
+// pass): item i owns blocks [block0, block0 + ceil(nvals / 32)); same summation order as reduce_partials_kernel; the
+// float value of each sum is written to out_f.
+__global__ void __launch_bounds__(1024) reduce_partials_multi_kernel(const immb_reduce_item* __restrict__ items, int n_items) {
+  __shared__ double sm[32][33];
+  int it = 0;
+  while (it + 1 < n_items && (int)blockIdx.x >= items[it + 1].block0) ++it;
+  const immb_reduce_item m = items[it];
+  const int v = ((int)blockIdx.x - m.block0) * 32 + threadIdx.x;
+  const int nblocks = m.nblocks, nvals = m.nvals;
+  double s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.0;
+  if (v < nvals) {
+    const double* pv = m.partials + v;
+    int b = threadIdx.y;
+    for (; b + 7 * 32 < nblocks; b += 8 * 32) {
+      double t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] = __ldcg(pv + (size_t)(b + 32 * j) * nvals);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += t[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (b + 32 * j < nblocks) s[j] += __ldcg(pv + (size_t)(b + 32 * j) * nvals);
+  }
+  sm[threadIdx.y][threadIdx.x] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+  __syncthreads();
+  if (threadIdx.y == 0 && v < nvals) {
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+#pragma unroll
+    for (int r = 0; r < 32; r += 4) {
+      t0 += sm[r][threadIdx.x]; t1 += sm[r + 1][threadIdx.x]; t2 += sm[r + 2][threadIdx.x]; t3 += sm[r + 3][threadIdx.x];
+    }
+    m.out_f[v] = (float)((t0 + t1) + (t2 + t3));
+  }
+}
+
 // Second level of the conv-epilogue BN statistics fused with bn_finalize: block = 32 channels x 32 row lanes sums the
 // partial rows of sum(y) and sum(y^2) in the same fixed order as reduce_partials_kernel, then lane row 0 finalises its
 // channel (one launch instead of two per BN layer; deterministic, no atomics).
@@ -1944,7 +1983,8 @@ extern "C" int immb_bn_bwd_apply(const float* g, int gcs, const float* y, int yc
                                  const float* scale, const float* shift, const float* mean,
                                  const float* invstd, int relu, const double* sums, void* dy_hi,
                                  void* dy_lo, float* dgamma, float* dbeta, double* dbias_acc, double* scratch,
-                                 size_t scratch_elems, int32_t* dy_scale, float* dbias_out, void* stream) {
+                                 size_t scratch_elems, int32_t* dy_scale, float* dbias_out, int defer_dbias,
+                                 void* stream) {
   IMMB_REQUIRE(g && y && sums && dy_hi && dgamma && dbeta && dbias_acc, "bn_bwd_apply: bad args");
   const bool v4 = vec_ok(C, gcs) && ycs % 4 == 0 && C <= 256 && aligned16(g) && aligned16(y) && aligned16(dy_hi) &&
                   aligned16(dy_lo);
@@ -1962,15 +2002,27 @@ extern "C" int immb_bn_bwd_apply(const float* g, int gcs, const float* y, int yc
     int rc = check_launch("bn_bwd_apply");
     if (rc) return rc;
     if (!two) {
-      IMMB_REQUIRE(!dbias_out, "bn_bwd_apply: the float bias-gradient output needs the two-level (scratch) path");
+      IMMB_REQUIRE(!dbias_out && !defer_dbias, "bn_bwd_apply: the float bias-gradient output needs the two-level (scratch) path");
       return rc;
     }
+    if (defer_dbias) return rc;       // the caller reduces scratch[immb_bn_bwd_apply_blocks][C] later (immb_reduce_partials_multi)
     return launch_reduce_partials(scratch, grid, C, dbias_acc, ST(stream), dbias_out);
   } else {
     bn_bwd_apply_kernel<<<red_grid(npix, C), dim3(32, kRedRows), 0, ST(stream)>>>(
         g, gcs, y, ycs, npix, C, scale, shift, mean, invstd, relu, sums, (float*)dy_hi, (float*)dy_lo, dgamma, dbeta, dbias_acc);
   }
   return check_launch("bn_bwd_apply");
+}
+
+extern "C" int immb_bn_bwd_apply_blocks(int64_t npix, int C) {
+  if (npix <= 0 || C <= 0 || !vec_ok(C, C) || C > 256) return 0;
+  return vred_grid(npix, vred_pix(npix, C, true));
+}
+
+extern "C" int immb_reduce_partials_multi(const immb_reduce_item* items, int n_items, int total_blocks, void* stream) {
+  IMMB_REQUIRE(items && n_items > 0 && total_blocks > 0, "reduce_partials_multi: bad args");
+  reduce_partials_multi_kernel<<<total_blocks, dim3(32, 32), 0, ST(stream)>>>(items, n_items);
+  return check_launch("reduce_partials_multi");
 }
 
 extern "C" int immb_bias_grad(const void* g_hi, const void* g_lo, int gcs, int64_t npix, int C, double* acc,

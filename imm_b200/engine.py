@@ -517,6 +517,32 @@ class IMMEngine(object):
       L.dgrad_stats_rows = (int(_lib.lib().immb_conv2d_dgrad_stats_rows(L.desc()))
                             if (L.needs_dgrad and getattr(L, 'producer', None) is not None) else 0)
       n_scr = max(n_scr, L.dgrad_stats_rows * 2 * L.cin)
+    # deferred bias-gradient reduction: per-layer partial buffers + device tables of immb_reduce_item
+    import ctypes
+    self._db_table = None
+    items, ren_items = [], []
+    for key, L in self.layers.items():
+      L.db_partials = None
+      if not L.bn:
+        continue
+      nb = int(call('immb_bn_bwd_apply_blocks', L.N * L.Ho * L.Wo, L.cout))
+      if nb <= 0:
+        continue
+      L.db_partials = torch.empty(nb * L.cout, dtype=torch.float64, device=dev)
+      it = (L.db_partials.data_ptr(), L.db.data_ptr(), nb, L.cout)
+      (ren_items if key.startswith('model/renderer/') else items).append(it)
+
+    def table(lst):
+      arr, b0 = (_lib.ReduceItem * len(lst))(), 0
+      for i, (part, out, nb, nv) in enumerate(lst):
+        arr[i].partials, arr[i].out_f, arr[i].nblocks, arr[i].nvals, arr[i].block0 = part, out, nb, nv, b0
+        b0 += (nv + 31) // 32
+      raw = torch.frombuffer(bytearray(ctypes.string_at(ctypes.addressof(arr), ctypes.sizeof(arr))), dtype=torch.uint8)
+      return raw.to(dev), len(lst), b0
+    if items and ren_items:
+      self._db_table_enc, self._db_n_enc, self._db_blocks_enc = table(items)
+      self._db_table_ren, self._db_n_ren, self._db_blocks_ren = table(ren_items)
+      self._db_table, self._db_n, self._db_blocks = table(items + ren_items)
     self.bn_scratch = torch.empty(n_scr, dtype=torch.float64, device=dev)
     self.bn_scratch_pose = torch.empty(n_scr, dtype=torch.float64, device=dev)      # the pose-branch stream's own scratch
 
@@ -950,11 +976,17 @@ class IMMEngine(object):
       else:
         call('immb_bn_bwd_reduce', g, gcs, L.y, L.cout, npix, L.cout, L.scale, L.shift, L.mean, L.invstd, relu,
              L.bsums, sc, sc.numel(), st)
-      # the bias gradient comes out of the second-level reduction as float (no accumulator, no cast launch)
-      direct_db = sc.numel() >= int(call('immb_bn_scratch_elems', npix, L.cout)) > 0
-      call('immb_bn_bwd_apply', g, gcs, L.y, L.cout, npix, L.cout, L.scale, L.shift, L.mean, L.invstd, relu,
-           L.bsums, L.dy.hi, L.dy.lo, L.dgamma, L.dbeta, L.dbias_acc, sc, sc.numel(), L.dy.scale,
-           L.db if direct_db else None, st)
+      if L.db_partials is not None:
+        # the per-block partial sums of the bias gradient stay in the layer's own buffer; ONE launch at the end of the
+        # backward pass reduces them for all layers (no accumulator, no cast, no second-level launch per layer)
+        call('immb_bn_bwd_apply', g, gcs, L.y, L.cout, npix, L.cout, L.scale, L.shift, L.mean, L.invstd, relu,
+             L.bsums, L.dy.hi, L.dy.lo, L.dgamma, L.dbeta, L.dbias_acc, L.db_partials, L.db_partials.numel(), L.dy.scale,
+             None, 1, st)
+        direct_db = True
+      else:
+        direct_db = False
+        call('immb_bn_bwd_apply', g, gcs, L.y, L.cout, npix, L.cout, L.scale, L.shift, L.mean, L.invstd, relu,
+             L.bsums, L.dy.hi, L.dy.lo, L.dgamma, L.dbeta, L.dbias_acc, sc, sc.numel(), L.dy.scale, None, 0, st)
       dy = L.dy
     else:
       dy = g if isinstance(g, Planes) else None
@@ -1068,6 +1100,11 @@ class IMMEngine(object):
       g = self._block_bwd(L, g, gcs)
       gcs = L.xcs
     comm = None
+    early_ren_db = allreduce is not None and self.overlap_allreduce and self._db_table is not None
+    if early_ren_db:
+      # the renderer's bias gradients belong to the first bucket: reduce their partials now (items are in layer order,
+      # the renderer's are the tail of the table)
+      call('immb_reduce_partials_multi', self._db_table_ren, self._db_n_ren, self._db_blocks_ren, _lib.stream_ptr())
     if allreduce is not None and self.overlap_allreduce:
       if self.comm_stream is None:
         self.comm_stream = torch.cuda.Stream(device=self.dev)
@@ -1109,6 +1146,11 @@ class IMMEngine(object):
       self._join(self.pose_stream, 'bwd_join')
     if self.wgrad_stream is not None:
       self._join(self.wgrad_stream, 'wg_join')
+    if self._db_table is not None:
+      if early_ren_db:
+        call('immb_reduce_partials_multi', self._db_table_enc, self._db_n_enc, self._db_blocks_enc, _lib.stream_ptr())
+      else:
+        call('immb_reduce_partials_multi', self._db_table, self._db_n, self._db_blocks, _lib.stream_ptr())
     if allreduce is not None:
       if comm is not None:
         allreduce(self.flat_g[:self.ren_grad_offset])

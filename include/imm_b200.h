@@ -234,7 +234,17 @@ int immb_bn_bwd_apply(const float* g, int g_cstride, const float* y, int y_cstri
                       const float* scale, const float* shift, const float* mean, const float* invstd,
                       int relu, const double* sums, void* dy_hi, void* dy_lo, float* dgamma, float* dbeta,
                       double* dbias_acc, double* scratch, size_t scratch_elems, int32_t* dy_scale, float* dbias_out,
-                      void* stream);
+                      int defer_dbias, void* stream);
+/* defer_dbias != 0 (scratch path): the bias-gradient partials stay in scratch as [immb_bn_bwd_apply_blocks(npix, C)][C]
+ * doubles; the caller sums the partials of ALL layers with one immb_reduce_partials_multi launch (items: device array;
+ * item i owns blocks [block0, block0 + ceil(nvals / 32)); out_f[v] = float(sum over nblocks rows), fixed order). */
+typedef struct {
+  const double* partials;
+  float* out_f;
+  int32_t nblocks, nvals, block0, reserved_;
+} immb_reduce_item;
+int immb_bn_bwd_apply_blocks(int64_t npix, int C);
+int immb_reduce_partials_multi(const immb_reduce_item* items, int n_items, int total_blocks, void* stream);
 /* column sums: acc[C] (double, zeroed) += sum over pixels of g[:, c] */
 int immb_bias_grad(const void* g_hi, const void* g_lo, int g_cstride, int64_t npix, int C, double* acc,
                    const int32_t* g_scale, void* stream);
