@@ -523,7 +523,8 @@ static int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, i
                         int esize = 4) {
   uint64_t dims[5], str[4];
   const uint64_t es = (uint64_t)esize;
-  uint32_t box[5] = {(uint32_t)(128 / esize), (uint32_t)box_w, 1, (uint32_t)box_h, (uint32_t)box_n};
+  const uint32_t row_bytes = swz == CU_TENSOR_MAP_SWIZZLE_64B ? 64 : 128;
+  uint32_t box[5] = {(uint32_t)(row_bytes / esize), (uint32_t)box_w, 1, (uint32_t)box_h, (uint32_t)box_n};
   if (!parity_split) {
     dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = N;
     str[0] = (uint64_t)cs * es; str[1] = (uint64_t)W * cs * es; str[2] = (uint64_t)W * cs * es;
@@ -561,8 +562,10 @@ static int make_w_map(CUtensorMap* m, const void* base, int taps, int Nn, int Kd
 // the standard 128-byte swizzle for both majors
 int tc_make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int cs, bool parity_split,
                     int box_w, int box_h, int box_n, int swizzle_mn, int esize) {
-  return make_act_map(m, base, N, H, W, C, cs, parity_split, box_w, box_h, box_n,
-                      (swizzle_mn && esize == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, esize);
+  CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B;
+  if (swizzle_mn == 2) swz = CU_TENSOR_MAP_SWIZZLE_64B;                       // 64-byte rows (32 fp16 channels)
+  else if (swizzle_mn && esize == 4) swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  return make_act_map(m, base, N, H, W, C, cs, parity_split, box_w, box_h, box_n, swz, esize);
 }
 int tc_make_w_map(CUtensorMap* m, const void* base, int taps, int Nn, int Kd, int bn, int esize) {
   return make_w_map(m, base, taps, Nn, Kd, bn, esize);

@@ -1379,25 +1379,31 @@ struct Wg16Params {
 
 // RPC = filter rows per CTA: 1 (the CTA's row comes from blockIdx.z) or 3 (narrow N tiles: the twelve accumulators of all
 // three rows fit TMEM, X and dY are streamed once instead of three times; the window then carries the 2 halo rows)
-template <int BN, int STAGES, int RPC = 1>
+// C32 (layers with <= 32 input channels): the X window is fetched as 64-byte rows (32 channels, SWIZZLE_64B), so that an
+// MMA's M = 128 is FOUR column-tap atoms of 32 channels one pixel apart (s = 0..3, the 4th ignored) instead of two
+// half-empty 64-channel atoms: one MMA group per filter row instead of two.
+template <int BN, int STAGES, int RPC = 1, bool C32 = false>
 struct Wg16Cfg {
   static constexpr uint32_t A_ROWS = 4 + RPC - 1;
-  static constexpr uint32_t A_PLANE = A_ROWS * 16 * 128;                  // 8192 B window (12288 B with the halo rows)
+  static constexpr uint32_t A_ROW_BYTES = C32 ? 64 : 128;
+  static constexpr uint32_t A_PITCH = 16 * A_ROW_BYTES;                    // bytes between image rows of the window
+  static constexpr uint32_t A_PLANE = (A_ROWS * A_PITCH + 1023) / 1024 * 1024;
+  static constexpr int GROUPS = C32 ? 1 : 2;                              // MMA groups per filter row
   static constexpr uint32_t NB = (BN + 63) / 64;                          // dY boxes of 64 channels
   static constexpr uint32_t B_PLANE = NB * 4096;
   static constexpr uint32_t STAGE_BYTES = (A_PLANE + B_PLANE) * 2;        // hi + lo planes of both operands
   static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
-  static constexpr int ACC_COLS = RPC * 4 * BN;
+  static constexpr int ACC_COLS = RPC * GROUPS * 2 * BN;
   static constexpr int TMEM_COLS = ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512));
-  static_assert(ACC_COLS <= 512, "four accumulators of BN columns per filter row");
+  static_assert(ACC_COLS <= 512, "[main | cross] accumulators of BN columns per MMA group and filter row");
 };
 
-template <int BN, int STAGES, int RPC>
+template <int BN, int STAGES, int RPC, bool C32>
 __global__ void __launch_bounds__(192, 1)
 conv_tc2_wgrad16_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_constant__ CUtensorMap mapX_lo,
                         const __grid_constant__ CUtensorMap mapY_hi, const __grid_constant__ CUtensorMap mapY_lo,
                         const __grid_constant__ Wg16Params p) {
-  using Cfg = Wg16Cfg<BN, STAGES, RPC>;
+  using Cfg = Wg16Cfg<BN, STAGES, RPC, C32>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
@@ -1406,7 +1412,7 @@ conv_tc2_wgrad16_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __gri
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
-  const int ci0 = blockIdx.x * 64;
+  const int ci0 = blockIdx.x * (C32 ? 32 : 64);
   const int n_off = blockIdx.y * BN;
   const int r = RPC == 3 ? 0 : blockIdx.z / p.splits;       // first filter row of this CTA
   const int split = RPC == 3 ? blockIdx.z : blockIdx.z - r * p.splits;
@@ -1437,7 +1443,7 @@ conv_tc2_wgrad16_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __gri
       const int n = tile / (p.tiles_w * p.tiles_h);
       uint8_t* st = smem + s * Cfg::STAGE_BYTES;
       if (elect_one()) {
-        mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+        mbar_expect_tx(&full[s], 2 * (Cfg::A_ROWS * Cfg::A_PITCH + Cfg::B_PLANE));
         tma_load_5d(st, &mapX_hi, &full[s], ci0, twi * 8 - 1, 0, thi * 4 + r - 1, n);
         tma_load_5d(st + Cfg::A_PLANE, &mapX_lo, &full[s], ci0, twi * 8 - 1, 0, thi * 4 + r - 1, n);
         uint8_t* sb = st + Cfg::A_PLANE * 2;
@@ -1470,11 +1476,12 @@ conv_tc2_wgrad16_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __gri
 #pragma unroll
             for (int rr = 0; rr < RPC; ++rr) {
 #pragma unroll
-              for (int g = 0; g < 2; ++g) {                               // g = 0: taps s = 0,1;  g = 1: tap s = 2 (+ ignored)
-                const uint32_t ao = ((uint32_t)(2 * j + rr) * 16u + (uint32_t)(2 * g)) * 128u;
-                const uint64_t da_hi = smem_desc_sw128(a_hi + ao, 128, 2048, 2);
-                const uint64_t da_lo = smem_desc_sw128(a_lo + ao, 128, 2048, 2);
-                const uint32_t d_main = tmem_base + (uint32_t)((rr * 2 + g) * 2 * BN);
+              for (int g = 0; g < Cfg::GROUPS; ++g) {                     // g = 0: taps s = 0,1 (C32: s = 0..3);  g = 1: tap s = 2 (+ ignored)
+                const uint32_t ao = (uint32_t)(2 * j + rr) * Cfg::A_PITCH + (uint32_t)(2 * g) * Cfg::A_ROW_BYTES;
+                // LBO = one pixel (the next column tap), SBO = one image row (the next 8 K rows); C32: 64-byte swizzle
+                const uint64_t da_hi = smem_desc_sw128(a_hi + ao, Cfg::A_ROW_BYTES, Cfg::A_PITCH, C32 ? 4 : 2);
+                const uint64_t da_lo = smem_desc_sw128(a_lo + ao, Cfg::A_ROW_BYTES, Cfg::A_PITCH, C32 ? 4 : 2);
+                const uint32_t d_main = tmem_base + (uint32_t)((rr * Cfg::GROUPS + g) * 2 * BN);
                 const uint32_t d_cross = d_main + (uint32_t)BN;
                 mma_f16(d_main, da_hi, db_hi, idesc, acc);
                 mma_f16(d_cross, da_hi, db_lo, idesc, acc);
@@ -1491,15 +1498,15 @@ conv_tc2_wgrad16_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __gri
   } else if (num_k > 0) {
     const int q = warp & 3;
     const int m = q * 32 + lane;
-    const int g_row = m >> 6;                  // MN atom of this TMEM lane: column tap s = 2*g + g_row
-    const int ci = ci0 + (m & 63);
+    const int g_row = C32 ? (m >> 5) : (m >> 6);      // MN atom of this TMEM lane: column tap s = 2*g + g_row (C32: s = g_row)
+    const int ci = ci0 + (C32 ? (m & 31) : (m & 63));
     const int e = __ldg(p.x_scale) + __ldg(p.dy_scale);
     const float s_main = exp2i(-e), s_cross = exp2i(-e - 11);
     mbar_wait(tmem_full, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int rg = 0; rg < 2 * RPC; ++rg) {
-      const int rr = rg >> 1, g = rg & 1;
+    for (int rg = 0; rg < Cfg::GROUPS * RPC; ++rg) {
+      const int rr = rg / Cfg::GROUPS, g = rg % Cfg::GROUPS;
       const int s_tap = 2 * g + g_row;
       const bool row_ok = (s_tap < 3) && (ci < p.Cin);
 #pragma unroll 1
@@ -1533,12 +1540,12 @@ conv_tc2_wgrad16_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __gri
   }
 }
 
-template <int BN, int RPC>
+template <int BN, int RPC, bool C32 = false>
 static int launch_wg16(const CUtensorMap& x_hi, const CUtensorMap& x_lo, const CUtensorMap& y_hi,
                        const CUtensorMap& y_lo, const Wg16Params& p, dim3 grid, cudaStream_t st) {
   constexpr int STAGES = BN <= 64 ? 6 : 5;
-  using Cfg = Wg16Cfg<BN, STAGES, RPC>;
-  auto kern = conv_tc2_wgrad16_kernel<BN, STAGES, RPC>;
+  using Cfg = Wg16Cfg<BN, STAGES, RPC, C32>;
+  auto kern = conv_tc2_wgrad16_kernel<BN, STAGES, RPC, C32>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
@@ -1562,7 +1569,10 @@ static int conv_tc2_wgrad16_run(const immb_conv_desc* d, const void* x_hi, const
   p.x_scale = d->x_scale; p.dy_scale = d->y_scale;
   const int bn = d->Cout > 64 ? 128 : (d->Cout > 32 ? 64 : 32);      // (narrower tiles would read past their TMEM columns)
   const int n_tiles = ceil_div(d->Cout, bn);
-  const int c_tiles = ceil_div(d->Cin, 64);
+  static int c32_on = -1;
+  if (c32_on < 0) { const char* ev = getenv("IMMB_WG_C32"); c32_on = (ev && atoi(ev) == 0) ? 0 : 1; }
+  const bool c32 = c32_on && bn == 32 && d->Cin <= 32;                 // 32-channel window atoms (SWIZZLE_64B)
+  const int c_tiles = ceil_div(d->Cin, c32 ? 32 : 64);
   const int rpc = bn == 32 ? 3 : 1;                                  // all three filter rows in one CTA when TMEM allows
   int splits = kNumSMs / (c_tiles * n_tiles * (rpc == 3 ? 1 : 3));
   if (splits > p.total_tiles) splits = p.total_tiles;
@@ -1575,13 +1585,15 @@ static int conv_tc2_wgrad16_run(const immb_conv_desc* d, const void* x_hi, const
   CUtensorMap mx_hi, mx_lo, my_hi, my_lo;
   int rc;
   const int box_h = 4 + rpc - 1;
-  if ((rc = tc_make_act_map(&mx_hi, x_hi, d->N, d->H, d->W, d->Cin, d->x_cstride, false, 16, box_h, 1, 1, 2))) return rc;
-  if ((rc = tc_make_act_map(&mx_lo, x_lo, d->N, d->H, d->W, d->Cin, d->x_cstride, false, 16, box_h, 1, 1, 2))) return rc;
+  const int xsw = c32 ? 2 : 1;        // tc_make_act_map: 2 = 32-channel rows with the 64-byte swizzle
+  if ((rc = tc_make_act_map(&mx_hi, x_hi, d->N, d->H, d->W, d->Cin, d->x_cstride, false, 16, box_h, 1, xsw, 2))) return rc;
+  if ((rc = tc_make_act_map(&mx_lo, x_lo, d->N, d->H, d->W, d->Cin, d->x_cstride, false, 16, box_h, 1, xsw, 2))) return rc;
   if ((rc = tc_make_act_map(&my_hi, dy_hi, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, 8, 4, 1, 1, 2))) return rc;
   if ((rc = tc_make_act_map(&my_lo, dy_lo, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, 8, 4, 1, 1, 2))) return rc;
   dim3 grid(c_tiles, n_tiles, (rpc == 3 ? 1 : 3) * splits);
   if (bn == 128) return launch_wg16<128, 1>(mx_hi, mx_lo, my_hi, my_lo, p, grid, st);
   if (bn == 64) return launch_wg16<64, 1>(mx_hi, mx_lo, my_hi, my_lo, p, grid, st);
+  if (c32) return launch_wg16<32, 3, true>(mx_hi, mx_lo, my_hi, my_lo, p, grid, st);
   return launch_wg16<32, 3>(mx_hi, mx_lo, my_hi, my_lo, p, grid, st);
 }
 

@@ -1991,7 +1991,8 @@ extern "C" int immb_bn_bwd_apply(const float* g, int gcs, const float* y, int yc
   IMMB_REQUIRE(!dy_scale || (v4 && dy_lo), "bn_bwd_apply: fp16 planes need the vectorised path");
   if (v4) {
     BnBwdArgs a{g, y, scale, shift, mean, invstd, gcs, ycs, relu};
-    const bool two = scratch && scratch_elems >= immb_bn_scratch_elems(npix, C);
+    // two-level path: one row of C partial sums per block (immb_bn_bwd_apply_blocks rows)
+    const bool two = scratch && scratch_elems >= (size_t)vred_grid(npix, vred_pix(npix, C, true)) * (size_t)C;
     const int ppb = vred_pix(npix, C, two), grid = vred_grid(npix, ppb);
     if (dy_scale)
       bn_bwd_apply4_kernel<true><<<grid, 256, vred_smem(1), ST(stream)>>>(a, npix, C, sums, make_pl<true>(dy_hi, dy_lo, dy_scale),
