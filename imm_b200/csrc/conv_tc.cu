@@ -663,10 +663,16 @@ static int dispatch_fwd(int bn, int passes, const CUtensorMap& a_hi, const CUten
   // longest K loop of any CTA of this launch
   int max_k = p.n_taps * p.kchunks;
   for (int c = 1; c < p.n_classes; ++c) max_k = p.n_taps_c[c - 1] * p.kchunks > max_k ? p.n_taps_c[c - 1] * p.kchunks : max_k;
-  if (!f16 && passes == 3 && max_k <= 18 && bn <= 64) {
-    if (bn == 16) return launch_fwd<16, 3, false, true>(a_hi, a_lo, b_hi, b_lo, p, grid, st);
-    if (bn == 32) return launch_fwd<32, 3, false, true>(a_hi, a_lo, b_hi, b_lo, p, grid, st);
-    if (bn == 64) return launch_fwd<64, 3, false, true>(a_hi, a_lo, b_hi, b_lo, p, grid, st);
+  if (passes == 3 && max_k <= 18 && bn <= 64) {
+    if (f16) {
+      if (bn == 16) return launch_fwd<16, 3, true, true>(a_hi, a_lo, b_hi, b_lo, p, grid, st);
+      if (bn == 32) return launch_fwd<32, 3, true, true>(a_hi, a_lo, b_hi, b_lo, p, grid, st);
+      if (bn == 64) return launch_fwd<64, 3, true, true>(a_hi, a_lo, b_hi, b_lo, p, grid, st);
+    } else {
+      if (bn == 16) return launch_fwd<16, 3, false, true>(a_hi, a_lo, b_hi, b_lo, p, grid, st);
+      if (bn == 32) return launch_fwd<32, 3, false, true>(a_hi, a_lo, b_hi, b_lo, p, grid, st);
+      if (bn == 64) return launch_fwd<64, 3, false, true>(a_hi, a_lo, b_hi, b_lo, p, grid, st);
+    }
   }
   if (f16) {
     if (passes != 3) return set_error(IMMB_ERR_INVALID, "conv_tc: single-pass fp16 is not built");

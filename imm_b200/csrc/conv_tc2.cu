@@ -350,7 +350,10 @@ struct Tc2PairCfg {
   static constexpr uint32_t B_FIT = ROOM / B_SLOT;
   // ring depth 6 for streaming; layers whose whole weight operand fits (narrow layers: 9 taps x 1-2 chunks of <= 8 KB)
   // use the region as resident storage (Tc2Params::b_resident), so take what the budget gives up to 18 slots
-  static constexpr uint32_t B_SLOTS = B_FIT > 18 ? 18 : B_FIT;
+#ifndef IMMB_PAIR_B_CAP
+#define IMMB_PAIR_B_CAP 18
+#endif
+  static constexpr uint32_t B_SLOTS = B_FIT > IMMB_PAIR_B_CAP ? IMMB_PAIR_B_CAP : B_FIT;
   static_assert(B_SLOTS >= 2, "weight ring needs two slots");
   static constexpr uint32_t SMEM_BYTES = A_SLOTS * A_SLOT + B_SLOTS * B_SLOT + STATS_BYTES + 1024 + 512;
   // 3-pass: the two cross terms (hi*lo, lo*hi; ~2^-11 of the main term) accumulate in their OWN TMEM columns
@@ -1597,8 +1600,246 @@ static int conv_tc2_wgrad16_run(const immb_conv_desc* d, const void* x_hi, const
   return launch_wg16<32, 3>(mx_hi, mx_lo, my_hi, my_lo, p, grid, st);
 }
 
+// =============================================================================================================
+// fp16 wgrad of the STRIDE-2 3x3 layers (TF SAME on even sizes: no padding before, one row / column after):
+//   dW[r][s][ci][co] = sum_{n,i,j} X[n, 2i+r, 2j+s, ci] * dY[n, i, j, co]
+// X is read through its parity-split view (c + wpar*C, w/2, hpar, h/2, n): tap (r, s) is the view's channel block
+// wpar = s & 1 at row parity hpar = r & 1, shifted by (r >> 1, s >> 1) view pixels -- so each tap is again a plain
+// shifted window and the kernel is the stride-1 one with a different operand map.  One CTA = one filter row r, one
+// chunk of input channels, BN output channels, a split-K range of 4x8-pixel dY tiles.
+//   C32 (C = 32): one 128-byte view row holds BOTH column parities of a pixel pair = taps s = 0 | 1 (32 rows each);
+//       the same window one view pixel further = s = 2 | (unused): ONE MMA of M = 128 covers the filter row.
+//   else (64 | C): the wpar = 0 and wpar = 1 chunks are separate windows: MMA group 0 = the wpar-0 window at shifts
+//       0 and 1 (s = 0, 2), group 1 = the wpar-1 window (s = 1, upper atom unused).
+// =============================================================================================================
+template <int BN, int STAGES, bool C32>
+struct Wg16S2Cfg {
+  static constexpr uint32_t NWIN = C32 ? 1 : 2;                           // X windows per plane per stage
+  static constexpr uint32_t A_WIN = 4 * 16 * 128;                         // 4 view rows x 16 view pixels x 128 B
+  static constexpr uint32_t A_PLANE = NWIN * A_WIN;
+  static constexpr uint32_t NB = (BN + 63) / 64;
+  static constexpr uint32_t B_PLANE = NB * 4096;
+  static constexpr uint32_t STAGE_BYTES = (A_PLANE + B_PLANE) * 2;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int GROUPS = C32 ? 1 : 2;
+  static constexpr int ACC_COLS = GROUPS * 2 * BN;
+  static constexpr int TMEM_COLS = ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512));
+  static_assert(ACC_COLS <= 512, "accumulators");
+};
+
+template <int BN, int STAGES, bool C32>
+__global__ void __launch_bounds__(192, 1)
+conv_tc2_wgrad16_s2_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_constant__ CUtensorMap mapX_lo,
+                           const __grid_constant__ CUtensorMap mapY_hi, const __grid_constant__ CUtensorMap mapY_lo,
+                           const __grid_constant__ Wg16Params p) {
+  using Cfg = Wg16S2Cfg<BN, STAGES, C32>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const int ci0 = C32 ? 0 : blockIdx.x * 64;
+  const int n_off = blockIdx.y * BN;
+  const int r = blockIdx.z / p.splits;
+  const int split = blockIdx.z - r * p.splits;
+  const int hpar = r & 1, dh = r >> 1;
+  const int t_begin = split * p.tiles_per_split;
+  int t_end = t_begin + p.tiles_per_split;
+  if (t_end > p.total_tiles) t_end = p.total_tiles;
+  const int num_k = t_end - t_begin;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    for (int kt = 0; kt < num_k; ++kt) {
+      const int s = kt % STAGES;
+      const uint32_t ph = (kt / STAGES) & 1;
+      mbar_wait(&empty[s], ph ^ 1);
+      const int tile = t_begin + kt;
+      const int twi = tile % p.tiles_w;
+      const int thi = (tile / p.tiles_w) % p.tiles_h;
+      const int n = tile / (p.tiles_w * p.tiles_h);
+      uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+      if (elect_one()) {
+        mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+#pragma unroll
+        for (uint32_t wv = 0; wv < Cfg::NWIN; ++wv) {
+          const int c = ci0 + (int)wv * p.Cin;                            // view channel of the wpar = wv chunk
+          tma_load_5d(st + wv * Cfg::A_WIN, &mapX_hi, &full[s], c, twi * 8, hpar, thi * 4 + dh, n);
+          tma_load_5d(st + Cfg::A_PLANE + wv * Cfg::A_WIN, &mapX_lo, &full[s], c, twi * 8, hpar, thi * 4 + dh, n);
+        }
+        uint8_t* sb = st + Cfg::A_PLANE * 2;
+#pragma unroll
+        for (uint32_t j = 0; j < Cfg::NB; ++j) {
+          tma_load_5d(sb + j * 4096, &mapY_hi, &full[s], n_off + (int)j * 64, twi * 8, 0, thi * 4, n);
+          tma_load_5d(sb + Cfg::B_PLANE + j * 4096, &mapY_lo, &full[s], n_off + (int)j * 64, twi * 8, 0, thi * 4, n);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    if (num_k > 0) {
+      constexpr uint32_t idesc = idesc_f16(128, BN, 1, 1);
+      for (int kt = 0; kt < num_k; ++kt) {
+        const int s = kt % STAGES;
+        const uint32_t ph = (kt / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint32_t a_lo = a_hi + Cfg::A_PLANE;
+        const uint32_t b_hi = a_hi + Cfg::A_PLANE * 2;
+        const uint32_t b_lo = b_hi + Cfg::B_PLANE;
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {                                   // dY rows 2j, 2j+1 of the tile = K 16
+            const uint32_t acc = (kt > 0 || j > 0) ? 1u : 0u;
+            const uint64_t db_hi = smem_desc_sw128(b_hi + (uint32_t)j * 2048u, 4096, 1024, 2);
+            const uint64_t db_lo = smem_desc_sw128(b_lo + (uint32_t)j * 2048u, 4096, 1024, 2);
+#pragma unroll
+            for (int g = 0; g < Cfg::GROUPS; ++g) {
+              // window g, view rows 2j / 2j+1; MN atoms = the window at view-pixel shifts 0 and 1 (LBO = 128 B)
+              const uint32_t ao = (uint32_t)g * Cfg::A_WIN + (uint32_t)(2 * j) * 2048u;
+              const uint64_t da_hi = smem_desc_sw128(a_hi + ao, 128, 2048, 2);
+              const uint64_t da_lo = smem_desc_sw128(a_lo + ao, 128, 2048, 2);
+              const uint32_t d_main = tmem_base + (uint32_t)(g * 2 * BN);
+              const uint32_t d_cross = d_main + (uint32_t)BN;
+              mma_f16(d_main, da_hi, db_hi, idesc, acc);
+              mma_f16(d_cross, da_hi, db_lo, idesc, acc);
+              mma_f16(d_cross, da_lo, db_hi, idesc, 1u);
+            }
+          }
+          mma_commit(&empty[s]);
+          if (kt == num_k - 1) mma_commit(tmem_full);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (num_k > 0) {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int atom = m >> 6;                   // view-pixel shift of this TMEM lane's MN atom
+    const int e = __ldg(p.x_scale) + __ldg(p.dy_scale);
+    const float s_main = exp2i(-e), s_cross = exp2i(-e - 11);
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int g = 0; g < Cfg::GROUPS; ++g) {
+      // column tap and input channel of this lane
+      int s_tap, ci;
+      if (C32) { s_tap = 2 * atom + ((m >> 5) & 1); ci = m & 31; }
+      else { s_tap = g == 0 ? 2 * atom : (atom == 0 ? 1 : 3); ci = ci0 + (m & 63); }
+      const bool row_ok = (s_tap < 3) && (ci < p.Cin);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32], v2[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 2 * BN + c0), v);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 2 * BN + BN + c0), v2);
+        if (!row_ok) continue;
+        const int col0 = n_off + c0;
+        if (col0 >= p.Cout) continue;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(v2[j], s_cross, v[j] * s_main);
+        float* o = p.dw + ((size_t)(r * 3 + s_tap) * p.Cin + ci) * p.Cout + col0;
+        if ((p.Cout & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dw) & 15) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (col0 + j < p.Cout) red_add_v4(o + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.Cout) atomicAdd(o + j, v[j]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN, bool C32>
+static int launch_wg16_s2(const CUtensorMap& x_hi, const CUtensorMap& x_lo, const CUtensorMap& y_hi,
+                          const CUtensorMap& y_lo, const Wg16Params& p, dim3 grid, cudaStream_t st) {
+  constexpr int STAGES = BN <= 64 ? 6 : 4;
+  using Cfg = Wg16S2Cfg<BN, STAGES, C32>;
+  auto kern = conv_tc2_wgrad16_s2_kernel<BN, STAGES, C32>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "conv_tc2_wgrad16_s2 smem attr: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  kern<<<grid, 192, Cfg::SMEM_BYTES, st>>>(x_hi, x_lo, y_hi, y_lo, p);
+  return check_launch("conv_tc2_wgrad16_s2_kernel");
+}
+
+// stride-2 3x3, even sizes (TF SAME: pads before = 0), contiguous input channels, C = 32 or a multiple of 64
+bool conv_tc2_wgrad_s2_eligible(const immb_conv_desc* d) {
+  if (!conv_tc2_enabled()) return false;
+  if (d->x_layout != IMMB_XLAYOUT_NHWC || d->kh != 3 || d->kw != 3 || d->stride != 2) return false;
+  if (d->H % 2 || d->W % 2 || d->pad_t != 0 || d->pad_l != 0) return false;
+  if (d->Ho % 4 || d->Wo % 8 || d->x_cstride != d->Cin) return false;
+  return d->Cin == 32 || d->Cin % 64 == 0;
+}
+
+static int conv_tc2_wgrad16_s2_run(const immb_conv_desc* d, const void* x_hi, const void* x_lo, const void* dy_hi,
+                                   const void* dy_lo, float* dw, cudaStream_t st) {
+  if (!d->x_scale || !d->y_scale) return set_error(IMMB_ERR_INVALID, "conv_tc2_wgrad: fp16 planes need x_scale / y_scale");
+  if (d->y_cstride % 8) return set_error(IMMB_ERR_UNSUPPORTED, "conv_tc2_wgrad: fp16 planes need 8-channel strides");
+  Wg16Params p;
+  memset(&p, 0, sizeof(p));
+  p.tiles_w = d->Wo / 8; p.tiles_h = d->Ho / 4; p.n_img = d->N;
+  p.total_tiles = p.tiles_w * p.tiles_h * d->N;
+  p.dw = dw; p.Cin = d->Cin; p.Cout = d->Cout;
+  p.x_scale = d->x_scale; p.dy_scale = d->y_scale;
+  const bool c32 = d->Cin == 32;
+  const int bn = d->Cout > 64 ? 128 : (d->Cout > 32 ? 64 : 32);
+  const int n_tiles = ceil_div(d->Cout, bn);
+  const int c_tiles = c32 ? 1 : d->Cin / 64;
+  int splits = kNumSMs / (c_tiles * n_tiles * 3);
+  if (splits > p.total_tiles) splits = p.total_tiles;
+  if (splits < 1) splits = 1;
+  p.tiles_per_split = ceil_div(p.total_tiles, splits);
+  splits = ceil_div(p.total_tiles, p.tiles_per_split);
+  p.splits = splits;
+  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)9 * d->Cin * d->Cout, st);
+  if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "wgrad memset: %s", cudaGetErrorString(e));
+  CUtensorMap mx_hi, mx_lo, my_hi, my_lo;
+  int rc;
+  // parity-split view of X, 16 view pixels x 4 view rows per window
+  if ((rc = tc_make_act_map(&mx_hi, x_hi, d->N, d->H, d->W, d->Cin, d->x_cstride, true, 16, 4, 1, 1, 2))) return rc;
+  if ((rc = tc_make_act_map(&mx_lo, x_lo, d->N, d->H, d->W, d->Cin, d->x_cstride, true, 16, 4, 1, 1, 2))) return rc;
+  if ((rc = tc_make_act_map(&my_hi, dy_hi, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, 8, 4, 1, 1, 2))) return rc;
+  if ((rc = tc_make_act_map(&my_lo, dy_lo, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, 8, 4, 1, 1, 2))) return rc;
+  dim3 grid(c_tiles, n_tiles, 3 * splits);
+  if (c32) {
+    if (bn == 128) return launch_wg16_s2<128, true>(mx_hi, mx_lo, my_hi, my_lo, p, grid, st);
+    if (bn == 64) return launch_wg16_s2<64, true>(mx_hi, mx_lo, my_hi, my_lo, p, grid, st);
+    return launch_wg16_s2<32, true>(mx_hi, mx_lo, my_hi, my_lo, p, grid, st);
+  }
+  if (bn == 128) return launch_wg16_s2<128, false>(mx_hi, mx_lo, my_hi, my_lo, p, grid, st);
+  if (bn == 64) return launch_wg16_s2<64, false>(mx_hi, mx_lo, my_hi, my_lo, p, grid, st);
+  return launch_wg16_s2<32, false>(mx_hi, mx_lo, my_hi, my_lo, p, grid, st);
+}
+
 bool conv_tc2_wgrad_eligible(const immb_conv_desc* d) {
   if (!conv_tc2_enabled()) return false;
+  if (prec_is_f16(d->precision) && conv_tc2_wgrad_s2_eligible(d)) return true;
   if (d->x_layout != IMMB_XLAYOUT_NHWC || d->kh != 3 || d->kw != 3 || d->stride != 1) return false;
   if (d->H % 4 || d->W % 8 || d->pad_t != 1 || d->pad_l != 1) return false;
   return true;
@@ -1622,6 +1863,7 @@ static int launch_wg2(const CUtensorMap& x_hi, const CUtensorMap& x_lo, const CU
 
 int conv_tc2_wgrad_run(const immb_conv_desc* d, const void* x_hi_, const void* x_lo_, const void* dy_hi_,
                        const void* dy_lo_, float* dw, cudaStream_t st) {
+  if (prec_is_f16(d->precision) && d->stride == 2) return conv_tc2_wgrad16_s2_run(d, x_hi_, x_lo_, dy_hi_, dy_lo_, dw, st);
   if (prec_is_f16(d->precision)) return conv_tc2_wgrad16_run(d, x_hi_, x_lo_, dy_hi_, dy_lo_, dw, st);
   const float *x_hi = (const float*)x_hi_, *x_lo = (const float*)x_lo_, *dy_hi = (const float*)dy_hi_, *dy_lo = (const float*)dy_lo_;
   const int passes = d->precision == IMMB_PREC_TF32 ? 1 : 3;

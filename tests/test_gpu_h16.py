@@ -77,8 +77,10 @@ H16_CASES = [
   (1, 32, 32, 32, 9, 3, 1, None),        # renderer last conv: Cout = 9 in a 16-channel-stride tensor
   (3, 16, 16, 64, 96, 3, 1, None),       # N tile of 96, odd image count
   (1, 16, 16, 320, 192, 3, 1, None),
-  (4, 8, 8, 128, 128, 3, 1, None),       # 8x8 maps: conv_tc_kernel (fwd / dgrad only: no halo wgrad at H % 4 ... W % 8)
-  (2, 32, 32, 32, 64, 3, 2, None),       # stride 2 (fwd / dgrad only)
+  (4, 8, 8, 128, 128, 3, 1, None),       # 8x8 maps: conv_tc_kernel forward / dgrad, halo wgrad
+  (2, 32, 32, 32, 64, 3, 2, None),       # stride 2, C = 32: both column parities of the view in one 64-channel window
+  (2, 64, 64, 64, 128, 3, 2, None),      # stride 2, C = 64: one window per column parity
+  (1, 32, 32, 128, 256, 3, 2, None),     # stride 2, C = 128: two channel chunks, two N tiles
 ]
 
 
@@ -96,7 +98,7 @@ def test_conv_h16_engine(case):
   engines = [_lib.lib().immb_conv_engine_for(d, op) for op in range(3)]
   assert engines[:2] == [_lib.ENGINE_TC] * 2
   has_wgrad = engines[2] == _lib.ENGINE_TC
-  assert has_wgrad == (stride == 1 and H % 4 == 0 and W % 8 == 0 and k == 3)
+  assert has_wgrad == (k == 3 and ((stride == 1 and H % 4 == 0 and W % 8 == 0) or (stride == 2 and (H // 2) % 4 == 0 and (W // 2) % 8 == 0)))
   tol = 2e-5 if k * k * Cin < 2048 else 6e-5
   xd = x.double()[..., :Cin].clone().requires_grad_(True)
   wd = w.double().clone().requires_grad_(True)
