@@ -445,41 +445,50 @@ __global__ void bn_apply4_kernel(const float* __restrict__ y, int64_t npix, int 
   out.finish(amax);
 }
 
+// One thread = one INPUT pixel x 4 channels -> its 2x2 block of the x2 output (TF1 legacy bilinear: out[2i] = in[i],
+// out[2i+1] = (in[i] + in[i+1]) / 2, last odd sample clamps): the four activated neighbours are computed once and
+// serve four outputs (the per-output version evaluated 16 BN+ReLU and 4 loads per output quad).  Same expressions,
+// same rounding as before.
 template <bool H16>
 __global__ void bn_apply_up2x4_kernel(const float* __restrict__ y, int N, int H, int W, int C, int ycs,
                                       const float* __restrict__ scale, const float* __restrict__ shift,
                                       int relu, Pl<H16> out, int ocs) {
-  const int Ho = 2 * H, Wo = 2 * W, q = C >> 2;
-  int64_t total = (int64_t)N * Ho * Wo * q;
+  const int Wo = 2 * W, q = C >> 2;
+  const int64_t total = (int64_t)N * H * W * q;
   out.init();
   float amax = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % q) * 4;
+    const int c = (int)(i % q) * 4;
     int64_t p = i / q;
-    int wo = (int)(p % Wo);
-    int64_t t = p / Wo;
-    int ho = (int)(t % Ho);
-    int n = (int)(t / Ho);
-    int h0 = ho >> 1, w0 = wo >> 1;
-    int h1 = min(h0 + 1, H - 1), w1 = min(w0 + 1, W - 1);
-    float fh = (ho & 1) ? 0.5f : 0.f, fw = (wo & 1) ? 0.5f : 0.f;
-    float4 sc = ld4(scale + c), sh = ld4(shift + c);
+    const int w0 = (int)(p % W);
+    int64_t t = p / W;
+    const int h0 = (int)(t % H);
+    const int n = (int)(t / H);
+    const int h1 = min(h0 + 1, H - 1), w1 = min(w0 + 1, W - 1);
+    const float4 sc = ld4(scale + c), sh = ld4(shift + c);
     const float* base = y + (int64_t)n * H * W * ycs + c;
-    float4 a00 = bn_act4(ld4(base + ((int64_t)h0 * W + w0) * ycs), sc, sh, relu);
-    float4 a01 = bn_act4(ld4(base + ((int64_t)h0 * W + w1) * ycs), sc, sh, relu);
-    float4 a10 = bn_act4(ld4(base + ((int64_t)h1 * W + w0) * ycs), sc, sh, relu);
-    float4 a11 = bn_act4(ld4(base + ((int64_t)h1 * W + w1) * ycs), sc, sh, relu);
-    float4 v;
+    const float4 a00 = bn_act4(ld4(base + ((int64_t)h0 * W + w0) * ycs), sc, sh, relu);
+    const float4 a01 = bn_act4(ld4(base + ((int64_t)h0 * W + w1) * ycs), sc, sh, relu);
+    const float4 a10 = bn_act4(ld4(base + ((int64_t)h1 * W + w0) * ycs), sc, sh, relu);
+    const float4 a11 = bn_act4(ld4(base + ((int64_t)h1 * W + w1) * ycs), sc, sh, relu);
+    const int64_t orow = ((int64_t)n * 2 * H + 2 * h0) * Wo + 2 * w0;
+#pragma unroll
+    for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+      for (int dw = 0; dw < 2; ++dw) {
+        const float fh = dh ? 0.5f : 0.f, fw = dw ? 0.5f : 0.f;
+        float4 v;
 #define IMMB_LERP(f)                                          \
-    {                                                         \
-      float top = a00.f + (a01.f - a00.f) * fw;               \
-      float bot = a10.f + (a11.f - a10.f) * fw;               \
-      v.f = top + (bot - top) * fh;                           \
-    }
-    IMMB_LERP(x) IMMB_LERP(y) IMMB_LERP(z) IMMB_LERP(w)
+        {                                                     \
+          float top = a00.f + (a01.f - a00.f) * fw;           \
+          float bot = a10.f + (a11.f - a10.f) * fw;           \
+          v.f = top + (bot - top) * fh;                       \
+        }
+        IMMB_LERP(x) IMMB_LERP(y) IMMB_LERP(z) IMMB_LERP(w)
 #undef IMMB_LERP
-    out.store4((size_t)(p * ocs + c), v, amax);
+        out.store4((size_t)((orow + (int64_t)dh * Wo + dw) * ocs + c), v, amax);
+      }
   }
   out.finish(amax);
 }
@@ -1196,6 +1205,100 @@ __global__ void __launch_bounds__(256) vgg_conv1_1_fused_kernel(const float* __r
   out.finish(amax);
 }
 
+// Tiled version (R % 32 == 0): one block = an 8 x 32-pixel tile of one image.  Phase 1 puts the normalised gray values
+// of the 10 x 34 halo into shared memory (the per-thread version recomputed 9 taps x 3 loads for every 16 channels:
+// ncu showed 935 instructions per thread and the L1 pipe at 93 %).  Phase 2: thread = 16 channels x 4 consecutive pixels;
+// the 3 x 6 gray window lives in registers, each filter tap's 16 weights are read once per 4 pixels from a bank-conflict-
+// free layout (channel groups 20 floats apart).  ~300 instructions per 16 outputs.
+template <int COUT, bool H16>
+__global__ void __launch_bounds__(256) vgg_conv1_1_tiled_kernel(const float* __restrict__ gt, const float* __restrict__ pred,
+                                                                int pcs, int B, int R, const float* __restrict__ w,
+                                                                const float* __restrict__ bias, Pl<H16> out, int img_begin) {
+  static_assert(COUT == 64, "4 channel groups of 16");
+  constexpr int TH = 8, TW = 32, GW = TW + 2 + 2;             // gray row pitch 36 floats
+  __shared__ float gs[TH + 2][GW];
+  __shared__ __align__(16) float ws[9][4][20];
+  __shared__ float bs[COUT];
+  out.init();
+  float amax = 0.f;
+  for (int i = threadIdx.x; i < 9 * COUT; i += 256) ws[i / COUT][(i % COUT) >> 4][i & 15] = __ldg(w + i);
+  for (int i = threadIdx.x; i < COUT; i += 256) bs[i] = __ldg(bias + i);
+  const int tiles_w = R / TW, tiles_h = R / TH;
+  const int tw = blockIdx.x % tiles_w, th = (blockIdx.x / tiles_w) % tiles_h;
+  const int64_t n = img_begin + blockIdx.x / (tiles_w * tiles_h);      // image index in [gt ; pred]
+  const float* src = n < B ? gt + (size_t)n * R * R * 3 : pred + (size_t)(n - B) * R * R * pcs;
+  const int sp = n < B ? 3 : pcs;
+  for (int i = threadIdx.x; i < (TH + 2) * (TW + 2); i += 256) {
+    const int gy = i / (TW + 2), gx = i - gy * (TW + 2);
+    const int hh = th * TH + gy - 1, ww = tw * TW + gx - 1;
+    float v = 0.f;
+    if (hh >= 0 && hh < R && ww >= 0 && ww < R) v = gray_norm(src + ((size_t)hh * R + ww) * sp);
+    gs[gy][gx] = v;
+  }
+  __syncthreads();
+  const int cg = threadIdx.x & 3, slot = threadIdx.x >> 2;
+  const int row = slot >> 3, col0 = (slot & 7) * 4;
+  float win[3][6];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 6; ++b) win[a][b] = gs[row + a][col0 + b];
+  float acc[4][16];
+#pragma unroll
+  for (int px = 0; px < 4; ++px)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[px][j] = bs[cg * 16 + j];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    float wv[16];
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 q = *reinterpret_cast<const float4*>(&ws[t][cg][j]);
+      wv[j] = q.x; wv[j + 1] = q.y; wv[j + 2] = q.z; wv[j + 3] = q.w;
+    }
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      const float g = win[t / 3][px + t % 3];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[px][j] = fmaf(g, wv[j], acc[px][j]);
+    }
+  }
+  const size_t pix0 = ((size_t)n * R + (th * TH + row)) * R + tw * TW + col0;
+#pragma unroll
+  for (int px = 0; px < 4; ++px) {
+    const size_t o = (pix0 + px) * COUT + cg * 16;
+    if constexpr (H16) {
+      uint32_t hw[8], lw[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float v0 = fmaxf(acc[px][2 * u], 0.f), v1 = fmaxf(acc[px][2 * u + 1], 0.f);
+        uint16_t h0, l0, h1, l1;
+        amax = fmaxf(amax, fmaxf(v0, v1));
+        split_h16(v0 * out.mul, h0, l0);
+        split_h16(v1 * out.mul, h1, l1);
+        hw[u] = pack2(h0, h1);
+        lw[u] = pack2(l0, l1);
+      }
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out.hi + o), "r"(hw[0]), "r"(hw[1]),
+                   "r"(hw[2]), "r"(hw[3]), "r"(hw[4]), "r"(hw[5]), "r"(hw[6]), "r"(hw[7]) : "memory");
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out.lo + o), "r"(lw[0]), "r"(lw[1]),
+                   "r"(lw[2]), "r"(lw[3]), "r"(lw[4]), "r"(lw[5]), "r"(lw[6]), "r"(lw[7]) : "memory");
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; j += 8) {
+        float h[8], l[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) split_tf32(fmaxf(acc[px][j + u], 0.f), h[u], l[u]);
+        asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out.hi + o + j), "f"(h[0]), "f"(h[1]),
+                     "f"(h[2]), "f"(h[3]), "f"(h[4]), "f"(h[5]), "f"(h[6]), "f"(h[7]) : "memory");
+        asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out.lo + o + j), "f"(l[0]), "f"(l[1]),
+                     "f"(l[2]), "f"(l[3]), "f"(l[4]), "f"(l[5]), "f"(l[6]), "f"(l[7]) : "memory");
+      }
+    }
+  }
+  out.finish(amax);
+}
+
 // first-layer staging: image [N,H,W,3] -> [N,H,W+8,4] (3 zero columns left, 5 right, 4th channel zero)
 __global__ void stage_image_rowwin_kernel(const float* __restrict__ img, int N, int H, int W, float* x_hi,
                                           float* x_lo) {
@@ -1408,34 +1511,55 @@ __global__ void __launch_bounds__(256) vgg_conv1_1_bwd_fused_kernel(
     Pl<HI> dyp, const float* __restrict__ w,
     const float* __restrict__ gt, const float* __restrict__ pred, int pcs, const float* __restrict__ mask,
     const float* __restrict__ coef_in, int R, Pl<HO> gp) {
-  constexpr int COUT = 64, T = 16, HW = T + 2;
+  constexpr int COUT = 64, T = 16, HW = T + 2, NP = HW * HW;
+  // weights: channel groups 20 floats apart (the four 16-channel quarters of a pixel read different banks);
+  // per-tap planes of the contracted halo (phase 2 reads consecutive addresses across a warp)
+  __shared__ __align__(16) float ws[9][4][20];
+  __shared__ float patch[9][NP + 4];
   dyp.init();
   gp.init();
   float amax = 0.f;
-  __shared__ float ws[9][COUT];
-  __shared__ float patch[HW * HW][9];
-  for (int i = threadIdx.x; i < 9 * COUT; i += 256) ws[i / COUT][i % COUT] = __ldg(w + i);
+  for (int i = threadIdx.x; i < 9 * COUT; i += 256) ws[i / COUT][(i % COUT) >> 4][i & 15] = __ldg(w + i);
   const int tiles = R / T;
   const int tw = blockIdx.x % tiles, th = (blockIdx.x / tiles) % tiles;
   const int64_t n = blockIdx.x / (tiles * tiles);
   __syncthreads();
   const int part = threadIdx.x & 3;                       // 16-channel quarter of a pixel
-  for (int it = 0; it < (HW * HW + 63) / 64; ++it) {        // uniform trip count: the shuffles below need whole warps
+  for (int it = 0; it < (NP + 63) / 64; ++it) {            // uniform trip count: the shuffles below need whole warps
     const int q = it * 64 + (threadIdx.x >> 2);
-    const bool valid = q < HW * HW;
+    const bool valid = q < NP;
     const int hh = th * T + q / HW - 1, ww = tw * T + q % HW - 1;
     float acc[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) acc[t] = 0.f;
     if (valid && hh >= 0 && hh < R && ww >= 0 && ww < R) {
       const size_t base = (((size_t)n * R + hh) * R + ww) * COUT + part * 16;
+      float v[16];
+      if constexpr (HI) {
+        // 16 channels = 32 bytes per plane: two 128-bit loads each
+        const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(dyp.hi + base)), h1 = __ldg(reinterpret_cast<const uint4*>(dyp.hi + base + 8));
+        const uint4 l0 = __ldg(reinterpret_cast<const uint4*>(dyp.lo + base)), l1 = __ldg(reinterpret_cast<const uint4*>(dyp.lo + base + 8));
+        const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
 #pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        const float4 v = dyp.load4(base + j);
-        const int c = part * 16 + j;
+        for (int u = 0; u < 8; ++u) {
+          v[2 * u] = join_h16((uint16_t)(hw[u] & 0xFFFFu), (uint16_t)(lw[u] & 0xFFFFu)) * dyp.inv;
+          v[2 * u + 1] = join_h16((uint16_t)(hw[u] >> 16), (uint16_t)(lw[u] >> 16)) * dyp.inv;
+        }
+      } else {
 #pragma unroll
-        for (int t = 0; t < 9; ++t)
-          acc[t] += v.x * ws[t][c] + v.y * ws[t][c + 1] + v.z * ws[t][c + 2] + v.w * ws[t][c + 3];
+        for (int j = 0; j < 16; j += 4) {
+          const float4 t4 = dyp.load4(base + j);
+          v[j] = t4.x; v[j + 1] = t4.y; v[j + 2] = t4.z; v[j + 3] = t4.w;
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 q4 = *reinterpret_cast<const float4*>(&ws[t][part][j]);
+          acc[t] += v[j] * q4.x + v[j + 1] * q4.y + v[j + 2] * q4.z + v[j + 3] * q4.w;
+        }
       }
     }
 #pragma unroll
@@ -1445,7 +1569,7 @@ __global__ void __launch_bounds__(256) vgg_conv1_1_bwd_fused_kernel(
     }
     if (valid && part == 0) {
 #pragma unroll
-      for (int t = 0; t < 9; ++t) patch[q][t] = acc[t];
+      for (int t = 0; t < 9; ++t) patch[t][q] = acc[t];
     }
   }
   __syncthreads();
@@ -1453,7 +1577,7 @@ __global__ void __launch_bounds__(256) vgg_conv1_1_bwd_fused_kernel(
   const int h = th * T + hl, wq = tw * T + wl;
   float gg = 0.f;
 #pragma unroll
-  for (int t = 0; t < 9; ++t) gg += patch[(hl + 1 - (t / 3 - 1)) * HW + (wl + 1 - (t % 3 - 1))][t];
+  for (int t = 0; t < 9; ++t) gg += patch[t][(hl + 1 - (t / 3 - 1)) * HW + (wl + 1 - (t % 3 - 1))];
   gg *= (1.0f / 3.0f) * (1.0f / 255.0f);
   const size_t p = ((size_t)n * R + h) * R + wq;
   const float cm = __ldg(coef_in) * (mask ? __ldg(mask + p) : 1.f);
@@ -1927,7 +2051,7 @@ extern "C" int immb_bn_apply(const float* y, int N, int H, int W, int C, int ycs
     IMMB_REQUIRE(v4 && out_lo, "bn_apply: fp16 planes need the vectorised path (C % 4 == 0, aligned rows)");
     const Pl<true> o = make_pl<true>(out_hi, out_lo, out_scale);
     if (up2x)
-      bn_apply_up2x4_kernel<true><<<ew_grid(npix * C), 256, 0, ST(stream)>>>(y, N, H, W, C, ycs, scale, shift, relu, o, ocs);
+      bn_apply_up2x4_kernel<true><<<ew_grid(npix * C / 4), 256, 0, ST(stream)>>>(y, N, H, W, C, ycs, scale, shift, relu, o, ocs);
     else
       bn_apply4_kernel<true><<<ew_grid(npix * C / 4 / 4), 256, 0, ST(stream)>>>(y, npix, C, ycs, scale, shift, relu, o, ocs, log2_or_neg(C / 4));
     return check_launch("bn_apply");
@@ -1936,7 +2060,7 @@ extern "C" int immb_bn_apply(const float* y, int N, int H, int W, int C, int ycs
   const Pl<false> o = make_pl<false>(out_hi, out_lo, nullptr);
   if (up2x) {
     if (v4)
-      bn_apply_up2x4_kernel<false><<<ew_grid(npix * C), 256, 0, ST(stream)>>>(y, N, H, W, C, ycs, scale, shift, relu, o, ocs);
+      bn_apply_up2x4_kernel<false><<<ew_grid(npix * C / 4), 256, 0, ST(stream)>>>(y, N, H, W, C, ycs, scale, shift, relu, o, ocs);
     else
       bn_apply_up2x_kernel<<<ew_grid(npix * 4 * C), 256, 0, ST(stream)>>>(y, N, H, W, C, ycs, scale, shift,
                                                                            relu, ohi, olo, ocs);
@@ -2096,6 +2220,19 @@ extern "C" int immb_vgg_conv1_1_fused(const float* gt, const float* pred, int pc
   IMMB_REQUIRE(out_lo && aligned32(out_hi) && aligned32(out_lo), "vgg_conv1_1_fused: split output planes must be 32-byte aligned");
   const int64_t per = (int64_t)B * R * R;
   const int64_t p0 = which == 2 ? per : 0, p1 = which == 1 ? per : 2 * per;
+  static int tiled_on = -1;
+  if (tiled_on < 0) { const char* ev = getenv("IMMB_CONV11_TILED"); tiled_on = (ev && atoi(ev) == 0) ? 0 : 1; }
+  if (tiled_on && R % 32 == 0) {
+    const int img0 = which == 2 ? B : 0, n_img = which == 0 ? 2 * B : B;
+    const int grid = n_img * (R / 32) * (R / 8);
+    if (out_scale)
+      vgg_conv1_1_tiled_kernel<64, true><<<grid, 256, 0, ST(stream)>>>(gt, pred, pcs, B, R, w, bias,
+                                                                       make_pl<true>(out_hi, out_lo, out_scale), img0);
+    else
+      vgg_conv1_1_tiled_kernel<64, false><<<grid, 256, 0, ST(stream)>>>(gt, pred, pcs, B, R, w, bias,
+                                                                        make_pl<false>(out_hi, out_lo, nullptr), img0);
+    return check_launch("vgg_conv1_1_fused");
+  }
   int64_t blocks = (p1 - p0 + 63) / 64;
   if (blocks > (int64_t)kNumSMs * 32) blocks = (int64_t)kNumSMs * 32;
   if (out_scale)

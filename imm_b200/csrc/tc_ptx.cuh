@@ -240,9 +240,13 @@ __device__ __forceinline__ void mma_commit_pair(uint64_t* bar, uint16_t cta_mask
       "h"(cta_mask)
       : "memory");
 }
-// arrive on the leader CTA's copy of `bar` (works from either CTA of the pair)
+// arrive on the leader CTA's copy of `bar` (works from either CTA of the pair).  RELAXED: the arrival only hands a
+// drained TMEM accumulator back to the MMA issuer, and the TMEM reads were completed by tcgen05.wait::ld + the
+// before_thread_sync fence.  A .release.cluster arrive compiles to MEMBAR.ALL.GPU + ERRBAR, which also waits for the
+// epilogue's global STORES of the tile to become visible GPU-wide: ncu's source view showed a quarter of all warp samples
+// of the narrow-tile launches on those instructions, i.e. every tile paid a full store-drain latency (~2.5 us).
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask)
                : "memory");
 }
 
