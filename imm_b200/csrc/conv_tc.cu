@@ -154,20 +154,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
         mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t a_hi = smem_u32(smem + s * Cfg::STAGE_BYTES);
-        const uint32_t a_lo = a_hi + Cfg::A_BYTES;
         const uint32_t b_hi = a_hi + Cfg::A_BYTES * Cfg::NPL;
         const int kc_ = kt % p.kchunks;
         const int nk = (F16 && kc_ == p.kchunks - 1) ? p.k_last : 4;
         if (elect_one()) {
+        // one descriptor per operand and stage; k-steps ADD to its start-address field (32 bytes = +2): rebuilding the
+        // fields per MMA cost ~13 instructions per MMA on the single issuing thread (the narrow tiles were bound by it)
+        const uint64_t da0_hi = smem_desc_sw128(a_hi, 16, 1024), db0_hi = smem_desc_sw128(b_hi, 16, 1024);
+        const uint64_t da0_lo = da0_hi + (uint64_t)(Cfg::A_BYTES >> 4);
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {
           if (k4 < nk) {
-          const uint32_t ko = k4 * 32;    // 8 tf32 / 16 fp16 = 32 bytes along K inside the 128-byte swizzle row
-          const uint64_t da_hi = smem_desc_sw128(a_hi + ko, 16, 1024);
-          const uint64_t db_hi = smem_desc_sw128(b_hi + ko, 16, 1024);
+          const uint64_t da_hi = da0_hi + (uint64_t)(2 * k4);     // 8 tf32 / 16 fp16 = 32 bytes along K inside the 128-byte swizzle row
+          const uint64_t db_hi = db0_hi + (uint64_t)(2 * k4);
           mma_kind<F16>(tmem_base, da_hi, db_hi, PASSES == 3 ? idesc2 : idesc, (kt > 0 || k4 > 0) ? 1u : 0u);
           if (PASSES == 3) {
-            const uint64_t da_lo = smem_desc_sw128(a_lo + ko, 16, 1024);
+            const uint64_t da_lo = da0_lo + (uint64_t)(2 * k4);
             // TF32: lo*hi joins the main columns; F16: the lo plane carries 2^11, so it joins hi*lo in the cross columns
             mma_kind<F16>(F16 ? tmem_base + BN : tmem_base, da_lo, db_hi, idesc, 1u);
           }
@@ -200,15 +202,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
       if (PASSES == 3) {
         float v2[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c0), v2);
+        tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c0), v2);
+        tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = F16 ? fmaf(v2[j], s_cross, v[j] * s_main) : v[j] + v2[j];
-      } else if (F16) {
+      } else {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        if (F16) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] *= s_main;
+          for (int j = 0; j < 32; ++j) v[j] *= s_main;
+        }
       }
       if (!row_ok) continue;
       const int col0 = n_off + c0;
@@ -419,21 +425,21 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_c
         mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t a_hi = smem_u32(smem + s * Cfg::STAGE_BYTES);
-        const uint32_t a_lo = a_hi + Cfg::A_BYTES;
         const uint32_t b_hi = a_hi + Cfg::A_BYTES * Cfg::NPL;
-        const uint32_t b_lo = b_hi + Cfg::B_BYTES;
         if (elect_one()) {
+        // MN-major tf32: SWIZZLE_128B_BASE32B; 32-channel groups are LBO = 4096 B apart (one TMA box each),
+        // 4-pixel K atoms are SBO = 512 B apart.  One descriptor per operand and stage; k-steps add to the address field.
+        const uint64_t da0_hi = smem_desc_sw128(a_hi, 4096, 512, 1), db0_hi = smem_desc_sw128(b_hi, 4096, 512, 1);
+        const uint64_t da0_lo = da0_hi + (uint64_t)(Cfg::A_BYTES >> 4), db0_lo = db0_hi + (uint64_t)(Cfg::B_BYTES >> 4);
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {
-          const uint32_t ko = k4 * 1024;     // 8 pixels = 8 rows x 128 B
-          // MN-major tf32: SWIZZLE_128B_BASE32B; 32-channel groups are LBO = 4096 B apart (one TMA box each),
-          // 4-pixel K atoms are SBO = 512 B apart
-          const uint64_t da_hi = smem_desc_sw128(a_hi + ko, 4096, 512, 1);
-          const uint64_t db_hi = smem_desc_sw128(b_hi + ko, 4096, 512, 1);
+          const uint64_t ko = (uint64_t)(k4 * (1024 >> 4));     // 8 pixels = 8 rows x 128 B
+          const uint64_t da_hi = da0_hi + ko;
+          const uint64_t db_hi = db0_hi + ko;
           mma_tf32(tmem_base, da_hi, db_hi, idesc, (kt > 0 || k4 > 0) ? 1u : 0u);
           if (PASSES == 3) {
-            const uint64_t da_lo = smem_desc_sw128(a_lo + ko, 4096, 512, 1);
-            const uint64_t db_lo = smem_desc_sw128(b_lo + ko, 4096, 512, 1);
+            const uint64_t da_lo = da0_lo + ko;
+            const uint64_t db_lo = db0_lo + ko;
             mma_tf32(tmem_base, da_hi, db_lo, idesc, 1u);
             mma_tf32(tmem_base, da_lo, db_hi, idesc, 1u);
           }

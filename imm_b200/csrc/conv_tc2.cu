@@ -12,6 +12,7 @@
 // The CTA is persistent (grid = #SMs, static tile scheduler) with TWO TMEM accumulators, so the epilogue of tile i
 // (tcgen05.ld -> bias/ReLU/split -> stores) overlaps the MMAs of tile i+1, and the TMA producer never drains.
 // Rings: A (2 halo slots), B (per-tap weight slices, 2-4 slots), TMEM (2 accumulators).
+#include <type_traits>
 #include <cudaTypedefs.h>
 #include <cstdlib>
 #include <cstring>
@@ -29,6 +30,8 @@ struct Tc2Tap {
 struct Tc2Params {
   int tiles_w, tiles_h, n_img, n_tiles_n, total_tiles;
   int m_tiles, total_pairs;      // cluster mode: ceil(m_tiles / 2) * n_tiles_n pair iterations
+  int tw_sh, th_sh, nn_sh;       // log2 + 1 of tiles_w / tiles_h / n_tiles_n when a power of two, else 0 (pair kernel: the
+                                 // tile decode is on the epilogue's per-tile critical path; three divisions cost ~100 instructions)
   int kchunks;
   Tc2Tap taps[9];
   float* out_hi;
@@ -345,8 +348,23 @@ struct Tc2PairCfg {
   static constexpr uint32_t B_SLOT = B_PLANE * NPLB;
   // fused BN statistics (3-pass layers only: the frozen 2-pass tower has no BN): per epilogue warp, per N tile (<= 2),
   // sum and sum of squares of BN2 channels in double
-  static constexpr uint32_t STATS_BYTES = PASSES == 3 ? 4 * 2 * 2 * BN2 * 8 + 4 * 256 * 4 : 0;     // + BN constants [4][256]
-  static constexpr uint32_t ROOM = 232448 - 1024 - 512 - A_SLOTS * A_SLOT - STATS_BYTES;
+  // Narrow N tiles are bound by the LATENCY of the epilogue (TMEM read -> bias -> statistics shuffles -> stores: one warp
+  // per 32 accumulator lanes has nothing to overlap them with; ncu: the MMA warp waits on t_empty 57 % of the time at
+  // BN2 = 32), so they run TWO sets of four epilogue warps, set s draining accumulator stage s (tiles alternate).
+#ifndef IMMB_PAIR_EPI_SETS
+#define IMMB_PAIR_EPI_SETS 2
+#endif
+  static constexpr int EPI_SETS = (BN2 <= 64) ? IMMB_PAIR_EPI_SETS : 1;
+  // how the two sets share the work: BN2 = 64 -> both sets drain EVERY tile, set s its 32-column chunk s (halves the
+  // per-tile drain latency; works with two accumulator stages); BN2 = 32 (one chunk) -> tiles alternate between the sets,
+  // and the accumulator ring is 4 deep so that the MMA warp can run ahead of the longer per-tile drain
+  static constexpr bool EPI_SPLIT_COLS = EPI_SETS == 2 && BN2 == 64;
+  static constexpr bool EPI_ALT_TILES = EPI_SETS == 2 && !EPI_SPLIT_COLS;
+  static constexpr int THREADS = 64 + 128 * EPI_SETS;
+  static constexpr uint32_t STATS_ROWS = 4 * EPI_SETS;
+  static constexpr uint32_t STATS_BYTES = PASSES == 3 ? STATS_ROWS * 2 * 2 * BN2 * 8 + 4 * 256 * 4 : 0;     // + BN constants [4][256]
+  static constexpr uint32_t BIAS_BYTES = 2048;            // the layer's bias vector (<= 512 channels), staged once
+  static constexpr uint32_t ROOM = 232448 - 1024 - 512 - A_SLOTS * A_SLOT - STATS_BYTES - BIAS_BYTES;
   static constexpr uint32_t B_FIT = ROOM / B_SLOT;
   // ring depth 6 for streaming; layers whose whole weight operand fits (narrow layers: 9 taps x 1-2 chunks of <= 8 KB)
   // use the region as resident storage (Tc2Params::b_resident), so take what the budget gives up to 18 slots
@@ -355,7 +373,7 @@ struct Tc2PairCfg {
 #endif
   static constexpr uint32_t B_SLOTS = B_FIT > IMMB_PAIR_B_CAP ? IMMB_PAIR_B_CAP : B_FIT;
   static_assert(B_SLOTS >= 2, "weight ring needs two slots");
-  static constexpr uint32_t SMEM_BYTES = A_SLOTS * A_SLOT + B_SLOTS * B_SLOT + STATS_BYTES + 1024 + 512;
+  static constexpr uint32_t SMEM_BYTES = A_SLOTS * A_SLOT + B_SLOTS * B_SLOT + STATS_BYTES + BIAS_BYTES + 1024 + 512;
   // 3-pass: the two cross terms (hi*lo, lo*hi; ~2^-11 of the main term) accumulate in their OWN TMEM columns
   // [BN2, 2*BN2) and are added to the main accumulator once, in the epilogue.  The tensor core truncates the fp32
   // accumulator at every MMA, a biased error that grows linearly with the number of accumulating MMAs; keeping the
@@ -371,14 +389,19 @@ struct Tc2PairCfg {
   static constexpr bool CONCAT = PASSES == 3 && BN2 <= 64;
   static constexpr int ACC_COLS = CONCAT ? 3 * BN2 : (CROSS ? 2 * BN2 : BN2);
   static_assert(2 * ACC_COLS <= 512, "two accumulator sets must fit the 512 TMEM columns (cross accumulator: BN2 <= 128)");
-  static constexpr int TMEM_COLS = 2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512));
+#ifndef IMMB_PAIR_ACC_STAGES
+#define IMMB_PAIR_ACC_STAGES 4
+#endif
+  static constexpr int ACC_STAGES = (BN2 <= 64 && IMMB_PAIR_ACC_STAGES * ACC_COLS <= 512) ? IMMB_PAIR_ACC_STAGES : 2;
+  static constexpr int ACC_TOTAL = ACC_STAGES * ACC_COLS;
+  static constexpr int TMEM_COLS = ACC_TOTAL <= 64 ? 64 : (ACC_TOTAL <= 128 ? 128 : (ACC_TOTAL <= 256 ? 256 : 512));
   static_assert(BN2 % 32 == 0 && BN2 <= 256, "pair N tile: multiple of 32 up to 256");
 };
 
 // BNR: the BN-backward-sums epilogue (stats_mode 2) is a separate instantiation so that its registers do not weigh on
 // the forward / plain-dgrad variants (a high register count squeezes the glue kernels that co-run on the side streams)
 template <int BN2, int PASSES, bool BNR, bool F16>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__((Tc2PairCfg<BN2, PASSES, F16>::THREADS), 1)
 conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
                      const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
                      const __grid_constant__ Tc2Params p) {
@@ -399,16 +422,21 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
   uint64_t* b_full = a_empty + Cfg::A_SLOTS;
   uint64_t* b_empty = b_full + Cfg::B_SLOTS;
   uint64_t* t_full = b_empty + Cfg::B_SLOTS;
-  uint64_t* t_empty = t_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
-  double* stats_sm = reinterpret_cast<double*>(b_base + Cfg::B_SLOTS * Cfg::B_SLOT + 512);     // [4 warps][2 n tiles][2][BN2]
+  uint64_t* t_empty = t_full + Cfg::ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + Cfg::ACC_STAGES);
+  static_assert((2 * Cfg::A_SLOTS + 2 * Cfg::B_SLOTS + 2 * Cfg::ACC_STAGES + 1) * 8 <= 512, "barrier block");
+  double* stats_sm = reinterpret_cast<double*>(b_base + Cfg::B_SLOTS * Cfg::B_SLOT + 512);     // [epilogue warps][2 n tiles][2][BN2]
+  float* bias_sm = reinterpret_cast<float*>(b_base + Cfg::B_SLOTS * Cfg::B_SLOT + 512 + Cfg::STATS_BYTES);
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (uint32_t i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (uint32_t i = 0; i < Cfg::B_SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 8); }
+    for (int i = 0; i < Cfg::ACC_STAGES; ++i) {
+      mbar_init(&t_full[i], 1);
+      mbar_init(&t_empty[i], Cfg::EPI_SPLIT_COLS ? 16 : 8);      // one arrival per draining warp of both CTAs
+    }
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -427,14 +455,17 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
   // pair iteration -> (n tile, the two m tiles); CTA `crank` owns m tile 2*jm + crank (clamped to the last m tile when
   // the count is odd: that CTA recomputes it with stores disabled)
   auto decode = [&](int it, int& img, int& th, int& tw, int& n_off, bool& live) {
-    const int nt = it % p.n_tiles_n;
-    int mt = (it / p.n_tiles_n) * 2 + (int)crank;
+    int nt, jm;
+    if (p.nn_sh) { nt = it & (p.n_tiles_n - 1); jm = it >> (p.nn_sh - 1); }
+    else { nt = it % p.n_tiles_n; jm = it / p.n_tiles_n; }
+    int mt = jm * 2 + (int)crank;
     live = true;
     if (mt >= p.m_tiles) { mt = p.m_tiles - 1; live = false; }
-    tw = mt % p.tiles_w;
-    int r = mt / p.tiles_w;
-    th = r % p.tiles_h;
-    img = r / p.tiles_h;
+    int r;
+    if (p.tw_sh) { tw = mt & (p.tiles_w - 1); r = mt >> (p.tw_sh - 1); }
+    else { tw = mt % p.tiles_w; r = mt / p.tiles_w; }
+    if (p.th_sh) { th = r & (p.tiles_h - 1); img = r >> (p.th_sh - 1); }
+    else { th = r % p.tiles_h; img = r / p.tiles_h; }
     n_off = nt * BN2;
   };
 
@@ -499,7 +530,7 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
         tc_fence_after();
       }
       for (int t = tile0; t < n_iter_total; t += tstep) {
-        const uint32_t acc = ti & 1, tph = (ti >> 1) & 1;
+        const uint32_t acc = ti % Cfg::ACC_STAGES, tph = (ti / Cfg::ACC_STAGES) & 1;
         mbar_wait(&t_empty[acc], tph ^ 1);            // the epilogues of BOTH CTAs have drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * Cfg::ACC_COLS;
@@ -507,56 +538,74 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
           const uint32_t as = ai % Cfg::A_SLOTS, aph = (ai / Cfg::A_SLOTS) & 1;
           mbar_wait(&a_full[as], aph);
           const uint32_t a_hi = smem_u32(a_base + as * Cfg::A_SLOT);
-          const uint32_t a_lo = a_hi + Cfg::A_PLANE;
           const int last_tap = p.n_taps - 1;
           const uint32_t sbo = (uint32_t)p.a_sbo;
           const int nk = (kc == p.kchunks - 1) ? p.k_last : 4;       // 32-byte k-steps holding real channels
-          for (int tap = 0; tap <= last_tap; ++tap) {
-            const uint32_t bs = resident ? (uint32_t)(kc * p.n_taps + tap) : bi % Cfg::B_SLOTS;
-            const uint32_t bph = (bi / Cfg::B_SLOTS) & 1;
-            if (!resident) {
-              mbar_wait(&b_full[bs], bph);
-              tc_fence_after();
-            } else if (tap == 0) {
-              tc_fence_after();                       // (the a_full wait above ordered this chunk's activation box)
-            }
-            const uint32_t b_hi = smem_u32(b_base + bs * Cfg::B_SLOT);
-            const uint32_t b_lo = b_hi + Cfg::B_PLANE;
-            const uint32_t a_off = p.a_off[tap];
-            if (elect_one()) {
+          // Descriptors advance by ADDING to a 64-bit value (start-address field = addr >> 4; the k-step is 32 bytes = +2):
+          // rebuilding them from their fields per MMA cost ~13 SASS instructions per MMA on the single issuing thread, and
+          // the narrow layers (18-36 short MMAs per tile) were bound by exactly that instruction stream (ncu source view).
+          const uint64_t da0_hi = smem_desc_sw128(a_hi, 16, sbo, 2, 0);
+          const uint64_t db0_hi = smem_desc_sw128(smem_u32(b_base), 16, 1024);
+          const uint32_t accf0 = kc > 0 ? 1u : 0u;
+          // nk_c: compile-time count of k-steps (straight-line MMA stream: 4 = full 128-byte rows, 2 = the 32-channel fp16
+          // layers) or 0 = use the runtime value
+          auto issue_tap = [&](int tap, uint32_t bs, auto nk_c) {
+            constexpr int NKC = decltype(nk_c)::value;
+            const uint64_t a_off16 = (uint64_t)(p.a_off[tap] >> 4);
+            const uint64_t da_hi0 = da0_hi + a_off16;
+            const uint64_t db_hi0 = db0_hi + (uint64_t)bs * (uint64_t)(Cfg::B_SLOT >> 4);
+            const uint32_t accf = (accf0 | (tap > 0 ? 1u : 0u));
 #pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4) {
-                if (k4 < nk) {
-                  const uint32_t ko = k4 * 32;
-                  const uint64_t da_hi = smem_desc_sw128(a_hi + a_off + ko, 16, sbo, 2, 0);
-                  const uint64_t db_hi = smem_desc_sw128(b_hi + ko, 16, 1024);
-                  const uint32_t first = (kc > 0 || tap > 0 || k4 > 0) ? 1u : 0u;
-                  if (Cfg::CONCAT) {
-                    const uint64_t da_lo = smem_desc_sw128(a_lo + a_off + ko, 16, sbo, 2, 0);
-                    mma_kind_pair<F16>(tmem_d, da_hi, db_hi, idesc2, first);               // hi*hi and hi*lo in one pass over A_hi
-                    mma_kind_pair<F16>(tmem_d + 2 * BN2, da_lo, db_hi, idesc, first);      // lo*hi: third column block
-                  } else if (PASSES == 3) {
-                    mma_kind_pair<F16>(tmem_d, da_hi, db_hi, idesc, first);
-                    const uint64_t db_lo = smem_desc_sw128(b_lo + ko, 16, 1024);
-                    const uint64_t da_lo = smem_desc_sw128(a_lo + a_off + ko, 16, sbo, 2, 0);
-                    mma_kind_pair<F16>(tmem_d + BN2, da_hi, db_lo, idesc, first);      // cross terms: own accumulator
-                    mma_kind_pair<F16>(tmem_d + BN2, da_lo, db_hi, idesc, 1u);
-                  } else if (PASSES == 2) {
-                    mma_kind_pair<F16>(tmem_d, da_hi, db_hi, idesc, first);
-                    const uint64_t da_lo = smem_desc_sw128(a_lo + a_off + ko, 16, sbo, 2, 0);
-                    if (F16) mma_kind_pair<F16>(tmem_d + BN2, da_lo, db_hi, idesc, first);   // lo carries 2^11: cross accumulator
-                    else mma_kind_pair<F16>(tmem_d, da_lo, db_hi, idesc, 1u);
-                  } else {
-                    mma_kind_pair<F16>(tmem_d, da_hi, db_hi, idesc, first);
-                  }
+            for (int k4 = 0; k4 < (NKC ? NKC : 4); ++k4) {
+              if (NKC || k4 < nk) {
+                const uint64_t da_hi = da_hi0 + (uint64_t)(2 * k4), da_lo = da_hi0 + (uint64_t)((Cfg::A_PLANE >> 4) + 2 * k4);
+                const uint64_t db_hi = db_hi0 + (uint64_t)(2 * k4), db_lo = db_hi0 + (uint64_t)((Cfg::B_PLANE >> 4) + 2 * k4);
+                (void)db_lo;
+                const uint32_t first = k4 > 0 ? 1u : accf;
+                if (Cfg::CONCAT) {
+                  mma_kind_pair<F16>(tmem_d, da_hi, db_hi, idesc2, first);               // hi*hi and hi*lo in one pass over A_hi
+                  mma_kind_pair<F16>(tmem_d + 2 * BN2, da_lo, db_hi, idesc, first);      // lo*hi: third column block
+                } else if (PASSES == 3) {
+                  mma_kind_pair<F16>(tmem_d, da_hi, db_hi, idesc, first);
+                  mma_kind_pair<F16>(tmem_d + BN2, da_hi, db_lo, idesc, first);      // cross terms: own accumulator
+                  mma_kind_pair<F16>(tmem_d + BN2, da_lo, db_hi, idesc, 1u);
+                } else if (PASSES == 2) {
+                  mma_kind_pair<F16>(tmem_d, da_hi, db_hi, idesc, first);
+                  if (F16) mma_kind_pair<F16>(tmem_d + BN2, da_lo, db_hi, idesc, first);   // lo carries 2^11: cross accumulator
+                  else mma_kind_pair<F16>(tmem_d, da_lo, db_hi, idesc, 1u);
+                } else {
+                  mma_kind_pair<F16>(tmem_d, da_hi, db_hi, idesc, first);
                 }
               }
-              if (!resident) mma_commit_pair(&b_empty[bs], (uint16_t)3);
-              if (tap == last_tap) mma_commit_pair(&a_empty[as], (uint16_t)3);
-              if (tap == last_tap && kc == p.kchunks - 1) mma_commit_pair(&t_full[acc], (uint16_t)3);
+            }
+          };
+          if (resident) {
+            // the whole weight operand is in place: one election per chunk, no per-tap barrier traffic
+            tc_fence_after();                         // (the a_full wait above ordered this chunk's activation box)
+            if (elect_one()) {
+              const uint32_t bs0 = (uint32_t)(kc * p.n_taps);
+              if (nk == 4) { for (int tap = 0; tap <= last_tap; ++tap) issue_tap(tap, bs0 + tap, std::integral_constant<int, 4>{}); }
+              else if (nk == 2) { for (int tap = 0; tap <= last_tap; ++tap) issue_tap(tap, bs0 + tap, std::integral_constant<int, 2>{}); }
+              else { for (int tap = 0; tap <= last_tap; ++tap) issue_tap(tap, bs0 + tap, std::integral_constant<int, 0>{}); }
+              mma_commit_pair(&a_empty[as], (uint16_t)3);
+              if (kc == p.kchunks - 1) mma_commit_pair(&t_full[acc], (uint16_t)3);
             }
             __syncwarp();
-            ++bi;
+          } else {
+            for (int tap = 0; tap <= last_tap; ++tap) {
+              const uint32_t bs = bi % Cfg::B_SLOTS, bph = (bi / Cfg::B_SLOTS) & 1;
+              mbar_wait(&b_full[bs], bph);
+              tc_fence_after();
+              if (elect_one()) {
+                if (nk == 4) issue_tap(tap, bs, std::integral_constant<int, 4>{});
+                else issue_tap(tap, bs, std::integral_constant<int, 0>{});
+                mma_commit_pair(&b_empty[bs], (uint16_t)3);
+                if (tap == last_tap) mma_commit_pair(&a_empty[as], (uint16_t)3);
+                if (tap == last_tap && kc == p.kchunks - 1) mma_commit_pair(&t_full[acc], (uint16_t)3);
+              }
+              __syncwarp();
+              ++bi;
+            }
           }
           ++ai;
         }
@@ -564,8 +613,10 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
       }
     }
   } else {
-    // ===== epilogue (warps 2..5 of both CTAs; each CTA drains its own 128 TMEM lanes) =====
+    // ===== epilogue (warps 2.. of both CTAs; each CTA drains its own 128 TMEM lanes; with two sets of four warps, set s
+    // takes the tiles of accumulator stage s) =====
     const int q = warp & 3;
+    const int eset = (warp - 2) >> 2;
     const int m = q * 32 + lane;
     const int hl = m >> 3, wl = m & 7;
     const bool vec8 = (p.ocs % 8 == 0) && (p.n_store % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.out_hi) & 31) == 0) &&
@@ -581,8 +632,14 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
     }
     const bool vec16h = F16 && p.out_lo && (p.ocs % 16 == 0) && (p.n_store % 16 == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.out_hi) & 31) == 0) && ((reinterpret_cast<uintptr_t>(p.out_lo) & 31) == 0);
-    double* my_stats = stats_sm + (size_t)q * (2 * 2 * BN2);      // this warp's private rows: no cross-warp races
-    float* bn_const = reinterpret_cast<float*>(stats_sm + 4 * 2 * 2 * BN2);     // [scale | shift | mean | invstd][256]
+    double* my_stats = stats_sm + (size_t)(eset * 4 + q) * (2 * 2 * BN2);      // this warp's private rows: no cross-warp races
+    float* bn_const = reinterpret_cast<float*>(stats_sm + Cfg::STATS_ROWS * 2 * 2 * BN2);     // [scale | shift | mean | invstd][256]
+    const bool bias_staged = p.bias != nullptr && p.n_cols <= 512;
+    if (bias_staged) {
+      // every epilogue warp writes the same values (benign); it only reads them after its own __syncwarp
+      for (int c = lane; c < p.n_cols; c += 32) bias_sm[c] = __ldg(p.bias + c);
+      __syncwarp();
+    }
     if (do_stats) {
       for (int i = lane; i < 2 * 2 * BN2; i += 32) my_stats[i] = 0.0;
       if (BNR) {
@@ -598,16 +655,17 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
     }
     uint32_t ti = 0;
     for (int t = tile0; t < n_iter_total; t += tstep) {
+      const uint32_t acc = ti % Cfg::ACC_STAGES, tph = (ti / Cfg::ACC_STAGES) & 1;
+      if (Cfg::EPI_ALT_TILES && (int)(ti & 1) != eset) { ++ti; continue; }
       int img, th, tw, n_off;
       bool live;
       decode(t, img, th, tw, n_off, live);
-      const uint32_t acc = ti & 1, tph = (ti >> 1) & 1;
       const int h = th * 16 + hl, w = tw * 8 + wl;
       const size_t pix = ((size_t)img * p.H + h) * p.W + w;
       mbar_wait(&t_full[acc], tph);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN2; c0 += 32) {
+      for (int c0 = Cfg::EPI_SPLIT_COLS ? 32 * eset : 0; c0 < (Cfg::EPI_SPLIT_COLS ? 32 * eset + 32 : BN2); c0 += 32) {
         const int col0 = n_off + c0;
         if (col0 >= p.n_cols) break;             // warp-uniform
         float v[32];
@@ -615,10 +673,11 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
           // columns: CTA-half h of the N tile holds [main | hi*lo] for its BH channels; lo*hi follows at 2*BN2 in channel order
           const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS;
           float va[32], vb[32], vc[32];
-          tmem_ld32(tb + (uint32_t)(2 * BN2 + c0), vc);
+          tmem_ld32_nowait(tb + (uint32_t)(2 * BN2 + c0), vc);
           if (Cfg::BH == 16) {                  // BN2 = 32: 16 main + 16 cross columns per half
-            tmem_ld32(tb, va);
-            tmem_ld32(tb + 32u, vb);
+            tmem_ld32_nowait(tb, va);
+            tmem_ld32_nowait(tb + 32u, vb);
+            tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float c_lo = va[16 + j] + vc[j], c_hi = vb[16 + j] + vc[16 + j];
@@ -626,32 +685,43 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
               v[16 + j] = F16 ? fmaf(c_hi, s_cross, vb[j] * s_main) : vb[j] + c_hi;
             }
           } else {                              // BN2 = 64: a 32-channel chunk is one CTA half
-            tmem_ld32(tb + (uint32_t)(2 * c0), va);
-            tmem_ld32(tb + (uint32_t)(2 * c0 + 32), vb);
+            tmem_ld32_nowait(tb + (uint32_t)(2 * c0), va);
+            tmem_ld32_nowait(tb + (uint32_t)(2 * c0 + 32), vb);
+            tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float c = vb[j] + vc[j];
               v[j] = F16 ? fmaf(c, s_cross, va[j] * s_main) : va[j] + c;
             }
           }
-        } else {
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS + (uint32_t)c0, v);
-        }
-        if (Cfg::CONCAT) {
         } else if (Cfg::CROSS) {
           float v2[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS + (uint32_t)(BN2 + c0), v2);
+          tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS + (uint32_t)c0, v);
+          tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS + (uint32_t)(BN2 + c0), v2);
+          tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = F16 ? fmaf(v2[j], s_cross, v[j] * s_main) : v[j] + v2[j];
+        } else {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS + (uint32_t)c0, v);
+        }
+        if (Cfg::CONCAT || Cfg::CROSS) {
         } else if (F16) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] *= s_main;
         }
         if (!live) continue;
         if (p.bias) {
+          if (bias_staged && col0 + 32 <= p.n_cols) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.n_cols) v[j] += __ldg(p.bias + col0 + j);
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_sm + col0 + j);
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.n_cols) v[j] += __ldg(p.bias + col0 + j);
+          }
         }
         if (do_stats) {
           // per-channel sum / sum of squares of this warp's 32 pixel rows: butterfly transpose-reduce (31 shuffles per
@@ -813,15 +883,24 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
       // one partial row per (CTA, epilogue warp): [sum over n_cols | sum of squares over n_cols]; summed in a fixed
       // order by the second level (immb_bn_stats_from_partials): deterministic, no atomics
       __syncwarp();
-      double* out = p.stats + ((size_t)blockIdx.x * 4 + q) * (size_t)(2 * p.n_cols);
-      for (int nt = 0; nt < p.n_tiles_n && nt < 2; ++nt)
-        for (int c = lane; c < BN2; c += 32) {
-          const int col = nt * BN2 + c;
-          if (col < p.n_cols) {
-            out[col] = my_stats[(size_t)nt * (2 * BN2) + c];
-            out[p.n_cols + col] = my_stats[(size_t)nt * (2 * BN2) + BN2 + c];
+      if (Cfg::EPI_SETS == 2) asm volatile("bar.sync 1, 256;" ::: "memory");      // set 1's rows are final: set 0 folds them in
+      if (eset == 0) {
+        double* out = p.stats + ((size_t)blockIdx.x * 4 + q) * (size_t)(2 * p.n_cols);
+        const double* other = my_stats + (size_t)4 * (2 * 2 * BN2);                // same lane quarter, second set
+        for (int nt = 0; nt < p.n_tiles_n && nt < 2; ++nt)
+          for (int c = lane; c < BN2; c += 32) {
+            const int col = nt * BN2 + c;
+            if (col < p.n_cols) {
+              double a = my_stats[(size_t)nt * (2 * BN2) + c], b = my_stats[(size_t)nt * (2 * BN2) + BN2 + c];
+              if (Cfg::EPI_SETS == 2) {
+                a += other[(size_t)nt * (2 * BN2) + c];
+                b += other[(size_t)nt * (2 * BN2) + BN2 + c];
+              }
+              out[col] = a;
+              out[p.n_cols + col] = b;
+            }
           }
-        }
+      }
     }
   }
   tc_fence_before();
@@ -840,6 +919,13 @@ int tc_make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C
                     int box_w, int box_h, int box_n, int swizzle_mn, int esize = 4);
 int tc_make_w_map(CUtensorMap* m, const void* base, int taps, int Nn, int Kd, int bn, int esize = 4);
 int tc_pick_bn(int ncols);
+
+static inline int pow2_sh(int v) {          // log2(v) + 1 for a power of two, else 0
+  if (v <= 0 || (v & (v - 1))) return 0;
+  int s = 0;
+  while ((1 << s) < v) ++s;
+  return s + 1;
+}
 
 bool conv_tc2_enabled() {
   static int on = -1;
@@ -959,7 +1045,7 @@ static int launch_tc2_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, con
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(192);
+  cfg.blockDim = dim3(Cfg::THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1010,6 +1096,7 @@ int conv_tc2_run(const immb_conv_desc* d, int op, const void* act_hi, const void
   p.total_tiles = p.tiles_w * p.tiles_h * p.n_img * p.n_tiles_n;
   p.m_tiles = p.tiles_w * p.tiles_h * p.n_img;
   p.total_pairs = ceil_div(p.m_tiles, 2) * p.n_tiles_n;
+  p.tw_sh = pow2_sh(p.tiles_w); p.th_sh = pow2_sh(p.tiles_h); p.nn_sh = pow2_sh(p.n_tiles_n);
   // cluster mode pays off when the weight slice dominates the operand traffic (wide N tiles) and there is enough work
   const int cmode = conv_tc2_cluster_mode();
   const bool cluster = !pair && cmode > 0 && bn >= 32 && (bn % 32 == 0 || bn == 96) && (cmode == 2 ? bn >= 32 : bn >= 64) &&
@@ -1157,6 +1244,7 @@ int conv_tc2_rowwin_fwd(const immb_conv_desc* d, const float* x_hi, const float*
   p.m_tiles = p.tiles_w * p.tiles_h * p.n_img;
   p.total_tiles = p.m_tiles * p.n_tiles_n;
   p.total_pairs = ceil_div(p.m_tiles, 2) * p.n_tiles_n;
+  p.tw_sh = pow2_sh(p.tiles_w); p.th_sh = pow2_sh(p.tiles_h); p.nn_sh = pow2_sh(p.n_tiles_n);
   p.kchunks = 1; p.k_last = 4;
   p.n_taps = 7; p.a_sbo = 1024; p.a_plane_bytes = 22 * 8 * 128; p.box_dw = 0; p.box_dh = -3;
   for (int r = 0; r < 7; ++r) { p.taps[r].b_tap = r; p.a_off[r] = (uint32_t)r * 1024u; }
@@ -1289,20 +1377,23 @@ conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_
         const uint32_t b_hi = a_hi + Cfg::A_PLANE * Cfg::NPL;
         const uint32_t b_lo = b_hi + Cfg::B_PLANE;
         if (elect_one()) {
+        // one descriptor per operand and stage; the MMAs add constants to its start-address field
+        const uint64_t da0_hi = smem_desc_sw128(a_hi, 128, 512, 1), db0_hi = smem_desc_sw128(b_hi, 4096, 512, 1);
+        const uint64_t da0_lo = da0_hi + (uint64_t)(Cfg::A_PLANE >> 4), db0_lo = db0_hi + (uint64_t)(Cfg::B_PLANE >> 4);
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
           const uint32_t tmem_d = tmem_base + (uint32_t)(r * Cfg::ACC);
 #pragma unroll
           for (int hl = 0; hl < 4; ++hl) {
-            const uint32_t ao = (uint32_t)((hl + r) * 16) * 128u;        // halo row hl+r, column tap s via LBO
-            const uint32_t bo_ = (uint32_t)hl * 1024u;                    // dY rows hl*8 .. hl*8+7
-            const uint64_t da_hi = smem_desc_sw128(a_hi + ao, 128, 512, 1);
-            const uint64_t db_hi = smem_desc_sw128(b_hi + bo_, 4096, 512, 1);
+            const uint64_t ao = (uint64_t)(((hl + r) * 16 * 128) >> 4);   // halo row hl+r, column tap s via LBO
+            const uint64_t bo_ = (uint64_t)((hl * 1024) >> 4);            // dY rows hl*8 .. hl*8+7
+            const uint64_t da_hi = da0_hi + ao;
+            const uint64_t db_hi = db0_hi + bo_;
             mma_tf32(tmem_d, da_hi, db_hi, Cfg::CONCAT ? idesc2 : idesc, (kt > 0 || hl > 0) ? 1u : 0u);
             if (PASSES == 3) {
-              const uint64_t da_lo = smem_desc_sw128(a_lo + ao, 128, 512, 1);
+              const uint64_t da_lo = da0_lo + ao;
               if (!Cfg::CONCAT) {
-                const uint64_t db_lo = smem_desc_sw128(b_lo + bo_, 4096, 512, 1);
+                const uint64_t db_lo = db0_lo + bo_;
                 mma_tf32(tmem_d, da_hi, db_lo, idesc, 1u);
               }
               mma_tf32(tmem_d, da_lo, db_hi, idesc, 1u);
@@ -1471,19 +1562,25 @@ conv_tc2_wgrad16_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __gri
         const uint32_t b_hi = a_hi + Cfg::A_PLANE * 2;
         const uint32_t b_lo = b_hi + Cfg::B_PLANE;
         if (elect_one()) {
+          // one descriptor per operand and stage, advanced by ADDING to the start-address field (rebuilding the fields
+          // per MMA cost ~13 instructions per MMA on the single issuing thread: more than a 16-cycle N = 32 MMA lasts).
+          // A: LBO = one pixel (the next column tap), SBO = one image row (the next 8 K rows); C32: 64-byte swizzle
+          const uint64_t da0_hi = smem_desc_sw128(a_hi, Cfg::A_ROW_BYTES, Cfg::A_PITCH, C32 ? 4 : 2);
+          const uint64_t da0_lo = da0_hi + (uint64_t)(Cfg::A_PLANE >> 4);
+          const uint64_t db0_hi = smem_desc_sw128(b_hi, 4096, 1024, 2);
+          const uint64_t db0_lo = db0_hi + (uint64_t)(Cfg::B_PLANE >> 4);
 #pragma unroll
           for (int j = 0; j < 2; ++j) {                                   // image rows 2j, 2j+1 of the tile = K 16
             const uint32_t acc = (kt > 0 || j > 0) ? 1u : 0u;
-            const uint64_t db_hi = smem_desc_sw128(b_hi + (uint32_t)j * 2048u, 4096, 1024, 2);
-            const uint64_t db_lo = smem_desc_sw128(b_lo + (uint32_t)j * 2048u, 4096, 1024, 2);
+            const uint64_t db_hi = db0_hi + (uint64_t)(j * (2048 >> 4));
+            const uint64_t db_lo = db0_lo + (uint64_t)(j * (2048 >> 4));
 #pragma unroll
             for (int rr = 0; rr < RPC; ++rr) {
 #pragma unroll
               for (int g = 0; g < Cfg::GROUPS; ++g) {                     // g = 0: taps s = 0,1 (C32: s = 0..3);  g = 1: tap s = 2 (+ ignored)
-                const uint32_t ao = (uint32_t)(2 * j + rr) * Cfg::A_PITCH + (uint32_t)(2 * g) * Cfg::A_ROW_BYTES;
-                // LBO = one pixel (the next column tap), SBO = one image row (the next 8 K rows); C32: 64-byte swizzle
-                const uint64_t da_hi = smem_desc_sw128(a_hi + ao, Cfg::A_ROW_BYTES, Cfg::A_PITCH, C32 ? 4 : 2);
-                const uint64_t da_lo = smem_desc_sw128(a_lo + ao, Cfg::A_ROW_BYTES, Cfg::A_PITCH, C32 ? 4 : 2);
+                const uint64_t ao = (uint64_t)(((uint32_t)(2 * j + rr) * Cfg::A_PITCH + (uint32_t)(2 * g) * Cfg::A_ROW_BYTES) >> 4);
+                const uint64_t da_hi = da0_hi + ao;
+                const uint64_t da_lo = da0_lo + ao;
                 const uint32_t d_main = tmem_base + (uint32_t)((rr * Cfg::GROUPS + g) * 2 * BN);
                 const uint32_t d_cross = d_main + (uint32_t)BN;
                 mma_f16(d_main, da_hi, db_hi, idesc, acc);
@@ -1515,8 +1612,9 @@ conv_tc2_wgrad16_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __gri
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32], v2[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(rg * 2 * BN + c0), v);
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(rg * 2 * BN + BN + c0), v2);
+        tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(rg * 2 * BN + c0), v);
+        tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(rg * 2 * BN + BN + c0), v2);
+        tmem_ld_wait();
         if (!row_ok) continue;
         const int col0 = n_off + c0;
         if (col0 >= p.Cout) continue;
@@ -1702,17 +1800,19 @@ conv_tc2_wgrad16_s2_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __
         const uint32_t b_hi = a_hi + Cfg::A_PLANE * 2;
         const uint32_t b_lo = b_hi + Cfg::B_PLANE;
         if (elect_one()) {
+          const uint64_t da0_hi = smem_desc_sw128(a_hi, 128, 2048, 2), db0_hi = smem_desc_sw128(b_hi, 4096, 1024, 2);
+          const uint64_t da0_lo = da0_hi + (uint64_t)(Cfg::A_PLANE >> 4), db0_lo = db0_hi + (uint64_t)(Cfg::B_PLANE >> 4);
 #pragma unroll
           for (int j = 0; j < 2; ++j) {                                   // dY rows 2j, 2j+1 of the tile = K 16
             const uint32_t acc = (kt > 0 || j > 0) ? 1u : 0u;
-            const uint64_t db_hi = smem_desc_sw128(b_hi + (uint32_t)j * 2048u, 4096, 1024, 2);
-            const uint64_t db_lo = smem_desc_sw128(b_lo + (uint32_t)j * 2048u, 4096, 1024, 2);
+            const uint64_t db_hi = db0_hi + (uint64_t)(j * (2048 >> 4));
+            const uint64_t db_lo = db0_lo + (uint64_t)(j * (2048 >> 4));
 #pragma unroll
             for (int g = 0; g < Cfg::GROUPS; ++g) {
               // window g, view rows 2j / 2j+1; MN atoms = the window at view-pixel shifts 0 and 1 (LBO = 128 B)
-              const uint32_t ao = (uint32_t)g * Cfg::A_WIN + (uint32_t)(2 * j) * 2048u;
-              const uint64_t da_hi = smem_desc_sw128(a_hi + ao, 128, 2048, 2);
-              const uint64_t da_lo = smem_desc_sw128(a_lo + ao, 128, 2048, 2);
+              const uint64_t ao = (uint64_t)(((uint32_t)g * Cfg::A_WIN + (uint32_t)(2 * j) * 2048u) >> 4);
+              const uint64_t da_hi = da0_hi + ao;
+              const uint64_t da_lo = da0_lo + ao;
               const uint32_t d_main = tmem_base + (uint32_t)(g * 2 * BN);
               const uint32_t d_cross = d_main + (uint32_t)BN;
               mma_f16(d_main, da_hi, db_hi, idesc, acc);
@@ -1744,8 +1844,9 @@ conv_tc2_wgrad16_s2_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32], v2[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 2 * BN + c0), v);
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 2 * BN + BN + c0), v2);
+        tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 2 * BN + c0), v);
+        tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 2 * BN + BN + c0), v2);
+        tmem_ld_wait();
         if (!row_ok) continue;
         const int col0 = n_off + c0;
         if (col0 >= p.Cout) continue;

@@ -1929,7 +1929,9 @@ __global__ void __launch_bounds__(256) tps_warp_kernel(const float* __restrict__
 
 static inline int ew_grid(int64_t total, int block = 256) {
   int64_t g = (total + block - 1) / block;
-  int64_t cap = (int64_t)kNumSMs * 16;
+  // 148 * 12 blocks = a whole number of waves at 2, 3, 4 or 6 resident blocks per SM (the grid-stride kernels hold
+  // 45-112 registers; ncu showed 5.33 waves at the old cap of 148 * 16 with 3 blocks per SM: a third-full last wave)
+  int64_t cap = (int64_t)kNumSMs * 12;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return (int)g;
@@ -1957,11 +1959,12 @@ static inline int vred_pix(int64_t npix, int C, bool two_level) {
     if (ppb > 2048) ppb = 2048;
     return (int)ppb;
   }
+  // ONE wave: these kernels hold 76-80 registers (3 blocks of 256 threads per SM), and a grid of 2.3 waves (ncu: 1024
+  // blocks on the 128x128x32 tensors) leaves the last wave a third full -> at most 148 * 3 blocks, equal shares
   const int64_t unit = (int64_t)(1024 / C) * 4;          // pixel rows per block (256 threads / (C/4) quads) x 4 in flight
-  int64_t ppb = npix / ((int64_t)kNumSMs * 6);
-  ppb = ppb / unit * unit;
+  int64_t ppb = (npix + (int64_t)kNumSMs * 3 - 1) / ((int64_t)kNumSMs * 3);
+  ppb = (ppb + unit - 1) / unit * unit;
   if (ppb < unit) ppb = unit;
-  if (ppb > 1024) ppb = 1024 / unit * unit;
   return (int)ppb;
 }
 static inline int vred_grid(int64_t npix, int ppb) { return (int)((npix + ppb - 1) / ppb); }

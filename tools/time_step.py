@@ -16,7 +16,8 @@ for _ in range(3): eng.train_step(inp['image'], inp['future_image'], inp['mask']
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 n0 = _lib.launch_count(); t0 = time.time(); e0.record()
-K = 5
+import os
+K = int(os.environ.get('IMMB_TS_STEPS', '20'))
 for _ in range(K): eng.train_step(inp['image'], inp['future_image'], inp['mask'])
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
