@@ -187,6 +187,10 @@ def selftest_n2():
   dist_step_check.main()
 
 
+def _trace(msg):
+  pass
+
+
 def main_cuda(args):
   import torch
   import torch.distributed as dist
@@ -233,7 +237,9 @@ def main_cuda(args):
                      allreduce=allreduce)
     for i in range(warmup):
       step(i)
+      _trace('warmup step %d enqueued (graphs %s)' % (i, 'on' if eng._graphs is not None else 'off'))
     barrier()
+    _trace('warmup done')
     if sampler is not None:
       sampler.mark_begin()
     n0, r0 = _lib.launch_count(), eng.graph_replays
@@ -260,6 +266,7 @@ def main_cuda(args):
   ms, launches = time_resident(eng, resident, args.steps, args.warmup, sampler)
   clocks = sampler.stop() if rank == 0 else None
   value = B * world / (ms * 1e-3)
+  _trace('resident arm done: %.2f ms/step' % ms)
 
   # ---- end-to-end arm: public API, pinned host inputs, H2D inside the timed region, loss read back -----------
   train_op_inputs = {'i': 0}
@@ -281,6 +288,7 @@ def main_cuda(args):
   e3.record()
   barrier()
   ms_e2e = max_over_ranks(e2.elapsed_time(e3)) / args.steps
+  _trace('e2e arm done: %.2f ms/step' % ms_e2e)
   h2d = sum(v.numel() * v.element_size() for v in host[0].values()) * world
   e2e = {'value': B * world / (ms_e2e * 1e-3), 'unit': 'pairs/s', 'ms_per_step': ms_e2e,
          'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4 * world,
@@ -300,10 +308,12 @@ def main_cuda(args):
   eng.wgrad_stream, eng.pose_stream, eng.gt_stream = saved_streams
   prof, _lib.PROFILE = _lib.PROFILE, None
   roofline = build_roofline(prof, ms, B, cfg, eng)
+  _trace('roofline step done')
 
   # ---- the other BASELINE configs this GPU count is named for (+ the strong-scaling split of config 2) ----------
   other = {}
   if not args.no_other_configs:
+    eng.release_graphs()
     del model, eng, resident, host, train_op
     torch.cuda.empty_cache()
     todo = []
@@ -324,13 +334,34 @@ def main_cuda(args):
                     'ms_per_step': ms2, 'pairs_per_s': per_gpu * world / (ms2 * 1e-3),
                     'tflops_algorithmic': CONFIGS[k2]['gflop'] * per_gpu * world / ms2,
                     'scaling': 'strong' if tag == 'c2_strong' else 'weak', 'inputs': 'resident in HBM'}
+      m2.engine.release_graphs()
       del m2, h2, r2
       torch.cuda.empty_cache()
 
-  if world > 1:
+  def shutdown():
+    """Tear the process group down without ever hanging: CUDA graphs that captured NCCL kernels keep the communicator
+    busy (destroy_process_group() then waits forever), so drop every graph first, and bound the destroy itself."""
+    if world == 1:
+      return
+    import gc
+    try:
+      model.engine.release_graphs()
+    except NameError:
+      pass
+    gc.collect()
+    torch.cuda.synchronize()
     dist.barrier()
-    dist.destroy_process_group()
+    torch.cuda.synchronize()
+    t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    t.start()
+    t.join(timeout=30.0)
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if t.is_alive():
+      os._exit(0)       # the result line is out; do not let communicator teardown hold the box
+
   if rank != 0:
+    shutdown()
     return
   cpu = None
   if world == 1 and not args.no_cpu_baseline:
@@ -347,6 +378,7 @@ def main_cuda(args):
           'streams': roofline.pop('streams')}
   print(json.dumps(line))
   sys.stdout.flush()
+  shutdown()
 
 
 def build_roofline(prof, ms_step, B, cfg, eng):
@@ -428,6 +460,14 @@ if __name__ == '__main__':
   ap.add_argument('--selftest-n2', action='store_true', help='run tests/dist_step_check.py (under torchrun, >= 2 ranks)')
   a = ap.parse_args()
   a.warmup = max(a.warmup, 3) if a.impl == 'cuda' else a.warmup
+  # a stuck collective must end as a traceback of every thread and a non-zero exit, never as a hung GPU box
+  import faulthandler
+  faulthandler.dump_traceback_later(int(os.environ.get('IMMB_BENCH_WATCHDOG', '1500')), exit=True)
+  if os.environ.get('IMMB_BENCH_TRACE'):
+    def _trace(msg, _t0=[time.time()]):
+      sys.stderr.write('[bench rank %s +%.1fs] %s\n' % (os.environ.get('RANK', '0'), time.time() - _t0[0], msg))
+      sys.stderr.flush()
+    globals()['_trace'] = _trace
   if a.selftest_n2:
     selftest_n2()
   elif a.impl == 'reference':

@@ -66,6 +66,15 @@ def renderer_spec(n_filters_render, final_res, n_final_out, start_res=16):
   return spec
 
 
+
+def _dbg(msg):
+  """IMMB_BENCH_TRACE=1: progress lines on stderr (where a multi-rank run stops, if it ever does)."""
+  if os.environ.get('IMMB_BENCH_TRACE'):
+    import sys
+    sys.stderr.write('[engine rank %s] %s\n' % (os.environ.get('RANK', '0'), msg))
+    sys.stderr.flush()
+
+
 class Planes(object):
   """A split tensor: hi (+ optional lo) planes of identical shape [N,H,W,Cs].
   fp32 planes = TF32 pair; fp16 planes ("H16", include/imm_b200.h) carry `scale`, a view of the tensor's scale record
@@ -228,6 +237,11 @@ class IMMEngine(object):
     # and captured into the step graph (IMMB_GRAPH_NCCL=0: eager all-reduce between a fwd+bwd graph and an optimiser graph)
     self.overlap_allreduce = bool(int(os.environ.get('IMMB_AR_OVERLAP', '1')))
     self.graph_nccl = bool(int(os.environ.get('IMMB_GRAPH_NCCL', '1')))
+    # graphs that captured NCCL kernels must be gone before the communicator is torn down (see release_graphs)
+    import atexit
+    import weakref
+    ref = weakref.ref(self)
+    atexit.register(lambda: ref() is not None and ref().release_graphs())
     self.comm_stream, self._allreduce_fn = None, None
     self._pack_table = None
     self.graph_replays, self.graph_launches_per_step = 0, 0
@@ -1251,6 +1265,18 @@ class IMMEngine(object):
     self.optimizer_step(clip_value, lr=lr, beta1=beta1, beta2=beta2, eps=eps)
     return self.total_loss
 
+  def release_graphs(self):
+    """Drop the captured step graphs (the next train_step re-captures).  Required before the NCCL process group is
+    destroyed when the all-reduce was captured into the graph: a live graph holding NCCL kernels keeps the communicator
+    busy and destroy_process_group() never returns."""
+    if getattr(self, '_graphs', None) is not None:
+      torch.cuda.synchronize(self.dev)
+      for g in self._graphs:
+        if g is not None:
+          g.reset()
+      self._graphs = None
+      self._graph_key = None
+
   def _capture_graphs(self, key, image, future_image, mask):
     clip_value, beta1, beta2, eps, has_allreduce, has_mask = key
     dev = self.dev
@@ -1268,6 +1294,7 @@ class IMMEngine(object):
     g_fb, g_opt = torch.cuda.CUDAGraph(), None
     n0 = _lib.launch_count()
     one_graph = has_allreduce and self.graph_nccl
+    _dbg('capture begin (one_graph=%s, overlap=%s)' % (one_graph, self.overlap_allreduce))
     if one_graph:
       # the whole step incl. the two bucketed NCCL all-reduces as ONE graph (NCCL >= 2.9 collectives are capturable)
       try:
@@ -1297,6 +1324,7 @@ class IMMEngine(object):
     for dst, src in zip((self.flat_p, self.flat_m, self.flat_v, self.flat_bn, self.agg), saved):
       dst.copy_(src)
     self._graphs, self._graph_key = (g_fb, g_opt), key
+    _dbg('capture done (%s)' % ('one graph' if g_opt is None else 'two graphs + all-reduce between'))
     self.graph_launches_per_step = _lib.launch_count() - n0     # kernels recorded into the graphs (= launched per replay)
 
   # ------------------------------------------------------------------------------------------------
