@@ -354,15 +354,20 @@ struct Tc2PairCfg {
 #ifndef IMMB_PAIR_EPI_SETS
 #define IMMB_PAIR_EPI_SETS 2
 #endif
-  static constexpr int EPI_SETS = (BN2 <= 64) ? IMMB_PAIR_EPI_SETS : 1;
+#ifndef IMMB_PAIR_WIDE_SETS
+#define IMMB_PAIR_WIDE_SETS 1
+#endif
+  static constexpr int EPI_SETS = (BN2 <= 64 || IMMB_PAIR_WIDE_SETS) ? IMMB_PAIR_EPI_SETS : 1;
   // how the two sets share the work: BN2 = 64 -> both sets drain EVERY tile, set s its 32-column chunk s (halves the
   // per-tile drain latency; works with two accumulator stages); BN2 = 32 (one chunk) -> tiles alternate between the sets,
   // and the accumulator ring is 4 deep so that the MMA warp can run ahead of the longer per-tile drain
-  static constexpr bool EPI_SPLIT_COLS = EPI_SETS == 2 && BN2 == 64;
+  static constexpr bool EPI_SPLIT_COLS = EPI_SETS == 2 && BN2 >= 64;      // set s: 32-column chunks s, s + 2, ...
   static constexpr bool EPI_ALT_TILES = EPI_SETS == 2 && !EPI_SPLIT_COLS;
   static constexpr int THREADS = 64 + 128 * EPI_SETS;
   static constexpr uint32_t STATS_ROWS = 4 * EPI_SETS;
-  static constexpr uint32_t STATS_BYTES = PASSES == 3 ? STATS_ROWS * 2 * 2 * BN2 * 8 + 4 * 256 * 4 : 0;     // + BN constants [4][256]
+  // statistics columns a warp holds per N tile: all BN2 (tiles alternate) or only its own chunks (columns split)
+  static constexpr uint32_t STATS_W = EPI_SPLIT_COLS ? ((BN2 / 32 + 1) / 2) * 32 : BN2;
+  static constexpr uint32_t STATS_BYTES = PASSES == 3 ? STATS_ROWS * 2 * 2 * STATS_W * 8 + 4 * 256 * 4 : 0;     // + BN constants [4][256]
   static constexpr uint32_t BIAS_BYTES = 2048;            // the layer's bias vector (<= 512 channels), staged once
   static constexpr uint32_t ROOM = 232448 - 1024 - 512 - A_SLOTS * A_SLOT - STATS_BYTES - BIAS_BYTES;
   static constexpr uint32_t B_FIT = ROOM / B_SLOT;
@@ -632,8 +637,9 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
     }
     const bool vec16h = F16 && p.out_lo && (p.ocs % 16 == 0) && (p.n_store % 16 == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.out_hi) & 31) == 0) && ((reinterpret_cast<uintptr_t>(p.out_lo) & 31) == 0);
-    double* my_stats = stats_sm + (size_t)(eset * 4 + q) * (2 * 2 * BN2);      // this warp's private rows: no cross-warp races
-    float* bn_const = reinterpret_cast<float*>(stats_sm + Cfg::STATS_ROWS * 2 * 2 * BN2);     // [scale | shift | mean | invstd][256]
+    constexpr int SW = (int)Cfg::STATS_W;
+    double* my_stats = stats_sm + (size_t)(eset * 4 + q) * (2 * 2 * SW);      // this warp's private rows: no cross-warp races
+    float* bn_const = reinterpret_cast<float*>(stats_sm + Cfg::STATS_ROWS * 2 * 2 * SW);     // [scale | shift | mean | invstd][256]
     const bool bias_staged = p.bias != nullptr && p.n_cols <= 512;
     if (bias_staged) {
       // every epilogue warp writes the same values (benign); it only reads them after its own __syncwarp
@@ -641,7 +647,7 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
       __syncwarp();
     }
     if (do_stats) {
-      for (int i = lane; i < 2 * 2 * BN2; i += 32) my_stats[i] = 0.0;
+      for (int i = lane; i < 2 * 2 * SW; i += 32) my_stats[i] = 0.0;
       if (BNR) {
         // every epilogue warp stages the full table itself (identical values: benign), so no cross-warp barrier is needed
         for (int c = lane; c < p.n_cols && c < 256; c += 32) {
@@ -662,10 +668,30 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
       decode(t, img, th, tw, n_off, live);
       const int h = th * 16 + hl, w = tw * 8 + wl;
       const size_t pix = ((size_t)img * p.H + h) * p.W + w;
+#ifndef IMMB_PAIR_NO_PREFETCH
+      if ((BNR && do_stats) || p.relu_src) {
+        // the epilogue's own global reads (the BN layer's y row / the ReLU mask row of this thread's pixel) would otherwise
+        // pay a full DRAM latency per tile with nothing to overlap: pull the NEXT tile's rows into L2 now
+        const int tn = t + tstep * (Cfg::EPI_ALT_TILES ? 2 : 1);
+        if (tn < n_iter_total) {
+          int img2, th2, tw2, n_off2;
+          bool live2;
+          decode(tn, img2, th2, tw2, n_off2, live2);
+          const size_t pix2 = ((size_t)img2 * p.H + th2 * 16 + hl) * p.W + tw2 * 8 + wl;
+          for (int c0 = Cfg::EPI_SPLIT_COLS ? 32 * eset : 0; c0 < BN2; c0 += (Cfg::EPI_SPLIT_COLS ? 64 : 32)) {
+            if (n_off2 + c0 >= p.n_cols) break;
+            const void* ptr = (BNR && do_stats) ? (const void*)(p.bnr_y + pix2 * p.bnr_ycs + n_off2 + c0)
+                            : (F16 ? (const void*)(reinterpret_cast<const uint16_t*>(p.relu_src) + pix2 * p.relu_cs + n_off2 + c0)
+                                   : (const void*)(p.relu_src + pix2 * p.relu_cs + n_off2 + c0));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+          }
+        }
+      }
+#endif
       mbar_wait(&t_full[acc], tph);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = Cfg::EPI_SPLIT_COLS ? 32 * eset : 0; c0 < (Cfg::EPI_SPLIT_COLS ? 32 * eset + 32 : BN2); c0 += 32) {
+      for (int c0 = Cfg::EPI_SPLIT_COLS ? 32 * eset : 0; c0 < BN2; c0 += (Cfg::EPI_SPLIT_COLS ? 64 : 32)) {
         const int col0 = n_off + c0;
         if (col0 >= p.n_cols) break;             // warp-uniform
         float v[32];
@@ -762,9 +788,10 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
             }
           }
           const int nt = (n_off / BN2) & 1;
-          double* row = my_stats + (size_t)nt * (2 * BN2);
-          row[c0 + lane] += (double)s1[0];
-          row[BN2 + c0 + lane] += (double)s2[0];
+          double* row = my_stats + (size_t)nt * (2 * SW);
+          const int sc0 = Cfg::EPI_SPLIT_COLS ? (c0 >> 6) * 32 : c0;       // column split: this warp's chunks are packed
+          row[sc0 + lane] += (double)s1[0];
+          row[SW + sc0 + lane] += (double)s2[0];
         }
         if (p.relu) {
 #pragma unroll
@@ -883,23 +910,35 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
       // one partial row per (CTA, epilogue warp): [sum over n_cols | sum of squares over n_cols]; summed in a fixed
       // order by the second level (immb_bn_stats_from_partials): deterministic, no atomics
       __syncwarp();
-      if (Cfg::EPI_SETS == 2) asm volatile("bar.sync 1, 256;" ::: "memory");      // set 1's rows are final: set 0 folds them in
-      if (eset == 0) {
-        double* out = p.stats + ((size_t)blockIdx.x * 4 + q) * (size_t)(2 * p.n_cols);
-        const double* other = my_stats + (size_t)4 * (2 * 2 * BN2);                // same lane quarter, second set
+      double* out = p.stats + ((size_t)blockIdx.x * 4 + q) * (size_t)(2 * p.n_cols);
+      if (Cfg::EPI_SPLIT_COLS) {
+        // the two sets own disjoint columns of the same row: each warp writes its own chunks, nothing to merge
         for (int nt = 0; nt < p.n_tiles_n && nt < 2; ++nt)
-          for (int c = lane; c < BN2; c += 32) {
-            const int col = nt * BN2 + c;
+          for (int c0 = 32 * eset; c0 < BN2; c0 += 64) {
+            const int col = nt * BN2 + c0 + lane, sc = (c0 >> 6) * 32 + lane;
             if (col < p.n_cols) {
-              double a = my_stats[(size_t)nt * (2 * BN2) + c], b = my_stats[(size_t)nt * (2 * BN2) + BN2 + c];
-              if (Cfg::EPI_SETS == 2) {
-                a += other[(size_t)nt * (2 * BN2) + c];
-                b += other[(size_t)nt * (2 * BN2) + BN2 + c];
-              }
-              out[col] = a;
-              out[p.n_cols + col] = b;
+              out[col] = my_stats[(size_t)nt * (2 * SW) + sc];
+              out[p.n_cols + col] = my_stats[(size_t)nt * (2 * SW) + SW + sc];
             }
           }
+      } else {
+        if (Cfg::EPI_SETS == 2) asm volatile("bar.sync 1, 256;" ::: "memory");      // set 1's rows are final: set 0 folds them in
+        if (eset == 0) {
+          const double* other = my_stats + (size_t)4 * (2 * 2 * SW);                // same lane quarter, second set
+          for (int nt = 0; nt < p.n_tiles_n && nt < 2; ++nt)
+            for (int c = lane; c < BN2; c += 32) {
+              const int col = nt * BN2 + c;
+              if (col < p.n_cols) {
+                double a = my_stats[(size_t)nt * (2 * SW) + c], b = my_stats[(size_t)nt * (2 * SW) + SW + c];
+                if (Cfg::EPI_SETS == 2) {
+                  a += other[(size_t)nt * (2 * SW) + c];
+                  b += other[(size_t)nt * (2 * SW) + SW + c];
+                }
+                out[col] = a;
+                out[p.n_cols + col] = b;
+              }
+            }
+        }
       }
     }
   }
