@@ -331,6 +331,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
 // empty / accumulator-full barriers are per CTA and receive the leader's multicast commits; the accumulator-empty
 // barrier lives in the leader and counts the 4 epilogue warps of BOTH CTAs.
 // =============================================================================================================
+// (value, compensation) fp32 pair accumulation (Knuth TwoSum; -fmad / reassociation cannot touch plain adds and subs)
+__device__ __forceinline__ float2 two_sum_acc(float2 a, float x) {
+  const float t = __fadd_rn(a.x, x);
+  const float bp = __fadd_rn(t, -a.x);
+  const float e = __fadd_rn(__fadd_rn(a.x, -__fadd_rn(t, -bp)), __fadd_rn(x, -bp));
+  return make_float2(t, __fadd_rn(a.y, e));
+}
+__device__ __forceinline__ double pair_value(double slot) {       // the double slot holds a float2 pair
+  const float2 v = *reinterpret_cast<const float2*>(&slot);
+  return (double)v.x + (double)v.y;
+}
+
 template <int BN2, int PASSES, bool F16 = false>
 struct Tc2PairCfg {
   static constexpr uint32_t NPLA = PASSES >= 2 ? 2 : 1;
@@ -788,10 +800,13 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
             }
           }
           const int nt = (n_off / BN2) & 1;
-          double* row = my_stats + (size_t)nt * (2 * SW);
+          // running sums as an unevaluated fp32 pair (value, compensation) in the 8 bytes of the double slot: TwoSum keeps
+          // the rounding error of every add (~2^-46 relative overall), and costs 7 FADDs where the DADD it replaces showed
+          // as 30 % of the epilogue's samples (math-pipe stall; ncu source view of the 128-wide statistics layers)
+          float2* row = reinterpret_cast<float2*>(my_stats + (size_t)nt * (2 * SW));
           const int sc0 = Cfg::EPI_SPLIT_COLS ? (c0 >> 6) * 32 : c0;       // column split: this warp's chunks are packed
-          row[sc0 + lane] += (double)s1[0];
-          row[SW + sc0 + lane] += (double)s2[0];
+          row[sc0 + lane] = two_sum_acc(row[sc0 + lane], s1[0]);
+          row[SW + sc0 + lane] = two_sum_acc(row[SW + sc0 + lane], s2[0]);
         }
         if (p.relu) {
 #pragma unroll
@@ -917,8 +932,8 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
           for (int c0 = 32 * eset; c0 < BN2; c0 += 64) {
             const int col = nt * BN2 + c0 + lane, sc = (c0 >> 6) * 32 + lane;
             if (col < p.n_cols) {
-              out[col] = my_stats[(size_t)nt * (2 * SW) + sc];
-              out[p.n_cols + col] = my_stats[(size_t)nt * (2 * SW) + SW + sc];
+              out[col] = pair_value(my_stats[(size_t)nt * (2 * SW) + sc]);
+              out[p.n_cols + col] = pair_value(my_stats[(size_t)nt * (2 * SW) + SW + sc]);
             }
           }
       } else {
@@ -929,10 +944,10 @@ conv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_c
             for (int c = lane; c < BN2; c += 32) {
               const int col = nt * BN2 + c;
               if (col < p.n_cols) {
-                double a = my_stats[(size_t)nt * (2 * SW) + c], b = my_stats[(size_t)nt * (2 * SW) + SW + c];
+                double a = pair_value(my_stats[(size_t)nt * (2 * SW) + c]), b = pair_value(my_stats[(size_t)nt * (2 * SW) + SW + c]);
                 if (Cfg::EPI_SETS == 2) {
-                  a += other[(size_t)nt * (2 * SW) + c];
-                  b += other[(size_t)nt * (2 * SW) + SW + c];
+                  a += pair_value(other[(size_t)nt * (2 * SW) + c]);
+                  b += pair_value(other[(size_t)nt * (2 * SW) + SW + c]);
                 }
                 out[col] = a;
                 out[p.n_cols + col] = b;

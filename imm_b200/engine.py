@@ -325,8 +325,8 @@ class IMMEngine(object):
 
   def _pick_formats(self):
     """Which layers run on scaled fp16 planes: every conv whose forward, dgrad (if needed) and wgrad (if trainable) all
-    have an fp16-plane tensor-core kernel (the stride-1 3x3 layers and the frozen tower); the 7x7 first layers, the
-    stride-2 layers and the 1x1 heat-map conv stay on 3xTF32.  The planes BETWEEN two layers take the consumer's format."""
+    have an fp16-plane tensor-core kernel (the stride-1 and stride-2 3x3 layers and the frozen tower); the 7x7 first
+    layers and the 1x1 heat-map conv stay on 3xTF32.  The planes BETWEEN two layers take the consumer's format."""
     if not self.h16:
       return
     lib = _lib.lib()
@@ -1336,8 +1336,8 @@ class IMMEngine(object):
       n16 = sum(1 for L in list(self.layers.values()) + self._vgg_convs() if L.h16)
       return ('f16x3 (scaled fp16 split operands hi + lo*2^-11 with one power-of-two scale per tensor; tensor-core products '
               'hi*hi + (hi*lo + lo*hi)*2^-11 at kind::f16, fp32 accumulate: 22 significant bits per operand; %d of %d convs -- '
-              'the stride-1 3x3 layers and the frozen VGG16 tower (2 passes: weights rounded to fp16 planes) -- the 7x7 / '
-              'stride-2 / 1x1 layers run error-compensated 3xTF32)' % (n16, len(self.layers) + len(self._vgg_convs())))
+              'every 3x3 layer (stride 1 and 2) and the frozen VGG16 tower (2 passes: weights rounded to fp16 planes) -- the '
+              '7x7 first layers and the 1x1 heat-map conv run error-compensated 3xTF32)' % (n16, len(self.layers) + len(self._vgg_convs())))
     if self.precision == _lib.PREC_TF32:
       return 'tf32 (single pass; does not meet the parity bar)'
     return ('tf32x3 (fp32 storage; error-compensated TF32 tensor-core products hi*hi+hi*lo+lo*hi, fp32 accumulate; '
