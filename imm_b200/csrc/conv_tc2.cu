@@ -1538,7 +1538,16 @@ struct Wg16Cfg {
   static constexpr uint32_t A_PLANE = (A_ROWS * A_PITCH + 1023) / 1024 * 1024;
   static constexpr int GROUPS = C32 ? 1 : 2;                              // MMA groups per filter row
   static constexpr uint32_t NB = (BN + 63) / 64;                          // dY boxes of 64 channels
-  static constexpr uint32_t B_PLANE = NB * 4096;
+  // N concatenation (IMMB_WG_NCAT): the dY lo plane directly follows the hi plane in the stage, so ONE MMA of N = 2*BN
+  // against the hi descriptor yields [x_hi*dy_hi | x_hi*dy_lo] = the [main | cross] accumulator pair -- x_hi is read
+  // from shared memory once instead of twice (these kernels are bound by exactly those reads at N <= 64).  BN = 32 needs
+  // 32-channel N atoms for that: dY boxes of 32 channels with the 64-byte swizzle (B32), like the C32 x operand.
+#ifndef IMMB_WG_NCAT
+#define IMMB_WG_NCAT 1
+#endif
+  static constexpr bool NCAT = IMMB_WG_NCAT != 0;
+  static constexpr bool B32 = NCAT && BN == 32;
+  static constexpr uint32_t B_PLANE = B32 ? 2048 : NB * 4096;
   static constexpr uint32_t STAGE_BYTES = (A_PLANE + B_PLANE) * 2;        // hi + lo planes of both operands
   static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
   static constexpr int ACC_COLS = RPC * GROUPS * 2 * BN;
@@ -1621,13 +1630,17 @@ conv_tc2_wgrad16_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __gri
           // A: LBO = one pixel (the next column tap), SBO = one image row (the next 8 K rows); C32: 64-byte swizzle
           const uint64_t da0_hi = smem_desc_sw128(a_hi, Cfg::A_ROW_BYTES, Cfg::A_PITCH, C32 ? 4 : 2);
           const uint64_t da0_lo = da0_hi + (uint64_t)(Cfg::A_PLANE >> 4);
-          const uint64_t db0_hi = smem_desc_sw128(b_hi, 4096, 1024, 2);
+          // B: N atoms (64 channels x 8 pixels, or 32 x 8 with the 64-byte swizzle) are LBO apart, 8-pixel K groups SBO apart
+          const uint64_t db0_hi = Cfg::B32 ? smem_desc_sw128(b_hi, Cfg::B_PLANE, 512, 4) : smem_desc_sw128(b_hi, 4096, 1024, 2);
           const uint64_t db0_lo = db0_hi + (uint64_t)(Cfg::B_PLANE >> 4);
+          constexpr uint32_t idesc2 = idesc_f16(128, 2 * BN, 1, 1);
+          constexpr uint32_t kBStep = Cfg::B32 ? 1024 : 2048;              // two image rows of the dY tile
 #pragma unroll
           for (int j = 0; j < 2; ++j) {                                   // image rows 2j, 2j+1 of the tile = K 16
             const uint32_t acc = (kt > 0 || j > 0) ? 1u : 0u;
-            const uint64_t db_hi = db0_hi + (uint64_t)(j * (2048 >> 4));
-            const uint64_t db_lo = db0_lo + (uint64_t)(j * (2048 >> 4));
+            const uint64_t db_hi = db0_hi + (uint64_t)(j * (kBStep >> 4));
+            const uint64_t db_lo = db0_lo + (uint64_t)(j * (kBStep >> 4));
+            (void)db_lo;
 #pragma unroll
             for (int rr = 0; rr < RPC; ++rr) {
 #pragma unroll
@@ -1637,8 +1650,12 @@ conv_tc2_wgrad16_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __gri
                 const uint64_t da_lo = da0_lo + ao;
                 const uint32_t d_main = tmem_base + (uint32_t)((rr * Cfg::GROUPS + g) * 2 * BN);
                 const uint32_t d_cross = d_main + (uint32_t)BN;
-                mma_f16(d_main, da_hi, db_hi, idesc, acc);
-                mma_f16(d_cross, da_hi, db_lo, idesc, acc);
+                if (Cfg::NCAT) {
+                  mma_f16(d_main, da_hi, db_hi, idesc2, acc);              // [main | x_hi*dy_lo]
+                } else {
+                  mma_f16(d_main, da_hi, db_hi, idesc, acc);
+                  mma_f16(d_cross, da_hi, db_lo, idesc, acc);
+                }
                 mma_f16(d_cross, da_lo, db_hi, idesc, 1u);
               }
             }
@@ -1743,8 +1760,9 @@ static int conv_tc2_wgrad16_run(const immb_conv_desc* d, const void* x_hi, const
   const int xsw = c32 ? 2 : 1;        // tc_make_act_map: 2 = 32-channel rows with the 64-byte swizzle
   if ((rc = tc_make_act_map(&mx_hi, x_hi, d->N, d->H, d->W, d->Cin, d->x_cstride, false, 16, box_h, 1, xsw, 2))) return rc;
   if ((rc = tc_make_act_map(&mx_lo, x_lo, d->N, d->H, d->W, d->Cin, d->x_cstride, false, 16, box_h, 1, xsw, 2))) return rc;
-  if ((rc = tc_make_act_map(&my_hi, dy_hi, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, 8, 4, 1, 1, 2))) return rc;
-  if ((rc = tc_make_act_map(&my_lo, dy_lo, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, 8, 4, 1, 1, 2))) return rc;
+  const int ysw = (IMMB_WG_NCAT && bn == 32) ? 2 : 1;       // N concatenation at BN = 32: 32-channel boxes, 64-byte swizzle
+  if ((rc = tc_make_act_map(&my_hi, dy_hi, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, 8, 4, 1, ysw, 2))) return rc;
+  if ((rc = tc_make_act_map(&my_lo, dy_lo, d->N, d->Ho, d->Wo, d->Cout, d->y_cstride, false, 8, 4, 1, ysw, 2))) return rc;
   dim3 grid(c_tiles, n_tiles, (rpc == 3 ? 1 : 3) * splits);
   if (bn == 128) return launch_wg16<128, 1>(mx_hi, mx_lo, my_hi, my_lo, p, grid, st);
   if (bn == 64) return launch_wg16<64, 1>(mx_hi, mx_lo, my_hi, my_lo, p, grid, st);
@@ -1869,8 +1887,12 @@ conv_tc2_wgrad16_s2_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __
               const uint64_t da_lo = da0_lo + ao;
               const uint32_t d_main = tmem_base + (uint32_t)(g * 2 * BN);
               const uint32_t d_cross = d_main + (uint32_t)BN;
-              mma_f16(d_main, da_hi, db_hi, idesc, acc);
-              mma_f16(d_cross, da_hi, db_lo, idesc, acc);
+              if (IMMB_WG_NCAT && BN >= 64) {                               // the lo plane follows the hi plane: N = 2*BN
+                mma_f16(d_main, da_hi, db_hi, idesc_f16(128, 2 * BN, 1, 1), acc);
+              } else {
+                mma_f16(d_main, da_hi, db_hi, idesc, acc);
+                mma_f16(d_cross, da_hi, db_lo, idesc, acc);
+              }
               mma_f16(d_cross, da_lo, db_hi, idesc, 1u);
             }
           }
