@@ -63,6 +63,11 @@ __device__ __forceinline__ float load_split(const float* hi_p, const float* lo_p
 // (16x headroom above, 26 binades below).  Scale record in device memory: int32 {e, amax_bits}: producers read e and
 // atomicMax the bit pattern of the largest |v| they wrote; immb_scale_update turns amax into the next step's e.
 constexpr int kH16TargetExp = 12;
+// Tensors under DELAYED scaling (activations, gradients: this step's exponent comes from the previous step's maximum)
+// aim lower: 2^8, i.e. 256x headroom.  Early in training the gradient planes were observed to grow 20-40x from one
+// step to the next (tools/soak_step.py: dy maxima at step 31 of config 2), which saturated fp16 under the 16x headroom
+// of 2^12.  Weights are rescaled exactly from their current maximum every step and keep 2^12.
+constexpr int kH16DelayedTargetExp = 8;
 constexpr float kH16LoScale = 2048.f;               // 2^11
 constexpr float kH16LoInv = 1.f / 2048.f;
 

@@ -333,7 +333,15 @@ struct WgCfg {
   static constexpr uint32_t NPL = PASSES == 3 ? 2 : 1;
   static constexpr uint32_t STAGE_BYTES = (A_BYTES + B_BYTES) * NPL;
   static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
-  static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  // N concatenation (3-pass): the dY lo plane follows the hi plane in the stage, so ONE MMA of N = 2*BN against the hi
+  // descriptor gives [x_hi*dy_hi | x_hi*dy_lo] in 2*BN columns (the epilogue adds the halves): x_hi is read from shared
+  // memory once per k-step instead of twice -- these launches are bound by those reads, not by the tensor pipe.
+#ifndef IMMB_WGT_NCAT
+#define IMMB_WGT_NCAT 1
+#endif
+  static constexpr bool NCAT = IMMB_WGT_NCAT && PASSES == 3 && BN <= 128;
+  static constexpr int ACC = NCAT ? 2 * BN : BN;
+  static constexpr int TMEM_COLS = ACC <= 32 ? 32 : (ACC <= 64 ? 64 : (ACC <= 128 ? 128 : 256));
 };
 
 template <int BN, int PASSES, int STAGES>
@@ -436,12 +444,18 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_c
           const uint64_t ko = (uint64_t)(k4 * (1024 >> 4));     // 8 pixels = 8 rows x 128 B
           const uint64_t da_hi = da0_hi + ko;
           const uint64_t db_hi = db0_hi + ko;
+          if (Cfg::NCAT) {
+            const uint64_t da_lo = da0_lo + ko;
+            mma_tf32(tmem_base, da_hi, db_hi, idesc_tf32(kTileM, 2 * BN, 1, 1), (kt > 0 || k4 > 0) ? 1u : 0u);
+            mma_tf32(tmem_base, da_lo, db_hi, idesc, 1u);
+          } else {
           mma_tf32(tmem_base, da_hi, db_hi, idesc, (kt > 0 || k4 > 0) ? 1u : 0u);
           if (PASSES == 3) {
             const uint64_t da_lo = da0_lo + ko;
             const uint64_t db_lo = db0_lo + ko;
             mma_tf32(tmem_base, da_hi, db_lo, idesc, 1u);
             mma_tf32(tmem_base, da_lo, db_hi, idesc, 1u);
+          }
           }
         }
         mma_commit(&empty[s]);
@@ -467,7 +481,16 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapX_hi, const __grid_c
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (Cfg::NCAT) {
+        float v2[32];
+        tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c0), v2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += v2[j];
+      } else {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      }
       if (!row_ok) continue;
       const int col0 = n_off + c0;
       if (col0 >= p.Cout) continue;

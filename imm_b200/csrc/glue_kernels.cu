@@ -1766,11 +1766,11 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int taps, int C
 // H16 variant: the same two layouts as scaled fp16 pairs.  The tensor's scale exponent is derived here from its largest
 // magnitude (amax[0], produced by the optimiser / immb_multi_amax in the same step: weights need no delayed scaling)
 // and published in rec[0] for the convolutions that consume the planes.
-__device__ __forceinline__ int h16_exp_for(float amax) {
+__device__ __forceinline__ int h16_exp_for(float amax, int target = kH16TargetExp) {
   if (!(amax > 0.f) || !isfinite(amax)) return 0;
   int ex;
   frexpf(amax, &ex);                    // amax = m * 2^ex, m in [0.5, 1)  ->  amax * 2^(target - ex) < 2^target
-  int e = kH16TargetExp - ex;
+  int e = target - ex;
   return e > 100 ? 100 : (e < -100 ? -100 : e);
 }
 __global__ void pack_weights_h16_kernel(const float* __restrict__ w, int taps, int Cin, int Cout, int cin_pad,
@@ -1879,7 +1879,7 @@ __global__ void scale_update_kernel(int32_t* recs, int n, int32_t* overflow) {
   const float a = __uint_as_float(bits);
   const int e_old = recs[2 * i];
   if (!isfinite(a) || a * exp2i(e_old) > 65504.f) atomicAdd(overflow, 1);
-  if (isfinite(a)) recs[2 * i] = h16_exp_for(a);
+  if (isfinite(a)) recs[2 * i] = h16_exp_for(a, kH16DelayedTargetExp);
   recs[2 * i + 1] = 0;
 }
 

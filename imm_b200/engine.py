@@ -318,6 +318,11 @@ class IMMEngine(object):
     i = self.n_scale_recs
     self.n_scale_recs += 1
     assert i < self.scale_recs.shape[0]
+    if not hasattr(self, 'scale_tags'):
+      self.scale_tags = []
+    import sys
+    fr = sys._getframe(1)
+    self.scale_tags.append('%s:%d' % (fr.f_code.co_name, fr.f_lineno))      # who owns record i (diagnostics: tools/soak_step.py)
     return self.scale_recs[i]
 
   def _vgg_convs(self):

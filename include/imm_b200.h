@@ -189,8 +189,8 @@ int immb_split_planes(const float* v, void* hi, void* lo, int64_t n, int32_t* sc
  * fp16's normal range).  Every H16 tensor has a SCALE RECORD in device memory, int32 {e, amax_bits}: a kernel that
  * writes the planes reads e and atomically maxes the bit pattern of the largest |v| it wrote into amax_bits; a kernel
  * that reads the planes reads e.  immb_scale_update turns the observed maxima into the exponents of the NEXT step
- * (delayed scaling: largest magnitude near 2^12, i.e. 16x headroom before fp16 saturates and 26 binades of full
- * precision below), counts tensors whose maximum did not fit (overflow[0] += 1; immb_total_loss then poisons the loss
+ * (delayed scaling: largest magnitude near 2^8, i.e. 256x headroom before fp16 saturates -- gradient planes were seen to
+ * grow 20-40x between consecutive steps early in training -- and 22 binades of full hi precision below), counts tensors whose maximum did not fit (overflow[0] += 1; immb_total_loss then poisons the loss
  * with NaN so that the caller's NaN guard fires) and clears the maxima.  It must run while no H16 activation / gradient
  * tensor is live, i.e. between training steps.  Weight planes are rescaled by immb_pack_weights from the exact maximum
  * of the updated weights instead.

@@ -62,7 +62,8 @@ def test_h16_format_round_trip_and_split_kernel():
   call('immb_scale_update', recs, 3, ovf, ST())
   torch.cuda.synchronize()
   assert recs[:, 1].tolist() == [0, 0, 0]
-  assert recs[0, 0].item() == h16_exp(float(v.abs().max())) and recs[1, 0].item() == 5 and recs[2, 0].item() == 11
+  # delayed-scaling tensors aim at 2^8 (256x headroom); weights (exact, same-step scaling) at 2^12
+  assert recs[0, 0].item() == h16_exp(float(v.abs().max()), target=8) and recs[1, 0].item() == 5 and recs[2, 0].item() == 7
   assert ovf.item() == 1
 
 
