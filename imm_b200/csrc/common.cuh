@@ -62,6 +62,14 @@ __device__ __forceinline__ float load_split(const float* hi_p, const float* lo_p
 // (|t| >= 2^-14) for the elements that matter: e is chosen so that the tensor's largest magnitude sits near 2^12
 // (16x headroom above, 26 binades below).  Scale record in device memory: int32 {e, amax_bits}: producers read e and
 // atomicMax the bit pattern of the largest |v| they wrote; immb_scale_update turns amax into the next step's e.
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: launchers cache "already configured" per device slot
+constexpr int kMaxDevices = 64;
+inline int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  return dev & (kMaxDevices - 1);
+}
+
 constexpr int kH16TargetExp = 12;
 // Tensors under DELAYED scaling (activations, gradients: this step's exponent comes from the previous step's maximum)
 // aim lower: 2^8, i.e. 256x headroom.  Early in training the gradient planes were observed to grow 20-40x from one

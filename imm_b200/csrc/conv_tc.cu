@@ -675,7 +675,8 @@ static int launch_fwd(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CU
   constexpr int STAGES = SHORT ? 2 : (PASSES == 3 ? (BN <= 64 ? 4 : 3) : (BN <= 64 ? 6 : 4));
   using Cfg = FwdCfg<BN, PASSES, STAGES>;
   auto kern = conv_tc_kernel<BN, PASSES, STAGES, F16>;
-  static bool configured = false;
+  static bool configured_dev[kMaxDevices] = {};
+  bool& configured = configured_dev[current_device_slot()];      // the shared-memory opt-in is a per-device attribute
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "conv_tc smem attr: %s", cudaGetErrorString(e));
@@ -907,7 +908,8 @@ static int launch_wg(const CUtensorMap& x_hi, const CUtensorMap& x_lo, const CUt
   constexpr int STAGES = PASSES == 3 ? (BN <= 64 ? 4 : 3) : (BN <= 64 ? 6 : 4);
   using Cfg = WgCfg<BN, PASSES, STAGES>;
   auto kern = conv_tc_wgrad_kernel<BN, PASSES, STAGES>;
-  static bool configured = false;
+  static bool configured_dev[kMaxDevices] = {};
+  bool& configured = configured_dev[current_device_slot()];      // the shared-memory opt-in is a per-device attribute
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "conv_tc_wgrad smem attr: %s", cudaGetErrorString(e));

@@ -1016,7 +1016,8 @@ static int launch_tc2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CU
   using Cfg = Tc2Cfg<BN, PASSES>;
   if (!cluster) {
     auto kern = conv_tc2_kernel<BN, PASSES, 1>;
-    static bool configured = false;
+    static bool configured_dev[kMaxDevices] = {};
+  bool& configured = configured_dev[current_device_slot()];      // the shared-memory opt-in is a per-device attribute
     if (!configured) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
       if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "conv_tc2 smem attr: %s", cudaGetErrorString(e));
@@ -1027,7 +1028,8 @@ static int launch_tc2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CU
     return check_launch("conv_tc2_kernel");
   }
   auto kern = conv_tc2_kernel<BN, PASSES, 2>;
-  static bool configured2 = false;
+  static bool configured2_dev[kMaxDevices] = {};
+  bool& configured2 = configured2_dev[current_device_slot()];
   if (!configured2) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "conv_tc2 smem attr: %s", cudaGetErrorString(e));
@@ -1089,7 +1091,8 @@ static int launch_tc2_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, con
   if (!BNR && p.stats_mode == 2) return launch_tc2_pair<BN2, PASSES, true, F16>(a_hi, a_lo, b_hi, b_lo, p, st);
   using Cfg = Tc2PairCfg<BN2, PASSES, F16>;
   auto kern = conv_tc2_pair_kernel<BN2, PASSES, BNR, F16>;
-  static bool configured = false;
+  static bool configured_dev[kMaxDevices] = {};
+  bool& configured = configured_dev[current_device_slot()];      // the shared-memory opt-in is a per-device attribute
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "conv_tc2_pair smem attr: %s", cudaGetErrorString(e));
@@ -1718,7 +1721,8 @@ static int launch_wg16(const CUtensorMap& x_hi, const CUtensorMap& x_lo, const C
   constexpr int STAGES = BN <= 64 ? 6 : 5;
   using Cfg = Wg16Cfg<BN, STAGES, RPC, C32>;
   auto kern = conv_tc2_wgrad16_kernel<BN, STAGES, RPC, C32>;
-  static bool configured = false;
+  static bool configured_dev[kMaxDevices] = {};
+  bool& configured = configured_dev[current_device_slot()];      // the shared-memory opt-in is a per-device attribute
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "conv_tc2_wgrad16 smem attr: %s", cudaGetErrorString(e));
@@ -1955,7 +1959,8 @@ static int launch_wg16_s2(const CUtensorMap& x_hi, const CUtensorMap& x_lo, cons
   constexpr int STAGES = BN <= 64 ? 6 : 4;
   using Cfg = Wg16S2Cfg<BN, STAGES, C32>;
   auto kern = conv_tc2_wgrad16_s2_kernel<BN, STAGES, C32>;
-  static bool configured = false;
+  static bool configured_dev[kMaxDevices] = {};
+  bool& configured = configured_dev[current_device_slot()];      // the shared-memory opt-in is a per-device attribute
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "conv_tc2_wgrad16_s2 smem attr: %s", cudaGetErrorString(e));
@@ -2028,7 +2033,8 @@ static int launch_wg2(const CUtensorMap& x_hi, const CUtensorMap& x_lo, const CU
   constexpr int STAGES = PASSES == 3 ? (BN <= 64 ? 4 : 3) : 4;
   using Cfg = Wg2Cfg<BN, PASSES, STAGES>;
   auto kern = conv_tc2_wgrad_kernel<BN, PASSES, STAGES>;
-  static bool configured = false;
+  static bool configured_dev[kMaxDevices] = {};
+  bool& configured = configured_dev[current_device_slot()];      // the shared-memory opt-in is a per-device attribute
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(IMMB_ERR_CUDA, "conv_tc2_wgrad smem attr: %s", cudaGetErrorString(e));

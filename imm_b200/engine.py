@@ -206,6 +206,7 @@ class IMMEngine(object):
     self.inv_std = 1.0 / float(config.gauss_std)
     self.global_step = -1.0           # scripts/train.py:87-89,192: initialised to --reset-global-step (default -1)
     self.adam_t = 0
+    self.adam_betas = (0.9, 0.999)
     # H16 scale records (include/imm_b200.h "H16 planes"): one int32 {e, amax bits} per fp16 tensor
     self.scale_recs = torch.zeros((768, 2), dtype=torch.int32, device=self.dev)
     self.n_scale_recs = 0
@@ -586,6 +587,7 @@ class IMMEngine(object):
     self.flat_m.zero_()
     self.flat_v.zero_()
     self.adam_t = 0
+    self.adam_betas = (0.9, 0.999)
     self.global_step = -1.0
     self._invalidate_scales()
     self.repack_weights()
@@ -1213,6 +1215,7 @@ class IMMEngine(object):
       lr = self.learning_rate()
     self.adam_t += 1
     self.last_lr = lr
+    self.adam_betas = (float(beta1), float(beta2))      # checkpointed as beta1_power / beta2_power (TF AdamOptimizer)
     return lr * math.sqrt(1.0 - beta2 ** self.adam_t) / (1.0 - beta1 ** self.adam_t)
 
   def optimizer_step(self, clip_value=1.0, lr=None, beta1=0.9, beta2=0.999, eps=1e-8, allreduce=None):
@@ -1363,3 +1366,36 @@ class IMMEngine(object):
     out = torch.empty((B, size, size, K), dtype=torch.float32, device=self.dev)
     call('immb_gaussian_maps', mu.contiguous(), B, K, size, self.inv_std, out, _lib.stream_ptr())
     return out
+
+
+# ---- device scoping ---------------------------------------------------------------------------------------
+# Every public entry point runs with the engine's device current, so an engine on 'cuda:1' enqueues on cuda:1's streams
+# even when the caller never called torch.cuda.set_device (the C ABI launches on the CURRENT device's stream).
+def _on_engine_device(fn):
+  import functools
+
+  @functools.wraps(fn)
+  def wrapped(self, *args, **kwargs):
+    with torch.cuda.device(self.dev):
+      return fn(self, *args, **kwargs)
+  return wrapped
+
+
+def _init_on_device(fn):
+  import functools
+
+  @functools.wraps(fn)
+  def wrapped(self, config, batch, image_size=128, device='cuda:0', *args, **kwargs):
+    if not torch.cuda.is_available():
+      return fn(self, config, batch, image_size, device, *args, **kwargs)       # raises: there is no CPU fallback
+    with torch.cuda.device(torch.device(device)):
+      return fn(self, config, batch, image_size, device, *args, **kwargs)
+  return wrapped
+
+
+IMMEngine.__init__ = _init_on_device(IMMEngine.__init__)
+for _name in ('init_parameters', 'load_state', 'load_vgg_caffe_dict', 'load_vgg_hwio', 'repack_weights', 'forward', 'backward',
+              'optimizer_step', 'train_step', 'release_graphs', 'run_image_encoder', 'run_pose_branch', 'run_renderer',
+              'load_joint', 'loss_value', 'gaussian_maps'):
+  setattr(IMMEngine, _name, _on_engine_device(getattr(IMMEngine, _name)))
+del _name

@@ -240,8 +240,9 @@ class IMMModel(BaseModel):
         sd[k] = v.detach().cpu().clone()
     sd['global_step'] = torch.tensor(eng.global_step)
     if include_optimizer:
-      sd['beta1_power'] = torch.tensor(0.9 ** (eng.adam_t + 1))       # TF keeps beta^t for the NEXT step
-      sd['beta2_power'] = torch.tensor(0.999 ** (eng.adam_t + 1))
+      b1, b2 = eng.adam_betas                                          # the betas of the optimiser that ran the steps
+      sd['beta1_power'] = torch.tensor(b1 ** (eng.adam_t + 1))        # TF keeps beta^t for the NEXT step
+      sd['beta2_power'] = torch.tensor(b2 ** (eng.adam_t + 1))
       sd['__adam_t'] = torch.tensor(eng.adam_t)
       for k in eng.params:
         sd[k + '/Adam'] = eng.adam_m[k].detach().cpu().clone()
@@ -264,7 +265,14 @@ class IMMModel(BaseModel):
     import os
     from ..utils import tf_checkpoint
     if os.path.exists(fname + '.index'):
-      sd = {k: torch.from_numpy(v) for k, v in tf_checkpoint.CheckpointReader(fname).read_all().items()}
+      # only what this model can use is decoded: a checkpoint may carry entries without a numeric encoding here
+      # (DT_STRING object graphs of later TF1 savers, partitioned variables) that are none of this model's business
+      eng = self.engine
+      wanted = set(eng.params) | set(eng.buffers) | {'global_step', 'beta1_power', 'beta2_power'}
+      wanted |= {k + s_ for k in eng.params for s_ in ('/Adam', '/Adam_1')}
+      reader = tf_checkpoint.CheckpointReader(fname)
+      sd = {k: torch.from_numpy(reader.get_tensor(k)) for k in reader.entries
+            if k in wanted or k.startswith('SelfSupReconstructionLoss/vgg16/')}
     elif os.path.exists(fname):
       sd = torch.load(fname, map_location='cpu')
     else:
@@ -273,7 +281,7 @@ class IMMModel(BaseModel):
     return sd
 
   def load_state_dict(self, sd, vars_to_restore='model', ignore_missing_vars=False, reset_global_step=-1,
-                      exclude_vars=None):
+                      exclude_vars=None, adam_betas=None):
     """cnn_train_multi.py:404-433 semantics: 'model' = MODEL_VARIABLES (w, b, *_agg, global_step -- NOT the
     tf.layers BN variables), 'all' = every global variable incl. BN and Adam slots (--restore-optim)."""
     eng = self.engine
@@ -286,6 +294,9 @@ class IMMModel(BaseModel):
       if hit:
         names.pop(hit[0])
     missing = [k for k in names if k not in sd]
+    if vars_to_restore == 'all':     # tf.global_variables() includes the optimiser slots: the reference's Saver fails without them
+      missing += [k + s_ for k in eng.params for s_ in ('/Adam', '/Adam_1') if k + s_ not in sd]
+      missing += [k for k in ('beta1_power', 'beta2_power') if k not in sd and '__adam_t' not in sd]
     if missing and not ignore_missing_vars:
       raise KeyError('variables missing from the checkpoint: %s' % missing[:5])
     params = {k: sd[k] for k in names if k in sd and k in eng.params}
@@ -298,11 +309,12 @@ class IMMModel(BaseModel):
         eng.adam_t = int(sd['__adam_t'])
       elif 'beta1_power' in sd:       # TF keeps beta1^(t+1) (AdamOptimizer._finish); t = steps applied so far
         import math
+        b1, b2 = adam_betas if adam_betas is not None else eng.adam_betas      # betas of the run that wrote the file
         b1p, b2p = float(sd['beta1_power']), float(sd.get('beta2_power', 0.0))
-        if b1p > 1e-30:
-          eng.adam_t = max(int(round(math.log(b1p) / math.log(0.9))) - 1, 0)
-        elif b2p > 1e-30:
-          eng.adam_t = max(int(round(math.log(b2p) / math.log(0.999))) - 1, 0)
+        if b1p > 1e-30 and 0.0 < b1 < 1.0:
+          eng.adam_t = max(int(round(math.log(b1p) / math.log(b1))) - 1, 0)
+        elif b2p > 1e-30 and 0.0 < b2 < 1.0:
+          eng.adam_t = max(int(round(math.log(b2p) / math.log(b2))) - 1, 0)
         else:                         # both powers underflowed in fp32 (> ~87k steps): the bias correction is 1 anyway
           eng.adam_t = max(int(float(sd.get('global_step', 0))) + 1, 100000)
     eng.load_state(params, buffers, adam_m, adam_v)

@@ -367,8 +367,20 @@ class CheckpointReader(object):
       raise IOError('variable %r: data checksum mismatch' % name)
     return raw.view(dt).reshape(e['shape']).copy()
 
-  def read_all(self):
-    return OrderedDict((k, self.get_tensor(k)) for k in self.entries)
+  def read_all(self, skip_unsupported=True):
+    """Every variable of the bundle.  Entries this reader has no decoding for (non-numeric dtypes such as the DT_STRING
+    `_CHECKPOINTABLE_OBJECT_GRAPH` of later TF1 savers, partitioned variables) are skipped with a warning, or raise
+    NotImplementedError with skip_unsupported=False."""
+    out = OrderedDict()
+    for k in self.entries:
+      try:
+        out[k] = self.get_tensor(k)
+      except NotImplementedError as e:
+        if not skip_unsupported:
+          raise
+        import warnings
+        warnings.warn('checkpoint entry skipped: %s' % (e,))
+    return out
 
 
 def checkpoint_exists(fname):

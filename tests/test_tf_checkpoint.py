@@ -170,3 +170,22 @@ def test_round_trip_property_random_variable_sets(tmp_path):
       got = r.get_tensor(k)
       assert got.dtype == v.dtype and got.shape == v.shape and np.array_equal(got, v)
   run()
+
+
+def test_read_all_skips_entries_without_a_numeric_decoding(tmp_path):
+  """A bundle may carry entries this reader cannot decode (DT_STRING object graphs of later TF1 savers, partitioned
+  variables): read_all() skips them with a warning instead of making the whole checkpoint unreadable, get_tensor() and
+  read_all(skip_unsupported=False) still refuse them by name."""
+  import warnings
+  prefix = str(tmp_path / 'model.ckpt-7')
+  T.write_checkpoint(prefix, {'a/w': np.arange(6, dtype=np.float32).reshape(2, 3), 'global_step': np.float32(7)})
+  reader = T.CheckpointReader(prefix)
+  reader.entries['_CHECKPOINTABLE_OBJECT_GRAPH'] = dict(reader.entries['a/w'], dtype=7)      # DT_STRING
+  with warnings.catch_warnings(record=True) as w:
+    warnings.simplefilter('always')
+    got = reader.read_all()
+  assert sorted(got) == ['a/w', 'global_step'] and any('_CHECKPOINTABLE_OBJECT_GRAPH' in str(x.message) for x in w)
+  with pytest.raises(NotImplementedError):
+    reader.read_all(skip_unsupported=False)
+  with pytest.raises(NotImplementedError):
+    reader.get_tensor('_CHECKPOINTABLE_OBJECT_GRAPH')
