@@ -462,7 +462,8 @@ if __name__ == '__main__':
   a.warmup = max(a.warmup, 3) if a.impl == 'cuda' else a.warmup
   # a stuck collective must end as a traceback of every thread and a non-zero exit, never as a hung GPU box
   import faulthandler
-  faulthandler.dump_traceback_later(int(os.environ.get('IMMB_BENCH_WATCHDOG', '1500')), exit=True)
+  if a.impl == 'cuda':       # (the CPU reference arm has no collectives and may legitimately run for many minutes)
+    faulthandler.dump_traceback_later(int(os.environ.get('IMMB_BENCH_WATCHDOG', '1500')), exit=True)
   if os.environ.get('IMMB_BENCH_TRACE'):
     def _trace(msg, _t0=[time.time()]):
       sys.stderr.write('[bench rank %s +%.1fs] %s\n' % (os.environ.get('RANK', '0'), time.time() - _t0[0], msg))
