@@ -263,3 +263,21 @@ def test_conv_call_attribution_matches_engine_routing():
   v = _lib.conv_info('immb_conv2d_fwd', desc(B, 32, 256, 256, 3, 1, prec=_lib.PREC_F16X2))
   assert (v['kernel'], v['kind'], v['passes']) == ('conv_tc2_pair_kernel', 'f16', 2)
   assert _lib.conv_info('immb_conv2d_fwd', desc(B, 8, 512, 512, 3, 1, prec=_lib.PREC_F16X2))['passes'] == 3
+
+
+def test_top_kernel_json_is_derived_from_the_committed_captures():
+  """profiles/top_kernel.json (what bench.py quotes as ncu evidence: DRAM bytes per launch of the dominant kernel, its
+  tensor-pipe utilisation per tile family, GB/s of the HBM-bound kernels) must be exactly what tools/make_top_kernel.py
+  computes from the committed ncu exports -- no hand-edited numbers."""
+  import importlib.util
+  import json
+  spec = importlib.util.spec_from_file_location('make_top_kernel', os.path.join(ROOT, 'tools', 'make_top_kernel.py'))
+  mod = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(mod)
+  got = json.load(open(os.path.join(ROOT, 'profiles', 'top_kernel.json')))
+  want = json.loads(json.dumps(mod.build(hbm=got['hbm_peak_gbs'])))     # (the peak itself is pod-specific, driver-written)
+  assert got == want
+  assert got['launches'] == 52 and 0.3 < got['tensor_pipe_pct_time_weighted'] / 100.0 < 1.0
+  fam = got['hbm_kernels']
+  assert {'bn_apply4_kernel<1>', 'bn_bwd_apply4_kernel<1>', 'bn_bwd_reduce4_kernel'} <= set(fam)
+  assert all(0.0 < v['frac_of_hbm_peak'] < 1.0 for v in fam.values())

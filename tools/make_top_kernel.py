@@ -35,9 +35,11 @@ def load(path):
   return out
 
 
-def main():
-  peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-  hbm = float(peaks.get('hbm_gbs', peaks.get('hbm_gbs_burst', 6550.0)))
+def build(hbm=None):
+  """hbm: copy-bandwidth peak in GB/s (default: MEASURED_PEAKS.json of this pod)."""
+  if hbm is None:
+    peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    hbm = float(peaks.get('hbm_gbs', peaks.get('hbm_gbs_burst', 6550.0)))
   pair = [k for k in load(os.path.join(ROOT, 'profiles', 'r2f_pair_52launches_ncu_full_raw.csv')) if k['name'] == 'conv_tc2_pair_kernel']
   step = load(os.path.join(ROOT, 'profiles', 'r2g_step_metrics_raw.csv'))
   tot_ns = sum(k['ns'] for k in pair)
@@ -74,6 +76,11 @@ def main():
                       for n, f in sorted(hbm_fams.items(), key=lambda kv: -kv[1]['ns'])},
       'note': 'ncu launches are cold-cache and serialised (12.7 ms for the step vs 11.4 ms live): shares, not absolutes, carry over',
   }
+  return out
+
+
+def main():
+  out = build()
   json.dump(out, open(os.path.join(ROOT, 'profiles', 'top_kernel.json'), 'w'), indent=1)
   print(json.dumps(out, indent=1)[:3000])
 
