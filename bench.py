@@ -326,15 +326,25 @@ def main_cuda(args):
       if world == 1 and args.all_configs:
         todo += [(k2 + '_per_gpu_shape', k2, CONFIGS[k2]['per_gpu'], CONFIGS[k2]['name'] + ' -- ONE GPU of it') for k2 in ('c3', 'c4', 'c5')]
     for tag, k2, per_gpu, what in todo:
-      m2, h2, r2 = build_model(k2, per_gpu)
-      steps2 = max(5, args.steps // 2)
-      ms2, _ = time_resident(m2.engine, r2, steps2, 4)
-      other[tag] = {'what': what, 'per_gpu_batch': per_gpu, 'global_batch': per_gpu * world, 'n_gpus': world,
-                    'n_maps': CONFIGS[k2]['n_maps'], 'image_size': CONFIGS[k2]['image_size'], 'steps': steps2,
-                    'ms_per_step': ms2, 'pairs_per_s': per_gpu * world / (ms2 * 1e-3),
-                    'tflops_algorithmic': CONFIGS[k2]['gflop'] * per_gpu * world / ms2,
-                    'scaling': 'strong' if tag == 'c2_strong' else 'weak', 'inputs': 'resident in HBM'}
-      m2.engine.release_graphs()
+      # an extra config must never cost the headline line: a (rank-symmetric) failure is recorded and the run goes on
+      m2 = h2 = r2 = None
+      try:
+        m2, h2, r2 = build_model(k2, per_gpu)
+        steps2 = max(5, args.steps // 2)
+        ms2, _ = time_resident(m2.engine, r2, steps2, 4)
+        other[tag] = {'what': what, 'per_gpu_batch': per_gpu, 'global_batch': per_gpu * world, 'n_gpus': world,
+                      'n_maps': CONFIGS[k2]['n_maps'], 'image_size': CONFIGS[k2]['image_size'], 'steps': steps2,
+                      'ms_per_step': ms2, 'pairs_per_s': per_gpu * world / (ms2 * 1e-3),
+                      'tflops_algorithmic': CONFIGS[k2]['gflop'] * per_gpu * world / ms2,
+                      'scaling': 'strong' if tag == 'c2_strong' else 'weak', 'inputs': 'resident in HBM'}
+      except Exception as e:      # noqa: BLE001
+        other[tag] = {'what': what, 'per_gpu_batch': per_gpu, 'n_gpus': world, 'error': '%s: %s' % (type(e).__name__, e)}
+      _trace('other config %s: %s' % (tag, other[tag].get('ms_per_step', other[tag].get('error'))))
+      if m2 is not None:
+        try:
+          m2.engine.release_graphs()
+        except Exception:         # noqa: BLE001
+          pass
       del m2, h2, r2
       torch.cuda.empty_cache()
 
@@ -349,9 +359,12 @@ def main_cuda(args):
     except NameError:
       pass
     gc.collect()
-    torch.cuda.synchronize()
-    dist.barrier()
-    torch.cuda.synchronize()
+    try:
+      torch.cuda.synchronize()
+      dist.barrier()
+      torch.cuda.synchronize()
+    except Exception as e:        # noqa: BLE001  (the result line is already out on rank 0)
+      sys.stderr.write('bench.py: teardown barrier failed: %s\n' % (e,))
     t = threading.Thread(target=dist.destroy_process_group, daemon=True)
     t.start()
     t.join(timeout=30.0)
